@@ -1,0 +1,217 @@
+"""CPU ORACLE -- test infrastructure, not product code.
+
+ctypes wrapper around oracle/liboracle.so (plain-C restatement of the PETLION.jl hot path,
+see oracle/petlion_oracle.h).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+
+CATHODE = {"LCO": 0, "NMC": 1}
+METHOD = {"I": 0, "V": 1, "P": 2}
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "residual_impl.inc", "petlion_oracle.h")]
+    if (not force and os.path.exists(_LIB)
+            and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _LIB
+
+
+class Model(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n", "temperature", "aging", "cathode")]
+
+
+class Layout(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("Nx", "c_e", "c_s_p", "c_s_n", "T", "film", "SOH", "j", "phi_e", "phi_s", "j_s", "I",
+                 "N_diff", "N_alg", "N_tot")]
+
+
+class Run(C.Structure):
+    _fields_ = [("method", C.c_int), ("value", C.c_double), ("tf", C.c_double),
+                ("is_rest", C.c_int), ("new_run", C.c_int), ("t0", C.c_double)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("abstol_init", C.c_double),
+                ("reltol_init", C.c_double), ("maxiters", C.c_int), ("check_bounds", C.c_int),
+                ("interp_final", C.c_int), ("ida_maxord", C.c_int), ("ida_maxcor", C.c_int),
+                ("ida_maxnef", C.c_int), ("ida_maxncf", C.c_int)]
+
+
+class Bounds(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("V_max", "V_min", "SOC_max", "SOC_min", "T_max", "c_s_n_max", "I_max", "I_min",
+                 "eta_plating_min", "c_e_min", "dfilm_max")]
+
+
+class Summary(C.Structure):
+    _fields_ = [("t_end", C.c_double), ("V_end", C.c_double), ("I_end", C.c_double),
+                ("SOC_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int), ("n_res", C.c_int),
+                ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int),
+                ("n_newton_init", C.c_int)]
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        L = C.CDLL(_LIB)
+        L.orc_theta_name.restype = C.c_char_p
+        L.orc_calc_I1C.restype = C.c_double
+        L.orc_rng_u01.restype = C.c_double
+        L.orc_rng_u01.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_uint]
+        L.orc_jac_pattern.argtypes = [C.POINTER(Model), C.c_int, _ip, _ip]
+        L.orc_residual.argtypes = [C.POINTER(Model), _dp, C.POINTER(Run), C.c_double, _dp, _dp, _dp]
+        L.orc_jacobian.argtypes = [C.POINTER(Model), _dp, C.POINTER(Run), C.c_double, _dp, _dp,
+                                   C.c_double, _dp]
+        L.orc_initial_guess.argtypes = [C.POINTER(Model), _dp, C.c_double, _dp]
+        L.orc_newton_init.argtypes = [C.POINTER(Model), _dp, C.POINTER(Run), C.POINTER(Opts), _dp, _dp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def theta_names():
+    L = lib()
+    return [L.orc_theta_name(i).decode() for i in range(L.orc_ntheta())]
+
+
+def theta_defaults(cathode="LCO"):
+    L = lib()
+    th = np.zeros(L.orc_ntheta())
+    L.orc_theta_defaults(CATHODE[cathode], _p(th))
+    return th
+
+
+def theta_dict(cathode="LCO"):
+    return dict(zip(theta_names(), theta_defaults(cathode)))
+
+
+def make_model(cathode="LCO", N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10,
+               temperature=False, aging=False):
+    return Model(N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, int(bool(temperature)), int(bool(aging)),
+                 CATHODE[cathode])
+
+
+def layout(m):
+    Lo = Layout()
+    lib().orc_layout_make(C.byref(m), C.byref(Lo))
+    return Lo
+
+
+def default_opts(**kw):
+    o = Opts()
+    lib().orc_opts_defaults(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def default_bounds(cathode="LCO", **kw):
+    b = Bounds()
+    lib().orc_bounds_defaults(CATHODE[cathode], C.byref(b))
+    for k, v in kw.items():
+        setattr(b, k, v)
+    return b
+
+
+def make_run(method="I", value=-1.0, tf=1e6, is_rest=False, new_run=True, t0=0.0):
+    return Run(METHOD[method], float(value), float(tf), int(is_rest), int(new_run), float(t0))
+
+
+def calc_I1C(theta):
+    return lib().orc_calc_I1C(_p(np.ascontiguousarray(theta, dtype=np.float64)))
+
+
+def initial_guess(m, theta, SOC):
+    Y0 = np.zeros(layout(m).N_tot)
+    lib().orc_initial_guess(C.byref(m), _p(np.ascontiguousarray(theta)), float(SOC), _p(Y0))
+    return Y0
+
+
+def residual(m, theta, run, t, Y, YP):
+    res = np.zeros_like(Y)
+    lib().orc_residual(C.byref(m), _p(np.ascontiguousarray(theta)), C.byref(run), float(t),
+                       _p(np.ascontiguousarray(Y)), _p(np.ascontiguousarray(YP)), _p(res))
+    return res
+
+
+def jac_pattern(m, method="I"):
+    L = lib()
+    nnz = L.orc_jac_pattern(C.byref(m), METHOD[method], None, None)
+    N = layout(m).N_tot
+    colptr = np.zeros(N + 1, dtype=np.int32)
+    rowval = np.zeros(nnz, dtype=np.int32)
+    L.orc_jac_pattern(C.byref(m), METHOD[method], colptr.ctypes.data_as(_ip), rowval.ctypes.data_as(_ip))
+    return colptr, rowval
+
+
+def jacobian(m, theta, run, t, Y, YP, gamma):
+    L = lib()
+    nnz = L.orc_jac_pattern(C.byref(m), run.method, None, None)
+    nz = np.zeros(nnz)
+    L.orc_jacobian(C.byref(m), _p(np.ascontiguousarray(theta)), C.byref(run), float(t),
+                   _p(np.ascontiguousarray(Y)), _p(np.ascontiguousarray(YP)), float(gamma), _p(nz))
+    return nz
+
+
+def newton_init(m, theta, run, opts, Y):
+    Y = np.array(Y, dtype=np.float64)
+    YP = np.zeros_like(Y)
+    it = lib().orc_newton_init(C.byref(m), _p(np.ascontiguousarray(theta)), C.byref(run),
+                               C.byref(opts), _p(Y), _p(YP))
+    return it, Y, YP
+
+
+def simulate_batch(m, theta, run, opts, bounds, SOC0=1.0, values=None, state=None, n_save_max=0,
+                   nthreads=1):
+    """theta: [B, ntheta] (oracle order).  Returns dict of numpy arrays.
+    state: dict(Y, YP, SOC, t) from a previous call (simulate! continuation)."""
+    L = lib()
+    theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    B = theta.shape[0]
+    N = layout(m).N_tot
+    if state is None:
+        sY = np.zeros((B, N)); sYP = np.zeros((B, N)); sSOC = np.zeros(B); st = np.zeros(B)
+    else:
+        sY = np.array(state["Y"], dtype=np.float64); sYP = np.array(state["YP"], dtype=np.float64)
+        sSOC = np.array(state["SOC"], dtype=np.float64); st = np.array(state["t"], dtype=np.float64)
+    soc0 = np.ascontiguousarray(np.broadcast_to(np.asarray(SOC0, dtype=np.float64), (B,)))
+    out = (Summary * B)()
+    ns = max(int(n_save_max), 1)
+    tr = {k: np.full((B, ns), np.nan) for k in ("t", "V", "I", "SOC")}
+    trn = np.zeros(B, dtype=np.int32)
+    vals = None if values is None else np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (B,)))
+    L.orc_simulate_batch(C.byref(m), B, _p(theta), C.byref(run), None if vals is None else _p(vals),
+                         C.byref(opts), C.byref(bounds), _p(soc0), _p(sY), _p(sYP), _p(sSOC), _p(st),
+                         out, ns if n_save_max else 0,
+                         _p(tr["t"]) if n_save_max else None, _p(tr["V"]) if n_save_max else None,
+                         _p(tr["I"]) if n_save_max else None, _p(tr["SOC"]) if n_save_max else None,
+                         trn.ctypes.data_as(_ip), int(nthreads))
+    res = {f: np.array([getattr(o, f) for o in out]) for f, _ in Summary._fields_}
+    res.update(state=dict(Y=sY, YP=sYP, SOC=sSOC, t=st), traj=tr, traj_n=trn)
+    return res
+
+
+def rng_u01(seed, system_id, param_id):
+    return lib().orc_rng_u01(int(seed), int(system_id), int(param_id))
