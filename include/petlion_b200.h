@@ -1,0 +1,149 @@
+/*
+ * petlion_b200.h -- C ABI of the B200-native batched DFN integrator (libpetlion_b200.so).
+ *
+ * Drop-in boundary for PETLION.jl's hot path.  The reference has no FFI of its own; the seam is
+ * the set of Julia callables in `p.funcs` / `Jac_and_res` (src/structures.jl:315-334,
+ * src/physics_equations/scalar_residual.jl:435-487) consumed by `initialize_simulation!` and
+ * `solve!` (src/model_evaluation.jl:174-232, 312-333).  A Julia maintainer binds these entry
+ * points with `ccall`.  Every array is batch-major: row = one system,
+ * contiguous doubles.  Nothing returned is library-allocated; the caller owns all buffers.
+ *
+ * Return value: 0 ok, <0 error (text via plb_last_error()).  Per-system soft exits use the
+ * reference's run.info.flag codes 0..11 (src/checks.jl); per-system hard failures are negative.
+ * A handle is used by one host thread at a time; calls return after the stream has synchronised.
+ */
+#ifndef PETLION_B200_H
+#define PETLION_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plb_handle_s *plb_handle;
+
+enum { PLB_CATHODE_LCO = 0, PLB_CATHODE_NMC = 1 };
+enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2 }; /* method_I / method_V / method_P */
+enum { PLB_MEM_HOST = 0, PLB_MEM_DEVICE = 1 };                /* where the caller's buffers live */
+
+/* petlion(cathode; N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, temperature, aging) -- src/params.jl:119-174 */
+typedef struct {
+    int cathode;
+    int N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n;
+    int temperature; /* 0: isothermal (built).  1: not built yet -> plb_create fails loudly */
+    int aging;       /* 0: none (built).        1 (:SEI): not built yet                     */
+    int device;      /* CUDA device ordinal */
+} plb_model_desc;
+
+/* run_constant{method,value}: src/structures.jl:46-54; input kinds: src/physics_equations/input_methods.jl:5-74 */
+enum { PLB_INPUT_VALUE = 0, PLB_INPUT_HOLD = 1, PLB_INPUT_REST = 2 };
+typedef struct {
+    int method;      /* PLB_METHOD_* */
+    int input_kind;  /* PLB_INPUT_VALUE: a number; PLB_INPUT_HOLD: `:hold` (value taken from the previous
+                        state, incl. the reference's V=:hold quirk input_methods.jl:53-63);
+                        PLB_INPUT_REST: I = :rest (value 0; bounds not checked, src/checks.jl:12,388) */
+    double value;    /* used for PLB_INPUT_VALUE when `values` passed to the call is NULL */
+    double tf;       /* final time of this run (seconds, local to the run); reference default 1e6 */
+    int new_run;     /* 1: simulate(); 0: simulate!() continuation from state_* */
+    int reserved;
+} plb_run;
+
+/* options_simulation: src/structures.jl:266-285; defaults src/params.jl:256-280 */
+typedef struct {
+    double abstol, reltol, abstol_init, reltol_init;
+    int maxiters;
+    int check_bounds;
+    int interp_final;
+    int reserved;
+} plb_opts;
+
+/* boundary_stop_conditions: src/structures.jl:237-251 (NaN deactivates a bound) */
+typedef struct {
+    double V_max, V_min, SOC_max, SOC_min, T_max, c_s_n_max, I_max, I_min, eta_plating_min,
+        c_e_min, dfilm_max;
+} plb_bounds;
+
+/* per-system summary record (64 bytes) */
+typedef struct {
+    double t_end, V_end, I_end, SOC_end;
+    int flag;          /* run.info.flag: 0 tf, 1 V_min, 2 V_max, 3 SOC_min, 4 SOC_max, 5 T_max, 6 c_s_n,
+                          7 I_max, 8 I_min, 9 c_e_min, 10 dfilm, 11 eta_plating; <0 hard failure */
+    int n_steps;       /* accepted integrator steps */
+    int n_res, n_jac;  /* residual / Jacobian evaluations */
+    int n_netf, n_ncfn;/* error-test / Newton-convergence failures */
+    int n_newton_init; /* iterations of the algebraic initialisation */
+    int reserved;
+} plb_summary;
+
+#define PLB_FAIL_NEWTON_INIT (-1) /* "Could not initialize DAE" model_evaluation.jl:456 */
+#define PLB_FAIL_CONV (-2)        /* "Model failed to converge"  checks.jl:233-236        */
+#define PLB_FAIL_ERRTEST (-3)
+#define PLB_FAIL_MAXITERS (-4)    /* checks.jl:239 */
+#define PLB_FAIL_NONFINITE (-5)
+#define PLB_FAIL_INIT_BOUNDS (-6) /* check_initial_SOC, checks.jl:327-339 */
+
+const char *plb_last_error(void);
+
+/* petlion(...) : build the model handle (device workspaces, index tables). */
+int plb_create(const plb_model_desc *desc, plb_handle *out);
+int plb_destroy(plb_handle h);
+/* optional: CUDA stream (cudaStream_t passed as void*) used for PLB_MEM_DEVICE calls */
+int plb_set_stream(plb_handle h, void *cuda_stream);
+
+/* sizes: N.tot, N.diff, number of used parameters, nnz of J_full.sp for a method */
+int plb_nstates(plb_handle h);
+int plb_ndiff(plb_handle h);
+int plb_ntheta(plb_handle h);
+int plb_jac_nnz(plb_handle h, int method);
+
+/* theta_keys of the generated functions: alphabetically sorted used keys, UTF-8
+ * (src/generate_functions.jl:327-363, 387).  keys[i] points to static storage. */
+int plb_theta_keys(plb_handle h, const char **keys);
+int plb_theta_index(plb_handle h, const char *key_utf8);
+/* default parameter row (LCO()/LiC6()/system_LCO_LiC6 ...: src/params.jl) and default bounds/opts */
+int plb_theta_defaults(plb_handle h, double *theta_row);
+int plb_bounds_defaults(plb_handle h, plb_bounds *b);
+int plb_opts_defaults(plb_handle h, plb_opts *o);
+/* calc_I1C: src/physics_equations/auxiliary_states_and_coefficients.jl:631-647 */
+int plb_calc_I1C(plb_handle h, int B, const double *theta, double *I1C);
+
+/* J_full.sp: CSC pattern of [J_sp_base; J_sp_scalar'] (scalar_residual.jl:501); index base 0 or 1 */
+int plb_jac_pattern(plb_handle h, int method, int *colptr, int *rowval, int one_based);
+
+/* initial_guess!(Y0, SOC, theta_tot, X_applied) -- src/model_evaluation.jl:204 */
+int plb_initial_guess(plb_handle h, int B, const double *soc, const double *theta, double *Y0, int mem);
+
+/* R_full(res,t,Y,YP,p,run) -- model_evaluation.jl:263 ;  J_full(J,t,Y,YP,gamma,p,run) -- :264
+ * values: per-system control value [B] or NULL (then run->value).  Either output may be NULL. */
+int plb_resjac(plb_handle h, int B, const double *Y, const double *YP, const double *gamma,
+               const double *theta, const plb_run *run, const double *values, double *res,
+               double *nzval, int mem);
+
+/* newtons_method!(p,Y,YP,run,opts,R_alg,R_diff,J_alg) -- model_evaluation.jl:430-480.
+ * Y in/out [B x N], YP out [B x N]; status[B] = iterations (>0) or PLB_FAIL_NEWTON_INIT */
+int plb_newton_init(plb_handle h, int B, double *Y, double *YP, const double *theta,
+                    const plb_run *run, const double *values, const plb_opts *opts, int *status,
+                    int mem);
+
+/* simulate(p, tf; I|V|P=..., SOC, bounds..., opts...) / simulate!(sol, p, ...):
+ * replaces initialize_simulation! + IDA + solve! + exit_simulation!
+ * (model_evaluation.jl:10-97, 174-382; checks.jl:1-249; save_outputs.jl:11-40).
+ *   soc0[B]                      initial SOC (new runs)
+ *   state_Y[BxN], state_YP[BxN], state_SOC[B], state_t[B]   continuation state, in/out
+ *   summary[B]
+ *   traj_*[B x n_save_max] (optional, may be NULL; n_save_max may be 0), traj_n[B]
+ */
+int plb_simulate(plb_handle h, int B, const double *theta, const plb_run *run,
+                 const double *values, const plb_opts *opts, const plb_bounds *bounds,
+                 const double *soc0, double *state_Y, double *state_YP, double *state_SOC,
+                 double *state_t, plb_summary *summary, int n_save_max, double *traj_t,
+                 double *traj_V, double *traj_I, double *traj_SOC, int *traj_n, int mem);
+
+/* kernel launch counter (number of CUDA kernels this handle has launched) */
+long long plb_launch_count(plb_handle h);
+/* last kernel time in ms measured with CUDA events on the launching stream (0 if none) */
+float plb_last_kernel_ms(plb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -39,7 +39,7 @@ class Layout(C.Structure):
 
 class Run(C.Structure):
     _fields_ = [("method", C.c_int), ("value", C.c_double), ("tf", C.c_double),
-                ("is_rest", C.c_int), ("new_run", C.c_int), ("t0", C.c_double)]
+                ("input_kind", C.c_int), ("new_run", C.c_int), ("t0", C.c_double)]
 
 
 class Opts(C.Structure):
@@ -135,8 +135,11 @@ def default_bounds(cathode="LCO", **kw):
     return b
 
 
-def make_run(method="I", value=-1.0, tf=1e6, is_rest=False, new_run=True, t0=0.0):
-    return Run(METHOD[method], float(value), float(tf), int(is_rest), int(new_run), float(t0))
+INPUT = {"value": 0, "hold": 1, "rest": 2}
+
+
+def make_run(method="I", value=-1.0, tf=1e6, input_kind="value", new_run=True, t0=0.0):
+    return Run(METHOD[method], float(value), float(tf), INPUT[input_kind], int(new_run), float(t0))
 
 
 def calc_I1C(theta):

@@ -70,7 +70,7 @@ typedef struct {
     int method;   /* ORC_METHOD_* */
     double value; /* applied I [C-rate], V [V] or P [W/m^2] */
     double tf;    /* final (local) time */
-    int is_rest;  /* I = :rest  -> bounds are not checked (checks.jl:12,388) */
+    int input_kind; /* 0 number; 1 :hold (value from previous state); 2 :rest (checks.jl:12,388) */
     int new_run;  /* 1: fresh simulate(); 0: simulate!() continuation (adds tstop 1.0) */
     double t0;    /* global time offset (run.t0) */
 } orc_run;

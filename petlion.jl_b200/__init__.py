@@ -1,0 +1,16 @@
+"""petlion.jl_b200 -- B200-native batched implicit DAE integrator behind PETLION.jl's
+petlion()/simulate()/simulate!() API and its residual/Jacobian callback surface.
+
+Only what the hot path needs lives here: csrc/ (CUDA kernels + C ABI), codegen/ (sympy -> CUDA
+constitutive laws) and the host-side mirror of the reference interface (api.py).
+"""
+from . import _lib
+from ._lib import build
+from .api import EXIT_REASONS, Model, Solution, petlion, simulate, simulate_
+
+LCO = "LCO"
+NMC = "NMC"
+simulate_bang = simulate_   # Julia's simulate!
+
+__all__ = ["petlion", "simulate", "simulate_", "simulate_bang", "LCO", "NMC", "Model", "Solution", "build",
+           "EXIT_REASONS"]

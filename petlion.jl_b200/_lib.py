@@ -1,0 +1,116 @@
+"""ctypes binding of libpetlion_b200.so (C ABI: include/petlion_b200.h).
+
+This is the Python stand-in for the `ccall` layer a Julia host would use.
+There is NO CPU fallback: if the CUDA library is missing or no GPU is present, calls fail loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpetlion_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("plb_kernels.cu", "plb_device.cuh", "plb_integrator.cuh",
+                                            "laws_generated.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))
+    gen = os.path.join(CSRC, "laws_generated.cuh")
+    if not os.path.exists(gen):
+        subprocess.check_call(["python", os.path.join(_HERE, "codegen", "gen_laws.py")])
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH, os.path.join(CSRC, "plb_kernels.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("cathode", "N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n",
+                                       "temperature", "aging", "device")]
+
+
+class Run(C.Structure):
+    _fields_ = [("method", C.c_int), ("input_kind", C.c_int), ("value", C.c_double), ("tf", C.c_double),
+                ("new_run", C.c_int), ("reserved", C.c_int)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("abstol_init", C.c_double),
+                ("reltol_init", C.c_double), ("maxiters", C.c_int), ("check_bounds", C.c_int),
+                ("interp_final", C.c_int), ("reserved", C.c_int)]
+
+
+class Bounds(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("V_max", "V_min", "SOC_max", "SOC_min", "T_max", "c_s_n_max",
+                                          "I_max", "I_min", "eta_plating_min", "c_e_min", "dfilm_max")]
+
+
+class Summary(C.Structure):
+    _fields_ = [("t_end", C.c_double), ("V_end", C.c_double), ("I_end", C.c_double),
+                ("SOC_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int), ("n_res", C.c_int),
+                ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int), ("n_newton_init", C.c_int),
+                ("reserved", C.c_int)]
+
+
+SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", "f8"), ("flag", "i4"),
+                 ("n_steps", "i4"), ("n_res", "i4"), ("n_jac", "i4"), ("n_netf", "i4"), ("n_ncfn", "i4"),
+                 ("n_newton_init", "i4"), ("reserved", "i4")]
+
+EXPORTS = ["plb_last_error", "plb_create", "plb_destroy", "plb_set_stream", "plb_nstates", "plb_ndiff",
+           "plb_ntheta", "plb_jac_nnz", "plb_theta_keys", "plb_theta_index", "plb_theta_defaults",
+           "plb_bounds_defaults", "plb_opts_defaults", "plb_calc_I1C", "plb_jac_pattern",
+           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_simulate", "plb_launch_count",
+           "plb_last_kernel_ms"]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA extension; raise (never fall back) if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+                " petlion.jl_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.c_void_p
+        L.plb_last_error.restype = C.c_char_p
+        L.plb_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp)]
+        L.plb_destroy.argtypes = [vp]
+        L.plb_set_stream.argtypes = [vp, vp]
+        for f in ("plb_nstates", "plb_ndiff", "plb_ntheta"):
+            getattr(L, f).argtypes = [vp]
+        L.plb_jac_nnz.argtypes = [vp, C.c_int]
+        L.plb_theta_keys.argtypes = [vp, C.POINTER(C.c_char_p)]
+        L.plb_theta_index.argtypes = [vp, C.c_char_p]
+        L.plb_theta_defaults.argtypes = [vp, dp]
+        L.plb_bounds_defaults.argtypes = [vp, C.POINTER(Bounds)]
+        L.plb_opts_defaults.argtypes = [vp, C.POINTER(Opts)]
+        L.plb_calc_I1C.argtypes = [vp, C.c_int, dp, dp]
+        L.plb_jac_pattern.argtypes = [vp, C.c_int, ip, ip, C.c_int]
+        L.plb_initial_guess.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int]
+        L.plb_resjac.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.POINTER(Run), dp, dp, dp, C.c_int]
+        L.plb_newton_init.argtypes = [vp, C.c_int, dp, dp, dp, C.POINTER(Run), dp, C.POINTER(Opts), vp, C.c_int]
+        L.plb_simulate.argtypes = [vp, C.c_int, dp, C.POINTER(Run), dp, C.POINTER(Opts), C.POINTER(Bounds),
+                                   dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, vp, C.c_int]
+        L.plb_launch_count.argtypes = [vp]
+        L.plb_launch_count.restype = C.c_longlong
+        L.plb_last_kernel_ms.argtypes = [vp]
+        L.plb_last_kernel_ms.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("petlion_b200: " + lib().plb_last_error().decode("utf-8", "replace"))

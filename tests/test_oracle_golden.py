@@ -1,0 +1,130 @@
+"""CPU tests: the oracle against the reference's own known answers (executed-notebook outputs,
+tests/golden/reference_goldens.json, extracted by tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def _names():
+    return O.theta_names()
+
+
+def test_theta_defaults_match_reference_dict(goldens):
+    # examples/updating_parameters.ipynb cell 3 prints the full LCO dict
+    ref = goldens["theta_LCO"]
+    uni = {"T0": "T₀", "c_e0": "c_e₀", "t_plus": "t₊"}
+    greek = {"theta_": "θ_", "sigma_": "σ_", "eps_": "ϵ_", "lambda_": "λ_", "rho_": "ρ_"}
+    th = O.theta_dict("LCO")
+    checked = 0
+    for k, v in th.items():
+        rk = uni.get(k, k)
+        for a, b in greek.items():
+            if rk.startswith(a):
+                rk = b + rk[len(a):]
+        if rk in ref:
+            assert v == pytest.approx(ref[rk], rel=1e-15), k
+            checked += 1
+    assert checked >= 55
+
+
+def test_I1C_exact(goldens):
+    assert O.calc_I1C(O.theta_defaults("LCO")) == goldens["theta_LCO"]["I1C"]
+
+
+def test_layout_and_pattern_sizes():
+    m = O.make_model("LCO")
+    L = O.layout(m)
+    assert (L.N_diff, L.N_alg, L.N_tot) == (230, 71, 301)
+    cp, rv = O.jac_pattern(m, "I")
+    assert len(rv) == 2139                                          # SURVEY §8, [probe]
+    cp, rv = O.jac_pattern(m, "V")
+    assert len(rv) == 2140
+    # row-group counts quoted in SURVEY App. A
+    cp, rv = O.jac_pattern(m, "I")
+    rows = np.asarray(rv)
+    assert np.sum(rows < 30) == 108 and np.sum((rows >= 30) & (rows < 230)) == 1660
+    assert np.sum((rows >= 230) & (rows < 250)) == 100 and np.sum((rows >= 250) & (rows < 280)) == 192
+    assert np.sum((rows >= 280) & (rows < 300)) == 78 and np.sum(rows == 300) == 1
+
+
+def test_newton_init_V0_of_2C_charge(goldens):
+    # examples/model_inputs_and_outputs.ipynb: sol.V[1] of simulate(p, I=2, SOC=0, V_max=4.1)
+    m = O.make_model("LCO"); th = O.theta_defaults("LCO"); L = O.layout(m)
+    y0 = O.initial_guess(m, th, 0.0); y0[L.I] = 2.0
+    it, y, yp = O.newton_init(m, th, O.make_run("I", 2.0), O.default_opts(), y0)
+    assert it == 4
+    V0 = y[L.phi_s] - y[L.phi_s + 19]
+    assert abs(V0 - goldens["V_2C_charge"]["head13"][0]) < 5e-11
+
+
+@pytest.mark.parametrize("eps_p", ["0.385", "0.485", "0.585"])
+def test_ida_step_ladder_matches_notebook(goldens, eps_p):
+    """The three 1C discharges of examples/updating_parameters.ipynb cell 5: every IDA step time
+    (decoded from the SVG polyline) must be reproduced, with the same number of steps."""
+    m = O.make_model("LCO"); names = _names()
+    th = O.theta_defaults("LCO"); th[names.index("eps_p")] = float(eps_p)
+    r = O.simulate_batch(m, th, O.make_run("I", -1.0), O.default_opts(), O.default_bounds("LCO"),
+                         SOC0=1.0, n_save_max=400)
+    g = goldens["ladder_1C_discharge"]["eps_p"][eps_p]
+    gt, gV = np.array(g["t"]), np.array(g["V"])
+    n = r["traj_n"][0]
+    t, V = r["traj"]["t"][0, :n], r["traj"]["V"][0, :n]
+    assert n == len(gt)                                   # 81 / 66 / 55 points
+    assert r["flag"][0] == 3                              # "Below min. SOC"
+    assert abs(t[-1] - 3600.0) < 1e-6
+    # pixel resolution: ~2 ms absolute on small steps, ~1e-3 relative on large ones
+    assert np.all(np.abs(t - gt) <= 0.004 + 2e-3 * gt)
+    # voltage decoded to ~1e-4 V (+ tick-label calibration)
+    assert np.max(np.abs(V - gV)) < 1.5e-3
+    assert abs(V[-1] - gV[-1]) < 2e-4
+
+
+def test_printed_summary_1C(goldens):
+    m = O.make_model("LCO"); th = O.theta_defaults("LCO")
+    r = O.simulate_batch(m, th, O.make_run("I", -1.0), O.default_opts(), O.default_bounds("LCO"), SOC0=1.0)
+    s = goldens["summaries"]["1C_discharge"]
+    assert r["t_end"][0] == pytest.approx(s["t_s"], abs=1e-6)
+    assert r["V_end"][0] == pytest.approx(s["V"], abs=2e-3)      # printed by an older PETLION version
+    assert abs(r["SOC_end"][0]) < 1e-9
+
+
+def test_cccv_protocol_close_to_older_notebook(goldens):
+    """CC-CV notebook was executed with an older PETLION: indicative 3-digit agreement only."""
+    m = O.make_model("LCO"); th = O.theta_defaults("LCO")
+    b = O.default_bounds("LCO", V_max=4.1)
+    r = O.simulate_batch(m, th, O.make_run("I", 2.0), O.default_opts(), b, SOC0=0.0)
+    s = goldens["summaries"]["2C_CC_to_4.1V"]
+    assert r["flag"][0] == 2
+    assert r["t_end"][0] == pytest.approx(s["t_s"], rel=1e-3)
+    assert r["SOC_end"][0] == pytest.approx(s["SOC"], abs=5e-4)
+    r2 = O.simulate_batch(m, th, O.make_run("V", 0.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                          state=r["state"])
+    s2 = goldens["summaries"]["CV_hold"]
+    assert r2["flag"][0] == 4
+    assert r2["t_end"][0] == pytest.approx(s2["t_s"], rel=1e-3)
+    assert r2["I_end"][0] == pytest.approx(s2["I_C"], abs=2e-3)
+
+
+def test_jacobian_complex_step_vs_finite_difference():
+    m = O.make_model("LCO"); th = O.theta_defaults("LCO"); L = O.layout(m)
+    y = O.initial_guess(m, th, 0.5); y[L.I] = 1.0
+    it, y, yp = O.newton_init(m, th, O.make_run("I", 1.0), O.default_opts(), y)
+    run = O.make_run("I", 1.0)
+    cp, rv = O.jac_pattern(m, "I")
+    nz = O.jacobian(m, th, run, 0.0, y, yp, 0.7)
+    r0 = O.residual(m, th, run, 0.0, y, yp)
+    rng = np.random.default_rng(0)
+    for c in rng.choice(301, 25, replace=False):
+        h = 1e-6 * max(abs(y[c]), 1e-3)
+        y2 = y.copy(); y2[c] += h; yp2 = yp.copy(); yp2[c] += 0.7 * h
+        fd = (O.residual(m, th, run, 0.0, y2, yp2) - r0) / h
+        for k in range(cp[c], cp[c + 1]):
+            assert nz[k] == pytest.approx(fd[rv[k]], rel=2e-4, abs=1e-9 * max(1.0, abs(nz[k])))
+
+
+def test_rng_matches_numpy_copy():
+    from tests.util import splitmix_u01
+    for sid in (0, 1, 17, 65535):
+        for pid in range(7):
+            assert O.rng_u01(20211, sid, pid) == splitmix_u01(20211, np.array([sid]), pid)[0]
