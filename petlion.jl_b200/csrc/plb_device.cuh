@@ -373,6 +373,14 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     }
 }
 
+// out-of-line copy for the fused integrator (keeps its code inside the instruction cache)
+template <int CHEM, bool WITH_JAC>
+__device__ __noinline__ void lane_eval_ni(const ModelDesc& m, const WarpConst& C, const LaneRole& ro,
+                                          const LaneVec& y, const LaneVec& yp, double Iapp, int method,
+                                          double value, LaneVec& res, CtrlRow& ctrl, LaneJac& J) {
+    lane_eval<CHEM, WITH_JAC>(m, C, ro, y, yp, Iapp, method, value, res, ctrl, J);
+}
+
 // ------------------------------------------------------------------------------------------------
 // structured Newton-matrix factorisation / solve
 //   1. particle block (kap*MC - cj I) is identical for every particle of an electrode -> explicit
@@ -386,9 +394,9 @@ struct WarpFactor {
     double Sinv[NR * NR][2];   // [r*NR+c][electrode 0=p,1=n]
     double vb[NR][2];          // Sinv * b (b = surface-row j coupling)
     // per-lane data [field][lane]
-    double Dinv[9][32];        // inverse of the pivoted 3x3 diagonal block
-    double Lb[4][32];          // lower block entries: (ce,ce) (pe,ce) (pe,pe) (ps,ps)
-    double Ub[4][32];          // upper block entries, same positions
+    double Dinv[9][32];        // inverse of the pivoted 3x3 diagonal block D'_x
+    double Wm[9][32];          // W_x = L_x * Dinv_{x-1}     (forward sweep:  y_x = r_x - W_x y_{x-1})
+    double Pm[9][32];          // P_x = Dinv_x * U_x         (backward sweep: u_x = Dinv_x y_x - P_x u_{x+1})
     double z[3][32];           // T^{-1} e_I  (border column)
     double q[4][32];           // j elimination: q_ce, q_pe, q_ps, inv_den
     double jcs[32];            // a_cs (j row coefficient of the surface concentration)
@@ -398,51 +406,63 @@ struct WarpFactor {
     double pad;
 };
 
+// 3x3 inverse by the adjugate (forward error ~ cond * eps, invariant under row/column scaling)
 __device__ __forceinline__ void inv3x3(const double* a, double* o) {
-    // Gauss-Jordan with partial pivoting on a 3x3 held in registers
-    double m[3][6] = {{a[0], a[1], a[2], 1, 0, 0}, {a[3], a[4], a[5], 0, 1, 0}, {a[6], a[7], a[8], 0, 0, 1}};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        int p = k;
-        double mx = fabs(m[k][k]);
-#pragma unroll
-        for (int i = k + 1; i < 3; i++)
-            if (fabs(m[i][k]) > mx) { mx = fabs(m[i][k]); p = i; }
-#pragma unroll
-        for (int i = k + 1; i < 3; i++)
-            if (p == i) {
-#pragma unroll
-                for (int c = 0; c < 6; c++) { const double t = m[k][c]; m[k][c] = m[i][c]; m[i][c] = t; }
-            }
-        const double d = 1.0 / m[k][k];
-#pragma unroll
-        for (int c = 0; c < 6; c++) m[k][c] *= d;
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            if (i != k) {
-                const double f = m[i][k];
-#pragma unroll
-                for (int c = 0; c < 6; c++) m[i][c] = fma(-f, m[k][c], m[i][c]);
-            }
+    const double c00 = a[4] * a[8] - a[5] * a[7];
+    const double c01 = a[5] * a[6] - a[3] * a[8];
+    const double c02 = a[3] * a[7] - a[4] * a[6];
+    const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    const double id = 1.0 / det;
+    o[0] = c00 * id;
+    o[3] = c01 * id;
+    o[6] = c02 * id;
+    o[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+    o[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+    o[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+    o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+// The two sweeps of the block-Thomas solve, written as select-free fixed-point iterations along the
+// lanes: after k iterations lanes 0..k (forward) / N-1-k..N-1 (backward) hold their final values and
+// never change again, so Nx iterations reproduce the sequential recurrence exactly.
+//   forward :  y_x = r_x - W_x y_{x-1}          (W_0 = 0)
+//   backward:  u_x = c_x - P_x u_{x+1}          (c_x = Dinv_x y_x, P_{N-1} = 0)
+__device__ __forceinline__ void thomas_sweeps(int Nx, const double* Wm, const double* Pm, const double* Di,
+                                              const double* r, double* u) {
+    double y0 = r[0], y1 = r[1], y2 = r[2];
+    for (int it = 1; it < Nx; it++) {
+        const double a0 = shfl_up(y0), a1 = shfl_up(y1), a2 = shfl_up(y2);
+        y0 = r[0] - (Wm[0] * a0 + Wm[1] * a1 + Wm[2] * a2);
+        y1 = r[1] - (Wm[3] * a0 + Wm[4] * a1 + Wm[5] * a2);
+        y2 = r[2] - (Wm[6] * a0 + Wm[7] * a1 + Wm[8] * a2);
     }
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) o[i * 3 + c] = m[i][3 + c];
+    const double c0 = Di[0] * y0 + Di[1] * y1 + Di[2] * y2;
+    const double c1 = Di[3] * y0 + Di[4] * y1 + Di[5] * y2;
+    const double c2 = Di[6] * y0 + Di[7] * y1 + Di[8] * y2;
+    double u0 = c0, u1 = c1, u2 = c2;
+    for (int it = 1; it < Nx; it++) {
+        const double a0 = shfl_dn(u0), a1 = shfl_dn(u1), a2 = shfl_dn(u2);
+        u0 = c0 - (Pm[0] * a0 + Pm[1] * a1 + Pm[2] * a2);
+        u1 = c1 - (Pm[3] * a0 + Pm[4] * a1 + Pm[5] * a2);
+        u2 = c2 - (Pm[6] * a0 + Pm[7] * a1 + Pm[8] * a2);
+    }
+    u[0] = u0; u[1] = u1; u[2] = u2;
 }
 
 // alg_only: Newton on the algebraic block (newtons_method!, model_evaluation.jl:430-480):
 // c_e and c_s are frozen, the differential rows are replaced by identity.
-__device__ __forceinline__ void warp_factor(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
-                                            const CtrlRow& ctrl, double cj, bool alg_only,
-                                            WarpFactor& Fa, int lane) {
+__device__ __noinline__ void warp_factor(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
+                                         const CtrlRow& ctrl, double cj, bool alg_only,
+                                         WarpFactor& Fa, int lane) {
     // ---- 1. particle inverses -------------------------------------------------------------------
     if (!alg_only) {
         const int el = lane >> 4;                       // lanes 0-15 -> cathode, 16-31 -> anode
         const int l16 = lane & 15;
         const double kap = shfl_from(J.kap, el == 0 ? 0 : m.Nx - 1);
         for (int k = l16; k < NR * NR; k += 16) {
-            const int r = k / NR, c = k % NR;
+            const int r = k / NR, c = k - r * NR;
             Fa.Sinv[k][el] = kap * laws::MC[r][c] - (r == c ? cj : 0.0);
         }
         __syncwarp();
@@ -452,7 +472,7 @@ __device__ __forceinline__ void warp_factor(const ModelDesc& m, const LaneRole& 
             if (l16 < NR && l16 != p) Fa.Sinv[p * NR + l16][el] *= piv;
             __syncwarp();
             for (int k = l16; k < NR * NR; k += 16) {
-                const int r = k / NR, c = k % NR;
+                const int r = k / NR, c = k - r * NR;
                 if (r != p && c != p)
                     Fa.Sinv[k][el] = fma(-Fa.Sinv[r * NR + p][el], Fa.Sinv[p * NR + c][el], Fa.Sinv[k][el]);
             }
@@ -487,90 +507,51 @@ __device__ __forceinline__ void warp_factor(const ModelDesc& m, const LaneRole& 
     Dm[3] = (alg_only ? 0.0 : J.pcD) + sj1 * q_ce; Dm[4] = J.peD + sj1 * q_pe; Dm[5] = sj1 * q_ps;
     Dm[6] = sj2 * q_ce; Dm[7] = sj2 * q_pe; Dm[8] = J.psD + sj2 * q_ps;
     if (!ro.act) { Dm[0] = 1; Dm[1] = 0; Dm[2] = 0; Dm[3] = 0; Dm[4] = 1; Dm[5] = 0; Dm[6] = 0; Dm[7] = 0; Dm[8] = 1; }
+    // off-diagonal blocks: L = [[L0,0,0],[L1,L2,0],[0,0,L3]] (entries (ce,ce) (pe,ce) (pe,pe) (ps,ps)), U alike
     double L4[4] = {alg_only ? 0.0 : J.ceL, alg_only ? 0.0 : J.pcL, J.peL, J.psL};
     double U4[4] = {alg_only ? 0.0 : J.ceU, alg_only ? 0.0 : J.pcU, J.peU, J.psU};
     if (!ro.act || ro.x == 0) { L4[0] = L4[1] = L4[2] = L4[3] = 0.0; }
     if (!ro.act || ro.x >= m.Nx - 1) { U4[0] = U4[1] = U4[2] = U4[3] = 0.0; }
+    // U of the left neighbour (static during the factorisation)
+    const double Ul0 = shfl_up(U4[0]), Ul1 = shfl_up(U4[1]), Ul2 = shfl_up(U4[2]), Ul3 = shfl_up(U4[3]);
+    // ---- 3. block Thomas factorisation as a fixed-point iteration along the lanes ----------------
+    //   D'_x = D_x - W_x U_{x-1},  W_x = L_x Dinv_{x-1}   (lane 0: W = 0)
+    double Di[9], Wm[9];
+    inv3x3(Dm, Di);
 #pragma unroll
-    for (int k = 0; k < 4; k++) { Fa.Lb[k][lane] = L4[k]; Fa.Ub[k][lane] = U4[k]; }
-    // ---- 3. block Thomas factorisation along the lanes (serial in x, shuffles carry the pivot) ----
-    double P[9];   // Dinv_{x-1} * U_{x-1}, received from the left
+    for (int k = 0; k < 9; k++) Wm[k] = 0.0;
+    for (int it = 1; it < m.Nx; it++) {
+        double G[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) P[k] = 0.0;
-    double Di[9];
+        for (int k = 0; k < 9; k++) G[k] = shfl_up(Di[k]);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Di[k] = 0.0;
-    double zf[3] = {0.0, 0.0, J.ps_I};   // border column e_I restricted to this node (only Phi_s rows)
-    double zy[3] = {0.0, 0.0, 0.0};
-    for (int xx = 0; xx < m.Nx; xx++) {
-        // every lane executes the arithmetic; only lane xx keeps the result
+        for (int c = 0; c < 3; c++) {
+            Wm[c] = L4[0] * G[c];
+            Wm[3 + c] = L4[1] * G[c] + L4[2] * G[3 + c];
+            Wm[6 + c] = L4[3] * G[6 + c];
+        }
         double Dp[9];
-        // Dp = Dm - L * P ; L = [[L0,0,0],[L1,L2,0],[0,0,L3]]
-        Dp[0] = Dm[0] - L4[0] * P[0]; Dp[1] = Dm[1] - L4[0] * P[1]; Dp[2] = Dm[2] - L4[0] * P[2];
-        Dp[3] = Dm[3] - (L4[1] * P[0] + L4[2] * P[3]);
-        Dp[4] = Dm[4] - (L4[1] * P[1] + L4[2] * P[4]);
-        Dp[5] = Dm[5] - (L4[1] * P[2] + L4[2] * P[5]);
-        Dp[6] = Dm[6] - L4[3] * P[6]; Dp[7] = Dm[7] - L4[3] * P[7]; Dp[8] = Dm[8] - L4[3] * P[8];
-        double Dinv[9];
-        inv3x3(Dp, Dinv);
-        // forward-substituted border column: zy = zf - L * (Dinv_{x-1} zy_{x-1}) (received as tz)
-        // compute products to pass right: Pn = Dinv * U ; U = [[U0,0,0],[U1,U2,0],[0,0,U3]]
-        double Pn[9];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            Pn[i * 3 + 0] = Dinv[i * 3 + 0] * U4[0] + Dinv[i * 3 + 1] * U4[1];
-            Pn[i * 3 + 1] = Dinv[i * 3 + 1] * U4[2];
-            Pn[i * 3 + 2] = Dinv[i * 3 + 2] * U4[3];
+            Dp[i * 3 + 0] = Dm[i * 3 + 0] - (Wm[i * 3 + 0] * Ul0 + Wm[i * 3 + 1] * Ul1);
+            Dp[i * 3 + 1] = Dm[i * 3 + 1] - Wm[i * 3 + 1] * Ul2;
+            Dp[i * 3 + 2] = Dm[i * 3 + 2] - Wm[i * 3 + 2] * Ul3;
         }
-        if (lane == xx) {
+        if (lane > 0) inv3x3(Dp, Di);
+    }
+    double Pm[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) Di[k] = Dinv[k];
-        }
-        // pass Pn from lane xx to lane xx+1
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const double v = shfl_up(Pn[k]);
-            if (lane == xx + 1) P[k] = v;
-        }
+    for (int i = 0; i < 3; i++) {
+        Pm[i * 3 + 0] = Di[i * 3 + 0] * U4[0] + Di[i * 3 + 1] * U4[1];
+        Pm[i * 3 + 1] = Di[i * 3 + 1] * U4[2];
+        Pm[i * 3 + 2] = Di[i * 3 + 2] * U4[3];
     }
 #pragma unroll
-    for (int k = 0; k < 9; k++) Fa.Dinv[k][lane] = Di[k];
-    __syncwarp();
-    // ---- 4. border: z = T^{-1} e_I via the generic solve, then the Schur complement -------------
-    // forward
-    double t3[3] = {0.0, 0.0, 0.0};   // Dinv_{x-1} * y_{x-1}
-    for (int xx = 0; xx < m.Nx; xx++) {
-        double yv[3];
-        yv[0] = zf[0] - L4[0] * t3[0];
-        yv[1] = zf[1] - (L4[1] * t3[0] + L4[2] * t3[1]);
-        yv[2] = zf[2] - L4[3] * t3[2];
-        if (lane == xx) { zy[0] = yv[0]; zy[1] = yv[1]; zy[2] = yv[2]; }
-        double tn[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) tn[i] = Di[i * 3] * yv[0] + Di[i * 3 + 1] * yv[1] + Di[i * 3 + 2] * yv[2];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const double v = shfl_up(tn[i]);
-            if (lane == xx + 1) t3[i] = v;
-        }
-    }
-    // backward
-    double u3[3] = {0.0, 0.0, 0.0}, un[3] = {0.0, 0.0, 0.0};   // un = u_{x+1}
-    for (int xx = m.Nx - 1; xx >= 0; xx--) {
-        double v[3];
-        v[0] = zy[0] - U4[0] * un[0];
-        v[1] = zy[1] - (U4[1] * un[0] + U4[2] * un[1]);
-        v[2] = zy[2] - U4[3] * un[2];
-        double uu[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) uu[i] = Di[i * 3] * v[0] + Di[i * 3 + 1] * v[1] + Di[i * 3 + 2] * v[2];
-        if (lane == xx) { u3[0] = uu[0]; u3[1] = uu[1]; u3[2] = uu[2]; }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const double w = shfl_dn(uu[i]);
-            if (lane == xx - 1) un[i] = w;
-        }
-    }
+    for (int k = 0; k < 9; k++) { Fa.Dinv[k][lane] = Di[k]; Fa.Wm[k][lane] = Wm[k]; Fa.Pm[k][lane] = Pm[k]; }
+    // ---- 4. border: z = T^{-1} e_I, then the Schur complement ------------------------------------
+    const double zf[3] = {0.0, 0.0, J.ps_I};   // border column e_I restricted to this node (Phi_s rows only)
+    double u3[3];
+    thomas_sweeps(m.Nx, Wm, Pm, Di, zf, u3);
     Fa.z[0][lane] = u3[0]; Fa.z[1][lane] = u3[1]; Fa.z[2][lane] = u3[2];
     const double z0 = shfl_from(u3[2], 0), zN = shfl_from(u3[2], m.Nx - 1);
     if (lane == 0) {
@@ -583,8 +564,8 @@ __device__ __forceinline__ void warp_factor(const ModelDesc& m, const LaneRole& 
 
 // Solve J * d = g for one right-hand side held node-wise in registers (g in, d out, in place).
 // gI: control-row right-hand side (uniform); returns dI (uniform).
-__device__ __forceinline__ double warp_solve(const ModelDesc& m, const LaneRole& ro, const WarpFactor& Fa,
-                                             bool alg_only, LaneVec& g, double gI, int lane) {
+__device__ __noinline__ double warp_solve(const ModelDesc& m, const LaneRole& ro, const WarpFactor& Fa,
+                                          bool alg_only, LaneVec& g, double gI, int lane) {
     const int el = ro.sec == 2 ? 1 : 0;
     // particle: s = Sinv * g_cs
     double s[NR];
@@ -609,45 +590,11 @@ __device__ __forceinline__ double warp_solve(const ModelDesc& m, const LaneRole&
     rf[1] = g.pe - Fa.sj[1][lane] * q0;
     rf[2] = (ro.elec ? g.ps : 0.0) - Fa.sj[2][lane] * q0;
     if (!ro.act) { rf[0] = rf[1] = rf[2] = 0.0; }
-    double Di[9], L4[4], U4[4];
+    double Di[9], Wm[9], Pm[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) Di[k] = Fa.Dinv[k][lane];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { L4[k] = Fa.Lb[k][lane]; U4[k] = Fa.Ub[k][lane]; }
-    // forward sweep
-    double yv[3] = {0.0, 0.0, 0.0}, t3[3] = {0.0, 0.0, 0.0};
-    for (int xx = 0; xx < m.Nx; xx++) {
-        double yy[3];
-        yy[0] = rf[0] - L4[0] * t3[0];
-        yy[1] = rf[1] - (L4[1] * t3[0] + L4[2] * t3[1]);
-        yy[2] = rf[2] - L4[3] * t3[2];
-        if (lane == xx) { yv[0] = yy[0]; yv[1] = yy[1]; yv[2] = yy[2]; }
-        double tn[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) tn[i] = Di[i * 3] * yy[0] + Di[i * 3 + 1] * yy[1] + Di[i * 3 + 2] * yy[2];
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const double v = shfl_up(tn[i]);
-            if (lane == xx + 1) t3[i] = v;
-        }
-    }
-    // backward sweep
-    double u3[3] = {0.0, 0.0, 0.0}, un[3] = {0.0, 0.0, 0.0};
-    for (int xx = m.Nx - 1; xx >= 0; xx--) {
-        double v[3];
-        v[0] = yv[0] - U4[0] * un[0];
-        v[1] = yv[1] - (U4[1] * un[0] + U4[2] * un[1]);
-        v[2] = yv[2] - U4[3] * un[2];
-        double uu[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) uu[i] = Di[i * 3] * v[0] + Di[i * 3 + 1] * v[1] + Di[i * 3 + 2] * v[2];
-        if (lane == xx) { u3[0] = uu[0]; u3[1] = uu[1]; u3[2] = uu[2]; }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const double w = shfl_dn(uu[i]);
-            if (lane == xx - 1) un[i] = w;
-        }
-    }
+    for (int k = 0; k < 9; k++) { Di[k] = Fa.Dinv[k][lane]; Wm[k] = Fa.Wm[k][lane]; Pm[k] = Fa.Pm[k][lane]; }
+    double u3[3];
+    thomas_sweeps(m.Nx, Wm, Pm, Di, rf, u3);
     // border
     const double x0 = shfl_from(u3[2], 0), xN = shfl_from(u3[2], m.Nx - 1);
     const double dI = (gI - Fa.g_ps0 * x0 - Fa.g_psN * xN) * Fa.schur_inv;

@@ -116,7 +116,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     int iter;
     bool ok = false;
     for (iter = 1; iter <= 100; iter++) {
-        lane_eval<CHEM, true>(m, w.C, ro, y, yp, I, rc.method, rc.value, res, ctrl, J);   // R_alg, J_alg
+        lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, I, rc.method, rc.value, res, ctrl, J);   // R_alg, J_alg
         n_res++; n_jac++;
         warp_factor(m, ro, J, ctrl, 0.0, true, w.Fa, lane);
         const double dI = warp_solve(m, ro, w.Fa, true, res, ctrl.res, lane);
@@ -131,7 +131,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     }
     if (!ok) return FAIL_NEWTON_INIT;
     // R_diff(YP,t,Y,YP): YP_diff = rhs of the differential rows (:460)
-    lane_eval<CHEM, false>(m, w.C, ro, y, yp, I, rc.method, rc.value, res, ctrl, J);
+    lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, I, rc.method, rc.value, res, ctrl, J);
     n_res++;
     LaneVec ypo;
     ypo.ce = res.ce;
@@ -146,7 +146,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
         yn.ce = y.ce + dt * ypo.ce;
 #pragma unroll
         for (int r = 0; r < NR; r++) yn.cs[r] = y.cs[r] + dt * ypo.cs[r];
-        lane_eval<CHEM, false>(m, w.C, ro, yn, yp, I, rc.method, rc.value, res, ctrl, J);
+        lane_eval_ni<CHEM, false>(m, w.C, ro, yn, yp, I, rc.method, rc.value, res, ctrl, J);
         n_res++;
         const double dI = warp_solve(m, ro, w.Fa, true, res, ctrl.res, lane);
         ypo.j = -res.j / dt; ypo.pe = -res.pe / dt; ypo.ps = -res.ps / dt;
@@ -271,7 +271,7 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
         for (int r = 0; r < NR; r++) { y.cs[r] = yp0.cs[r] + ee.cs[r]; yp.cs[r] = ypp0.cs[r] + M.cj * ee.cs[r]; }
         double Iy = Ip0 + eeI;
         if (callLSetup) {
-            lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
+            lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
             M.nre++; M.nje++;
             warp_factor(m, ro, J, ctrl, M.cj, false, w.Fa, lane);
             // a non-finite factorisation is a recoverable lsetup failure
@@ -280,7 +280,7 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
             M.cjold = M.cj; M.cjratio = 1.0; M.ss = 20.0;
             jcur = true;
         } else {
-            lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
+            lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
             M.nre++;
         }
         int mi = 0;
@@ -330,7 +330,7 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
 #pragma unroll
             for (int r = 0; r < NR; r++) { y.cs[r] = yp0.cs[r] + ee.cs[r]; yp.cs[r] = ypp0.cs[r] + M.cj * ee.cs[r]; }
             Iy = Ip0 + eeI;
-            lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
+            lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
             M.nre++;
         }
         if (retval == 0) break;

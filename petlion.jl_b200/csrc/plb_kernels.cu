@@ -46,93 +46,97 @@ struct ResJacArgs {
     double value;
     double *res, *nzval;
     int nnz;
-    const int16_t* pos;   // [JS_COUNT][32]
+    const int16_t* src;   // [nnz]: >= 0 staging index (slot*32+lane) of a lane-computed entry;
+                          //        < 0: particle-block entry, code = -1-src: bit1 electrode, bit0 diagonal
+    const double* mcv;    // [nnz]: MC coefficient of particle-block entries
 };
 
 constexpr int K1_WARPS = 4;
+constexpr int K1_NSTAGE = JS_CS0 + 3;   // lane-computed slots: 0..JS_CS_J, then the three control-row slots
+__host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 struct K1Warp {
-    double Y[VS], YP[VS], R[VS];
+    double S[K1_NSTAGE][32];
     WarpConst C;
 };
 
+// K1: one warp evaluates F and the CSC values of dF/dY + gamma dF/dY' of one system at a time.
+// HBM traffic per system is exactly the algorithmic 8*(3N + n_theta + nnz) bytes: Y, Y', theta rows
+// are read once (lane-mapped, L1-coalesced), res and nzval rows are written once with lane-consecutive
+// 8-byte stores.  77 % of nzval is the constant particle stencil scaled by D_s/Rp^2 (minus gamma on
+// the diagonal): those entries are produced in the coalesced write loop from a position table, never
+// staged; only the ~500 lane-computed entries go through a 6.4 KB shared-memory stage.
 template <int CHEM>
-__global__ void __launch_bounds__(K1_WARPS * 32) k_resjac(ResJacArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(K1_WARPS * 32, 4) k_resjac(ResJacArgs a) {
+    __shared__ K1Warp ws[K1_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ModelDesc& m = a.m;
     const int N = m.N_tot;
-    int16_t* pos = reinterpret_cast<int16_t*>(smem_raw);
-    const size_t pos_bytes = ((size_t)JS_COUNT * 32 * sizeof(int16_t) + 15) & ~size_t(15);
-    K1Warp* wsp = reinterpret_cast<K1Warp*>(smem_raw + pos_bytes) + warp;
-    const size_t nz_off = pos_bytes + sizeof(K1Warp) * K1_WARPS;
-    double* nz = reinterpret_cast<double*>(smem_raw + nz_off) + (size_t)warp * ((a.nnz + 1) & ~1);
-    for (int i = threadIdx.x; i < JS_COUNT * 32; i += blockDim.x) pos[i] = a.pos[i];
-    __syncthreads();
+    K1Warp& w = ws[warp];
     const LaneRole ro = make_role(m, lane);
     const int nwarps = gridDim.x * K1_WARPS;
     for (int sys = blockIdx.x * K1_WARPS + warp; sys < a.B; sys += nwarps) {
-        K1Warp& w = *wsp;
-        // coalesced row loads (reference layout), staged in shared memory
-        const double* gY = a.Y + (size_t)sys * N;
-        const double* gYP = a.YP + (size_t)sys * N;
-        for (int i = lane; i < N; i += 32) { w.Y[i] = gY[i]; w.YP[i] = gYP[i]; }
-        setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
-        __syncwarp();
+        const double* __restrict__ gY = a.Y + (size_t)sys * N;
+        const double* __restrict__ gYP = a.YP + (size_t)sys * N;
         LaneVec y, yp, res;
-        y.ce = ro.act ? w.Y[ro.x] : 0.0; yp.ce = ro.act ? w.YP[ro.x] : 0.0;
-        y.pe = ro.act ? w.Y[m.off_pe + ro.x] : 0.0; yp.pe = 0.0;
+        y.ce = ro.act ? gY[ro.x] : 0.0; yp.ce = ro.act ? gYP[ro.x] : 0.0;
+        y.pe = ro.act ? gY[m.off_pe + ro.x] : 0.0; yp.pe = 0.0;
         if (ro.elec) {
 #pragma unroll
-            for (int r = 0; r < NR; r++) { y.cs[r] = w.Y[m.off_cs + ro.e * NR + r]; yp.cs[r] = w.YP[m.off_cs + ro.e * NR + r]; }
-            y.j = w.Y[m.off_j + ro.e]; y.ps = w.Y[m.off_ps + ro.e];
+            for (int r = 0; r < NR; r++) { y.cs[r] = gY[m.off_cs + ro.e * NR + r]; yp.cs[r] = gYP[m.off_cs + ro.e * NR + r]; }
+            y.j = gY[m.off_j + ro.e]; y.ps = gY[m.off_ps + ro.e];
         } else {
 #pragma unroll
             for (int r = 0; r < NR; r++) { y.cs[r] = 0.0; yp.cs[r] = 0.0; }
             y.j = 0.0; y.ps = 0.0;
         }
         yp.j = 0.0; yp.ps = 0.0;
-        const double Iapp = w.Y[m.off_I];
+        const double Iapp = gY[m.off_I];
         const double value = a.values ? a.values[sys] : a.value;
+        setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
         LaneJac J;
         CtrlRow ctrl;
         if (a.nzval) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iapp, a.method, value, res, ctrl, J);
         else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iapp, a.method, value, res, ctrl, J);
         if (a.res) {
-            if (ro.act) { w.R[ro.x] = res.ce; w.R[m.off_pe + ro.x] = res.pe; }
+            double* __restrict__ gR = a.res + (size_t)sys * N;
+            if (ro.act) { gR[ro.x] = res.ce; gR[m.off_pe + ro.x] = res.pe; }
             if (ro.elec) {
 #pragma unroll
-                for (int r = 0; r < NR; r++) w.R[m.off_cs + ro.e * NR + r] = res.cs[r];
-                w.R[m.off_j + ro.e] = res.j;
-                w.R[m.off_ps + ro.e] = res.ps;
+                for (int r = 0; r < NR; r++) gR[m.off_cs + ro.e * NR + r] = res.cs[r];
+                gR[m.off_j + ro.e] = res.j;
+                gR[m.off_ps + ro.e] = res.ps;
             }
-            if (lane == 0) w.R[m.off_I] = ctrl.res;
-            __syncwarp();
-            double* gR = a.res + (size_t)sys * N;
-            for (int i = lane; i < N; i += 32) gR[i] = w.R[i];
+            if (lane == 0) gR[m.off_I] = ctrl.res;
         }
         if (a.nzval) {
             const double g = a.gamma ? a.gamma[sys] : 0.0;
-            auto put = [&](int slot, double v) {
-                const int p = pos[slot * 32 + lane];
-                if (p >= 0) nz[p] = v;
-            };
-            put(JS_CE_L, J.ceL); put(JS_CE_D, J.ceD - g); put(JS_CE_U, J.ceU); put(JS_CE_J, J.ce_j);
-            put(JS_J_CS, J.j_cs); put(JS_J_CE, J.j_ce); put(JS_J_PE, J.j_pe); put(JS_J_PS, J.j_ps); put(JS_J_J, -1.0);
-            put(JS_PE_L, J.peL); put(JS_PE_D, J.peD); put(JS_PE_U, J.peU);
-            put(JS_PC_L, J.pcL); put(JS_PC_D, J.pcD); put(JS_PC_U, J.pcU); put(JS_PE_J, J.pe_j);
-            put(JS_PS_L, J.psL); put(JS_PS_D, J.psD); put(JS_PS_U, J.psU); put(JS_PS_J, J.ps_j); put(JS_PS_I, J.ps_I);
-            put(JS_CS_J, J.cs_j);
-#pragma unroll
-            for (int r = 0; r < NR; r++)
-#pragma unroll
-                for (int c = 0; c < NR; c++)
-                    if (laws::mc_mask(r) & (1u << c))
-                        put(JS_CS0 + r * NR + c, J.kap * laws::MC[r][c] - (r == c ? g : 0.0));
-            put(JS_CTRL_PS0, ctrl.g_ps0); put(JS_CTRL_PSN, ctrl.g_psN); put(JS_CTRL_I, ctrl.g_I);
+            w.S[JS_CE_L][lane] = J.ceL; w.S[JS_CE_D][lane] = J.ceD - g; w.S[JS_CE_U][lane] = J.ceU; w.S[JS_CE_J][lane] = J.ce_j;
+            w.S[JS_J_CS][lane] = J.j_cs; w.S[JS_J_CE][lane] = J.j_ce; w.S[JS_J_PE][lane] = J.j_pe; w.S[JS_J_PS][lane] = J.j_ps;
+            w.S[JS_J_J][lane] = -1.0;
+            w.S[JS_PE_L][lane] = J.peL; w.S[JS_PE_D][lane] = J.peD; w.S[JS_PE_U][lane] = J.peU;
+            w.S[JS_PC_L][lane] = J.pcL; w.S[JS_PC_D][lane] = J.pcD; w.S[JS_PC_U][lane] = J.pcU; w.S[JS_PE_J][lane] = J.pe_j;
+            w.S[JS_PS_L][lane] = J.psL; w.S[JS_PS_D][lane] = J.psD; w.S[JS_PS_U][lane] = J.psU; w.S[JS_PS_J][lane] = J.ps_j;
+            w.S[JS_PS_I][lane] = J.ps_I;
+            w.S[JS_CS_J][lane] = J.cs_j;
+            w.S[k1_stage_slot(JS_CTRL_PS0)][lane] = ctrl.g_ps0;
+            w.S[k1_stage_slot(JS_CTRL_PSN)][lane] = ctrl.g_psN;
+            w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
             __syncwarp();
-            double* gN = a.nzval + (size_t)sys * a.nnz;
-            for (int i = lane; i < a.nnz; i += 32) gN[i] = nz[i];
+            const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
+            const double* Sflat = &w.S[0][0];
+            double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
+#pragma unroll 4
+            for (int p = lane; p < a.nnz; p += 32) {
+                const int sidx = a.src[p];
+                double v;
+                if (sidx >= 0) v = Sflat[sidx];
+                else {
+                    const int code = -1 - sidx;
+                    v = ((code & 2) ? kap_n : kap_p) * a.mcv[p] - ((code & 1) ? g : 0.0);
+                }
+                gN[p] = v;
+            }
         }
         __syncwarp();
     }
@@ -276,7 +280,8 @@ struct plb_handle_s {
     std::vector<int> keys;               // indices into KEYS, reference (sorted) order
     // CSC patterns per method
     std::vector<int> colptr[3], rowval[3];
-    int16_t* d_pos[3] = {nullptr, nullptr, nullptr};
+    int16_t* d_src[3] = {nullptr, nullptr, nullptr};
+    double* d_mcv[3] = {nullptr, nullptr, nullptr};
     int* d_counter = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -337,6 +342,8 @@ static bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row
 
 static int build_patterns(plb_handle_s* h) {
     const ModelDesc& m = h->m;
+    double h_MC[NR][NR];
+    CUDA_OK(cudaMemcpyFromSymbol(h_MC, laws::MC, sizeof(h_MC)));
     for (int method = 0; method < 3; method++) {
         std::vector<std::pair<int, int>> ent;   // (col, row)
         for (int lane = 0; lane < 32; lane++)
@@ -355,14 +362,30 @@ static int build_patterns(plb_handle_s* h) {
             h->colptr[method][ent[k].first + 1]++;
         }
         for (int c = 0; c < m.N_tot; c++) h->colptr[method][c + 1] += h->colptr[method][c];
-        std::vector<int16_t> pos((size_t)JS_COUNT * 32, -1);
+        // per CSC position: where K1 takes the value from
+        std::vector<int16_t> src(ent.size(), 0);
+        std::vector<double> mcv(ent.size(), 0.0);
+        std::vector<char> seen(ent.size(), 0);
         for (int lane = 0; lane < 32; lane++)
             for (int s = 0; s < JS_COUNT; s++) {
                 int r, c;
-                if (slot_rc(m, method, s, lane, r, c)) pos[(size_t)s * 32 + lane] = (int16_t)idx[{c, r}];
+                if (!slot_rc(m, method, s, lane, r, c)) continue;
+                const int p = idx[{c, r}];
+                seen[p] = 1;
+                if (s >= JS_CS0 && s < JS_CS0 + NR * NR) {
+                    const int rr = (s - JS_CS0) / NR, cc = (s - JS_CS0) % NR;
+                    const int el = lane >= m.Np + m.Ns ? 1 : 0;
+                    src[p] = (int16_t)(-1 - (el * 2 + (rr == cc ? 1 : 0)));
+                    mcv[p] = h_MC[rr][cc];
+                } else {
+                    src[p] = (int16_t)(k1_stage_slot(s) * 32 + lane);
+                }
             }
-        CUDA_OK(cudaMalloc(&h->d_pos[method], pos.size() * sizeof(int16_t)));
-        CUDA_OK(cudaMemcpy(h->d_pos[method], pos.data(), pos.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+        for (char c : seen) if (!c) return fail("internal: Jacobian position without a source");
+        CUDA_OK(cudaMalloc(&h->d_src[method], src.size() * sizeof(int16_t)));
+        CUDA_OK(cudaMemcpy(h->d_src[method], src.data(), src.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&h->d_mcv[method], mcv.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(h->d_mcv[method], mcv.data(), mcv.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     return 0;
 }
@@ -411,7 +434,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
 
 int plb_destroy(plb_handle h) {
     if (!h) return 0;
-    for (int i = 0; i < 3; i++) cudaFree(h->d_pos[i]);
+    for (int i = 0; i < 3; i++) { cudaFree(h->d_src[i]); cudaFree(h->d_mcv[i]); }
     cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -564,17 +587,14 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
     memset(&a, 0, sizeof a);
     a.m = m; a.B = B; a.Y = Y; a.YP = YP; a.gamma = gamma; a.theta = theta; a.values = values;
     a.method = run->method; a.value = run->value; a.res = res; a.nzval = nzval; a.nnz = nnz;
-    a.pos = h->d_pos[run->method];
-    const size_t pos_bytes = ((size_t)JS_COUNT * 32 * sizeof(int16_t) + 15) & ~size_t(15);
-    const size_t smem = pos_bytes + sizeof(K1Warp) * K1_WARPS + sizeof(double) * K1_WARPS * ((nnz + 1) & ~1);
-    const int per_sm = 2;
-    const int grid = std::min((B + K1_WARPS - 1) / K1_WARPS, h->num_sms * per_sm);
+    a.src = h->d_src[run->method];
+    a.mcv = h->d_mcv[run->method];
+    const size_t smem = 0;
+    const int grid = std::min((B + K1_WARPS - 1) / K1_WARPS, h->num_sms * 4 * 2);
     CUDA_OK(cudaEventRecord(h->ev0, s));
     if (m.chem == CHEM_LCO) {
-        CUDA_OK(cudaFuncSetAttribute(k_resjac<CHEM_LCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_resjac<CHEM_LCO><<<grid, K1_WARPS * 32, smem, s>>>(a);
     } else {
-        CUDA_OK(cudaFuncSetAttribute(k_resjac<CHEM_NMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_resjac<CHEM_NMC><<<grid, K1_WARPS * 32, smem, s>>>(a);
     }
     CUDA_OK(cudaEventRecord(h->ev1, s));
