@@ -46,17 +46,19 @@ struct ResJacArgs {
     double value;
     double *res, *nzval;
     int nnz;
-    const int16_t* src;   // [nnz]: >= 0 staging index (slot*32+lane) of a lane-computed entry;
-                          //        < 0: particle-block entry, code = -1-src: bit1 electrode, bit0 diagonal
-    const double* mcv;    // [nnz]: MC coefficient of particle-block entries
+    const int* src;       // [nnz] recipe per CSC position: bits 0-15 index into the warp's value table
+                          //   (lane-computed entries: slot*32+lane; particle entries: K1_NSTAGE*32 + r*NR+c),
+                          //   bit 16 particle-block entry, bit 17 anode, bit 18 diagonal
 };
 
 constexpr int K1_WARPS = 4;
 constexpr int K1_NSTAGE = JS_CS0 + 3;   // lane-computed slots: 0..JS_CS_J, then the three control-row slots
+constexpr int K1_SRC_MAX = 2304;        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 struct K1Warp {
-    double S[K1_NSTAGE][32];
+    double S[K1_NSTAGE][32];   // lane-computed Jacobian entries
+    double MCs[NR * NR];       // particle stencil coefficients (contiguous with S: one value table)
     WarpConst C;
 };
 
@@ -64,11 +66,19 @@ struct K1Warp {
 // HBM traffic per system is exactly the algorithmic 8*(3N + n_theta + nnz) bytes: Y, Y', theta rows
 // are read once (lane-mapped, L1-coalesced), res and nzval rows are written once with lane-consecutive
 // 8-byte stores.  77 % of nzval is the constant particle stencil scaled by D_s/Rp^2 (minus gamma on
-// the diagonal): those entries are produced in the coalesced write loop from a position table, never
-// staged; only the ~500 lane-computed entries go through a 6.4 KB shared-memory stage.
+// the diagonal): those entries are produced in the coalesced, branch-free write loop from a recipe
+// table held in shared memory, never staged; only the ~500 lane-computed entries go through a
+// 6.4 KB shared-memory stage.
 template <int CHEM>
 __global__ void __launch_bounds__(K1_WARPS * 32, 4) k_resjac(ResJacArgs a) {
     __shared__ K1Warp ws[K1_WARPS];
+    __shared__ int src_s[K1_SRC_MAX];
+    for (int i = threadIdx.x; i < a.nnz; i += blockDim.x) src_s[i] = a.src[i];
+    {
+        K1Warp& w0 = ws[threadIdx.x >> 5];
+        for (int i = threadIdx.x & 31; i < NR * NR; i += 32) w0.MCs[i] = laws::MC[i / NR][i % NR];
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ModelDesc& m = a.m;
     const int N = m.N_tot;
@@ -124,18 +134,15 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 4) k_resjac(ResJacArgs a) {
             w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
             __syncwarp();
             const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
-            const double* Sflat = &w.S[0][0];
+            const double* tab = &w.S[0][0];
             double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
 #pragma unroll 4
             for (int p = lane; p < a.nnz; p += 32) {
-                const int sidx = a.src[p];
-                double v;
-                if (sidx >= 0) v = Sflat[sidx];
-                else {
-                    const int code = -1 - sidx;
-                    v = ((code & 2) ? kap_n : kap_p) * a.mcv[p] - ((code & 1) ? g : 0.0);
-                }
-                gN[p] = v;
+                const int rc = src_s[p];
+                const double t = tab[rc & 0xffff];
+                const double kap = (rc & (1 << 17)) ? kap_n : kap_p;
+                const double gd = (rc & (1 << 18)) ? g : 0.0;
+                gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
             }
         }
         __syncwarp();
@@ -280,8 +287,7 @@ struct plb_handle_s {
     std::vector<int> keys;               // indices into KEYS, reference (sorted) order
     // CSC patterns per method
     std::vector<int> colptr[3], rowval[3];
-    int16_t* d_src[3] = {nullptr, nullptr, nullptr};
-    double* d_mcv[3] = {nullptr, nullptr, nullptr};
+    int* d_src[3] = {nullptr, nullptr, nullptr};
     int* d_counter = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -342,8 +348,7 @@ static bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row
 
 static int build_patterns(plb_handle_s* h) {
     const ModelDesc& m = h->m;
-    double h_MC[NR][NR];
-    CUDA_OK(cudaMemcpyFromSymbol(h_MC, laws::MC, sizeof(h_MC)));
+
     for (int method = 0; method < 3; method++) {
         std::vector<std::pair<int, int>> ent;   // (col, row)
         for (int lane = 0; lane < 32; lane++)
@@ -363,29 +368,24 @@ static int build_patterns(plb_handle_s* h) {
         }
         for (int c = 0; c < m.N_tot; c++) h->colptr[method][c + 1] += h->colptr[method][c];
         // per CSC position: where K1 takes the value from
-        std::vector<int16_t> src(ent.size(), 0);
-        std::vector<double> mcv(ent.size(), 0.0);
-        std::vector<char> seen(ent.size(), 0);
+        if ((int)ent.size() > K1_SRC_MAX) return fail("internal: K1_SRC_MAX too small");
+        std::vector<int> src(ent.size(), -1);
         for (int lane = 0; lane < 32; lane++)
             for (int s = 0; s < JS_COUNT; s++) {
                 int r, c;
                 if (!slot_rc(m, method, s, lane, r, c)) continue;
                 const int p = idx[{c, r}];
-                seen[p] = 1;
                 if (s >= JS_CS0 && s < JS_CS0 + NR * NR) {
                     const int rr = (s - JS_CS0) / NR, cc = (s - JS_CS0) % NR;
                     const int el = lane >= m.Np + m.Ns ? 1 : 0;
-                    src[p] = (int16_t)(-1 - (el * 2 + (rr == cc ? 1 : 0)));
-                    mcv[p] = h_MC[rr][cc];
+                    src[p] = (K1_NSTAGE * 32 + rr * NR + cc) | (1 << 16) | (el << 17) | ((rr == cc ? 1 : 0) << 18);
                 } else {
-                    src[p] = (int16_t)(k1_stage_slot(s) * 32 + lane);
+                    src[p] = k1_stage_slot(s) * 32 + lane;
                 }
             }
-        for (char c : seen) if (!c) return fail("internal: Jacobian position without a source");
-        CUDA_OK(cudaMalloc(&h->d_src[method], src.size() * sizeof(int16_t)));
-        CUDA_OK(cudaMemcpy(h->d_src[method], src.data(), src.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMalloc(&h->d_mcv[method], mcv.size() * sizeof(double)));
-        CUDA_OK(cudaMemcpy(h->d_mcv[method], mcv.data(), mcv.size() * sizeof(double), cudaMemcpyHostToDevice));
+        for (int v : src) if (v < 0) return fail("internal: Jacobian position without a source");
+        CUDA_OK(cudaMalloc(&h->d_src[method], src.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpy(h->d_src[method], src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     return 0;
 }
@@ -434,7 +434,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
 
 int plb_destroy(plb_handle h) {
     if (!h) return 0;
-    for (int i = 0; i < 3; i++) { cudaFree(h->d_src[i]); cudaFree(h->d_mcv[i]); }
+    for (int i = 0; i < 3; i++) cudaFree(h->d_src[i]);
     cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -588,7 +588,6 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
     a.m = m; a.B = B; a.Y = Y; a.YP = YP; a.gamma = gamma; a.theta = theta; a.values = values;
     a.method = run->method; a.value = run->value; a.res = res; a.nzval = nzval; a.nnz = nnz;
     a.src = h->d_src[run->method];
-    a.mcv = h->d_mcv[run->method];
     const size_t smem = 0;
     const int grid = std::min((B + K1_WARPS - 1) / K1_WARPS, h->num_sms * 4 * 2);
     CUDA_OK(cudaEventRecord(h->ev0, s));
