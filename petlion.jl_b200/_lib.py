@@ -9,7 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpetlion_b200.so")
+LIB_PATH = os.environ.get("PLB_LIB", os.path.join(CSRC, "libpetlion_b200.so"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in ("plb_kernels.cu", "plb_device.cuh", "plb_integrator.cuh",
-                                            "laws_generated.cuh")]
+                                            "plb_tick.cuh", "laws_generated.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))
     gen = os.path.join(CSRC, "laws_generated.cuh")
     if not os.path.exists(gen):

@@ -453,9 +453,9 @@ __device__ __forceinline__ void thomas_sweeps(int Nx, const double* Wm, const do
 
 // alg_only: Newton on the algebraic block (newtons_method!, model_evaluation.jl:430-480):
 // c_e and c_s are frozen, the differential rows are replaced by identity.
-__device__ __noinline__ void warp_factor(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
-                                         const CtrlRow& ctrl, double cj, bool alg_only,
-                                         WarpFactor& Fa, int lane) {
+__device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
+                                                 const CtrlRow& ctrl, double cj, bool alg_only,
+                                                 WarpFactor& Fa, int lane) {
     // ---- 1. particle inverses -------------------------------------------------------------------
     if (!alg_only) {
         const int el = lane >> 4;                       // lanes 0-15 -> cathode, 16-31 -> anode
@@ -564,8 +564,8 @@ __device__ __noinline__ void warp_factor(const ModelDesc& m, const LaneRole& ro,
 
 // Solve J * d = g for one right-hand side held node-wise in registers (g in, d out, in place).
 // gI: control-row right-hand side (uniform); returns dI (uniform).
-__device__ __noinline__ double warp_solve(const ModelDesc& m, const LaneRole& ro, const WarpFactor& Fa,
-                                          bool alg_only, LaneVec& g, double gI, int lane) {
+__device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const LaneRole& ro, const WarpFactor& Fa,
+                                                  bool alg_only, LaneVec& g, double gI, int lane) {
     const int el = ro.sec == 2 ? 1 : 0;
     // particle: s = Sinv * g_cs
     double s[NR];
@@ -608,6 +608,16 @@ __device__ __noinline__ double warp_solve(const ModelDesc& m, const LaneRole& ro
 #pragma unroll
     for (int r = 0; r < NR; r++) g.cs[r] = (ro.elec && !alg_only) ? s[r] - Fa.vb[r][el] * dj : 0.0;
     return dI;
+}
+
+// out-of-line copies for the operator-level Newton-init kernel
+__device__ __noinline__ void warp_factor(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
+                                         const CtrlRow& ctrl, double cj, bool alg_only, WarpFactor& Fa, int lane) {
+    warp_factor_impl(m, ro, J, ctrl, cj, alg_only, Fa, lane);
+}
+__device__ __noinline__ double warp_solve(const ModelDesc& m, const LaneRole& ro, const WarpFactor& Fa,
+                                          bool alg_only, LaneVec& g, double gI, int lane) {
+    return warp_solve_impl(m, ro, Fa, alg_only, g, gI, lane);
 }
 
 }  // namespace plb

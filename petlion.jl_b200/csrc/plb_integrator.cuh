@@ -43,11 +43,31 @@ struct IdaCoef {
     double cprev[6];               // interpolation weights at the previous return time
 };
 
-struct WarpWS {
-    double vec[V_COUNT][VS];
+// Number of workspace vectors that live in global memory (L2-resident, L1-cached) instead of
+// shared memory: ids [0, PLB_NGLOBAL).  6 = the BDF history phi_0..phi_5; the predictor, weights and
+// correction stay in shared memory.  Fewer shared-memory bytes per system = more systems per SM.
+#ifndef PLB_NGLOBAL
+#define PLB_NGLOBAL 0
+#endif
+constexpr int NGLOBAL = PLB_NGLOBAL;
+constexpr int NSHARED = V_COUNT - NGLOBAL;
+
+struct WarpSmem {
+    double svec[NSHARED > 0 ? NSHARED : 1][VS];
     WarpConst C;
     WarpFactor Fa;
     IdaCoef K;
+};
+
+struct WarpWS {
+    double* gbase;     // this warp's slice of the global workspace: NGLOBAL vectors of VS doubles
+    double* sbase;     // shared-memory vectors
+    WarpConst& C;
+    WarpFactor& Fa;
+    IdaCoef& K;
+    __device__ __forceinline__ double* v(int id) const {
+        return id < NGLOBAL ? gbase + id * VS : sbase + (id - NGLOBAL) * VS;
+    }
 };
 
 // internal vector layout: c_e[Nx] | c_s radial-major [NR][Ne] | j[Ne] | Phi_e[Nx] | Phi_s[Ne] | I
@@ -169,7 +189,7 @@ struct Ida {
 
 __device__ __forceinline__ void ewt_set(const ModelDesc& m, WarpWS& w, const Opts& o, int lane) {
     for (int i = lane; i < m.N_tot; i += 32)
-        w.vec[V_EWT][i] = 1.0 / (o.reltol * fabs(w.vec[V_PHI0][i]) + o.abstol);
+        w.v(V_EWT)[i] = 1.0 / (o.reltol * fabs(w.v(V_PHI0)[i]) + o.abstol);
     __syncwarp();
 }
 
@@ -218,7 +238,7 @@ __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, 
     ck = fmax(ck, K.alpha[M.kk]);
     for (int k = M.ns; k <= M.kk; k++) {
         const double bk = K.beta[k];
-        for (int i = lane; i < m.N_tot; i += 32) w.vec[V_PHI0 + k][i] *= bk;
+        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI0 + k)[i] *= bk;
     }
     M.tn += M.hh;
     __syncwarp();
@@ -235,9 +255,9 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
     // predictor
     for (int i = lane; i < m.N_tot; i += 32) {
         double yv = 0.0, ypv = 0.0;
-        for (int j = 0; j <= M.kk; j++) yv += w.vec[V_PHI0 + j][i];
-        for (int j = 1; j <= M.kk; j++) ypv += K.gamma[j] * w.vec[V_PHI0 + j][i];
-        w.vec[V_YPRED][i] = yv; w.vec[V_YPPRED][i] = ypv; w.vec[V_EE][i] = 0.0;
+        for (int j = 0; j <= M.kk; j++) yv += w.v(V_PHI0 + j)[i];
+        for (int j = 1; j <= M.kk; j++) ypv += K.gamma[j] * w.v(V_PHI0 + j)[i];
+        w.v(V_YPRED)[i] = yv; w.v(V_YPPRED)[i] = ypv; w.v(V_EE)[i] = 0.0;
     }
     __syncwarp();
     M.cjratio = M.cj / M.cjold;
@@ -248,8 +268,8 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
     }
     LaneVec yp0, ypp0;     // predictor in registers (node mapping)
     double Ip0, Ipp0;
-    load_lane(m, ro, w.vec[V_YPRED], yp0, Ip0);
-    load_lane(m, ro, w.vec[V_YPPRED], ypp0, Ipp0);
+    load_lane(m, ro, w.v(V_YPRED), yp0, Ip0);
+    load_lane(m, ro, w.v(V_YPPRED), ypp0, Ipp0);
     LaneVec ee;
     double eeI = 0.0;
     ee.ce = ee.j = ee.pe = ee.ps = 0.0;
@@ -260,7 +280,7 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
     double oldnrm = 0.0;
     LaneVec ewt;
     double ewtI;
-    load_lane(m, ro, w.vec[V_EWT], ewt, ewtI);
+    load_lane(m, ro, w.v(V_EWT), ewt, ewtI);
     for (;;) {
         LaneVec y, yp, res;
         LaneJac J;
@@ -343,7 +363,7 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
         }
         break;
     }
-    store_lane(m, ro, w.vec[V_EE], ee, eeI, lane);
+    store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
     __syncwarp();
     return retval;
 }
@@ -351,11 +371,11 @@ __device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const Lane
 __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Ida& M, double ck,
                                                double& err_k, double& err_km1, int lane) {
     const IdaCoef& K = w.K;
-    const double* ee = w.vec[V_EE];
-    const double* ewt = w.vec[V_EWT];
+    const double* ee = w.v(V_EE);
+    const double* ewt = w.v(V_EWT);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    const double* pk = w.vec[V_PHI0 + M.kk];
-    const double* pk1 = w.vec[V_PHI0 + (M.kk > 0 ? M.kk - 1 : 0)];
+    const double* pk = w.v(V_PHI0 + M.kk);
+    const double* pk1 = w.v(V_PHI0 + (M.kk > 0 ? M.kk - 1 : 0));
     for (int i = lane; i < m.N_tot; i += 32) {
         const double e = ee[i], wt = ewt[i];
         const double a = e * wt; s0 = fma(a, a, s0);
@@ -388,15 +408,15 @@ __device__ __forceinline__ void ida_restore(const ModelDesc& m, WarpWS& w, Ida& 
         for (int j = 1; j <= M.kk; j++) K.psi[j - 1] = K.psi[j] - M.hh;
     for (int j = M.ns; j <= M.kk; j++) {
         const double s = 1.0 / K.beta[j];
-        for (int i = lane; i < m.N_tot; i += 32) w.vec[V_PHI0 + j][i] *= s;
+        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI0 + j)[i] *= s;
     }
     __syncwarp();
 }
 
 __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w, const Opts& o, Ida& M,
                                                   double err_k, double err_km1, int lane) {
-    const double* ee = w.vec[V_EE];
-    const double* ewt = w.vec[V_EWT];
+    const double* ee = w.v(V_EE);
+    const double* ewt = w.v(V_EWT);
     M.nst++;
     const int kdiff = M.kk - M.kused;
     M.kused = M.kk;
@@ -412,7 +432,7 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
         else if (M.kk + 1 >= M.ns || kdiff == 1) action = 2;
         if (action == 0) {
             double s = 0.0;
-            const double* pk = w.vec[V_PHI0 + M.kk + 1];
+            const double* pk = w.v(V_PHI0 + M.kk + 1);
             for (int i = lane; i < m.N_tot; i += 32) { const double a = (ee[i] - pk[i]) * ewt[i]; s = fma(a, a, s); }
             const double enorm = sqrt(warp_sum(s) / m.N_tot);
             err_kp1 = enorm / (M.kk + 2);
@@ -438,10 +458,10 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
     // phi updates
     for (int i = lane; i < m.N_tot; i += 32) {
         const double e = ee[i];
-        if (M.kused < o.maxord) w.vec[V_PHI0 + M.kused + 1][i] = e;
-        double acc = w.vec[V_PHI0 + M.kused][i] + e;
-        w.vec[V_PHI0 + M.kused][i] = acc;
-        for (int j = M.kused - 1; j >= 0; j--) { acc += w.vec[V_PHI0 + j][i]; w.vec[V_PHI0 + j][i] = acc; }
+        if (M.kused < o.maxord) w.v(V_PHI0 + M.kused + 1)[i] = e;
+        double acc = w.v(V_PHI0 + M.kused)[i] + e;
+        w.v(V_PHI0 + M.kused)[i] = acc;
+        for (int j = M.kused - 1; j >= 0; j--) { acc += w.v(V_PHI0 + j)[i]; w.v(V_PHI0 + j)[i] = acc; }
     }
     __syncwarp();
 }
@@ -490,7 +510,7 @@ __device__ __forceinline__ int ida_step(const ModelDesc& m, WarpWS& w, const Lan
         if (M.nst == 0) {
             __syncwarp();
             if (lane == 0) K.psi[0] = M.hh;
-            for (int i = lane; i < m.N_tot; i += 32) w.vec[V_PHI1][i] *= M.rr;
+            for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.rr;
             __syncwarp();
         }
         if (!(fabs(M.hh) > 0.0) || isinf(M.hh)) return FAIL_CONV;
@@ -511,7 +531,7 @@ __device__ __forceinline__ int ida_solve_one_step(const ModelDesc& m, WarpWS& w,
         M.hh = M.hin;
         if (M.hh == 0.0) {
             M.hh = 0.001 * tdist;
-            const double ypnorm = wrms(m, w.vec[V_PHI1], w.vec[V_EWT], lane);
+            const double ypnorm = wrms(m, w.v(V_PHI1), w.v(V_EWT), lane);
             if (ypnorm > 0.5 / M.hh) M.hh = 0.5 / ypnorm;
             if (tout < M.tn) M.hh = -M.hh;
         }
@@ -519,7 +539,7 @@ __device__ __forceinline__ int ida_solve_one_step(const ModelDesc& m, WarpWS& w,
             if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
         }
         M.kk = 0; M.kused = 0;
-        for (int i = lane; i < m.N_tot; i += 32) w.vec[V_PHI1][i] *= M.hh;
+        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.hh;
         __syncwarp();
     } else {
         if (M.tstopset) {
@@ -533,7 +553,7 @@ __device__ __forceinline__ int ida_solve_one_step(const ModelDesc& m, WarpWS& w,
         ewt_set(m, w, o, lane);
     }
     {
-        const double nrm = wrms(m, w.vec[V_PHI0], w.vec[V_EWT], lane);
+        const double nrm = wrms(m, w.v(V_PHI0), w.v(V_EWT), lane);
         if (ur * nrm > 1.0) { tret = M.tn; return FAIL_CONV; }
     }
     const int sflag = ida_step<CHEM>(m, w, ro, rc, o, M, lane);
@@ -553,12 +573,12 @@ __device__ __forceinline__ int ida_solve_one_step(const ModelDesc& m, WarpWS& w,
 // interpolated value / derivative of component i (internal index) with weights (c, d), order kord
 __device__ __forceinline__ double interp_y(const WarpWS& w, const double* c, int kord, int i) {
     double y = 0.0;
-    for (int j = 0; j <= kord; j++) y = fma(c[j], w.vec[V_PHI0 + j][i], y);
+    for (int j = 0; j <= kord; j++) y = fma(c[j], w.v(V_PHI0 + j)[i], y);
     return y;
 }
 __device__ __forceinline__ double interp_yp(const WarpWS& w, const double* d, int kord, int i) {
     double y = 0.0;
-    for (int j = 1; j <= kord; j++) y = fma(d[j - 1], w.vec[V_PHI0 + j][i], y);
+    for (int j = 1; j <= kord; j++) y = fma(d[j - 1], w.v(V_PHI0 + j)[i], y);
     return y;
 }
 
@@ -662,6 +682,7 @@ struct SimArgs {
     double *tr_t, *tr_V, *tr_I, *tr_SOC;
     int* tr_n;
     int* counter;
+    double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]
 };
 
 // simulate / simulate! for one system -- model_evaluation.jl:10-97, 174-232, 312-382
@@ -677,8 +698,8 @@ __device__ void simulate_system(const SimArgs& a, int sys, WarpWS& w, int lane) 
     Summary out;
     out.t_end = 0; out.V_end = 0; out.I_end = 0; out.SOC_end = 0; out.flag = -1; out.n_steps = 0;
     out.n_res = 0; out.n_jac = 0; out.n_netf = 0; out.n_ncfn = 0; out.n_newton_init = 0; out.reserved = 0;
-    double* Y0 = w.vec[V_PHI0];
-    double* YP0 = w.vec[V_PHI1];
+    double* Y0 = w.v(V_PHI0);
+    double* YP0 = w.v(V_PHI1);
     double SOC, t0;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
     double I_prev_state = 0.0;
@@ -758,7 +779,7 @@ __device__ void simulate_system(const SimArgs& a, int sys, WarpWS& w, int lane) 
         M.kk = 0; M.kused = 0; M.knew = 0; M.phase = 0; M.ns = 0; M.nst = 0; M.tstopset = 0;
         M.nre = nres; M.nje = njac; M.netf = 0; M.ncfn = 0;
         for (int k = 2; k < 6; k++)
-            for (int i = lane; i < N; i += 32) w.vec[V_PHI0 + k][i] = 0.0;
+            for (int i = lane; i < N; i += 32) w.v(V_PHI0 + k)[i] = 0.0;
         __syncwarp();
         // tstops: [1.0 if continuing; tf] (:288-310)
         double tstops[2];
@@ -801,7 +822,7 @@ __device__ void simulate_system(const SimArgs& a, int sys, WarpWS& w, int lane) 
                         retried = true;
                         // phi1 currently holds h_failed-scaled YP0: undo and restart the first step
                         const double sc = 1.0 / w.K.psi[0];
-                        for (int i = lane; i < N; i += 32) w.vec[V_PHI1][i] *= sc;
+                        for (int i = lane; i < N; i += 32) w.v(V_PHI1)[i] *= sc;
                         __syncwarp();
                         M.hin = a.o.reltol;
                         continue;

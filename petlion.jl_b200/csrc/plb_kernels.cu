@@ -161,15 +161,31 @@ struct AuxArgs {
     Opts o;
     double *Y, *YP;
     int* status;
+    double* gws;
 };
 
-constexpr int SIM_WARPS = 6;
+#ifndef PLB_SIM_WARPS
+#define PLB_SIM_WARPS 6           // warps (systems in flight) per CTA
+#endif
+#ifndef PLB_SIM_CTAS
+#define PLB_SIM_CTAS 1            // CTAs per SM the register/shared-memory budget is sized for
+#endif
+constexpr int SIM_WARPS = PLB_SIM_WARPS;
+constexpr int SIM_CTAS = PLB_SIM_CTAS;
+
+__device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+    double* g = gws + ((size_t)blockIdx.x * SIM_WARPS + warp) * (size_t)(NGLOBAL > 0 ? NGLOBAL : 1) * VS;
+    return WarpWS{g, &sm.svec[0][0], sm.C, sm.Fa, sm.K};
+}
+
+#include "plb_tick.cuh"
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32) k_initguess(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_initguess(AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpWS& w = reinterpret_cast<WarpWS*>(smem_raw)[warp];
+    WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
     for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
@@ -202,25 +218,25 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_initguess(AuxArgs a) {
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32) k_newton(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_newton(AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpWS& w = reinterpret_cast<WarpWS*>(smem_raw)[warp];
+    WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
     const int N = m.N_tot;
     for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
         setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
-        for (int i = lane; i < N; i += 32) w.vec[V_PHI0][i] = a.Y[(size_t)sys * N + ref_index(m, i)];
+        for (int i = lane; i < N; i += 32) w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
         __syncwarp();
         RunCtl rc;
         rc.method = a.method;
         rc.value = a.values ? a.values[sys] : a.value;
         int nres = 0, njac = 0;
-        const int it = newton_init<CHEM>(m, w, ro, rc, a.o, w.vec[V_PHI0], w.vec[V_PHI1], lane, nres, njac);
+        const int it = newton_init<CHEM>(m, w, ro, rc, a.o, w.v(V_PHI0), w.v(V_PHI1), lane, nres, njac);
         for (int i = lane; i < N; i += 32) {
-            a.Y[(size_t)sys * N + ref_index(m, i)] = w.vec[V_PHI0][i];
-            a.YP[(size_t)sys * N + ref_index(m, i)] = it > 0 ? w.vec[V_PHI1][i] : 0.0;
+            a.Y[(size_t)sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
+            a.YP[(size_t)sys * N + ref_index(m, i)] = it > 0 ? w.v(V_PHI1)[i] : 0.0;
         }
         if (lane == 0 && a.status) a.status[sys] = it;
         __syncwarp();
@@ -228,18 +244,11 @@ __global__ void __launch_bounds__(SIM_WARPS * 32) k_newton(AuxArgs a) {
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32) k_simulate(SimArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_simulate(SimArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpWS& w = reinterpret_cast<WarpWS*>(smem_raw)[warp];
-    // persistent warps pulling systems from a global queue (step counts vary ~1.5x across a batch)
-    for (;;) {
-        int sys = 0;
-        if (lane == 0) sys = atomicAdd(a.counter, 1);
-        sys = __shfl_sync(FULL, sys, 0);
-        if (sys >= a.B) break;
-        simulate_system<CHEM>(a, sys, w, lane);
-    }
+    // persistent CTAs; every warp pulls systems from a global queue (step counts vary ~1.5x across
+    // a batch) and all warps of the CTA tick in lockstep through the heavy phases (plb_tick.cuh)
+    simulate_cta<CHEM>(a, smem_raw);
 }
 
 // =================================================================================================
@@ -289,6 +298,8 @@ struct plb_handle_s {
     std::vector<int> colptr[3], rowval[3];
     int* d_src[3] = {nullptr, nullptr, nullptr};
     int* d_counter = nullptr;
+    double* d_gws = nullptr;             // global workspace of the persistent warps
+    int sim_grid = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
@@ -426,6 +437,8 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     h->num_sms = prop.multiProcessorCount;
     if (build_patterns(h)) { delete h; return -1; }
     CUDA_OK(cudaMalloc(&h->d_counter, sizeof(int)));
+    h->sim_grid = h->num_sms * SIM_CTAS;
+    CUDA_OK(cudaMalloc(&h->d_gws, (size_t)h->sim_grid * SIM_WARPS * (NGLOBAL > 0 ? NGLOBAL : 1) * VS * sizeof(double)));
     CUDA_OK(cudaEventCreate(&h->ev0));
     CUDA_OK(cudaEventCreate(&h->ev1));
     *out = h;
@@ -436,6 +449,7 @@ int plb_destroy(plb_handle h) {
     if (!h) return 0;
     for (int i = 0; i < 3; i++) cudaFree(h->d_src[i]);
     cudaFree(h->d_counter);
+    cudaFree(h->d_gws);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -551,9 +565,9 @@ int plb_initial_guess(plb_handle h, int B, const double* soc, const double* thet
         stage_inout(b3, Y0, hostY, (size_t)B * m.N_tot, mem, false, s)) return -1;
     AuxArgs a;
     memset(&a, 0, sizeof a);
-    a.m = m; a.B = B; a.theta = theta; a.soc = soc; a.Y = Y0;
-    const size_t smem = sizeof(WarpWS) * SIM_WARPS;
-    const int grid = std::min((B + SIM_WARPS - 1) / SIM_WARPS, h->num_sms * 4);
+    a.m = m; a.B = B; a.theta = theta; a.soc = soc; a.Y = Y0; a.gws = h->d_gws;
+    const size_t smem = sizeof(WarpSmem) * SIM_WARPS;
+    const int grid = std::min((B + SIM_WARPS - 1) / SIM_WARPS, h->sim_grid);
     if (m.chem == CHEM_LCO) {
         CUDA_OK(cudaFuncSetAttribute(k_initguess<CHEM_LCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_initguess<CHEM_LCO><<<grid, SIM_WARPS * 32, smem, s>>>(a);
@@ -621,9 +635,9 @@ int plb_newton_init(plb_handle h, int B, double* Y, double* YP, const double* th
     AuxArgs a;
     memset(&a, 0, sizeof a);
     a.m = m; a.B = B; a.theta = theta; a.values = values; a.method = run->method; a.value = run->value;
-    a.o = to_opts(opts); a.Y = Y; a.YP = YP; a.status = status;
-    const size_t smem = sizeof(WarpWS) * SIM_WARPS;
-    const int grid = std::min((B + SIM_WARPS - 1) / SIM_WARPS, h->num_sms);
+    a.o = to_opts(opts); a.Y = Y; a.YP = YP; a.status = status; a.gws = h->d_gws;
+    const size_t smem = sizeof(WarpSmem) * SIM_WARPS;
+    const int grid = std::min((B + SIM_WARPS - 1) / SIM_WARPS, h->sim_grid);
     if (m.chem == CHEM_LCO) {
         CUDA_OK(cudaFuncSetAttribute(k_newton<CHEM_LCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_newton<CHEM_LCO><<<grid, SIM_WARPS * 32, smem, s>>>(a);
@@ -677,9 +691,10 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
     a.n_save_max = n_save_max > 0 ? n_save_max : 0;
     a.tr_t = tr_t; a.tr_V = tr_V; a.tr_I = tr_I; a.tr_SOC = tr_SOC; a.tr_n = tr_n;
     a.counter = h->d_counter;
+    a.gws = h->d_gws;
     CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
-    const size_t smem = sizeof(WarpWS) * SIM_WARPS;
-    const int grid = std::min((B + SIM_WARPS - 1) / SIM_WARPS, h->num_sms);
+    const size_t smem = sizeof(WarpSmem) * SIM_WARPS;
+    const int grid = std::min((B + SIM_WARPS - 1) / SIM_WARPS, h->sim_grid);
     CUDA_OK(cudaEventRecord(h->ev0, s));
     if (m.chem == CHEM_LCO) {
         CUDA_OK(cudaFuncSetAttribute(k_simulate<CHEM_LCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

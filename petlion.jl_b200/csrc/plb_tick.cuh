@@ -1,0 +1,627 @@
+// plb_tick.cuh -- the fused integrator as a CTA-synchronous "tick" machine.
+//
+// Why: the per-system program (residual ~1.4k, factorisation ~1.7k, solve ~1.2k SASS instructions of
+// straight-line FP64 code) does not fit the SM instruction cache.  With every warp at a different
+// point of it, ncu showed sm__icc_request_hit_rate ~50 % and the GPC-level instruction cache at 70 % of
+// peak: the kernel was instruction-fetch bound and adding warps made it slower.  Here every warp of
+// a CTA still owns one system end to end, but all warps execute the three heavy phases in lockstep
+// (one residual evaluation per warp per tick), so a single instruction stream per SM serves all of
+// its systems.  The light per-state glue (predictor, error test, stop checks, ...) runs between the
+// barriers, unaligned.
+//
+// One tick per warp = exactly one evaluation of F (optionally with the Jacobian + factorisation)
+// followed by one linear solve.  The nested loops of the reference
+//   solve! -> IDASolve(ONE_STEP) -> IDAStep retry loop -> IDANls lsetup retry -> Newton iteration
+// (model_evaluation.jl:312-333 and SUNDIALS IDA) and of newtons_method! (model_evaluation.jl:430-480)
+// are flattened into the states below; decision logic is unchanged from plb_integrator.cuh.
+#pragma once
+#include "plb_integrator.cuh"
+
+namespace plb {
+
+enum TickState { ST_FETCH = 0, ST_INIT_ITER, ST_INIT_RDIFF, ST_INIT_DT, ST_NLS, ST_EXHAUSTED };
+enum Pending { PEND_NONE = 0, PEND_RETURNED, PEND_BEGIN, PEND_FINISH };
+
+struct SimState {
+    int state, sys, pending;
+    RunCtl rc;
+    Ida M;
+    double SOC, t0, t, tprev, tg_prev, I_prev;
+    PrevVals pv;
+    int flag, iter, hard, nsave, kord, retried;
+    double tstop0, tstop1;
+    int ntstops, itstop;
+    int ni_iter, n_newton_init;
+    // nonlinear solve (IDANls / Newton iteration)
+    int callLSetup, jcur, mi;
+    double oldnrm;
+    // step attempt (IDAStep)
+    double saved_t, ck, err_k, err_km1;
+    int ncf, nef;
+    // last solver return
+    int ret_fl;
+    double ret_t;
+    double dt_init;
+};
+
+// ---- pieces of ida_nls -------------------------------------------------------------------------------
+__device__ __forceinline__ void nls_begin(const ModelDesc& m, WarpWS& w, SimState& S, int lane) {
+    Ida& M = S.M;
+    const IdaCoef& K = w.K;
+    S.callLSetup = 0;
+    if (M.nst == 0) { M.cjold = M.cj; M.ss = 20.0; S.callLSetup = 1; }
+#pragma unroll 1
+    for (int i = lane; i < m.N_tot; i += 32) {
+        double yv = 0.0, ypv = 0.0;
+#pragma unroll 1
+        for (int j = 0; j <= M.kk; j++) {
+            const double p = w.v(V_PHI0 + j)[i];
+            yv += p;
+            if (j > 0) ypv = fma(K.gamma[j], p, ypv);
+        }
+        w.v(V_YPRED)[i] = yv; w.v(V_YPPRED)[i] = ypv; w.v(V_EE)[i] = 0.0;
+    }
+    __syncwarp();
+    M.cjratio = M.cj / M.cjold;
+    const double temp1 = (1.0 - 0.25) / (1.0 + 0.25), temp2 = 1.0 / temp1;
+    if (M.cjratio < temp1 || M.cjratio > temp2) S.callLSetup = 1;
+    if (M.cj != M.cjlast) M.ss = 100.0;
+    S.jcur = 0; S.mi = 0; S.oldnrm = 0.0;
+}
+
+// after the solve of one Newton iteration: returns -99 continue, 0 converged, >0 recoverable failure
+__device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const LaneRole& ro, const Opts& o,
+                                        SimState& S, LaneVec& d, double dI, int lane) {
+    Ida& M = S.M;
+    if (M.cjratio != 1.0) {
+        const double sc = 2.0 / (1.0 + M.cjratio);
+        d.ce *= sc; d.j *= sc; d.pe *= sc; d.ps *= sc; dI *= sc;
+#pragma unroll
+        for (int r = 0; r < NR; r++) d.cs[r] *= sc;
+    }
+    LaneVec ee, ewt;
+    double eeI, ewtI;
+    load_lane(m, ro, w.v(V_EE), ee, eeI);
+    load_lane(m, ro, w.v(V_EWT), ewt, ewtI);
+    double s = 0.0;
+    if (ro.act) {
+        ee.ce += d.ce; ee.pe += d.pe;
+        s = fma(d.ce * ewt.ce, d.ce * ewt.ce, s);
+        s = fma(d.pe * ewt.pe, d.pe * ewt.pe, s);
+    }
+    if (ro.elec) {
+        ee.j += d.j; ee.ps += d.ps;
+        s = fma(d.j * ewt.j, d.j * ewt.j, s);
+        s = fma(d.ps * ewt.ps, d.ps * ewt.ps, s);
+#pragma unroll
+        for (int r = 0; r < NR; r++) { ee.cs[r] += d.cs[r]; s = fma(d.cs[r] * ewt.cs[r], d.cs[r] * ewt.cs[r], s); }
+    }
+    eeI += dI;
+    store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
+    __syncwarp();
+    const double delnrm = sqrt((warp_sum(s) + (dI * ewtI) * (dI * ewtI)) / m.N_tot);
+    int retval = -99;
+    if (S.mi == 0) {
+        S.oldnrm = delnrm;
+        if (delnrm <= 1e-4 * (1e-4 * 0.33)) retval = 0;
+    } else {
+        const double rate = pow(delnrm / S.oldnrm, 1.0 / S.mi);
+        if (rate > 0.9) retval = 2;
+        else M.ss = rate / (1.0 - rate);
+    }
+    if (retval == -99 && M.ss * delnrm <= 0.33) retval = 0;
+    if (retval == -99) {
+        S.mi++;
+        if (S.mi >= o.maxcor) retval = 2;
+    }
+    return retval;
+}
+
+// start one attempt of IDAStep: coefficients, predictor, lsetup decision
+__device__ __forceinline__ void attempt_begin(const ModelDesc& m, WarpWS& w, SimState& S, int lane) {
+    S.ck = ida_set_coeffs(m, w, S.M, lane);
+    nls_begin(m, w, S, lane);
+    S.state = ST_NLS;
+}
+
+// IDASolve(ONE_STEP) up to the first residual evaluation.  Returns true if an evaluation is needed
+// (state = ST_NLS), false if the call returned (S.ret_fl / S.ret_t set).
+__device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const Opts& o, SimState& S, int lane) {
+    Ida& M = S.M;
+    const double ur = DBL_EPSILON;
+    const double tout = S.itstop == 0 ? S.tstop0 : S.tstop1;
+    M.tstop = tout; M.tstopset = 1;
+    if (M.nst == 0) {
+        ewt_set(m, w, o, lane);
+        const double tdist = fabs(tout - M.tn);
+        M.hh = M.hin;
+        if (M.hh == 0.0) {
+            M.hh = 0.001 * tdist;
+            const double ypnorm = wrms(m, w.v(V_PHI1), w.v(V_EWT), lane);
+            if (ypnorm > 0.5 / M.hh) M.hh = 0.5 / ypnorm;
+            if (tout < M.tn) M.hh = -M.hh;
+        }
+        if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
+        M.kk = 0; M.kused = 0;
+#pragma unroll 1
+        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.hh;
+        __syncwarp();
+    } else {
+        const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
+        if (fabs(M.tn - M.tstop) <= troundoff) {
+            S.ret_t = M.tretlast = M.tstop; M.tstopset = 0; S.ret_fl = 1;
+            return false;
+        }
+        if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
+        ewt_set(m, w, o, lane);
+    }
+    {
+        const double nrm = wrms(m, w.v(V_PHI0), w.v(V_EWT), lane);
+        if (ur * nrm > 1.0) { S.ret_t = M.tn; S.ret_fl = FAIL_CONV; return false; }
+    }
+    // IDAStep prologue
+    S.saved_t = M.tn; S.ncf = 0; S.nef = 0; S.err_k = 0.0; S.err_km1 = 0.0;
+    if (M.nst == 0) {
+        M.kk = 1; M.kused = 0; M.hused = 0.0; M.cj = 1.0 / M.hh; M.phase = 0; M.ns = 0;
+        __syncwarp();
+        if (lane == 0) w.K.psi[0] = M.hh;
+        __syncwarp();
+    }
+    attempt_begin(m, w, S, lane);
+    return true;
+}
+
+// IDAStopTest2 after a successful step
+__device__ __forceinline__ void solve_end(SimState& S) {
+    Ida& M = S.M;
+    const double ur = DBL_EPSILON;
+    if (M.tstopset) {
+        const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
+        if (fabs(M.tn - M.tstop) <= troundoff) {
+            S.ret_t = M.tretlast = M.tstop; M.tstopset = 0; S.ret_fl = 1;
+            return;
+        }
+        if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
+    }
+    S.ret_t = M.tretlast = M.tn; S.ret_fl = 0;
+}
+
+// The Newton loop of one attempt ended with `retval` (0 ok, >0 recoverable failure): error test,
+// step completion or retry bookkeeping (IDAStep / IDAHandleNFlag).  Sets S.pending.
+__device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const Opts& o, SimState& S, int retval, int lane) {
+    Ida& M = S.M;
+    bool errfail = false;
+    if (retval == 0) errfail = ida_test_error(m, w, M, S.ck, S.err_k, S.err_km1, lane);
+    if (retval == 0 && !errfail) {
+        ida_complete_step(m, w, o, M, S.err_k, S.err_km1, lane);
+        solve_end(S);
+        S.pending = PEND_RETURNED;
+        return;
+    }
+    ida_restore(m, w, M, S.saved_t, lane);
+    M.phase = 1;
+    int fail = 0;
+    if (retval != 0) {
+        M.ncfn++; S.ncf++;
+        M.rr = 0.25;
+        M.hh *= M.rr;
+        if (S.ncf >= o.maxncf) fail = FAIL_CONV;
+    } else {
+        S.nef++; M.netf++;
+        if (S.nef == 1) {
+            const double err_knew = (M.kk == M.knew) ? S.err_k : S.err_km1;
+            M.kk = M.knew;
+            M.rr = 0.9 * pow(2.0 * err_knew + 1e-4, -1.0 / (M.kk + 1));
+            M.rr = fmax(0.25, fmin(0.9, M.rr));
+            M.hh *= M.rr;
+        } else if (S.nef == 2) {
+            M.kk = M.knew; M.rr = 0.25; M.hh *= M.rr;
+        } else if (S.nef < o.maxnef) {
+            M.kk = 1; M.rr = 0.25; M.hh *= M.rr;
+        } else fail = FAIL_ERRTEST;
+    }
+    if (!fail) {
+        if (M.nst == 0) {
+            __syncwarp();
+            if (lane == 0) w.K.psi[0] = M.hh;
+#pragma unroll 1
+            for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.rr;
+            __syncwarp();
+        }
+        if (!(fabs(M.hh) > 0.0) || isinf(M.hh)) fail = FAIL_CONV;
+    }
+    if (fail) {
+        S.ret_t = M.tretlast = M.tn; S.ret_fl = fail;
+        S.pending = PEND_RETURNED;
+        return;
+    }
+    attempt_begin(m, w, S, lane);   // PREDICT_AGAIN
+}
+
+// one turn of solve! after step!(int) returned (model_evaluation.jl:320-328, checks.jl:226-249)
+// returns true to continue stepping
+__device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+    const ModelDesc& m = a.m;
+    Ida& M = S.M;
+    const int N = m.N_tot;
+    const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
+    const double tcur_stop = S.itstop == 0 ? S.tstop0 : S.tstop1;
+    if (S.ret_fl == 1 || S.ret_t >= tcur_stop) { if (S.itstop < S.ntstops - 1) S.itstop++; }
+    S.t = S.ret_t;
+    S.iter++;
+    if (S.ret_fl < 0 || S.t == S.tprev) {
+        if (S.t == 0.0 && S.iter == 2 && !S.retried && M.nst == 0) {
+            S.retried = 1;
+            const double sc = 1.0 / w.K.psi[0];
+#pragma unroll 1
+            for (int i = lane; i < N; i += 32) w.v(V_PHI1)[i] *= sc;
+            __syncwarp();
+            M.hin = a.o.reltol;
+            return true;
+        }
+        S.hard = (S.ret_fl == FAIL_ERRTEST) ? FAIL_ERRTEST : FAIL_CONV;
+        return false;
+    }
+    __syncwarp();
+    if (lane == 0) S.kord = getsol_weights(M, w.K, S.t, w.K.cvals, w.K.dvals);
+    S.kord = __shfl_sync(FULL, S.kord, 0);
+    __syncwarp();
+    const double Ic = interp_y(w, w.K.cvals, S.kord, m.off_I);
+    const double Vc = interp_y(w, w.K.cvals, S.kord, iP0) - interp_y(w, w.K.cvals, S.kord, iPN);
+    const double tg = S.t + S.t0;
+    S.SOC = S.SOC + 0.5 * (tg - S.tg_prev) * (Ic + S.I_prev) / 3600.0;
+    const size_t so = (size_t)S.sys * a.n_save_max;
+    if (lane == 0 && S.nsave < a.n_save_max) {
+        if (a.tr_t) a.tr_t[so + S.nsave] = tg;
+        if (a.tr_V) a.tr_V[so + S.nsave] = Vc;
+        if (a.tr_I) a.tr_I[so + S.nsave] = Ic;
+        if (a.tr_SOC) a.tr_SOC[so + S.nsave] = S.SOC;
+    }
+    S.nsave++;
+    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, lane);
+    if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return false; }
+    if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { S.hard = FAIL_NONFINITE; return false; }
+    if (S.flag != -1) return false;
+    S.I_prev = Ic;
+    S.tg_prev = tg;
+    S.tprev = S.t;
+    return true;
+}
+
+// exit_simulation! (model_evaluation.jl:335-382) + summary / state hand-back
+__device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S, bool integrated, int lane) {
+    const ModelDesc& m = a.m;
+    const Ida& M = S.M;
+    const int N = m.N_tot;
+    const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
+    Summary out;
+    out.reserved = 0;
+    double t_end = S.t + S.t0, SOC_end = S.SOC, V_end = 0.0, I_end = 0.0;
+    const size_t so = (size_t)S.sys * a.n_save_max;
+    if (integrated) {
+        double fr = 1.0;
+        bool do_interp = false;
+        if (S.hard) S.flag = S.hard;
+        else if (a.o.interp_final && S.flag != 0 && S.flag != -1 && S.t > 1.0) { do_interp = true; fr = S.pv.frac; }
+        __syncwarp();
+        if (lane == 0) {
+            if (S.nsave <= 1) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = M.nst == 0 ? 1.0 : 1.0 / w.K.psi[0]; }
+            if (do_interp) { double dp[6]; getsol_weights(M, w.K, S.tprev, w.K.cprev, dp); }
+        }
+        __syncwarp();
+        double ps0 = 0.0, psN = 0.0, If = 0.0;
+#pragma unroll 1
+        for (int i = lane; i < N; i += 32) {
+            const double yn = interp_y(w, w.K.cvals, S.kord, i);
+            double yf = yn;
+            if (do_interp) { const double ypv = interp_y(w, w.K.cprev, S.kord, i); yf = fr * (yn - ypv) + ypv; }
+            a.sY[(size_t)S.sys * N + ref_index(m, i)] = yf;
+            if (a.sYP) a.sYP[(size_t)S.sys * N + ref_index(m, i)] = interp_yp(w, w.K.dvals, S.kord, i);
+            if (i == iP0) ps0 = yf;
+            if (i == iPN) psN = yf;
+            if (i == m.off_I) If = yf;
+        }
+        ps0 = warp_sum(ps0); psN = warp_sum(psN); If = warp_sum(If);
+        V_end = ps0 - psN; I_end = If;
+        if (do_interp) {
+            const double ti = fr * (S.t - S.tprev) + S.tprev;
+            const double tgi = ti + S.t0, tgl = S.t + S.t0;
+            SOC_end = S.SOC + 0.5 * (tgi - tgl) * (If + If) / 3600.0;
+            t_end = tgi;
+            if (lane == 0 && S.nsave - 1 < a.n_save_max && S.nsave >= 1) {
+                if (a.tr_t) a.tr_t[so + S.nsave - 1] = tgi;
+                if (a.tr_V) a.tr_V[so + S.nsave - 1] = V_end;
+                if (a.tr_I) a.tr_I[so + S.nsave - 1] = I_end;
+                if (a.tr_SOC) a.tr_SOC[so + S.nsave - 1] = SOC_end;
+            }
+        }
+    } else {
+        // failed before integration: hand the (initial) state back
+#pragma unroll 1
+        for (int i = lane; i < N; i += 32) {
+            a.sY[(size_t)S.sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
+            if (a.sYP) a.sYP[(size_t)S.sys * N + ref_index(m, i)] = 0.0;
+        }
+        S.nsave = 1;
+        t_end = S.t0;
+    }
+    out.t_end = t_end; out.V_end = V_end; out.I_end = I_end; out.SOC_end = SOC_end;
+    out.flag = S.flag; out.n_steps = S.nsave - 1;
+    out.n_res = M.nre; out.n_jac = M.nje; out.n_netf = M.netf; out.n_ncfn = M.ncfn;
+    out.n_newton_init = S.n_newton_init;
+    if (lane == 0) {
+        a.out[S.sys] = out;
+        a.sSOC[S.sys] = SOC_end;
+        a.st[S.sys] = t_end;
+        if (a.tr_n) a.tr_n[S.sys] = S.nsave < a.n_save_max ? S.nsave : a.n_save_max;
+    }
+    __syncwarp();
+    S.state = ST_FETCH;
+}
+
+// initialize_simulation! up to the first Newton-init evaluation (model_evaluation.jl:174-214)
+template <int CHEM>
+__device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, const LaneRole& ro, SimState& S, int lane) {
+    const ModelDesc& m = a.m;
+    int sys = 0;
+    if (lane == 0) sys = atomicAdd(a.counter, 1);
+    sys = __shfl_sync(FULL, sys, 0);
+    if (sys >= a.B) { S.state = ST_EXHAUSTED; return; }
+    S.sys = sys;
+    const int N = m.N_tot;
+    setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
+    S.rc.method = a.method;
+    S.rc.value = a.values ? a.values[sys] : a.value;
+    double* Y0 = w.v(V_PHI0);
+    const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
+    if (a.new_run) {
+        S.SOC = a.soc0 ? a.soc0[sys] : 1.0;
+        const double* th = w.C.theta;
+        const double csp = th[TF_c_max_p] * (S.SOC * (th[TF_theta_max_p] - th[TF_theta_min_p]) + th[TF_theta_min_p]);
+        const double csn = th[TF_c_max_n] * (S.SOC * (th[TF_theta_max_n] - th[TF_theta_min_n]) + th[TF_theta_min_n]);
+        LaneVec y0;
+        y0.ce = th[TF_c_e0]; y0.j = 0.0; y0.pe = 0.0; y0.ps = 0.0;
+        const double cs0 = ro.sec == 0 ? csp : csn;
+#pragma unroll
+        for (int r = 0; r < NR; r++) y0.cs[r] = cs0;
+        if (ro.elec) {
+            const double thx = cs0 * w.C.sec[SC_inv_cmax][ro.sec];
+            double U, dU, dUdT = 0.0, ddUdT = 0.0;
+            if (CHEM == CHEM_LCO) {
+                if (ro.sec == 0) laws::OCV_LCO(thx, U, dU, dUdT, ddUdT);
+                else laws::OCV_LiC6(thx, sqrt(fmax(thx, 1e-4)), U, dU, dUdT, ddUdT);
+                if (w.C.g[GC_dUdT_on] != 0.0) U += dUdT * (w.C.g[GC_T] - kTref);
+            } else {
+                if (ro.sec == 0) laws::OCV_NMC(thx, U, dU);
+                else laws::OCV_LiC6_NMC(thx, U, dU);
+            }
+            y0.ps = U;
+        }
+        store_lane(m, ro, Y0, y0, 0.0, lane);
+        S.t0 = 0.0;
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < N; i += 32) Y0[i] = a.sY[(size_t)sys * N + ref_index(m, i)];
+        S.SOC = a.sSOC[sys];
+        S.t0 = ::nextafter(a.st[sys], DBL_MAX);   // initial_time, model_evaluation.jl:112
+    }
+    __syncwarp();
+    const double I_prev_state = Y0[m.off_I];
+    // initial_current! (input_methods.jl:11-107)
+    {
+        double Ig;
+        const double V0 = Y0[iP0] - Y0[iPN];
+        if (a.input_kind == 1) {
+            if (S.rc.method == METHOD_I) { S.rc.value = I_prev_state; Ig = I_prev_state; }
+            else if (S.rc.method == METHOD_V) { S.rc.value = V0; Ig = V0; }   // sic: input_methods.jl:58
+            else { S.rc.value = I_prev_state * w.C.g[GC_I1C] * V0; Ig = I_prev_state; }
+        } else if (a.input_kind == 2) {
+            S.rc.value = 0.0; Ig = 0.0;
+        } else if (S.rc.method == METHOD_I) Ig = S.rc.value;
+        else if (S.rc.method == METHOD_V) {
+            if (!a.new_run && I_prev_state != 0.0) Ig = I_prev_state;
+            else Ig = S.rc.value > V0 ? 1.0 : -1.0;
+        } else Ig = S.rc.value / (V0 * w.C.g[GC_I1C]);
+        __syncwarp();
+        if (lane == 0) Y0[m.off_I] = Ig;
+        __syncwarp();
+    }
+    Ida& M = S.M;
+    M.tn = 0.0; M.hh = 0.0; M.hused = 0.0; M.cj = 0.0; M.cjlast = 0.0; M.cjold = 0.0; M.cjratio = 1.0;
+    M.ss = 20.0; M.rr = 0.0; M.hin = 0.0; M.tstop = 0.0; M.tretlast = 0.0;
+    M.kk = 0; M.kused = 0; M.knew = 0; M.phase = 0; M.ns = 0; M.nst = 0; M.tstopset = 0;
+    M.nre = 0; M.nje = 0; M.netf = 0; M.ncfn = 0;
+    S.t = 0.0; S.tprev = 0.0; S.flag = -1; S.iter = 1; S.hard = 0; S.nsave = 0; S.kord = 1; S.retried = 0;
+    S.ni_iter = 0; S.n_newton_init = 0; S.pending = PEND_NONE;
+    S.state = ST_INIT_ITER;
+}
+
+// after newtons_method!: rest of initialize_simulation! (model_evaluation.jl:216-231)
+__device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+    const ModelDesc& m = a.m;
+    const int N = m.N_tot;
+    const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
+    const double* Y0 = w.v(V_PHI0);
+    if (a.new_run) {   // check_initial_SOC, checks.jl:327-339
+        const double I0 = Y0[m.off_I];
+        if (I0 != 0 && ((S.SOC >= a.b.SOC_max && I0 > 0) || (S.SOC <= a.b.SOC_min && I0 < 0))) {
+            S.flag = FAIL_INIT_BOUNDS;
+            finish(a, w, S, false, lane);
+            return;
+        }
+    }
+    for (int k = 2; k < 6; k++) {
+#pragma unroll 1
+        for (int i = lane; i < N; i += 32) w.v(V_PHI0 + k)[i] = 0.0;
+    }
+    __syncwarp();
+    S.ntstops = 0; S.itstop = 0;
+    if (!a.new_run && 1.0 < a.tf) { S.tstop0 = 1.0; S.tstop1 = a.tf; S.ntstops = 2; }
+    else { S.tstop0 = a.tf; S.tstop1 = a.tf; S.ntstops = 1; }
+    __syncwarp();
+    if (lane == 0) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = 1.0; }   // y = phi0, yp = phi1 = YP0
+    __syncwarp();
+    const double Vc = Y0[iP0] - Y0[iPN], Ic = Y0[m.off_I];
+    S.I_prev = Ic;
+    const size_t so = (size_t)S.sys * a.n_save_max;
+    if (lane == 0 && S.nsave < a.n_save_max) {
+        if (a.tr_t) a.tr_t[so + S.nsave] = S.t0;
+        if (a.tr_V) a.tr_V[so + S.nsave] = Vc;
+        if (a.tr_I) a.tr_I[so + S.nsave] = Ic;
+        if (a.tr_SOC) a.tr_SOC[so + S.nsave] = S.SOC;
+    }
+    S.nsave++;
+    S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
+    S.kord = 1;
+    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, lane);
+    S.tg_prev = S.t0;
+    S.pending = (S.flag == -1) ? PEND_BEGIN : PEND_FINISH;
+}
+
+template <int CHEM>
+__device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* smem_raw) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpWS w = make_ws(smem_raw, a.gws, warp);
+    const ModelDesc& m = a.m;
+    const LaneRole ro = make_role(m, lane);
+    SimState S;
+    S.state = ST_FETCH; S.pending = PEND_NONE; S.sys = 0;
+    for (;;) {
+        // ------------------------------ PRE: get to an evaluation point ---------------------------------
+        if (S.state == ST_FETCH) fetch_and_setup<CHEM>(a, w, ro, S, lane);
+        LaneVec y, yp, res;
+        double Iy = 0.0;
+        bool do_eval = S.state != ST_EXHAUSTED, need_jac = false, alg_only = false, do_solve = false;
+        yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0;
+#pragma unroll
+        for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
+        if (do_eval) {
+            if (S.state == ST_NLS) {
+                LaneVec e, p;
+                double eI, pI;
+                load_lane(m, ro, w.v(V_YPRED), y, Iy);
+                load_lane(m, ro, w.v(V_EE), e, eI);
+                load_lane(m, ro, w.v(V_YPPRED), p, pI);
+                const double cj = S.M.cj;
+                y.ce += e.ce; y.j += e.j; y.pe += e.pe; y.ps += e.ps; Iy += eI;
+                yp.ce = p.ce + cj * e.ce;
+#pragma unroll
+                for (int r = 0; r < NR; r++) { y.cs[r] += e.cs[r]; yp.cs[r] = p.cs[r] + cj * e.cs[r]; }
+                need_jac = S.callLSetup != 0; do_solve = true;
+            } else {
+                load_lane(m, ro, w.v(V_PHI0), y, Iy);
+                alg_only = true;
+                if (S.state == ST_INIT_ITER) { need_jac = true; do_solve = true; }
+                else if (S.state == ST_INIT_DT) {
+                    LaneVec p;
+                    double pI;
+                    load_lane(m, ro, w.v(V_PHI1), p, pI);
+                    y.ce += S.dt_init * p.ce;
+#pragma unroll
+                    for (int r = 0; r < NR; r++) y.cs[r] += S.dt_init * p.cs[r];
+                    do_solve = true;
+                }
+            }
+        }
+        // ------------------------------ aligned heavy phases --------------------------------------------
+        if (!__syncthreads_or(do_eval)) break;
+        const int any_jac = __syncthreads_or(do_eval && need_jac);
+        LaneJac J;
+        CtrlRow ctrl;
+        ctrl.res = 0.0; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0;
+        if (do_eval) {
+            // each warp picks the variant from its OWN state only, so a system's arithmetic (and therefore
+            // its bits) never depends on which other systems share the CTA
+            if (need_jac) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, S.rc.method, S.rc.value, res, ctrl, J);
+            else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, S.rc.method, S.rc.value, res, ctrl, J);
+            S.M.nre++;
+        }
+        bool lsetup_bad = false;
+        if (any_jac) {
+            __syncthreads();
+            if (do_eval && need_jac) {
+                warp_factor_impl(m, ro, J, ctrl, alg_only ? 0.0 : S.M.cj, alg_only, w.Fa, lane);
+                S.M.nje++;
+                const double chk = w.Fa.schur_inv;
+                lsetup_bad = !(chk == chk) || isinf(chk);
+            }
+        }
+        __syncthreads();
+        double dI = 0.0;
+        if (do_eval && do_solve && !lsetup_bad) {
+            double gI = ctrl.res;
+            if (S.state == ST_NLS) {   // Newton update of the BDF step: delta = -J^{-1} F
+                res.ce = -res.ce; res.j = -res.j; res.pe = -res.pe; res.ps = -res.ps; gI = -gI;
+#pragma unroll
+                for (int r = 0; r < NR; r++) res.cs[r] = -res.cs[r];
+            }
+            dI = warp_solve_impl(m, ro, w.Fa, alg_only, res, gI, lane);
+        }
+        // ------------------------------ POST: per-state glue --------------------------------------------
+        if (do_eval) {
+            if (S.state == ST_NLS) {
+                int retval;
+                if (lsetup_bad) retval = 1;
+                else {
+                    if (need_jac) { S.M.cjold = S.M.cj; S.M.cjratio = 1.0; S.M.ss = 20.0; S.jcur = 1; S.callLSetup = 0; }
+                    retval = nls_post(m, w, ro, a.o, S, res, dI, lane);
+                }
+                if (retval > 0 && !S.jcur && !lsetup_bad) {
+                    // recoverable failure with a stale Jacobian: redo once with a fresh one
+                    S.callLSetup = 1; S.mi = 0;
+#pragma unroll 1
+                    for (int i = lane; i < m.N_tot; i += 32) w.v(V_EE)[i] = 0.0;
+                    __syncwarp();
+                } else if (retval != -99) {
+                    after_nls(m, w, a.o, S, retval, lane);
+                }
+            } else if (S.state == ST_INIT_ITER) {
+                // Y_new .-= factor \ res ; absolute 2-norm of the update (model_evaluation.jl:451-454)
+                double s = 0.0;
+                if (ro.elec) { y.j -= res.j; y.ps -= res.ps; s += res.j * res.j + res.ps * res.ps; }
+                if (ro.act) { y.pe -= res.pe; s += res.pe * res.pe; }
+                Iy -= dI;
+                s = warp_sum(s) + dI * dI;
+                store_lane(m, ro, w.v(V_PHI0), y, Iy, lane);
+                __syncwarp();
+                S.ni_iter++;
+                const bool bad = lsetup_bad || !(s == s) || isinf(s);
+                if (bad || (S.ni_iter >= 100 && !(sqrt(s) < a.o.reltol_init))) {
+                    S.flag = FAIL_NEWTON_INIT; S.n_newton_init = FAIL_NEWTON_INIT;
+                    finish(a, w, S, false, lane);
+                } else if (sqrt(s) < a.o.reltol_init) {
+                    S.n_newton_init = S.ni_iter;
+                    S.state = ST_INIT_RDIFF;
+                }
+            } else if (S.state == ST_INIT_RDIFF) {
+                // R_diff(YP,t,Y,YP): YP_diff = rhs (model_evaluation.jl:460); algebraic part still zero
+                LaneVec ypo;
+                ypo.ce = res.ce; ypo.j = 0.0; ypo.pe = 0.0; ypo.ps = 0.0;
+#pragma unroll
+                for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
+                store_lane(m, ro, w.v(V_PHI1), ypo, 0.0, lane);
+                __syncwarp();
+                const double c0 = fabs(w.C.theta[TF_c_e0]);
+                const double epsv = ::nextafter(c0, DBL_MAX) - c0;
+                S.dt_init = fmax(10.0 * a.o.reltol_init, sqrt(epsv));   // :464
+                S.state = ST_INIT_DT;
+            } else {   // ST_INIT_DT: YP_alg = -(factor \ R_alg(Y + dt YP)) / dt  (:466-476)
+                LaneVec ypo;
+                double pI;
+                load_lane(m, ro, w.v(V_PHI1), ypo, pI);
+                ypo.j = -res.j / S.dt_init; ypo.pe = -res.pe / S.dt_init; ypo.ps = -res.ps / S.dt_init;
+                store_lane(m, ro, w.v(V_PHI1), ypo, -dI / S.dt_init, lane);
+                __syncwarp();
+                begin_integration(a, w, S, lane);
+            }
+            // between evaluations: host loop of solve! until the next evaluation is needed
+            while (S.pending != PEND_NONE) {
+                if (S.pending == PEND_RETURNED) S.pending = host_after_return(a, w, S, lane) ? PEND_BEGIN : PEND_FINISH;
+                if (S.pending == PEND_BEGIN) S.pending = solve_begin(m, w, a.o, S, lane) ? PEND_NONE : PEND_RETURNED;
+                if (S.pending == PEND_FINISH) { finish(a, w, S, true, lane); S.pending = PEND_NONE; }
+            }
+        }
+    }
+}
+
+}  // namespace plb
