@@ -294,11 +294,17 @@ def main():
             ref = O.simulate_batch(O.make_model("LCO"), tho[:sample], O.make_run("I", -1.0), O.default_opts(),
                                    O.default_bounds("LCO"), SOC0=1.0, nthreads=cores)
             dt = time.perf_counter() - t0
-            same = float(np.mean(ref["n_steps"] == summ["n_steps"][:sample]))
-            dv = float(np.max(np.abs(ref["V_end"] - summ["V_end"][:sample]) / np.abs(ref["V_end"])))
+            gs = summ[:sample]
+            same_mask = (ref["n_steps"] == gs["n_steps"]) & (ref["flag"] == gs["flag"])
+            good = same_mask & (ref["flag"] >= 0)
+            dv = float(np.max(np.abs(ref["V_end"][good] - gs["V_end"][good]) / np.abs(ref["V_end"][good])))
+            dtt = float(np.max(np.abs(ref["t_end"][good] - gs["t_end"][good]) / np.abs(ref["t_end"][good])))
             cpu_baseline = {"value": sample / dt, "unit": "sims/s", "cores": cores, "kind": "port",
                             "sample": f"first {sample} systems of the same batch, {cores} threads, {dt:.1f} s wall",
-                            "parity_identical_step_counts": same, "parity_max_rel_dV_end": dv}
+                            "parity": {"identical_step_count_and_flag": float(np.mean(same_mask)),
+                                       "max_rel_dV_end_on_identical": dv, "max_rel_dt_end_on_identical": dtt,
+                                       "hard_failures_cpu": int(np.sum(ref["flag"] < 0)),
+                                       "hard_failures_gpu": int(np.sum(gs["flag"] < 0))}}
 
     if rank == 0:
         ok = summ["flag"] >= 0
