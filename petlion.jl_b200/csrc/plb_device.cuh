@@ -454,6 +454,7 @@ __device__ __forceinline__ LaneChain make_chain(int Nx, int lane) {
 __device__ __forceinline__ void thomas_sweeps(int Nx, const LaneChain& ch, const double* Wm, const double* Pm,
                                               const double* Di, const double* r, double* u) {
     double y0 = r[0], y1 = r[1], y2 = r[2];
+#pragma unroll 1
     for (int it = 0; it < ch.n_in; it++) {
         const double a0 = shfl_from(y0, ch.pred), a1 = shfl_from(y1, ch.pred), a2 = shfl_from(y2, ch.pred);
         y0 = r[0] - (Wm[0] * a0 + Wm[1] * a1 + Wm[2] * a2);
@@ -478,6 +479,7 @@ __device__ __forceinline__ void thomas_sweeps(int Nx, const LaneChain& ch, const
     const double p0 = ch.is_mid ? 0.0 : Pm[0], p1 = ch.is_mid ? 0.0 : Pm[1], p2 = ch.is_mid ? 0.0 : Pm[2];
     const double p3 = ch.is_mid ? 0.0 : Pm[3], p4 = ch.is_mid ? 0.0 : Pm[4], p5 = ch.is_mid ? 0.0 : Pm[5];
     const double p6 = ch.is_mid ? 0.0 : Pm[6], p7 = ch.is_mid ? 0.0 : Pm[7], p8 = ch.is_mid ? 0.0 : Pm[8];
+#pragma unroll 1
     for (int it = 0; it < ch.n_out; it++) {
         const double a0 = shfl_from(u0, ch.succ), a1 = shfl_from(u1, ch.succ), a2 = shfl_from(u2, ch.succ);
         u0 = c0 - (p0 * a0 + p1 * a1 + p2 * a2);
@@ -502,6 +504,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
             Fa.Sinv[k][el] = kap * laws::MC[r][c] - (r == c ? cj : 0.0);
         }
         __syncwarp();
+#pragma unroll 1
         for (int p = 0; p < NR; p++) {
             const double piv = 1.0 / Fa.Sinv[p * NR + p][el];
             __syncwarp();
@@ -571,6 +574,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     inv3x3(Dm, Di);
 #pragma unroll
     for (int k = 0; k < 9; k++) Wm[k] = 0.0;
+#pragma unroll 1
     for (int it = 0; it < ch.n_in + 1; it++) {
         double G[9];
 #pragma unroll

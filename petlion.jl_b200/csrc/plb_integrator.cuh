@@ -187,9 +187,23 @@ struct Ida {
     int nre, nje, netf, ncfn;
 };
 
+// ------------------------------------------------------------------------------------------------
+// vector passes over the N_tot components: element i = lane + 32*k, k < NEL, fully unrolled so the
+// NEL independent chains overlap (these passes sit on the latency-critical path between two
+// residual evaluations).  Summation order per lane (k ascending, then the xor-tree) is fixed.
+// ------------------------------------------------------------------------------------------------
+constexpr int NEL = (VS + 31) / 32;
+#ifndef PLB_ELEM_UNROLL
+#define PLB_ELEM_UNROLL 1
+#endif
+#define PLB_STR_(x) #x
+#define PLB_STR(x) PLB_STR_(x)
+#define PLB_FOR_ELEMS(i, N) _Pragma(PLB_STR(unroll PLB_ELEM_UNROLL)) for (int i = lane; i < (N); i += 32)
+
 __device__ __forceinline__ void ewt_set(const ModelDesc& m, WarpWS& w, const Opts& o, int lane) {
-    for (int i = lane; i < m.N_tot; i += 32)
-        w.v(V_EWT)[i] = 1.0 / (o.reltol * fabs(w.v(V_PHI0)[i]) + o.abstol);
+    const double* p0 = w.v(V_PHI0);
+    double* ew = w.v(V_EWT);
+    PLB_FOR_ELEMS(i, m.N_tot) ew[i] = 1.0 / (o.reltol * fabs(p0[i]) + o.abstol);
     __syncwarp();
 }
 
@@ -199,6 +213,7 @@ __device__ __forceinline__ int getsol_weights(const Ida& M, const IdaCoef& K, do
     const double delt = t - M.tn;
     double cc = 1.0, dd = 0.0, gam = delt / K.psi[0];
     c[0] = cc;
+#pragma unroll 1
     for (int j = 1; j <= kord; j++) {
         dd = dd * gam + cc / K.psi[j - 1];
         cc = cc * gam;
@@ -208,6 +223,7 @@ __device__ __forceinline__ int getsol_weights(const Ida& M, const IdaCoef& K, do
     return kord;
 }
 
+// IDASetCoeffs, scalar part (the phi scaling is fused into predict_pass).  Returns ck.
 __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, Ida& M, int lane) {
     IdaCoef& K = w.K;
     if (M.hh != M.hused || M.kk != M.kused) M.ns = 0;
@@ -217,6 +233,7 @@ __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, 
         if (lane == 0) {
             K.beta[0] = 1.0; K.alpha[0] = 1.0; K.gamma[0] = 0.0; K.sigma[0] = 1.0;
             double temp1 = M.hh;
+#pragma unroll 1
             for (int i = 1; i <= M.kk; i++) {
                 const double temp2 = K.psi[i - 1];
                 K.psi[i - 1] = temp1;
@@ -231,141 +248,40 @@ __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, 
     }
     __syncwarp();
     double alphas = 0.0, alpha0 = 0.0;
+#pragma unroll 1
     for (int i = 0; i < M.kk; i++) { alphas -= 1.0 / (i + 1); alpha0 -= K.alpha[i]; }
     M.cjlast = M.cj;
     M.cj = -alphas / M.hh;
     double ck = fabs(K.alpha[M.kk] + alphas - alpha0);
     ck = fmax(ck, K.alpha[M.kk]);
-    for (int k = M.ns; k <= M.kk; k++) {
-        const double bk = K.beta[k];
-        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI0 + k)[i] *= bk;
-    }
     M.tn += M.hh;
-    __syncwarp();
     return ck;
 }
 
-// nonlinear solve: 0 ok, >0 recoverable failure
-template <int CHEM>
-__device__ __forceinline__ int ida_nls(const ModelDesc& m, WarpWS& w, const LaneRole& ro, const RunCtl& rc,
-                                       const Opts& o, Ida& M, int lane) {
+// phi_k *= beta_k (k = ns..kk: "phi-star"), predictor y = sum phi_j, y' = sum gamma_j phi_j, ee = 0
+__device__ __forceinline__ void predict_pass(const ModelDesc& m, WarpWS& w, const Ida& M, int lane) {
     const IdaCoef& K = w.K;
-    bool callLSetup = false;
-    if (M.nst == 0) { M.cjold = M.cj; M.ss = 20.0; callLSetup = true; }
-    // predictor
-    for (int i = lane; i < m.N_tot; i += 32) {
+    double be[6], ga[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { be[j] = K.beta[j]; ga[j] = K.gamma[j]; }
+    double* yp_ = w.v(V_YPRED);
+    double* ypp_ = w.v(V_YPPRED);
+    double* ee_ = w.v(V_EE);
+    PLB_FOR_ELEMS(i, m.N_tot) {
         double yv = 0.0, ypv = 0.0;
-        for (int j = 0; j <= M.kk; j++) yv += w.v(V_PHI0 + j)[i];
-        for (int j = 1; j <= M.kk; j++) ypv += K.gamma[j] * w.v(V_PHI0 + j)[i];
-        w.v(V_YPRED)[i] = yv; w.v(V_YPPRED)[i] = ypv; w.v(V_EE)[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            if (j <= M.kk) {
+                double* ph = w.v(V_PHI0 + j);
+                double p = ph[i];
+                if (j >= M.ns) { p *= be[j]; ph[i] = p; }
+                yv += p;
+                if (j > 0) ypv = fma(ga[j], p, ypv);
+            }
+        }
+        yp_[i] = yv; ypp_[i] = ypv; ee_[i] = 0.0;
     }
     __syncwarp();
-    M.cjratio = M.cj / M.cjold;
-    {
-        const double temp1 = (1.0 - 0.25) / (1.0 + 0.25), temp2 = 1.0 / temp1;
-        if (M.cjratio < temp1 || M.cjratio > temp2) callLSetup = true;
-        if (M.cj != M.cjlast) M.ss = 100.0;
-    }
-    LaneVec yp0, ypp0;     // predictor in registers (node mapping)
-    double Ip0, Ipp0;
-    load_lane(m, ro, w.v(V_YPRED), yp0, Ip0);
-    load_lane(m, ro, w.v(V_YPPRED), ypp0, Ipp0);
-    LaneVec ee;
-    double eeI = 0.0;
-    ee.ce = ee.j = ee.pe = ee.ps = 0.0;
-#pragma unroll
-    for (int r = 0; r < NR; r++) ee.cs[r] = 0.0;
-    bool jcur = false;
-    int retval = 0;
-    double oldnrm = 0.0;
-    LaneVec ewt;
-    double ewtI;
-    load_lane(m, ro, w.v(V_EWT), ewt, ewtI);
-    for (;;) {
-        LaneVec y, yp, res;
-        LaneJac J;
-        CtrlRow ctrl;
-        y.ce = yp0.ce + ee.ce; y.j = yp0.j + ee.j; y.pe = yp0.pe + ee.pe; y.ps = yp0.ps + ee.ps;
-        yp.ce = ypp0.ce + M.cj * ee.ce; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0;
-#pragma unroll
-        for (int r = 0; r < NR; r++) { y.cs[r] = yp0.cs[r] + ee.cs[r]; yp.cs[r] = ypp0.cs[r] + M.cj * ee.cs[r]; }
-        double Iy = Ip0 + eeI;
-        if (callLSetup) {
-            lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
-            M.nre++; M.nje++;
-            warp_factor(m, ro, J, ctrl, M.cj, false, w.Fa, lane);
-            // a non-finite factorisation is a recoverable lsetup failure
-            const double chk = w.Fa.schur_inv;
-            if (!(chk == chk) || isinf(chk)) { retval = 1; break; }
-            M.cjold = M.cj; M.cjratio = 1.0; M.ss = 20.0;
-            jcur = true;
-        } else {
-            lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
-            M.nre++;
-        }
-        int mi = 0;
-        for (;;) {
-            // delta = -J^{-1} F, scaled by 2/(1+cjratio) when the Jacobian is stale
-            res.ce = -res.ce; res.j = -res.j; res.pe = -res.pe; res.ps = -res.ps;
-#pragma unroll
-            for (int r = 0; r < NR; r++) res.cs[r] = -res.cs[r];
-            double dI = warp_solve(m, ro, w.Fa, false, res, -ctrl.res, lane);
-            if (M.cjratio != 1.0) {
-                const double sc = 2.0 / (1.0 + M.cjratio);
-                res.ce *= sc; res.j *= sc; res.pe *= sc; res.ps *= sc; dI *= sc;
-#pragma unroll
-                for (int r = 0; r < NR; r++) res.cs[r] *= sc;
-            }
-            double s = 0.0;
-            if (ro.act) {
-                ee.ce += res.ce; ee.pe += res.pe;
-                s = fma(res.ce * ewt.ce, res.ce * ewt.ce, s);
-                s = fma(res.pe * ewt.pe, res.pe * ewt.pe, s);
-            }
-            if (ro.elec) {
-                ee.j += res.j; ee.ps += res.ps;
-                s = fma(res.j * ewt.j, res.j * ewt.j, s);
-                s = fma(res.ps * ewt.ps, res.ps * ewt.ps, s);
-#pragma unroll
-                for (int r = 0; r < NR; r++) { ee.cs[r] += res.cs[r]; s = fma(res.cs[r] * ewt.cs[r], res.cs[r] * ewt.cs[r], s); }
-            }
-            eeI += dI;
-            const double delnrm = sqrt((warp_sum(s) + (dI * ewtI) * (dI * ewtI)) / m.N_tot);
-            // idaNlsConvTest
-            retval = -99;
-            if (mi == 0) {
-                oldnrm = delnrm;
-                if (delnrm <= 1e-4 * (1e-4 * 0.33)) retval = 0;
-            } else {
-                const double rate = pow(delnrm / oldnrm, 1.0 / mi);
-                if (rate > 0.9) retval = 2;
-                else M.ss = rate / (1.0 - rate);
-            }
-            if (retval == -99 && M.ss * delnrm <= 0.33) retval = 0;
-            if (retval >= 0) break;
-            mi++;
-            if (mi >= o.maxcor) { retval = 2; break; }
-            y.ce = yp0.ce + ee.ce; y.j = yp0.j + ee.j; y.pe = yp0.pe + ee.pe; y.ps = yp0.ps + ee.ps;
-            yp.ce = ypp0.ce + M.cj * ee.ce;
-#pragma unroll
-            for (int r = 0; r < NR; r++) { y.cs[r] = yp0.cs[r] + ee.cs[r]; yp.cs[r] = ypp0.cs[r] + M.cj * ee.cs[r]; }
-            Iy = Ip0 + eeI;
-            lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, rc.method, rc.value, res, ctrl, J);
-            M.nre++;
-        }
-        if (retval == 0) break;
-        if (retval > 0 && !jcur) {
-            callLSetup = true;
-            ee.ce = ee.j = ee.pe = ee.ps = 0.0; eeI = 0.0;
-#pragma unroll
-            for (int r = 0; r < NR; r++) ee.cs[r] = 0.0;
-            continue;
-        }
-        break;
-    }
-    store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
-    __syncwarp();
-    return retval;
 }
 
 __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Ida& M, double ck,
@@ -376,7 +292,7 @@ __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Id
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     const double* pk = w.v(V_PHI0 + M.kk);
     const double* pk1 = w.v(V_PHI0 + (M.kk > 0 ? M.kk - 1 : 0));
-    for (int i = lane; i < m.N_tot; i += 32) {
+    PLB_FOR_ELEMS(i, m.N_tot) {
         const double e = ee[i], wt = ewt[i];
         const double a = e * wt; s0 = fma(a, a, s0);
         const double d1 = (pk[i] + e); const double b = d1 * wt; s1 = fma(b, b, s1);
@@ -404,11 +320,17 @@ __device__ __forceinline__ void ida_restore(const ModelDesc& m, WarpWS& w, Ida& 
     IdaCoef& K = w.K;
     M.tn = saved_t;
     __syncwarp();
-    if (lane == 0)
+    if (lane == 0) {
+#pragma unroll 1
         for (int j = 1; j <= M.kk; j++) K.psi[j - 1] = K.psi[j] - M.hh;
-    for (int j = M.ns; j <= M.kk; j++) {
-        const double s = 1.0 / K.beta[j];
-        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI0 + j)[i] *= s;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        if (j >= M.ns && j <= M.kk) {
+            const double sc = 1.0 / K.beta[j];
+            double* ph = w.v(V_PHI0 + j);
+            PLB_FOR_ELEMS(i, m.N_tot) ph[i] *= sc;
+        }
     }
     __syncwarp();
 }
@@ -433,7 +355,7 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
         if (action == 0) {
             double s = 0.0;
             const double* pk = w.v(V_PHI0 + M.kk + 1);
-            for (int i = lane; i < m.N_tot; i += 32) { const double a = (ee[i] - pk[i]) * ewt[i]; s = fma(a, a, s); }
+            PLB_FOR_ELEMS(i, m.N_tot) { const double a = (ee[i] - pk[i]) * ewt[i]; s = fma(a, a, s); }
             const double enorm = sqrt(warp_sum(s) / m.N_tot);
             err_kp1 = enorm / (M.kk + 2);
             const double terr_k = (M.kk + 1) * err_k, terr_kp1 = (M.kk + 2) * err_kp1;
@@ -455,129 +377,31 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
         else if (M.rr <= 1.0) { M.rr = fmax(0.5, fmin(0.9, M.rr)); hnew = M.hh * M.rr; }
         M.hh = hnew;
     }
-    // phi updates
-    for (int i = lane; i < m.N_tot; i += 32) {
+    // phi updates: phi[kused+1] = ee ; phi[kused] += ee ; phi[j] += phi[j+1] (j = kused-1..0)
+    PLB_FOR_ELEMS(i, m.N_tot) {
         const double e = ee[i];
-        if (M.kused < o.maxord) w.v(V_PHI0 + M.kused + 1)[i] = e;
-        double acc = w.v(V_PHI0 + M.kused)[i] + e;
-        w.v(V_PHI0 + M.kused)[i] = acc;
-        for (int j = M.kused - 1; j >= 0; j--) { acc += w.v(V_PHI0 + j)[i]; w.v(V_PHI0 + j)[i] = acc; }
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 5; j >= 0; j--) {
+            double* ph = w.v(V_PHI0 + j);
+            if (j == M.kused + 1 && M.kused < o.maxord) ph[i] = e;
+            if (j == M.kused) { acc = ph[i] + e; ph[i] = acc; }
+            else if (j < M.kused) { acc += ph[i]; ph[i] = acc; }
+        }
     }
     __syncwarp();
-}
-
-// IDAStep: 0 ok, <0 failure code
-template <int CHEM>
-__device__ __forceinline__ int ida_step(const ModelDesc& m, WarpWS& w, const LaneRole& ro, const RunCtl& rc,
-                                        const Opts& o, Ida& M, int lane) {
-    IdaCoef& K = w.K;
-    const double saved_t = M.tn;
-    int ncf = 0, nef = 0;
-    if (M.nst == 0) {
-        M.kk = 1; M.kused = 0; M.hused = 0.0; M.cj = 1.0 / M.hh; M.phase = 0; M.ns = 0;
-        __syncwarp();
-        if (lane == 0) K.psi[0] = M.hh;
-        __syncwarp();
-    }
-    double err_k = 0.0, err_km1 = 0.0;
-    for (;;) {
-        const double ck = ida_set_coeffs(m, w, M, lane);
-        const int nflag = ida_nls<CHEM>(m, w, ro, rc, o, M, lane);
-        bool errfail = false;
-        if (nflag == 0) errfail = ida_test_error(m, w, M, ck, err_k, err_km1, lane);
-        if (nflag == 0 && !errfail) break;
-        ida_restore(m, w, M, saved_t, lane);
-        M.phase = 1;
-        if (nflag != 0) {
-            M.ncfn++; ncf++;
-            M.rr = 0.25;
-            M.hh *= M.rr;
-            if (ncf >= o.maxncf) return FAIL_CONV;
-        } else {
-            nef++; M.netf++;
-            if (nef == 1) {
-                const double err_knew = (M.kk == M.knew) ? err_k : err_km1;
-                M.kk = M.knew;
-                M.rr = 0.9 * pow(2.0 * err_knew + 1e-4, -1.0 / (M.kk + 1));
-                M.rr = fmax(0.25, fmin(0.9, M.rr));
-                M.hh *= M.rr;
-            } else if (nef == 2) {
-                M.kk = M.knew; M.rr = 0.25; M.hh *= M.rr;
-            } else if (nef < o.maxnef) {
-                M.kk = 1; M.rr = 0.25; M.hh *= M.rr;
-            } else return FAIL_ERRTEST;
-        }
-        if (M.nst == 0) {
-            __syncwarp();
-            if (lane == 0) K.psi[0] = M.hh;
-            for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.rr;
-            __syncwarp();
-        }
-        if (!(fabs(M.hh) > 0.0) || isinf(M.hh)) return FAIL_CONV;
-    }
-    ida_complete_step(m, w, o, M, err_k, err_km1, lane);
-    return 0;
-}
-
-// IDASolve(ONE_STEP) with a stop time.  Returns 0 / 1 (tstop return) / <0.  *tret = return time.
-template <int CHEM>
-__device__ __forceinline__ int ida_solve_one_step(const ModelDesc& m, WarpWS& w, const LaneRole& ro,
-                                                  const RunCtl& rc, const Opts& o, Ida& M, double tout,
-                                                  double& tret, int lane) {
-    const double ur = DBL_EPSILON;
-    if (M.nst == 0) {
-        ewt_set(m, w, o, lane);
-        const double tdist = fabs(tout - M.tn);
-        M.hh = M.hin;
-        if (M.hh == 0.0) {
-            M.hh = 0.001 * tdist;
-            const double ypnorm = wrms(m, w.v(V_PHI1), w.v(V_EWT), lane);
-            if (ypnorm > 0.5 / M.hh) M.hh = 0.5 / ypnorm;
-            if (tout < M.tn) M.hh = -M.hh;
-        }
-        if (M.tstopset) {
-            if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
-        }
-        M.kk = 0; M.kused = 0;
-        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.hh;
-        __syncwarp();
-    } else {
-        if (M.tstopset) {
-            const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
-            if (fabs(M.tn - M.tstop) <= troundoff) {
-                tret = M.tretlast = M.tstop; M.tstopset = 0;
-                return 1;
-            }
-            if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
-        }
-        ewt_set(m, w, o, lane);
-    }
-    {
-        const double nrm = wrms(m, w.v(V_PHI0), w.v(V_EWT), lane);
-        if (ur * nrm > 1.0) { tret = M.tn; return FAIL_CONV; }
-    }
-    const int sflag = ida_step<CHEM>(m, w, ro, rc, o, M, lane);
-    if (sflag != 0) { tret = M.tretlast = M.tn; return sflag; }
-    if (M.tstopset) {
-        const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
-        if (fabs(M.tn - M.tstop) <= troundoff) {
-            tret = M.tretlast = M.tstop; M.tstopset = 0;
-            return 1;
-        }
-        if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
-    }
-    tret = M.tretlast = M.tn;
-    return 0;
 }
 
 // interpolated value / derivative of component i (internal index) with weights (c, d), order kord
 __device__ __forceinline__ double interp_y(const WarpWS& w, const double* c, int kord, int i) {
     double y = 0.0;
+#pragma unroll 1
     for (int j = 0; j <= kord; j++) y = fma(c[j], w.v(V_PHI0 + j)[i], y);
     return y;
 }
 __device__ __forceinline__ double interp_yp(const WarpWS& w, const double* d, int kord, int i) {
     double y = 0.0;
+#pragma unroll 1
     for (int j = 1; j <= kord; j++) y = fma(d[j - 1], w.v(V_PHI0 + j)[i], y);
     return y;
 }
@@ -587,16 +411,16 @@ struct PrevVals {   // boundary_stop_prev_values, structures.jl:174-184
 };
 
 // check_simulation_stop! -- checks.jl:1-224 (isothermal, no SEI: T and dfilm checks inactive)
-__device__ __forceinline__ void check_stop(const ModelDesc& m, const WarpWS& w, const RunCtl& rc,
-                                           const Opts& o, const Bounds& b, bool is_rest, double tf,
-                                           PrevVals& pv, int& flag, double t, const double* c,
-                                           const double* d, int kord, double SOC, int lane) {
+__device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, const RunCtl& rc,
+                                        const Opts& o, const Bounds& b, bool is_rest, double tf,
+                                        PrevVals& pv, int& flag, double t, const double* c,
+                                        const double* d, int kord, double SOC, double Ic, double V, int lane) {
     const double eps = t < 1.0 ? o.reltol : 0.0;
     if (t >= tf) { flag = 0; return; }
     if (!o.check_bounds || is_rest) return;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
-    const double Ic = interp_y(w, c, kord, m.off_I), dIc = interp_yp(w, d, kord, m.off_I);
     if (rc.method != METHOD_I) {   // check_stop_I :31-54
+        const double dIc = interp_yp(w, d, kord, m.off_I);
         if ((Ic - b.I_max > eps) && dIc > 0) {
             const double tf_ = (pv.I - b.I_max) / (pv.I - Ic);
             if (tf_ < pv.frac) { pv.frac = tf_; flag = 7; }
@@ -606,15 +430,19 @@ __device__ __forceinline__ void check_stop(const ModelDesc& m, const WarpWS& w, 
         }
         pv.I = Ic;
     }
-    if (rc.method != METHOD_V) {   // check_stop_V :56-80
-        const double V = interp_y(w, c, kord, iP0) - interp_y(w, c, kord, iPN);
-        const double dV = interp_yp(w, d, kord, iP0) - interp_yp(w, d, kord, iPN);
-        if ((b.V_min - V > eps) && dV < 0) {
-            const double tf_ = (pv.V - b.V_min) / (pv.V - V);
-            if (tf_ < pv.frac) { pv.frac = tf_; flag = 1; }
-        } else if ((V - b.V_max > eps) && dV > 0) {
-            const double tf_ = (pv.V - b.V_max) / (pv.V - V);
-            if (tf_ < pv.frac) { pv.frac = tf_; flag = 2; }
+    if (rc.method != METHOD_V) {   // check_stop_V :56-80 (the derivative is only needed past a bound)
+        if (b.V_min - V > eps) {
+            const double dV = interp_yp(w, d, kord, iP0) - interp_yp(w, d, kord, iPN);
+            if (dV < 0) {
+                const double tf_ = (pv.V - b.V_min) / (pv.V - V);
+                if (tf_ < pv.frac) { pv.frac = tf_; flag = 1; }
+            }
+        } else if (V - b.V_max > eps) {
+            const double dV = interp_yp(w, d, kord, iP0) - interp_yp(w, d, kord, iPN);
+            if (dV > 0) {
+                const double tf_ = (pv.V - b.V_max) / (pv.V - V);
+                if (tf_ < pv.frac) { pv.frac = tf_; flag = 2; }
+            }
         }
         pv.V = V;
     }
@@ -684,230 +512,5 @@ struct SimArgs {
     int* counter;
     double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]
 };
-
-// simulate / simulate! for one system -- model_evaluation.jl:10-97, 174-232, 312-382
-template <int CHEM>
-__device__ void simulate_system(const SimArgs& a, int sys, WarpWS& w, int lane) {
-    const ModelDesc& m = a.m;
-    const LaneRole ro = make_role(m, lane);
-    const int N = m.N_tot;
-    setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
-    RunCtl rc;
-    rc.method = a.method;
-    rc.value = a.values ? a.values[sys] : a.value;
-    Summary out;
-    out.t_end = 0; out.V_end = 0; out.I_end = 0; out.SOC_end = 0; out.flag = -1; out.n_steps = 0;
-    out.n_res = 0; out.n_jac = 0; out.n_netf = 0; out.n_ncfn = 0; out.n_newton_init = 0; out.reserved = 0;
-    double* Y0 = w.v(V_PHI0);
-    double* YP0 = w.v(V_PHI1);
-    double SOC, t0;
-    const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
-    double I_prev_state = 0.0;
-    // ---- initialize_simulation! :174-232 ------------------------------------------------------------
-    if (a.new_run) {
-        // initial_guess! (states_definition.jl:80-121)
-        SOC = a.soc0 ? a.soc0[sys] : 1.0;
-        const double* th = w.C.theta;
-        const double csp = th[TF_c_max_p] * (SOC * (th[TF_theta_max_p] - th[TF_theta_min_p]) + th[TF_theta_min_p]);
-        const double csn = th[TF_c_max_n] * (SOC * (th[TF_theta_max_n] - th[TF_theta_min_n]) + th[TF_theta_min_n]);
-        LaneVec y0;
-        y0.ce = th[TF_c_e0]; y0.j = 0.0; y0.pe = 0.0; y0.ps = 0.0;
-        const double cs0 = ro.sec == 0 ? csp : csn;
-#pragma unroll
-        for (int r = 0; r < NR; r++) y0.cs[r] = cs0;
-        if (ro.elec) {
-            const double thx = cs0 * w.C.sec[SC_inv_cmax][ro.sec];
-            double U, dU, dUdT = 0.0, ddUdT = 0.0;
-            if (CHEM == CHEM_LCO) {
-                if (ro.sec == 0) laws::OCV_LCO(thx, U, dU, dUdT, ddUdT);
-                else laws::OCV_LiC6(thx, sqrt(fmax(thx, 1e-4)), U, dU, dUdT, ddUdT);
-                if (w.C.g[GC_dUdT_on] != 0.0) U += dUdT * (w.C.g[GC_T] - kTref);
-            } else {
-                if (ro.sec == 0) laws::OCV_NMC(thx, U, dU);
-                else laws::OCV_LiC6_NMC(thx, U, dU);
-            }
-            y0.ps = U;
-        }
-        store_lane(m, ro, Y0, y0, 0.0, lane);
-        t0 = 0.0;
-    } else {
-        for (int i = lane; i < N; i += 32) Y0[i] = a.sY[(size_t)sys * N + ref_index(m, i)];
-        SOC = a.sSOC[sys];
-        t0 = ::nextafter(a.st[sys], DBL_MAX);   // initial_time, model_evaluation.jl:112
-    }
-    __syncwarp();
-    I_prev_state = Y0[m.off_I];
-    // initial_current! (input_methods.jl:11-107)
-    {
-        double Ig;
-        const double V0 = Y0[iP0] - Y0[iPN];
-        if (a.input_kind == 1) {              // :hold -- value from the previous state
-            if (rc.method == METHOD_I) { rc.value = I_prev_state; Ig = I_prev_state; }
-            else if (rc.method == METHOD_V) { rc.value = V0; Ig = V0; }   // sic: input_methods.jl:58
-            else { rc.value = I_prev_state * w.C.g[GC_I1C] * V0; Ig = I_prev_state; }
-        } else if (a.input_kind == 2) {       // :rest
-            rc.value = 0.0; Ig = 0.0;
-        } else if (rc.method == METHOD_I) Ig = rc.value;
-        else if (rc.method == METHOD_V) {
-            if (!a.new_run && I_prev_state != 0.0) Ig = I_prev_state;
-            else Ig = rc.value > V0 ? 1.0 : -1.0;
-        } else Ig = rc.value / (V0 * w.C.g[GC_I1C]);
-        __syncwarp();
-        if (lane == 0) Y0[m.off_I] = Ig;
-        __syncwarp();
-    }
-    int nres = 0, njac = 0;
-    const int nit = newton_init<CHEM>(m, w, ro, rc, a.o, Y0, YP0, lane, nres, njac);
-    out.n_newton_init = nit;
-    out.n_res = nres; out.n_jac = njac;
-    bool done = false;
-    if (nit < 0) { out.flag = FAIL_NEWTON_INIT; done = true; }
-    if (!done && a.new_run) {   // check_initial_SOC, checks.jl:327-339
-        const double I0 = Y0[m.off_I];
-        if (I0 != 0 && ((SOC >= a.b.SOC_max && I0 > 0) || (SOC <= a.b.SOC_min && I0 < 0))) {
-            out.flag = FAIL_INIT_BOUNDS; done = true;
-        }
-    }
-    const size_t so = (size_t)sys * a.n_save_max;
-    int nsave = 0;
-    double t = 0.0, tprev = 0.0;
-    double SOC_end = SOC, t_end = t0, V_end = 0.0, I_end = 0.0;
-    if (!done) {
-        Ida M;
-        M.tn = 0.0; M.hh = 0.0; M.hused = 0.0; M.cj = 0.0; M.cjlast = 0.0; M.cjold = 0.0; M.cjratio = 1.0;
-        M.ss = 20.0; M.rr = 0.0; M.hin = 0.0; M.tstop = 0.0; M.tretlast = 0.0;
-        M.kk = 0; M.kused = 0; M.knew = 0; M.phase = 0; M.ns = 0; M.nst = 0; M.tstopset = 0;
-        M.nre = nres; M.nje = njac; M.netf = 0; M.ncfn = 0;
-        for (int k = 2; k < 6; k++)
-            for (int i = lane; i < N; i += 32) w.v(V_PHI0 + k)[i] = 0.0;
-        __syncwarp();
-        // tstops: [1.0 if continuing; tf] (:288-310)
-        double tstops[2];
-        int ntstops = 0, itstop = 0;
-        if (!a.new_run && 1.0 < a.tf) tstops[ntstops++] = 1.0;
-        tstops[ntstops++] = a.tf;
-        // first output row and t = 0 stop check (:225-230)
-        double cw[6] = {1, 0, 0, 0, 0, 0}, dw[6] = {1, 0, 0, 0, 0, 0};   // y = phi0, yp = phi1 (= YP0 before scaling)
-        double Vc = Y0[iP0] - Y0[iPN], Ic = Y0[m.off_I];
-        double I_prev = Ic;
-        if (lane == 0 && nsave < a.n_save_max) {
-            if (a.tr_t) a.tr_t[so + nsave] = t0;
-            if (a.tr_V) a.tr_V[so + nsave] = Vc;
-            if (a.tr_I) a.tr_I[so + nsave] = Ic;
-            if (a.tr_SOC) a.tr_SOC[so + nsave] = SOC;
-        }
-        nsave++;
-        PrevVals pv;
-        pv.frac = 1.0; pv.V = -1; pv.SOC = -1; pv.c_s_n = -1; pv.I = -1; pv.eta_plating = -1; pv.c_e_min = -1;
-        int flag = -1;
-        check_stop(m, w, rc, a.o, a.b, a.input_kind == 2, a.tf, pv, flag, 0.0, cw, dw, 1, SOC, lane);
-        int iter = 1, hard = 0;
-        bool retried = false;
-        double tg_prev = t0;
-        int kord = 1, kord_prev = 1;
-        if (flag == -1) {
-            // solve! (:312-333)
-            for (;;) {
-                tprev = t;
-                // remember the interpolation weights of the previous return point for the final interp
-                M.tstop = tstops[itstop]; M.tstopset = 1;
-                double tret = t;
-                const int fl = ida_solve_one_step<CHEM>(m, w, ro, rc, a.o, M, tstops[itstop], tret, lane);
-                if (fl == 1 || tret >= tstops[itstop]) { if (itstop < ntstops - 1) itstop++; }
-                t = tret;
-                iter++;
-                if (fl < 0 || t == tprev) {
-                    // check_solve (checks.jl:226-237): one retry of the very first step with h = reltol
-                    if (t == 0.0 && iter == 2 && !retried && M.nst == 0) {
-                        retried = true;
-                        // phi1 currently holds h_failed-scaled YP0: undo and restart the first step
-                        const double sc = 1.0 / w.K.psi[0];
-                        for (int i = lane; i < N; i += 32) w.v(V_PHI1)[i] *= sc;
-                        __syncwarp();
-                        M.hin = a.o.reltol;
-                        continue;
-                    }
-                    hard = (fl == FAIL_ERRTEST) ? FAIL_ERRTEST : FAIL_CONV;
-                    break;
-                }
-                kord_prev = kord;
-                kord = getsol_weights(M, w.K, t, cw, dw);
-                Ic = interp_y(w, cw, kord, m.off_I);
-                Vc = interp_y(w, cw, kord, iP0) - interp_y(w, cw, kord, iPN);
-                // set_vars! -> SOC trapezoid (save_outputs.jl:31, scalar_residual.jl:103-111)
-                const double tg = t + t0;
-                SOC = SOC + 0.5 * (tg - tg_prev) * (Ic + I_prev) / 3600.0;
-                if (lane == 0 && nsave < a.n_save_max) {
-                    if (a.tr_t) a.tr_t[so + nsave] = tg;
-                    if (a.tr_V) a.tr_V[so + nsave] = Vc;
-                    if (a.tr_I) a.tr_I[so + nsave] = Ic;
-                    if (a.tr_SOC) a.tr_SOC[so + nsave] = SOC;
-                }
-                nsave++;
-                check_stop(m, w, rc, a.o, a.b, a.input_kind == 2, a.tf, pv, flag, t, cw, dw, kord, SOC, lane);
-                if (iter == a.o.maxiters) { hard = FAIL_MAXITERS; break; }
-                if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { hard = FAIL_NONFINITE; break; }
-                if (flag != -1) break;
-                I_prev = Ic;
-                tg_prev = tg;
-            }
-        }
-        (void)kord_prev;
-        // exit_simulation! (:335-382)
-        t_end = t + t0;
-        SOC_end = SOC;
-        double fr = 1.0;
-        bool do_interp = false;
-        if (hard) flag = hard;
-        else if (a.o.interp_final && flag != 0 && flag != -1 && t > 1.0) { do_interp = true; fr = pv.frac; }
-        // weights of the previous return point (Y_prev = interpolant at tprev; exact at mesh points)
-        double cp[6] = {1, 0, 0, 0, 0, 0}, dp[6];
-        if (do_interp) getsol_weights(M, w.K, tprev, cp, dp);
-        // final state (reference layout) and outputs
-        double ps0 = 0.0, psN = 0.0, If = 0.0;
-        for (int i = lane; i < N; i += 32) {
-            const double yn = interp_y(w, cw, kord, i);
-            double yf = yn;
-            if (do_interp) { const double ypv = interp_y(w, cp, kord, i); yf = fr * (yn - ypv) + ypv; }
-            a.sY[(size_t)sys * N + ref_index(m, i)] = yf;
-            if (a.sYP) a.sYP[(size_t)sys * N + ref_index(m, i)] = interp_yp(w, dw, kord, i);
-            if (i == iP0) ps0 = yf;
-            if (i == iPN) psN = yf;
-            if (i == m.off_I) If = yf;
-        }
-        ps0 = warp_sum(ps0); psN = warp_sum(psN); If = warp_sum(If);
-        V_end = ps0 - psN; I_end = If;
-        if (do_interp) {
-            const double ti = fr * (t - tprev) + tprev;
-            const double tgi = ti + t0, tgl = t + t0;
-            SOC_end = SOC + 0.5 * (tgi - tgl) * (If + If) / 3600.0;
-            t_end = tgi;
-            if (lane == 0 && nsave - 1 < a.n_save_max && nsave >= 1) {
-                if (a.tr_t) a.tr_t[so + nsave - 1] = tgi;
-                if (a.tr_V) a.tr_V[so + nsave - 1] = V_end;
-                if (a.tr_I) a.tr_I[so + nsave - 1] = I_end;
-                if (a.tr_SOC) a.tr_SOC[so + nsave - 1] = SOC_end;
-            }
-        }
-        out.flag = flag;
-        out.n_res = M.nre; out.n_jac = M.nje; out.n_netf = M.netf; out.n_ncfn = M.ncfn;
-    } else {
-        // failed before integration: hand the initial state back
-        for (int i = lane; i < N; i += 32) {
-            a.sY[(size_t)sys * N + ref_index(m, i)] = Y0[i];
-            if (a.sYP) a.sYP[(size_t)sys * N + ref_index(m, i)] = 0.0;
-        }
-        nsave = 1;
-    }
-    out.t_end = t_end; out.V_end = V_end; out.I_end = I_end; out.SOC_end = SOC_end;
-    out.n_steps = nsave - 1;
-    if (lane == 0) {
-        a.out[sys] = out;
-        a.sSOC[sys] = SOC_end;
-        a.st[sys] = t_end;
-        if (a.tr_n) a.tr_n[sys] = nsave < a.n_save_max ? nsave : a.n_save_max;
-    }
-    __syncwarp();
-}
 
 }  // namespace plb

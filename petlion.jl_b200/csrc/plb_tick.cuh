@@ -47,21 +47,9 @@ struct SimState {
 // ---- pieces of ida_nls -------------------------------------------------------------------------------
 __device__ __forceinline__ void nls_begin(const ModelDesc& m, WarpWS& w, SimState& S, int lane) {
     Ida& M = S.M;
-    const IdaCoef& K = w.K;
     S.callLSetup = 0;
     if (M.nst == 0) { M.cjold = M.cj; M.ss = 20.0; S.callLSetup = 1; }
-#pragma unroll 1
-    for (int i = lane; i < m.N_tot; i += 32) {
-        double yv = 0.0, ypv = 0.0;
-#pragma unroll 1
-        for (int j = 0; j <= M.kk; j++) {
-            const double p = w.v(V_PHI0 + j)[i];
-            yv += p;
-            if (j > 0) ypv = fma(K.gamma[j], p, ypv);
-        }
-        w.v(V_YPRED)[i] = yv; w.v(V_YPPRED)[i] = ypv; w.v(V_EE)[i] = 0.0;
-    }
-    __syncwarp();
+    predict_pass(m, w, M, lane);
     M.cjratio = M.cj / M.cjold;
     const double temp1 = (1.0 - 0.25) / (1.0 + 0.25), temp2 = 1.0 / temp1;
     if (M.cjratio < temp1 || M.cjratio > temp2) S.callLSetup = 1;
@@ -143,8 +131,7 @@ __device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const
         }
         if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
         M.kk = 0; M.kused = 0;
-#pragma unroll 1
-        for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.hh;
+        { double* p1 = w.v(V_PHI1); PLB_FOR_ELEMS(i, m.N_tot) p1[i] *= M.hh; }
         __syncwarp();
     } else {
         const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
@@ -155,7 +142,8 @@ __device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const
         if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
         ewt_set(m, w, o, lane);
     }
-    {
+    if (o.reltol < ur) {
+        // IDA's "too much accuracy requested" test: |y_i| ewt_i < 1/rtol, so uround*||y|| > 1 needs rtol < uround
         const double nrm = wrms(m, w.v(V_PHI0), w.v(V_EWT), lane);
         if (ur * nrm > 1.0) { S.ret_t = M.tn; S.ret_fl = FAIL_CONV; return false; }
     }
@@ -266,8 +254,14 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
     if (lane == 0) S.kord = getsol_weights(M, w.K, S.t, w.K.cvals, w.K.dvals);
     S.kord = __shfl_sync(FULL, S.kord, 0);
     __syncwarp();
-    const double Ic = interp_y(w, w.K.cvals, S.kord, m.off_I);
-    const double Vc = interp_y(w, w.K.cvals, S.kord, iP0) - interp_y(w, w.K.cvals, S.kord, iPN);
+    double Ic = 0.0, vp = 0.0, vn = 0.0;
+#pragma unroll 1
+    for (int j = 0; j <= S.kord; j++) {
+        const double cj_ = w.K.cvals[j];
+        const double* ph = w.v(V_PHI0 + j);
+        Ic = fma(cj_, ph[m.off_I], Ic); vp = fma(cj_, ph[iP0], vp); vn = fma(cj_, ph[iPN], vn);
+    }
+    const double Vc = vp - vn;
     const double tg = S.t + S.t0;
     S.SOC = S.SOC + 0.5 * (tg - S.tg_prev) * (Ic + S.I_prev) / 3600.0;
     const size_t so = (size_t)S.sys * a.n_save_max;
@@ -278,7 +272,7 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
         if (a.tr_SOC) a.tr_SOC[so + S.nsave] = S.SOC;
     }
     S.nsave++;
-    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, lane);
+    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, Ic, Vc, lane);
     if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return false; }
     if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { S.hard = FAIL_NONFINITE; return false; }
     if (S.flag != -1) return false;
@@ -473,7 +467,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
     S.nsave++;
     S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
     S.kord = 1;
-    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, lane);
+    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, Ic, Vc, lane);
     S.tg_prev = S.t0;
     S.pending = (S.flag == -1) ? PEND_BEGIN : PEND_FINISH;
 }
