@@ -244,3 +244,60 @@ def test_nmc_variant(P):
     assert s2["flag"][0] == ref2["flag"][0] == 0
     assert s2["n_steps"][0] == ref2["n_steps"][0]
     np.testing.assert_allclose(s2["V_end"], ref2["V_end"], rtol=1e-6)
+
+
+def test_simulate_power_control(P, lco):
+    """method_P (constant power, scalar_residual.jl:189-197): the control row has a zero... no, a V*I1C
+    diagonal and two Phi_s entries; exercised through the Schur-complement border."""
+    m = O.make_model("LCO")
+    B = 16
+    tho = util.oracle_theta_batch(B, first=300)
+    th = util.product_theta_from_oracle(lco, tho)
+    util.set_theta_batch(lco, th)
+    sol = P.simulate(lco, 900.0, P=-60.0, SOC=0.9)
+    ref = O.simulate_batch(m, tho, O.make_run("P", -60.0, tf=900.0), O.default_opts(), O.default_bounds("LCO"),
+                           SOC0=0.9, n_save_max=512, nthreads=8)
+    assert np.all(ref["flag"] == 0)
+    _compare_runs(sol, ref, min_identical=0.9)
+    # power is held: P = I * I1C * V
+    I1C = lco.I1C(B)
+    s = sol.results[-1].summary
+    np.testing.assert_allclose(s["I_end"] * I1C * s["V_end"], -60.0, rtol=1e-6)
+
+
+def test_gitt_protocol_nmc(P):
+    """configs[3] protocol at test size: NMC, SOC0 = 0, repeated {I=+1 for 180 s ; I=:rest for 1200 s}
+    through simulate!/continuation (examples/GITT.ipynb)."""
+    m = O.make_model("NMC")
+    p = P.petlion("NMC")
+    B = 6
+    names = O.theta_names()
+    tho = np.tile(O.theta_defaults("NMC"), (B, 1))
+    u = util.splitmix_u01(util.SEED, np.arange(B), 3)
+    tho[:, names.index("D_sp")] *= 10.0 ** (0.3 * (2 * u - 1))
+    tho[:, names.index("k_n")] *= 10.0 ** (0.3 * (2 * util.splitmix_u01(util.SEED, np.arange(B), 4) - 1))
+    th = util.product_theta_from_oracle(p, tho)
+    util.set_theta_batch(p, th)
+    opts, bounds = O.default_opts(), O.default_bounds("NMC")
+    sol, state = None, None
+    for cyc in range(3):
+        sol = P.simulate(p, 180.0, I=1, SOC=0) if sol is None else P.simulate_(sol, p, 180.0, I=1)
+        ref = O.simulate_batch(m, tho, O.make_run("I", 1.0, tf=180.0, new_run=state is None), opts, bounds,
+                               SOC0=0.0, state=state, n_save_max=512)
+        state = ref["state"]
+        s = sol.results[-1].summary
+        assert np.array_equal(s["flag"], ref["flag"]) and np.all(s["flag"] == 0)
+        assert np.mean(s["n_steps"] == ref["n_steps"]) >= 0.8
+        np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=1e-6)
+        np.testing.assert_allclose(s["SOC_end"], ref["SOC_end"], rtol=1e-6, atol=1e-9)
+        P.simulate_(sol, p, 1200.0, I="rest")
+        ref = O.simulate_batch(m, tho, O.make_run("I", 0.0, tf=1200.0, input_kind="rest", new_run=False), opts, bounds,
+                               state=state, n_save_max=512)
+        state = ref["state"]
+        s = sol.results[-1].summary
+        assert np.array_equal(s["flag"], ref["flag"]) and np.all(s["flag"] == 0)
+        np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=1e-6)
+        np.testing.assert_allclose(s["t_end"], ref["t_end"], rtol=1e-9)
+    assert len(sol.results) == 6
+    # global time is continuous across runs
+    assert np.all(np.diff(sol.t[0, :sol.n_points[0]]) >= 0)
