@@ -51,6 +51,9 @@ struct ResJacArgs {
                           //   bit 16 particle-block entry, bit 17 anode, bit 18 diagonal
 };
 
+#ifndef PLB_K1_CTAS
+#define PLB_K1_CTAS 3
+#endif
 constexpr int K1_WARPS = 4;
 constexpr int K1_NSTAGE = JS_CS0 + 3;   // lane-computed slots: 0..JS_CS_J, then the three control-row slots
 constexpr int K1_SRC_MAX = 2304;        // >= nnz of every built variant
@@ -70,7 +73,7 @@ struct K1Warp {
 // table held in shared memory, never staged; only the ~500 lane-computed entries go through a
 // 6.4 KB shared-memory stage.
 template <int CHEM>
-__global__ void __launch_bounds__(K1_WARPS * 32, 4) k_resjac(ResJacArgs a) {
+__global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArgs a) {
     __shared__ K1Warp ws[K1_WARPS];
     __shared__ int src_s[K1_SRC_MAX];
     for (int i = threadIdx.x; i < a.nnz; i += blockDim.x) src_s[i] = a.src[i];
@@ -603,7 +606,7 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
     a.method = run->method; a.value = run->value; a.res = res; a.nzval = nzval; a.nnz = nnz;
     a.src = h->d_src[run->method];
     const size_t smem = 0;
-    const int grid = std::min((B + K1_WARPS - 1) / K1_WARPS, h->num_sms * 4 * 2);
+    const int grid = std::min((B + K1_WARPS - 1) / K1_WARPS, h->num_sms * PLB_K1_CTAS * 2);
     CUDA_OK(cudaEventRecord(h->ev0, s));
     if (m.chem == CHEM_LCO) {
         k_resjac<CHEM_LCO><<<grid, K1_WARPS * 32, smem, s>>>(a);
