@@ -57,8 +57,8 @@ class Bounds(C.Structure):
 
 class Summary(C.Structure):
     _fields_ = [("t_end", C.c_double), ("V_end", C.c_double), ("I_end", C.c_double),
-                ("SOC_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int), ("n_res", C.c_int),
-                ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int),
+                ("SOC_end", C.c_double), ("T_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int),
+                ("n_res", C.c_int), ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int),
                 ("n_newton_init", C.c_int)]
 
 

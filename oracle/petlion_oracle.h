@@ -96,6 +96,7 @@ typedef struct {
 /* per-simulation result summary */
 typedef struct {
     double t_end, V_end, I_end, SOC_end;
+    double T_end;  /* temperature_weighting(T) of the final state (T0 for isothermal models) */
     int flag;      /* 0..11 as checks.jl ; <0 hard failure */
     int n_steps;   /* accepted IDA steps (= saved points - 1) */
     int n_res, n_jac, n_netf, n_ncfn, n_newton_init;

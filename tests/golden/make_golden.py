@@ -126,6 +126,24 @@ try:
 except Exception as e:  # pragma: no cover
     gold["ladder_CCCV_older_version"] = {"error": str(e)}
 
+# ---- fast_charging_CC-CT-CV.ipynb (current PETLION wording; temperature=true) -------------
+nb = json.load(open(os.path.join(EX, "fast_charging_CC-CT-CV.ipynb")))
+svg = cell_svg(nb, 17)
+pls = polylines(svg)
+xs, ys, box = decode_axes(pls)
+xticks = [x for x in xs if x != box[0]]          # ticks at 0, 500, 1000, 1500 s
+px_per_s = (xticks[-1] - xticks[0]) / 1500.0
+data = [p for p in pls if len(p) > 5][0]
+tt = [(x - xticks[0]) / px_per_s for x, _ in data]
+# segment 1 = simulate(p, I=4) until T_max: its last point is the interpolated end point, repeated
+# as the first point of the next run
+n1 = next(i for i in range(1, len(tt)) if tt[i] <= tt[i - 1])   # the duplicated hand-over point
+gold["ladder_4C_thermal"] = {
+    "run": "p=petlion(LCO; temperature=true); SOC=0; T_max=313.15; V_max=4.1; simulate(p, I=4)",
+    "note": "t decoded from SVG pixels (~1 ms resolution); V as raw y pixels (linear in V)",
+    "t": tt[:n1], "y_px": [y for _, y in data[:n1]], "n_points_all_runs": len(data),
+}
+
 # ---- printed summaries --------------------------------------------------------
 gold["summaries"] = {
     "1C_discharge": {"t_s": 3600.0, "V": 2.9357, "P": -85.8094, "SOC": -0.0, "exit": "SOC_min",
@@ -134,6 +152,10 @@ gold["summaries"] = {
                       "src": "CC-CV.ipynb:66-75 (older version)"},
     "CV_hold": {"t_s": 2440.61, "I_C": 0.1955, "P": 23.432, "SOC": 1.0001, "exit": "SOC_max",
                 "src": "CC-CV.ipynb:103-112 (older version)"},
+    "thermal_4C_to_Tmax": {"t_s": 357.56, "V": 4.0312, "P": 471.33, "SOC": 0.3973, "T_C": 40.0,
+                           "exit": "T_max", "src": "fast_charging_CC-CT-CV.ipynb cell 7 (current version)"},
+    "thermal_CV_after_CT": {"t_s": 1865.61, "I_C": 0.1959, "P": 23.47, "SOC": 1.0, "T_C": 25.6963,
+                            "exit": "SOC_max", "src": "fast_charging_CC-CT-CV.ipynb cell 13 (after a dT=:hold run)"},
     "benchmark_median_ms": 2.616,
 }
 

@@ -128,3 +128,67 @@ def test_rng_matches_numpy_copy():
     for sid in (0, 1, 17, 65535):
         for pid in range(7):
             assert O.rng_u01(20211, sid, pid) == splitmix_u01(20211, np.array([sid]), pid)[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# temperature=true (351 DAEs): examples/fast_charging_CC-CT-CV.ipynb, executed with the current PETLION
+# ---------------------------------------------------------------------------------------------------
+def _thermal_run():
+    m = O.make_model("LCO", temperature=True); th = O.theta_defaults("LCO")
+    b = O.default_bounds("LCO", T_max=40 + 273.15, V_max=4.1, I_max=4.0, I_min=1 / 20)
+    r = O.simulate_batch(m, th, O.make_run("I", 4.0), O.default_opts(), b, SOC0=0.0, n_save_max=400)
+    return m, th, b, r
+
+
+def test_thermal_layout_and_pattern():
+    m = O.make_model("LCO", temperature=True)
+    L = O.layout(m)
+    assert (L.N_diff, L.N_alg, L.N_tot) == (280, 71, 351)
+    assert L.T == 230 and L.j == 280
+    cp, rv = O.jac_pattern(m, "I")
+    assert len(rv) == 2883
+
+
+def test_thermal_printed_summary(goldens):
+    """simulate(p, I=4) from SOC 0 with T_max = 40 C: every printed digit of the reference's summary."""
+    m, th, b, r = _thermal_run()
+    s = goldens["summaries"]["thermal_4C_to_Tmax"]
+    assert r["flag"][0] == 5                                        # "Above max. temperature"
+    assert round(r["t_end"][0], 2) == s["t_s"]
+    assert round(r["V_end"][0], 4) == s["V"]
+    assert round(r["V_end"][0] * 4.0 * O.calc_I1C(th), 2) == s["P"]
+    assert round(r["SOC_end"][0], 4) == s["SOC"]
+    assert round(r["T_end"][0] - 273.15, 4) == s["T_C"]
+
+
+def test_thermal_step_ladder_matches_notebook(goldens):
+    """All 76 IDA steps of the thermal 4C charge (SVG polyline of cell 17) are reproduced."""
+    m, th, b, r = _thermal_run()
+    g = goldens["ladder_4C_thermal"]
+    gt, gy = np.array(g["t"]), np.array(g["y_px"])
+    n = r["traj_n"][0]
+    t, V = r["traj"]["t"][0, :n], r["traj"]["V"][0, :n]
+    assert n == len(gt) == 77
+    assert np.all(np.abs(t - gt) <= 0.002 + 1e-3 * gt)             # pixel resolution ~1 ms
+    # the y pixels are an affine image of V: fit the two calibration constants, check the other 75
+    A = np.vstack([gy, np.ones(n)]).T
+    c = np.linalg.lstsq(A, V, rcond=None)[0]
+    assert np.max(np.abs(A @ c - V)) < 2e-5
+
+
+def test_thermal_jacobian_complex_step_vs_finite_difference():
+    m = O.make_model("LCO", temperature=True); th = O.theta_defaults("LCO"); L = O.layout(m)
+    y = O.initial_guess(m, th, 0.5); y[L.I] = 2.0
+    y[L.T:L.T + 50] += np.linspace(3.0, 9.0, 50)                    # a temperature profile
+    run = O.make_run("I", 2.0)
+    it, y, yp = O.newton_init(m, th, run, O.default_opts(), y)
+    cp, rv = O.jac_pattern(m, "I")
+    nz = O.jacobian(m, th, run, 0.0, y, yp, 0.7)
+    r0 = O.residual(m, th, run, 0.0, y, yp)
+    for c in list(range(L.T, L.T + 50, 7)) + [0, 9, 29, L.phi_e, L.phi_e + 2, L.phi_s + 2, L.phi_s + 17, L.j + 3, L.I]:
+        h = 1e-5 * max(abs(y[c]), 1e-2)                              # central difference
+        yb = y.copy(); yb[c] += h; ypb = yp.copy(); ypb[c] += 0.7 * h
+        ya = y.copy(); ya[c] -= h; ypa = yp.copy(); ypa[c] -= 0.7 * h
+        fd = (O.residual(m, th, run, 0.0, yb, ypb) - O.residual(m, th, run, 0.0, ya, ypa)) / (2 * h)
+        for k in range(cp[c], cp[c + 1]):
+            assert nz[k] == pytest.approx(fd[rv[k]], rel=1e-4, abs=1e-6 * max(1.0, abs(nz[k]))), (c, rv[k])
