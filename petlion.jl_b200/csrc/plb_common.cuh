@@ -1,0 +1,140 @@
+// plb_common.cuh -- plain types shared by the host side (plb_kernels.cu) and the two device variants.
+//
+// The device code (plb_device.cuh, plb_integrator.cuh, plb_tick.cuh, plb_variant.cuh) is compiled twice,
+// once per model family, into namespaces plb::iso (isothermal, N = 301) and plb::th (temperature = true,
+// N = 351): plb_variant_iso.cu / plb_variant_th.cu.  The reference does the same thing at model-build
+// time: `petlion(...; temperature=true)` generates a different residual/Jacobian
+// (/root/reference/src/generate_functions.jl:102-164, src/params.jl:119-174).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plb {
+
+constexpr double kF = 96485.3321233;     // const_Faradays,  structures.jl:10
+constexpr double kR = 8.31446261815324;  // const_Ideal_Gas, structures.jl:11
+constexpr double kTref = 298.15;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum { CHEM_LCO = 0, CHEM_NMC = 1 };
+enum { METHOD_I = 0, METHOD_V = 1, METHOD_P = 2 };
+
+// canonical parameter fields (ASCII names of the reference keys); the thermal block is only part of a
+// theta row when temperature = true
+enum ThetaField {
+    TF_D_n, TF_D_p, TF_D_s, TF_D_sn, TF_D_sp, TF_Ea_D_sn, TF_Ea_D_sp, TF_Ea_k_n, TF_Ea_k_p,
+    TF_Rp_n, TF_Rp_p, TF_T0, TF_brugg_n, TF_brugg_p, TF_brugg_s, TF_c_e0, TF_c_max_n, TF_c_max_p,
+    TF_k_n, TF_k_p, TF_l_n, TF_l_p, TF_l_s, TF_t_plus, TF_theta_max_n, TF_theta_max_p,
+    TF_theta_min_n, TF_theta_min_p, TF_sigma_n, TF_sigma_p, TF_eps_fn, TF_eps_fp, TF_eps_n,
+    TF_eps_p, TF_eps_s,
+    // thermal (params.jl:5-117, 177-226)
+    TF_Cp_a, TF_Cp_n, TF_Cp_p, TF_Cp_s, TF_Cp_z, TF_T_amb, TF_h_cell, TF_l_a, TF_l_z,
+    TF_lambda_a, TF_lambda_n, TF_lambda_p, TF_lambda_s, TF_lambda_z,
+    TF_rho_a, TF_rho_n, TF_rho_p, TF_rho_s, TF_rho_z, TF_sigma_a, TF_sigma_z,
+    TF_COUNT
+};
+
+// model descriptor (by value into kernels)
+struct ModelDesc {
+    int Np, Ns, Nn, Nx, Ne;      // nodes per section, Nx = Np+Ns+Nn <= 32, Ne = Np+Nn
+    int Na, Nz;                  // current-collector nodes (thermal models), else 0
+    int thermal;                 // temperature = true
+    int chem;                    // CHEM_*
+    int ntheta;                  // length of one theta row (reference order, used keys only)
+    int theta_stride;            // row stride in doubles
+    int mid;                     // meeting node of the twisted block elimination
+    // reference layout offsets (external.jl:275-365):
+    //   c_e | c_s (particle-major) | [T: a|p|s|n|z] | j | Phi_e | Phi_s | I
+    int off_cs, off_T, off_j, off_pe, off_ps, off_I, N_diff, N_tot;
+    int8_t slot[TF_COUNT];       // theta field -> position in the row (-1: not a key of this variant)
+};
+
+struct Opts {
+    double abstol, reltol, abstol_init, reltol_init;
+    int maxiters, check_bounds, interp_final;
+    int maxord, maxcor, maxnef, maxncf;   // Sundials.jl IDA(): 5, 3, 7, 10
+};
+struct Bounds {
+    double V_max, V_min, SOC_max, SOC_min, T_max, c_s_n_max, I_max, I_min, eta_plating_min, c_e_min,
+        dfilm_max;
+};
+struct Summary {   // == plb_summary (include/petlion_b200.h), 80 bytes
+    double t_end, V_end, I_end, SOC_end, T_end, aux_end;
+    int flag, n_steps, n_res, n_jac, n_netf, n_ncfn, n_newton_init, reserved;
+};
+
+constexpr int FAIL_NEWTON_INIT = -1, FAIL_CONV = -2, FAIL_ERRTEST = -3, FAIL_MAXITERS = -4,
+              FAIL_NONFINITE = -5, FAIL_INIT_BOUNDS = -6;
+
+struct ResJacArgs {
+    ModelDesc m;
+    int B;
+    const double *Y, *YP, *gamma, *theta, *values;
+    int method;
+    double value;
+    double *res, *nzval;
+    int nnz;
+    const int* src;       // [nnz] recipe per CSC position (see plb_variant.cuh)
+};
+
+struct AuxArgs {
+    ModelDesc m;
+    int B;
+    const double *theta, *soc, *values;
+    int method;
+    double value;
+    Opts o;
+    double *Y, *YP;
+    int* status;
+    double* gws;
+    // linear-solve operator (plb_linear_solve): J(Y, YP, gamma) x = rhs
+    const double *gamma, *rhs;
+    double* x;
+};
+
+struct SimArgs {
+    ModelDesc m;
+    int B;
+    const double* theta;
+    const double* values;     // per-system control value or nullptr
+    int method;
+    double value, tf;
+    int input_kind, new_run;   // 0 value, 1 :hold, 2 :rest
+    Opts o;
+    Bounds b;
+    const double* soc0;
+    double *sY, *sYP, *sSOC, *st;
+    Summary* out;
+    int n_save_max;
+    double *tr_t, *tr_V, *tr_I, *tr_SOC, *tr_T;
+    int* tr_n;
+    int* counter;
+    double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]
+};
+
+// what the host needs to know about a compiled variant
+struct VariantInfo {
+    int sim_warps, sim_ctas;        // warps per CTA / CTAs per SM of the persistent integrator
+    int k1_warps, k1_ctas;
+    size_t sim_smem, k1_smem;       // dynamic shared memory per CTA
+    int vs, nglobal;                // workspace vector stride, history vectors parked in global memory
+    int n_slots, n_stage, k1_src_max;
+};
+
+// launchers, one set per variant (defined in plb_variant.cuh)
+#define PLB_DECLARE_VARIANT(NS)                                                                     \
+    namespace NS {                                                                                  \
+    VariantInfo info();                                                                             \
+    /* structural enumeration of one lane's Jacobian entries: (row, col) in the reference layout */ \
+    bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& col);           \
+    int slot_recipe(const ModelDesc& m, int slot, int lane);                                        \
+    cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s);                       \
+    cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s);                       \
+    cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s);                          \
+    cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s);                        \
+    cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s);                        \
+    }
+PLB_DECLARE_VARIANT(iso)
+PLB_DECLARE_VARIANT(th)
+
+}  // namespace plb
