@@ -8,7 +8,7 @@ the HBM roofline fraction of the residual+Jacobian kernel.
 One "step" = one pass of the hot path over one batch of synthetic input: B = 65 536 independent
 1C CC discharges (LCO, N=(10,10,10), N_r=10, isothermal, SOC 1 -> SOC_min/V_min) with randomised
 {D_s, k, eps} (BASELINE.json configs[1]), per GPU (weak scaling: simulations are independent,
-ranks share nothing; one NCCL all-gather collects the 64-byte per-system summaries).
+ranks share nothing; one NCCL all-gather collects the 80-byte per-system summaries).
 """
 import argparse
 import ctypes as C
@@ -167,7 +167,7 @@ def main():
     d_soc0 = torch.ones(B, **f64)
     d_Y = torch.zeros(B, N, **f64); d_YP = torch.zeros(B, N, **f64)
     d_SOC = torch.zeros(B, **f64); d_t = torch.zeros(B, **f64)
-    d_sum = torch.zeros(B, 8, **f64)                           # 64-byte summary records
+    d_sum = torch.zeros(B, 10, **f64)                          # 80-byte summary records
     d_trn = torch.zeros(B, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, **f64)        # > 126 MB L2
     run = _lib.Run(0, 0, -1.0, 1e6, 1, 0)
@@ -177,7 +177,7 @@ def main():
     def step_device():
         _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(b),
                                   d_soc0.data_ptr(), d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(),
-                                  d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None,
+                                  d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, None,
                                   d_trn.data_ptr(), 1))
 
     def barrier():
@@ -204,7 +204,7 @@ def main():
     clocks = sampler.stop()
     # one NCCL all-gather of the fixed-size summaries (the only collective on this path)
     if world > 1:
-        gathered = torch.empty(world * B, 8, **f64)
+        gathered = torch.empty(world * B, 10, **f64)
         dist.all_gather_into_tensor(gathered, d_sum)
         tmax = torch.tensor([ms_local], **f64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -220,7 +220,7 @@ def main():
     h_soc0 = torch.ones(B, dtype=torch.float64).pin_memory()
     h_Y = torch.zeros(B, N, dtype=torch.float64).pin_memory()
     h_SOC = torch.zeros(B, dtype=torch.float64).pin_memory(); h_t = torch.zeros(B, dtype=torch.float64).pin_memory()
-    h_sum = torch.zeros(B, 8, dtype=torch.float64).pin_memory()
+    h_sum = torch.zeros(B, 10, dtype=torch.float64).pin_memory()
     h_trt = torch.zeros(B, N_SAVE_E2E, dtype=torch.float64).pin_memory()
     h_trV = torch.zeros(B, N_SAVE_E2E, dtype=torch.float64).pin_memory()
     h_trn = torch.zeros(B, dtype=torch.int32).pin_memory()
@@ -228,7 +228,7 @@ def main():
     def step_e2e():
         _lib.check(L.plb_simulate(h, B, h_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(b),
                                   h_soc0.data_ptr(), h_Y.data_ptr(), None, h_SOC.data_ptr(), h_t.data_ptr(),
-                                  h_sum.data_ptr(), N_SAVE_E2E, h_trt.data_ptr(), h_trV.data_ptr(), None, None,
+                                  h_sum.data_ptr(), N_SAVE_E2E, h_trt.data_ptr(), h_trV.data_ptr(), None, None, None,
                                   h_trn.data_ptr(), 0))
 
     h2d = h_theta.numel() * 8 + h_soc0.numel() * 8
@@ -254,7 +254,7 @@ def main():
         run_mid = _lib.Run(0, 0, -1.0, 1800.0, 1, 0)
         _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run_mid), None, C.byref(o), C.byref(b),
                                   d_soc0.data_ptr(), d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(),
-                                  d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, d_trn.data_ptr(), 1))
+                                  d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, None, d_trn.data_ptr(), 1))
         nnz = L.plb_jac_nnz(h, 0)
         d_res = torch.empty(B, N, **f64); d_nz = torch.empty(B, nnz, **f64)
         d_gam = torch.full((B,), 0.05, **f64)

@@ -29,7 +29,8 @@ enum { PLB_MEM_HOST = 0, PLB_MEM_DEVICE = 1 };                /* where the calle
 typedef struct {
     int cathode;
     int N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n;
-    int temperature; /* 0: isothermal (built).  1: not built yet -> plb_create fails loudly */
+    int temperature; /* 0: isothermal.  1: temperature=true (LCO only: NMC has no thermal parameters;
+                        needs N_p, N_n >= 5 and N_a + N_z <= N_p + N_s + N_n)                  */
     int aging;       /* 0: none (built).        1 (:SEI): not built yet                     */
     int device;      /* CUDA device ordinal */
 } plb_model_desc;
@@ -62,9 +63,11 @@ typedef struct {
         c_e_min, dfilm_max;
 } plb_bounds;
 
-/* per-system summary record (64 bytes) */
+/* per-system summary record (80 bytes) */
 typedef struct {
     double t_end, V_end, I_end, SOC_end;
+    double T_end;      /* temperature_weighting(T) of the final state [K] (T0 for isothermal models) */
+    double aux_end;    /* reserved (0) */
     int flag;          /* run.info.flag: 0 tf, 1 V_min, 2 V_max, 3 SOC_min, 4 SOC_max, 5 T_max, 6 c_s_n,
                           7 I_max, 8 I_min, 9 c_e_min, 10 dfilm, 11 eta_plating; <0 hard failure */
     int n_steps;       /* accepted integrator steps */
@@ -124,19 +127,33 @@ int plb_newton_init(plb_handle h, int B, double *Y, double *YP, const double *th
                     const plb_run *run, const double *values, const plb_opts *opts, int *status,
                     int mem);
 
+/* KLU's role inside IDA (model_evaluation.jl:265-271, 417-428): evaluate J = dF/dY + gamma dF/dY' at
+ * (Y, Y'), factorise it with the structured solver the integrator uses, and solve J x = rhs.
+ * All arrays [B x N] in the reference state order; gamma[B]; status[B] (optional) 0 ok / -1 singular. */
+int plb_linear_solve(plb_handle h, int B, const double *Y, const double *YP, const double *gamma,
+                     const double *theta, const plb_run *run, const double *values,
+                     const double *rhs, double *x, int *status, int mem);
+
 /* simulate(p, tf; I|V|P=..., SOC, bounds..., opts...) / simulate!(sol, p, ...):
  * replaces initialize_simulation! + IDA + solve! + exit_simulation!
  * (model_evaluation.jl:10-97, 174-382; checks.jl:1-249; save_outputs.jl:11-40).
  *   soc0[B]                      initial SOC (new runs)
  *   state_Y[BxN], state_YP[BxN], state_SOC[B], state_t[B]   continuation state, in/out
  *   summary[B]
- *   traj_*[B x n_save_max] (optional, may be NULL; n_save_max may be 0), traj_n[B]
+ *   traj_*[B x n_save_max] (optional, may be NULL; n_save_max may be 0), traj_n[B];
+ *   traj_T = temperature_weighting(T) per saved step (thermal models; T0 otherwise)
  */
 int plb_simulate(plb_handle h, int B, const double *theta, const plb_run *run,
                  const double *values, const plb_opts *opts, const plb_bounds *bounds,
                  const double *soc0, double *state_Y, double *state_YP, double *state_SOC,
                  double *state_t, plb_summary *summary, int n_save_max, double *traj_t,
-                 double *traj_V, double *traj_I, double *traj_SOC, int *traj_n, int mem);
+                 double *traj_V, double *traj_I, double *traj_SOC, double *traj_T, int *traj_n,
+                 int mem);
+
+/* diagnostic: launch geometry of a compiled model family (temperature 0/1): out[8] = {integrator warps
+ * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared
+ * memory per CTA [B], workspace vector stride, Jacobian slots per lane}.  Needs no GPU. */
+int plb_variant_info(int temperature, long long *out);
 
 /* kernel launch counter (number of CUDA kernels this handle has launched) */
 long long plb_launch_count(plb_handle h);

@@ -17,8 +17,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("plb_kernels.cu", "plb_device.cuh", "plb_integrator.cuh",
-                                            "plb_tick.cuh", "laws_generated.cuh")]
+    units = ("plb_kernels.cu", "plb_variant_iso.cu", "plb_variant_th.cu")
+    srcs = [os.path.join(CSRC, f) for f in units + ("plb_common.cuh", "plb_variant.cuh", "plb_device.cuh",
+                                                    "plb_integrator.cuh", "plb_tick.cuh", "laws_generated.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))
     gen = os.path.join(CSRC, "laws_generated.cuh")
     if not os.path.exists(gen):
@@ -27,9 +28,17 @@ def build(force=False, verbose=False):
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "plb_kernels.cu")]
-    subprocess.check_call(cmd)
+    # one translation unit per model family (isothermal / thermal) + the host ABI, compiled in parallel
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    objs, procs = [], []
+    for u in units:
+        o = os.path.join(CSRC, u[:-3] + ".o")
+        objs.append(o)
+        procs.append(subprocess.Popen([nvcc] + flags + ["-c", "-o", o, os.path.join(CSRC, u)]))
+    for p_ in procs:
+        if p_.wait() != 0:
+            raise subprocess.CalledProcessError(p_.returncode, p_.args)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
@@ -56,19 +65,20 @@ class Bounds(C.Structure):
 
 class Summary(C.Structure):
     _fields_ = [("t_end", C.c_double), ("V_end", C.c_double), ("I_end", C.c_double),
-                ("SOC_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int), ("n_res", C.c_int),
+                ("SOC_end", C.c_double), ("T_end", C.c_double), ("aux_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int), ("n_res", C.c_int),
                 ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int), ("n_newton_init", C.c_int),
                 ("reserved", C.c_int)]
 
 
-SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", "f8"), ("flag", "i4"),
+SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", "f8"), ("T_end", "f8"),
+                 ("aux_end", "f8"), ("flag", "i4"),
                  ("n_steps", "i4"), ("n_res", "i4"), ("n_jac", "i4"), ("n_netf", "i4"), ("n_ncfn", "i4"),
                  ("n_newton_init", "i4"), ("reserved", "i4")]
 
 EXPORTS = ["plb_last_error", "plb_create", "plb_destroy", "plb_set_stream", "plb_nstates", "plb_ndiff",
            "plb_ntheta", "plb_jac_nnz", "plb_theta_keys", "plb_theta_index", "plb_theta_defaults",
            "plb_bounds_defaults", "plb_opts_defaults", "plb_calc_I1C", "plb_jac_pattern",
-           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_simulate", "plb_launch_count",
+           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_variant_info", "plb_launch_count",
            "plb_last_kernel_ms"]
 
 _lib = None
@@ -101,8 +111,9 @@ def lib():
         L.plb_initial_guess.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int]
         L.plb_resjac.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.POINTER(Run), dp, dp, dp, C.c_int]
         L.plb_newton_init.argtypes = [vp, C.c_int, dp, dp, dp, C.POINTER(Run), dp, C.POINTER(Opts), vp, C.c_int]
+        L.plb_linear_solve.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.POINTER(Run), dp, dp, dp, vp, C.c_int]
         L.plb_simulate.argtypes = [vp, C.c_int, dp, C.POINTER(Run), dp, C.POINTER(Opts), C.POINTER(Bounds),
-                                   dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, vp, C.c_int]
+                                   dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, vp, C.c_int]
         L.plb_launch_count.argtypes = [vp]
         L.plb_launch_count.restype = C.c_longlong
         L.plb_last_kernel_ms.argtypes = [vp]

@@ -163,12 +163,30 @@ class Model:
                                      vals.ctypes.data, C.byref(o), st.ctypes.data, 0))
         return st, Y, YP
 
+    def linear_solve(self, Y, YP, gamma, rhs, method="I", value=0.0, theta=None):
+        """x = (dF/dY + gamma dF/dY')^{-1} rhs with the integrator's structured factorisation (KLU's role)."""
+        L = _lib.lib()
+        Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
+        YP = np.ascontiguousarray(np.atleast_2d(YP), dtype=np.float64)
+        rhs = np.ascontiguousarray(np.atleast_2d(rhs), dtype=np.float64)
+        B = Y.shape[0]
+        th = self.theta_matrix(B) if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gamma, dtype=np.float64), (B,)))
+        vals = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (B,)))
+        run = _lib.Run(METHODS[method], 0, 0.0, 1e6, 1, 0)
+        x = np.zeros_like(Y)
+        st = np.zeros(B, dtype=np.int32)
+        _lib.check(L.plb_linear_solve(self._h, B, Y.ctypes.data, YP.ctypes.data, g.ctypes.data, th.ctypes.data,
+                                      C.byref(run), vals.ctypes.data, rhs.ctypes.data, x.ctypes.data,
+                                      st.ctypes.data, 0))
+        return x, st
+
 
 class Solution:
     """`sol`: per-system trajectories t, V, I, SOC [B, n] (+ n_points), final state Y, results list."""
 
     def __init__(self):
-        self.t = self.V = self.I = self.SOC = None
+        self.t = self.V = self.I = self.SOC = self.T = None
         self.n_points = None
         self.Y = self.YP = None
         self._SOC_end = self._t_end = None
@@ -270,25 +288,26 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
         soc0 = None
     ns = p.opts.n_save_max if n_save_max is None else n_save_max
     summ = np.zeros(B, dtype=_lib.SUMMARY_DTYPE)
-    tr = {k: np.full((B, max(ns, 1)), np.nan) for k in ("t", "V", "I", "SOC")}
+    tr = {k: np.full((B, max(ns, 1)), np.nan) for k in ("t", "V", "I", "SOC", "T")}
     trn = np.zeros(B, dtype=np.int32)
     _lib.check(L.plb_simulate(p._h, B, th.ctypes.data, C.byref(run), None if vals is None else vals.ctypes.data,
                               C.byref(o), C.byref(bounds), None if soc0 is None else soc0.ctypes.data,
                               sY.ctypes.data, sYP.ctypes.data, sSOC.ctypes.data, st.ctypes.data,
                               summ.ctypes.data, ns, tr["t"].ctypes.data if ns else None,
                               tr["V"].ctypes.data if ns else None, tr["I"].ctypes.data if ns else None,
-                              tr["SOC"].ctypes.data if ns else None, trn.ctypes.data, 0))
+                              tr["SOC"].ctypes.data if ns else None, tr["T"].ctypes.data if ns else None,
+                              trn.ctypes.data, 0))
     hard = summ["flag"] < 0
     if B == 1 and hard[0]:
         # the reference throws for a single simulation (model_evaluation.jl:456, checks.jl:233-239)
         raise RuntimeError(HARD_FAILURES.get(int(summ["flag"][0]), "simulation failed"))
     sol.Y, sol.YP, sol._SOC_end, sol._t_end = sY, sYP, sSOC, st
     if sol.t is None or new_run:
-        sol.t, sol.V, sol.I, sol.SOC, sol.n_points = tr["t"], tr["V"], tr["I"], tr["SOC"], trn.copy()
+        sol.t, sol.V, sol.I, sol.SOC, sol.T, sol.n_points = tr["t"], tr["V"], tr["I"], tr["SOC"], tr["T"], trn.copy()
     else:
         # append the new run's rows after the existing ones (per system)
         width = int((sol.n_points + trn).max())
-        for k in ("t", "V", "I", "SOC"):
+        for k in ("t", "V", "I", "SOC", "T"):
             old = getattr(sol, k)
             new = np.full((B, width), np.nan)
             for s in range(B):

@@ -11,51 +11,36 @@
 //   physics behind them: physics_equations/residuals.jl:6-106 (c_e), 128-180 (c_s Fickian FD),
 //     491-517 (j), 554-654 (Phi_e), 656-703 (Phi_s); auxiliary_states_and_coefficients.jl:6-52
 //   KLU factor/solve inside IDA and newtons_method!            model_evaluation.jl:265-271, 417-452
+//
+// This header is compiled twice (plb_variant_iso.cu: PLB_TH=0, namespace plb::iso; plb_variant_th.cu:
+// PLB_TH=1, namespace plb::th).  With PLB_TH=1 the temperature is a state (temperature = true,
+// residuals_T!: residuals.jl:299-489, build_heat_generation_rates!: auxiliary_states_and_coefficients.jl:
+// 344-518): every lane also owns T of its node, lanes 0..Na-1 / Nx-Nz..Nx-1 own one current-collector
+// node each, and the node blocks of the Newton matrix are 4x4 (c_e, Phi_e, Phi_s, T).
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
+#include "plb_common.cuh"
 #include "laws_generated.cuh"
 
+#ifndef PLB_TH
+#error "define PLB_TH (0/1) and PLB_NS before including the variant headers"
+#endif
+
 namespace plb {
+namespace PLB_NS {
 
-constexpr double kF = 96485.3321233;     // const_Faradays,  structures.jl:10
-constexpr double kR = 8.31446261815324;  // const_Ideal_Gas, structures.jl:11
-constexpr double kTref = 298.15;
+constexpr bool TH = PLB_TH != 0;
 constexpr int NR = laws::NR;
-constexpr unsigned FULL = 0xffffffffu;
-
-enum { CHEM_LCO = 0, CHEM_NMC = 1 };
-enum { METHOD_I = 0, METHOD_V = 1, METHOD_P = 2 };
-
-// canonical parameter fields used by the isothermal model (ASCII names of the reference keys)
-enum ThetaField {
-    TF_D_n, TF_D_p, TF_D_s, TF_D_sn, TF_D_sp, TF_Ea_D_sn, TF_Ea_D_sp, TF_Ea_k_n, TF_Ea_k_p,
-    TF_Rp_n, TF_Rp_p, TF_T0, TF_brugg_n, TF_brugg_p, TF_brugg_s, TF_c_e0, TF_c_max_n, TF_c_max_p,
-    TF_k_n, TF_k_p, TF_l_n, TF_l_p, TF_l_s, TF_t_plus, TF_theta_max_n, TF_theta_max_p,
-    TF_theta_min_n, TF_theta_min_p, TF_sigma_n, TF_sigma_p, TF_eps_fn, TF_eps_fp, TF_eps_n,
-    TF_eps_p, TF_eps_s, TF_COUNT
-};
-
-// model descriptor (by value into kernels)
-struct ModelDesc {
-    int Np, Ns, Nn, Nx, Ne;      // nodes per section, Nx = Np+Ns+Nn <= 32, Ne = Np+Nn
-    int chem;                    // CHEM_*
-    int ntheta;                  // length of one theta row (reference order, used keys only)
-    int theta_stride;            // row stride in doubles
-    // reference layout offsets (external.jl:275-365): c_e | c_s (particle-major) | j | Phi_e | Phi_s | I
-    int off_cs, off_j, off_pe, off_ps, off_I, N_diff, N_tot;
-    int8_t slot[TF_COUNT];       // theta field -> position in the row (-1: not a key of this variant)
-};
 
 // ------------------------------------------------------------------------------------------------
 // per-warp shared-memory constants derived from theta once per system
 // ------------------------------------------------------------------------------------------------
 enum SecField {
     SC_h, SC_inv_h, SC_inv_por, SC_pb, SC_Dlin, SC_src_ce, SC_hFa, SC_psf, SC_kap, SC_inv_Rp,
-    SC_Rp_Ds, SC_k2, SC_cmax, SC_inv_cmax, SC_COUNT
+    SC_Rp_Ds, SC_k2, SC_cmax, SC_inv_cmax,
+    // thermal: 1/(rho Cp), F a, sigma_eff, Ea_D/R, Ea_k/R   (SC_kap, SC_Rp_Ds, SC_k2 are then the values at T_ref)
+    SC_irc, SC_Fa, SC_sig, SC_EaD, SC_Eak, SC_COUNT
 };
-enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_COUNT };
+enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_Tamb, GC_COUNT };
 
 struct WarpConst {
     double sec[SC_COUNT][4];   // [field][section p,s,n,pad]
@@ -63,6 +48,14 @@ struct WarpConst {
     double dinv[32];           // 1 / (centre distance across face x|x+1)
     double beta[32];           // harmonic-mean weight of face x|x+1
     double theta[TF_COUNT + 1];
+#if PLB_TH
+    // heat conduction (residuals.jl:299-446): coefficients of T[x-1]-T[x] and T[x+1]-T[x] in the T row of
+    // node x, already divided by h*rho*Cp; same for this lane's current-collector node (xL, xR), its
+    // convective boundary term xbc*(T_amb - T) and its Joule term xq*I^2
+    double tL[32], tR[32], xL[32], xR[32], xbc[32], xq[32];
+    double cinv[32];           // 1 / (distance between the centres of nodes x-1 and x+1)
+    double s5[3][8];           // h, lambda, rho*Cp of the five sections a,p,s,n,z
+#endif
 };
 
 struct LaneRole {
@@ -70,6 +63,8 @@ struct LaneRole {
     int sec;      // 0 p, 1 s, 2 n, 3 inactive
     int e;        // electrode index (p: x, n: x-Ns), -1 otherwise
     bool act, elec, first_e, last_e;   // first/last node of its electrode
+    bool cha, chz;                     // owns a node of the positive / negative current collector (thermal)
+    int ix;                            // offset of that node inside the T block, -1 otherwise
 };
 
 __device__ __forceinline__ LaneRole make_role(const ModelDesc& m, int lane) {
@@ -81,12 +76,17 @@ __device__ __forceinline__ LaneRole make_role(const ModelDesc& m, int lane) {
     r.e = r.sec == 0 ? lane : (r.sec == 2 ? lane - m.Ns : -1);
     r.first_e = (r.sec == 0 && lane == 0) || (r.sec == 2 && lane == m.Np + m.Ns);
     r.last_e = (r.sec == 0 && lane == m.Np - 1) || (r.sec == 2 && lane == m.Nx - 1);
+    r.cha = TH && lane < m.Na;
+    r.chz = TH && lane >= m.Nx - m.Nz && lane < m.Nx;
+    r.ix = r.cha ? lane : (r.chz ? m.Na + m.Nx + (lane - (m.Nx - m.Nz)) : -1);
     return r;
 }
 
-// one node's unknowns held in registers
+// one node's unknowns held in registers (T: temperature of the node, Tx: of this lane's current-
+// collector node; both only exist in the thermal variant)
 struct LaneVec {
     double ce, cs[NR], j, pe, ps;
+    double T, Tx;
 };
 
 __device__ __forceinline__ double shfl_dn(double v) { return __shfl_down_sync(FULL, v, 1); }
@@ -136,7 +136,7 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         const bool Tref = (T == kTref);   // temperature_switch, custom_functions.jl:1
         double Ds = s == 0 ? th[TF_D_sp] : th[TF_D_sn];
         double k = s == 0 ? th[TF_k_p] : th[TF_k_n];
-        if (!Tref && s != 1) {            // D_s_eff / rxn_rate Arrhenius, custom_functions.jl:16-57
+        if (!TH && !Tref && s != 1) {     // D_s_eff / rxn_rate Arrhenius, custom_functions.jl:16-57
             const double EaD = s == 0 ? th[TF_Ea_D_sp] : th[TF_Ea_D_sn];
             const double Eak = s == 0 ? th[TF_Ea_k_p] : th[TF_Ea_k_n];
             Ds = Ds * exp(-EaD / kR * (1.0 / T - 1.0 / kTref));
@@ -157,6 +157,15 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         C.sec[SC_k2][s] = s == 1 ? 0.0 : 2.0 * k;
         C.sec[SC_cmax][s] = cmax;
         C.sec[SC_inv_cmax][s] = 1.0 / cmax;
+        if (TH) {
+            const double rho = s == 0 ? th[TF_rho_p] : (s == 1 ? th[TF_rho_s] : th[TF_rho_n]);
+            const double Cp = s == 0 ? th[TF_Cp_p] : (s == 1 ? th[TF_Cp_s] : th[TF_Cp_n]);
+            C.sec[SC_irc][s] = 1.0 / (rho * Cp);
+            C.sec[SC_Fa][s] = kF * a;
+            C.sec[SC_sig][s] = s == 1 ? 0.0 : sig;
+            C.sec[SC_EaD][s] = s == 1 ? 0.0 : (s == 0 ? th[TF_Ea_D_sp] : th[TF_Ea_D_sn]) / kR;
+            C.sec[SC_Eak][s] = s == 1 ? 0.0 : (s == 0 ? th[TF_Ea_k_p] : th[TF_Ea_k_n]) / kR;
+        }
         if (s == 0) {
             const double I1C = calc_I1C(th);
             C.g[GC_T] = T;
@@ -164,7 +173,8 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
             C.g[GC_Kc] = 2 * kR * (1 - th[TF_t_plus]) / kF;
             C.g[GC_I1C] = I1C;
             C.g[GC_psI_p] = I1C * h / sig;     // d res_Phi_s[first p] / dI   (residuals.jl:679)
-            C.g[GC_dUdT_on] = (m.chem == CHEM_LCO && !Tref) ? 1.0 : 0.0;
+            C.g[GC_dUdT_on] = (m.chem == CHEM_LCO && (TH || !Tref)) ? 1.0 : 0.0;
+            if (TH) C.g[GC_Tamb] = th[TF_T_amb];
         }
         if (s == 2) C.g[GC_psI_n] = -calc_I1C(th) * h / sig;   // d res_Phi_s[last n] / dI (residuals.jl:680)
     }
@@ -183,6 +193,63 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         C.beta[lane] = b;
     }
     __syncwarp();
+#if PLB_TH
+    // ---- heat conduction coefficients, residuals.jl:299-446 (five sections a | p | s | n | z) -------
+    if (lane < 5) {
+        const int q = lane;
+        const double l = q == 0 ? th[TF_l_a] : (q == 4 ? th[TF_l_z] : C.sec[SC_h][q - 1]);
+        const int n = q == 0 ? m.Na : m.Nz;
+        C.s5[0][q] = (q == 0 || q == 4) ? (1.0 / n) * l : l;
+        C.s5[1][q] = q == 0 ? th[TF_lambda_a] : (q == 1 ? th[TF_lambda_p] : (q == 2 ? th[TF_lambda_s] : (q == 3 ? th[TF_lambda_n] : th[TF_lambda_z])));
+        C.s5[2][q] = q == 0 ? th[TF_rho_a] * th[TF_Cp_a] : (q == 4 ? th[TF_rho_z] * th[TF_Cp_z] : 1.0 / C.sec[SC_irc][q - 1]);
+    }
+    __syncwarp();
+    {
+        // conductance between the centres of two adjacent cells: lambda/h inside a section, harmonic-mean
+        // lambda over the centre distance across an interface (residuals.jl:363-446)
+        auto cond = [&](int qa, int qb) -> double {
+            const double ha = C.s5[0][qa], hb = C.s5[0][qb], la = C.s5[1][qa], lb = C.s5[1][qb];
+            if (qa == qb) return la / ha;
+            const double be = (ha / 2) / (ha / 2 + hb / 2);
+            const double lm = la * lb / (be * lb + (1.0 - be) * la);
+            return lm / (ha / 2 + hb / 2);
+        };
+        const int x = lane;
+        auto sec5 = [&](int xx) -> int { return xx < 0 ? 0 : (xx < m.Np ? 1 : (xx < m.Np + m.Ns ? 2 : (xx < m.Nx ? 3 : 4))); };
+        double tL = 0.0, tR = 0.0;
+        if (x < m.Nx) {
+            const int q = sec5(x);
+            const double sc = 1.0 / (C.s5[0][q] * C.s5[2][q]);
+            tL = cond(sec5(x - 1), q) * sc;
+            tR = cond(q, sec5(x + 1)) * sc;
+        }
+        C.tL[lane] = tL; C.tR[lane] = tR;
+        double xL = 0.0, xR = 0.0, xbc = 0.0, xq = 0.0;
+        const double I1C = C.g[GC_I1C];
+        if (lane < m.Na) {
+            const int k = lane;
+            const double sc = 1.0 / (C.s5[0][0] * C.s5[2][0]);
+            xL = k > 0 ? cond(0, 0) * sc : 0.0;
+            xR = (k < m.Na - 1 ? cond(0, 0) : cond(0, 1)) * sc;
+            xbc = k == 0 ? th[TF_h_cell] * sc : 0.0;                       // T_BC_sx, residuals.jl:318
+            xq = I1C * I1C / (th[TF_sigma_a] * C.s5[2][0]);                // residuals.jl:461
+        } else if (lane >= m.Nx - m.Nz && lane < m.Nx) {
+            const int k = lane - (m.Nx - m.Nz);
+            const double sc = 1.0 / (C.s5[0][4] * C.s5[2][4]);
+            xL = (k > 0 ? cond(4, 4) : cond(3, 4)) * sc;
+            xR = k < m.Nz - 1 ? cond(4, 4) * sc : 0.0;
+            xbc = k == m.Nz - 1 ? th[TF_h_cell] * sc : 0.0;               // T_BC_dx, residuals.jl:319
+            xq = I1C * I1C / (th[TF_sigma_z] * C.s5[2][4]);                // residuals.jl:465
+        }
+        C.xL[lane] = xL; C.xR[lane] = xR; C.xbc[lane] = xbc; C.xq[lane] = xq;
+        // central differences of thermal_derivatives (auxiliary_states_and_coefficients.jl:363-486):
+        // (f[x+1]-f[x-1]) / (distance between the two centres), also across the section interfaces
+        double ci = 0.0;
+        if (x > 0 && x < m.Nx - 1) ci = 1.0 / (1.0 / C.dinv[x - 1] + 1.0 / C.dinv[x]);
+        C.cinv[lane] = ci;
+    }
+    __syncwarp();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,6 +266,15 @@ struct LaneJac {
     double psL, psD, psU, ps_j, ps_I;
     // particle: block = kap*MC - cj*I ; surface-row d/dj
     double kap, cs_j;
+#if PLB_TH
+    // temperature columns of the c_s, j and Phi_e rows
+    double csT[NR], j_T, peTL, peTD, peTU;
+    // T row of the node: conduction (T_TD without the -cj term), d/dj, d/d cs_surf, and the stencils of
+    // thermal_derivatives over nodes x-2..x+2 (index 2 = own node) for c_e, Phi_e, Phi_s
+    double T_TL, T_TD, T_TU, T_j, T_cs, T_ce[5], T_pe[5], T_ps[5];
+    // this lane's current-collector node: tridiagonal (Tx_D without -cj) and d/dI
+    double Tx_L, Tx_D, Tx_U, Tx_I;
+#endif
 };
 
 // Control row (scalar_residual.jl:167-202): residual and its three possible Jacobian entries
@@ -212,13 +288,14 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
                                           int method, double value, LaneVec& res, CtrlRow& ctrl,
                                           LaneJac& J) {
     const int s = ro.sec < 3 ? ro.sec : 1;
-    const double T = C.g[GC_T];
+    const double T = TH ? (ro.act ? y.T : kTref) : C.g[GC_T];
     // ---- node-local electrolyte properties: build_K_eff!/build_D_eff! (:302-328) -----------------
-    double K = 0.0, dK = 0.0, D = 0.0, dD = 0.0;
+    double K = 0.0, dK = 0.0, D = 0.0, dD = 0.0, dKT = 0.0;
     const double ce = ro.act ? y.ce : 1000.0;
     {
         const double pb = C.sec[SC_pb][s];
-        laws::K_eff(ce, T, K, dK);
+        if (TH) { laws::K_eff_T(ce, T, K, dK, dKT); dKT *= pb; }
+        else laws::K_eff(ce, T, K, dK);
         K *= pb; dK *= pb;
         if (CHEM == CHEM_LCO) { D = C.sec[SC_Dlin][s]; dD = 0.0; }   // D_eff_linear
         else { laws::D_eff_nl(ce, T, D, dD); D *= pb; dD *= pb; }
@@ -230,6 +307,9 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     const double b = C.beta[ro.x], dinv = C.dinv[ro.x];
     double Nf = 0.0, Q = 0.0;
     double dN_cL = 0.0, dN_cR = 0.0, dQ_cL = 0.0, dQ_cR = 0.0, wK = 0.0;
+    double dQ_TL = 0.0, dQ_TR = 0.0;
+    double TRn = T, dKTR = 0.0;
+    if (TH) { TRn = shfl_dn(T); dKTR = shfl_dn(dKT); }
     if (has_face) {
         const double denK = b * KR + (1.0 - b) * K;
         const double Khat = K * KR / denK;                          // interpolate_electrolyte_grid
@@ -237,7 +317,8 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         const double Dhat = D * DR / denD;
         const double denc = b * ceR + (1.0 - b) * ce;
         const double cbar = ce * ceR / denc;                        // interpolate_electrolyte_concentration
-        const double Tbar = T * T / (b * T + (1.0 - b) * T);        // interpolate_temperature
+        const double denT = b * TRn + (1.0 - b) * T;
+        const double Tbar = T * TRn / denT;                         // interpolate_temperature
         const double dc = (ceR - ce) * dinv;                        // ..._concetration_fluxes
         const double G = Khat * Tbar * dc / cbar;                   // prod_tot, residuals.jl:631-635
         wK = Khat * dinv;
@@ -255,17 +336,39 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
             dQ_cR = dKh_cR * dinv * (peR - y.pe) - C.g[GC_Kc] * dG_cR;
             dN_cL = -Dhat * dinv + dDh_cL * dc;
             dN_cR = Dhat * dinv + dDh_cR * dc;
+            if (TH) {
+                const double iT2 = 1.0 / (denT * denT);
+                const double dKh_TL = b * KR * KR * iK2 * dKT, dKh_TR = (1.0 - b) * K * K * iK2 * dKTR;
+                const double dTb_TL = b * TRn * TRn * iT2, dTb_TR = (1.0 - b) * T * T * iT2;
+                const double dcc = dc * icb;
+                dQ_TL = dKh_TL * dinv * (peR - y.pe) - C.g[GC_Kc] * dcc * (dKh_TL * Tbar + Khat * dTb_TL);
+                dQ_TR = dKh_TR * dinv * (peR - y.pe) - C.g[GC_Kc] * dcc * (dKh_TR * Tbar + Khat * dTb_TR);
+            }
         }
     }
     // left face x-1|x comes from lane x-1
     double NfL = shfl_up(Nf), QL = shfl_up(Q), wKL = shfl_up(wK);
     double dNL_cL = 0.0, dNL_cR = 0.0, dQL_cL = 0.0, dQL_cR = 0.0;
+    double dQL_TL = 0.0, dQL_TR = 0.0;
     if (WITH_JAC) { dNL_cL = shfl_up(dN_cL); dNL_cR = shfl_up(dN_cR); dQL_cL = shfl_up(dQ_cL); dQL_cR = shfl_up(dQ_cR); }
-    if (ro.x == 0) { NfL = 0.0; QL = 0.0; wKL = 0.0; dNL_cL = dNL_cR = dQL_cL = dQL_cR = 0.0; }
+    if (WITH_JAC && TH) { dQL_TL = shfl_up(dQ_TL); dQL_TR = shfl_up(dQ_TR); }
+    if (ro.x == 0) { NfL = 0.0; QL = 0.0; wKL = 0.0; dNL_cL = dNL_cR = dQL_cL = dQL_cR = 0.0; dQL_TL = dQL_TR = 0.0; }
 
     // ---- electrode-node quantities ------------------------------------------------------------------
     double jtot = 0.0, jcalc = 0.0;
-    double dj_cs = 0.0, dj_ce = 0.0, dj_eta = 0.0;
+    double dj_cs = 0.0, dj_ce = 0.0, dj_eta = 0.0, dj_T = 0.0;
+    // thermal: Arrhenius factors of D_s_eff / rxn_rate at the node temperature (custom_functions.jl:16-57),
+    // surface OCV data for the heat sources
+    double kapx = C.sec[SC_kap][s], k2x = C.sec[SC_k2][s], xco = C.g[GC_xcoef], RpDs = C.sec[SC_Rp_Ds][s];
+    double dkapT = 0.0, eta_h = 0.0, dUdT_h = 0.0, ddUdT_h = 0.0, dUtot_h = 0.0;
+    if (TH && ro.elec) {
+        const double iT = 1.0 / T;
+        const double dre = iT - 1.0 / kTref;
+        const double aD = exp(-C.sec[SC_EaD][s] * dre), ak = exp(-C.sec[SC_Eak][s] * dre);
+        kapx *= aD; RpDs /= aD; k2x *= ak;
+        dkapT = kapx * C.sec[SC_EaD][s] * iT * iT;
+        xco = 0.5 * kF / (kR * T);
+    }
     if (ro.elec) {
         jtot = y.j;                                                          // build_j_total!
         const double cs_s = y.cs[NR - 1];                                    // build_c_s_star!
@@ -288,17 +391,23 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         const double cmax = C.sec[SC_cmax][s];
         const double arg = ce * cs_s * (cmax - cs_s);
         const double sq = arg > 0.0 ? sqrt(arg) : 0.0;                       // sqrt_ReLU
-        const double xx = C.g[GC_xcoef] * eta;
+        const double xx = xco * eta;
         const double em = expm1(xx);
         const double sh = 0.5 * (em + em / (em + 1.0));                      // sinh(xx)
-        const double k2 = C.sec[SC_k2][s];
+        const double k2 = k2x;
         jcalc = k2 * sq * sh;
+        if (TH) { eta_h = eta; dUdT_h = dUdT; ddUdT_h = ddUdT; dUtot_h = dU; }
         if (WITH_JAC) {
             const double ch = sh + 1.0 / (em + 1.0);                         // cosh = sinh + exp(-x)
             const double isq = arg > 0.0 ? 0.5 / sq : 0.0;
-            dj_eta = k2 * sq * ch * C.g[GC_xcoef];
+            dj_eta = k2 * sq * ch * xco;
             dj_ce = k2 * sh * isq * cs_s * (cmax - cs_s);
             dj_cs = k2 * sh * isq * ce * (cmax - 2.0 * cs_s) - dj_eta * dU * C.sec[SC_inv_cmax][s];
+            if (TH) {
+                // d/dT: k(T), eta(T) through U = U0 + dUdT (T - Tref), and the 1/T in the sinh argument
+                const double iT = 1.0 / T;
+                dj_T = jcalc * C.sec[SC_Eak][s] * iT * iT + k2 * sq * ch * (-xco * dUdT - xx * iT);
+            }
         }
     }
 
@@ -312,14 +421,17 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     // ---- residuals_j!, residuals.jl:491-517 ; residuals_Phi_s!, residuals.jl:656-703 ----------------
     const double psL = shfl_up(y.ps), psR = shfl_dn(y.ps);
     if (ro.elec) {
-        const double kap = C.sec[SC_kap][s];
-        const double d1bc = -y.j * C.sec[SC_Rp_Ds][s];
+        const double kap = kapx;
+        const double d1bc = -y.j * RpDs;
 #pragma unroll
         for (int r = 0; r < NR; r++) {
             double acc = 0.0;
 #pragma unroll
             for (int c = 0; c < NR; c++)
                 if (laws::mc_mask(r) & (1u << c)) acc = fma(laws::MC[r][c], y.cs[c], acc);
+#if PLB_TH
+            if (WITH_JAC) J.csT[r] = dkapT * acc;     // kap*BJ*d1bc = -BJ*j/Rp does not depend on T
+#endif
             if (r == NR - 1) acc = fma(laws::BJ, d1bc, acc);
             res.cs[r] = kap * acc - yp.cs[r];
         }
@@ -336,7 +448,81 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         for (int r = 0; r < NR; r++) res.cs[r] = 0.0;
         res.j = 0.0;
         res.ps = 0.0;
+#if PLB_TH
+        if (WITH_JAC) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) J.csT[r] = 0.0;
+        }
+#endif
     }
+#if PLB_TH
+    // ---- residuals_T!, residuals.jl:299-489; heat sources auxiliary_states_and_coefficients.jl:344-518 --
+    {
+        // thermal_derivatives: one-sided 3-point differences at the outer ends of the cell (c_e, Phi_e) and
+        // of each electrode (Phi_s), central differences elsewhere.  w*[k] multiplies the value at x-2+k.
+        const bool x0 = ro.x == 0, xN = ro.x == m.Nx - 1;
+        const double h2 = 0.5 * C.sec[SC_inv_h][s], ci = C.cinv[ro.x];
+        double we[5], ws[5];
+        we[0] = xN ? h2 : 0.0;
+        we[1] = xN ? -4.0 * h2 : (x0 ? 0.0 : -ci);
+        we[2] = x0 ? -3.0 * h2 : (xN ? 3.0 * h2 : 0.0);
+        we[3] = x0 ? 4.0 * h2 : (xN ? 0.0 : ci);
+        we[4] = x0 ? -h2 : 0.0;
+        ws[0] = (ro.elec && ro.last_e) ? h2 : 0.0;
+        ws[1] = !ro.elec ? 0.0 : (ro.last_e ? -4.0 * h2 : (ro.first_e ? 0.0 : -h2));
+        ws[2] = !ro.elec ? 0.0 : (ro.first_e ? -3.0 * h2 : (ro.last_e ? 3.0 * h2 : 0.0));
+        ws[3] = !ro.elec ? 0.0 : (ro.first_e ? 4.0 * h2 : (ro.last_e ? 0.0 : h2));
+        ws[4] = (ro.elec && ro.first_e) ? -h2 : 0.0;
+        if (!ro.act) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) { we[k] = 0.0; ws[k] = 0.0; }
+        }
+        const double ceL1 = shfl_up(ce), ceL2 = __shfl_up_sync(FULL, ce, 2), ceR2 = __shfl_down_sync(FULL, ce, 2);
+        const double peL1 = shfl_up(y.pe), peL2 = __shfl_up_sync(FULL, y.pe, 2), peR2 = __shfl_down_sync(FULL, y.pe, 2);
+        const double psL2 = __shfl_up_sync(FULL, y.ps, 2), psR2 = __shfl_down_sync(FULL, y.ps, 2);
+        const double dPe = we[0] * peL2 + we[1] * peL1 + we[2] * y.pe + we[3] * peR + we[4] * peR2;
+        const double dCe = we[0] * ceL2 + we[1] * ceL1 + we[2] * ce + we[3] * ceR + we[4] * ceR2;
+        const double dPs = ws[0] * psL2 + ws[1] * psL + ws[2] * y.ps + ws[3] * psR + ws[4] * psR2;
+        const double Kc = C.g[GC_Kc], irc = C.sec[SC_irc][s], Fa = C.sec[SC_Fa][s], sig = C.sec[SC_sig][s];
+        const double ice = 1.0 / ce;
+        const double Qohm = K * dPe * dPe + Kc * K * T * (dCe * ice) * dPe + sig * dPs * dPs;
+        const double Qrr = ro.elec ? Fa * jtot * (T * dUdT_h + eta_h) : 0.0;     // Q_rev + Q_rxn
+        // neighbours of the temperature stencil: the two end nodes talk to the current collectors
+        double TL = shfl_up(T), TR = TRn;
+        const double Ta_last = shfl_from(y.Tx, m.Na - 1), Tz_first = shfl_from(y.Tx, m.Nx - m.Nz);
+        if (x0) TL = Ta_last;
+        if (xN) TR = Tz_first;
+        const double tL = C.tL[ro.x], tR = C.tR[ro.x];
+        res.T = ro.act ? tL * (TL - T) + tR * (TR - T) + irc * (Qohm + Qrr) - yp.T : 0.0;
+        // current-collector node of this lane
+        const double TxU = shfl_up(y.Tx), TxD = shfl_dn(y.Tx);
+        const double T_first = shfl_from(T, 0), T_last = shfl_from(T, m.Nx - 1);
+        double TxL = TxU, TxR = TxD;
+        if (ro.cha && ro.x == m.Na - 1) TxR = T_first;
+        if (ro.chz && ro.x == m.Nx - m.Nz) TxL = T_last;
+        const double xL = C.xL[ro.x], xR = C.xR[ro.x], xbc = C.xbc[ro.x], xq = C.xq[ro.x];
+        res.Tx = (ro.cha || ro.chz)
+                     ? xL * (TxL - y.Tx) + xR * (TxR - y.Tx) + xq * Iapp * Iapp + xbc * (C.g[GC_Tamb] - y.Tx) - yp.Tx
+                     : 0.0;
+        if (WITH_JAC) {
+            J.T_TL = tL; J.T_TU = tR;
+            J.T_TD = -(tL + tR) + irc * (dKT * dPe * dPe + Kc * dPe * (dCe * ice) * (dKT * T + K));
+            J.T_j = ro.elec ? irc * Fa * (T * dUdT_h + eta_h) : 0.0;
+            J.T_cs = ro.elec ? irc * Fa * jtot * (T * ddUdT_h - dUtot_h) * C.sec[SC_inv_cmax][s] : 0.0;
+            const double gpe = irc * (2.0 * K * dPe + Kc * K * T * dCe * ice);
+            const double gce = irc * Kc * K * T * dPe * ice;
+            const double gps = irc * 2.0 * sig * dPs;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { J.T_pe[k] = gpe * we[k]; J.T_ce[k] = gce * we[k]; J.T_ps[k] = gps * ws[k]; }
+            const double src_j = ro.elec ? irc * Fa * jtot : 0.0;      // d(Q_rxn)/d eta
+            J.T_pe[2] -= src_j;
+            J.T_ps[2] += src_j;
+            J.T_ce[2] += irc * (dK * dPe * dPe + Kc * T * dPe * dCe * (dK * ice - K * ice * ice));
+            if (!ro.act) { J.T_TL = 0.0; J.T_TU = 0.0; J.T_TD = 0.0; }
+            J.Tx_L = xL; J.Tx_U = xR; J.Tx_D = -(xL + xR) - xbc; J.Tx_I = 2.0 * xq * Iapp;
+        }
+    }
+#endif
     // ---- control row: scalar_residual!, scalar_residual.jl:167; calc_V/P :86-87 ----------------------
     {
         const double ps0 = shfl_from(y.ps, 0), psN = shfl_from(y.ps, m.Nx - 1);
@@ -368,8 +554,13 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         J.psD = ro.elec ? -((ro.first_e || ro.last_e) ? 1.0 : 2.0) : 1.0;
         J.ps_j = ro.elec ? -C.sec[SC_psf][s] : 0.0;
         J.ps_I = (ro.sec == 0 && ro.first_e) ? C.g[GC_psI_p] : ((ro.sec == 2 && ro.last_e) ? C.g[GC_psI_n] : 0.0);
-        J.kap = C.sec[SC_kap][s];
+        J.kap = kapx;
         J.cs_j = ro.elec ? -laws::BJ * C.sec[SC_inv_Rp][s] : 0.0;
+#if PLB_TH
+        J.j_T = dj_T;
+        if (last) { J.peTL = 0.0; J.peTD = 0.0; J.peTU = 0.0; }
+        else { J.peTL = dQL_TL; J.peTD = dQL_TR - dQ_TL; J.peTU = -dQ_TR; }
+#endif
     }
 }
 
@@ -381,6 +572,7 @@ __device__ __noinline__ void lane_eval_ni(const ModelDesc& m, const WarpConst& C
     lane_eval<CHEM, WITH_JAC>(m, C, ro, y, yp, Iapp, method, value, res, ctrl, J);
 }
 
+#if !PLB_TH
 // ------------------------------------------------------------------------------------------------
 // structured Newton-matrix factorisation / solve
 //   1. particle block (kap*MC - cj I) is identical for every particle of an electrode -> explicit
@@ -691,6 +883,484 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     return dI;
 }
 
+#else   // PLB_TH ===================================================================================
+// ------------------------------------------------------------------------------------------------
+// structured Newton-matrix factorisation / solve, thermal variant (N = 351).  The algebra below is
+// the one prototyped (and checked against dense LAPACK solves of the oracle's Jacobian) in
+// tests/proto_thermal_solver.py:
+//   1. particle block kap(T_x)*MC - cj I differs from node to node (Arrhenius D_s), but MC = EV diag(EL) EVI
+//      is a fixed matrix with a real spectrum, so the block is diagonal in a constant basis: a particle
+//      solve is two constant 10x10 mat-vecs and ten reciprocals kept per node (no per-node LU);
+//   2. c_s and j are eliminated node-locally (T-row included: it sees j and the surface concentration);
+//   3. the current-collector temperature chains (scalar tridiagonal, one node per lane) are folded into
+//      the T-diagonal of the two end nodes;
+//   4. 4x4-block tridiagonal system in (c_e, Phi_e, Phi_s, T): twisted block-Thomas along the lanes.
+//      The T rows of four nodes (the ends of the cell and the inner ends of the electrodes) reach two
+//      nodes away through the one-sided differences of thermal_derivatives; with the twisted ordering
+//      those couplings point either two nodes back (absorbed into the incoming block and the right-hand
+//      side) or, at the chain heads, two nodes ahead (absorbed into the outgoing block of the next node
+//      and into the last back-substitution step) -- exact, no fill outside the block tridiagonal;
+//   5. the applied current is a border, as in the isothermal variant.
+// ------------------------------------------------------------------------------------------------
+struct WarpFactor {
+    double Dinv[16][32], Wm[16][32], Pm[16][32];
+    double Fr[4][32];          // T-row multiplier for the node two behind in the chain
+    double Eo[3][32];          // chain heads: T-row coupling to (c_e, Phi_e, Phi_s) two nodes ahead
+    double z[4][32], zx[32];   // border column solution
+    double q[5][32];           // j elimination: q_ce, q_pe, q_ps, q_T, inv_den
+    double jcs[32];
+    double sj[4][32];          // effective d(row)/dj for rows ce, pe, ps, T
+    double tcs[32];            // T-row coefficient of the surface concentration
+    double pd[NR][32];         // 1 / (kap_x * EL_i - cj)
+    double wT[NR][32];         // EVI * (d res_cs / dT)
+    double csj[32];
+    double chm[32], chip[32], chup[32], hm[32];   // collector chains: multiplier, 1/pivot, successor coupling; end-node multiplier
+    double schur_inv, g_ps0, g_psN, pad;
+};
+
+// 4x4 inverse by the adjugate (2x2 sub-determinants), row-major
+__device__ __forceinline__ void inv4x4(const double* a, double* b) {
+    const double s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+    const double s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+    const double c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+    const double c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const double i = 1.0 / det;
+    b[0] = (a[5] * c5 - a[6] * c4 + a[7] * c3) * i;
+    b[1] = (-a[1] * c5 + a[2] * c4 - a[3] * c3) * i;
+    b[2] = (a[13] * s5 - a[14] * s4 + a[15] * s3) * i;
+    b[3] = (-a[9] * s5 + a[10] * s4 - a[11] * s3) * i;
+    b[4] = (-a[4] * c5 + a[6] * c2 - a[7] * c1) * i;
+    b[5] = (a[0] * c5 - a[2] * c2 + a[3] * c1) * i;
+    b[6] = (-a[12] * s5 + a[14] * s2 - a[15] * s1) * i;
+    b[7] = (a[8] * s5 - a[10] * s2 + a[11] * s1) * i;
+    b[8] = (a[4] * c4 - a[5] * c2 + a[7] * c0) * i;
+    b[9] = (-a[0] * c4 + a[1] * c2 - a[3] * c0) * i;
+    b[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * i;
+    b[11] = (-a[8] * s4 + a[9] * s2 - a[11] * s0) * i;
+    b[12] = (-a[4] * c3 + a[5] * c1 - a[6] * c0) * i;
+    b[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * i;
+    b[14] = (-a[12] * s3 + a[13] * s1 - a[14] * s0) * i;
+    b[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * i;
+}
+
+// chain bookkeeping of one lane for the twisted elimination (meeting node m.mid, inside the separator)
+struct LaneChain {
+    int pred, succ, pred2, succ2;   // one / two nodes back and ahead along this lane's chain
+    int pos;                        // position in the chain (heads 0), -1 for the meeting node / inactive lanes
+    bool is_mid, rightc;
+    int n_in, n_out;                // iterations of the inward / outward sweeps
+    int posA, posB;                 // chain positions of the two inner electrode ends (T rows reaching two back)
+    // current-collector chains
+    int cpred, csucc, ctail;        // chain neighbours; ctail: lane owning the chain node adjacent to this END node
+    bool ch, is_tail;
+    int nch;
+};
+__device__ __forceinline__ LaneChain make_chain(const ModelDesc& m, const LaneRole& ro, int lane) {
+    LaneChain c;
+    const int Nx = m.Nx, mid = m.mid;
+    c.is_mid = lane == mid;
+    const bool left = lane < mid, right = lane > mid && lane < Nx;
+    c.rightc = right;
+    c.pred = left ? (lane > 0 ? lane - 1 : lane) : (right ? (lane < Nx - 1 ? lane + 1 : lane) : (lane == mid ? lane - 1 : lane));
+    c.succ = left ? lane + 1 : (right ? lane - 1 : lane);
+    c.pred2 = left ? (lane > 1 ? lane - 2 : 0) : (right ? (lane < Nx - 2 ? lane + 2 : Nx - 1) : lane);
+    c.succ2 = left ? (lane + 2 < Nx ? lane + 2 : Nx - 1) : (right ? (lane >= 2 ? lane - 2 : 0) : lane);
+    c.pos = left ? lane : (right ? Nx - 1 - lane : -1);
+    const int a = mid - 1, b = Nx - mid - 2;
+    c.n_in = a > b ? a : b;
+    c.n_out = mid > Nx - 1 - mid ? mid : Nx - 1 - mid;
+    c.posA = m.Np - 1;
+    c.posB = m.Nn - 1;
+    c.ch = ro.cha || ro.chz;
+    c.cpred = ro.cha ? (lane > 0 ? lane - 1 : 0) : (lane < 31 ? lane + 1 : 31);
+    c.csucc = ro.cha ? (lane < 31 ? lane + 1 : 31) : (lane > 0 ? lane - 1 : 0);
+    c.is_tail = (ro.cha && lane == m.Na - 1) || (ro.chz && lane == Nx - m.Nz);
+    c.ctail = lane == 0 ? m.Na - 1 : Nx - m.Nz;
+    c.nch = m.Na > m.Nz ? m.Na : m.Nz;
+    return c;
+}
+
+// dense 4x4 (row-major) times 4-vector
+#define PLB_MV4(M, v0, v1, v2, v3, r)                                                  \
+    ((M)[(r) * 4 + 0] * (v0) + (M)[(r) * 4 + 1] * (v1) + (M)[(r) * 4 + 2] * (v2) + (M)[(r) * 4 + 3] * (v3))
+
+// Solve the matrix WITHOUT the border: block right-hand side rb[4] (after the node-local elimination),
+// chain right-hand side rx; returns u[4], ux.  Di/Wm/Pm: this lane's factor blocks in registers.
+__device__ __forceinline__ void core_solve(const ModelDesc& m, const LaneChain& ch, const WarpFactor& Fa,
+                                           const double* Di, const double* Wm, const double* Pm,
+                                           const double* rb, double rx, double* u, double& ux, int lane) {
+    // 1. collector chains, forward
+    const double chm = Fa.chm[lane];
+    double yx = rx;
+#pragma unroll 1
+    for (int it = 0; it < ch.nch - 1; it++) yx = rx - chm * shfl_from(yx, ch.cpred);
+    // 2. fold into the two end nodes
+    double r0 = rb[0], r1 = rb[1], r2 = rb[2], r3 = rb[3] - Fa.hm[lane] * shfl_from(yx, ch.ctail);
+    // 3. twisted block-Thomas, inward
+    const double f0 = Fa.Fr[0][lane], f1 = Fa.Fr[1][lane], f2 = Fa.Fr[2][lane], f3 = Fa.Fr[3][lane];
+    double y0 = r0, y1 = r1, y2 = r2, y3 = r3;
+#pragma unroll 1
+    for (int it = 0; it < ch.n_in; it++) {
+        if (it == ch.posA - 1 || it == ch.posB - 1) {
+            // the T row of an inner electrode end also sees the node two back, final by now
+            const double b0 = shfl_from(y0, ch.pred2), b1 = shfl_from(y1, ch.pred2), b2 = shfl_from(y2, ch.pred2), b3 = shfl_from(y3, ch.pred2);
+            if (ch.pos == it + 1) r3 -= f0 * b0 + f1 * b1 + f2 * b2 + f3 * b3;
+        }
+        const double a0 = shfl_from(y0, ch.pred), a1 = shfl_from(y1, ch.pred), a2 = shfl_from(y2, ch.pred), a3 = shfl_from(y3, ch.pred);
+        y0 = r0 - PLB_MV4(Wm, a0, a1, a2, a3, 0);
+        y1 = r1 - PLB_MV4(Wm, a0, a1, a2, a3, 1);
+        y2 = r2 - PLB_MV4(Wm, a0, a1, a2, a3, 2);
+        y3 = r3 - PLB_MV4(Wm, a0, a1, a2, a3, 3);
+    }
+    {   // the meeting node takes both neighbours
+        const int mid = m.mid;
+        const double a0 = shfl_from(y0, mid - 1), a1 = shfl_from(y1, mid - 1), a2 = shfl_from(y2, mid - 1), a3 = shfl_from(y3, mid - 1);
+        const double b0 = shfl_from(y0, mid + 1), b1 = shfl_from(y1, mid + 1), b2 = shfl_from(y2, mid + 1), b3 = shfl_from(y3, mid + 1);
+        if (ch.is_mid) {
+            y0 = r0 - PLB_MV4(Wm, a0, a1, a2, a3, 0) - PLB_MV4(Pm, b0, b1, b2, b3, 0);
+            y1 = r1 - PLB_MV4(Wm, a0, a1, a2, a3, 1) - PLB_MV4(Pm, b0, b1, b2, b3, 1);
+            y2 = r2 - PLB_MV4(Wm, a0, a1, a2, a3, 2) - PLB_MV4(Pm, b0, b1, b2, b3, 2);
+            y3 = r3 - PLB_MV4(Wm, a0, a1, a2, a3, 3) - PLB_MV4(Pm, b0, b1, b2, b3, 3);
+        }
+    }
+    const double c0 = PLB_MV4(Di, y0, y1, y2, y3, 0), c1 = PLB_MV4(Di, y0, y1, y2, y3, 1);
+    const double c2 = PLB_MV4(Di, y0, y1, y2, y3, 2), c3 = PLB_MV4(Di, y0, y1, y2, y3, 3);
+    double u0 = c0, u1 = c1, u2 = c2, u3 = c3;
+    const double pz = ch.is_mid ? 0.0 : 1.0;   // the meeting node has no outward update
+#pragma unroll 1
+    for (int it = 0; it < ch.n_out; it++) {
+        const double a0 = shfl_from(u0, ch.succ), a1 = shfl_from(u1, ch.succ), a2 = shfl_from(u2, ch.succ), a3 = shfl_from(u3, ch.succ);
+        u0 = c0 - pz * PLB_MV4(Pm, a0, a1, a2, a3, 0);
+        u1 = c1 - pz * PLB_MV4(Pm, a0, a1, a2, a3, 1);
+        u2 = c2 - pz * PLB_MV4(Pm, a0, a1, a2, a3, 2);
+        u3 = c3 - pz * PLB_MV4(Pm, a0, a1, a2, a3, 3);
+    }
+    {   // chain heads: their T row also reaches two nodes ahead
+        const double a0 = shfl_from(u0, ch.succ2), a1 = shfl_from(u1, ch.succ2), a2 = shfl_from(u2, ch.succ2);
+        const double t = Fa.Eo[0][lane] * a0 + Fa.Eo[1][lane] * a1 + Fa.Eo[2][lane] * a2;
+        u0 -= Di[3] * t; u1 -= Di[7] * t; u2 -= Di[11] * t; u3 -= Di[15] * t;
+    }
+    u[0] = u0; u[1] = u1; u[2] = u2; u[3] = u3;
+    // 4. collector chains, backward
+    const double uT = shfl_from(u3, lane < m.Na ? 0 : m.Nx - 1);
+    const double chip = Fa.chip[lane], chup = Fa.chup[lane];
+    double v = yx * chip;
+#pragma unroll 1
+    for (int it = 0; it < ch.nch; it++) {
+        const double us = shfl_from(v, ch.csucc);
+        v = (yx - chup * (ch.is_tail ? uT : us)) * chip;
+    }
+    ux = ch.ch ? v : 0.0;
+}
+
+// alg_only: Newton on the algebraic block (newtons_method!, model_evaluation.jl:430-480): c_e, c_s and
+// all temperatures are frozen, the differential rows are replaced by identity.
+__device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
+                                                 const CtrlRow& ctrl, double cj, bool alg_only,
+                                                 WarpFactor& Fa, int lane) {
+    const LaneChain ch = make_chain(m, ro, lane);
+    const bool dyn = !alg_only;
+    // ---- 1. particles in the eigen-basis of MC ---------------------------------------------------
+    double beta = 0.0, tau = 0.0;
+    if (dyn) {
+        double pd[NR];
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            pd[i] = ro.elec ? 1.0 / (J.kap * laws::EL[i] - cj) : 0.0;
+            Fa.pd[i][lane] = pd[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            double w = 0.0;
+#pragma unroll
+            for (int c = 0; c < NR; c++) w = fma(laws::EVI[i][c], J.csT[c], w);
+            Fa.wT[i][lane] = w;
+            beta = fma(laws::EV[NR - 1][i] * pd[i], laws::EVI[i][NR - 1], beta);
+            tau = fma(laws::EV[NR - 1][i] * pd[i], w, tau);
+        }
+        beta *= J.cs_j;
+    }
+    Fa.csj[lane] = J.cs_j;
+    // ---- 2. node-local elimination of c_s and j -------------------------------------------------
+    double q[4] = {0.0, 0.0, 0.0, 0.0}, inv_den = 0.0;
+    if (ro.elec) {
+        inv_den = 1.0 / (-1.0 - J.j_cs * beta);
+        q[0] = dyn ? -J.j_ce * inv_den : 0.0;
+        q[1] = -J.j_pe * inv_den;
+        q[2] = -J.j_ps * inv_den;
+        q[3] = dyn ? -(J.j_T - J.j_cs * tau) * inv_den : 0.0;
+    }
+    const double sj[4] = {dyn ? J.ce_j : 0.0, J.pe_j, J.ps_j, dyn ? J.T_j - J.T_cs * beta : 0.0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) { Fa.q[k][lane] = q[k]; Fa.sj[k][lane] = sj[k]; }
+    Fa.q[4][lane] = inv_den;
+    Fa.jcs[lane] = J.j_cs;
+    Fa.tcs[lane] = dyn ? J.T_cs : 0.0;
+    double Dm[16];
+    Dm[0] = dyn ? J.ceD - cj : 1.0; Dm[1] = 0.0; Dm[2] = 0.0; Dm[3] = 0.0;
+    Dm[4] = dyn ? J.pcD : 0.0; Dm[5] = J.peD; Dm[6] = 0.0; Dm[7] = dyn ? J.peTD : 0.0;
+    Dm[8] = 0.0; Dm[9] = 0.0; Dm[10] = J.psD; Dm[11] = 0.0;
+    Dm[12] = dyn ? J.T_ce[2] : 0.0; Dm[13] = dyn ? J.T_pe[2] : 0.0; Dm[14] = dyn ? J.T_ps[2] : 0.0;
+    Dm[15] = dyn ? J.T_TD - cj - J.T_cs * tau : 1.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) Dm[r * 4 + c] = fma(sj[r], q[c], Dm[r * 4 + c]);
+    if (!ro.act) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) Dm[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    }
+    // off-diagonal blocks, 9 structural entries each: (0,0) (1,0) (1,1) (1,3) (2,2) (3,0) (3,1) (3,2) (3,3)
+    double L9[9] = {dyn ? J.ceL : 0.0, dyn ? J.pcL : 0.0, J.peL, dyn ? J.peTL : 0.0, J.psL,
+                    dyn ? J.T_ce[1] : 0.0, dyn ? J.T_pe[1] : 0.0, dyn ? J.T_ps[1] : 0.0, dyn ? J.T_TL : 0.0};
+    double U9[9] = {dyn ? J.ceU : 0.0, dyn ? J.pcU : 0.0, J.peU, dyn ? J.peTU : 0.0, J.psU,
+                    dyn ? J.T_ce[3] : 0.0, dyn ? J.T_pe[3] : 0.0, dyn ? J.T_ps[3] : 0.0, dyn ? J.T_TU : 0.0};
+    if (!ro.act || ro.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) L9[k] = 0.0;
+    }
+    if (!ro.act || ro.x >= m.Nx - 1) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) U9[k] = 0.0;
+    }
+    const bool useE = dyn && ro.act;
+    const double E2m[3] = {useE ? J.T_ce[0] : 0.0, useE ? J.T_pe[0] : 0.0, useE ? J.T_ps[0] : 0.0};
+    const double E2p[3] = {useE ? J.T_ce[4] : 0.0, useE ? J.T_pe[4] : 0.0, useE ? J.T_ps[4] : 0.0};
+    // ---- 3. collector chains ----------------------------------------------------------------------
+    {
+        const bool chd = ch.ch && dyn;
+        const double cin = chd ? (ro.cha ? J.Tx_L : J.Tx_U) : 0.0;
+        const double cout = chd ? (ro.cha ? J.Tx_U : J.Tx_L) : 0.0;
+        const double di = chd ? J.Tx_D - cj : 1.0;
+        const double cop = shfl_from(cout, ch.cpred);
+        double pv = di, mm = 0.0;
+#pragma unroll 1
+        for (int it = 0; it < ch.nch - 1; it++) {
+            const double pp = shfl_from(pv, ch.cpred);
+            mm = cin / pp;
+            pv = di - mm * cop;
+        }
+        Fa.chm[lane] = mm; Fa.chip[lane] = 1.0 / pv; Fa.chup[lane] = cout;
+        const double pvt = shfl_from(pv, ch.ctail), cot = shfl_from(cout, ch.ctail);
+        const double hc = !dyn ? 0.0 : (ro.x == 0 ? J.T_TL : (ro.x == m.Nx - 1 ? J.T_TU : 0.0));
+        const double hm = hc / pvt;
+        Dm[15] -= hm * cot;
+        Fa.hm[lane] = hm;
+    }
+    // ---- 4. twisted block-Thomas factorisation ------------------------------------------------------
+    double Cin[9], Cout[9], Cp[9], Ein[3], Eout[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { Cin[k] = ch.rightc ? U9[k] : L9[k]; Cout[k] = ch.rightc ? L9[k] : U9[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Ein[k] = ch.rightc ? E2p[k] : E2m[k]; Eout[k] = ch.rightc ? E2m[k] : E2p[k]; }
+    const bool has_pred = ch.pred != lane;
+    if (!has_pred) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) Cin[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) Cp[k] = shfl_from(Cout[k], ch.pred);
+    const bool hasF = ch.pos >= 2 && (Ein[0] != 0.0 || Ein[1] != 0.0 || Ein[2] != 0.0);
+    double Di[16], Wm[16], Fr[4] = {0.0, 0.0, 0.0, 0.0};
+    double Xo[12], Xp[12];   // dense 4x3 extension of the outgoing block of a position-1 node, and the predecessor's
+#pragma unroll
+    for (int k = 0; k < 12; k++) { Xo[k] = 0.0; Xp[k] = 0.0; }
+    inv4x4(Dm, Di);
+#pragma unroll
+    for (int k = 0; k < 16; k++) Wm[k] = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < ch.n_in + 1; it++) {
+        double G[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) G[k] = shfl_from(Di[k], ch.pred);
+        if (it == ch.posA - 1 || it == ch.posB - 1) {
+            // absorb the coupling to the node two back: F = Ein * Dinv_{p-2}; Cin(T row) -= F * Cout_{p-2}
+            double Fn[4] = {0.0, 0.0, 0.0, 0.0}, Cq[9];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) Fn[c] = fma(Ein[k], shfl_from(Di[k * 4 + c], ch.pred2), Fn[c]);
+#pragma unroll
+            for (int k = 0; k < 9; k++) Cq[k] = shfl_from(Cout[k], ch.pred2);
+            if (ch.pos == it + 1 && hasF) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) Fr[c] = Fn[c];
+                Cin[5] -= Fn[0] * Cq[0] + Fn[1] * Cq[1] + Fn[3] * Cq[5];
+                Cin[6] -= Fn[1] * Cq[2] + Fn[3] * Cq[6];
+                Cin[7] -= Fn[2] * Cq[4] + Fn[3] * Cq[7];
+                Cin[8] -= Fn[1] * Cq[3] + Fn[3] * Cq[8];
+            }
+        }
+        // W = Cin * G (Cin sparse)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            Wm[c] = Cin[0] * G[c];
+            Wm[4 + c] = Cin[1] * G[c] + Cin[2] * G[4 + c] + Cin[3] * G[12 + c];
+            Wm[8 + c] = Cin[4] * G[8 + c];
+            Wm[12 + c] = Cin[5] * G[c] + Cin[6] * G[4 + c] + Cin[7] * G[8 + c] + Cin[8] * G[12 + c];
+        }
+        if (it == 1 && ch.pos == 2) {
+            // the predecessor's outgoing block was extended by a chain head: fold W * Xp into D for good
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    Dm[r * 4 + c] -= Wm[r * 4 + 0] * Xp[c] + Wm[r * 4 + 1] * Xp[3 + c] + Wm[r * 4 + 2] * Xp[6 + c] + Wm[r * 4 + 3] * Xp[9 + c];
+        }
+        double Dp[16];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            Dp[r * 4 + 0] = Dm[r * 4 + 0] - (Wm[r * 4 + 0] * Cp[0] + Wm[r * 4 + 1] * Cp[1] + Wm[r * 4 + 3] * Cp[5]);
+            Dp[r * 4 + 1] = Dm[r * 4 + 1] - (Wm[r * 4 + 1] * Cp[2] + Wm[r * 4 + 3] * Cp[6]);
+            Dp[r * 4 + 2] = Dm[r * 4 + 2] - (Wm[r * 4 + 2] * Cp[4] + Wm[r * 4 + 3] * Cp[7]);
+            Dp[r * 4 + 3] = Dm[r * 4 + 3] - (Wm[r * 4 + 1] * Cp[3] + Wm[r * 4 + 3] * Cp[8]);
+        }
+        if (has_pred) inv4x4(Dp, Di);
+        if (it == 0) {
+            // a chain head's T row reaches this node's successor: X = -W(:,T) * Eout_head extends Cout
+            const double e0 = shfl_from(Eout[0], ch.pred), e1 = shfl_from(Eout[1], ch.pred), e2 = shfl_from(Eout[2], ch.pred);
+            const bool p1 = ch.pos == 1;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                Xo[r * 3 + 0] = p1 ? -Wm[r * 4 + 3] * e0 : 0.0;
+                Xo[r * 3 + 1] = p1 ? -Wm[r * 4 + 3] * e1 : 0.0;
+                Xo[r * 3 + 2] = p1 ? -Wm[r * 4 + 3] * e2 : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 12; k++) Xp[k] = shfl_from(Xo[k], ch.pred);
+        }
+    }
+    // P = Dinv * (Cout + Xo)
+    double Pm[16];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const double d0 = Di[r * 4 + 0], d1 = Di[r * 4 + 1], d2 = Di[r * 4 + 2], d3 = Di[r * 4 + 3];
+        Pm[r * 4 + 0] = d0 * (Cout[0] + Xo[0]) + d1 * (Cout[1] + Xo[3]) + d2 * Xo[6] + d3 * (Cout[5] + Xo[9]);
+        Pm[r * 4 + 1] = d0 * Xo[1] + d1 * (Cout[2] + Xo[4]) + d2 * Xo[7] + d3 * (Cout[6] + Xo[10]);
+        Pm[r * 4 + 2] = d0 * Xo[2] + d1 * Xo[5] + d2 * (Cout[4] + Xo[8]) + d3 * (Cout[7] + Xo[11]);
+        Pm[r * 4 + 3] = d1 * Cout[3] + d3 * Cout[8];
+    }
+    {   // meeting node: second neighbour (mid+1, right chain): Wr = U_mid Dinv_{mid+1}, stored in Pm
+        const int mid = m.mid;
+        double G[16], q9[9];
+#pragma unroll
+        for (int k = 0; k < 16; k++) G[k] = shfl_from(Di[k], mid + 1);
+#pragma unroll
+        for (int k = 0; k < 9; k++) q9[k] = shfl_from(L9[k], mid + 1);
+        if (ch.is_mid) {
+            double Wr[16];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                Wr[c] = U9[0] * G[c];
+                Wr[4 + c] = U9[1] * G[c] + U9[2] * G[4 + c] + U9[3] * G[12 + c];
+                Wr[8 + c] = U9[4] * G[8 + c];
+                Wr[12 + c] = U9[5] * G[c] + U9[6] * G[4 + c] + U9[7] * G[8 + c] + U9[8] * G[12 + c];
+            }
+            double Dp[16];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                Dp[r * 4 + 0] = Dm[r * 4 + 0] - (Wm[r * 4 + 0] * Cp[0] + Wm[r * 4 + 1] * Cp[1] + Wm[r * 4 + 3] * Cp[5])
+                                - (Wr[r * 4 + 0] * q9[0] + Wr[r * 4 + 1] * q9[1] + Wr[r * 4 + 3] * q9[5]);
+                Dp[r * 4 + 1] = Dm[r * 4 + 1] - (Wm[r * 4 + 1] * Cp[2] + Wm[r * 4 + 3] * Cp[6]) - (Wr[r * 4 + 1] * q9[2] + Wr[r * 4 + 3] * q9[6]);
+                Dp[r * 4 + 2] = Dm[r * 4 + 2] - (Wm[r * 4 + 2] * Cp[4] + Wm[r * 4 + 3] * Cp[7]) - (Wr[r * 4 + 2] * q9[4] + Wr[r * 4 + 3] * q9[7]);
+                Dp[r * 4 + 3] = Dm[r * 4 + 3] - (Wm[r * 4 + 1] * Cp[3] + Wm[r * 4 + 3] * Cp[8]) - (Wr[r * 4 + 1] * q9[3] + Wr[r * 4 + 3] * q9[8]);
+            }
+            inv4x4(Dp, Di);
+#pragma unroll
+            for (int k = 0; k < 16; k++) Pm[k] = Wr[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) { Fa.Dinv[k][lane] = Di[k]; Fa.Wm[k][lane] = Wm[k]; Fa.Pm[k][lane] = Pm[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) Fa.Fr[k][lane] = Fr[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) Fa.Eo[k][lane] = Eout[k];
+    __syncwarp();
+    // ---- 5. border: z = core^{-1} (dF/dI column), then the Schur complement ------------------------
+    const double zb[4] = {0.0, 0.0, J.ps_I, 0.0};
+    double u4[4], ux;
+    core_solve(m, ch, Fa, Di, Wm, Pm, zb, (ch.ch && dyn) ? J.Tx_I : 0.0, u4, ux, lane);
+#pragma unroll
+    for (int k = 0; k < 4; k++) Fa.z[k][lane] = u4[k];
+    Fa.zx[lane] = ux;
+    const double z0 = shfl_from(u4[2], 0), zN = shfl_from(u4[2], m.Nx - 1);
+    if (lane == 0) {
+        Fa.schur_inv = 1.0 / (ctrl.g_I - ctrl.g_ps0 * z0 - ctrl.g_psN * zN);
+        Fa.g_ps0 = ctrl.g_ps0;
+        Fa.g_psN = ctrl.g_psN;
+    }
+    __syncwarp();
+}
+
+// Solve J * d = g for one right-hand side held node-wise in registers (g in, d out, in place).
+__device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const LaneRole& ro, const WarpFactor& Fa,
+                                                  bool alg_only, LaneVec& g, double gI, int lane) {
+    const LaneChain ch = make_chain(m, ro, lane);
+    const bool dyn = !alg_only;
+    // particle right-hand side into the eigen-basis: w0 = EVI * g_cs ; s9 = surface component of A^{-1} g_cs
+    double s9 = 0.0;
+    if (dyn) {
+        double w0[NR];
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            double w = 0.0;
+#pragma unroll
+            for (int c = 0; c < NR; c++) w = fma(laws::EVI[i][c], g.cs[c], w);
+            w0[i] = ro.elec ? w : 0.0;
+            s9 = fma(laws::EV[NR - 1][i] * Fa.pd[i][lane], w0[i], s9);
+        }
+#pragma unroll
+        for (int i = 0; i < NR; i++) g.cs[i] = w0[i];
+    }
+    const double q0 = ro.elec ? (g.j - Fa.jcs[lane] * s9) * Fa.q[4][lane] : 0.0;
+    double rb[4];
+    rb[0] = dyn ? g.ce - Fa.sj[0][lane] * q0 : 0.0;
+    rb[1] = g.pe - Fa.sj[1][lane] * q0;
+    rb[2] = (ro.elec ? g.ps : 0.0) - Fa.sj[2][lane] * q0;
+    rb[3] = dyn ? g.T - Fa.sj[3][lane] * q0 - Fa.tcs[lane] * s9 : 0.0;
+    if (!ro.act) { rb[0] = rb[1] = rb[2] = rb[3] = 0.0; }
+    double Di[16], Wm[16], Pm[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { Di[k] = Fa.Dinv[k][lane]; Wm[k] = Fa.Wm[k][lane]; Pm[k] = Fa.Pm[k][lane]; }
+    double u4[4], ux;
+    core_solve(m, ch, Fa, Di, Wm, Pm, rb, (ch.ch && dyn) ? g.Tx : 0.0, u4, ux, lane);
+    // border
+    const double x0 = shfl_from(u4[2], 0), xN = shfl_from(u4[2], m.Nx - 1);
+    const double dI = (gI - Fa.g_ps0 * x0 - Fa.g_psN * xN) * Fa.schur_inv;
+#pragma unroll
+    for (int k = 0; k < 4; k++) u4[k] -= Fa.z[k][lane] * dI;
+    ux -= Fa.zx[lane] * dI;
+    // back-substitute j and the particle
+    const double dj = ro.elec ? q0 + Fa.q[0][lane] * u4[0] + Fa.q[1][lane] * u4[1] + Fa.q[2][lane] * u4[2] + Fa.q[3][lane] * u4[3] : 0.0;
+    if (dyn) {
+        double v[NR];
+        const double bj = Fa.csj[lane] * dj;
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+            v[i] = Fa.pd[i][lane] * (g.cs[i] - laws::EVI[i][NR - 1] * bj - Fa.wT[i][lane] * u4[3]);
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < NR; i++) acc = fma(laws::EV[r][i], v[i], acc);
+            g.cs[r] = ro.elec ? acc : 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < NR; r++) g.cs[r] = 0.0;
+    }
+    g.ce = dyn ? u4[0] : 0.0;
+    g.pe = u4[1];
+    g.ps = ro.elec ? u4[2] : 0.0;
+    g.T = dyn ? u4[3] : 0.0;
+    g.Tx = dyn ? ux : 0.0;
+    g.j = dj;
+    return dI;
+}
+#endif  // PLB_TH
+
 // out-of-line copies for the operator-level Newton-init kernel
 __device__ __noinline__ void warp_factor(const ModelDesc& m, const LaneRole& ro, const LaneJac& J,
                                          const CtrlRow& ctrl, double cj, bool alg_only, WarpFactor& Fa, int lane) {
@@ -701,4 +1371,5 @@ __device__ __noinline__ double warp_solve(const ModelDesc& m, const LaneRole& ro
     return warp_solve_impl(m, ro, Fa, alg_only, g, gI, lane);
 }
 
+}  // namespace PLB_NS
 }  // namespace plb

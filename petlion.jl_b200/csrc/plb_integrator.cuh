@@ -16,25 +16,9 @@
 #include "plb_device.cuh"
 
 namespace plb {
+namespace PLB_NS {
 
-struct Opts {
-    double abstol, reltol, abstol_init, reltol_init;
-    int maxiters, check_bounds, interp_final;
-    int maxord, maxcor, maxnef, maxncf;   // Sundials.jl IDA(): 5, 3, 7, 10
-};
-struct Bounds {
-    double V_max, V_min, SOC_max, SOC_min, T_max, c_s_n_max, I_max, I_min, eta_plating_min, c_e_min,
-        dfilm_max;
-};
-struct Summary {
-    double t_end, V_end, I_end, SOC_end;
-    int flag, n_steps, n_res, n_jac, n_netf, n_ncfn, n_newton_init, reserved;
-};
-
-constexpr int FAIL_NEWTON_INIT = -1, FAIL_CONV = -2, FAIL_ERRTEST = -3, FAIL_MAXITERS = -4,
-              FAIL_NONFINITE = -5, FAIL_INIT_BOUNDS = -6;
-
-constexpr int VS = 304;   // vector stride in doubles (N_tot = 301 padded)
+constexpr int VS = TH ? 352 : 304;   // vector stride in doubles (N_tot = 301 / 351 padded)
 enum VecId { V_PHI0 = 0, V_PHI1, V_PHI2, V_PHI3, V_PHI4, V_PHI5, V_YPRED, V_YPPRED, V_EWT, V_EE, V_COUNT };
 
 struct IdaCoef {
@@ -73,7 +57,7 @@ struct WarpWS {
     }
 };
 
-// internal vector layout: c_e[Nx] | c_s radial-major [NR][Ne] | j[Ne] | Phi_e[Nx] | Phi_s[Ne] | I
+// internal vector layout: c_e[Nx] | c_s radial-major [NR][Ne] | [T: a|p|s|n|z] | j[Ne] | Phi_e[Nx] | Phi_s[Ne] | I
 // (the reference layout is particle-major for c_s; radial-major makes lane accesses conflict-free)
 __device__ __forceinline__ void load_lane(const ModelDesc& m, const LaneRole& ro, const double* v,
                                           LaneVec& y, double& I) {
@@ -89,6 +73,10 @@ __device__ __forceinline__ void load_lane(const ModelDesc& m, const LaneRole& ro
         for (int r = 0; r < NR; r++) y.cs[r] = 0.0;
         y.j = 0.0; y.ps = 0.0;
     }
+    if (TH) {
+        y.T = ro.act ? v[m.off_T + m.Na + ro.x] : 0.0;
+        y.Tx = ro.ix >= 0 ? v[m.off_T + ro.ix] : 0.0;
+    }
     I = v[m.off_I];
 }
 __device__ __forceinline__ void store_lane(const ModelDesc& m, const LaneRole& ro, double* v,
@@ -100,11 +88,15 @@ __device__ __forceinline__ void store_lane(const ModelDesc& m, const LaneRole& r
         v[m.off_j + ro.e] = y.j;
         v[m.off_ps + ro.e] = y.ps;
     }
+    if (TH) {
+        if (ro.act) v[m.off_T + m.Na + ro.x] = y.T;
+        if (ro.ix >= 0) v[m.off_T + ro.ix] = y.Tx;
+    }
     if (lane == 0) v[m.off_I] = I;
 }
 // reference (particle-major) layout <-> internal index
 __device__ __forceinline__ int ref_index(const ModelDesc& m, int i) {
-    if (i < m.off_cs || i >= m.off_j) return i;
+    if (i < m.off_cs || i >= m.off_cs + NR * m.Ne) return i;
     const int k = i - m.off_cs, r = k / m.Ne, e = k % m.Ne;
     return m.off_cs + e * NR + r;
 }
@@ -133,7 +125,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     CtrlRow ctrl;
     double I;
     load_lane(m, ro, Y, y, I);
-    yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0;
+    yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0;
 #pragma unroll
     for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
     int iter;
@@ -158,6 +150,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     n_res++;
     LaneVec ypo;
     ypo.ce = res.ce;
+    ypo.T = TH ? res.T : 0.0; ypo.Tx = TH ? res.Tx : 0.0;
 #pragma unroll
     for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
     // estimate dY_alg/dt (:462-477): Delta_t = max(10 reltol_init, sqrt(eps(c_e0)))
@@ -167,6 +160,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
         const double dt = fmax(10.0 * o.reltol_init, sqrt(epsv));
         LaneVec yn = y;
         yn.ce = y.ce + dt * ypo.ce;
+        if (TH) { yn.T = y.T + dt * ypo.T; yn.Tx = y.Tx + dt * ypo.Tx; }
 #pragma unroll
         for (int r = 0; r < NR; r++) yn.cs[r] = y.cs[r] + dt * ypo.cs[r];
         lane_eval_ni<CHEM, false>(m, w.C, ro, yn, yp, I, rc.method, rc.value, res, ctrl, J);
@@ -410,10 +404,33 @@ __device__ __forceinline__ double interp_yp(const WarpWS& w, const double* d, in
 }
 
 struct PrevVals {   // boundary_stop_prev_values, structures.jl:174-184
-    double frac, V, SOC, c_s_n, I, eta_plating, c_e_min;
+    double frac, V, SOC, c_s_n, I, eta_plating, c_e_min, T;
 };
 
-// check_simulation_stop! -- checks.jl:1-224 (isothermal, no SEI: T and dfilm checks inactive)
+// temperature_weighting(T): length-weighted mean over the five sections
+// (auxiliary_states_and_coefficients.jl:649-676) of a vector given by interpolation weights (c, kord);
+// deriv: weights d of the derivative instead.  Isothermal variant: T0.
+__device__ __forceinline__ double weighted_T(const ModelDesc& m, const WarpWS& w, const double* c, int kord,
+                                             bool deriv, int lane) {
+#if PLB_TH
+    const int NT = m.Na + m.Nx + m.Nz;
+    double s = 0.0;
+    for (int i = lane; i < NT; i += 32) {
+        const int x = i - m.Na;
+        const int q = i < m.Na ? 0 : (x < m.Np ? 1 : (x < m.Np + m.Ns ? 2 : (x < m.Nx ? 3 : 4)));
+        double v = 0.0;
+        for (int j = deriv ? 1 : 0; j <= kord; j++) v = fma(c[deriv ? j - 1 : j], w.v(V_PHI0 + j)[m.off_T + i], v);
+        s = fma(v, w.C.s5[0][q], s);
+    }
+    s = warp_sum(s);
+    const double* th = w.C.theta;
+    return s / (th[TF_l_a] + th[TF_l_p] + th[TF_l_s] + th[TF_l_n] + th[TF_l_z]);
+#else
+    return deriv ? 0.0 : w.C.g[GC_T];
+#endif
+}
+
+// check_simulation_stop! -- checks.jl:1-224 (no SEI: the dfilm check is inactive; T only when thermal)
 __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, const RunCtl& rc,
                                         const Opts& o, const Bounds& b, bool is_rest, double tf,
                                         PrevVals& pv, int& flag, double t, const double* c,
@@ -458,6 +475,17 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
         if (tf_ < pv.frac) { pv.frac = tf_; flag = 4; }
     }
     pv.SOC = SOC;
+#if PLB_TH
+    // check_stop_T :106-124
+    if (b.T_max == b.T_max) {
+        const double Tw = weighted_T(m, w, c, kord, false, lane);
+        if (Tw - b.T_max > eps && weighted_T(m, w, d, kord, true, lane) > 0) {
+            const double tf_ = (pv.T - b.T_max) / (pv.T - Tw);
+            if (tf_ < pv.frac) { pv.frac = tf_; flag = 5; }
+        }
+        pv.T = Tw;
+    }
+#endif
     // check_stop_c_s_surf :141-161
     if (b.c_s_n_max == b.c_s_n_max) {
         double mx = -INFINITY;
@@ -496,24 +524,7 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
     }
 }
 
-struct SimArgs {
-    ModelDesc m;
-    int B;
-    const double* theta;
-    const double* values;     // per-system control value or nullptr
-    int method;
-    double value, tf;
-    int input_kind, new_run;   // 0 value, 1 :hold, 2 :rest
-    Opts o;
-    Bounds b;
-    const double* soc0;
-    double *sY, *sYP, *sSOC, *st;
-    Summary* out;
-    int n_save_max;
-    double *tr_t, *tr_V, *tr_I, *tr_SOC;
-    int* tr_n;
-    int* counter;
-    double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]
-};
 
+
+}  // namespace PLB_NS
 }  // namespace plb

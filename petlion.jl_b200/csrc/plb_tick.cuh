@@ -18,6 +18,7 @@
 #include "plb_integrator.cuh"
 
 namespace plb {
+namespace PLB_NS {
 
 enum TickState { ST_FETCH = 0, ST_INIT_ITER, ST_INIT_RDIFF, ST_INIT_DT, ST_NLS, ST_EXHAUSTED };
 enum Pending { PEND_NONE = 0, PEND_RETURNED, PEND_BEGIN, PEND_FINISH };
@@ -64,6 +65,7 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
     if (M.cjratio != 1.0) {
         const double sc = 2.0 / (1.0 + M.cjratio);
         d.ce *= sc; d.j *= sc; d.pe *= sc; d.ps *= sc; dI *= sc;
+        if (TH) { d.T *= sc; d.Tx *= sc; }
 #pragma unroll
         for (int r = 0; r < NR; r++) d.cs[r] *= sc;
     }
@@ -83,6 +85,10 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
         s = fma(d.ps * ewt.ps, d.ps * ewt.ps, s);
 #pragma unroll
         for (int r = 0; r < NR; r++) { ee.cs[r] += d.cs[r]; s = fma(d.cs[r] * ewt.cs[r], d.cs[r] * ewt.cs[r], s); }
+    }
+    if (TH) {
+        if (ro.act) { ee.T += d.T; s = fma(d.T * ewt.T, d.T * ewt.T, s); }
+        if (ro.ix >= 0) { ee.Tx += d.Tx; s = fma(d.Tx * ewt.Tx, d.Tx * ewt.Tx, s); }
     }
     eeI += dI;
     store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
@@ -271,6 +277,10 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
         if (a.tr_I) a.tr_I[so + S.nsave] = Ic;
         if (a.tr_SOC) a.tr_SOC[so + S.nsave] = S.SOC;
     }
+    if (a.tr_T && S.nsave < a.n_save_max) {
+        const double Tw = weighted_T(m, w, w.K.cvals, S.kord, false, lane);
+        if (lane == 0) a.tr_T[so + S.nsave] = Tw;
+    }
     S.nsave++;
     check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, Ic, Vc, lane);
     if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return false; }
@@ -289,8 +299,8 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
     const int N = m.N_tot;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
     Summary out;
-    out.reserved = 0;
-    double t_end = S.t + S.t0, SOC_end = S.SOC, V_end = 0.0, I_end = 0.0;
+    out.reserved = 0; out.aux_end = 0.0;
+    double t_end = S.t + S.t0, SOC_end = S.SOC, V_end = 0.0, I_end = 0.0, T_end = TH ? 0.0 : w.C.g[GC_T];
     const size_t so = (size_t)S.sys * a.n_save_max;
     if (integrated) {
         double fr = 1.0;
@@ -303,7 +313,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
             if (do_interp) { double dp[6]; getsol_weights(M, w.K, S.tprev, w.K.cprev, dp); }
         }
         __syncwarp();
-        double ps0 = 0.0, psN = 0.0, If = 0.0;
+        double ps0 = 0.0, psN = 0.0, If = 0.0, Tw = 0.0;
 #pragma unroll 1
         for (int i = lane; i < N; i += 32) {
             const double yn = interp_y(w, w.K.cvals, S.kord, i);
@@ -314,9 +324,22 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
             if (i == iP0) ps0 = yf;
             if (i == iPN) psN = yf;
             if (i == m.off_I) If = yf;
+#if PLB_TH
+            if (i >= m.off_T && i < m.off_j) {   // temperature_weighting of the final state
+                const int k = i - m.off_T, x = k - m.Na;
+                const int q = k < m.Na ? 0 : (x < m.Np ? 1 : (x < m.Np + m.Ns ? 2 : (x < m.Nx ? 3 : 4)));
+                Tw = fma(yf, w.C.s5[0][q], Tw);
+            }
+#endif
         }
         ps0 = warp_sum(ps0); psN = warp_sum(psN); If = warp_sum(If);
         V_end = ps0 - psN; I_end = If;
+#if PLB_TH
+        {
+            const double* th = w.C.theta;
+            T_end = warp_sum(Tw) / (th[TF_l_a] + th[TF_l_p] + th[TF_l_s] + th[TF_l_n] + th[TF_l_z]);
+        }
+#endif
         if (do_interp) {
             const double ti = fr * (S.t - S.tprev) + S.tprev;
             const double tgi = ti + S.t0, tgl = S.t + S.t0;
@@ -327,6 +350,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
                 if (a.tr_V) a.tr_V[so + S.nsave - 1] = V_end;
                 if (a.tr_I) a.tr_I[so + S.nsave - 1] = I_end;
                 if (a.tr_SOC) a.tr_SOC[so + S.nsave - 1] = SOC_end;
+                if (a.tr_T) a.tr_T[so + S.nsave - 1] = T_end;
             }
         }
     } else {
@@ -338,8 +362,9 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
         }
         S.nsave = 1;
         t_end = S.t0;
+        if (TH) T_end = w.C.g[GC_T];
     }
-    out.t_end = t_end; out.V_end = V_end; out.I_end = I_end; out.SOC_end = SOC_end;
+    out.t_end = t_end; out.V_end = V_end; out.I_end = I_end; out.SOC_end = SOC_end; out.T_end = T_end;
     out.flag = S.flag; out.n_steps = S.nsave - 1;
     out.n_res = M.nre; out.n_jac = M.nje; out.n_netf = M.netf; out.n_ncfn = M.ncfn;
     out.n_newton_init = S.n_newton_init;
@@ -375,6 +400,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
         const double csn = th[TF_c_max_n] * (S.SOC * (th[TF_theta_max_n] - th[TF_theta_min_n]) + th[TF_theta_min_n]);
         LaneVec y0;
         y0.ce = th[TF_c_e0]; y0.j = 0.0; y0.pe = 0.0; y0.ps = 0.0;
+        y0.T = th[TF_T0]; y0.Tx = th[TF_T0];
         const double cs0 = ro.sec == 0 ? csp : csn;
 #pragma unroll
         for (int r = 0; r < NR; r++) y0.cs[r] = cs0;
@@ -464,7 +490,12 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
         if (a.tr_I) a.tr_I[so + S.nsave] = Ic;
         if (a.tr_SOC) a.tr_SOC[so + S.nsave] = S.SOC;
     }
+    if (a.tr_T && S.nsave < a.n_save_max) {
+        const double Tw = weighted_T(m, w, w.K.cvals, 1, false, lane);
+        if (lane == 0) a.tr_T[so + S.nsave] = Tw;
+    }
     S.nsave++;
+    S.pv.T = -1;
     S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
     S.kord = 1;
     check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, Ic, Vc, lane);
@@ -486,7 +517,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         LaneVec y, yp, res;
         double Iy = 0.0;
         bool do_eval = S.state != ST_EXHAUSTED, need_jac = false, alg_only = false, do_solve = false;
-        yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0;
+        yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0;
 #pragma unroll
         for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
         if (do_eval) {
@@ -499,6 +530,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 const double cj = S.M.cj;
                 y.ce += e.ce; y.j += e.j; y.pe += e.pe; y.ps += e.ps; Iy += eI;
                 yp.ce = p.ce + cj * e.ce;
+                if (TH) { y.T += e.T; y.Tx += e.Tx; yp.T = p.T + cj * e.T; yp.Tx = p.Tx + cj * e.Tx; }
 #pragma unroll
                 for (int r = 0; r < NR; r++) { y.cs[r] += e.cs[r]; yp.cs[r] = p.cs[r] + cj * e.cs[r]; }
                 need_jac = S.callLSetup != 0; do_solve = true;
@@ -511,6 +543,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                     double pI;
                     load_lane(m, ro, w.v(V_PHI1), p, pI);
                     y.ce += S.dt_init * p.ce;
+                    if (TH) { y.T += S.dt_init * p.T; y.Tx += S.dt_init * p.Tx; }
 #pragma unroll
                     for (int r = 0; r < NR; r++) y.cs[r] += S.dt_init * p.cs[r];
                     do_solve = true;
@@ -546,6 +579,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             double gI = ctrl.res;
             if (S.state == ST_NLS) {   // Newton update of the BDF step: delta = -J^{-1} F
                 res.ce = -res.ce; res.j = -res.j; res.pe = -res.pe; res.ps = -res.ps; gI = -gI;
+                if (TH) { res.T = -res.T; res.Tx = -res.Tx; }
 #pragma unroll
                 for (int r = 0; r < NR; r++) res.cs[r] = -res.cs[r];
             }
@@ -591,6 +625,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 // R_diff(YP,t,Y,YP): YP_diff = rhs (model_evaluation.jl:460); algebraic part still zero
                 LaneVec ypo;
                 ypo.ce = res.ce; ypo.j = 0.0; ypo.pe = 0.0; ypo.ps = 0.0;
+                ypo.T = TH ? res.T : 0.0; ypo.Tx = TH ? res.Tx : 0.0;
 #pragma unroll
                 for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
                 store_lane(m, ro, w.v(V_PHI1), ypo, 0.0, lane);
@@ -618,4 +653,5 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
     }
 }
 
+}  // namespace PLB_NS
 }  // namespace plb

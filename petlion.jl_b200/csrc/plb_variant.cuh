@@ -1,0 +1,465 @@
+// plb_variant.cuh -- kernels and launchers of ONE model family; included by plb_variant_iso.cu (PLB_TH=0,
+// namespace plb::iso) and plb_variant_th.cu (PLB_TH=1, namespace plb::th).
+//
+// Kernels (all FP64, sm_100a, warp-per-system):
+//   k_resjac     K1: batched residual + CSC Jacobian values  (R_full / J_full callback surface,
+//                /root/reference/src/physics_equations/scalar_residual.jl:558-602)
+//   k_initguess  initial_guess!                                (states_definition.jl:80-121)
+//   k_newton     K3: newtons_method!                           (model_evaluation.jl:430-480)
+//   k_linsolve   factorize + solve of the Newton matrix        (KLU inside IDA, model_evaluation.jl:265-271, 417-428)
+//   k_simulate   K4: fused persistent integrator               (model_evaluation.jl:312-382 + IDA)
+#pragma once
+#include "plb_integrator.cuh"
+
+namespace plb {
+namespace PLB_NS {
+
+// =================================================================================================
+// K1: residual + Jacobian (CSC nzval) over a batch
+// =================================================================================================
+// canonical enumeration of one lane's Jacobian entries ("slots"); the host builds, per slot and
+// lane, the position in the reference's CSC ordering (or -1).
+enum JacSlot {
+    JS_CE_L = 0, JS_CE_D, JS_CE_U, JS_CE_J,
+    JS_J_CS, JS_J_CE, JS_J_PE, JS_J_PS, JS_J_J,
+    JS_PE_L, JS_PE_D, JS_PE_U, JS_PC_L, JS_PC_D, JS_PC_U, JS_PE_J,
+    JS_PS_L, JS_PS_D, JS_PS_U, JS_PS_J, JS_PS_I,
+    JS_CS_J,
+#if PLB_TH
+    JS_CS_T0,                                       // 10 slots: d res_cs[r] / dT
+    JS_J_T = JS_CS_T0 + NR, JS_PE_TL, JS_PE_TD, JS_PE_TU,
+    JS_T_TL, JS_T_TD, JS_T_TU, JS_T_J, JS_T_CS,
+    JS_T_CE0,                                       // 5 slots each: nodes x-2 .. x+2
+    JS_T_PE0 = JS_T_CE0 + 5, JS_T_PS0 = JS_T_PE0 + 5,
+    JS_TX_L = JS_T_PS0 + 5, JS_TX_D, JS_TX_U, JS_TX_I,
+    JS_KAP,                                         // staging only: D_s(T_x)/Rp^2 of the node
+    JS_CS0,
+#else
+    JS_CS0,                      // 100 particle-block slots r*NR+c
+#endif
+    JS_CTRL_PS0 = JS_CS0 + NR * NR, JS_CTRL_PSN, JS_CTRL_I,
+    JS_COUNT
+};
+
+#ifndef PLB_K1_CTAS
+#define PLB_K1_CTAS (PLB_TH ? 2 : 3)
+#endif
+constexpr int K1_WARPS = 4;
+constexpr int K1_NSTAGE = JS_CS0 + 3;   // lane-computed slots: 0..JS_CS0-1, then the three control-row slots
+constexpr int K1_SRC_MAX = TH ? 3072 : 2304;        // >= nnz of every built variant
+__host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
+
+struct K1Warp {
+    double S[K1_NSTAGE][32];   // lane-computed Jacobian entries
+    double MCs[NR * NR];       // particle stencil coefficients (contiguous with S: one value table)
+    WarpConst C;
+};
+constexpr size_t K1_SMEM = sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX;
+
+// K1: one warp evaluates F and the CSC values of dF/dY + gamma dF/dY' of one system at a time.
+// HBM traffic per system is exactly the algorithmic 8*(3N + n_theta + nnz) bytes: Y, Y', theta rows
+// are read once (lane-mapped, L1-coalesced), res and nzval rows are written once with lane-consecutive
+// 8-byte stores.  Most of nzval is the constant particle stencil scaled by D_s/Rp^2 (minus gamma on
+// the diagonal): those entries are produced in the coalesced, branch-free write loop from a recipe
+// table held in shared memory, never staged; only the lane-computed entries go through a
+// shared-memory stage.
+//   recipe bits: 0-15 index into the warp's value table (lane-computed: slot*32+lane; particle entries:
+//   K1_NSTAGE*32 + r*NR+c), 16 particle-block entry, 17 anode (isothermal: D_s per electrode),
+//   18 diagonal, 19-23 node (thermal: D_s(T) per node)
+template <int CHEM>
+__global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArgs a) {
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Warp* ws = reinterpret_cast<K1Warp*>(k1_raw);
+    int* src_s = reinterpret_cast<int*>(k1_raw + sizeof(K1Warp) * K1_WARPS);
+    for (int i = threadIdx.x; i < a.nnz; i += blockDim.x) src_s[i] = a.src[i];
+    {
+        K1Warp& w0 = ws[threadIdx.x >> 5];
+        for (int i = threadIdx.x & 31; i < NR * NR; i += 32) w0.MCs[i] = laws::MC[i / NR][i % NR];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ModelDesc& m = a.m;
+    const int N = m.N_tot;
+    K1Warp& w = ws[warp];
+    const LaneRole ro = make_role(m, lane);
+    const int nwarps = gridDim.x * K1_WARPS;
+    for (int sys = blockIdx.x * K1_WARPS + warp; sys < a.B; sys += nwarps) {
+        const double* __restrict__ gY = a.Y + (size_t)sys * N;
+        const double* __restrict__ gYP = a.YP + (size_t)sys * N;
+        LaneVec y, yp, res;
+        y.ce = ro.act ? gY[ro.x] : 0.0; yp.ce = ro.act ? gYP[ro.x] : 0.0;
+        y.pe = ro.act ? gY[m.off_pe + ro.x] : 0.0; yp.pe = 0.0;
+        if (ro.elec) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) { y.cs[r] = gY[m.off_cs + ro.e * NR + r]; yp.cs[r] = gYP[m.off_cs + ro.e * NR + r]; }
+            y.j = gY[m.off_j + ro.e]; y.ps = gY[m.off_ps + ro.e];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) { y.cs[r] = 0.0; yp.cs[r] = 0.0; }
+            y.j = 0.0; y.ps = 0.0;
+        }
+        yp.j = 0.0; yp.ps = 0.0;
+        y.T = 0.0; y.Tx = 0.0; yp.T = 0.0; yp.Tx = 0.0;
+        if (TH) {
+            if (ro.act) { y.T = gY[m.off_T + m.Na + ro.x]; yp.T = gYP[m.off_T + m.Na + ro.x]; }
+            if (ro.ix >= 0) { y.Tx = gY[m.off_T + ro.ix]; yp.Tx = gYP[m.off_T + ro.ix]; }
+        }
+        const double Iapp = gY[m.off_I];
+        const double value = a.values ? a.values[sys] : a.value;
+        setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
+        LaneJac J;
+        CtrlRow ctrl;
+        if (a.nzval) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iapp, a.method, value, res, ctrl, J);
+        else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iapp, a.method, value, res, ctrl, J);
+        if (a.res) {
+            double* __restrict__ gR = a.res + (size_t)sys * N;
+            if (ro.act) { gR[ro.x] = res.ce; gR[m.off_pe + ro.x] = res.pe; }
+            if (ro.elec) {
+#pragma unroll
+                for (int r = 0; r < NR; r++) gR[m.off_cs + ro.e * NR + r] = res.cs[r];
+                gR[m.off_j + ro.e] = res.j;
+                gR[m.off_ps + ro.e] = res.ps;
+            }
+            if (TH) {
+                if (ro.act) gR[m.off_T + m.Na + ro.x] = res.T;
+                if (ro.ix >= 0) gR[m.off_T + ro.ix] = res.Tx;
+            }
+            if (lane == 0) gR[m.off_I] = ctrl.res;
+        }
+        if (a.nzval) {
+            const double g = a.gamma ? a.gamma[sys] : 0.0;
+            w.S[JS_CE_L][lane] = J.ceL; w.S[JS_CE_D][lane] = J.ceD - g; w.S[JS_CE_U][lane] = J.ceU; w.S[JS_CE_J][lane] = J.ce_j;
+            w.S[JS_J_CS][lane] = J.j_cs; w.S[JS_J_CE][lane] = J.j_ce; w.S[JS_J_PE][lane] = J.j_pe; w.S[JS_J_PS][lane] = J.j_ps;
+            w.S[JS_J_J][lane] = -1.0;
+            w.S[JS_PE_L][lane] = J.peL; w.S[JS_PE_D][lane] = J.peD; w.S[JS_PE_U][lane] = J.peU;
+            w.S[JS_PC_L][lane] = J.pcL; w.S[JS_PC_D][lane] = J.pcD; w.S[JS_PC_U][lane] = J.pcU; w.S[JS_PE_J][lane] = J.pe_j;
+            w.S[JS_PS_L][lane] = J.psL; w.S[JS_PS_D][lane] = J.psD; w.S[JS_PS_U][lane] = J.psU; w.S[JS_PS_J][lane] = J.ps_j;
+            w.S[JS_PS_I][lane] = J.ps_I;
+            w.S[JS_CS_J][lane] = J.cs_j;
+#if PLB_TH
+#pragma unroll
+            for (int r = 0; r < NR; r++) w.S[JS_CS_T0 + r][lane] = J.csT[r];
+            w.S[JS_J_T][lane] = J.j_T;
+            w.S[JS_PE_TL][lane] = J.peTL; w.S[JS_PE_TD][lane] = J.peTD; w.S[JS_PE_TU][lane] = J.peTU;
+            w.S[JS_T_TL][lane] = J.T_TL; w.S[JS_T_TD][lane] = J.T_TD - g; w.S[JS_T_TU][lane] = J.T_TU;
+            w.S[JS_T_J][lane] = J.T_j; w.S[JS_T_CS][lane] = J.T_cs;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                w.S[JS_T_CE0 + k][lane] = J.T_ce[k]; w.S[JS_T_PE0 + k][lane] = J.T_pe[k]; w.S[JS_T_PS0 + k][lane] = J.T_ps[k];
+            }
+            w.S[JS_TX_L][lane] = J.Tx_L; w.S[JS_TX_D][lane] = J.Tx_D - g; w.S[JS_TX_U][lane] = J.Tx_U; w.S[JS_TX_I][lane] = J.Tx_I;
+            w.S[JS_KAP][lane] = J.kap;
+#endif
+            w.S[k1_stage_slot(JS_CTRL_PS0)][lane] = ctrl.g_ps0;
+            w.S[k1_stage_slot(JS_CTRL_PSN)][lane] = ctrl.g_psN;
+            w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
+            __syncwarp();
+            const double* tab = &w.S[0][0];
+            double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
+#if PLB_TH
+#pragma unroll 4
+            for (int p = lane; p < a.nnz; p += 32) {
+                const int rc = src_s[p];
+                const double t = tab[rc & 0xffff];
+                const double kap = tab[JS_KAP * 32 + ((rc >> 19) & 31)];
+                const double gd = (rc & (1 << 18)) ? g : 0.0;
+                gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
+            }
+#else
+            const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
+#pragma unroll 4
+            for (int p = lane; p < a.nnz; p += 32) {
+                const int rc = src_s[p];
+                const double t = tab[rc & 0xffff];
+                const double kap = (rc & (1 << 17)) ? kap_n : kap_p;
+                const double gd = (rc & (1 << 18)) ? g : 0.0;
+                gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
+            }
+#endif
+        }
+        __syncwarp();
+    }
+}
+
+// structural enumeration of the Jacobian: (row, col) in the reference layout for slot/lane
+bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& col) {
+    const int Np = m.Np, Ns = m.Ns, Nx = m.Nx;
+    if (lane >= Nx) return false;
+    const int x = lane;
+    const bool isp = x < Np, isn = x >= Np + Ns, elec = isp || isn;
+    const int e = isp ? x : x - Ns;
+    const bool first_e = (isp && x == 0) || (isn && x == Np + Ns);
+    const bool last_e = (isp && x == Np - 1) || (isn && x == Nx - 1);
+    const int r_ce = x, r_pe = m.off_pe + x, r_j = m.off_j + e, r_ps = m.off_ps + e, I = m.off_I;
+    auto cs = [&](int r) { return m.off_cs + e * NR + r; };
+    const bool last = x == Nx - 1;
+    switch (slot) {
+        case JS_CE_L: row = r_ce; col = x - 1; return x > 0;
+        case JS_CE_D: row = r_ce; col = x; return true;
+        case JS_CE_U: row = r_ce; col = x + 1; return x < Nx - 1;
+        case JS_CE_J: row = r_ce; col = r_j; return elec;
+        case JS_J_CS: row = r_j; col = cs(NR - 1); return elec;
+        case JS_J_CE: row = r_j; col = x; return elec;
+        case JS_J_PE: row = r_j; col = r_pe; return elec;
+        case JS_J_PS: row = r_j; col = r_ps; return elec;
+        case JS_J_J: row = r_j; col = r_j; return elec;
+        case JS_PE_L: row = r_pe; col = r_pe - 1; return x > 0 && !last;
+        case JS_PE_D: row = r_pe; col = r_pe; return true;
+        case JS_PE_U: row = r_pe; col = r_pe + 1; return !last;
+        case JS_PC_L: row = r_pe; col = x - 1; return x > 0 && !last;
+        case JS_PC_D: row = r_pe; col = x; return !last;
+        case JS_PC_U: row = r_pe; col = x + 1; return !last;
+        case JS_PE_J: row = r_pe; col = r_j; return elec && !last;
+        case JS_PS_L: row = r_ps; col = r_ps - 1; return elec && !first_e;
+        case JS_PS_D: row = r_ps; col = r_ps; return elec;
+        case JS_PS_U: row = r_ps; col = r_ps + 1; return elec && !last_e;
+        case JS_PS_J: row = r_ps; col = r_j; return elec;
+        case JS_PS_I: row = r_ps; col = I; return (isp && first_e) || (isn && last_e);
+        case JS_CS_J: row = cs(NR - 1); col = r_j; return elec;
+        case JS_CTRL_PS0: row = I; col = m.off_ps; return lane == 0 && method != METHOD_I;
+        case JS_CTRL_PSN: row = I; col = m.off_ps + m.Ne - 1; return lane == Nx - 1 && method != METHOD_I;
+        case JS_CTRL_I: row = I; col = I; return lane == 0 && method != METHOD_V;
+        default: break;
+    }
+    if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {
+        const int r = (slot - JS_CS0) / NR, c = (slot - JS_CS0) % NR;
+        row = cs(r); col = cs(c);
+        return elec && (laws::mc_mask(r) & (1u << c));
+    }
+#if PLB_TH
+    const int rT = m.off_T + m.Na + x;
+    const bool cha = lane < m.Na, chz = lane >= Nx - m.Nz;
+    const int kx = cha ? lane : lane - (Nx - m.Nz);
+    const int rX = cha ? m.off_T + lane : m.off_T + m.Na + Nx + kx;
+    if (slot >= JS_CS_T0 && slot < JS_CS_T0 + NR) { row = cs(slot - JS_CS_T0); col = rT; return elec; }
+    switch (slot) {
+        case JS_J_T: row = r_j; col = rT; return elec;
+        case JS_PE_TL: row = r_pe; col = rT - 1; return x > 0 && !last;
+        case JS_PE_TD: row = r_pe; col = rT; return !last;
+        case JS_PE_TU: row = r_pe; col = rT + 1; return !last;
+        case JS_T_TL: row = rT; col = rT - 1; return true;     // node 0: last node of the positive collector
+        case JS_T_TD: row = rT; col = rT; return true;
+        case JS_T_TU: row = rT; col = rT + 1; return true;     // node Nx-1: first node of the negative collector
+        case JS_T_J: row = rT; col = r_j; return elec;
+        case JS_T_CS: row = rT; col = cs(NR - 1); return elec;
+        case JS_TX_L: row = rX; col = rX - 1; return (cha && kx > 0) || chz;
+        case JS_TX_D: row = rX; col = rX; return cha || chz;
+        case JS_TX_U: row = rX; col = rX + 1; return cha || (chz && kx < m.Nz - 1);
+        case JS_TX_I: row = rX; col = I; return cha || chz;
+        default: break;
+    }
+    // stencils of thermal_derivatives: one-sided (own node and two inward) at the ends, central elsewhere
+    auto stencil = [&](int d, bool lo_end, bool hi_end, bool own) -> bool {
+        if (lo_end) return d >= 0;
+        if (hi_end) return d <= 0;
+        return d == -1 || d == 1 || (d == 0 && own);
+    };
+    if (slot >= JS_T_CE0 && slot < JS_T_CE0 + 5) {
+        const int d = slot - JS_T_CE0 - 2;
+        row = rT; col = x + d;
+        return stencil(d, x == 0, last, true);               // own node: K_eff(c_e) and dc_e/c_e
+    }
+    if (slot >= JS_T_PE0 && slot < JS_T_PE0 + 5) {
+        const int d = slot - JS_T_PE0 - 2;
+        row = rT; col = r_pe + d;
+        return stencil(d, x == 0, last, elec);               // own node only through eta
+    }
+    if (slot >= JS_T_PS0 && slot < JS_T_PS0 + 5) {
+        const int d = slot - JS_T_PS0 - 2;
+        row = rT; col = r_ps + d;
+        return elec && stencil(d, first_e, last_e, true);    // own node through eta
+    }
+#endif
+    return false;
+}
+
+// where K1 takes the value of the CSC position fed by (slot, lane) from
+int slot_recipe(const ModelDesc& m, int slot, int lane) {
+    if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {
+        const int rr = (slot - JS_CS0) / NR, cc = (slot - JS_CS0) % NR;
+        const int el = lane >= m.Np + m.Ns ? 1 : 0;
+        return (K1_NSTAGE * 32 + rr * NR + cc) | (1 << 16) | (el << 17) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
+    }
+    return k1_stage_slot(slot) * 32 + lane;
+}
+
+// =================================================================================================
+// initial_guess!, newtons_method!, linear solve, simulate
+// =================================================================================================
+#ifndef PLB_SIM_WARPS
+#define PLB_SIM_WARPS (PLB_TH ? 4 : 6)   // warps (systems in flight) per CTA
+#endif
+#ifndef PLB_SIM_CTAS
+#define PLB_SIM_CTAS 1            // CTAs per SM the register/shared-memory budget is sized for
+#endif
+constexpr int SIM_WARPS = PLB_SIM_WARPS;
+constexpr int SIM_CTAS = PLB_SIM_CTAS;
+constexpr size_t SIM_SMEM = sizeof(WarpSmem) * SIM_WARPS;
+
+__device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+    double* g = gws + ((size_t)blockIdx.x * SIM_WARPS + warp) * (size_t)(NGLOBAL > 0 ? NGLOBAL : 1) * VS;
+    return WarpWS{g, &sm.svec[0][0], sm.C, sm.Fa, sm.K};
+}
+
+}  // namespace PLB_NS
+}  // namespace plb
+
+#include "plb_tick.cuh"
+
+namespace plb {
+namespace PLB_NS {
+
+// initial_guess of one node (states_definition.jl:80-121): c_s from the SOC, c_e0, T0, Phi_s = U(c_s*)
+template <int CHEM>
+__device__ __forceinline__ void initial_lane(const ModelDesc& m, const WarpConst& C, const LaneRole& ro,
+                                             double SOC, LaneVec& y0) {
+    const double* th = C.theta;
+    const double csp = th[TF_c_max_p] * (SOC * (th[TF_theta_max_p] - th[TF_theta_min_p]) + th[TF_theta_min_p]);
+    const double csn = th[TF_c_max_n] * (SOC * (th[TF_theta_max_n] - th[TF_theta_min_n]) + th[TF_theta_min_n]);
+    y0.ce = th[TF_c_e0]; y0.j = 0.0; y0.pe = 0.0; y0.ps = 0.0;
+    y0.T = th[TF_T0]; y0.Tx = th[TF_T0];
+    const double cs0 = ro.sec == 0 ? csp : csn;
+#pragma unroll
+    for (int r = 0; r < NR; r++) y0.cs[r] = cs0;
+    if (ro.elec) {
+        const double thx = cs0 * C.sec[SC_inv_cmax][ro.sec];
+        double U, dU, dUdT = 0.0, ddUdT = 0.0;
+        if (CHEM == CHEM_LCO) {
+            if (ro.sec == 0) laws::OCV_LCO(thx, U, dU, dUdT, ddUdT);
+            else laws::OCV_LiC6(thx, sqrt(fmax(thx, 1e-4)), U, dU, dUdT, ddUdT);
+            if (C.g[GC_dUdT_on] != 0.0) U += dUdT * (C.g[GC_T] - kTref);
+        } else {
+            if (ro.sec == 0) laws::OCV_NMC(thx, U, dU);
+            else laws::OCV_LiC6_NMC(thx, U, dU);
+        }
+        y0.ps = U;
+    }
+}
+
+template <int CHEM>
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_initguess(AuxArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpWS w = make_ws(smem_raw, a.gws, warp);
+    const ModelDesc& m = a.m;
+    const LaneRole ro = make_role(m, lane);
+    const int N = m.N_tot;
+    for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
+        setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
+        LaneVec y0;
+        initial_lane<CHEM>(m, w.C, ro, a.soc[sys], y0);
+        store_lane(m, ro, w.v(V_PHI0), y0, 0.0, lane);
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) a.Y[(size_t)sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
+        __syncwarp();
+    }
+}
+
+template <int CHEM>
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_newton(AuxArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpWS w = make_ws(smem_raw, a.gws, warp);
+    const ModelDesc& m = a.m;
+    const LaneRole ro = make_role(m, lane);
+    const int N = m.N_tot;
+    for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
+        setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
+        for (int i = lane; i < N; i += 32) w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
+        __syncwarp();
+        RunCtl rc;
+        rc.method = a.method;
+        rc.value = a.values ? a.values[sys] : a.value;
+        int nres = 0, njac = 0;
+        const int it = newton_init<CHEM>(m, w, ro, rc, a.o, w.v(V_PHI0), w.v(V_PHI1), lane, nres, njac);
+        for (int i = lane; i < N; i += 32) {
+            a.Y[(size_t)sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
+            a.YP[(size_t)sys * N + ref_index(m, i)] = it > 0 ? w.v(V_PHI1)[i] : 0.0;
+        }
+        if (lane == 0 && a.status) a.status[sys] = it;
+        __syncwarp();
+    }
+}
+
+// x = (dF/dY + gamma dF/dY')^{-1} rhs at the state (Y, Y'): Jacobian evaluation, structured
+// factorisation and one solve -- what KLU does for IDA (model_evaluation.jl:265-271)
+template <int CHEM>
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_linsolve(AuxArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpWS w = make_ws(smem_raw, a.gws, warp);
+    const ModelDesc& m = a.m;
+    const LaneRole ro = make_role(m, lane);
+    const int N = m.N_tot;
+    for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
+        setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
+        for (int i = lane; i < N; i += 32) {
+            w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
+            w.v(V_PHI1)[i] = a.YP[(size_t)sys * N + ref_index(m, i)];
+            w.v(V_EE)[i] = a.rhs[(size_t)sys * N + ref_index(m, i)];
+        }
+        __syncwarp();
+        LaneVec y, yp, res, g;
+        double Iy, Ip, gI;
+        load_lane(m, ro, w.v(V_PHI0), y, Iy);
+        load_lane(m, ro, w.v(V_PHI1), yp, Ip);
+        load_lane(m, ro, w.v(V_EE), g, gI);
+        LaneJac J;
+        CtrlRow ctrl;
+        lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, Iy, a.method, a.values ? a.values[sys] : a.value, res, ctrl, J);
+        const double cj = a.gamma ? a.gamma[sys] : 0.0;
+        warp_factor(m, ro, J, ctrl, cj, false, w.Fa, lane);
+        const double dI = warp_solve(m, ro, w.Fa, false, g, gI, lane);
+        __syncwarp();
+        store_lane(m, ro, w.v(V_EE), g, dI, lane);
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) a.x[(size_t)sys * N + ref_index(m, i)] = w.v(V_EE)[i];
+        if (lane == 0 && a.status) a.status[sys] = (w.Fa.schur_inv == w.Fa.schur_inv) ? 0 : -1;
+        __syncwarp();
+    }
+}
+
+template <int CHEM>
+__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_simulate(SimArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // persistent CTAs; every warp pulls systems from a global queue (step counts vary ~1.5x across
+    // a batch) and all warps of the CTA tick in lockstep through the heavy phases (plb_tick.cuh)
+    simulate_cta<CHEM>(a, smem_raw);
+}
+
+// =================================================================================================
+// launchers (host)
+// =================================================================================================
+VariantInfo info() {
+    VariantInfo v;
+    v.sim_warps = SIM_WARPS; v.sim_ctas = SIM_CTAS; v.k1_warps = K1_WARPS; v.k1_ctas = PLB_K1_CTAS;
+    v.sim_smem = SIM_SMEM; v.k1_smem = K1_SMEM; v.vs = VS; v.nglobal = NGLOBAL;
+    v.n_slots = JS_COUNT; v.n_stage = K1_NSTAGE; v.k1_src_max = K1_SRC_MAX;
+    return v;
+}
+
+#define PLB_LAUNCH(KERNEL, ARGS, GRID, BLOCK, SMEM, STREAM)                                                         \
+    do {                                                                                                            \
+        cudaError_t e_;                                                                                             \
+        if ((ARGS).m.chem == CHEM_LCO) {                                                                            \
+            e_ = cudaFuncSetAttribute(KERNEL<CHEM_LCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
+            if (e_ != cudaSuccess) return e_;                                                                       \
+            KERNEL<CHEM_LCO><<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(ARGS);                                          \
+        } else {                                                                                                    \
+            if (TH) return cudaErrorInvalidValue; /* the NMC parameter set has no thermal parameters */            \
+            e_ = cudaFuncSetAttribute(KERNEL<PLB_TH ? CHEM_LCO : CHEM_NMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
+            if (e_ != cudaSuccess) return e_;                                                                       \
+            KERNEL<PLB_TH ? CHEM_LCO : CHEM_NMC><<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(ARGS);                      \
+        }                                                                                                           \
+        return cudaGetLastError();                                                                                  \
+    } while (0)
+
+cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_resjac, a, grid, K1_WARPS * 32, K1_SMEM, s); }
+cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_initguess, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
+cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_newton, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
+cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_linsolve, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
+cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_simulate, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
+
+}  // namespace PLB_NS
+}  // namespace plb

@@ -2,7 +2,7 @@
 
 Simulations are independent, so the path shards with NO data-path collective: rank r owns the
 contiguous block [r*B/G, (r+1)*B/G) of systems.  The only collective is one all-gather of the
-fixed-size (64-byte) per-system summary records after the integrate kernel -- `nccl` on GPUs,
+fixed-size (80-byte) per-system summary records after the integrate kernel -- `nccl` on GPUs,
 `gloo` in the CPU tests.
 """
 import numpy as np
@@ -16,7 +16,7 @@ def shard_bounds(B, world, rank):
 
 
 def gather_summaries(local, B, group=None):
-    """all-gather variable-size blocks of the [n_local, 8] float64 summary records into [B, 8]"""
+    """all-gather variable-size blocks of the [n_local, 10] float64 summary records into [B, 10]"""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -30,5 +30,5 @@ def gather_summaries(local, B, group=None):
 
 
 def summaries_as_f64(summ):
-    """structured numpy summary array -> [B, 8] float64 view (64-byte records)"""
-    return np.ascontiguousarray(summ).view(np.float64).reshape(len(summ), 8)
+    """structured numpy summary array -> [B, 10] float64 view (80-byte records)"""
+    return np.ascontiguousarray(summ).view(np.float64).reshape(len(summ), 10)

@@ -24,7 +24,7 @@ th, _ = synth_theta(p, B1, 0)
 d_theta = torch.from_numpy(th).to(dev)
 d_soc0 = torch.ones(B1, **f64)
 d_Y = torch.zeros(B1, N, **f64); d_YP = torch.zeros(B1, N, **f64)
-d_SOC = torch.zeros(B1, **f64); d_t = torch.zeros(B1, **f64); d_sum = torch.zeros(B1, 8, **f64)
+d_SOC = torch.zeros(B1, **f64); d_t = torch.zeros(B1, **f64); d_sum = torch.zeros(B1, 10, **f64)
 d_trn = torch.zeros(B1, dtype=torch.int32, device=dev)
 o = _lib.Opts(); L.plb_opts_defaults(h, C.byref(o))
 b = _lib.Bounds(); L.plb_bounds_defaults(h, C.byref(b))
@@ -35,7 +35,7 @@ def sim(B, tf):
     run = _lib.Run(0, 0, -1.0, tf, 1, 0)
     _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(b), d_soc0.data_ptr(),
                               d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(), d_t.data_ptr(), d_sum.data_ptr(), 0,
-                              None, None, None, None, d_trn.data_ptr(), 1))
+                              None, None, None, None, None, d_trn.data_ptr(), 1))
 
 
 sim(B1, 1800.0)                      # launch 1: mid-discharge states for K1

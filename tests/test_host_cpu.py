@@ -85,6 +85,9 @@ def test_generated_laws_match_reference_formulas():
     assert a["ddUdT"] == pytest.approx((b["dUdT"] - cm["dUdT"]) / (2 * h), rel=2e-6)
     a = run("K_eff", c=1100.0, T=300.0); b = run("K_eff", c=1100.0 + 1e-3, T=300.0); cm = run("K_eff", c=1100.0 - 1e-3, T=300.0)
     assert a["dKdc"] == pytest.approx((b["K"] - cm["K"]) / 2e-3, rel=1e-6)
+    a = run("K_eff_T", c=1100.0, T=310.0); b = run("K_eff_T", c=1100.0, T=310.0 + 1e-3); cm = run("K_eff_T", c=1100.0, T=310.0 - 1e-3)
+    assert a["dKdT"] == pytest.approx((b["K"] - cm["K"]) / 2e-3, rel=1e-6)
+    assert a["K"] == run("K_eff", c=1100.0, T=310.0)["K"]
     a = run("D_eff_nl", c=1100.0, T=300.0); b = run("D_eff_nl", c=1100.0 + 1e-3, T=300.0); cm = run("D_eff_nl", c=1100.0 - 1e-3, T=300.0)
     assert a["dDdc"] == pytest.approx((b["D"] - cm["D"]) / 2e-3, rel=1e-6)
 
@@ -94,7 +97,13 @@ def test_generated_particle_operator_matches_oracle_residual():
     import oracle as O
     src = open(os.path.join(ROOT, "petlion.jl_b200", "csrc", "laws_generated.cuh")).read()
     rows = re.findall(r"^\s+\{([^}]*)\},$", src, flags=re.M)
-    MC = np.array([[float(x) for x in r.split(",")] for r in rows])
+    MC = np.array([[float(x) for x in r.split(",")] for r in rows[:10]])      # MC, then EV and EVI
+    EV = np.array([[float(x) for x in r.split(",")] for r in rows[10:20]])
+    EVI = np.array([[float(x) for x in r.split(",")] for r in rows[20:30]])
+    EL = np.array([float(x) for x in re.search(r"EL\[NR\] = \{([^}]*)\}", src).group(1).split(",")])
+    # eigen-basis of the particle operator used by the thermal variant's solver
+    np.testing.assert_allclose(EV @ np.diag(EL) @ EVI, MC, rtol=0, atol=1e-11 * np.abs(MC).max())
+    np.testing.assert_allclose(EV @ EVI, np.eye(10), atol=1e-13)
     BJ = float(re.search(r"BJ = ([0-9.eE+-]+);", src).group(1))
     assert MC.shape == (10, 10)
     m = O.make_model("LCO"); th = O.theta_defaults("LCO"); L = O.layout(m); names = O.theta_names()
