@@ -108,6 +108,10 @@ struct plb_handle_s {
     long long launches = 0;
     float last_ms = 0.f;
     int num_sms = 0;
+    // device staging buffers of PLB_MEM_HOST calls: grow-only, reused from call to call (a cudaMalloc /
+    // cudaFree pair per argument and call costs more than the transfers themselves)
+    void* pool_ptr[20] = {};
+    size_t pool_cap[20] = {};
 };
 
 const char* plb_last_error(void) { return g_err.c_str(); }
@@ -216,6 +220,7 @@ int plb_variant_info(int temperature, long long* out) {
 int plb_destroy(plb_handle h) {
     if (!h) return 0;
     for (int i = 0; i < 3; i++) cudaFree(h->d_src[i]);
+    for (int i = 0; i < 20; i++) if (h->pool_ptr[i]) cudaFree(h->pool_ptr[i]);
     cudaFree(h->d_counter);
     cudaFree(h->d_gws);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -281,12 +286,30 @@ int plb_jac_pattern(plb_handle h, int method, int* colptr, int* rowval, int one_
     return 0;
 }
 
-// device staging helper for PLB_MEM_HOST calls
+// device staging helper for PLB_MEM_HOST calls: slot `k` of the handle's grow-only pool
 struct DevBuf {
     void* p = nullptr;
     size_t n = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { n = bytes; return bytes ? (cudaMalloc(&p, bytes) == cudaSuccess ? 0 : -1) : 0; }
+    plb_handle_s* h = nullptr;
+    int k = 0;
+    int alloc(size_t bytes) {
+        n = bytes;
+        if (!bytes) return 0;
+        if (h->pool_cap[k] < bytes) {
+            if (h->pool_ptr[k]) cudaFree(h->pool_ptr[k]);
+            h->pool_ptr[k] = nullptr; h->pool_cap[k] = 0;
+            if (cudaMalloc(&h->pool_ptr[k], bytes) != cudaSuccess) return -1;
+            h->pool_cap[k] = bytes;
+        }
+        p = h->pool_ptr[k];
+        return 0;
+    }
+};
+// the staging slots of one API call
+struct DevBufs {
+    DevBuf b[20];
+    explicit DevBufs(plb_handle_s* h) { for (int i = 0; i < 20; i++) { b[i].h = h; b[i].k = i; } }
+    DevBuf& operator[](int i) { return b[i]; }
 };
 template <class T>
 static int stage_in(DevBuf& b, const T*& ptr, size_t count, int mem, cudaStream_t s) {
@@ -327,7 +350,8 @@ int plb_initial_guess(plb_handle h, int B, const double* soc, const double* thet
     if (B <= 0) return 0;
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
-    DevBuf b1, b2, b3;
+    DevBufs db(h);
+    DevBuf &b1 = db[0], &b2 = db[1], &b3 = db[2];
     double* hostY;
     if (stage_in(b1, soc, (size_t)B, mem, s) || stage_in(b2, theta, (size_t)B * m.ntheta, mem, s) ||
         stage_inout(b3, Y0, hostY, (size_t)B * m.N_tot, mem, false, s)) return -1;
@@ -350,7 +374,8 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     const int nnz = (int)h->rowval[run->method].size();
-    DevBuf b1, b2, b3, b4, b5, b6, b7;
+    DevBufs db(h);
+    DevBuf &b1 = db[0], &b2 = db[1], &b3 = db[2], &b4 = db[3], &b5 = db[4], &b6 = db[5], &b7 = db[6];
     double *hostR, *hostN;
     if (stage_in(b1, Y, (size_t)B * m.N_tot, mem, s) || stage_in(b2, YP, (size_t)B * m.N_tot, mem, s) ||
         stage_in(b3, gamma, (size_t)B, mem, s) || stage_in(b4, theta, (size_t)B * m.ntheta, mem, s) ||
@@ -379,7 +404,8 @@ int plb_newton_init(plb_handle h, int B, double* Y, double* YP, const double* th
     if (!run || !opts) return fail("plb_newton_init: null run/opts");
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
-    DevBuf b1, b2, b3, b4, b5;
+    DevBufs db(h);
+    DevBuf &b1 = db[0], &b2 = db[1], &b3 = db[2], &b4 = db[3], &b5 = db[4];
     double *hostY, *hostYP;
     int* hostS;
     if (stage_in(b1, theta, (size_t)B * m.ntheta, mem, s) || stage_in(b2, values, (size_t)B, mem, s) ||
@@ -408,7 +434,8 @@ int plb_linear_solve(plb_handle h, int B, const double* Y, const double* YP, con
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     const size_t BN = (size_t)B * m.N_tot;
-    DevBuf b1, b2, b3, b4, b5, b6, b7, b8;
+    DevBufs db(h);
+    DevBuf &b1 = db[0], &b2 = db[1], &b3 = db[2], &b4 = db[3], &b5 = db[4], &b6 = db[5], &b7 = db[6], &b8 = db[7];
     double* hostX;
     int* hostS;
     if (stage_in(b1, Y, BN, mem, s) || stage_in(b2, YP, BN, mem, s) || stage_in(b3, gamma, (size_t)B, mem, s) ||
@@ -443,7 +470,7 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     const size_t BN = (size_t)B * m.N_tot, BS = (size_t)B * (n_save_max > 0 ? n_save_max : 0);
-    DevBuf b[16];
+    DevBufs b(h);
     double *hY, *hYP, *hSOC, *ht, *htt, *htV, *htI, *htS, *htT;
     int* htn;
     plb_summary* hsum;
