@@ -22,7 +22,10 @@ extern "C" {
 typedef struct plb_handle_s *plb_handle;
 
 enum { PLB_CATHODE_LCO = 0, PLB_CATHODE_NMC = 1 };
-enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2 }; /* method_I / method_V / method_P */
+/* method_I / method_V / method_P (scalar_residual.jl:167-202); PLB_METHOD_DT = the `dT` input of thermal
+ * models (constant spatially-averaged temperature: control row val - temperature_weighting(Y'[T]),
+ * src/physics_equations/input_methods.jl:182-189; dT=:hold == dT=0) */
+enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2, PLB_METHOD_DT = 3 };
 enum { PLB_MEM_HOST = 0, PLB_MEM_DEVICE = 1 };                /* where the caller's buffers live */
 
 /* petlion(cathode; N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, temperature, aging) -- src/params.jl:119-174 */

@@ -47,7 +47,11 @@ typedef struct {
 #define ORC_NTHETA ((int)(sizeof(orc_theta) / sizeof(double)))
 
 enum { ORC_CATHODE_LCO = 0, ORC_CATHODE_NMC = 1 };
-enum { ORC_METHOD_I = 0, ORC_METHOD_V = 1, ORC_METHOD_P = 2 };
+/* method_I / method_V / method_P (scalar_residual.jl:167-202) and `dT` = the constant_temperature
+ * residual of input_methods.jl:182-189 (control row  val - temperature_weighting(Y'[T])).
+ * ORC_METHOD_DT_ALG is internal: the same row inside newtons_method!, where the reference substitutes
+ * Y'_diff -> rhs_diff(Y) (scalar_residual.jl:347-363). */
+enum { ORC_METHOD_I = 0, ORC_METHOD_V = 1, ORC_METHOD_P = 2, ORC_METHOD_DT = 3, ORC_METHOD_DT_ALG = 4 };
 
 /* model structure: petlion(cathode; N_p, ..., temperature, aging) -- src/params.jl:119-174 */
 typedef struct {

@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 
 CATHODES = {"LCO": 0, "NMC": 1}
-METHODS = {"I": 0, "V": 1, "P": 2}
+METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3}
 EXIT_REASONS = {  # src/checks.jl
     -1: "running", 0: "Final time reached", 1: "Below min. voltage", 2: "Above max. voltage",
     3: "Below min. SOC", 4: "Above max. SOC", 5: "Above max. temperature", 6: "Above max. c_s_n",
@@ -251,14 +251,18 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
             # check_input_arguments, checks.jl:278-325
             raise TypeError(f"ERROR\n--------\n Invalid keyword argument: {k}")
     if len(method_kw) == 0:
-        raise TypeError("ERROR\n--------\n No inputs are selected, choose one from: (I, V, P)")
+        raise TypeError("ERROR\n--------\n No inputs are selected, choose one from: (I, V, P, dT)")
     if len(method_kw) > 1:
-        raise TypeError("ERROR\n--------\n Cannot select more than one input from: (I, V, P)")
+        raise TypeError("ERROR\n--------\n Cannot select more than one input from: (I, V, P, dT)")
     (name, inp), = method_kw.items()
     new_run = sol is None or sol.isempty()
     kind, value, vals = 0, 0.0, None
+    if name == "dT" and not p.numerics.temperature:
+        raise ValueError("Temperature must be enabled when using `dT`.")      # input_methods.jl:183
     if isinstance(inp, str):
-        if inp == "hold":
+        if inp == "hold" and name == "dT":
+            kind = 1       # custom_res!: :hold needs no previous run for a residual input (hold_val = 0)
+        elif inp == "hold":
             if new_run:
                 raise ValueError("Cannot use `:hold` without a previous simulation.")   # checks.jl:385
             kind = 1

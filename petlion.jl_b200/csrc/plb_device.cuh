@@ -40,7 +40,7 @@ enum SecField {
     // thermal: 1/(rho Cp), F a, sigma_eff, Ea_D/R, Ea_k/R   (SC_kap, SC_Rp_Ds, SC_k2 are then the values at T_ref)
     SC_irc, SC_Fa, SC_sig, SC_EaD, SC_Eak, SC_COUNT
 };
-enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_Tamb, GC_COUNT };
+enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_Tamb, GC_invL, GC_COUNT };
 
 struct WarpConst {
     double sec[SC_COUNT][4];   // [field][section p,s,n,pad]
@@ -174,7 +174,10 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
             C.g[GC_I1C] = I1C;
             C.g[GC_psI_p] = I1C * h / sig;     // d res_Phi_s[first p] / dI   (residuals.jl:679)
             C.g[GC_dUdT_on] = (m.chem == CHEM_LCO && (TH || !Tref)) ? 1.0 : 0.0;
-            if (TH) C.g[GC_Tamb] = th[TF_T_amb];
+            if (TH) {
+                C.g[GC_Tamb] = th[TF_T_amb];
+                C.g[GC_invL] = 1.0 / (th[TF_l_a] + th[TF_l_p] + th[TF_l_s] + th[TF_l_n] + th[TF_l_z]);
+            }
         }
         if (s == 2) C.g[GC_psI_n] = -calc_I1C(th) * h / sig;   // d res_Phi_s[last n] / dI (residuals.jl:680)
     }
@@ -280,6 +283,9 @@ struct LaneJac {
 // Control row (scalar_residual.jl:167-202): residual and its three possible Jacobian entries
 struct CtrlRow {
     double res, g_ps0, g_psN, g_I;
+    // dT control (thermal variant): coefficients of this lane's Y'[T] / Y'[collector T] in the row
+    // (-temperature_weighting weights); zero for the other methods
+    double gTn, gTx;
 };
 
 template <int CHEM, bool WITH_JAC>
@@ -527,7 +533,23 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     {
         const double ps0 = shfl_from(y.ps, 0), psN = shfl_from(y.ps, m.Nx - 1);
         const double V = ps0 - psN;
+        ctrl.gTn = 0.0; ctrl.gTx = 0.0;
         if (method == METHOD_I) { ctrl.res = Iapp - value; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; }
+#if PLB_TH
+        else if (method == METHOD_DT || method == METHOD_DT_ALG) {
+            // run_residual of the constant-temperature mode: val - temperature_weighting(Y'[T])
+            // (scalar_residual.jl:172, auxiliary_states_and_coefficients.jl:649-679)
+            const double invL = C.g[GC_invL];
+            const double wn = ro.act ? C.s5[0][1 + s] * invL : 0.0;
+            const double wc = ro.cha ? C.s5[0][0] * invL : (ro.chz ? C.s5[0][4] * invL : 0.0);
+            const bool alg = method == METHOD_DT_ALG;
+            const double a = alg ? wn * (res.T + yp.T) + wc * (res.Tx + yp.Tx) : wn * yp.T + wc * yp.Tx;
+            ctrl.res = value - warp_sum(a);
+            ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.gTn = -wn; ctrl.gTx = -wc;
+            // inside newtons_method! the row depends on I through the Joule heating of the collectors
+            ctrl.g_I = alg ? -warp_sum(wc * 2.0 * C.xq[ro.x] * Iapp) : 0.0;
+        }
+#endif
         else if (method == METHOD_V) { ctrl.res = V - value; ctrl.g_ps0 = 1.0; ctrl.g_psN = -1.0; ctrl.g_I = 0.0; }
         else {
             const double I1C = C.g[GC_I1C];
@@ -915,8 +937,36 @@ struct WarpFactor {
     double wT[NR][32];         // EVI * (d res_cs / dT)
     double csj[32];
     double chm[32], chip[32], chup[32], hm[32];   // collector chains: multiplier, 1/pivot, successor coupling; end-node multiplier
-    double schur_inv, g_ps0, g_psN, pad;
+    double gT[32], gX[32];     // dT control: border-row entries on this lane's T / collector T
+    double schur_inv, g_ps0, g_psN;
+    double mode;               // border row: 0 (Phi_s ends + I), 1 dT in the DAE, 2 dT inside newtons_method!
 };
+
+// border row times a block solution.  mode 1: the row has entries on every temperature; mode 2 (algebraic
+// initialisation of the dT mode): the row is -sum_x w_x d(rhs_T[x])/d(j, Phi_e, Phi_s), whose coefficients
+// are parked in Fa.pd[0..9] / Fa.wT[0] (the particle data is not used in that mode):
+//   pd[0]: j ; pd[1..5]: Phi_e at x-2..x+2 ; pd[6..9], wT[0]: Phi_s at x-2..x+2
+__device__ __forceinline__ double border_dot(const ModelDesc& m, const WarpFactor& Fa, int mode, const double* u4,
+                                             double ux, double dj, int lane) {
+    const double x0 = shfl_from(u4[2], 0), xN = shfl_from(u4[2], m.Nx - 1);
+    double g = Fa.g_ps0 * x0 + Fa.g_psN * xN;
+    if (mode == 1) g += warp_sum(Fa.gT[lane] * u4[3] + Fa.gX[lane] * ux);
+    if (mode == 2) {
+        double a = Fa.pd[0][lane] * dj;
+        a = fma(Fa.pd[1][lane], __shfl_up_sync(FULL, u4[1], 2), a);
+        a = fma(Fa.pd[2][lane], __shfl_up_sync(FULL, u4[1], 1), a);
+        a = fma(Fa.pd[3][lane], u4[1], a);
+        a = fma(Fa.pd[4][lane], __shfl_down_sync(FULL, u4[1], 1), a);
+        a = fma(Fa.pd[5][lane], __shfl_down_sync(FULL, u4[1], 2), a);
+        a = fma(Fa.pd[6][lane], __shfl_up_sync(FULL, u4[2], 2), a);
+        a = fma(Fa.pd[7][lane], __shfl_up_sync(FULL, u4[2], 1), a);
+        a = fma(Fa.pd[8][lane], u4[2], a);
+        a = fma(Fa.pd[9][lane], __shfl_down_sync(FULL, u4[2], 1), a);
+        a = fma(Fa.wT[0][lane], __shfl_down_sync(FULL, u4[2], 2), a);
+        g += warp_sum(a);
+    }
+    return g;
+}
 
 // 4x4 inverse by the adjugate (2x2 sub-determinants), row-major
 __device__ __forceinline__ void inv4x4(const double* a, double* b) {
@@ -1285,12 +1335,24 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
     for (int k = 0; k < 4; k++) Fa.z[k][lane] = u4[k];
     Fa.zx[lane] = ux;
-    const double z0 = shfl_from(u4[2], 0), zN = shfl_from(u4[2], m.Nx - 1);
-    if (lane == 0) {
-        Fa.schur_inv = 1.0 / (ctrl.g_I - ctrl.g_ps0 * z0 - ctrl.g_psN * zN);
-        Fa.g_ps0 = ctrl.g_ps0;
-        Fa.g_psN = ctrl.g_psN;
+    const bool isdt = ctrl.gTn != 0.0 || ctrl.gTx != 0.0;     // same on every active lane
+    const int mode = __any_sync(FULL, isdt) ? (dyn ? 1 : 2) : 0;
+    Fa.gT[lane] = cj * ctrl.gTn; Fa.gX[lane] = cj * ctrl.gTx;
+    if (mode == 2) {
+        // d(control row)/d(algebraic unknowns) = sum_x gTn[x] * (T row of node x); the collector rows only see I
+        Fa.pd[0][lane] = ctrl.gTn * J.T_j;
+#pragma unroll
+        for (int k = 0; k < 5; k++) Fa.pd[1 + k][lane] = ctrl.gTn * J.T_pe[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) Fa.pd[6 + k][lane] = ctrl.gTn * J.T_ps[k];
+        Fa.wT[0][lane] = ctrl.gTn * J.T_ps[4];
     }
+    if (lane == 0) { Fa.g_ps0 = ctrl.g_ps0; Fa.g_psN = ctrl.g_psN; Fa.mode = (double)mode; }
+    __syncwarp();
+    // the border column has no entry in the j rows: dj of the column solution is q . z
+    const double djz = ro.elec ? q[0] * u4[0] + q[1] * u4[1] + q[2] * u4[2] + q[3] * u4[3] : 0.0;
+    const double gz = border_dot(m, Fa, mode, u4, ux, djz, lane);
+    if (lane == 0) Fa.schur_inv = 1.0 / (ctrl.g_I - gz);
     __syncwarp();
 }
 
@@ -1327,8 +1389,9 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     double u4[4], ux;
     core_solve(m, ch, Fa, Di, Wm, Pm, rb, (ch.ch && dyn) ? g.Tx : 0.0, u4, ux, lane);
     // border
-    const double x0 = shfl_from(u4[2], 0), xN = shfl_from(u4[2], m.Nx - 1);
-    const double dI = (gI - Fa.g_ps0 * x0 - Fa.g_psN * xN) * Fa.schur_inv;
+    const int mode = (int)Fa.mode;
+    const double dj0 = ro.elec ? q0 + Fa.q[0][lane] * u4[0] + Fa.q[1][lane] * u4[1] + Fa.q[2][lane] * u4[2] + Fa.q[3][lane] * u4[3] : 0.0;
+    const double dI = (gI - border_dot(m, Fa, mode, u4, ux, dj0, lane)) * Fa.schur_inv;
 #pragma unroll
     for (int k = 0; k < 4; k++) u4[k] -= Fa.z[k][lane] * dI;
     ux -= Fa.zx[lane] * dI;

@@ -130,8 +130,9 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
     int iter;
     bool ok = false;
+    const int meth = rc.method == METHOD_DT ? METHOD_DT_ALG : rc.method;
     for (iter = 1; iter <= 100; iter++) {
-        lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, I, rc.method, rc.value, res, ctrl, J);   // R_alg, J_alg
+        lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, I, meth, rc.value, res, ctrl, J);   // R_alg, J_alg
         n_res++; n_jac++;
         warp_factor(m, ro, J, ctrl, 0.0, true, w.Fa, lane);
         const double dI = warp_solve(m, ro, w.Fa, true, res, ctrl.res, lane);
@@ -146,7 +147,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     }
     if (!ok) return FAIL_NEWTON_INIT;
     // R_diff(YP,t,Y,YP): YP_diff = rhs of the differential rows (:460)
-    lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, I, rc.method, rc.value, res, ctrl, J);
+    lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, I, meth, rc.value, res, ctrl, J);
     n_res++;
     LaneVec ypo;
     ypo.ce = res.ce;
@@ -163,7 +164,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
         if (TH) { yn.T = y.T + dt * ypo.T; yn.Tx = y.Tx + dt * ypo.Tx; }
 #pragma unroll
         for (int r = 0; r < NR; r++) yn.cs[r] = y.cs[r] + dt * ypo.cs[r];
-        lane_eval_ni<CHEM, false>(m, w.C, ro, yn, yp, I, rc.method, rc.value, res, ctrl, J);
+        lane_eval_ni<CHEM, false>(m, w.C, ro, yn, yp, I, meth, rc.value, res, ctrl, J);
         n_res++;
         const double dI = warp_solve(m, ro, w.Fa, true, res, ctrl.res, lane);
         ypo.j = -res.j / dt; ypo.pe = -res.pe / dt; ypo.ps = -res.ps / dt;
@@ -477,7 +478,7 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
     pv.SOC = SOC;
 #if PLB_TH
     // check_stop_T :106-124
-    if (b.T_max == b.T_max) {
+    if (b.T_max == b.T_max && rc.method != METHOD_DT) {
         const double Tw = weighted_T(m, w, c, kord, false, lane);
         if (Tw - b.T_max > eps && weighted_T(m, w, d, kord, true, lane) > 0) {
             const double tf_ = (pv.T - b.T_max) / (pv.T - Tw);

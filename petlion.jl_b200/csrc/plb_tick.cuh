@@ -431,7 +431,12 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
     {
         double Ig;
         const double V0 = Y0[iP0] - Y0[iPN];
-        if (a.input_kind == 1) {
+        if (S.rc.method == METHOD_DT) {
+            // run_residual: custom_res! (model_evaluation.jl:155-170) -> value, or 0 for :hold;
+            // initial_current! (input_methods.jl:173-176): the previous current, else 1
+            if (a.input_kind == 1) S.rc.value = 0.0;
+            Ig = a.new_run ? 1.0 : I_prev_state;
+        } else if (a.input_kind == 1) {
             if (S.rc.method == METHOD_I) { S.rc.value = I_prev_state; Ig = I_prev_state; }
             else if (S.rc.method == METHOD_V) { S.rc.value = V0; Ig = V0; }   // sic: input_methods.jl:58
             else { S.rc.value = I_prev_state * w.C.g[GC_I1C] * V0; Ig = I_prev_state; }
@@ -555,12 +560,14 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         const int any_jac = __syncthreads_or(do_eval && need_jac);
         LaneJac J;
         CtrlRow ctrl;
-        ctrl.res = 0.0; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0;
+        ctrl.res = 0.0; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; ctrl.gTn = 0.0; ctrl.gTx = 0.0;
         if (do_eval) {
             // each warp picks the variant from its OWN state only, so a system's arithmetic (and therefore
             // its bits) never depends on which other systems share the CTA
-            if (need_jac) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, S.rc.method, S.rc.value, res, ctrl, J);
-            else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, S.rc.method, S.rc.value, res, ctrl, J);
+            // the dT control row takes its newtons_method! form during the algebraic initialisation
+            const int meth = (alg_only && S.rc.method == METHOD_DT) ? METHOD_DT_ALG : S.rc.method;
+            if (need_jac) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
+            else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
             S.M.nre++;
         }
         bool lsetup_bad = false;

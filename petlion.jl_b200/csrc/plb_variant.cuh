@@ -38,6 +38,7 @@ enum JacSlot {
     JS_CS0,                      // 100 particle-block slots r*NR+c
 #endif
     JS_CTRL_PS0 = JS_CS0 + NR * NR, JS_CTRL_PSN, JS_CTRL_I,
+    JS_CTRL_T, JS_CTRL_TX,       // dT control row: entries on this lane's T / collector T (thermal variant)
     JS_COUNT
 };
 
@@ -45,7 +46,7 @@ enum JacSlot {
 #define PLB_K1_CTAS (PLB_TH ? 2 : 3)
 #endif
 constexpr int K1_WARPS = 4;
-constexpr int K1_NSTAGE = JS_CS0 + 3;   // lane-computed slots: 0..JS_CS0-1, then the three control-row slots
+constexpr int K1_NSTAGE = JS_CS0 + 5;   // lane-computed slots: 0..JS_CS0-1, then the five control-row slots
 constexpr int K1_SRC_MAX = TH ? 3072 : 2304;        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
@@ -153,6 +154,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArg
             w.S[k1_stage_slot(JS_CTRL_PS0)][lane] = ctrl.g_ps0;
             w.S[k1_stage_slot(JS_CTRL_PSN)][lane] = ctrl.g_psN;
             w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
+            w.S[k1_stage_slot(JS_CTRL_T)][lane] = g * ctrl.gTn;
+            w.S[k1_stage_slot(JS_CTRL_TX)][lane] = g * ctrl.gTx;
             __syncwarp();
             const double* tab = &w.S[0][0];
             double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
@@ -216,9 +219,9 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         case JS_PS_J: row = r_ps; col = r_j; return elec;
         case JS_PS_I: row = r_ps; col = I; return (isp && first_e) || (isn && last_e);
         case JS_CS_J: row = cs(NR - 1); col = r_j; return elec;
-        case JS_CTRL_PS0: row = I; col = m.off_ps; return lane == 0 && method != METHOD_I;
-        case JS_CTRL_PSN: row = I; col = m.off_ps + m.Ne - 1; return lane == Nx - 1 && method != METHOD_I;
-        case JS_CTRL_I: row = I; col = I; return lane == 0 && method != METHOD_V;
+        case JS_CTRL_PS0: row = I; col = m.off_ps; return lane == 0 && (method == METHOD_V || method == METHOD_P);
+        case JS_CTRL_PSN: row = I; col = m.off_ps + m.Ne - 1; return lane == Nx - 1 && (method == METHOD_V || method == METHOD_P);
+        case JS_CTRL_I: row = I; col = I; return lane == 0 && (method == METHOD_I || method == METHOD_P);
         default: break;
     }
     if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {
@@ -246,6 +249,8 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         case JS_TX_D: row = rX; col = rX; return cha || chz;
         case JS_TX_U: row = rX; col = rX + 1; return cha || (chz && kx < m.Nz - 1);
         case JS_TX_I: row = rX; col = I; return cha || chz;
+        case JS_CTRL_T: row = I; col = rT; return method == METHOD_DT;
+        case JS_CTRL_TX: row = I; col = rX; return method == METHOD_DT && (cha || chz);
         default: break;
     }
     // stencils of thermal_derivatives: one-sided (own node and two inward) at the ends, central elsewhere

@@ -144,6 +144,20 @@ gold["ladder_4C_thermal"] = {
     "t": tt[:n1], "y_px": [y for _, y in data[:n1]], "n_points_all_runs": len(data),
 }
 
+# current trace of the same three runs (cell 18): calibrated with the two printed currents (4C on the first
+# run, 0.1959C at the very end).  The dT=:hold run starts at the duplicated hand-over point.
+svgI = cell_svg(nb, 18)
+dataI = [p for p in polylines(svgI) if len(p) > 5][0]
+yI = [y for _, y in dataI]
+aI = (4.0 - 0.1959) / (yI[0] - yI[-1])
+Iref = [4.0 + (y - yI[0]) * aI for y in yI]
+n2 = next(i for i in range(n1 + 1, len(tt)) if tt[i] <= tt[i - 1] and tt[i] > 600.0)   # hand-over to V=:hold
+gold["trace_CT_hold"] = {
+    "run": "simulate!(sol, p, dT=:hold) after the 4C run above (fast_charging_CC-CT-CV.ipynb cell 11)",
+    "note": "I in C-rate decoded from the SVG of cell 18 (resolution ~2e-4 C); t from cell 17 (~1 ms)",
+    "t": tt[n1:n2], "I": Iref[n1:n2],
+}
+
 # ---- printed summaries --------------------------------------------------------
 gold["summaries"] = {
     "1C_discharge": {"t_s": 3600.0, "V": 2.9357, "P": -85.8094, "SOC": -0.0, "exit": "SOC_min",
@@ -154,6 +168,8 @@ gold["summaries"] = {
                 "src": "CC-CV.ipynb:103-112 (older version)"},
     "thermal_4C_to_Tmax": {"t_s": 357.56, "V": 4.0312, "P": 471.33, "SOC": 0.3973, "T_C": 40.0,
                            "exit": "T_max", "src": "fast_charging_CC-CT-CV.ipynb cell 7 (current version)"},
+    "thermal_CT_hold": {"t_s": 686.41, "I_C": 2.7892, "V": 4.1, "P": 334.26, "SOC": 0.6714, "T_C": 40.0,
+                        "exit": "V_max", "src": "fast_charging_CC-CT-CV.ipynb cell 11 (current version)"},
     "thermal_CV_after_CT": {"t_s": 1865.61, "I_C": 0.1959, "P": 23.47, "SOC": 1.0, "T_C": 25.6963,
                             "exit": "SOC_max", "src": "fast_charging_CC-CT-CV.ipynb cell 13 (after a dT=:hold run)"},
     "benchmark_median_ms": 2.616,

@@ -303,3 +303,98 @@ def test_thermal_discharge_and_tight_tolerance(P, lcoT, mT):
     s = sol.results[-1].summary
     np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=1e-6)
     np.testing.assert_allclose(s["T_end"], ref["T_end"], rtol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# dT = :hold (constant-temperature control, input_methods.jl:182-189) and the README's CC-CT-CV fast charge
+# ---------------------------------------------------------------------------------------------------
+def test_dT_pattern_and_resjac(lcoT, mT):
+    cp, rv = O.jac_pattern(mT, "dT")
+    cp2, rv2 = lcoT.jac_pattern("dT")
+    assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+    B = 8
+    tho = util.oracle_theta_batch(B, first=300)
+    Y, YP = physical_states(mT, tho)
+    gam = np.random.default_rng(9).uniform(0.01, 50.0, size=B)
+    _check_resjac(lcoT, mT, tho, Y, YP, gam, "dT", 0.0, 1e-9, "physical")
+
+
+def test_dT_linear_solve_equals_dense(lcoT, mT):
+    B = 5
+    tho = util.oracle_theta_batch(B, first=60)
+    th = util.product_theta_from_oracle(lcoT, tho)
+    Y, YP = physical_states(mT, tho)
+    gam = np.array([50.0, 5.0, 0.5, 0.05, 2.0])
+    run = O.make_run("dT", 0.0)
+    cp, rv = O.jac_pattern(mT, "dT")
+    N = len(cp) - 1
+    rng = np.random.default_rng(4)
+    Js, rhs = [], []
+    for s in range(B):
+        nz = O.jacobian(mT, tho[s], run, 0.0, Y[s], YP[s], gam[s])
+        J = np.zeros((N, N))
+        for c in range(N):
+            J[rv[cp[c]:cp[c + 1]], c] = nz[cp[c]:cp[c + 1]]
+        Js.append(J); rhs.append(rng.normal(size=N) * np.abs(J).max(axis=1) * 1e-3)
+    rhs = np.stack(rhs)
+    x, st = lcoT.linear_solve(Y, YP, gam, rhs, method="dT", value=0.0, theta=th)
+    for s in range(B):
+        xr = np.linalg.solve(Js[s], rhs[s])
+        rr = np.linalg.norm(Js[s] @ x[s] - rhs[s]) / np.linalg.norm(rhs[s])
+        rr_ref = np.linalg.norm(Js[s] @ xr - rhs[s]) / np.linalg.norm(rhs[s])
+        print("dT solve", s, rr, rr_ref)
+        assert rr < 10 * rr_ref + 1e-12, (s, rr, rr_ref)
+
+
+def test_dT_newton_init_parity(lcoT, mT):
+    """the algebraic re-initialisation when the control switches from I = 4C to dT = 0: I drops to ~3.3C"""
+    L = O.layout(mT)
+    B = 8
+    tho = util.oracle_theta_batch(B, first=500)
+    th = util.product_theta_from_oracle(lcoT, tho)
+    Y0, _ = physical_states(mT, tho, t_mid=200.0)
+    st, Y, YP = lcoT.newton_init(Y0, method="dT", value=0.0, theta=th)
+    for s in range(B):
+        it, y, yp = O.newton_init(mT, tho[s], O.make_run("dT", 0.0), O.default_opts(), Y0[s])
+        assert st[s] == it, (s, st[s], it)
+        np.testing.assert_allclose(Y[s], y, rtol=1e-9, atol=1e-12)
+        assert abs(Y[s][L.I] - 4.0) > 0.1
+
+
+def test_cc_ct_cv_fast_charge(P, lcoT, mT, goldens):
+    """README.md:23-37 / examples/fast_charging_CC-CT-CV.ipynb: simulate(I=4) -> simulate!(dT=:hold) ->
+    simulate!(V=:hold), nominal cell plus a small randomised batch, against the oracle; the nominal cell also
+    against the notebook's printed summaries (3 digits: see tests/test_oracle_golden.py for why not more)."""
+    B = 12
+    tho = util.oracle_theta_batch(B, first=4000)
+    tho[0] = O.theta_defaults("LCO")
+    th = util.product_theta_from_oracle(lcoT, tho)
+    util.set_theta_batch(lcoT, th)
+    b = O.default_bounds("LCO", **T_BOUNDS)
+    sol = P.simulate(lcoT, I=4, SOC=0, **T_BOUNDS)
+    r1 = O.simulate_batch(mT, tho, O.make_run("I", 4.0), O.default_opts(), b, SOC0=0.0, n_save_max=512, nthreads=8)
+    _compare(sol, r1, min_identical=0.9)
+    P.simulate_(sol, lcoT, dT="hold", **T_BOUNDS)
+    r2 = O.simulate_batch(mT, tho, O.make_run("dT", 0.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                          state=r1["state"], n_save_max=512, nthreads=8)
+    s2 = sol.results[-1].summary
+    print("CT: gpu steps", s2["n_steps"], "ref", r2["n_steps"], "flags", s2["flag"], r2["flag"])
+    same = (s2["n_steps"] == r2["n_steps"]) & (s2["flag"] == r2["flag"])
+    assert np.mean(same) >= 0.6
+    np.testing.assert_allclose(s2["t_end"][same], r2["t_end"][same], rtol=1e-5)
+    np.testing.assert_allclose(s2["I_end"][same], r2["I_end"][same], rtol=1e-5)
+    np.testing.assert_allclose(s2["T_end"][same], r2["T_end"][same], rtol=1e-6)
+    # everybody, including the systems whose step sequence flipped somewhere: integration-tolerance agreement
+    np.testing.assert_allclose(s2["t_end"], r2["t_end"], rtol=5e-3)
+    np.testing.assert_allclose(s2["I_end"], r2["I_end"], rtol=5e-3)
+    g = goldens["summaries"]["thermal_CT_hold"]
+    assert s2["t_end"][0] == pytest.approx(g["t_s"], rel=1e-3) and s2["I_end"][0] == pytest.approx(g["I_C"], rel=1e-3)
+    assert s2["T_end"][0] - 273.15 == pytest.approx(40.0, abs=1e-3)
+    P.simulate_(sol, lcoT, V="hold", **T_BOUNDS)
+    s3 = sol.results[-1].summary
+    g3 = goldens["summaries"]["thermal_CV_after_CT"]
+    assert s3["flag"][0] == 4 and sol.results[-1].exit_reason[0] == "Above max. SOC"
+    assert s3["t_end"][0] == pytest.approx(g3["t_s"], rel=1e-2)
+    assert s3["I_end"][0] == pytest.approx(g3["I_C"], rel=3e-2)
+    assert s3["T_end"][0] - 273.15 == pytest.approx(g3["T_C"], abs=0.05)
+    assert len(sol.results) == 3

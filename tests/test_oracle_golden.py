@@ -192,3 +192,59 @@ def test_thermal_jacobian_complex_step_vs_finite_difference():
         fd = (O.residual(m, th, run, 0.0, yb, ypb) - O.residual(m, th, run, 0.0, ya, ypa)) / (2 * h)
         for k in range(cp[c], cp[c + 1]):
             assert nz[k] == pytest.approx(fd[rv[k]], rel=1e-4, abs=1e-6 * max(1.0, abs(nz[k]))), (c, rv[k])
+
+
+# ---------------------------------------------------------------------------------------------------
+# dT = :hold (constant-temperature mode) and the CV hold that follows: cells 11 and 13 of the same notebook
+# ---------------------------------------------------------------------------------------------------
+def test_thermal_CT_hold_start_matches_notebook(goldens):
+    """simulate!(sol, p, dT=:hold): the algebraic re-initialisation (I jumps from 4C to 3.28C) and the first
+    28 steps reproduce the notebook's current trace to plotting precision."""
+    m, th, b, r1 = _thermal_run()
+    r2 = O.simulate_batch(m, th, O.make_run("dT", 0.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                          state=r1["state"], n_save_max=400)
+    g = goldens["trace_CT_hold"]
+    gt, gI = np.array(g["t"]), np.array(g["I"])
+    t, I = r2["traj"]["t"][0], r2["traj"]["I"][0]
+    assert r2["n_newton_init"][0] == 3
+    np.testing.assert_allclose(I[:29], gI[:29], atol=3e-4)
+    np.testing.assert_allclose(t[:29], gt[:29], atol=2e-3)
+    assert abs(I[0] - 3.28) < 5e-4
+
+
+def test_thermal_CT_CV_printed_summaries(goldens):
+    """After step 28 a step-size decision is marginal (rr = 1.998 against the threshold 2: the oracle keeps h,
+    the reference doubled it), so from there the two integrations differ at the level of the integration
+    tolerance (reltol = 1e-3): printed end values agree to ~1e-3 relative; both bracket the converged
+    values (t = 686.69 s, I = 2.7890C; then t = 1875.6 s, I = 0.1910C at reltol 1e-5)."""
+    m, th, b, r1 = _thermal_run()
+    r2 = O.simulate_batch(m, th, O.make_run("dT", 0.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                          state=r1["state"])
+    s = goldens["summaries"]["thermal_CT_hold"]
+    assert r2["flag"][0] == 2                                        # "Above max. voltage"
+    assert r2["t_end"][0] == pytest.approx(s["t_s"], rel=1e-3)
+    assert r2["I_end"][0] == pytest.approx(s["I_C"], rel=1e-3)
+    assert r2["SOC_end"][0] == pytest.approx(s["SOC"], rel=1e-3)
+    assert r2["V_end"][0] == pytest.approx(4.1, abs=1e-9)
+    assert r2["T_end"][0] - 273.15 == pytest.approx(s["T_C"], abs=1e-3)   # the mean temperature is held
+    r3 = O.simulate_batch(m, th, O.make_run("V", 0.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                          state=r2["state"])
+    s3 = goldens["summaries"]["thermal_CV_after_CT"]
+    assert r3["flag"][0] == 4                                        # "Above max. SOC"
+    assert r3["t_end"][0] == pytest.approx(s3["t_s"], rel=1e-2)
+    assert r3["I_end"][0] == pytest.approx(s3["I_C"], rel=3e-2)
+    assert r3["T_end"][0] - 273.15 == pytest.approx(s3["T_C"], abs=0.05)
+
+
+def test_dT_jacobian_pattern_and_values():
+    m = O.make_model("LCO", temperature=True); th = O.theta_defaults("LCO"); L = O.layout(m)
+    cp, rv = O.jac_pattern(m, "dT")
+    assert len(rv) == 2883 - 1 + 50                                  # control row: the 50 temperatures
+    ctrl_cols = [c for c in range(L.N_tot) if L.I in rv[cp[c]:cp[c + 1]]]
+    assert ctrl_cols == list(range(L.T, L.T + 50))
+    y = O.initial_guess(m, th, 0.4); y[L.I] = 3.0
+    nz = O.jacobian(m, th, O.make_run("dT", 0.0), 0.0, y, np.zeros_like(y), 2.5)
+    vals = np.array([nz[cp[c] + list(rv[cp[c]:cp[c + 1]]).index(L.I)] for c in ctrl_cols])
+    names = O.theta_names(); d = dict(zip(names, th))
+    w = np.repeat([d["l_a"], d["l_p"], d["l_s"], d["l_n"], d["l_z"]], 10) / 10 / (d["l_a"] + d["l_p"] + d["l_s"] + d["l_n"] + d["l_z"])
+    np.testing.assert_allclose(vals, -2.5 * w, rtol=1e-12)           # -gamma * temperature_weighting weights
