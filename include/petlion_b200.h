@@ -34,7 +34,7 @@ typedef struct {
     int N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n;
     int temperature; /* 0: isothermal.  1: temperature=true (LCO only: NMC has no thermal parameters;
                         needs N_p, N_n >= 5 and N_a + N_z <= N_p + N_s + N_n)                  */
-    int aging;       /* 0: none (built).        1 (:SEI): not built yet                     */
+    int aging;       /* 0: none.  1: aging=:SEI (LCO, isothermal; adds film, SOH, j_s: N = 322 for 10/10/10) */
     int device;      /* CUDA device ordinal */
 } plb_model_desc;
 
@@ -70,7 +70,7 @@ typedef struct {
 typedef struct {
     double t_end, V_end, I_end, SOC_end;
     double T_end;      /* temperature_weighting(T) of the final state [K] (T0 for isothermal models) */
-    double aux_end;    /* reserved (0) */
+    double aux_end;    /* SOH of the final state when aging=:SEI, else 0 */
     int flag;          /* run.info.flag: 0 tf, 1 V_min, 2 V_max, 3 SOC_min, 4 SOC_max, 5 T_max, 6 c_s_n,
                           7 I_max, 8 I_min, 9 c_e_min, 10 dfilm, 11 eta_plating; <0 hard failure */
     int n_steps;       /* accepted integrator steps */
@@ -153,10 +153,10 @@ int plb_simulate(plb_handle h, int B, const double *theta, const plb_run *run,
                  double *traj_V, double *traj_I, double *traj_SOC, double *traj_T, int *traj_n,
                  int mem);
 
-/* diagnostic: launch geometry of a compiled model family (temperature 0/1): out[8] = {integrator warps
+/* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared
  * memory per CTA [B], workspace vector stride, Jacobian slots per lane}.  Needs no GPU. */
-int plb_variant_info(int temperature, long long *out);
+int plb_variant_info(int family, long long *out);
 
 /* kernel launch counter (number of CUDA kernels this handle has launched) */
 long long plb_launch_count(plb_handle h);

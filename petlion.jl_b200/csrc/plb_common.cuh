@@ -1,8 +1,8 @@
 // plb_common.cuh -- plain types shared by the host side (plb_kernels.cu) and the two device variants.
 //
-// The device code (plb_device.cuh, plb_integrator.cuh, plb_tick.cuh, plb_variant.cuh) is compiled twice,
-// once per model family, into namespaces plb::iso (isothermal, N = 301) and plb::th (temperature = true,
-// N = 351): plb_variant_iso.cu / plb_variant_th.cu.  The reference does the same thing at model-build
+// The device code (plb_device.cuh, plb_integrator.cuh, plb_tick.cuh, plb_variant.cuh) is compiled once per
+// model family, into namespaces plb::iso (isothermal, N = 301), plb::th (temperature = true, N = 351) and
+// plb::sei (aging = :SEI, N = 322): plb_variant_iso.cu / plb_variant_th.cu / plb_variant_sei.cu.  The reference does the same thing at model-build
 // time: `petlion(...; temperature=true)` generates a different residual/Jacobian
 // (/root/reference/src/generate_functions.jl:102-164, src/params.jl:119-174).
 #pragma once
@@ -35,6 +35,8 @@ enum ThetaField {
     TF_Cp_a, TF_Cp_n, TF_Cp_p, TF_Cp_s, TF_Cp_z, TF_T_amb, TF_h_cell, TF_l_a, TF_l_z,
     TF_lambda_a, TF_lambda_n, TF_lambda_p, TF_lambda_s, TF_lambda_z,
     TF_rho_a, TF_rho_n, TF_rho_p, TF_rho_s, TF_rho_z, TF_sigma_a, TF_sigma_z,
+    // aging = :SEI (params.jl:58-117); rho_n above is shared with the thermal block
+    TF_M_n, TF_R_SEI, TF_Uref_s, TF_i_0_jside, TF_k_n_aging, TF_w,
     TF_COUNT
 };
 
@@ -43,13 +45,14 @@ struct ModelDesc {
     int Np, Ns, Nn, Nx, Ne;      // nodes per section, Nx = Np+Ns+Nn <= 32, Ne = Np+Nn
     int Na, Nz;                  // current-collector nodes (thermal models), else 0
     int thermal;                 // temperature = true
+    int aging;                   // aging = :SEI
     int chem;                    // CHEM_*
     int ntheta;                  // length of one theta row (reference order, used keys only)
     int theta_stride;            // row stride in doubles
     int mid;                     // meeting node of the twisted block elimination
     // reference layout offsets (external.jl:275-365):
-    //   c_e | c_s (particle-major) | [T: a|p|s|n|z] | j | Phi_e | Phi_s | I
-    int off_cs, off_T, off_j, off_pe, off_ps, off_I, N_diff, N_tot;
+    //   c_e | c_s (particle-major) | [T: a|p|s|n|z] | [film | SOH] | j | Phi_e | Phi_s | [j_s] | I
+    int off_cs, off_T, off_film, off_SOH, off_j, off_pe, off_ps, off_js, off_I, N_diff, N_tot;
     int8_t slot[TF_COUNT];       // theta field -> position in the row (-1: not a key of this variant)
 };
 
@@ -140,5 +143,6 @@ struct VariantInfo {
     }
 PLB_DECLARE_VARIANT(iso)
 PLB_DECLARE_VARIANT(th)
+PLB_DECLARE_VARIANT(sei)
 
 }  // namespace plb

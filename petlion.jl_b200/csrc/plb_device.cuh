@@ -28,7 +28,14 @@
 namespace plb {
 namespace PLB_NS {
 
+#ifndef PLB_SEI
+#define PLB_SEI 0
+#endif
+#if PLB_TH && PLB_SEI
+#error "temperature = true together with aging = :SEI is not built"
+#endif
 constexpr bool TH = PLB_TH != 0;
+constexpr bool SEI = PLB_SEI != 0;
 constexpr int NR = laws::NR;
 
 // ------------------------------------------------------------------------------------------------
@@ -40,7 +47,9 @@ enum SecField {
     // thermal: 1/(rho Cp), F a, sigma_eff, Ea_D/R, Ea_k/R   (SC_kap, SC_Rp_Ds, SC_k2 are then the values at T_ref)
     SC_irc, SC_Fa, SC_sig, SC_EaD, SC_Eak, SC_COUNT
 };
-enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_Tamb, GC_invL, GC_COUNT };
+enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_Tamb, GC_invL,
+                 // aging = :SEI: R_SEI, 1/k_n_aging, Uref_s, i_0_jside/F, w, M_n/rho_n
+                 GC_RSEI, GC_ikag, GC_Uref, GC_i0F, GC_w, GC_Mrho, GC_COUNT };
 
 struct WarpConst {
     double sec[SC_COUNT][4];   // [field][section p,s,n,pad]
@@ -55,6 +64,9 @@ struct WarpConst {
     double tL[32], tR[32], xL[32], xR[32], xbc[32], xq[32];
     double cinv[32];           // 1 / (distance between the centres of nodes x-1 and x+1)
     double s5[3][8];           // h, lambda, rho*Cp of the five sections a,p,s,n,z
+#endif
+#if PLB_SEI
+    double cSOH[32];           // d(rhs_SOH)/d j_s of this lane's anode node (residuals.jl:278-297)
 #endif
 };
 
@@ -87,6 +99,7 @@ __device__ __forceinline__ LaneRole make_role(const ModelDesc& m, int lane) {
 struct LaneVec {
     double ce, cs[NR], j, pe, ps;
     double T, Tx;
+    double js, film, soh;      // aging = :SEI: side-reaction flux and film thickness (anode lanes), SOH (uniform)
 };
 
 __device__ __forceinline__ double shfl_dn(double v) { return __shfl_down_sync(FULL, v, 1); }
@@ -174,6 +187,10 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
             C.g[GC_I1C] = I1C;
             C.g[GC_psI_p] = I1C * h / sig;     // d res_Phi_s[first p] / dI   (residuals.jl:679)
             C.g[GC_dUdT_on] = (m.chem == CHEM_LCO && (TH || !Tref)) ? 1.0 : 0.0;
+            if (SEI) {
+                C.g[GC_RSEI] = th[TF_R_SEI]; C.g[GC_ikag] = 1.0 / th[TF_k_n_aging]; C.g[GC_Uref] = th[TF_Uref_s];
+                C.g[GC_i0F] = th[TF_i_0_jside] / kF; C.g[GC_w] = th[TF_w]; C.g[GC_Mrho] = th[TF_M_n] / th[TF_rho_n];
+            }
             if (TH) {
                 C.g[GC_Tamb] = th[TF_T_amb];
                 C.g[GC_invL] = 1.0 / (th[TF_l_a] + th[TF_l_p] + th[TF_l_s] + th[TF_l_n] + th[TF_l_z]);
@@ -196,6 +213,35 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         C.beta[lane] = b;
     }
     __syncwarp();
+#if PLB_SEI
+    {
+        // residuals_SOH! (residuals.jl:278-297): rhs = F a_n/(3600 I1C) * trapz over the anode of j_s after a
+        // quadratic extrapolation to both ends (extrapolate_section / extrap_x_0, external.jl:496-522): linear
+        // in j_s, so every anode lane keeps its own weight
+        const int N = m.Nn, k = lane - (m.Np + m.Ns) + 1;      // 1-based node inside the section
+        double wk = 0.0;
+        if (k >= 1 && k <= N) {
+            auto xs = [&](int i) -> double { return i <= 0 ? 0.0 : (i > N ? 1.0 : (1.0 / (2.0 * N)) + (i - 1) * ((1.0 - 1.0 / N) / (N - 1))); };
+            const double x1 = xs(1), x2 = xs(2), x3 = xs(3);
+            const double r = (x3 - x1) / (x2 - x1);
+            const double den = x3 * x3 - x1 * x1 - (x2 * x2 - x1 * x1) / (x2 - x1) * (x3 - x1);
+            auto ext = [&](int i) -> double {     // weight of the i-th node from the end (1..3) in the end value
+                const double c = (i == 1 ? r - 1.0 : (i == 2 ? -r : 1.0)) / den;
+                const double b = ((i == 2 ? 1.0 : 0.0) - (i == 1 ? 1.0 : 0.0) - c * (x2 * x2 - x1 * x1)) / (x2 - x1);
+                return (i == 1 ? 1.0 : 0.0) - c * x1 * x1 - b * x1;
+            };
+            const double l = th[TF_l_n];
+            wk = 0.5 * (xs(k + 1) * l - xs(k - 1) * l);
+            const double w0 = 0.5 * (xs(1) * l - xs(0) * l), wN = 0.5 * (xs(N + 1) * l - xs(N) * l);
+            if (k <= 3) wk += w0 * ext(k);
+            if (k >= N - 2) wk += wN * ext(N + 1 - k);
+            const double eps_sn = 1.0 - (th[TF_eps_fn] + th[TF_eps_n]);
+            wk *= kF * (3 * eps_sn / th[TF_Rp_n]) / (3600 * C.g[GC_I1C]);
+        }
+        C.cSOH[lane] = wk;
+    }
+    __syncwarp();
+#endif
 #if PLB_TH
     // ---- heat conduction coefficients, residuals.jl:299-446 (five sections a | p | s | n | z) -------
     if (lane < 5) {
@@ -269,6 +315,12 @@ struct LaneJac {
     double psL, psD, psU, ps_j, ps_I;
     // particle: block = kap*MC - cj*I ; surface-row d/dj
     double kap, cs_j;
+#if PLB_SEI
+    // aging = :SEI (anode lanes): the j row gains d/dj (through the film resistance) and d/dfilm; the j_s row;
+    // the film row (d/dj_s; -cj on the diagonal); d(rhs_SOH)/dj_s.  The c_e, Phi_e, Phi_s rows see j + j_s,
+    // so their d/dj_s equals their d/dj.
+    double j_j, j_film, js_ps, js_pe, js_j, js_js, js_film, js_I, film_js, soh_js;
+#endif
 #if PLB_TH
     // temperature columns of the c_s, j and Phi_e rows
     double csT[NR], j_T, peTL, peTD, peTU;
@@ -375,8 +427,11 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         dkapT = kapx * C.sec[SC_EaD][s] * iT * iT;
         xco = 0.5 * kF / (kR * T);
     }
+    const bool sei_n = SEI && ro.sec == 2;
+    double Rfilm = 0.0;
     if (ro.elec) {
-        jtot = y.j;                                                          // build_j_total!
+        jtot = sei_n ? y.j + y.js : y.j;                                     // build_j_total!
+        if (sei_n) Rfilm = C.g[GC_RSEI] + y.film * C.g[GC_ikag];
         const double cs_s = y.cs[NR - 1];                                    // build_c_s_star!
         const double th = cs_s * C.sec[SC_inv_cmax][s];
         double U, dU, dUdT = 0.0, ddUdT = 0.0;
@@ -392,7 +447,7 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
             if (ro.sec == 0) laws::OCV_NMC(th, U, dU);
             else laws::OCV_LiC6_NMC(th, U, dU);
         }
-        const double eta = y.ps - y.pe - U;                                  // build_eta!
+        const double eta = y.ps - y.pe - U - (sei_n ? kF * y.j * Rfilm : 0.0);   // build_eta! (:272-300)
         // rxn_BV, custom_functions.jl:212-231
         const double cmax = C.sec[SC_cmax][s];
         const double arg = ce * cs_s * (cmax - cs_s);
@@ -409,6 +464,10 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
             dj_eta = k2 * sq * ch * xco;
             dj_ce = k2 * sh * isq * cs_s * (cmax - cs_s);
             dj_cs = k2 * sh * isq * ce * (cmax - 2.0 * cs_s) - dj_eta * dU * C.sec[SC_inv_cmax][s];
+#if PLB_SEI
+            J.j_j = -1.0 - (sei_n ? dj_eta * kF * Rfilm : 0.0);
+            J.j_film = sei_n ? -dj_eta * kF * y.j * C.g[GC_ikag] : 0.0;
+#endif
             if (TH) {
                 // d/dT: k(T), eta(T) through U = U0 + dUdT (T - Tref), and the 1/T in the sinh argument
                 const double iT = 1.0 / T;
@@ -461,6 +520,33 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         }
 #endif
     }
+#if PLB_SEI
+    // ---- aging = :SEI: residuals_j_s! (residuals.jl:519-552), residuals_film! (:260-276), residuals_SOH! (:278-297)
+    {
+        double jsc = 0.0, Dn = 0.0;
+        const bool charging = Iapp * C.g[GC_I1C] > 0.0;                   // I_density > 0, :546
+        if (sei_n && charging) {
+            const double eta_s = y.ps - y.pe - C.g[GC_Uref] - kF * jtot * Rfilm;
+            const double xs = 0.5 * kF / (kR * T);
+            const double Ir = Iapp * C.g[GC_I1C] / C.g[GC_I1C];
+            jsc = -fabs(C.g[GC_i0F] * pow(Ir, C.g[GC_w]) * (-exp(-xs * eta_s)));
+            Dn = -xs * jsc;                                               // d j_s_calc / d eta_s
+        }
+        res.js = sei_n ? y.js - jsc : 0.0;
+        res.film = sei_n ? -y.js * C.g[GC_Mrho] - yp.film : 0.0;
+        res.soh = warp_sum(sei_n ? C.cSOH[ro.x] * y.js : 0.0) - yp.soh;
+        if (WITH_JAC) {
+            J.js_ps = -Dn; J.js_pe = Dn;
+            J.js_j = Dn * kF * Rfilm;
+            J.js_js = sei_n ? 1.0 + Dn * kF * Rfilm : 1.0;
+            J.js_film = Dn * kF * jtot * C.g[GC_ikag];
+            J.js_I = (sei_n && charging) ? -C.g[GC_w] * jsc / Iapp : 0.0;
+            J.film_js = sei_n ? -C.g[GC_Mrho] : 0.0;
+            J.soh_js = sei_n ? C.cSOH[ro.x] : 0.0;
+            if (!ro.elec) { J.j_j = -1.0; J.j_film = 0.0; }
+        }
+    }
+#endif
 #if PLB_TH
     // ---- residuals_T!, residuals.jl:299-489; heat sources auxiliary_states_and_coefficients.jl:344-518 --
     {
@@ -615,6 +701,13 @@ struct WarpFactor {
     double q[4][32];           // j elimination: q_ce, q_pe, q_ps, inv_den
     double jcs[32];            // a_cs (j row coefficient of the surface concentration)
     double sj[3][32];          // d(row)/dj for rows ce, pe, ps
+#if PLB_SEI
+    // aging = :SEI: j, j_s and film are eliminated together node-locally.  Mi = inverse of the 3x3 local
+    // matrix (rows j, j_s, film), cpl = couplings of those rows to (c_e, Phi_e, Phi_s) and I:
+    // j_ce, j_pe, j_ps, js_pe, js_ps, js_I ; sohc = d(rhs_SOH)/dj_s ; cjv = cj of this factorisation
+    double Mi[9][32], cpl[6][32], sohc[32];
+    double cjv, pad2;
+#endif
     double schur_inv;          // 1/(g_I - g_ps0*z_ps[0] - g_psN*z_ps[N-1])
     double g_ps0, g_psN;
     double pad;
@@ -741,6 +834,40 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     // ---- 2. node-local elimination of c_s and j -------------------------------------------------
     const int el = ro.sec == 2 ? 1 : 0;
     double q_ce = 0.0, q_pe = 0.0, q_ps = 0.0, inv_den = 0.0;
+#if PLB_SEI
+    double qI = 0.0;     // (dj + dj_s) also feels dI through the side-reaction rate law
+    {
+        // local 3x3 system of (dj, dj_s, dfilm) after the particle elimination (dcs_surf = p0 + p1*dj):
+        //   [ j_j + j_cs p1   0       j_film  ] [dj   ]   [ g_j - j_cs p0 - (j_ce, j_pe, j_ps).u          ]
+        //   [ js_j            js_js   js_film ] [dj_s ] = [ g_js - (js_pe, js_ps).(u_pe, u_ps) - js_I dI  ]
+        //   [ 0               film_js -cj     ] [dfilm]   [ g_film                                        ]
+        // cathode lanes: rows/columns 2 and 3 are the identity.  alg_only freezes the film.
+        const bool sn = ro.sec == 2;
+        const double p1 = alg_only ? 0.0 : -Fa.vb[NR - 1][el];
+        double M3[9], Mi[9];
+        M3[0] = (ro.elec ? J.j_j : -1.0) + (ro.elec ? J.j_cs * p1 : 0.0); M3[1] = 0.0; M3[2] = (sn && !alg_only) ? J.j_film : 0.0;
+        M3[3] = sn ? J.js_j : 0.0; M3[4] = sn ? J.js_js : 1.0; M3[5] = (sn && !alg_only) ? J.js_film : 0.0;
+        M3[6] = 0.0; M3[7] = (sn && !alg_only) ? J.film_js : 0.0; M3[8] = (sn && !alg_only) ? -cj : 1.0;
+        inv3x3(M3, Mi);
+#pragma unroll
+        for (int k = 0; k < 9; k++) Fa.Mi[k][lane] = Mi[k];
+        const double c_jce = (ro.elec && !alg_only) ? J.j_ce : 0.0, c_jpe = ro.elec ? J.j_pe : 0.0, c_jps = ro.elec ? J.j_ps : 0.0;
+        const double c_spe = sn ? J.js_pe : 0.0, c_sps = sn ? J.js_ps : 0.0, c_sI = sn ? J.js_I : 0.0;
+        Fa.cpl[0][lane] = c_jce; Fa.cpl[1][lane] = c_jpe; Fa.cpl[2][lane] = c_jps;
+        Fa.cpl[3][lane] = c_spe; Fa.cpl[4][lane] = c_sps; Fa.cpl[5][lane] = c_sI;
+        Fa.sohc[lane] = (sn && !alg_only) ? J.soh_js : 0.0;
+        if (lane == 0) Fa.cjv = alg_only ? 0.0 : cj;
+        // the other rows see dj + dj_s = m.(local right-hand side), m = (1,1,0) Mi
+        const double m0 = Mi[0] + Mi[3], m1 = Mi[1] + Mi[4];
+        if (ro.elec) {
+            q_ce = -m0 * c_jce;
+            q_pe = -(m0 * c_jpe + m1 * c_spe);
+            q_ps = -(m0 * c_jps + m1 * c_sps);
+            qI = -m1 * c_sI;
+            inv_den = m0;
+        }
+    }
+#else
     if (ro.elec) {
         // dcs_surf = p0 + p1*dj with p1 = -(Sinv b)[surf]
         const double p1 = alg_only ? 0.0 : -Fa.vb[NR - 1][el];
@@ -749,6 +876,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         q_pe = -J.j_pe * inv_den;
         q_ps = -J.j_ps * inv_den;
     }
+#endif
     Fa.q[0][lane] = q_ce; Fa.q[1][lane] = q_pe; Fa.q[2][lane] = q_ps; Fa.q[3][lane] = inv_den;
     Fa.jcs[lane] = J.j_cs;
     const double sj0 = alg_only ? 0.0 : J.ce_j, sj1 = J.pe_j, sj2 = J.ps_j;
@@ -843,7 +971,12 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
     for (int k = 0; k < 9; k++) { Fa.Dinv[k][lane] = Di[k]; Fa.Wm[k][lane] = Wm[k]; Fa.Pm[k][lane] = Pm[k]; }
     // ---- 4. border: z = T^{-1} e_I, then the Schur complement ------------------------------------
+#if PLB_SEI
+    // border column dF/dI: the Phi_s end rows, plus (through dj + dj_s) the I-dependence of the j_s rows
+    const double zf[3] = {sj0 * qI, sj1 * qI, J.ps_I + sj2 * qI};
+#else
     const double zf[3] = {0.0, 0.0, J.ps_I};   // border column e_I restricted to this node (Phi_s rows only)
+#endif
     double u3[3];
     thomas_sweeps(m.Nx, ch, Wm, Pm, Di, zf, u3);
     Fa.z[0][lane] = u3[0]; Fa.z[1][lane] = u3[1]; Fa.z[2][lane] = u3[2];
@@ -877,8 +1010,20 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 #pragma unroll
         for (int r = 0; r < NR; r++) s[r] = 0.0;
     }
+#if PLB_SEI
+    const bool sn = ro.sec == 2;
+    double Mi[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Mi[k] = Fa.Mi[k][lane];
+    // local right-hand side of (j, j_s, film) after the particle elimination
+    double v0 = ro.elec ? g.j - Fa.jcs[lane] * p0 : 0.0;
+    double v1 = sn ? g.js : 0.0;
+    const double v2 = (sn && !alg_only) ? g.film : 0.0;
+    const double q0 = ro.elec ? (Mi[0] + Mi[3]) * v0 + (Mi[1] + Mi[4]) * v1 + (Mi[2] + Mi[5]) * v2 : 0.0;
+#else
     const double inv_den = Fa.q[3][lane];
     const double q0 = ro.elec ? (g.j - Fa.jcs[lane] * p0) * inv_den : 0.0;
+#endif
     double rf[3];
     rf[0] = alg_only ? 0.0 : g.ce - Fa.sj[0][lane] * q0;
     rf[1] = g.pe - Fa.sj[1][lane] * q0;
@@ -894,8 +1039,21 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     const double x0 = shfl_from(u3[2], 0), xN = shfl_from(u3[2], m.Nx - 1);
     const double dI = (gI - Fa.g_ps0 * x0 - Fa.g_psN * xN) * Fa.schur_inv;
     u3[0] -= Fa.z[0][lane] * dI; u3[1] -= Fa.z[1][lane] * dI; u3[2] -= Fa.z[2][lane] * dI;
-    // back-substitute j and the particle
+    // back-substitute j (and j_s, film) and the particle
+#if PLB_SEI
+    v0 -= Fa.cpl[0][lane] * u3[0] + Fa.cpl[1][lane] * u3[1] + Fa.cpl[2][lane] * u3[2];
+    v1 -= Fa.cpl[3][lane] * u3[1] + Fa.cpl[4][lane] * u3[2] + Fa.cpl[5][lane] * dI;
+    const double dj = ro.elec ? Mi[0] * v0 + Mi[1] * v1 + Mi[2] * v2 : 0.0;
+    const double djs = sn ? Mi[3] * v0 + Mi[4] * v1 + Mi[5] * v2 : 0.0;
+    const double dfilm = (sn && !alg_only) ? Mi[6] * v0 + Mi[7] * v1 + Mi[8] * v2 : 0.0;
+    // SOH: its column only holds -cj on the diagonal; its row is dense over j_s (residuals.jl:278-297)
+    const double sj_sum = warp_sum(Fa.sohc[lane] * djs);
+    g.soh = alg_only ? 0.0 : (g.soh - sj_sum) / (-Fa.cjv);
+    g.js = djs;
+    g.film = dfilm;
+#else
     const double dj = ro.elec ? q0 + Fa.q[0][lane] * u3[0] + Fa.q[1][lane] * u3[1] + Fa.q[2][lane] * u3[2] : 0.0;
+#endif
     g.ce = alg_only ? 0.0 : u3[0];
     g.pe = u3[1];
     g.ps = ro.elec ? u3[2] : 0.0;

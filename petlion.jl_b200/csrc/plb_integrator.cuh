@@ -18,7 +18,7 @@
 namespace plb {
 namespace PLB_NS {
 
-constexpr int VS = TH ? 352 : 304;   // vector stride in doubles (N_tot = 301 / 351 padded)
+constexpr int VS = TH ? 352 : (SEI ? 336 : 304);   // vector stride in doubles (N_tot = 301 / 351 / 322 padded)
 enum VecId { V_PHI0 = 0, V_PHI1, V_PHI2, V_PHI3, V_PHI4, V_PHI5, V_YPRED, V_YPPRED, V_EWT, V_EE, V_COUNT };
 
 struct IdaCoef {
@@ -77,6 +77,12 @@ __device__ __forceinline__ void load_lane(const ModelDesc& m, const LaneRole& ro
         y.T = ro.act ? v[m.off_T + m.Na + ro.x] : 0.0;
         y.Tx = ro.ix >= 0 ? v[m.off_T + ro.ix] : 0.0;
     }
+    if (SEI) {
+        const int k = ro.x - (m.Np + m.Ns);
+        y.js = ro.sec == 2 ? v[m.off_js + k] : 0.0;
+        y.film = ro.sec == 2 ? v[m.off_film + k] : 0.0;
+        y.soh = v[m.off_SOH];
+    }
     I = v[m.off_I];
 }
 __device__ __forceinline__ void store_lane(const ModelDesc& m, const LaneRole& ro, double* v,
@@ -91,6 +97,11 @@ __device__ __forceinline__ void store_lane(const ModelDesc& m, const LaneRole& r
     if (TH) {
         if (ro.act) v[m.off_T + m.Na + ro.x] = y.T;
         if (ro.ix >= 0) v[m.off_T + ro.ix] = y.Tx;
+    }
+    if (SEI) {
+        const int k = ro.x - (m.Np + m.Ns);
+        if (ro.sec == 2) { v[m.off_js + k] = y.js; v[m.off_film + k] = y.film; }
+        if (lane == 0) v[m.off_SOH] = y.soh;
     }
     if (lane == 0) v[m.off_I] = I;
 }
@@ -125,7 +136,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     CtrlRow ctrl;
     double I;
     load_lane(m, ro, Y, y, I);
-    yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0;
+    yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0; yp.js = 0.0; yp.film = 0.0; yp.soh = 0.0;
 #pragma unroll
     for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
     int iter;
@@ -140,6 +151,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
         double s = 0.0;
         if (ro.elec) { y.j -= res.j; y.ps -= res.ps; s += res.j * res.j + res.ps * res.ps; }
         if (ro.act) { y.pe -= res.pe; s += res.pe * res.pe; }
+        if (SEI && ro.sec == 2) { y.js -= res.js; s += res.js * res.js; }
         I -= dI;
         s = warp_sum(s) + dI * dI;
         if (!(s == s) || isinf(s)) return FAIL_NEWTON_INIT;
@@ -152,6 +164,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     LaneVec ypo;
     ypo.ce = res.ce;
     ypo.T = TH ? res.T : 0.0; ypo.Tx = TH ? res.Tx : 0.0;
+    ypo.film = SEI ? res.film : 0.0; ypo.soh = SEI ? res.soh : 0.0; ypo.js = 0.0;
 #pragma unroll
     for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
     // estimate dY_alg/dt (:462-477): Delta_t = max(10 reltol_init, sqrt(eps(c_e0)))
@@ -162,12 +175,14 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
         LaneVec yn = y;
         yn.ce = y.ce + dt * ypo.ce;
         if (TH) { yn.T = y.T + dt * ypo.T; yn.Tx = y.Tx + dt * ypo.Tx; }
+        if (SEI) { yn.film = y.film + dt * ypo.film; yn.soh = y.soh + dt * ypo.soh; }
 #pragma unroll
         for (int r = 0; r < NR; r++) yn.cs[r] = y.cs[r] + dt * ypo.cs[r];
         lane_eval_ni<CHEM, false>(m, w.C, ro, yn, yp, I, meth, rc.value, res, ctrl, J);
         n_res++;
         const double dI = warp_solve(m, ro, w.Fa, true, res, ctrl.res, lane);
         ypo.j = -res.j / dt; ypo.pe = -res.pe / dt; ypo.ps = -res.ps / dt;
+        if (SEI) ypo.js = -res.js / dt;
         store_lane(m, ro, Y, y, I, lane);
         store_lane(m, ro, YP, ypo, -dI / dt, lane);
     }
@@ -405,7 +420,7 @@ __device__ __forceinline__ double interp_yp(const WarpWS& w, const double* d, in
 }
 
 struct PrevVals {   // boundary_stop_prev_values, structures.jl:174-184
-    double frac, V, SOC, c_s_n, I, eta_plating, c_e_min, T;
+    double frac, V, SOC, c_s_n, I, eta_plating, c_e_min, T, dfilm;
 };
 
 // temperature_weighting(T): length-weighted mean over the five sections
@@ -485,6 +500,20 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
             if (tf_ < pv.frac) { pv.frac = tf_; flag = 5; }
         }
         pv.T = Tw;
+    }
+#endif
+#if PLB_SEI
+    // check_stop_dfilm :204-224 (the largest film growth rate over the anode; no derivative-sign test)
+    {
+        double mx = -INFINITY;
+        for (int k = lane; k < m.Nn; k += 32) mx = fmax(mx, interp_yp(w, d, kord, m.off_film + k));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+        if (b.dfilm_max == b.dfilm_max && mx - b.dfilm_max > eps) {
+            const double tf_ = (pv.dfilm - b.dfilm_max) / (pv.dfilm - mx);
+            if (tf_ < pv.frac) { pv.frac = tf_; flag = 10; }
+        }
+        pv.dfilm = mx;
     }
 #endif
     // check_stop_c_s_surf :141-161

@@ -31,11 +31,11 @@ constexpr int NR_HOST = 10;   // N_r of the built variants (laws::NR)
         if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-struct KeyDef { const char* utf8; const char* ascii; int field; double lco, nmc; int thermal_only; };
+struct KeyDef { const char* utf8; const char* ascii; int field; double lco, nmc; int only; };   // only: bit 0 thermal, bit 1 aging (0: always)
 // reference keys (UTF-8) <-> canonical fields, with the defaults of src/params.jl:5-117,177-226 (LCO)
 // and :295-367, 428-445 (NMC).  nmc = NaN: key not part of the NMC parameter set.  The table is in the
-// reference's key order (Symbols sorted by code point); thermal_only keys are only used by the
-// generated functions of a temperature = true model.
+// reference's key order (Symbols sorted by code point); `only` marks the keys that the generated functions
+// use only when temperature = true (bit 0) and/or aging = :SEI (bit 1).
 static const double NA = NAN;
 static const KeyDef KEYS[] = {
     {"Cp_a", "Cp_a", TF_Cp_a, 897.0, NA, 1}, {"Cp_n", "Cp_n", TF_Cp_n, 700.0, NA, 1}, {"Cp_p", "Cp_p", TF_Cp_p, 700.0, NA, 1},
@@ -44,19 +44,24 @@ static const KeyDef KEYS[] = {
     {"D_sn", "D_sn", TF_D_sn, 3.9e-14, 1.5e-14, 0}, {"D_sp", "D_sp", TF_D_sp, 1e-14, 2e-14, 0},
     {"Ea_D_sn", "Ea_D_sn", TF_Ea_D_sn, 5000.0, 4e4, 0}, {"Ea_D_sp", "Ea_D_sp", TF_Ea_D_sp, 5000.0, 2.5e4, 0},
     {"Ea_k_n", "Ea_k_n", TF_Ea_k_n, 5000.0, 3e4, 0}, {"Ea_k_p", "Ea_k_p", TF_Ea_k_p, 5000.0, 3e4, 0},
+    {"M_n", "M_n", TF_M_n, 7.3e-4, NA, 2}, {"R_SEI", "R_SEI", TF_R_SEI, 0.01, NA, 2},
     {"Rp_n", "Rp_n", TF_Rp_n, 2e-6, 10e-6, 0}, {"Rp_p", "Rp_p", TF_Rp_p, 2e-6, 7.5e-6, 0},
     {"T_amb", "T_amb", TF_T_amb, 25 + 273.15, NA, 1},
     {"T\xe2\x82\x80", "T0", TF_T0, 25 + 273.15, 25 + 273.15, 0},
+    {"Uref_s", "Uref_s", TF_Uref_s, 0.4, NA, 2},
     {"brugg_n", "brugg_n", TF_brugg_n, 4.0, 1.5, 0}, {"brugg_p", "brugg_p", TF_brugg_p, 4.0, 1.5, 0},
     {"brugg_s", "brugg_s", TF_brugg_s, 4.0, 1.5, 0},
     {"c_e\xe2\x82\x80", "c_e0", TF_c_e0, 1000.0, 1200.0, 0},
     {"c_max_n", "c_max_n", TF_c_max_n, 30555.0, 31080.0, 0}, {"c_max_p", "c_max_p", TF_c_max_p, 51554.0, 51830.0, 0},
     {"h_cell", "h_cell", TF_h_cell, 1.0, NA, 1},
-    {"k_n", "k_n", TF_k_n, 5.0310e-11, 6.3466e-10, 0}, {"k_p", "k_p", TF_k_p, 2.334e-11, 6.3066e-10, 0},
+    {"i_0_jside", "i_0_jside", TF_i_0_jside, 1.5e-6, NA, 2},
+    {"k_n", "k_n", TF_k_n, 5.0310e-11, 6.3466e-10, 0}, {"k_n_aging", "k_n_aging", TF_k_n_aging, 1.0, NA, 2},
+    {"k_p", "k_p", TF_k_p, 2.334e-11, 6.3066e-10, 0},
     {"l_a", "l_a", TF_l_a, 10e-6, NA, 1},
     {"l_n", "l_n", TF_l_n, 88e-6, 48e-6, 0}, {"l_p", "l_p", TF_l_p, 80e-6, 41.6e-6, 0}, {"l_s", "l_s", TF_l_s, 25e-6, 25e-6, 0},
     {"l_z", "l_z", TF_l_z, 10e-6, NA, 1},
     {"t\xe2\x82\x8a", "t_plus", TF_t_plus, 0.364, 0.38, 0},
+    {"w", "w", TF_w, 2.0, NA, 2},
     {"\xce\xb8_max_n", "theta_max_n", TF_theta_max_n, 0.85510, 0.790813, 0},
     {"\xce\xb8_max_p", "theta_max_p", TF_theta_max_p, 0.49550, 0.359749, 0},
     {"\xce\xb8_min_n", "theta_min_n", TF_theta_min_n, 0.01429, 0.001, 0},
@@ -64,7 +69,7 @@ static const KeyDef KEYS[] = {
     {"\xce\xbb_a", "lambda_a", TF_lambda_a, 237.0, NA, 1}, {"\xce\xbb_n", "lambda_n", TF_lambda_n, 1.7, NA, 1},
     {"\xce\xbb_p", "lambda_p", TF_lambda_p, 2.1, NA, 1}, {"\xce\xbb_s", "lambda_s", TF_lambda_s, 0.16, NA, 1},
     {"\xce\xbb_z", "lambda_z", TF_lambda_z, 401.0, NA, 1},
-    {"\xcf\x81_a", "rho_a", TF_rho_a, 2700.0, NA, 1}, {"\xcf\x81_n", "rho_n", TF_rho_n, 2500.0, NA, 1},
+    {"\xcf\x81_a", "rho_a", TF_rho_a, 2700.0, NA, 1}, {"\xcf\x81_n", "rho_n", TF_rho_n, 2500.0, NA, 3},
     {"\xcf\x81_p", "rho_p", TF_rho_p, 2500.0, NA, 1}, {"\xcf\x81_s", "rho_s", TF_rho_s, 1100.0, NA, 1},
     {"\xcf\x81_z", "rho_z", TF_rho_z, 8940.0, NA, 1},
     {"\xcf\x83_a", "sigma_a", TF_sigma_a, 3.55e7, NA, 1},
@@ -90,6 +95,8 @@ static const Variant V_ISO = {iso::info, iso::slot_rc, iso::slot_recipe, iso::la
                               iso::launch_newton, iso::launch_linsolve, iso::launch_simulate};
 static const Variant V_TH = {th::info, th::slot_rc, th::slot_recipe, th::launch_resjac, th::launch_initguess,
                              th::launch_newton, th::launch_linsolve, th::launch_simulate};
+static const Variant V_SEI = {sei::info, sei::slot_rc, sei::slot_recipe, sei::launch_resjac, sei::launch_initguess,
+                              sei::launch_newton, sei::launch_linsolve, sei::launch_simulate};
 
 struct plb_handle_s {
     plb_model_desc desc;
@@ -156,7 +163,8 @@ static int build_patterns(plb_handle_s* h) {
 
 int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (!d || !out) return fail("plb_create: null argument");
-    if (d->aging) return fail("plb_create: aging=:SEI is not built yet");
+    if (d->aging && d->temperature) return fail("plb_create: aging=:SEI together with temperature=true is not built yet");
+    if (d->aging && d->cathode != PLB_CATHODE_LCO) return fail("plb_create: aging=:SEI needs the LCO parameter set");
     if (d->N_r_p != NR_HOST || d->N_r_n != NR_HOST) return fail("plb_create: only N_r_p = N_r_n = 10 is built");
     if (d->N_p < 2 || d->N_s < 2 || d->N_n < 2 || d->N_p + d->N_s + d->N_n > 32)
         return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 32 (one lane per node)");
@@ -174,26 +182,30 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     CUDA_OK(cudaSetDevice(d->device));
     plb_handle_s* h = new plb_handle_s();
     h->desc = *d;
-    h->v = d->temperature ? &V_TH : &V_ISO;
+    h->v = d->temperature ? &V_TH : (d->aging ? &V_SEI : &V_ISO);
     h->n_methods = d->temperature ? 4 : 3;
     h->vi = h->v->info();
     ModelDesc& m = h->m;
     memset(&m, 0, sizeof m);
     m.Np = d->N_p; m.Ns = d->N_s; m.Nn = d->N_n; m.Nx = m.Np + m.Ns + m.Nn; m.Ne = m.Np + m.Nn;
     m.thermal = d->temperature ? 1 : 0;
+    m.aging = d->aging ? 1 : 0;
     m.Na = m.thermal ? d->N_a : 0; m.Nz = m.thermal ? d->N_z : 0;
     m.chem = d->cathode == PLB_CATHODE_LCO ? CHEM_LCO : CHEM_NMC;
     m.mid = m.thermal ? m.Np + m.Ns / 2 : m.Nx / 2;
     m.off_cs = m.Nx; m.off_T = m.off_cs + NR_HOST * m.Ne;
-    m.off_j = m.off_T + (m.thermal ? m.Na + m.Nx + m.Nz : 0); m.N_diff = m.off_j;
-    m.off_pe = m.off_j + m.Ne; m.off_ps = m.off_pe + m.Nx; m.off_I = m.off_ps + m.Ne; m.N_tot = m.off_I + 1;
+    m.off_film = m.off_T + (m.thermal ? m.Na + m.Nx + m.Nz : 0);
+    m.off_SOH = m.off_film + (m.aging ? m.Nn : 0);
+    m.off_j = m.off_SOH + (m.aging ? 1 : 0); m.N_diff = m.off_j;
+    m.off_pe = m.off_j + m.Ne; m.off_ps = m.off_pe + m.Nx; m.off_js = m.off_ps + m.Ne;
+    m.off_I = m.off_js + (m.aging ? m.Nn : 0); m.N_tot = m.off_I + 1;
     if (m.N_tot > h->vi.vs) { delete h; return fail("plb_create: system too large for the workspace stride"); }
     for (int f = 0; f < TF_COUNT; f++) m.slot[f] = -1;
     // used keys in the reference's (code-point sorted) order; KEYS[] is already sorted that way
     for (int k = 0; k < (int)(sizeof(KEYS) / sizeof(KEYS[0])); k++) {
         const double dv = d->cathode == PLB_CATHODE_LCO ? KEYS[k].lco : KEYS[k].nmc;
         if (dv != dv) continue;
-        if (KEYS[k].thermal_only && !m.thermal) continue;
+        if (KEYS[k].only && !((KEYS[k].only & 1) && m.thermal) && !((KEYS[k].only & 2) && m.aging)) continue;
         m.slot[KEYS[k].field] = (int8_t)h->keys.size();
         h->keys.push_back(k);
     }
@@ -212,8 +224,8 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     return 0;
 }
 
-int plb_variant_info(int temperature, long long* out) {
-    const VariantInfo v = temperature ? th::info() : iso::info();
+int plb_variant_info(int family, long long* out) {
+    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : iso::info());
     out[0] = v.sim_warps; out[1] = v.sim_ctas; out[2] = (long long)v.sim_smem; out[3] = v.k1_warps;
     out[4] = v.k1_ctas; out[5] = (long long)v.k1_smem; out[6] = v.vs; out[7] = v.n_slots;
     return 0;

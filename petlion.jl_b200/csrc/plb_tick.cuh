@@ -66,6 +66,7 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
         const double sc = 2.0 / (1.0 + M.cjratio);
         d.ce *= sc; d.j *= sc; d.pe *= sc; d.ps *= sc; dI *= sc;
         if (TH) { d.T *= sc; d.Tx *= sc; }
+        if (SEI) { d.js *= sc; d.film *= sc; d.soh *= sc; }
 #pragma unroll
         for (int r = 0; r < NR; r++) d.cs[r] *= sc;
     }
@@ -89,6 +90,14 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
     if (TH) {
         if (ro.act) { ee.T += d.T; s = fma(d.T * ewt.T, d.T * ewt.T, s); }
         if (ro.ix >= 0) { ee.Tx += d.Tx; s = fma(d.Tx * ewt.Tx, d.Tx * ewt.Tx, s); }
+    }
+    if (SEI) {
+        if (ro.sec == 2) {
+            ee.js += d.js; s = fma(d.js * ewt.js, d.js * ewt.js, s);
+            ee.film += d.film; s = fma(d.film * ewt.film, d.film * ewt.film, s);
+        }
+        ee.soh += d.soh;
+        if (lane == 0) s = fma(d.soh * ewt.soh, d.soh * ewt.soh, s);
     }
     eeI += dI;
     store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
@@ -313,7 +322,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
             if (do_interp) { double dp[6]; getsol_weights(M, w.K, S.tprev, w.K.cprev, dp); }
         }
         __syncwarp();
-        double ps0 = 0.0, psN = 0.0, If = 0.0, Tw = 0.0;
+        double ps0 = 0.0, psN = 0.0, If = 0.0, Tw = 0.0, aux = 0.0;
 #pragma unroll 1
         for (int i = lane; i < N; i += 32) {
             const double yn = interp_y(w, w.K.cvals, S.kord, i);
@@ -324,6 +333,9 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
             if (i == iP0) ps0 = yf;
             if (i == iPN) psN = yf;
             if (i == m.off_I) If = yf;
+#if PLB_SEI
+            if (i == m.off_SOH) aux = yf;
+#endif
 #if PLB_TH
             if (i >= m.off_T && i < m.off_j) {   // temperature_weighting of the final state
                 const int k = i - m.off_T, x = k - m.Na;
@@ -334,6 +346,8 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
         }
         ps0 = warp_sum(ps0); psN = warp_sum(psN); If = warp_sum(If);
         V_end = ps0 - psN; I_end = If;
+        if (SEI) out.aux_end = warp_sum(aux);       // SOH of the final state
+        (void)Tw; (void)aux;
 #if PLB_TH
         {
             const double* th = w.C.theta;
@@ -401,6 +415,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
         LaneVec y0;
         y0.ce = th[TF_c_e0]; y0.j = 0.0; y0.pe = 0.0; y0.ps = 0.0;
         y0.T = th[TF_T0]; y0.Tx = th[TF_T0];
+        y0.js = 0.0; y0.film = 0.0; y0.soh = 1.0;
         const double cs0 = ro.sec == 0 ? csp : csn;
 #pragma unroll
         for (int r = 0; r < NR; r++) y0.cs[r] = cs0;
@@ -500,7 +515,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
         if (lane == 0) a.tr_T[so + S.nsave] = Tw;
     }
     S.nsave++;
-    S.pv.T = -1;
+    S.pv.T = -1; S.pv.dfilm = -1;
     S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
     S.kord = 1;
     check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, Ic, Vc, lane);
@@ -522,7 +537,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         LaneVec y, yp, res;
         double Iy = 0.0;
         bool do_eval = S.state != ST_EXHAUSTED, need_jac = false, alg_only = false, do_solve = false;
-        yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0;
+        yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0; yp.js = 0.0; yp.film = 0.0; yp.soh = 0.0;
 #pragma unroll
         for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
         if (do_eval) {
@@ -536,6 +551,10 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 y.ce += e.ce; y.j += e.j; y.pe += e.pe; y.ps += e.ps; Iy += eI;
                 yp.ce = p.ce + cj * e.ce;
                 if (TH) { y.T += e.T; y.Tx += e.Tx; yp.T = p.T + cj * e.T; yp.Tx = p.Tx + cj * e.Tx; }
+                if (SEI) {
+                    y.js += e.js; y.film += e.film; y.soh += e.soh;
+                    yp.film = p.film + cj * e.film; yp.soh = p.soh + cj * e.soh;
+                }
 #pragma unroll
                 for (int r = 0; r < NR; r++) { y.cs[r] += e.cs[r]; yp.cs[r] = p.cs[r] + cj * e.cs[r]; }
                 need_jac = S.callLSetup != 0; do_solve = true;
@@ -549,6 +568,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                     load_lane(m, ro, w.v(V_PHI1), p, pI);
                     y.ce += S.dt_init * p.ce;
                     if (TH) { y.T += S.dt_init * p.T; y.Tx += S.dt_init * p.Tx; }
+                    if (SEI) { y.film += S.dt_init * p.film; y.soh += S.dt_init * p.soh; }
 #pragma unroll
                     for (int r = 0; r < NR; r++) y.cs[r] += S.dt_init * p.cs[r];
                     do_solve = true;
@@ -587,6 +607,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             if (S.state == ST_NLS) {   // Newton update of the BDF step: delta = -J^{-1} F
                 res.ce = -res.ce; res.j = -res.j; res.pe = -res.pe; res.ps = -res.ps; gI = -gI;
                 if (TH) { res.T = -res.T; res.Tx = -res.Tx; }
+                if (SEI) { res.js = -res.js; res.film = -res.film; res.soh = -res.soh; }
 #pragma unroll
                 for (int r = 0; r < NR; r++) res.cs[r] = -res.cs[r];
             }
@@ -615,6 +636,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 double s = 0.0;
                 if (ro.elec) { y.j -= res.j; y.ps -= res.ps; s += res.j * res.j + res.ps * res.ps; }
                 if (ro.act) { y.pe -= res.pe; s += res.pe * res.pe; }
+                if (SEI && ro.sec == 2) { y.js -= res.js; s += res.js * res.js; }
                 Iy -= dI;
                 s = warp_sum(s) + dI * dI;
                 store_lane(m, ro, w.v(V_PHI0), y, Iy, lane);
@@ -633,6 +655,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 LaneVec ypo;
                 ypo.ce = res.ce; ypo.j = 0.0; ypo.pe = 0.0; ypo.ps = 0.0;
                 ypo.T = TH ? res.T : 0.0; ypo.Tx = TH ? res.Tx : 0.0;
+                ypo.film = SEI ? res.film : 0.0; ypo.soh = SEI ? res.soh : 0.0; ypo.js = 0.0;
 #pragma unroll
                 for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
                 store_lane(m, ro, w.v(V_PHI1), ypo, 0.0, lane);
@@ -646,6 +669,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 double pI;
                 load_lane(m, ro, w.v(V_PHI1), ypo, pI);
                 ypo.j = -res.j / S.dt_init; ypo.pe = -res.pe / S.dt_init; ypo.ps = -res.ps / S.dt_init;
+                if (SEI) ypo.js = -res.js / S.dt_init;
                 store_lane(m, ro, w.v(V_PHI1), ypo, -dI / S.dt_init, lane);
                 __syncwarp();
                 begin_integration(a, w, S, lane);

@@ -25,6 +25,11 @@ enum JacSlot {
     JS_PE_L, JS_PE_D, JS_PE_U, JS_PC_L, JS_PC_D, JS_PC_U, JS_PE_J,
     JS_PS_L, JS_PS_D, JS_PS_U, JS_PS_J, JS_PS_I,
     JS_CS_J,
+#if PLB_SEI
+    // aging = :SEI (anode lanes): j row d/dfilm; j_s row; film row; SOH row; d/dj_s of the c_e, Phi_e, Phi_s rows
+    JS_J_FILM, JS_JS_PS, JS_JS_PE, JS_JS_J, JS_JS_JS, JS_JS_FILM, JS_JS_I, JS_FILM_JS, JS_FILM_D,
+    JS_SOH_JS, JS_SOH_D, JS_CE_JS, JS_PE_JS, JS_PS_JS,
+#endif
 #if PLB_TH
     JS_CS_T0,                                       // 10 slots: d res_cs[r] / dT
     JS_J_T = JS_CS_T0 + NR, JS_PE_TL, JS_PE_TD, JS_PE_TU,
@@ -101,6 +106,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArg
         }
         yp.j = 0.0; yp.ps = 0.0;
         y.T = 0.0; y.Tx = 0.0; yp.T = 0.0; yp.Tx = 0.0;
+        y.js = 0.0; y.film = 0.0; y.soh = 0.0; yp.js = 0.0; yp.film = 0.0; yp.soh = 0.0;
+        if (SEI) {
+            const int k = ro.x - (m.Np + m.Ns);
+            if (ro.sec == 2) { y.js = gY[m.off_js + k]; y.film = gY[m.off_film + k]; yp.film = gYP[m.off_film + k]; }
+            y.soh = gY[m.off_SOH]; yp.soh = gYP[m.off_SOH];
+        }
         if (TH) {
             if (ro.act) { y.T = gY[m.off_T + m.Na + ro.x]; yp.T = gYP[m.off_T + m.Na + ro.x]; }
             if (ro.ix >= 0) { y.Tx = gY[m.off_T + ro.ix]; yp.Tx = gYP[m.off_T + ro.ix]; }
@@ -125,13 +136,28 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArg
                 if (ro.act) gR[m.off_T + m.Na + ro.x] = res.T;
                 if (ro.ix >= 0) gR[m.off_T + ro.ix] = res.Tx;
             }
+            if (SEI) {
+                const int k = ro.x - (m.Np + m.Ns);
+                if (ro.sec == 2) { gR[m.off_js + k] = res.js; gR[m.off_film + k] = res.film; }
+                if (lane == 0) gR[m.off_SOH] = res.soh;
+            }
             if (lane == 0) gR[m.off_I] = ctrl.res;
         }
         if (a.nzval) {
             const double g = a.gamma ? a.gamma[sys] : 0.0;
             w.S[JS_CE_L][lane] = J.ceL; w.S[JS_CE_D][lane] = J.ceD - g; w.S[JS_CE_U][lane] = J.ceU; w.S[JS_CE_J][lane] = J.ce_j;
             w.S[JS_J_CS][lane] = J.j_cs; w.S[JS_J_CE][lane] = J.j_ce; w.S[JS_J_PE][lane] = J.j_pe; w.S[JS_J_PS][lane] = J.j_ps;
+#if PLB_SEI
+            w.S[JS_J_J][lane] = J.j_j;
+            w.S[JS_J_FILM][lane] = J.j_film;
+            w.S[JS_JS_PS][lane] = J.js_ps; w.S[JS_JS_PE][lane] = J.js_pe; w.S[JS_JS_J][lane] = J.js_j;
+            w.S[JS_JS_JS][lane] = J.js_js; w.S[JS_JS_FILM][lane] = J.js_film; w.S[JS_JS_I][lane] = J.js_I;
+            w.S[JS_FILM_JS][lane] = J.film_js; w.S[JS_FILM_D][lane] = -g;
+            w.S[JS_SOH_JS][lane] = J.soh_js; w.S[JS_SOH_D][lane] = -g;
+            w.S[JS_CE_JS][lane] = J.ce_j; w.S[JS_PE_JS][lane] = J.pe_j; w.S[JS_PS_JS][lane] = J.ps_j;
+#else
             w.S[JS_J_J][lane] = -1.0;
+#endif
             w.S[JS_PE_L][lane] = J.peL; w.S[JS_PE_D][lane] = J.peD; w.S[JS_PE_U][lane] = J.peU;
             w.S[JS_PC_L][lane] = J.pcL; w.S[JS_PC_D][lane] = J.pcD; w.S[JS_PC_U][lane] = J.pcU; w.S[JS_PE_J][lane] = J.pe_j;
             w.S[JS_PS_L][lane] = J.psL; w.S[JS_PS_D][lane] = J.psD; w.S[JS_PS_U][lane] = J.psU; w.S[JS_PS_J][lane] = J.ps_j;
@@ -229,6 +255,29 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         row = cs(r); col = cs(c);
         return elec && (laws::mc_mask(r) & (1u << c));
     }
+#if PLB_SEI
+    {
+        const int k = x - (Np + Ns);
+        const int r_js = m.off_js + k, r_film = m.off_film + k, r_soh = m.off_SOH;
+        switch (slot) {
+            case JS_J_FILM: row = r_j; col = r_film; return isn;
+            case JS_JS_PS: row = r_js; col = r_ps; return isn;
+            case JS_JS_PE: row = r_js; col = r_pe; return isn;
+            case JS_JS_J: row = r_js; col = r_j; return isn;
+            case JS_JS_JS: row = r_js; col = r_js; return isn;
+            case JS_JS_FILM: row = r_js; col = r_film; return isn;
+            case JS_JS_I: row = r_js; col = I; return isn;
+            case JS_FILM_JS: row = r_film; col = r_js; return isn;
+            case JS_FILM_D: row = r_film; col = r_film; return isn;
+            case JS_SOH_JS: row = r_soh; col = r_js; return isn;
+            case JS_SOH_D: row = r_soh; col = r_soh; return lane == 0;
+            case JS_CE_JS: row = r_ce; col = r_js; return isn;
+            case JS_PE_JS: row = r_pe; col = r_js; return isn && !last;
+            case JS_PS_JS: row = r_ps; col = r_js; return isn;
+            default: break;
+        }
+    }
+#endif
 #if PLB_TH
     const int rT = m.off_T + m.Na + x;
     const bool cha = lane < m.Na, chz = lane >= Nx - m.Nz;
@@ -292,7 +341,7 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // initial_guess!, newtons_method!, linear solve, simulate
 // =================================================================================================
 #ifndef PLB_SIM_WARPS
-#define PLB_SIM_WARPS (PLB_TH ? 4 : 6)   // warps (systems in flight) per CTA
+#define PLB_SIM_WARPS (PLB_TH ? 4 : (PLB_SEI ? 5 : 6))   // warps (systems in flight) per CTA
 #endif
 #ifndef PLB_SIM_CTAS
 #define PLB_SIM_CTAS 1            // CTAs per SM the register/shared-memory budget is sized for
@@ -324,6 +373,7 @@ __device__ __forceinline__ void initial_lane(const ModelDesc& m, const WarpConst
     const double csn = th[TF_c_max_n] * (SOC * (th[TF_theta_max_n] - th[TF_theta_min_n]) + th[TF_theta_min_n]);
     y0.ce = th[TF_c_e0]; y0.j = 0.0; y0.pe = 0.0; y0.ps = 0.0;
     y0.T = th[TF_T0]; y0.Tx = th[TF_T0];
+    y0.js = 0.0; y0.film = 0.0; y0.soh = 1.0;
     const double cs0 = ro.sec == 0 ? csp : csn;
 #pragma unroll
     for (int r = 0; r < NR; r++) y0.cs[r] = cs0;
@@ -452,10 +502,10 @@ VariantInfo info() {
             if (e_ != cudaSuccess) return e_;                                                                       \
             KERNEL<CHEM_LCO><<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(ARGS);                                          \
         } else {                                                                                                    \
-            if (TH) return cudaErrorInvalidValue; /* the NMC parameter set has no thermal parameters */            \
-            e_ = cudaFuncSetAttribute(KERNEL<PLB_TH ? CHEM_LCO : CHEM_NMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
+            if (TH || SEI) return cudaErrorInvalidValue; /* NMC carries no thermal / aging parameters */           \
+            e_ = cudaFuncSetAttribute(KERNEL<(PLB_TH || PLB_SEI) ? CHEM_LCO : CHEM_NMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
             if (e_ != cudaSuccess) return e_;                                                                       \
-            KERNEL<PLB_TH ? CHEM_LCO : CHEM_NMC><<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(ARGS);                      \
+            KERNEL<(PLB_TH || PLB_SEI) ? CHEM_LCO : CHEM_NMC><<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(ARGS);          \
         }                                                                                                           \
         return cudaGetLastError();                                                                                  \
     } while (0)
