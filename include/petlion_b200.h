@@ -153,7 +153,7 @@ int plb_simulate(plb_handle h, int B, const double *theta, const plb_run *run,
                  double *traj_V, double *traj_I, double *traj_SOC, double *traj_T, int *traj_n,
                  int mem);
 
-/* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI): out[8] = {integrator warps
+/* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI, 3 wide, 4 wide SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared
  * memory per CTA [B], workspace vector stride, Jacobian slots per lane}.  Needs no GPU. */
 int plb_variant_info(int family, long long *out);

@@ -126,6 +126,7 @@ struct VariantInfo {
     size_t sim_smem, k1_smem;       // dynamic shared memory per CTA
     int vs, nglobal;                // workspace vector stride, history vectors parked in global memory
     int n_slots, n_stage, k1_src_max;
+    int lanes;                      // lanes per system: 32, or 64 in the wide families
 };
 
 // launchers, one set per variant (defined in plb_variant.cuh)
@@ -144,5 +145,7 @@ struct VariantInfo {
 PLB_DECLARE_VARIANT(iso)
 PLB_DECLARE_VARIANT(th)
 PLB_DECLARE_VARIANT(sei)
+PLB_DECLARE_VARIANT(wide)
+PLB_DECLARE_VARIANT(wsei)
 
 }  // namespace plb

@@ -34,8 +34,23 @@ namespace PLB_NS {
 #if PLB_TH && PLB_SEI
 #error "temperature = true together with aging = :SEI is not built"
 #endif
+#ifndef PLB_WIDE
+#define PLB_WIDE 0
+#endif
+#if PLB_TH && PLB_WIDE
+#error "temperature = true on grids with more than 32 nodes is not built"
+#endif
 constexpr bool TH = PLB_TH != 0;
 constexpr bool SEI = PLB_SEI != 0;
+// "Wide" families (grids with 33..64 x-nodes, e.g. N = (20,20,20)): one system is owned by a GROUP of two
+// warps (64 lanes, lane x <-> node x as before).  Everything that is a warp shuffle / __syncwarp in the
+// 32-lane families goes through the grp_* primitives below: in a wide family they exchange through a
+// small shared-memory scratch area and a named barrier of the two warps, in the others they ARE the warp
+// intrinsics (identical code generation).
+constexpr bool WIDE = PLB_WIDE != 0;
+constexpr int LW = WIDE ? 64 : 32;          // lanes per system
+constexpr int XCH_K = 16;                   // doubles per lane of the exchange scratch (wide only)
+constexpr size_t XCH_BYTES_PER_GROUP = WIDE ? sizeof(double) * XCH_K * LW : 0;
 constexpr int NR = laws::NR;
 
 // ------------------------------------------------------------------------------------------------
@@ -54,8 +69,8 @@ enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, 
 struct WarpConst {
     double sec[SC_COUNT][4];   // [field][section p,s,n,pad]
     double g[GC_COUNT + 1];
-    double dinv[32];           // 1 / (centre distance across face x|x+1)
-    double beta[32];           // harmonic-mean weight of face x|x+1
+    double dinv[LW];           // 1 / (centre distance across face x|x+1)
+    double beta[LW];           // harmonic-mean weight of face x|x+1
     double theta[TF_COUNT + 1];
 #if PLB_TH
     // heat conduction (residuals.jl:299-446): coefficients of T[x-1]-T[x] and T[x+1]-T[x] in the T row of
@@ -66,7 +81,7 @@ struct WarpConst {
     double s5[3][8];           // h, lambda, rho*Cp of the five sections a,p,s,n,z
 #endif
 #if PLB_SEI
-    double cSOH[32];           // d(rhs_SOH)/d j_s of this lane's anode node (residuals.jl:278-297)
+    double cSOH[LW];           // d(rhs_SOH)/d j_s of this lane's anode node (residuals.jl:278-297)
 #endif
 };
 
@@ -102,14 +117,106 @@ struct LaneVec {
     double js, film, soh;      // aging = :SEI: side-reaction flux and film thickness (anode lanes), SOH (uniform)
 };
 
-__device__ __forceinline__ double shfl_dn(double v) { return __shfl_down_sync(FULL, v, 1); }
-__device__ __forceinline__ double shfl_up(double v) { return __shfl_up_sync(FULL, v, 1); }
-__device__ __forceinline__ double shfl_from(double v, int src) { return __shfl_sync(FULL, v, src); }
+// ---- group primitives ---------------------------------------------------------------------------
+__device__ __forceinline__ int grp_lane() { return WIDE ? (int)(threadIdx.x & 63) : (int)(threadIdx.x & 31); }
+__device__ __forceinline__ int grp_id() { return WIDE ? (int)(threadIdx.x >> 6) : (int)(threadIdx.x >> 5); }
+__device__ __forceinline__ void grp_sync() {
+#if PLB_WIDE
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + grp_id()) : "memory");
+#else
+    __syncwarp();
+#endif
+}
+#if PLB_WIDE
+// the exchange scratch of this thread's group: the first bytes of the CTA's dynamic shared memory
+__device__ __forceinline__ double* grp_xch() {
+    extern __shared__ __align__(16) unsigned char plb_dyn_smem[];
+    return reinterpret_cast<double*>(plb_dyn_smem) + (size_t)grp_id() * XCH_K * LW;
+}
+#endif
+__device__ __forceinline__ double shfl_from(double v, int src) {
+#if PLB_WIDE
+    double* x = grp_xch();
+    x[grp_lane()] = v;
+    grp_sync();
+    const double r = x[src];
+    grp_sync();
+    return r;
+#else
+    return __shfl_sync(FULL, v, src);
+#endif
+}
+// value of lane+1 / lane-1 (the end lanes get their own value back, like the warp intrinsics)
+__device__ __forceinline__ double shfl_dn(double v) {
+#if PLB_WIDE
+    const int l = grp_lane();
+    return shfl_from(v, l < LW - 1 ? l + 1 : l);
+#else
+    return __shfl_down_sync(FULL, v, 1);
+#endif
+}
+__device__ __forceinline__ double shfl_up(double v) {
+#if PLB_WIDE
+    const int l = grp_lane();
+    return shfl_from(v, l > 0 ? l - 1 : l);
+#else
+    return __shfl_up_sync(FULL, v, 1);
+#endif
+}
+// K values from the same source lane in one exchange
+template <int K>
+__device__ __forceinline__ void shfl_from_n(const double* v, int src, double* out) {
+#if PLB_WIDE
+    static_assert(K <= XCH_K, "exchange scratch too small");
+    double* x = grp_xch();
+    const int l = grp_lane();
+#pragma unroll
+    for (int k = 0; k < K; k++) x[k * LW + l] = v[k];
+    grp_sync();
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = x[k * LW + src];
+    grp_sync();
+#else
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = __shfl_sync(FULL, v[k], src);
+#endif
+}
+__device__ __forceinline__ int grp_bcast_int(int v, int src) {
+#if PLB_WIDE
+    return (int)shfl_from((double)v, src);
+#else
+    return __shfl_sync(FULL, v, src);
+#endif
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+#if PLB_WIDE
+    {   // the two warps of the group: both add the partial sums in the same order
+        double* x = grp_xch();
+        if ((threadIdx.x & 31) == 0) x[(threadIdx.x >> 5) & 1] = v;
+        grp_sync();
+        v = x[0] + x[1];
+        grp_sync();
+    }
+#endif
     return v;
 }
+__device__ __forceinline__ double grp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+#if PLB_WIDE
+    {
+        double* x = grp_xch();
+        if ((threadIdx.x & 31) == 0) x[(threadIdx.x >> 5) & 1] = v;
+        grp_sync();
+        v = fmax(x[0], x[1]);
+        grp_sync();
+    }
+#endif
+    return v;
+}
+__device__ __forceinline__ double grp_min(double v) { return -grp_max(-v); }
 
 // calc_I1C -- auxiliary_states_and_coefficients.jl:631-647
 __device__ __forceinline__ double calc_I1C(const double* th) {
@@ -124,11 +231,11 @@ __device__ __forceinline__ double calc_I1C(const double* th) {
 // build_auxiliary_states! -- auxiliary_states_and_coefficients.jl:6-52 (parameter-only parts)
 __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* __restrict__ theta_row,
                                              WarpConst& C, int lane) {
-    for (int f = lane; f < TF_COUNT; f += 32) {
+    for (int f = lane; f < TF_COUNT; f += LW) {
         const int s = m.slot[f];
         C.theta[f] = s >= 0 ? theta_row[s] : 0.0;
     }
-    __syncwarp();
+    grp_sync();
     const double* th = C.theta;
     if (lane < 3) {
         const int s = lane;
@@ -198,7 +305,7 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         }
         if (s == 2) C.g[GC_psI_n] = -calc_I1C(th) * h / sig;   // d res_Phi_s[last n] / dI (residuals.jl:680)
     }
-    __syncwarp();
+    grp_sync();
     {
         // face x | x+1 geometry: numerical_tools.jl:106-215
         const int x = lane;
@@ -212,7 +319,7 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         C.dinv[lane] = (x < m.Nx - 1) ? 1.0 / d : 0.0;
         C.beta[lane] = b;
     }
-    __syncwarp();
+    grp_sync();
 #if PLB_SEI
     {
         // residuals_SOH! (residuals.jl:278-297): rhs = F a_n/(3600 I1C) * trapz over the anode of j_s after a
@@ -240,7 +347,7 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         }
         C.cSOH[lane] = wk;
     }
-    __syncwarp();
+    grp_sync();
 #endif
 #if PLB_TH
     // ---- heat conduction coefficients, residuals.jl:299-446 (five sections a | p | s | n | z) -------
@@ -252,7 +359,7 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         C.s5[1][q] = q == 0 ? th[TF_lambda_a] : (q == 1 ? th[TF_lambda_p] : (q == 2 ? th[TF_lambda_s] : (q == 3 ? th[TF_lambda_n] : th[TF_lambda_z])));
         C.s5[2][q] = q == 0 ? th[TF_rho_a] * th[TF_Cp_a] : (q == 4 ? th[TF_rho_z] * th[TF_Cp_z] : 1.0 / C.sec[SC_irc][q - 1]);
     }
-    __syncwarp();
+    grp_sync();
     {
         // conductance between the centres of two adjacent cells: lambda/h inside a section, harmonic-mean
         // lambda over the centre distance across an interface (residuals.jl:363-446)
@@ -297,7 +404,7 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         if (x > 0 && x < m.Nx - 1) ci = 1.0 / (1.0 / C.dinv[x - 1] + 1.0 / C.dinv[x]);
         C.cinv[lane] = ci;
     }
-    __syncwarp();
+    grp_sync();
 #endif
 }
 
@@ -694,18 +801,18 @@ struct WarpFactor {
     double Sinv[NR * NR][2];   // [r*NR+c][electrode 0=p,1=n]
     double vb[NR][2];          // Sinv * b (b = surface-row j coupling)
     // per-lane data [field][lane]
-    double Dinv[9][32];        // inverse of the pivoted 3x3 diagonal block D'_x
-    double Wm[9][32];          // W_x = L_x * Dinv_{x-1}     (forward sweep:  y_x = r_x - W_x y_{x-1})
-    double Pm[9][32];          // P_x = Dinv_x * U_x         (backward sweep: u_x = Dinv_x y_x - P_x u_{x+1})
-    double z[3][32];           // T^{-1} e_I  (border column)
-    double q[4][32];           // j elimination: q_ce, q_pe, q_ps, inv_den
-    double jcs[32];            // a_cs (j row coefficient of the surface concentration)
-    double sj[3][32];          // d(row)/dj for rows ce, pe, ps
+    double Dinv[9][LW];        // inverse of the pivoted 3x3 diagonal block D'_x
+    double Wm[9][LW];          // W_x = L_x * Dinv_{x-1}     (forward sweep:  y_x = r_x - W_x y_{x-1})
+    double Pm[9][LW];          // P_x = Dinv_x * U_x         (backward sweep: u_x = Dinv_x y_x - P_x u_{x+1})
+    double z[3][LW];           // T^{-1} e_I  (border column)
+    double q[4][LW];           // j elimination: q_ce, q_pe, q_ps, inv_den
+    double jcs[LW];            // a_cs (j row coefficient of the surface concentration)
+    double sj[3][LW];          // d(row)/dj for rows ce, pe, ps
 #if PLB_SEI
     // aging = :SEI: j, j_s and film are eliminated together node-locally.  Mi = inverse of the 3x3 local
     // matrix (rows j, j_s, film), cpl = couplings of those rows to (c_e, Phi_e, Phi_s) and I:
     // j_ce, j_pe, j_ps, js_pe, js_ps, js_I ; sohc = d(rhs_SOH)/dj_s ; cjv = cj of this factorisation
-    double Mi[9][32], cpl[6][32], sohc[32];
+    double Mi[9][LW], cpl[6][LW], sohc[LW];
     double cjv, pad2;
 #endif
     double schur_inv;          // 1/(g_I - g_ps0*z_ps[0] - g_psN*z_ps[N-1])
@@ -763,15 +870,21 @@ __device__ __forceinline__ void thomas_sweeps(int Nx, const LaneChain& ch, const
     double y0 = r[0], y1 = r[1], y2 = r[2];
 #pragma unroll 1
     for (int it = 0; it < ch.n_in; it++) {
-        const double a0 = shfl_from(y0, ch.pred), a1 = shfl_from(y1, ch.pred), a2 = shfl_from(y2, ch.pred);
+        const double yv[3] = {y0, y1, y2};
+        double av[3];
+        shfl_from_n<3>(yv, ch.pred, av);
+        const double a0 = av[0], a1 = av[1], a2 = av[2];
         y0 = r[0] - (Wm[0] * a0 + Wm[1] * a1 + Wm[2] * a2);
         y1 = r[1] - (Wm[3] * a0 + Wm[4] * a1 + Wm[5] * a2);
         y2 = r[2] - (Wm[6] * a0 + Wm[7] * a1 + Wm[8] * a2);
     }
     {   // the meeting node takes both neighbours
         const int mid = Nx / 2;
-        const double a0 = shfl_from(y0, mid - 1), a1 = shfl_from(y1, mid - 1), a2 = shfl_from(y2, mid - 1);
-        const double b0 = shfl_from(y0, mid + 1), b1 = shfl_from(y1, mid + 1), b2 = shfl_from(y2, mid + 1);
+        const double yv[3] = {y0, y1, y2};
+        double av[3], bv[3];
+        shfl_from_n<3>(yv, mid - 1, av);
+        shfl_from_n<3>(yv, mid + 1, bv);
+        const double a0 = av[0], a1 = av[1], a2 = av[2], b0 = bv[0], b1 = bv[1], b2 = bv[2];
         if (ch.is_mid) {
             y0 = r[0] - (Wm[0] * a0 + Wm[1] * a1 + Wm[2] * a2) - (Pm[0] * b0 + Pm[1] * b1 + Pm[2] * b2);
             y1 = r[1] - (Wm[3] * a0 + Wm[4] * a1 + Wm[5] * a2) - (Pm[3] * b0 + Pm[4] * b1 + Pm[5] * b2);
@@ -788,7 +901,10 @@ __device__ __forceinline__ void thomas_sweeps(int Nx, const LaneChain& ch, const
     const double p6 = ch.is_mid ? 0.0 : Pm[6], p7 = ch.is_mid ? 0.0 : Pm[7], p8 = ch.is_mid ? 0.0 : Pm[8];
 #pragma unroll 1
     for (int it = 0; it < ch.n_out; it++) {
-        const double a0 = shfl_from(u0, ch.succ), a1 = shfl_from(u1, ch.succ), a2 = shfl_from(u2, ch.succ);
+        const double uv[3] = {u0, u1, u2};
+        double av[3];
+        shfl_from_n<3>(uv, ch.succ, av);
+        const double a0 = av[0], a1 = av[1], a2 = av[2];
         u0 = c0 - (p0 * a0 + p1 * a1 + p2 * a2);
         u1 = c1 - (p3 * a0 + p4 * a1 + p5 * a2);
         u2 = c2 - (p6 * a0 + p7 * a1 + p8 * a2);
@@ -803,33 +919,38 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
                                                  WarpFactor& Fa, int lane) {
     // ---- 1. particle inverses -------------------------------------------------------------------
     if (!alg_only) {
-        const int el = lane >> 4;                       // lanes 0-15 -> cathode, 16-31 -> anode
-        const int l16 = lane & 15;
-        const double kap = shfl_from(J.kap, el == 0 ? 0 : m.Nx - 1);
-        for (int k = l16; k < NR * NR; k += 16) {
-            const int r = k / NR, c = k - r * NR;
-            Fa.Sinv[k][el] = kap * laws::MC[r][c] - (r == c ? cj : 0.0);
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int p = 0; p < NR; p++) {
-            const double piv = 1.0 / Fa.Sinv[p * NR + p][el];
-            __syncwarp();
-            if (l16 < NR && l16 != p) Fa.Sinv[p * NR + l16][el] *= piv;
-            __syncwarp();
+        // two 10x10 Gauss-Jordan inverses on the 32 lanes of the (first) warp: lanes 0-15 cathode, 16-31 anode
+        const double kap_p = shfl_from(J.kap, 0), kap_n = shfl_from(J.kap, m.Nx - 1);
+        const double csj_p = shfl_from(J.cs_j, 0), csj_n = shfl_from(J.cs_j, m.Nx - 1);
+        if (lane < 32) {
+            const int el = lane >> 4;
+            const int l16 = lane & 15;
+            const double kap = el == 0 ? kap_p : kap_n;
             for (int k = l16; k < NR * NR; k += 16) {
                 const int r = k / NR, c = k - r * NR;
-                if (r != p && c != p)
-                    Fa.Sinv[k][el] = fma(-Fa.Sinv[r * NR + p][el], Fa.Sinv[p * NR + c][el], Fa.Sinv[k][el]);
+                Fa.Sinv[k][el] = kap * laws::MC[r][c] - (r == c ? cj : 0.0);
             }
             __syncwarp();
-            if (l16 < NR) Fa.Sinv[l16 * NR + p][el] = (l16 == p) ? piv : -Fa.Sinv[l16 * NR + p][el] * piv;
-            __syncwarp();
+#pragma unroll 1
+            for (int p = 0; p < NR; p++) {
+                const double piv = 1.0 / Fa.Sinv[p * NR + p][el];
+                __syncwarp();
+                if (l16 < NR && l16 != p) Fa.Sinv[p * NR + l16][el] *= piv;
+                __syncwarp();
+                for (int k = l16; k < NR * NR; k += 16) {
+                    const int r = k / NR, c = k - r * NR;
+                    if (r != p && c != p)
+                        Fa.Sinv[k][el] = fma(-Fa.Sinv[r * NR + p][el], Fa.Sinv[p * NR + c][el], Fa.Sinv[k][el]);
+                }
+                __syncwarp();
+                if (l16 < NR) Fa.Sinv[l16 * NR + p][el] = (l16 == p) ? piv : -Fa.Sinv[l16 * NR + p][el] * piv;
+                __syncwarp();
+            }
+            // vb = Sinv * b,  b = cs_j * e_surf
+            const double csj = el == 0 ? csj_p : csj_n;
+            if (l16 < NR) Fa.vb[l16][el] = Fa.Sinv[l16 * NR + NR - 1][el] * csj;
         }
-        // vb = Sinv * b,  b = cs_j * e_surf
-        const double csj = shfl_from(J.cs_j, el == 0 ? 0 : m.Nx - 1);
-        if (l16 < NR) Fa.vb[l16][el] = Fa.Sinv[l16 * NR + NR - 1][el] * csj;
-        __syncwarp();
+        grp_sync();
     }
     // ---- 2. node-local elimination of c_s and j -------------------------------------------------
     const int el = ro.sec == 2 ? 1 : 0;
@@ -919,8 +1040,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll 1
     for (int it = 0; it < ch.n_in + 1; it++) {
         double G[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) G[k] = shfl_from(Di[k], ch.pred);
+        shfl_from_n<9>(Di, ch.pred, G);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             Wm[c] = Cin[0] * G[c];
@@ -945,8 +1065,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     }
     {   // meeting node: second neighbour (mid+1, right chain): Wr = U_mid Dinv_{mid+1}, stored in Pm
         double G[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) G[k] = shfl_from(Di[k], mid + 1);
+        shfl_from_n<9>(Di, mid + 1, G);
         const double q0 = shfl_from(L4[0], mid + 1), q1 = shfl_from(L4[1], mid + 1), q2 = shfl_from(L4[2], mid + 1), q3 = shfl_from(L4[3], mid + 1);
         if (ch.is_mid) {
             double Wr[9];
@@ -986,7 +1105,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         Fa.g_ps0 = ctrl.g_ps0;
         Fa.g_psN = ctrl.g_psN;
     }
-    __syncwarp();
+    grp_sync();
 }
 
 // Solve J * d = g for one right-hand side held node-wise in registers (g in, d out, in place).
@@ -1088,7 +1207,7 @@ struct WarpFactor {
     double Eo[3][32];          // chain heads: T-row coupling to (c_e, Phi_e, Phi_s) two nodes ahead
     double z[4][32], zx[32];   // border column solution
     double q[5][32];           // j elimination: q_ce, q_pe, q_ps, q_T, inv_den
-    double jcs[32];
+    double jcs[LW];
     double sj[4][32];          // effective d(row)/dj for rows ce, pe, ps, T
     double tcs[32];            // T-row coefficient of the surface concentration
     double pd[NR][32];         // 1 / (kap_x * EL_i - cj)

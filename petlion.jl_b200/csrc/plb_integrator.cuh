@@ -18,7 +18,8 @@
 namespace plb {
 namespace PLB_NS {
 
-constexpr int VS = TH ? 352 : (SEI ? 336 : 304);   // vector stride in doubles (N_tot = 301 / 351 / 322 padded)
+// vector stride in doubles (N_tot padded): 301 / 351 / 322 on the 32-node families, up to 642 (N=(20,20,20) with SEI) wide
+constexpr int VS = WIDE ? 656 : (TH ? 352 : (SEI ? 336 : 304));
 enum VecId { V_PHI0 = 0, V_PHI1, V_PHI2, V_PHI3, V_PHI4, V_PHI5, V_YPRED, V_YPPRED, V_EWT, V_EE, V_COUNT };
 
 struct IdaCoef {
@@ -114,7 +115,7 @@ __device__ __forceinline__ int ref_index(const ModelDesc& m, int i) {
 
 __device__ __forceinline__ double wrms(const ModelDesc& m, const double* v, const double* w, int lane) {
     double s = 0.0;
-    for (int i = lane; i < m.N_tot; i += 32) { const double p = v[i] * w[i]; s = fma(p, p, s); }
+    for (int i = lane; i < m.N_tot; i += LW) { const double p = v[i] * w[i]; s = fma(p, p, s); }
     return sqrt(warp_sum(s) / m.N_tot);
 }
 
@@ -186,7 +187,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
         store_lane(m, ro, Y, y, I, lane);
         store_lane(m, ro, YP, ypo, -dI / dt, lane);
     }
-    __syncwarp();
+    grp_sync();
     return iter;
 }
 
@@ -205,19 +206,19 @@ struct Ida {
 // NEL independent chains overlap (these passes sit on the latency-critical path between two
 // residual evaluations).  Summation order per lane (k ascending, then the xor-tree) is fixed.
 // ------------------------------------------------------------------------------------------------
-constexpr int NEL = (VS + 31) / 32;
+constexpr int NEL = (VS + LW - 1) / LW;
 #ifndef PLB_ELEM_UNROLL
 #define PLB_ELEM_UNROLL 1
 #endif
 #define PLB_STR_(x) #x
 #define PLB_STR(x) PLB_STR_(x)
-#define PLB_FOR_ELEMS(i, N) _Pragma(PLB_STR(unroll PLB_ELEM_UNROLL)) for (int i = lane; i < (N); i += 32)
+#define PLB_FOR_ELEMS(i, N) _Pragma(PLB_STR(unroll PLB_ELEM_UNROLL)) for (int i = lane; i < (N); i += LW)
 
 __device__ __forceinline__ void ewt_set(const ModelDesc& m, WarpWS& w, const Opts& o, int lane) {
     const double* p0 = w.v(V_PHI0);
     double* ew = w.v(V_EWT);
     PLB_FOR_ELEMS(i, m.N_tot) ew[i] = 1.0 / (o.reltol * fabs(p0[i]) + o.abstol);
-    __syncwarp();
+    grp_sync();
 }
 
 // interpolation weights of IDAGetSolution at time t -> c[0..kord], d[0..kord-1]
@@ -241,7 +242,7 @@ __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, 
     IdaCoef& K = w.K;
     if (M.hh != M.hused || M.kk != M.kused) M.ns = 0;
     M.ns = min(M.ns + 1, M.kused + 2);
-    __syncwarp();
+    grp_sync();
     if (M.kk + 1 >= M.ns) {
         if (lane == 0) {
             K.beta[0] = 1.0; K.alpha[0] = 1.0; K.gamma[0] = 0.0; K.sigma[0] = 1.0;
@@ -259,7 +260,7 @@ __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, 
             K.psi[M.kk] = temp1;
         }
     }
-    __syncwarp();
+    grp_sync();
     double alphas = 0.0, alpha0 = 0.0;
 #pragma unroll 1
     for (int i = 0; i < M.kk; i++) { alphas -= 1.0 / (i + 1); alpha0 -= K.alpha[i]; }
@@ -294,7 +295,7 @@ __device__ __forceinline__ void predict_pass(const ModelDesc& m, WarpWS& w, cons
         }
         yp_[i] = yv; ypp_[i] = ypv; ee_[i] = 0.0;
     }
-    __syncwarp();
+    grp_sync();
 }
 
 __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Ida& M, double ck,
@@ -332,7 +333,7 @@ __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Id
 __device__ __forceinline__ void ida_restore(const ModelDesc& m, WarpWS& w, Ida& M, double saved_t, int lane) {
     IdaCoef& K = w.K;
     M.tn = saved_t;
-    __syncwarp();
+    grp_sync();
     if (lane == 0) {
 #pragma unroll 1
         for (int j = 1; j <= M.kk; j++) K.psi[j - 1] = K.psi[j] - M.hh;
@@ -345,7 +346,7 @@ __device__ __forceinline__ void ida_restore(const ModelDesc& m, WarpWS& w, Ida& 
             PLB_FOR_ELEMS(i, m.N_tot) ph[i] *= sc;
         }
     }
-    __syncwarp();
+    grp_sync();
 }
 
 __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w, const Opts& o, Ida& M,
@@ -402,7 +403,7 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
             else if (j < M.kused) { acc += ph[i]; ph[i] = acc; }
         }
     }
-    __syncwarp();
+    grp_sync();
 }
 
 // interpolated value / derivative of component i (internal index) with weights (c, d), order kord
@@ -431,7 +432,7 @@ __device__ __forceinline__ double weighted_T(const ModelDesc& m, const WarpWS& w
 #if PLB_TH
     const int NT = m.Na + m.Nx + m.Nz;
     double s = 0.0;
-    for (int i = lane; i < NT; i += 32) {
+    for (int i = lane; i < NT; i += LW) {
         const int x = i - m.Na;
         const int q = i < m.Na ? 0 : (x < m.Np ? 1 : (x < m.Np + m.Ns ? 2 : (x < m.Nx ? 3 : 4)));
         double v = 0.0;
@@ -506,9 +507,8 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
     // check_stop_dfilm :204-224 (the largest film growth rate over the anode; no derivative-sign test)
     {
         double mx = -INFINITY;
-        for (int k = lane; k < m.Nn; k += 32) mx = fmax(mx, interp_yp(w, d, kord, m.off_film + k));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+        for (int k = lane; k < m.Nn; k += LW) mx = fmax(mx, interp_yp(w, d, kord, m.off_film + k));
+        mx = grp_max(mx);
         if (b.dfilm_max == b.dfilm_max && mx - b.dfilm_max > eps) {
             const double tf_ = (pv.dfilm - b.dfilm_max) / (pv.dfilm - mx);
             if (tf_ < pv.frac) { pv.frac = tf_; flag = 10; }
@@ -519,9 +519,8 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
     // check_stop_c_s_surf :141-161
     if (b.c_s_n_max == b.c_s_n_max) {
         double mx = -INFINITY;
-        for (int e = m.Np + lane; e < m.Ne; e += 32) mx = fmax(mx, interp_y(w, c, kord, m.off_cs + (NR - 1) * m.Ne + e));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+        for (int e = m.Np + lane; e < m.Ne; e += LW) mx = fmax(mx, interp_y(w, c, kord, m.off_cs + (NR - 1) * m.Ne + e));
+        mx = grp_max(mx);
         const double lim = b.c_s_n_max * w.C.theta[TF_c_max_n];
         if (Ic > 0 && mx - lim > eps) {
             const double tf_ = (pv.c_s_n - lim) / (pv.c_s_n - mx);
@@ -532,9 +531,8 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
     // check_stop_c_e :163-183
     if (b.c_e_min == b.c_e_min) {
         double mn = INFINITY;
-        for (int i = lane; i < m.Nx; i += 32) mn = fmin(mn, interp_y(w, c, kord, i));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL, mn, off));
+        for (int i = lane; i < m.Nx; i += LW) mn = fmin(mn, interp_y(w, c, kord, i));
+        mn = grp_min(mn);
         if (b.c_e_min - mn > eps) {
             const double tf_ = (pv.c_e_min - b.c_e_min) / (pv.c_e_min - mn);
             if (tf_ < pv.frac) { pv.frac = tf_; flag = 9; }

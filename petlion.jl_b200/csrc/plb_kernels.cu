@@ -97,6 +97,11 @@ static const Variant V_TH = {th::info, th::slot_rc, th::slot_recipe, th::launch_
                              th::launch_newton, th::launch_linsolve, th::launch_simulate};
 static const Variant V_SEI = {sei::info, sei::slot_rc, sei::slot_recipe, sei::launch_resjac, sei::launch_initguess,
                               sei::launch_newton, sei::launch_linsolve, sei::launch_simulate};
+// grids with 33..64 x-nodes: two warps per system
+static const Variant V_WIDE = {wide::info, wide::slot_rc, wide::slot_recipe, wide::launch_resjac, wide::launch_initguess,
+                               wide::launch_newton, wide::launch_linsolve, wide::launch_simulate};
+static const Variant V_WSEI = {wsei::info, wsei::slot_rc, wsei::slot_recipe, wsei::launch_resjac, wsei::launch_initguess,
+                               wsei::launch_newton, wsei::launch_linsolve, wsei::launch_simulate};
 
 struct plb_handle_s {
     plb_model_desc desc;
@@ -129,7 +134,7 @@ static int build_patterns(plb_handle_s* h) {
     const int n_slots = h->vi.n_slots;
     for (int method = 0; method < h->n_methods; method++) {
         std::vector<std::pair<int, int>> ent;   // (col, row)
-        for (int lane = 0; lane < 32; lane++)
+        for (int lane = 0; lane < h->vi.lanes; lane++)
             for (int s = 0; s < n_slots; s++) {
                 int r, c;
                 if (h->v->slot_rc(m, method, s, lane, r, c)) ent.push_back({c, r});
@@ -148,7 +153,7 @@ static int build_patterns(plb_handle_s* h) {
         // per CSC position: where K1 takes the value from
         if ((int)ent.size() > h->vi.k1_src_max) return fail("internal: K1_SRC_MAX too small");
         std::vector<int> src(ent.size(), -1);
-        for (int lane = 0; lane < 32; lane++)
+        for (int lane = 0; lane < h->vi.lanes; lane++)
             for (int s = 0; s < n_slots; s++) {
                 int r, c;
                 if (!h->v->slot_rc(m, method, s, lane, r, c)) continue;
@@ -166,8 +171,11 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (d->aging && d->temperature) return fail("plb_create: aging=:SEI together with temperature=true is not built yet");
     if (d->aging && d->cathode != PLB_CATHODE_LCO) return fail("plb_create: aging=:SEI needs the LCO parameter set");
     if (d->N_r_p != NR_HOST || d->N_r_n != NR_HOST) return fail("plb_create: only N_r_p = N_r_n = 10 is built");
-    if (d->N_p < 2 || d->N_s < 2 || d->N_n < 2 || d->N_p + d->N_s + d->N_n > 32)
-        return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 32 (one lane per node)");
+    const int Nx_ = d->N_p + d->N_s + d->N_n;
+    if (d->N_p < 2 || d->N_s < 2 || d->N_n < 2 || Nx_ > 64)
+        return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 64 (one lane per node, one or two warps per system)");
+    if (Nx_ > 32 && d->temperature)
+        return fail("plb_create: temperature=true on grids with more than 32 x-nodes is not built");
     if (d->cathode != PLB_CATHODE_LCO && d->cathode != PLB_CATHODE_NMC) return fail("plb_create: unknown cathode");
     if (d->temperature) {
         // NMC()/LiC6_NMC() carry no thermal parameters (params.jl:295-367): the reference cannot build it either
@@ -182,7 +190,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     CUDA_OK(cudaSetDevice(d->device));
     plb_handle_s* h = new plb_handle_s();
     h->desc = *d;
-    h->v = d->temperature ? &V_TH : (d->aging ? &V_SEI : &V_ISO);
+    h->v = d->temperature ? &V_TH : (Nx_ > 32 ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
     h->n_methods = d->temperature ? 4 : 3;
     h->vi = h->v->info();
     ModelDesc& m = h->m;
@@ -225,7 +233,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
 }
 
 int plb_variant_info(int family, long long* out) {
-    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : iso::info());
+    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : iso::info())));
     out[0] = v.sim_warps; out[1] = v.sim_ctas; out[2] = (long long)v.sim_smem; out[3] = v.k1_warps;
     out[4] = v.k1_ctas; out[5] = (long long)v.k1_smem; out[6] = v.vs; out[7] = v.n_slots;
     return 0;

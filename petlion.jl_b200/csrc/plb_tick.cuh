@@ -101,7 +101,7 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
     }
     eeI += dI;
     store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
-    __syncwarp();
+    grp_sync();
     const double delnrm = sqrt((warp_sum(s) + (dI * ewtI) * (dI * ewtI)) / m.N_tot);
     int retval = -99;
     if (S.mi == 0) {
@@ -147,7 +147,7 @@ __device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const
         if ((M.tn + M.hh - M.tstop) * M.hh > 0.0) M.hh = (M.tstop - M.tn) * (1.0 - 4.0 * ur);
         M.kk = 0; M.kused = 0;
         { double* p1 = w.v(V_PHI1); PLB_FOR_ELEMS(i, m.N_tot) p1[i] *= M.hh; }
-        __syncwarp();
+        grp_sync();
     } else {
         const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
         if (fabs(M.tn - M.tstop) <= troundoff) {
@@ -166,9 +166,9 @@ __device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const
     S.saved_t = M.tn; S.ncf = 0; S.nef = 0; S.err_k = 0.0; S.err_km1 = 0.0;
     if (M.nst == 0) {
         M.kk = 1; M.kused = 0; M.hused = 0.0; M.cj = 1.0 / M.hh; M.phase = 0; M.ns = 0;
-        __syncwarp();
+        grp_sync();
         if (lane == 0) w.K.psi[0] = M.hh;
-        __syncwarp();
+        grp_sync();
     }
     attempt_begin(m, w, S, lane);
     return true;
@@ -225,11 +225,11 @@ __device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const O
     }
     if (!fail) {
         if (M.nst == 0) {
-            __syncwarp();
+            grp_sync();
             if (lane == 0) w.K.psi[0] = M.hh;
 #pragma unroll 1
-            for (int i = lane; i < m.N_tot; i += 32) w.v(V_PHI1)[i] *= M.rr;
-            __syncwarp();
+            for (int i = lane; i < m.N_tot; i += LW) w.v(V_PHI1)[i] *= M.rr;
+            grp_sync();
         }
         if (!(fabs(M.hh) > 0.0) || isinf(M.hh)) fail = FAIL_CONV;
     }
@@ -257,18 +257,18 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
             S.retried = 1;
             const double sc = 1.0 / w.K.psi[0];
 #pragma unroll 1
-            for (int i = lane; i < N; i += 32) w.v(V_PHI1)[i] *= sc;
-            __syncwarp();
+            for (int i = lane; i < N; i += LW) w.v(V_PHI1)[i] *= sc;
+            grp_sync();
             M.hin = a.o.reltol;
             return true;
         }
         S.hard = (S.ret_fl == FAIL_ERRTEST) ? FAIL_ERRTEST : FAIL_CONV;
         return false;
     }
-    __syncwarp();
+    grp_sync();
     if (lane == 0) S.kord = getsol_weights(M, w.K, S.t, w.K.cvals, w.K.dvals);
-    S.kord = __shfl_sync(FULL, S.kord, 0);
-    __syncwarp();
+    S.kord = grp_bcast_int(S.kord, 0);
+    grp_sync();
     double Ic = 0.0, vp = 0.0, vn = 0.0;
 #pragma unroll 1
     for (int j = 0; j <= S.kord; j++) {
@@ -316,15 +316,15 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
         bool do_interp = false;
         if (S.hard) S.flag = S.hard;
         else if (a.o.interp_final && S.flag != 0 && S.flag != -1 && S.t > 1.0) { do_interp = true; fr = S.pv.frac; }
-        __syncwarp();
+        grp_sync();
         if (lane == 0) {
             if (S.nsave <= 1) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = M.nst == 0 ? 1.0 : 1.0 / w.K.psi[0]; }
             if (do_interp) { double dp[6]; getsol_weights(M, w.K, S.tprev, w.K.cprev, dp); }
         }
-        __syncwarp();
+        grp_sync();
         double ps0 = 0.0, psN = 0.0, If = 0.0, Tw = 0.0, aux = 0.0;
 #pragma unroll 1
-        for (int i = lane; i < N; i += 32) {
+        for (int i = lane; i < N; i += LW) {
             const double yn = interp_y(w, w.K.cvals, S.kord, i);
             double yf = yn;
             if (do_interp) { const double ypv = interp_y(w, w.K.cprev, S.kord, i); yf = fr * (yn - ypv) + ypv; }
@@ -370,7 +370,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
     } else {
         // failed before integration: hand the (initial) state back
 #pragma unroll 1
-        for (int i = lane; i < N; i += 32) {
+        for (int i = lane; i < N; i += LW) {
             a.sY[(size_t)S.sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
             if (a.sYP) a.sYP[(size_t)S.sys * N + ref_index(m, i)] = 0.0;
         }
@@ -388,7 +388,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
         a.st[S.sys] = t_end;
         if (a.tr_n) a.tr_n[S.sys] = S.nsave < a.n_save_max ? S.nsave : a.n_save_max;
     }
-    __syncwarp();
+    grp_sync();
     S.state = ST_FETCH;
 }
 
@@ -398,7 +398,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
     const ModelDesc& m = a.m;
     int sys = 0;
     if (lane == 0) sys = atomicAdd(a.counter, 1);
-    sys = __shfl_sync(FULL, sys, 0);
+    sys = grp_bcast_int(sys, 0);
     if (sys >= a.B) { S.state = ST_EXHAUSTED; return; }
     S.sys = sys;
     const int N = m.N_tot;
@@ -436,11 +436,11 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
         S.t0 = 0.0;
     } else {
 #pragma unroll 1
-        for (int i = lane; i < N; i += 32) Y0[i] = a.sY[(size_t)sys * N + ref_index(m, i)];
+        for (int i = lane; i < N; i += LW) Y0[i] = a.sY[(size_t)sys * N + ref_index(m, i)];
         S.SOC = a.sSOC[sys];
         S.t0 = ::nextafter(a.st[sys], DBL_MAX);   // initial_time, model_evaluation.jl:112
     }
-    __syncwarp();
+    grp_sync();
     const double I_prev_state = Y0[m.off_I];
     // initial_current! (input_methods.jl:11-107)
     {
@@ -462,9 +462,9 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
             if (!a.new_run && I_prev_state != 0.0) Ig = I_prev_state;
             else Ig = S.rc.value > V0 ? 1.0 : -1.0;
         } else Ig = S.rc.value / (V0 * w.C.g[GC_I1C]);
-        __syncwarp();
+        grp_sync();
         if (lane == 0) Y0[m.off_I] = Ig;
-        __syncwarp();
+        grp_sync();
     }
     Ida& M = S.M;
     M.tn = 0.0; M.hh = 0.0; M.hused = 0.0; M.cj = 0.0; M.cjlast = 0.0; M.cjold = 0.0; M.cjratio = 1.0;
@@ -492,15 +492,15 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
     }
     for (int k = 2; k < 6; k++) {
 #pragma unroll 1
-        for (int i = lane; i < N; i += 32) w.v(V_PHI0 + k)[i] = 0.0;
+        for (int i = lane; i < N; i += LW) w.v(V_PHI0 + k)[i] = 0.0;
     }
-    __syncwarp();
+    grp_sync();
     S.ntstops = 0; S.itstop = 0;
     if (!a.new_run && 1.0 < a.tf) { S.tstop0 = 1.0; S.tstop1 = a.tf; S.ntstops = 2; }
     else { S.tstop0 = a.tf; S.tstop1 = a.tf; S.ntstops = 1; }
-    __syncwarp();
+    grp_sync();
     if (lane == 0) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = 1.0; }   // y = phi0, yp = phi1 = YP0
-    __syncwarp();
+    grp_sync();
     const double Vc = Y0[iP0] - Y0[iPN], Ic = Y0[m.off_I];
     S.I_prev = Ic;
     const size_t so = (size_t)S.sys * a.n_save_max;
@@ -525,7 +525,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
 
 template <int CHEM>
 __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* smem_raw) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
@@ -626,8 +626,8 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                     // recoverable failure with a stale Jacobian: redo once with a fresh one
                     S.callLSetup = 1; S.mi = 0;
 #pragma unroll 1
-                    for (int i = lane; i < m.N_tot; i += 32) w.v(V_EE)[i] = 0.0;
-                    __syncwarp();
+                    for (int i = lane; i < m.N_tot; i += LW) w.v(V_EE)[i] = 0.0;
+                    grp_sync();
                 } else if (retval != -99) {
                     after_nls(m, w, a.o, S, retval, lane);
                 }
@@ -640,7 +640,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 Iy -= dI;
                 s = warp_sum(s) + dI * dI;
                 store_lane(m, ro, w.v(V_PHI0), y, Iy, lane);
-                __syncwarp();
+                grp_sync();
                 S.ni_iter++;
                 const bool bad = lsetup_bad || !(s == s) || isinf(s);
                 if (bad || (S.ni_iter >= 100 && !(sqrt(s) < a.o.reltol_init))) {
@@ -659,7 +659,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
 #pragma unroll
                 for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
                 store_lane(m, ro, w.v(V_PHI1), ypo, 0.0, lane);
-                __syncwarp();
+                grp_sync();
                 const double c0 = fabs(w.C.theta[TF_c_e0]);
                 const double epsv = ::nextafter(c0, DBL_MAX) - c0;
                 S.dt_init = fmax(10.0 * a.o.reltol_init, sqrt(epsv));   // :464
@@ -671,7 +671,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 ypo.j = -res.j / S.dt_init; ypo.pe = -res.pe / S.dt_init; ypo.ps = -res.ps / S.dt_init;
                 if (SEI) ypo.js = -res.js / S.dt_init;
                 store_lane(m, ro, w.v(V_PHI1), ypo, -dI / S.dt_init, lane);
-                __syncwarp();
+                grp_sync();
                 begin_integration(a, w, S, lane);
             }
             // between evaluations: host loop of solve! until the next evaluation is needed

@@ -48,19 +48,19 @@ enum JacSlot {
 };
 
 #ifndef PLB_K1_CTAS
-#define PLB_K1_CTAS (PLB_TH ? 2 : 3)
+#define PLB_K1_CTAS (PLB_WIDE ? 1 : (PLB_TH ? 2 : 3))
 #endif
-constexpr int K1_WARPS = 4;
+constexpr int K1_WARPS = WIDE ? 2 : 4;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 5;   // lane-computed slots: 0..JS_CS0-1, then the five control-row slots
-constexpr int K1_SRC_MAX = TH ? 3072 : 2304;        // >= nnz of every built variant
+constexpr int K1_SRC_MAX = WIDE ? 4864 : (TH ? 3072 : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 struct K1Warp {
-    double S[K1_NSTAGE][32];   // lane-computed Jacobian entries
+    double S[K1_NSTAGE][LW];   // lane-computed Jacobian entries
     double MCs[NR * NR];       // particle stencil coefficients (contiguous with S: one value table)
     WarpConst C;
 };
-constexpr size_t K1_SMEM = sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX;
+constexpr size_t K1_SMEM = XCH_BYTES_PER_GROUP * K1_WARPS + sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX;
 
 // K1: one warp evaluates F and the CSC values of dF/dY + gamma dF/dY' of one system at a time.
 // HBM traffic per system is exactly the algorithmic 8*(3N + n_theta + nnz) bytes: Y, Y', theta rows
@@ -73,17 +73,18 @@ constexpr size_t K1_SMEM = sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX;
 //   K1_NSTAGE*32 + r*NR+c), 16 particle-block entry, 17 anode (isothermal: D_s per electrode),
 //   18 diagonal, 19-23 node (thermal: D_s(T) per node)
 template <int CHEM>
-__global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArgs a) {
-    extern __shared__ __align__(16) unsigned char k1_raw[];
+__global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(ResJacArgs a) {
+    extern __shared__ __align__(16) unsigned char k1_raw0[];
+    unsigned char* k1_raw = k1_raw0 + XCH_BYTES_PER_GROUP * K1_WARPS;   // wide: the exchange scratch comes first
     K1Warp* ws = reinterpret_cast<K1Warp*>(k1_raw);
     int* src_s = reinterpret_cast<int*>(k1_raw + sizeof(K1Warp) * K1_WARPS);
     for (int i = threadIdx.x; i < a.nnz; i += blockDim.x) src_s[i] = a.src[i];
     {
-        K1Warp& w0 = ws[threadIdx.x >> 5];
-        for (int i = threadIdx.x & 31; i < NR * NR; i += 32) w0.MCs[i] = laws::MC[i / NR][i % NR];
+        K1Warp& w0 = ws[grp_id()];
+        for (int i = grp_lane(); i < NR * NR; i += LW) w0.MCs[i] = laws::MC[i / NR][i % NR];
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = grp_id(), lane = grp_lane();
     const ModelDesc& m = a.m;
     const int N = m.N_tot;
     K1Warp& w = ws[warp];
@@ -182,12 +183,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArg
             w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
             w.S[k1_stage_slot(JS_CTRL_T)][lane] = g * ctrl.gTn;
             w.S[k1_stage_slot(JS_CTRL_TX)][lane] = g * ctrl.gTx;
-            __syncwarp();
+            grp_sync();
             const double* tab = &w.S[0][0];
             double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
 #if PLB_TH
 #pragma unroll 4
-            for (int p = lane; p < a.nnz; p += 32) {
+            for (int p = lane; p < a.nnz; p += LW) {
                 const int rc = src_s[p];
                 const double t = tab[rc & 0xffff];
                 const double kap = tab[JS_KAP * 32 + ((rc >> 19) & 31)];
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArg
 #else
             const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
 #pragma unroll 4
-            for (int p = lane; p < a.nnz; p += 32) {
+            for (int p = lane; p < a.nnz; p += LW) {
                 const int rc = src_s[p];
                 const double t = tab[rc & 0xffff];
                 const double kap = (rc & (1 << 17)) ? kap_n : kap_p;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, PLB_K1_CTAS) k_resjac(ResJacArg
             }
 #endif
         }
-        __syncwarp();
+        grp_sync();
     }
 }
 
@@ -332,26 +333,26 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
     if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {
         const int rr = (slot - JS_CS0) / NR, cc = (slot - JS_CS0) % NR;
         const int el = lane >= m.Np + m.Ns ? 1 : 0;
-        return (K1_NSTAGE * 32 + rr * NR + cc) | (1 << 16) | (el << 17) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
+        return (K1_NSTAGE * LW + rr * NR + cc) | (1 << 16) | (el << 17) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
     }
-    return k1_stage_slot(slot) * 32 + lane;
+    return k1_stage_slot(slot) * LW + lane;
 }
 
 // =================================================================================================
 // initial_guess!, newtons_method!, linear solve, simulate
 // =================================================================================================
 #ifndef PLB_SIM_WARPS
-#define PLB_SIM_WARPS (PLB_TH ? 4 : (PLB_SEI ? 5 : 6))   // warps (systems in flight) per CTA
+#define PLB_SIM_WARPS (PLB_WIDE ? 2 : (PLB_TH ? 4 : (PLB_SEI ? 5 : 6)))   // systems (lane groups) in flight per CTA
 #endif
 #ifndef PLB_SIM_CTAS
 #define PLB_SIM_CTAS 1            // CTAs per SM the register/shared-memory budget is sized for
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
-constexpr size_t SIM_SMEM = sizeof(WarpSmem) * SIM_WARPS;
+constexpr size_t SIM_SMEM = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
 
 __device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
-    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw + XCH_BYTES_PER_GROUP * SIM_WARPS)[warp];
     double* g = gws + ((size_t)blockIdx.x * SIM_WARPS + warp) * (size_t)(NGLOBAL > 0 ? NGLOBAL : 1) * VS;
     return WarpWS{g, &sm.svec[0][0], sm.C, sm.Fa, sm.K};
 }
@@ -393,9 +394,9 @@ __device__ __forceinline__ void initial_lane(const ModelDesc& m, const WarpConst
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_initguess(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_initguess(AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
@@ -405,56 +406,56 @@ __global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_initguess(AuxArgs 
         LaneVec y0;
         initial_lane<CHEM>(m, w.C, ro, a.soc[sys], y0);
         store_lane(m, ro, w.v(V_PHI0), y0, 0.0, lane);
-        __syncwarp();
-        for (int i = lane; i < N; i += 32) a.Y[(size_t)sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
-        __syncwarp();
+        grp_sync();
+        for (int i = lane; i < N; i += LW) a.Y[(size_t)sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
+        grp_sync();
     }
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_newton(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_newton(AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
     const int N = m.N_tot;
     for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
         setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
-        for (int i = lane; i < N; i += 32) w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
-        __syncwarp();
+        for (int i = lane; i < N; i += LW) w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
+        grp_sync();
         RunCtl rc;
         rc.method = a.method;
         rc.value = a.values ? a.values[sys] : a.value;
         int nres = 0, njac = 0;
         const int it = newton_init<CHEM>(m, w, ro, rc, a.o, w.v(V_PHI0), w.v(V_PHI1), lane, nres, njac);
-        for (int i = lane; i < N; i += 32) {
+        for (int i = lane; i < N; i += LW) {
             a.Y[(size_t)sys * N + ref_index(m, i)] = w.v(V_PHI0)[i];
             a.YP[(size_t)sys * N + ref_index(m, i)] = it > 0 ? w.v(V_PHI1)[i] : 0.0;
         }
         if (lane == 0 && a.status) a.status[sys] = it;
-        __syncwarp();
+        grp_sync();
     }
 }
 
 // x = (dF/dY + gamma dF/dY')^{-1} rhs at the state (Y, Y'): Jacobian evaluation, structured
 // factorisation and one solve -- what KLU does for IDA (model_evaluation.jl:265-271)
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_linsolve(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_linsolve(AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
     const int N = m.N_tot;
     for (int sys = blockIdx.x * SIM_WARPS + warp; sys < a.B; sys += gridDim.x * SIM_WARPS) {
         setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
-        for (int i = lane; i < N; i += 32) {
+        for (int i = lane; i < N; i += LW) {
             w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
             w.v(V_PHI1)[i] = a.YP[(size_t)sys * N + ref_index(m, i)];
             w.v(V_EE)[i] = a.rhs[(size_t)sys * N + ref_index(m, i)];
         }
-        __syncwarp();
+        grp_sync();
         LaneVec y, yp, res, g;
         double Iy, Ip, gI;
         load_lane(m, ro, w.v(V_PHI0), y, Iy);
@@ -466,17 +467,17 @@ __global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_linsolve(AuxArgs a
         const double cj = a.gamma ? a.gamma[sys] : 0.0;
         warp_factor(m, ro, J, ctrl, cj, false, w.Fa, lane);
         const double dI = warp_solve(m, ro, w.Fa, false, g, gI, lane);
-        __syncwarp();
+        grp_sync();
         store_lane(m, ro, w.v(V_EE), g, dI, lane);
-        __syncwarp();
-        for (int i = lane; i < N; i += 32) a.x[(size_t)sys * N + ref_index(m, i)] = w.v(V_EE)[i];
+        grp_sync();
+        for (int i = lane; i < N; i += LW) a.x[(size_t)sys * N + ref_index(m, i)] = w.v(V_EE)[i];
         if (lane == 0 && a.status) a.status[sys] = (w.Fa.schur_inv == w.Fa.schur_inv) ? 0 : -1;
-        __syncwarp();
+        grp_sync();
     }
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * 32, SIM_CTAS) k_simulate(SimArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_simulate(SimArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // persistent CTAs; every warp pulls systems from a global queue (step counts vary ~1.5x across
     // a batch) and all warps of the CTA tick in lockstep through the heavy phases (plb_tick.cuh)
@@ -490,7 +491,7 @@ VariantInfo info() {
     VariantInfo v;
     v.sim_warps = SIM_WARPS; v.sim_ctas = SIM_CTAS; v.k1_warps = K1_WARPS; v.k1_ctas = PLB_K1_CTAS;
     v.sim_smem = SIM_SMEM; v.k1_smem = K1_SMEM; v.vs = VS; v.nglobal = NGLOBAL;
-    v.n_slots = JS_COUNT; v.n_stage = K1_NSTAGE; v.k1_src_max = K1_SRC_MAX;
+    v.n_slots = JS_COUNT; v.n_stage = K1_NSTAGE; v.k1_src_max = K1_SRC_MAX; v.lanes = LW;
     return v;
 }
 
@@ -510,11 +511,11 @@ VariantInfo info() {
         return cudaGetLastError();                                                                                  \
     } while (0)
 
-cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_resjac, a, grid, K1_WARPS * 32, K1_SMEM, s); }
-cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_initguess, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
-cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_newton, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
-cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_linsolve, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
-cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_simulate, a, grid, SIM_WARPS * 32, SIM_SMEM, s); }
+cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_resjac, a, grid, K1_WARPS * LW, K1_SMEM, s); }
+cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_initguess, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
+cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_newton, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
+cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_linsolve, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
+cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_simulate, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 
 }  // namespace PLB_NS
 }  // namespace plb

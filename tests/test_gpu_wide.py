@@ -1,0 +1,143 @@
+"""GPU parity tests of the wide families: grids with 33..64 x-nodes, two warps per system.
+BASELINE.json configs[4]: LCO, aging = :SEI, N = (20,20,20) -> 642 DAEs; and the same grid without aging (602)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+GRID = dict(N_p=20, N_s=20, N_n=20)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import petlion_b200
+    return petlion_b200
+
+
+@pytest.fixture(scope="module", params=["plain", "sei"])
+def fam(request, P):
+    aging = request.param == "sei"
+    p = P.petlion("LCO", aging="SEI" if aging else False, **GRID)
+    m = O.make_model("LCO", aging=aging, **GRID)
+    return p, m, aging
+
+
+def test_sizes_and_pattern(fam):
+    p, m, aging = fam
+    L = O.layout(m)
+    assert p.N.tot == L.N_tot == (642 if aging else 602)
+    assert p.N.diff == L.N_diff
+    for method in ("I", "V", "P"):
+        cp, rv = O.jac_pattern(m, method)
+        cp2, rv2 = p.jac_pattern(method)
+        assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2), method
+
+
+def _states(m, tho, cur, soc0, t_mid):
+    b = O.default_bounds("LCO", V_max=4.3)
+    r = O.simulate_batch(m, tho, O.make_run("I", cur, tf=t_mid), O.default_opts(), b, SOC0=soc0, nthreads=8)
+    assert np.all(r["flag"] == 0)
+    return r["state"]["Y"], r["state"]["YP"]
+
+
+@pytest.mark.parametrize("cur,soc0,method,value", [(1.0, 0.2, "I", 1.0), (-1.0, 0.9, "V", 3.8), (1.5, 0.3, "P", 150.0)])
+def test_resjac_parity(fam, cur, soc0, method, value):
+    p, m, aging = fam
+    B = 6
+    L = O.layout(m); N = L.N_tot
+    tho = util.oracle_theta_batch(B, first=10)
+    th = util.product_theta_from_oracle(p, tho)
+    Y, YP = _states(m, tho, cur, soc0, 600.0)
+    gam = np.random.default_rng(5).uniform(0.01, 50.0, size=B)
+    res, nz = p.resjac(Y, YP, gam, method=method, value=value, theta=th)
+    run = O.make_run(method, value)
+    cp, rv = O.jac_pattern(m, method)
+    cols = np.repeat(np.arange(N), np.diff(cp))
+    for s in range(B):
+        r_ref = O.residual(m, tho[s], run, 0.0, Y[s], YP[s])
+        j_ref = O.jacobian(m, tho[s], run, 0.0, Y[s], YP[s], gam[s])
+        scale = np.zeros(N)
+        np.maximum.at(scale, rv, np.abs(j_ref) * np.maximum(np.abs(Y[s][cols]), 1e-12))
+        scale = np.maximum(scale, np.abs(r_ref))
+        er = np.abs(res[s] - r_ref) / (scale + 1e-300)
+        assert er.max() < 1e-9, (s, int(er.argmax()), res[s][er.argmax()], r_ref[er.argmax()])
+        rowmax = np.zeros(N); np.maximum.at(rowmax, rv, np.abs(j_ref))
+        ej = np.abs(nz[s] - j_ref) / rowmax[rv]
+        k = int(ej.argmax())
+        assert ej.max() < 1e-9, (s, int(rv[k]), int(cols[k]), nz[s][k], j_ref[k])
+
+
+def test_linear_solve_equals_dense(fam):
+    p, m, aging = fam
+    B = 4
+    tho = util.oracle_theta_batch(B, first=40)
+    th = util.product_theta_from_oracle(p, tho)
+    Y, YP = _states(m, tho, 1.0, 0.2, 600.0)
+    gam = np.array([50.0, 1.0, 0.05, 0.01])
+    run = O.make_run("I", 1.0)
+    cp, rv = O.jac_pattern(m, "I")
+    N = len(cp) - 1
+    rng = np.random.default_rng(2)
+    Js, rhs = [], []
+    for s in range(B):
+        nzv = O.jacobian(m, tho[s], run, 0.0, Y[s], YP[s], gam[s])
+        J = np.zeros((N, N))
+        for c in range(N):
+            J[rv[cp[c]:cp[c + 1]], c] = nzv[cp[c]:cp[c + 1]]
+        Js.append(J); rhs.append(rng.normal(size=N) * np.abs(J).max(axis=1) * 1e-3)
+    rhs = np.stack(rhs)
+    x, st = p.linear_solve(Y, YP, gam, rhs, method="I", value=1.0, theta=th)
+    for s in range(B):
+        xr = np.linalg.solve(Js[s], rhs[s])
+        rr = np.linalg.norm(Js[s] @ x[s] - rhs[s]) / np.linalg.norm(rhs[s])
+        rr_ref = np.linalg.norm(Js[s] @ xr - rhs[s]) / np.linalg.norm(rhs[s])
+        print("wide solve", aging, s, rr, rr_ref)
+        assert rr < 20 * rr_ref + 1e-11, (s, rr, rr_ref)
+
+
+def test_newton_init_parity(fam):
+    p, m, aging = fam
+    L = O.layout(m)
+    B = 6
+    tho = util.oracle_theta_batch(B)
+    th = util.product_theta_from_oracle(p, tho)
+    soc = np.linspace(0.1, 0.9, B)
+    cur = np.where(np.arange(B) % 2 == 0, -1.0, 2.0)
+    Y0 = p.initial_guess(soc, theta=th)
+    for s in range(B):
+        np.testing.assert_allclose(Y0[s], O.initial_guess(m, tho[s], soc[s]), rtol=1e-13, atol=0)
+    Y0[:, L.I] = cur
+    st, Y, YP = p.newton_init(Y0, method="I", value=cur, theta=th)
+    opts = O.default_opts()
+    for s in range(B):
+        it, y, yp = O.newton_init(m, tho[s], O.make_run("I", cur[s]), opts, Y0[s])
+        assert st[s] == it
+        np.testing.assert_allclose(Y[s], y, rtol=1e-9, atol=1e-14)
+
+
+def test_simulate_parity(P, fam):
+    """configs[4] at test size: randomised batch; 1C charge (side reaction active with aging) and 1C discharge"""
+    p, m, aging = fam
+    B = 16
+    tho = util.oracle_theta_batch(B, first=8000)
+    th = util.product_theta_from_oracle(p, tho)
+    util.set_theta_batch(p, th)
+    b = O.default_bounds("LCO", V_max=4.2)
+    for cur, soc0 in ((1.0, 0.0), (-1.0, 1.0)):
+        sol = P.simulate(p, I=cur, SOC=soc0, V_max=4.2)
+        ref = O.simulate_batch(m, tho, O.make_run("I", cur), O.default_opts(), b, SOC0=soc0, n_save_max=512, nthreads=8)
+        s = sol.results[-1].summary
+        same = (s["n_steps"] == ref["n_steps"]) & (s["flag"] == ref["flag"])
+        print("wide", aging, cur, "identical", float(np.mean(same)), s["n_steps"][:6], ref["n_steps"][:6], s["flag"][:6], ref["flag"][:6])
+        assert np.mean(same) >= 0.8
+        np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=1e-6)
+        np.testing.assert_allclose(s["t_end"][same], ref["t_end"][same], rtol=1e-5)
+        for k in np.where(same)[0]:
+            n = ref["traj_n"][k]
+            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=1e-6)
+        if aging and cur > 0:
+            L = O.layout(m)
+            np.testing.assert_allclose(s["aux_end"][same], ref["state"]["Y"][same][:, L.SOH], rtol=1e-9)
