@@ -1,5 +1,5 @@
 """GPU parity tests of the wide families: grids with 33..64 x-nodes, two warps per system.
-BASELINE.json configs[4]: LCO, aging = :SEI, N = (20,20,20) -> 642 DAEs; and the same grid without aging (602)."""
+BASELINE.json configs[4]: LCO, aging = :SEI, N = (20,20,20) -> 642 DAEs; and the same grid without aging (601)."""
 import numpy as np
 import pytest
 
@@ -28,7 +28,7 @@ def fam(request, P):
 def test_sizes_and_pattern(fam):
     p, m, aging = fam
     L = O.layout(m)
-    assert p.N.tot == L.N_tot == (642 if aging else 602)
+    assert p.N.tot == L.N_tot == (642 if aging else 601)
     assert p.N.diff == L.N_diff
     for method in ("I", "V", "P"):
         cp, rv = O.jac_pattern(m, method)
