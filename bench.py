@@ -44,6 +44,11 @@ WORKLOADS = {
                  metric="GITT protocol sims/sec (NMC 301-DAE, FP64)", cathode="NMC", temperature=False,
                  batch=32768, soc0=0.0,
                  protocol=[seg for _ in range(20) for seg in (("I", 0, 1.0, 180.0, {}), ("I", 2, 0.0, 7200.0, {}))]),
+    "cfg5": dict(name="configs[4]: batch=65536 LCO with aging=:SEI on the refined grid N=(20,20,20) (642 DAEs, two warps per "
+                      "system), randomised {D_s,k,eps}; 1C charge to 4.2 V (side reaction active) then 1C discharge via simulate!",
+                 metric="charge+discharge sims/sec (LCO SEI 642-DAE, FP64)", cathode="LCO", temperature=False, aging=True,
+                 grid=dict(N_p=20, N_s=20, N_n=20), batch=65536, soc0=0.0,
+                 protocol=[("I", 0, 1.0, 1e6, {"V_max": 4.2}), ("I", 0, -1.0, 1e6, {"V_max": 4.2})]),
     "cfg5n10": dict(name="configs[4] physics on the N=(10,10,10) grid (322 DAEs; the refined N=(20,20,20) grid is not built): "
                          "batch=65536 LCO with aging=:SEI, randomised {D_s,k,eps}; 1C charge to 4.2 V (side reaction active) "
                          "then 1C discharge via simulate!",
@@ -119,7 +124,7 @@ def synth_theta(p, B, first, cathode="LCO"):
 def oracle_protocol(W, tho, nthreads, n_save_max=0):
     """the CPU oracle over the same protocol (checker / CPU baseline): returns the per-segment results"""
     import oracle as O
-    m = O.make_model(W["cathode"], temperature=W["temperature"], aging=W.get("aging", False))
+    m = O.make_model(W["cathode"], temperature=W["temperature"], aging=W.get("aging", False), **W.get("grid", {}))
     opts = O.default_opts()
     out, state = [], None
     for k, (method, kind, value, tf, bo) in enumerate(W["protocol"]):
@@ -140,7 +145,7 @@ def run_reference(args):
     from tests import util
     W = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    per_core = {"cfg2": 256, "cfg3": 48, "cfg4": 12, "cfg5n10": 96}[args.workload]
+    per_core = {"cfg2": 256, "cfg3": 48, "cfg4": 12, "cfg5": 12, "cfg5n10": 96}[args.workload]
     sample = per_core * cores if args.sample is None else args.sample
     tho = util.oracle_theta_batch(sample, cathode=W["cathode"])
     for _ in range(args.warmup):
@@ -195,7 +200,8 @@ def main():
     import petlion_b200 as P
     from petlion_b200 import _lib
     L = _lib.lib()
-    p = P.petlion(W["cathode"], temperature=W["temperature"], aging=W.get("aging", False), device=local_rank)
+    p = P.petlion(W["cathode"], temperature=W["temperature"], aging=W.get("aging", False), device=local_rank,
+                  **W.get("grid", {}))
     h = p._h
     B = args.batch
     N, nth = p.N.tot, len(p.θ_keys)
@@ -319,7 +325,7 @@ def main():
     cpu_baseline = None
     if rank == 0:
         # valid mid-run states: integrate the batch part of the way through segment 0, keep (Y, Y') on device
-        t_mid = {"cfg2": 1800.0, "cfg3": 150.0, "cfg4": 100.0, "cfg5n10": 1800.0}[args.workload]
+        t_mid = {"cfg2": 1800.0, "cfg3": 150.0, "cfg4": 100.0, "cfg5": 1800.0, "cfg5n10": 1800.0}[args.workload]
         run_mid = _lib.Run(run.method, 0, run.value, t_mid, 1, 0)
         _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run_mid), None, C.byref(o), C.byref(b),
                                   d_soc0.data_ptr(), d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(),
@@ -356,7 +362,7 @@ def main():
         # ---------------- CPU baseline: oracle port on the host cores, bounded sample ---------------
         if world == 1 and not args.no_cpu_baseline and len(segs) > 1:
             cores = os.cpu_count() or 1
-            per_core = {"cfg3": 48, "cfg4": 12, "cfg5n10": 96}[args.workload]
+            per_core = {"cfg3": 48, "cfg4": 12, "cfg5": 12, "cfg5n10": 96}[args.workload]
             sample = min(per_core * cores if args.sample is None else args.sample, B)
             t0 = time.perf_counter()
             rs = oracle_protocol(W, tho[:sample], cores)
