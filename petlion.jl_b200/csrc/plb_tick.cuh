@@ -20,6 +20,18 @@
 namespace plb {
 namespace PLB_NS {
 
+// alignment barriers inside a tick (a performance heuristic only: they keep the warps of a CTA on one
+// instruction stream through the factorisation and the solve; results do not depend on them)
+#ifndef PLB_TICK_SYNC_JAC
+#define PLB_TICK_SYNC_JAC 0
+#endif
+#ifndef PLB_TICK_SYNC_SOLVE
+#define PLB_TICK_SYNC_SOLVE 0     // measured (iso, 6 warps x 1 CTA): 172 k sims/s with it, 225 k without
+#endif
+#ifndef PLB_TICK_VOTE_JAC
+#define PLB_TICK_VOTE_JAC 0       // CTA-wide vote "does any warp factorise in this tick?": 225 k with, 229 k without
+#endif
+
 enum TickState { ST_FETCH = 0, ST_INIT_ITER, ST_INIT_RDIFF, ST_INIT_DT, ST_NLS, ST_EXHAUSTED };
 enum Pending { PEND_NONE = 0, PEND_RETURNED, PEND_BEGIN, PEND_FINISH };
 
@@ -577,7 +589,11 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         }
         // ------------------------------ aligned heavy phases --------------------------------------------
         if (!__syncthreads_or(do_eval)) break;
+#if PLB_TICK_VOTE_JAC
         const int any_jac = __syncthreads_or(do_eval && need_jac);
+#else
+        const int any_jac = do_eval && need_jac;
+#endif
         LaneJac J;
         CtrlRow ctrl;
         ctrl.res = 0.0; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; ctrl.gTn = 0.0; ctrl.gTx = 0.0;
@@ -592,7 +608,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         }
         bool lsetup_bad = false;
         if (any_jac) {
+#if PLB_TICK_SYNC_JAC
             __syncthreads();
+#endif
             if (do_eval && need_jac) {
                 warp_factor_impl(m, ro, J, ctrl, alg_only ? 0.0 : S.M.cj, alg_only, w.Fa, lane);
                 S.M.nje++;
@@ -600,7 +618,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 lsetup_bad = !(chk == chk) || isinf(chk);
             }
         }
+#if PLB_TICK_SYNC_SOLVE
         __syncthreads();
+#endif
         double dI = 0.0;
         if (do_eval && do_solve && !lsetup_bad) {
             double gI = ctrl.res;

@@ -342,10 +342,13 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // initial_guess!, newtons_method!, linear solve, simulate
 // =================================================================================================
 #ifndef PLB_SIM_WARPS
-#define PLB_SIM_WARPS (PLB_WIDE ? 2 : (PLB_TH ? 4 : (PLB_SEI ? 5 : 6)))   // systems (lane groups) in flight per CTA
+// systems (lane groups) in flight per CTA, and CTAs per SM.  One barrier per tick (plb_tick.cuh) keeps the
+// systems of a CTA on one instruction stream; with only that barrier left, one large CTA per SM is best for the
+// 32-lane families (measured, iso, sims/s on one B200: 6x1 229 k, 3x2 213 k, 2x3 200 k).
+#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? 4 : (PLB_SEI ? 5 : 6)))
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS 1            // CTAs per SM the register/shared-memory budget is sized for
+#define PLB_SIM_CTAS (PLB_WIDE ? 2 : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
