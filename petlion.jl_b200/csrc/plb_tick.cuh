@@ -28,6 +28,9 @@ namespace PLB_NS {
 #ifndef PLB_TICK_SYNC_SOLVE
 #define PLB_TICK_SYNC_SOLVE 0     // measured (iso, 6 warps x 1 CTA): 172 k sims/s with it, 225 k without
 #endif
+#ifndef PLB_TICK_SYNC_START
+#define PLB_TICK_SYNC_START 1     // the one barrier per tick that keeps a CTA's systems on one instruction stream
+#endif
 #ifndef PLB_TICK_VOTE_JAC
 #define PLB_TICK_VOTE_JAC 0       // CTA-wide vote "does any warp factorise in this tick?": 225 k with, 229 k without
 #endif
@@ -303,7 +306,13 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
         if (lane == 0) a.tr_T[so + S.nsave] = Tw;
     }
     S.nsave++;
-    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, Ic, Vc, lane);
+    {   // copies: check_stop is out of line, and S must not have its address taken (it would live in local memory)
+        PrevVals pv = S.pv;
+        int flag = S.flag;
+        const RunCtl rc = S.rc;
+        check_stop(m, w, rc, a.o, a.b, a.input_kind == 2, a.tf, pv, flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, Ic, Vc, lane);
+        S.pv = pv; S.flag = flag;
+    }
     if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return false; }
     if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { S.hard = FAIL_NONFINITE; return false; }
     if (S.flag != -1) return false;
@@ -530,7 +539,13 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
     S.pv.T = -1; S.pv.dfilm = -1;
     S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
     S.kord = 1;
-    check_stop(m, w, S.rc, a.o, a.b, a.input_kind == 2, a.tf, S.pv, S.flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, Ic, Vc, lane);
+    {
+        PrevVals pv = S.pv;
+        int flag = S.flag;
+        const RunCtl rc = S.rc;
+        check_stop(m, w, rc, a.o, a.b, a.input_kind == 2, a.tf, pv, flag, 0.0, w.K.cvals, w.K.dvals, 1, S.SOC, Ic, Vc, lane);
+        S.pv = pv; S.flag = flag;
+    }
     S.tg_prev = S.t0;
     S.pending = (S.flag == -1) ? PEND_BEGIN : PEND_FINISH;
 }
@@ -541,7 +556,13 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
     WarpWS w = make_ws(smem_raw, a.gws, warp);
     const ModelDesc& m = a.m;
     const LaneRole ro = make_role(m, lane);
+#if PLB_STATE_SMEM
+    static_assert(sizeof(SimState) <= STATE_BYTES, "STATE_BYTES too small");
+    // every lane of a warp writes the same values at the same instruction: one copy per physical warp
+    SimState& S = *reinterpret_cast<SimState*>(smem_raw + STATE_OFFSET + STATE_BYTES * (threadIdx.x >> 5));
+#else
     SimState S;
+#endif
     S.state = ST_FETCH; S.pending = PEND_NONE; S.sys = 0;
     for (;;) {
         // ------------------------------ PRE: get to an evaluation point ---------------------------------
@@ -588,7 +609,11 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             }
         }
         // ------------------------------ aligned heavy phases --------------------------------------------
+#if PLB_TICK_SYNC_START
         if (!__syncthreads_or(do_eval)) break;
+#else
+        if (!do_eval) break;
+#endif
 #if PLB_TICK_VOTE_JAC
         const int any_jac = __syncthreads_or(do_eval && need_jac);
 #else

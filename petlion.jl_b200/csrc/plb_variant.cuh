@@ -73,7 +73,7 @@ constexpr size_t K1_SMEM = XCH_BYTES_PER_GROUP * K1_WARPS + sizeof(K1Warp) * K1_
 //   K1_NSTAGE*32 + r*NR+c), 16 particle-block entry, 17 anode (isothermal: D_s per electrode),
 //   18 diagonal, 19-23 node (thermal: D_s(T) per node)
 template <int CHEM>
-__global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(ResJacArgs a) {
+__global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __grid_constant__ ResJacArgs a) {
     extern __shared__ __align__(16) unsigned char k1_raw0[];
     unsigned char* k1_raw = k1_raw0 + XCH_BYTES_PER_GROUP * K1_WARPS;   // wide: the exchange scratch comes first
     K1Warp* ws = reinterpret_cast<K1Warp*>(k1_raw);
@@ -352,7 +352,13 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
-constexpr size_t SIM_SMEM = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
+// optional: the warp-uniform integrator state (SimState, plb_tick.cuh) in shared memory instead of registers
+#ifndef PLB_STATE_SMEM
+#define PLB_STATE_SMEM 1          // measured (iso): 229 k sims/s in registers/local memory, 246 k in shared memory
+#endif
+constexpr size_t STATE_BYTES = PLB_STATE_SMEM ? 640 : 0;           // per physical warp
+constexpr size_t STATE_OFFSET = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
+constexpr size_t SIM_SMEM = STATE_OFFSET + STATE_BYTES * SIM_WARPS * (LW / 32);
 
 __device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw + XCH_BYTES_PER_GROUP * SIM_WARPS)[warp];
@@ -397,7 +403,7 @@ __device__ __forceinline__ void initial_lane(const ModelDesc& m, const WarpConst
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_initguess(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_initguess(const __grid_constant__ AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_initguess(AuxArgs 
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_newton(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_newton(const __grid_constant__ AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
@@ -444,7 +450,7 @@ __global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_newton(AuxArgs a) 
 // x = (dF/dY + gamma dF/dY')^{-1} rhs at the state (Y, Y'): Jacobian evaluation, structured
 // factorisation and one solve -- what KLU does for IDA (model_evaluation.jl:265-271)
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_linsolve(AuxArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_linsolve(const __grid_constant__ AuxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_linsolve(AuxArgs a
 }
 
 template <int CHEM>
-__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_simulate(SimArgs a) {
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_simulate(const __grid_constant__ SimArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // persistent CTAs; every warp pulls systems from a global queue (step counts vary ~1.5x across
     // a batch) and all warps of the CTA tick in lockstep through the heavy phases (plb_tick.cuh)
