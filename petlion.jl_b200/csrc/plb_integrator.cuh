@@ -353,6 +353,7 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
                                                   double err_k, double err_km1, int lane) {
     const double* ee = w.v(V_EE);
     const double* ewt = w.v(V_EWT);
+    __syncwarp();   // M (part of the shared-memory state) is read-modify-written by all lanes together
     M.nst++;
     const int kdiff = M.kk - M.kused;
     M.kused = M.kk;

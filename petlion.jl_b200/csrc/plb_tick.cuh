@@ -63,6 +63,7 @@ struct SimState {
 // ---- pieces of ida_nls -------------------------------------------------------------------------------
 __device__ __forceinline__ void nls_begin(const ModelDesc& m, WarpWS& w, SimState& S, int lane) {
     Ida& M = S.M;
+    __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     S.callLSetup = 0;
     if (M.nst == 0) { M.cjold = M.cj; M.ss = 20.0; S.callLSetup = 1; }
     predict_pass(m, w, M, lane);
@@ -118,6 +119,7 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
     store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
     grp_sync();
     const double delnrm = sqrt((warp_sum(s) + (dI * ewtI) * (dI * ewtI)) / m.N_tot);
+    __syncwarp();
     int retval = -99;
     if (S.mi == 0) {
         S.oldnrm = delnrm;
@@ -146,6 +148,7 @@ __device__ __forceinline__ void attempt_begin(const ModelDesc& m, WarpWS& w, Sim
 // (state = ST_NLS), false if the call returned (S.ret_fl / S.ret_t set).
 __device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const Opts& o, SimState& S, int lane) {
     Ida& M = S.M;
+    __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const double ur = DBL_EPSILON;
     const double tout = S.itstop == 0 ? S.tstop0 : S.tstop1;
     M.tstop = tout; M.tstopset = 1;
@@ -192,6 +195,7 @@ __device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const
 // IDAStopTest2 after a successful step
 __device__ __forceinline__ void solve_end(SimState& S) {
     Ida& M = S.M;
+    __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const double ur = DBL_EPSILON;
     if (M.tstopset) {
         const double troundoff = 100.0 * ur * (fabs(M.tn) + fabs(M.hh));
@@ -208,6 +212,7 @@ __device__ __forceinline__ void solve_end(SimState& S) {
 // step completion or retry bookkeeping (IDAStep / IDAHandleNFlag).  Sets S.pending.
 __device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const Opts& o, SimState& S, int retval, int lane) {
     Ida& M = S.M;
+    __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     bool errfail = false;
     if (retval == 0) errfail = ida_test_error(m, w, M, S.ck, S.err_k, S.err_km1, lane);
     if (retval == 0 && !errfail) {
@@ -261,6 +266,7 @@ __device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const O
 __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     Ida& M = S.M;
+    __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const int N = m.N_tot;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
     const double tcur_stop = S.itstop == 0 ? S.tstop0 : S.tstop1;
@@ -659,6 +665,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             dI = warp_solve_impl(m, ro, w.Fa, alg_only, res, gI, lane);
         }
         // ------------------------------ POST: per-state glue --------------------------------------------
+        __syncwarp();
         if (do_eval) {
             if (S.state == ST_NLS) {
                 int retval;

@@ -16,24 +16,26 @@ from bench import synth_theta  # noqa: E402
 B1 = int(os.environ.get("PROF_B1", 65536))
 B4 = int(os.environ.get("PROF_B4", 8192))
 L = _lib.lib()
-TH = bool(int(os.environ.get("PROF_THERMAL", "0")))
-p = P.petlion("LCO", temperature=TH)
+FAM = os.environ.get("PROF_FAMILY", "thermal" if int(os.environ.get("PROF_THERMAL", "0")) else "iso")   # iso|thermal|sei|wsei
+TH = FAM == "thermal"
+p = P.petlion("LCO", temperature=TH, aging="SEI" if FAM in ("sei", "wsei") else False,
+              **(dict(N_p=20, N_s=20, N_n=20) if FAM == "wsei" else {}))
 h = p._h
 N = p.N.tot
 dev = torch.device("cuda", 0)
 f64 = dict(dtype=torch.float64, device=dev)
 th, _ = synth_theta(p, B1, 0)
 d_theta = torch.from_numpy(th).to(dev)
-d_soc0 = torch.full((B1,), 0.0 if TH else 1.0, **f64)
-CUR = 4.0 if TH else -1.0
+d_soc0 = torch.full((B1,), 1.0 if FAM == "iso" else 0.0, **f64)
+CUR = 4.0 if TH else (1.0 if FAM in ("sei", "wsei") else -1.0)
 T_MID = 150.0 if TH else 1800.0
 d_Y = torch.zeros(B1, N, **f64); d_YP = torch.zeros(B1, N, **f64)
 d_SOC = torch.zeros(B1, **f64); d_t = torch.zeros(B1, **f64); d_sum = torch.zeros(B1, 10, **f64)
 d_trn = torch.zeros(B1, dtype=torch.int32, device=dev)
 o = _lib.Opts(); L.plb_opts_defaults(h, C.byref(o))
 b = _lib.Bounds(); L.plb_bounds_defaults(h, C.byref(b))
-if TH:
-    b.V_max = 4.1
+if FAM != "iso":
+    b.V_max = 4.1 if TH else 4.2
 L.plb_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
 
