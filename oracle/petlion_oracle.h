@@ -12,8 +12,11 @@
  * Parity status: the reference cannot be executed here (no Julia; IDA and KLU are
  * un-vendored third-party C libraries).  The oracle is pinned against the reference's
  * own executed-notebook outputs (tests/golden/reference_goldens.json): I1C, V(0+) and
- * V[1:13] of the 2C charge, the c_e rows, and the IDA step ladders of three 1C
- * discharges.  See DESIGN.md "Oracle pinning".
+ * V[1:13] of the 2C charge, the c_e rows, the IDA step ladders of three 1C discharges, and
+ * (temperature = true) every printed digit and all 76 steps of the thermal 4C charge plus the
+ * first 28 steps of its dT = :hold continuation.  See DESIGN.md section 2.
+ * PARITY UNPINNED for the aging = :SEI rows (film, SOH, j_s: residuals.jl:260-297, 519-552): the
+ * reference ships no executed SEI example, so that part is a restatement without a known answer.
  */
 #ifndef PETLION_ORACLE_H
 #define PETLION_ORACLE_H
