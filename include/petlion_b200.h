@@ -24,8 +24,10 @@ typedef struct plb_handle_s *plb_handle;
 enum { PLB_CATHODE_LCO = 0, PLB_CATHODE_NMC = 1 };
 /* method_I / method_V / method_P (scalar_residual.jl:167-202); PLB_METHOD_DT = the `dT` input of thermal
  * models (constant spatially-averaged temperature: control row val - temperature_weighting(Y'[T]),
- * src/physics_equations/input_methods.jl:182-189; dT=:hold == dT=0) */
-enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2, PLB_METHOD_DT = 3 };
+ * src/physics_equations/input_methods.jl:182-189; dT=:hold == dT=0);
+ * PLB_METHOD_ETA_P = method_eta_p: the plating overpotential Phi_s.n[1] - Phi_e.n[1] held at a value
+ * (scalar_residual.jl:92, 199-203; input_methods.jl:108-143) */
+enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2, PLB_METHOD_DT = 3, PLB_METHOD_ETA_P = 4 };
 enum { PLB_MEM_HOST = 0, PLB_MEM_DEVICE = 1 };                /* where the caller's buffers live */
 
 /* petlion(cathode; N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, temperature, aging) -- src/params.jl:119-174 */

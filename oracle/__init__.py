@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
 CATHODE = {"LCO": 0, "NMC": 1}
-METHOD = {"I": 0, "V": 1, "P": 2, "dT": 3}
+METHOD = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4}
 
 
 def build(force=False):

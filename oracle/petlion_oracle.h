@@ -54,7 +54,8 @@ enum { ORC_CATHODE_LCO = 0, ORC_CATHODE_NMC = 1 };
  * residual of input_methods.jl:182-189 (control row  val - temperature_weighting(Y'[T])).
  * ORC_METHOD_DT_ALG is internal: the same row inside newtons_method!, where the reference substitutes
  * Y'_diff -> rhs_diff(Y) (scalar_residual.jl:347-363). */
-enum { ORC_METHOD_I = 0, ORC_METHOD_V = 1, ORC_METHOD_P = 2, ORC_METHOD_DT = 3, ORC_METHOD_DT_ALG = 4 };
+/* ORC_METHOD_ETA: method_eta_p, the plating overpotential Phi_s.n[1] - Phi_e.n[1] (scalar_residual.jl:92, 199-203) */
+enum { ORC_METHOD_I = 0, ORC_METHOD_V = 1, ORC_METHOD_P = 2, ORC_METHOD_DT = 3, ORC_METHOD_ETA = 4, ORC_METHOD_DT_ALG = 5 };
 
 /* model structure: petlion(cathode; N_p, ..., temperature, aging) -- src/params.jl:119-174 */
 typedef struct {

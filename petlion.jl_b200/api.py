@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 
 CATHODES = {"LCO": 0, "NMC": 1}
-METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3}
+METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4}
 EXIT_REASONS = {  # src/checks.jl
     -1: "running", 0: "Final time reached", 1: "Below min. voltage", 2: "Above max. voltage",
     3: "Below min. SOC", 4: "Above max. SOC", 5: "Above max. temperature", 6: "Above max. c_s_n",
@@ -251,9 +251,9 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
             # check_input_arguments, checks.jl:278-325
             raise TypeError(f"ERROR\n--------\n Invalid keyword argument: {k}")
     if len(method_kw) == 0:
-        raise TypeError("ERROR\n--------\n No inputs are selected, choose one from: (I, V, P, dT)")
+        raise TypeError("ERROR\n--------\n No inputs are selected, choose one from: (I, V, P, dT, η_p)")
     if len(method_kw) > 1:
-        raise TypeError("ERROR\n--------\n Cannot select more than one input from: (I, V, P, dT)")
+        raise TypeError("ERROR\n--------\n Cannot select more than one input from: (I, V, P, dT, η_p)")
     (name, inp), = method_kw.items()
     new_run = sol is None or sol.isempty()
     kind, value, vals = 0, 0.0, None

@@ -20,8 +20,9 @@ enum { CHEM_LCO = 0, CHEM_NMC = 1 };
 // control row (scalar_residual.jl:167-202): applied current / voltage / power, and the constant-temperature
 // mode dT (input_methods.jl:182-189): val - temperature_weighting(Y'[T]).  METHOD_DT_ALG is the same row as
 // newtons_method! sees it, with Y'_T replaced by the right-hand side of the T rows (scalar_residual.jl:347-363).
-enum { METHOD_I = 0, METHOD_V = 1, METHOD_P = 2, METHOD_DT = 3, METHOD_DT_ALG = 4 };
-constexpr int N_METHODS = 4;
+// METHOD_ETA: method_eta_p, the plating overpotential Phi_s.n[1] - Phi_e.n[1] held at a value (scalar_residual.jl:92, 199-203)
+enum { METHOD_I = 0, METHOD_V = 1, METHOD_P = 2, METHOD_DT = 3, METHOD_ETA = 4, METHOD_DT_ALG = 5 };
+constexpr int N_METHODS = 5;
 
 // canonical parameter fields (ASCII names of the reference keys); the thermal block is only part of a
 // theta row when temperature = true

@@ -251,7 +251,9 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         const double a = s == 1 ? 0.0 : 3 * eps_act / Rp;                               // build_a!
         const double sig = (s == 0 ? th[TF_sigma_p] : th[TF_sigma_n]) * eps_act;       // build_sigma_eff
         const double Dl = s == 0 ? th[TF_D_p] : (s == 1 ? th[TF_D_s] : th[TF_D_n]);
-        const double pb = pow(por, brg);
+        // por^brugg: the shipped parameter sets use brugg = 4 (LCO) and 1.5 (NMC); a general pow() is ~150
+        // instructions that every evaluation of K1 would pay
+        const double pb = brg == 4.0 ? (por * por) * (por * por) : (brg == 1.5 ? por * sqrt(por) : pow(por, brg));
         const double T = th[TF_T0];
         const bool Tref = (T == kTref);   // temperature_switch, custom_functions.jl:1
         double Ds = s == 0 ? th[TF_D_sp] : th[TF_D_sn];
@@ -445,6 +447,8 @@ struct CtrlRow {
     // dT control (thermal variant): coefficients of this lane's Y'[T] / Y'[collector T] in the row
     // (-temperature_weighting weights); zero for the other methods
     double gTn, gTx;
+    // eta_p control: +g_eta on Phi_s and -g_eta on Phi_e of the first anode node; zero for the other methods
+    double g_eta;
 };
 
 template <int CHEM, bool WITH_JAC>
@@ -543,13 +547,18 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         const double th = cs_s * C.sec[SC_inv_cmax][s];
         double U, dU, dUdT = 0.0, ddUdT = 0.0;
         if (CHEM == CHEM_LCO) {
-            if (ro.sec == 0) laws::OCV_LCO(th, U, dU, dUdT, ddUdT);
-            else {
-                // sqrt_ReLU branches (custom_functions.jl:143, 210): physical range th > 1e-4
-                const double sq = sqrt(fmax(th, 1e-4));
-                laws::OCV_LiC6(th, sq, U, dU, dUdT, ddUdT);
+            // sqrt_ReLU branches (custom_functions.jl:143, 210): physical range th > 1e-4
+            const double sq = sqrt(fmax(th, 1e-4));
+            if (TH || C.g[GC_dUdT_on] != 0.0) {
+                if (ro.sec == 0) laws::OCV_LCO(th, U, dU, dUdT, ddUdT);
+                else laws::OCV_LiC6(th, sq, U, dU, dUdT, ddUdT);
+                U += dUdT * (T - kTref); dU += ddUdT * (T - kTref);
+            } else {
+                // isothermal run at T == T_ref: the entropic term is switched off (temperature_switch,
+                // custom_functions.jl:1), skip its two rational polynomials
+                if (ro.sec == 0) laws::OCV_LCO_U(th, U, dU);
+                else laws::OCV_LiC6_U(th, sq, U, dU);
             }
-            if (C.g[GC_dUdT_on] != 0.0) { U += dUdT * (T - kTref); dU += ddUdT * (T - kTref); }
         } else {
             if (ro.sec == 0) laws::OCV_NMC(th, U, dU);
             else laws::OCV_LiC6_NMC(th, U, dU);
@@ -726,8 +735,12 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     {
         const double ps0 = shfl_from(y.ps, 0), psN = shfl_from(y.ps, m.Nx - 1);
         const double V = ps0 - psN;
-        ctrl.gTn = 0.0; ctrl.gTx = 0.0;
-        if (method == METHOD_I) { ctrl.res = Iapp - value; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; }
+        ctrl.gTn = 0.0; ctrl.gTx = 0.0; ctrl.g_eta = 0.0;
+        if (method == METHOD_ETA) {
+            const int ln = m.Np + m.Ns;                                  // first anode node
+            ctrl.res = (shfl_from(y.ps, ln) - shfl_from(y.pe, ln)) - value;   // calc_eta_plating, scalar_residual.jl:92
+            ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 0.0; ctrl.g_eta = 1.0;
+        } else if (method == METHOD_I) { ctrl.res = Iapp - value; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; }
 #if PLB_TH
         else if (method == METHOD_DT || method == METHOD_DT_ALG) {
             // run_residual of the constant-temperature mode: val - temperature_weighting(Y'[T])
@@ -815,9 +828,9 @@ struct WarpFactor {
     double Mi[9][LW], cpl[6][LW], sohc[LW];
     double cjv, pad2;
 #endif
-    double schur_inv;          // 1/(g_I - g_ps0*z_ps[0] - g_psN*z_ps[N-1])
+    double schur_inv;          // 1/(g_I - g_ps0*z_ps[0] - g_psN*z_ps[N-1] - g_eta*(z_ps - z_pe)[first anode node])
     double g_ps0, g_psN;
-    double pad;
+    double g_eta;
 };
 
 // 3x3 inverse by the adjugate (forward error ~ cond * eps, invariant under row/column scaling)
@@ -1100,10 +1113,12 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     thomas_sweeps(m.Nx, ch, Wm, Pm, Di, zf, u3);
     Fa.z[0][lane] = u3[0]; Fa.z[1][lane] = u3[1]; Fa.z[2][lane] = u3[2];
     const double z0 = shfl_from(u3[2], 0), zN = shfl_from(u3[2], m.Nx - 1);
+    const double ze = shfl_from(u3[2] - u3[1], m.Np + m.Ns);
     if (lane == 0) {
-        Fa.schur_inv = 1.0 / (ctrl.g_I - ctrl.g_ps0 * z0 - ctrl.g_psN * zN);
+        Fa.schur_inv = 1.0 / (ctrl.g_I - ctrl.g_ps0 * z0 - ctrl.g_psN * zN - ctrl.g_eta * ze);
         Fa.g_ps0 = ctrl.g_ps0;
         Fa.g_psN = ctrl.g_psN;
+        Fa.g_eta = ctrl.g_eta;
     }
     grp_sync();
 }
@@ -1156,7 +1171,9 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     thomas_sweeps(m.Nx, ch, Wm, Pm, Di, rf, u3);
     // border
     const double x0 = shfl_from(u3[2], 0), xN = shfl_from(u3[2], m.Nx - 1);
-    const double dI = (gI - Fa.g_ps0 * x0 - Fa.g_psN * xN) * Fa.schur_inv;
+    double gx = Fa.g_ps0 * x0 + Fa.g_psN * xN;
+    if (Fa.g_eta != 0.0) gx += Fa.g_eta * shfl_from(u3[2] - u3[1], m.Np + m.Ns);      // eta_p control (uniform branch)
+    const double dI = (gI - gx) * Fa.schur_inv;
     u3[0] -= Fa.z[0][lane] * dI; u3[1] -= Fa.z[1][lane] * dI; u3[2] -= Fa.z[2][lane] * dI;
     // back-substitute j (and j_s, film) and the particle
 #if PLB_SEI
@@ -1217,6 +1234,7 @@ struct WarpFactor {
     double gT[32], gX[32];     // dT control: border-row entries on this lane's T / collector T
     double schur_inv, g_ps0, g_psN;
     double mode;               // border row: 0 (Phi_s ends + I), 1 dT in the DAE, 2 dT inside newtons_method!
+    double g_eta, pad3;        // eta_p control
 };
 
 // border row times a block solution.  mode 1: the row has entries on every temperature; mode 2 (algebraic
@@ -1227,6 +1245,7 @@ __device__ __forceinline__ double border_dot(const ModelDesc& m, const WarpFacto
                                              double ux, double dj, int lane) {
     const double x0 = shfl_from(u4[2], 0), xN = shfl_from(u4[2], m.Nx - 1);
     double g = Fa.g_ps0 * x0 + Fa.g_psN * xN;
+    if (Fa.g_eta != 0.0) g += Fa.g_eta * shfl_from(u4[2] - u4[1], m.Np + m.Ns);
     if (mode == 1) g += warp_sum(Fa.gT[lane] * u4[3] + Fa.gX[lane] * ux);
     if (mode == 2) {
         double a = Fa.pd[0][lane] * dj;
@@ -1624,7 +1643,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         for (int k = 0; k < 4; k++) Fa.pd[6 + k][lane] = ctrl.gTn * J.T_ps[k];
         Fa.wT[0][lane] = ctrl.gTn * J.T_ps[4];
     }
-    if (lane == 0) { Fa.g_ps0 = ctrl.g_ps0; Fa.g_psN = ctrl.g_psN; Fa.mode = (double)mode; }
+    if (lane == 0) { Fa.g_ps0 = ctrl.g_ps0; Fa.g_psN = ctrl.g_psN; Fa.mode = (double)mode; Fa.g_eta = ctrl.g_eta; }
     __syncwarp();
     // the border column has no entry in the j rows: dj of the column solution is q . z
     const double djz = ro.elec ? q[0] * u4[0] + q[1] * u4[1] + q[2] * u4[2] + q[3] * u4[3] : 0.0;

@@ -112,7 +112,8 @@ struct plb_handle_s {
     // CSC patterns per method
     std::vector<int> colptr[N_METHODS], rowval[N_METHODS];
     int* d_src[N_METHODS] = {};
-    int n_methods = 3;                   // I, V, P; thermal models add dT
+    bool has_dT = false;                 // methods: I, V, P, eta_p everywhere; dT only in thermal models
+    bool method_ok(int method) const { return method >= 0 && method < N_METHODS && (method != METHOD_DT || has_dT); }
     int* d_counter = nullptr;
     double* d_gws = nullptr;             // global workspace of the persistent warps
     int sim_grid = 0;
@@ -132,7 +133,8 @@ const char* plb_last_error(void) { return g_err.c_str(); }
 static int build_patterns(plb_handle_s* h) {
     const ModelDesc& m = h->m;
     const int n_slots = h->vi.n_slots;
-    for (int method = 0; method < h->n_methods; method++) {
+    for (int method = 0; method < N_METHODS; method++) {
+        if (!h->method_ok(method)) continue;
         std::vector<std::pair<int, int>> ent;   // (col, row)
         for (int lane = 0; lane < h->vi.lanes; lane++)
             for (int s = 0; s < n_slots; s++) {
@@ -191,7 +193,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     plb_handle_s* h = new plb_handle_s();
     h->desc = *d;
     h->v = d->temperature ? &V_TH : (Nx_ > 32 ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
-    h->n_methods = d->temperature ? 4 : 3;
+    h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
     ModelDesc& m = h->m;
     memset(&m, 0, sizeof m);
@@ -254,7 +256,7 @@ int plb_set_stream(plb_handle h, void* s) { h->stream = (cudaStream_t)s; return 
 int plb_nstates(plb_handle h) { return h->m.N_tot; }
 int plb_ndiff(plb_handle h) { return h->m.N_diff; }
 int plb_ntheta(plb_handle h) { return h->m.ntheta; }
-int plb_jac_nnz(plb_handle h, int method) { return (method < 0 || method >= h->n_methods) ? -1 : (int)h->rowval[method].size(); }
+int plb_jac_nnz(plb_handle h, int method) { return (!h->method_ok(method)) ? -1 : (int)h->rowval[method].size(); }
 long long plb_launch_count(plb_handle h) { return h->launches; }
 float plb_last_kernel_ms(plb_handle h) { return h->last_ms; }
 
@@ -301,7 +303,7 @@ int plb_calc_I1C(plb_handle h, int B, const double* theta, double* I1C) {
     return 0;
 }
 int plb_jac_pattern(plb_handle h, int method, int* colptr, int* rowval, int one_based) {
-    if (method < 0 || method >= h->n_methods) return fail("plb_jac_pattern: bad method");
+    if (!h->method_ok(method)) return fail("plb_jac_pattern: bad method");
     const int o = one_based ? 1 : 0;
     for (size_t i = 0; i < h->colptr[method].size(); i++) colptr[i] = h->colptr[method][i] + o;
     for (size_t i = 0; i < h->rowval[method].size(); i++) rowval[i] = h->rowval[method][i] + o;
@@ -392,7 +394,7 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
                const double* theta, const plb_run* run, const double* values, double* res,
                double* nzval, int mem) {
     if (B <= 0) return 0;
-    if (!run || run->method < 0 || run->method >= h->n_methods) return fail("plb_resjac: bad run (dT needs temperature=true)");
+    if (!run || !h->method_ok(run->method)) return fail("plb_resjac: bad run (dT needs temperature=true)");
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     const int nnz = (int)h->rowval[run->method].size();
@@ -451,7 +453,7 @@ int plb_linear_solve(plb_handle h, int B, const double* Y, const double* YP, con
                      const double* theta, const plb_run* run, const double* values, const double* rhs,
                      double* x, int* status, int mem) {
     if (B <= 0) return 0;
-    if (!run || run->method < 0 || run->method >= h->n_methods) return fail("plb_linear_solve: bad run");
+    if (!run || !h->method_ok(run->method)) return fail("plb_linear_solve: bad run");
     if (!Y || !YP || !theta || !rhs || !x) return fail("plb_linear_solve: null required argument");
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
@@ -484,12 +486,12 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
     if (B <= 0) return 0;
     if (!run || !opts || !bounds || !theta || !sY || !sSOC || !st || !summary)
         return fail("plb_simulate: null required argument");
-    if (run->method < 0 || run->method >= h->n_methods)
+    if (!h->method_ok(run->method))
         return fail(run->method == PLB_METHOD_DT ? "plb_simulate: Temperature must be enabled when using `dT`."   // input_methods.jl:183
                                                  : "plb_simulate: bad method");
     if (run->input_kind != PLB_INPUT_VALUE && run->new_run && run->input_kind == PLB_INPUT_HOLD)
         return fail("plb_simulate: Cannot use `:hold` without a previous simulation.");   // checks.jl:385
-    if (run->input_kind == PLB_INPUT_REST && (run->method == PLB_METHOD_V || run->method == PLB_METHOD_DT))
+    if (run->input_kind == PLB_INPUT_REST && run->method != PLB_METHOD_I && run->method != PLB_METHOD_P)
         return fail("plb_simulate: Unsupported input symbol.");
     static_assert(sizeof(plb_summary) == sizeof(Summary), "summary layout");
     const ModelDesc& m = h->m;

@@ -478,6 +478,12 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
             // initial_current! (input_methods.jl:173-176): the previous current, else 1
             if (a.input_kind == 1) S.rc.value = 0.0;
             Ig = a.new_run ? 1.0 : I_prev_state;
+        } else if (S.rc.method == METHOD_ETA) {
+            // initial_current! for method_eta_p (input_methods.jl:118-143)
+            const int ln = m.Np + m.Ns;
+            if (a.input_kind == 1) { S.rc.value = Y0[m.off_ps + m.Np] - Y0[m.off_pe + ln]; Ig = I_prev_state; }
+            else if (!a.new_run) Ig = I_prev_state;
+            else Ig = S.rc.value > V0 ? 1.0 : -1.0;
         } else if (a.input_kind == 1) {
             if (S.rc.method == METHOD_I) { S.rc.value = I_prev_state; Ig = I_prev_state; }
             else if (S.rc.method == METHOD_V) { S.rc.value = V0; Ig = V0; }   // sic: input_methods.jl:58
@@ -627,7 +633,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
 #endif
         LaneJac J;
         CtrlRow ctrl;
-        ctrl.res = 0.0; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; ctrl.gTn = 0.0; ctrl.gTx = 0.0;
+        ctrl.res = 0.0; ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 1.0; ctrl.gTn = 0.0; ctrl.gTx = 0.0; ctrl.g_eta = 0.0;
         if (do_eval) {
             // each warp picks the variant from its OWN state only, so a system's arithmetic (and therefore
             // its bits) never depends on which other systems share the CTA

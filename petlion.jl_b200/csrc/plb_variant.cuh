@@ -44,6 +44,7 @@ enum JacSlot {
 #endif
     JS_CTRL_PS0 = JS_CS0 + NR * NR, JS_CTRL_PSN, JS_CTRL_I,
     JS_CTRL_T, JS_CTRL_TX,       // dT control row: entries on this lane's T / collector T (thermal variant)
+    JS_CTRL_EPS, JS_CTRL_EPE,    // eta_p control row: Phi_s / Phi_e of the first anode node
     JS_COUNT
 };
 
@@ -51,7 +52,7 @@ enum JacSlot {
 #define PLB_K1_CTAS (PLB_WIDE ? 1 : (PLB_TH ? 2 : 3))
 #endif
 constexpr int K1_WARPS = WIDE ? 2 : 4;            // systems (lane groups) per CTA
-constexpr int K1_NSTAGE = JS_CS0 + 5;   // lane-computed slots: 0..JS_CS0-1, then the five control-row slots
+constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
 constexpr int K1_SRC_MAX = WIDE ? 4864 : (TH ? 3072 : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
             w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
             w.S[k1_stage_slot(JS_CTRL_T)][lane] = g * ctrl.gTn;
             w.S[k1_stage_slot(JS_CTRL_TX)][lane] = g * ctrl.gTx;
+            w.S[k1_stage_slot(JS_CTRL_EPS)][lane] = ctrl.g_eta;
+            w.S[k1_stage_slot(JS_CTRL_EPE)][lane] = -ctrl.g_eta;
             grp_sync();
             const double* tab = &w.S[0][0];
             double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
@@ -249,6 +252,8 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         case JS_CTRL_PS0: row = I; col = m.off_ps; return lane == 0 && (method == METHOD_V || method == METHOD_P);
         case JS_CTRL_PSN: row = I; col = m.off_ps + m.Ne - 1; return lane == Nx - 1 && (method == METHOD_V || method == METHOD_P);
         case JS_CTRL_I: row = I; col = I; return lane == 0 && (method == METHOD_I || method == METHOD_P);
+        case JS_CTRL_EPS: row = I; col = r_ps; return method == METHOD_ETA && x == Np + Ns;
+        case JS_CTRL_EPE: row = I; col = r_pe; return method == METHOD_ETA && x == Np + Ns;
         default: break;
     }
     if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {

@@ -301,3 +301,47 @@ def test_gitt_protocol_nmc(P):
     assert len(sol.results) == 6
     # global time is continuous across runs
     assert np.all(np.diff(sol.t[0, :sol.n_points[0]]) >= 0)
+
+
+def test_eta_p_control(P, lco):
+    """method_eta_p (scalar_residual.jl:92, 199-203; input_methods.jl:108-143): hold the plating overpotential
+    Phi_s.n[1] - Phi_e.n[1]; control row +1/-1 on two interior unknowns, zero corner, through the border."""
+    m = O.make_model("LCO"); L = O.layout(m)
+    cp, rv = O.jac_pattern(m, "η_p")
+    cp2, rv2 = lco.jac_pattern("η_p")
+    assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+    B = 12
+    tho = util.oracle_theta_batch(B, first=700)
+    th = util.product_theta_from_oracle(lco, tho)
+    util.set_theta_batch(lco, th)
+    b = O.default_bounds("LCO", V_max=4.2)
+    # 2C charge for 600 s, then hold the overpotential reached (eta_p = :hold) for another 600 s
+    sol = P.simulate(lco, 600.0, I=2, SOC=0.2, V_max=4.2)
+    r1 = O.simulate_batch(m, tho, O.make_run("I", 2.0, tf=600.0), O.default_opts(), b, SOC0=0.2, n_save_max=512, nthreads=8)
+    _compare_runs(sol, r1, min_identical=0.9)
+    P.simulate_(sol, lco, 600.0, eta_p="hold", V_max=4.2)
+    r2 = O.simulate_batch(m, tho, O.make_run("η_p", 0.0, tf=600.0, input_kind="hold", new_run=False), O.default_opts(), b,
+                          state=r1["state"], n_save_max=512, nthreads=8)
+    s2 = sol.results[-1].summary
+    same = (s2["n_steps"] == r2["n_steps"]) & (s2["flag"] == r2["flag"])
+    assert np.mean(same) >= 0.8, (s2["n_steps"], r2["n_steps"])
+    np.testing.assert_allclose(s2["V_end"][same], r2["V_end"][same], rtol=1e-6)
+    np.testing.assert_allclose(s2["I_end"][same], r2["I_end"][same], rtol=1e-6)
+    eta1 = r1["state"]["Y"][:, L.phi_s + 10] - r1["state"]["Y"][:, L.phi_e + 20]
+    eta2 = sol.Y[:, L.phi_s + 10] - sol.Y[:, L.phi_e + 20]
+    np.testing.assert_allclose(eta2, eta1, rtol=1e-6)                  # held
+    # operator level: residual + Jacobian with the eta_p row, and a fresh run with a number
+    Y, YP = r1["state"]["Y"], r1["state"]["YP"]
+    res, nz = lco.resjac(Y, YP, 0.3, method="η_p", value=0.05, theta=th)
+    for s in range(B):
+        run = O.make_run("η_p", 0.05)
+        np.testing.assert_allclose(res[s][L.I], O.residual(m, tho[s], run, 0.0, Y[s], YP[s])[L.I], rtol=1e-12)
+        j_ref = O.jacobian(m, tho[s], run, 0.0, Y[s], YP[s], 0.3)
+        rowmax = np.zeros(301); np.maximum.at(rowmax, rv, np.abs(j_ref))
+        assert np.max(np.abs(nz[s] - j_ref) / rowmax[rv]) < 1e-9
+    sol3 = P.simulate(lco, 300.0, eta_p=0.08, SOC=0.3, V_max=4.2)
+    r3 = O.simulate_batch(m, tho, O.make_run("η_p", 0.08, tf=300.0), O.default_opts(), b, SOC0=0.3, n_save_max=512, nthreads=8)
+    s3 = sol3.results[-1].summary
+    same = (s3["n_steps"] == r3["n_steps"]) & (s3["flag"] == r3["flag"])
+    assert np.mean(same) >= 0.8
+    np.testing.assert_allclose(s3["I_end"][same], r3["I_end"][same], rtol=1e-6)
