@@ -480,25 +480,29 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     double TRn = T, dKTR = 0.0;
     if (TH) { TRn = shfl_dn(T); dKTR = shfl_dn(dKT); }
     if (has_face) {
+        // harmonic means (numerical_tools.jl:106-191); one reciprocal per mean, shared with its derivatives
         const double denK = b * KR + (1.0 - b) * K;
-        const double Khat = K * KR / denK;                          // interpolate_electrolyte_grid
+        const double rK = __drcp_rn(denK);
+        const double Khat = K * KR * rK;                            // interpolate_electrolyte_grid
         const double denD = b * DR + (1.0 - b) * D;
-        const double Dhat = D * DR / denD;
+        const double rD = __drcp_rn(denD);
+        const double Dhat = D * DR * rD;
         const double denc = b * ceR + (1.0 - b) * ce;
-        const double cbar = ce * ceR / denc;                        // interpolate_electrolyte_concentration
+        const double rc = __drcp_rn(denc);
+        const double cbar = ce * ceR * rc;                          // interpolate_electrolyte_concentration
         const double denT = b * TRn + (1.0 - b) * T;
-        const double Tbar = T * TRn / denT;                         // interpolate_temperature
+        const double Tbar = TH ? T * TRn * __drcp_rn(denT) : T;     // interpolate_temperature (uniform T: the mean is T)
         const double dc = (ceR - ce) * dinv;                        // ..._concetration_fluxes
-        const double G = Khat * Tbar * dc / cbar;                   // prod_tot, residuals.jl:631-635
+        const double icb = __drcp_rn(cbar);
+        const double G = Khat * Tbar * dc * icb;                    // prod_tot, residuals.jl:631-635
         wK = Khat * dinv;
         Q = wK * (peR - y.pe) - C.g[GC_Kc] * G;
         Nf = Dhat * dinv * (ceR - ce);
         if (WITH_JAC) {
-            const double iK2 = 1.0 / (denK * denK), iD2 = 1.0 / (denD * denD), ic2 = 1.0 / (denc * denc);
+            const double iK2 = rK * rK, iD2 = rD * rD, ic2 = rc * rc;
             const double dKh_cL = b * KR * KR * iK2 * dK, dKh_cR = (1.0 - b) * K * K * iK2 * dKR;
             const double dDh_cL = b * DR * DR * iD2 * dD, dDh_cR = (1.0 - b) * D * D * iD2 * dDR;
             const double dcb_cL = b * ceR * ceR * ic2, dcb_cR = (1.0 - b) * ce * ce * ic2;
-            const double icb = 1.0 / cbar;
             const double dG_cL = Tbar * icb * (dKh_cL * dc - Khat * dinv - Khat * dc * dcb_cL * icb);
             const double dG_cR = Tbar * icb * (dKh_cR * dc + Khat * dinv - Khat * dc * dcb_cR * icb);
             dQ_cL = dKh_cL * dinv * (peR - y.pe) - C.g[GC_Kc] * dG_cL;
@@ -570,12 +574,13 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         const double sq = arg > 0.0 ? sqrt(arg) : 0.0;                       // sqrt_ReLU
         const double xx = xco * eta;
         const double em = expm1(xx);
-        const double sh = 0.5 * (em + em / (em + 1.0));                      // sinh(xx)
+        const double rem = __drcp_rn(em + 1.0);                              // exp(-xx)
+        const double sh = 0.5 * (em + em * rem);                             // sinh(xx)
         const double k2 = k2x;
         jcalc = k2 * sq * sh;
         if (TH) { eta_h = eta; dUdT_h = dUdT; ddUdT_h = ddUdT; dUtot_h = dU; }
         if (WITH_JAC) {
-            const double ch = sh + 1.0 / (em + 1.0);                         // cosh = sinh + exp(-x)
+            const double ch = sh + rem;                                      // cosh = sinh + exp(-x)
             const double isq = arg > 0.0 ? 0.5 / sq : 0.0;
             dj_eta = k2 * sq * ch * xco;
             dj_ce = k2 * sh * isq * cs_s * (cmax - cs_s);

@@ -51,7 +51,7 @@ def _load_generated():
         body = src[src.index("{", i) + 1: src.index("\n}", i)]
         code = "\n".join(ln.strip().replace("const double ", "") for ln in body.strip().split("\n"))
         env = dict(kw)
-        exec(code, {"exp": math.exp, "atan": math.atan, "sqrt": math.sqrt}, env)
+        exec(code, {"exp": math.exp, "atan": math.atan, "sqrt": math.sqrt, "__drcp_rn": lambda x: 1.0 / x}, env)
         return env
     return run
 
