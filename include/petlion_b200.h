@@ -79,7 +79,7 @@ typedef struct {
     int n_res, n_jac;  /* residual / Jacobian evaluations */
     int n_netf, n_ncfn;/* error-test / Newton-convergence failures */
     int n_newton_init; /* iterations of the algebraic initialisation */
-    int reserved;
+    int n_reinit;      /* re-initialisations at input discontinuities (checks.jl:341-364; table runs) */
 } plb_summary;
 
 #define PLB_FAIL_NEWTON_INIT (-1) /* "Could not initialize DAE" model_evaluation.jl:456 */
@@ -154,6 +154,34 @@ int plb_simulate(plb_handle h, int B, const double *theta, const plb_run *run,
                  double *state_t, plb_summary *summary, int n_save_max, double *traj_t,
                  double *traj_V, double *traj_I, double *traj_SOC, double *traj_T, int *traj_n,
                  int mem);
+
+/* run_function{method,func} (src/structures.jl:55-63; examples/variable_input_functions.ipynb): a
+ * time-varying I(t) / V(t) / P(t) / eta_p(t).  A Julia closure cannot cross the C ABI, so the function is
+ * a piecewise-linear table of the run's LOCAL time ("all times start at t = 0, even if the simulation
+ * follows another one"): knots t[n] non-decreasing, values v[n]; a repeated knot time is a jump, the
+ * function being right-continuous there (`t < 100 ? 1 : 0.5` is t = {0,100,100}, v = {1,1,0.5});
+ * constant outside the table.  tdiscon = opts.tdiscon (src/structures.jl:279): the integrator is made to
+ * stop at tdiscon - reltol/2 (model_evaluation.jl:295-297).  Table and tdiscon are HOST arrays. */
+typedef struct {
+    int n;
+    const double *t, *v;
+    int n_tdiscon;
+    const double *tdiscon;   /* ascending; may be NULL when n_tdiscon == 0 */
+} plb_input_table;
+
+/* simulate(p, tf; I = I_fun, tdiscon = [...]) with I_fun given by `table`.  Same arguments as plb_simulate;
+ * run->input_kind must be PLB_INPUT_VALUE, run->value is ignored and `scale[B]` (optional, `mem` decides
+ * host/device) multiplies the table per system: value_b(t) = scale[b] * table(t).
+ * Mirrors scalar_residual! for run_function (scalar_residual.jl:169-170: the function is evaluated at
+ * every residual evaluation), initial_current! (input_methods.jl:27-29, 64-74, 104-107), the stop list of
+ * postfix_integrator! (model_evaluation.jl:288-310), check_solve for run_function (checks.jl:251-268: a
+ * failed step is not an error) and check_reinitialization! (checks.jl:341-364). */
+int plb_simulate_table(plb_handle h, int B, const double *theta, const plb_run *run,
+                       const plb_input_table *table, const double *scale, const plb_opts *opts,
+                       const plb_bounds *bounds, const double *soc0, double *state_Y,
+                       double *state_YP, double *state_SOC, double *state_t, plb_summary *summary,
+                       int n_save_max, double *traj_t, double *traj_V, double *traj_I,
+                       double *traj_SOC, double *traj_T, int *traj_n, int mem);
 
 /* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI, 3 wide, 4 wide SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared

@@ -39,7 +39,10 @@ class Layout(C.Structure):
 
 class Run(C.Structure):
     _fields_ = [("method", C.c_int), ("value", C.c_double), ("tf", C.c_double),
-                ("input_kind", C.c_int), ("new_run", C.c_int), ("t0", C.c_double)]
+                ("input_kind", C.c_int), ("new_run", C.c_int), ("t0", C.c_double),
+                ("tab_n", C.c_int), ("tab_t", C.POINTER(C.c_double)), ("tab_v", C.POINTER(C.c_double)),
+                ("scale", C.c_double), ("n_tdiscon", C.c_int), ("tdiscon", C.POINTER(C.c_double)),
+                ("last_value", C.POINTER(C.c_double))]
 
 
 class Opts(C.Structure):
@@ -59,7 +62,7 @@ class Summary(C.Structure):
     _fields_ = [("t_end", C.c_double), ("V_end", C.c_double), ("I_end", C.c_double),
                 ("SOC_end", C.c_double), ("T_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int),
                 ("n_res", C.c_int), ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int),
-                ("n_newton_init", C.c_int)]
+                ("n_newton_init", C.c_int), ("n_reinit", C.c_int)]
 
 
 _lib = None
@@ -138,8 +141,29 @@ def default_bounds(cathode="LCO", **kw):
 INPUT = {"value": 0, "hold": 1, "rest": 2}
 
 
-def make_run(method="I", value=-1.0, tf=1e6, input_kind="value", new_run=True, t0=0.0):
-    return Run(METHOD[method], float(value), float(tf), INPUT[input_kind], int(new_run), float(t0))
+def make_run(method="I", value=-1.0, tf=1e6, input_kind="value", new_run=True, t0=0.0, table=None,
+             tdiscon=(), scale=1.0):
+    """table = (t_knots, v_knots): a run_function restricted to a piecewise-linear table (see orc_run)"""
+    r = Run(METHOD[method], float(value), float(tf), INPUT[input_kind], int(new_run), float(t0))
+    r.scale = float(scale)
+    if table is not None:
+        tt = np.ascontiguousarray(table[0], dtype=np.float64)
+        vv = np.ascontiguousarray(table[1], dtype=np.float64)
+        td = np.ascontiguousarray(sorted(tdiscon), dtype=np.float64)
+        assert tt.ndim == 1 and tt.shape == vv.shape and tt.size >= 1 and np.all(np.diff(tt) >= 0)
+        r._keep = (tt, vv, td)            # the struct only holds pointers
+        r.tab_n = tt.size; r.tab_t = _p(tt); r.tab_v = _p(vv)
+        r.n_tdiscon = td.size; r.tdiscon = _p(td) if td.size else None
+    return r
+
+
+def table_eval(table, t):
+    tt = np.ascontiguousarray(table[0], dtype=np.float64)
+    vv = np.ascontiguousarray(table[1], dtype=np.float64)
+    L = lib()
+    L.orc_table_eval.restype = C.c_double
+    L.orc_table_eval.argtypes = [C.c_int, _dp, _dp, C.c_double]
+    return L.orc_table_eval(tt.size, _p(tt), _p(vv), float(t))
 
 
 def calc_I1C(theta):

@@ -81,6 +81,18 @@ typedef struct {
     int input_kind; /* 0 number; 1 :hold (value from previous state); 2 :rest (checks.jl:12,388) */
     int new_run;  /* 1: fresh simulate(); 0: simulate!() continuation (adds tstop 1.0) */
     double t0;    /* global time offset (run.t0) */
+    /* run_function{method,func} (structures.jl:55) with func(t) restricted to a piecewise-linear table:
+     * knots tab_t[tab_n] non-decreasing in the run's LOCAL time (variable_input_functions.ipynb: "all times
+     * start at t = 0"), values tab_v[tab_n]; a repeated knot time is a jump and the function is
+     * right-continuous there (`t < 100 ? 1 : 0.5` == knots (0,1),(100,1),(100,0.5)); constant outside the
+     * table.  value(t) = scale * table(t).  tab_n == 0: run_constant.  tdiscon = opts.tdiscon
+     * (structures.jl:279), ascending.  last_value mirrors run.value[] (scalar_residual.jl:170). */
+    int tab_n;
+    const double *tab_t, *tab_v;
+    double scale;
+    int n_tdiscon;
+    const double *tdiscon;
+    double *last_value;
 } orc_run;
 
 /* options_simulation: src/structures.jl:266-285, defaults src/params.jl:256-280 */
@@ -108,6 +120,7 @@ typedef struct {
     int flag;      /* 0..11 as checks.jl ; <0 hard failure */
     int n_steps;   /* accepted IDA steps (= saved points - 1) */
     int n_res, n_jac, n_netf, n_ncfn, n_newton_init;
+    int n_reinit;  /* re-initialisations at input discontinuities (checks.jl:341-364) */
 } orc_summary;
 
 /* negative (hard-failure) flags */
@@ -159,6 +172,9 @@ int orc_simulate_batch(const orc_model *m, int B, const double *theta, const orc
                        int *traj_n, int nthreads);
 
 /* counter-based RNG shared by CPU and GPU sides: u in [0,1) */
+/* piecewise-linear table of a run_function (see orc_run) */
+double orc_table_eval(int n, const double *tt, const double *vv, double t);
+
 double orc_rng_u01(unsigned long long seed, unsigned long long system_id, unsigned param_id);
 
 #ifdef __cplusplus

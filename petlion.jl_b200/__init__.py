@@ -6,11 +6,11 @@ constitutive laws) and the host-side mirror of the reference interface (api.py).
 """
 from . import _lib
 from ._lib import build
-from .api import EXIT_REASONS, Model, Solution, petlion, simulate, simulate_
+from .api import EXIT_REASONS, Model, Solution, Table, petlion, simulate, simulate_
 
 LCO = "LCO"
 NMC = "NMC"
 simulate_bang = simulate_   # Julia's simulate!
 
-__all__ = ["petlion", "simulate", "simulate_", "simulate_bang", "LCO", "NMC", "Model", "Solution", "build",
+__all__ = ["petlion", "simulate", "simulate_", "simulate_bang", "LCO", "NMC", "Model", "Solution", "Table", "build",
            "EXIT_REASONS"]

@@ -68,18 +68,23 @@ class Summary(C.Structure):
     _fields_ = [("t_end", C.c_double), ("V_end", C.c_double), ("I_end", C.c_double),
                 ("SOC_end", C.c_double), ("T_end", C.c_double), ("aux_end", C.c_double), ("flag", C.c_int), ("n_steps", C.c_int), ("n_res", C.c_int),
                 ("n_jac", C.c_int), ("n_netf", C.c_int), ("n_ncfn", C.c_int), ("n_newton_init", C.c_int),
-                ("reserved", C.c_int)]
+                ("n_reinit", C.c_int)]
+
+
+class InputTable(C.Structure):
+    _fields_ = [("n", C.c_int), ("t", C.POINTER(C.c_double)), ("v", C.POINTER(C.c_double)),
+                ("n_tdiscon", C.c_int), ("tdiscon", C.POINTER(C.c_double))]
 
 
 SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", "f8"), ("T_end", "f8"),
                  ("aux_end", "f8"), ("flag", "i4"),
                  ("n_steps", "i4"), ("n_res", "i4"), ("n_jac", "i4"), ("n_netf", "i4"), ("n_ncfn", "i4"),
-                 ("n_newton_init", "i4"), ("reserved", "i4")]
+                 ("n_newton_init", "i4"), ("n_reinit", "i4")]
 
 EXPORTS = ["plb_last_error", "plb_create", "plb_destroy", "plb_set_stream", "plb_nstates", "plb_ndiff",
            "plb_ntheta", "plb_jac_nnz", "plb_theta_keys", "plb_theta_index", "plb_theta_defaults",
            "plb_bounds_defaults", "plb_opts_defaults", "plb_calc_I1C", "plb_jac_pattern",
-           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_variant_info", "plb_launch_count",
+           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_variant_info", "plb_launch_count",
            "plb_last_kernel_ms"]
 
 _lib = None
@@ -115,6 +120,9 @@ def lib():
         L.plb_linear_solve.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.POINTER(Run), dp, dp, dp, vp, C.c_int]
         L.plb_simulate.argtypes = [vp, C.c_int, dp, C.POINTER(Run), dp, C.POINTER(Opts), C.POINTER(Bounds),
                                    dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, vp, C.c_int]
+        L.plb_simulate_table.argtypes = [vp, C.c_int, dp, C.POINTER(Run), C.POINTER(InputTable), dp, C.POINTER(Opts),
+                                         C.POINTER(Bounds), dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, vp,
+                                         C.c_int]
         L.plb_launch_count.argtypes = [vp]
         L.plb_launch_count.restype = C.c_longlong
         L.plb_last_kernel_ms.argtypes = [vp]

@@ -74,7 +74,7 @@ class Model:
         L.plb_opts_defaults(h, C.byref(o))
         self.opts = _NS(SOC=1.0, outputs=("t", "V"), abstol=o.abstol, reltol=o.reltol, maxiters=o.maxiters,
                         check_bounds=bool(o.check_bounds), interp_final=bool(o.interp_final), verbose=False,
-                        n_save_max=512)
+                        n_save_max=512, tdiscon=[])
 
     theta = property(lambda self: self.θ)
 
@@ -233,11 +233,46 @@ _BOUND_NAMES = [n for n, _ in _lib.Bounds._fields_]
 _BOUND_ALIASES = {"η_plating_min": "eta_plating_min"}
 
 
+class Table:
+    """A run_function input (structures.jl:55-63, examples/variable_input_functions.ipynb) as data: a
+    piecewise-linear function of the run's local time.  A repeated knot time is a jump (right-continuous):
+    `I_fun1(t) = t < 100 ? 1 : 0.5`  ==  Table([0, 100, 100], [1, 1, 0.5]).  `scale` (scalar or per-system
+    array) multiplies the table per system.  Julia closures themselves cannot cross the C ABI."""
+
+    def __init__(self, t, v, scale=None):
+        self.t = np.ascontiguousarray(t, dtype=np.float64)
+        self.v = np.ascontiguousarray(v, dtype=np.float64)
+        if self.t.ndim != 1 or self.t.shape != self.v.shape or self.t.size < 1:
+            raise ValueError("Table: t and v must be 1-d arrays of the same, non-zero length")
+        if np.any(np.diff(self.t) < 0):
+            raise ValueError("Table: knot times must be non-decreasing")
+        self.scale = scale
+
+    @classmethod
+    def sample(cls, func, t_knots, scale=None):
+        """tabulate a continuous func(t) on the given knots"""
+        t = np.asarray(t_knots, dtype=np.float64)
+        return cls(t, [func(float(x)) for x in t], scale)
+
+    def jumps(self):
+        """times of the jumps, the natural `tdiscon`"""
+        return [float(a) for a, b in zip(self.t[:-1], self.t[1:]) if a == b]
+
+    def __call__(self, t):
+        k = int(np.searchsorted(self.t, t, side="right")) - 1
+        if k < 0:
+            return float(self.v[0])
+        if k == self.t.size - 1:
+            return float(self.v[-1])
+        return float(self.v[k] + (self.v[k + 1] - self.v[k]) * ((t - self.t[k]) / (self.t[k + 1] - self.t[k])))
+
+
 def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_init=None, reltol_init=None,
-             maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, **inputs):
+             maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, tdiscon=None, **inputs):
     """simulate(p, tf; I=..|V=..|P=.., SOC, V_max, V_min, SOC_max, ...) -- model_evaluation.jl:10-86.
 
-    Inputs may be numbers (scalar or per-system arrays), "hold" or "rest" (Julia :hold / :rest)."""
+    Inputs may be numbers (scalar or per-system arrays), "hold" or "rest" (Julia :hold / :rest), or a
+    `Table` (a tabulated run_function; `tdiscon` = the known discontinuities, structures.jl:279)."""
     L = _lib.lib()
     bounds = _lib.Bounds(**{n: getattr(p.bounds, n) for n in _BOUND_NAMES})
     method_kw = {}
@@ -256,7 +291,7 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
         raise TypeError("ERROR\n--------\n Cannot select more than one input from: (I, V, P, dT, η_p)")
     (name, inp), = method_kw.items()
     new_run = sol is None or sol.isempty()
-    kind, value, vals = 0, 0.0, None
+    kind, value, vals, table = 0, 0.0, None, None
     if name == "dT" and not p.numerics.temperature:
         raise ValueError("Temperature must be enabled when using `dT`.")      # input_methods.jl:183
     if isinstance(inp, str):
@@ -270,8 +305,14 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
             kind = 2
         else:
             raise ValueError("Unsupported input symbol.")                                # input_methods.jl:23
+    elif isinstance(inp, Table):
+        if name == "dT":
+            raise ValueError("dT takes a number or :hold")
+        table = inp
+        if inp.scale is not None:
+            vals = np.asarray(inp.scale, dtype=np.float64)
     elif callable(inp):
-        raise NotImplementedError("function inputs (run_function) cannot cross the C ABI; see DESIGN.md")
+        raise NotImplementedError("a closure cannot cross the C ABI: tabulate it with Table.sample(func, knots)")
     else:
         vals = np.asarray(inp, dtype=np.float64)
     B = p.batch_size(vals, SOC) if new_run else sol.Y.shape[0]
@@ -294,13 +335,21 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     summ = np.zeros(B, dtype=_lib.SUMMARY_DTYPE)
     tr = {k: np.full((B, max(ns, 1)), np.nan) for k in ("t", "V", "I", "SOC", "T")}
     trn = np.zeros(B, dtype=np.int32)
-    _lib.check(L.plb_simulate(p._h, B, th.ctypes.data, C.byref(run), None if vals is None else vals.ctypes.data,
-                              C.byref(o), C.byref(bounds), None if soc0 is None else soc0.ctypes.data,
-                              sY.ctypes.data, sYP.ctypes.data, sSOC.ctypes.data, st.ctypes.data,
-                              summ.ctypes.data, ns, tr["t"].ctypes.data if ns else None,
-                              tr["V"].ctypes.data if ns else None, tr["I"].ctypes.data if ns else None,
-                              tr["SOC"].ctypes.data if ns else None, tr["T"].ctypes.data if ns else None,
-                              trn.ctypes.data, 0))
+    tail = (C.byref(o), C.byref(bounds), None if soc0 is None else soc0.ctypes.data,
+            sY.ctypes.data, sYP.ctypes.data, sSOC.ctypes.data, st.ctypes.data,
+            summ.ctypes.data, ns, tr["t"].ctypes.data if ns else None,
+            tr["V"].ctypes.data if ns else None, tr["I"].ctypes.data if ns else None,
+            tr["SOC"].ctypes.data if ns else None, tr["T"].ctypes.data if ns else None,
+            trn.ctypes.data, 0)
+    vptr = None if vals is None else vals.ctypes.data
+    if table is not None:
+        dpp = C.POINTER(C.c_double)
+        td = np.ascontiguousarray(sorted(tdiscon if tdiscon is not None else p.opts.tdiscon), dtype=np.float64)
+        it = _lib.InputTable(table.t.size, table.t.ctypes.data_as(dpp), table.v.ctypes.data_as(dpp), td.size,
+                             td.ctypes.data_as(dpp) if td.size else None)
+        _lib.check(L.plb_simulate_table(p._h, B, th.ctypes.data, C.byref(run), C.byref(it), vptr, *tail))
+    else:
+        _lib.check(L.plb_simulate(p._h, B, th.ctypes.data, C.byref(run), vptr, *tail))
     hard = summ["flag"] < 0
     if B == 1 and hard[0]:
         # the reference throws for a single simulation (model_evaluation.jl:456, checks.jl:233-239)

@@ -68,7 +68,7 @@ struct Bounds {
 };
 struct Summary {   // == plb_summary (include/petlion_b200.h), 80 bytes
     double t_end, V_end, I_end, SOC_end, T_end, aux_end;
-    int flag, n_steps, n_res, n_jac, n_netf, n_ncfn, n_newton_init, reserved;
+    int flag, n_steps, n_res, n_jac, n_netf, n_ncfn, n_newton_init, n_reinit;
 };
 
 constexpr int FAIL_NEWTON_INIT = -1, FAIL_CONV = -2, FAIL_ERRTEST = -3, FAIL_MAXITERS = -4,
@@ -118,6 +118,12 @@ struct SimArgs {
     int* tr_n;
     int* counter;
     double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]
+    // run_function restricted to a piecewise-linear table of the run's local time (structures.jl:55,
+    // scalar_residual.jl:169-170): value(t) = scale[sys] * table(t); `values` then holds the scales.
+    // tab_n == 0: run_constant.  tstops: the merged, sorted stop list of postfix_integrator!
+    // (model_evaluation.jl:288-310) when a table is given.
+    int tab_n, n_tstops;
+    const double *tab_t, *tab_v, *tstops;
 };
 
 // what the host needs to know about a compiled variant

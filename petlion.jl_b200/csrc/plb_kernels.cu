@@ -479,10 +479,10 @@ int plb_linear_solve(plb_handle h, int B, const double* Y, const double* YP, con
     return 0;
 }
 
-int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, const double* values,
-                 const plb_opts* opts, const plb_bounds* bounds, const double* soc0, double* sY,
-                 double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
-                 double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
+static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run* run, const plb_input_table* tab,
+                         const double* values, const plb_opts* opts, const plb_bounds* bounds, const double* soc0,
+                         double* sY, double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
+                         double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
     if (B <= 0) return 0;
     if (!run || !opts || !bounds || !theta || !sY || !sSOC || !st || !summary)
         return fail("plb_simulate: null required argument");
@@ -494,6 +494,32 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
     if (run->input_kind == PLB_INPUT_REST && run->method != PLB_METHOD_I && run->method != PLB_METHOD_P)
         return fail("plb_simulate: Unsupported input symbol.");
     static_assert(sizeof(plb_summary) == sizeof(Summary), "summary layout");
+    // run_function as a table: validate, and merge the stop list of postfix_integrator!
+    // (model_evaluation.jl:288-310): sort([tdiscon .- reltol/2; 1.0 if continuing; tf]), non-positive entries
+    // dropped; entries at or past tf are never reached (the run ends at tf) and are left out
+    std::vector<double> tstops;
+    const double *tab_t = nullptr, *tab_v = nullptr, *d_tstops = nullptr;
+    if (tab) {
+        if (run->input_kind != PLB_INPUT_VALUE) return fail("plb_simulate_table: a table input cannot be :hold or :rest");
+        if (run->method == PLB_METHOD_DT) return fail("plb_simulate_table: dT takes a number or :hold");
+        if (tab->n < 1 || !tab->t || !tab->v) return fail("plb_simulate_table: empty table");
+        for (int k = 0; k < tab->n; k++) {
+            if (!std::isfinite(tab->t[k]) || !std::isfinite(tab->v[k])) return fail("plb_simulate_table: non-finite knot");
+            if (k && tab->t[k] < tab->t[k - 1]) return fail("plb_simulate_table: knot times must be non-decreasing");
+            if (k >= 2 && tab->t[k] == tab->t[k - 2]) return fail("plb_simulate_table: more than two knots at one time");
+        }
+        if (tab->n_tdiscon < 0 || (tab->n_tdiscon > 0 && !tab->tdiscon)) return fail("plb_simulate_table: bad tdiscon");
+        bool used1 = run->new_run || !(1.0 < run->tf);
+        for (int k = 0; k < tab->n_tdiscon; k++) {
+            if (k && tab->tdiscon[k] < tab->tdiscon[k - 1]) return fail("plb_simulate_table: tdiscon must be ascending");
+            const double ts = tab->tdiscon[k] - opts->reltol / 2;
+            if (!used1 && 1.0 <= ts) { tstops.push_back(1.0); used1 = true; }
+            if (ts > 0.0 && ts < run->tf) tstops.push_back(ts);
+        }
+        if (!used1) tstops.push_back(1.0);
+        tstops.push_back(run->tf);
+        tab_t = tab->t; tab_v = tab->v; d_tstops = tstops.data();
+    }
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     const size_t BN = (size_t)B * m.N_tot, BS = (size_t)B * (n_save_max > 0 ? n_save_max : 0);
@@ -511,6 +537,8 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
         stage_inout(b[10], tr_I, htI, BS, mem, false, s) || stage_inout(b[11], tr_SOC, htS, BS, mem, false, s) ||
         stage_inout(b[12], tr_n, htn, (size_t)B, mem, false, s) ||
         stage_inout(b[13], tr_T, htT, BS, mem, false, s)) return -1;
+    if (tab && (stage_in(b[14], tab_t, (size_t)tab->n, PLB_MEM_HOST, s) || stage_in(b[15], tab_v, (size_t)tab->n, PLB_MEM_HOST, s) ||
+                stage_in(b[16], d_tstops, tstops.size(), PLB_MEM_HOST, s))) return -1;
     SimArgs a;
     memset(&a, 0, sizeof a);
     a.m = m; a.B = B; a.theta = theta; a.values = values; a.method = run->method; a.value = run->value;
@@ -522,6 +550,7 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
     a.tr_t = tr_t; a.tr_V = tr_V; a.tr_I = tr_I; a.tr_SOC = tr_SOC; a.tr_T = tr_T; a.tr_n = tr_n;
     a.counter = h->d_counter;
     a.gws = h->d_gws;
+    if (tab) { a.tab_n = tab->n; a.tab_t = tab_t; a.tab_v = tab_v; a.n_tstops = (int)tstops.size(); a.tstops = d_tstops; }
     CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
     const int grid = std::min((B + h->vi.sim_warps - 1) / h->vi.sim_warps, h->sim_grid);
     CUDA_OK(cudaEventRecord(h->ev0, s));
@@ -535,4 +564,21 @@ int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, c
     CUDA_OK(cudaStreamSynchronize(s));
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
     return 0;
+}
+
+int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, const double* values,
+                 const plb_opts* opts, const plb_bounds* bounds, const double* soc0, double* sY,
+                 double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
+                 double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
+    return simulate_impl(h, B, theta, run, nullptr, values, opts, bounds, soc0, sY, sYP, sSOC, st, summary, n_save_max,
+                         tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_n, mem);
+}
+
+int plb_simulate_table(plb_handle h, int B, const double* theta, const plb_run* run, const plb_input_table* table,
+                       const double* scale, const plb_opts* opts, const plb_bounds* bounds, const double* soc0,
+                       double* sY, double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
+                       double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
+    if (!table) return fail("plb_simulate_table: null table");
+    return simulate_impl(h, B, theta, run, table, scale, opts, bounds, soc0, sY, sYP, sSOC, st, summary, n_save_max,
+                         tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_n, mem);
 }

@@ -58,7 +58,28 @@ struct SimState {
     int ret_fl;
     double ret_t;
     double dt_init;
+    // run_function (tabulated input): per-system scale, time of the algebraic initialisation in flight
+    // (0, or t + reltol for a re-initialisation at a discontinuity: checks.jl:341-364)
+    double scale, t_init;
+    int reinit, n_reinit;
 };
+
+// value of the tabulated input at local time t: last knot k with tab_t[k] <= t (right-continuous at a
+// repeated knot = jump), linear to the next knot, constant outside the table
+__device__ __noinline__ double table_eval(const double* __restrict__ tt, const double* __restrict__ vv, int n, double t) {
+    int lo = -1, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(tt + mid) <= t) lo = mid; else hi = mid;
+    }
+    if (lo < 0) return __ldg(vv);
+    if (lo == n - 1) return __ldg(vv + n - 1);
+    const double t0 = __ldg(tt + lo), t1 = __ldg(tt + lo + 1), v0 = __ldg(vv + lo), v1 = __ldg(vv + lo + 1);
+    return v0 + (v1 - v0) * ((t - t0) / (t1 - t0));
+}
+__device__ __forceinline__ double cur_tstop(const SimArgs& a, const SimState& S) {
+    return a.n_tstops ? __ldg(a.tstops + S.itstop) : (S.itstop == 0 ? S.tstop0 : S.tstop1);
+}
 
 // ---- pieces of ida_nls -------------------------------------------------------------------------------
 __device__ __forceinline__ void nls_begin(const ModelDesc& m, WarpWS& w, SimState& S, int lane) {
@@ -146,11 +167,13 @@ __device__ __forceinline__ void attempt_begin(const ModelDesc& m, WarpWS& w, Sim
 
 // IDASolve(ONE_STEP) up to the first residual evaluation.  Returns true if an evaluation is needed
 // (state = ST_NLS), false if the call returned (S.ret_fl / S.ret_t set).
-__device__ __forceinline__ bool solve_begin(const ModelDesc& m, WarpWS& w, const Opts& o, SimState& S, int lane) {
+__device__ __forceinline__ bool solve_begin(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+    const ModelDesc& m = a.m;
+    const Opts& o = a.o;
     Ida& M = S.M;
     __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const double ur = DBL_EPSILON;
-    const double tout = S.itstop == 0 ? S.tstop0 : S.tstop1;
+    const double tout = cur_tstop(a, S);
     M.tstop = tout; M.tstopset = 1;
     if (M.nst == 0) {
         ewt_set(m, w, o, lane);
@@ -262,18 +285,21 @@ __device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const O
 }
 
 // one turn of solve! after step!(int) returned (model_evaluation.jl:320-328, checks.jl:226-249)
-// returns true to continue stepping
-__device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+// returns 1 to continue stepping, 0 to finish, 2 when a re-initialisation (Newton on the algebraic block at
+// t + reltol, then IDAReInit) has been set up and the next tick is its first evaluation
+__device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     Ida& M = S.M;
     __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const int N = m.N_tot;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
-    const double tcur_stop = S.itstop == 0 ? S.tstop0 : S.tstop1;
+    const double tcur_stop = cur_tstop(a, S);
     if (S.ret_fl == 1 || S.ret_t >= tcur_stop) { if (S.itstop < S.ntstops - 1) S.itstop++; }
     S.t = S.ret_t;
     S.iter++;
-    if (S.ret_fl < 0 || S.t == S.tprev) {
+    // check_solve(run::run_function, ...) (checks.jl:251-268) has no "failed to converge" branch: a failed
+    // step stores its point again and the discontinuity check at the end of this function decides
+    if (!a.tab_n && (S.ret_fl < 0 || S.t == S.tprev)) {
         if (S.t == 0.0 && S.iter == 2 && !S.retried && M.nst == 0) {
             S.retried = 1;
             const double sc = 1.0 / w.K.psi[0];
@@ -281,10 +307,10 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
             for (int i = lane; i < N; i += LW) w.v(V_PHI1)[i] *= sc;
             grp_sync();
             M.hin = a.o.reltol;
-            return true;
+            return 1;
         }
         S.hard = (S.ret_fl == FAIL_ERRTEST) ? FAIL_ERRTEST : FAIL_CONV;
-        return false;
+        return 0;
     }
     grp_sync();
     if (lane == 0) S.kord = getsol_weights(M, w.K, S.t, w.K.cvals, w.K.dvals);
@@ -319,13 +345,48 @@ __device__ __forceinline__ bool host_after_return(const SimArgs& a, WarpWS& w, S
         check_stop(m, w, rc, a.o, a.b, a.input_kind == 2, a.tf, pv, flag, S.t, w.K.cvals, w.K.dvals, S.kord, S.SOC, Ic, Vc, lane);
         S.pv = pv; S.flag = flag;
     }
-    if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return false; }
-    if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { S.hard = FAIL_NONFINITE; return false; }
-    if (S.flag != -1) return false;
+    if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return 0; }
+    if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { S.hard = FAIL_NONFINITE; return 0; }
+    if (S.flag != -1) return 0;
     S.I_prev = Ic;
     S.tg_prev = tg;
+    const double dt_step = S.t - S.tprev;
     S.tprev = S.t;
-    return true;
+    if (a.tab_n && dt_step < 1e-3 * a.o.reltol) {
+        // check_reinitialization! (checks.jl:341-364): value(run) is what the last residual evaluation
+        // computed; a jump within the next reltol seconds restarts the DAE there
+        const double t_new = S.t + a.o.reltol;
+        const double v_old = S.rc.value, v_new = S.scale * table_eval(a.tab_t, a.tab_v, a.tab_n, t_new);
+        const double tol = fmax(a.o.abstol, a.o.reltol * fmax(fabs(v_old), fabs(v_new)));
+        if (!(fabs(v_old - v_new) <= tol)) {
+            // Y = int.u (the interpolant at t) becomes the Newton start; the history is discarded
+            grp_sync();
+#pragma unroll 1
+            for (int i = lane; i < N; i += LW) w.v(V_PHI0)[i] = interp_y(w, w.K.cvals, S.kord, i);
+            grp_sync();
+            S.t_init = t_new; S.reinit = 1; S.ni_iter = 0;
+            S.state = ST_INIT_ITER;
+            return 2;
+        }
+    }
+    return 1;
+}
+
+// IDAReInit(mem, t_new, Y, YP) after the re-initialisation's newtons_method! (checks.jl:358-361)
+__device__ __forceinline__ void reinit_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+    const ModelDesc& m = a.m;
+    for (int k = 2; k < 6; k++) {
+#pragma unroll 1
+        for (int i = lane; i < m.N_tot; i += LW) w.v(V_PHI0 + k)[i] = 0.0;
+    }
+    grp_sync();
+    Ida& M = S.M;
+    M.tn = S.t_init; M.tretlast = S.t_init;
+    M.hh = 0.0; M.hused = 0.0; M.cj = 0.0; M.cjlast = 0.0; M.cjold = 0.0; M.cjratio = 1.0;
+    M.ss = 20.0; M.rr = 0.0; M.tstop = 0.0;
+    M.kk = 0; M.kused = 0; M.knew = 0; M.phase = 0; M.ns = 0; M.nst = 0; M.tstopset = 0;
+    S.reinit = 0; S.n_reinit++;
+    S.pending = PEND_BEGIN;
 }
 
 // exit_simulation! (model_evaluation.jl:335-382) + summary / state hand-back
@@ -335,7 +396,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
     const int N = m.N_tot;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
     Summary out;
-    out.reserved = 0; out.aux_end = 0.0;
+    out.n_reinit = S.n_reinit; out.aux_end = 0.0;
     double t_end = S.t + S.t0, SOC_end = S.SOC, V_end = 0.0, I_end = 0.0, T_end = TH ? 0.0 : w.C.g[GC_T];
     const size_t so = (size_t)S.sys * a.n_save_max;
     if (integrated) {
@@ -431,7 +492,11 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
     const int N = m.N_tot;
     setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
     S.rc.method = a.method;
-    S.rc.value = a.values ? a.values[sys] : a.value;
+    S.t_init = 0.0; S.reinit = 0; S.n_reinit = 0; S.scale = 1.0;
+    if (a.tab_n) {   // run_function: initial_current! evaluates the function at t = 0 (input_methods.jl:27-29, 64-74, 104-107)
+        S.scale = a.values ? a.values[sys] : 1.0;
+        S.rc.value = S.scale * table_eval(a.tab_t, a.tab_v, a.tab_n, 0.0);
+    } else S.rc.value = a.values ? a.values[sys] : a.value;
     double* Y0 = w.v(V_PHI0);
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
     if (a.new_run) {
@@ -492,7 +557,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
             S.rc.value = 0.0; Ig = 0.0;
         } else if (S.rc.method == METHOD_I) Ig = S.rc.value;
         else if (S.rc.method == METHOD_V) {
-            if (!a.new_run && I_prev_state != 0.0) Ig = I_prev_state;
+            if (!a.new_run && (a.tab_n || I_prev_state != 0.0)) Ig = I_prev_state;   // :40-52 / :64-74
             else Ig = S.rc.value > V0 ? 1.0 : -1.0;
         } else Ig = S.rc.value / (V0 * w.C.g[GC_I1C]);
         grp_sync();
@@ -531,6 +596,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
     S.ntstops = 0; S.itstop = 0;
     if (!a.new_run && 1.0 < a.tf) { S.tstop0 = 1.0; S.tstop1 = a.tf; S.ntstops = 2; }
     else { S.tstop0 = a.tf; S.tstop1 = a.tf; S.ntstops = 1; }
+    if (a.n_tstops) S.ntstops = a.n_tstops;
     grp_sync();
     if (lane == 0) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = 1.0; }   // y = phi0, yp = phi1 = YP0
     grp_sync();
@@ -579,6 +645,14 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
     for (;;) {
         // ------------------------------ PRE: get to an evaluation point ---------------------------------
         if (S.state == ST_FETCH) fetch_and_setup<CHEM>(a, w, ro, S, lane);
+        if (a.tab_n && S.state != ST_EXHAUSTED) {
+            // run.func(t) of this tick's evaluation: IDA evaluates F at the trial time tn; newtons_method! at its
+            // t, except for the algebraic-derivative estimate, which passes dt itself as the time
+            // (model_evaluation.jl:469).  Done here, before the lane vectors are live, to keep the call cheap.
+            const double te = S.state == ST_NLS ? S.M.tn : (S.state == ST_INIT_DT ? S.dt_init : S.t_init);
+            __syncwarp();
+            S.rc.value = S.scale * table_eval(a.tab_t, a.tab_v, a.tab_n, te);
+        }
         LaneVec y, yp, res;
         double Iy = 0.0;
         bool do_eval = S.state != ST_EXHAUSTED, need_jac = false, alg_only = false, do_solve = false;
@@ -703,9 +777,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 const bool bad = lsetup_bad || !(s == s) || isinf(s);
                 if (bad || (S.ni_iter >= 100 && !(sqrt(s) < a.o.reltol_init))) {
                     S.flag = FAIL_NEWTON_INIT; S.n_newton_init = FAIL_NEWTON_INIT;
-                    finish(a, w, S, false, lane);
+                    finish(a, w, S, false, lane);   // (also for a failed re-initialisation: the run is reported from its start)
                 } else if (sqrt(s) < a.o.reltol_init) {
-                    S.n_newton_init = S.ni_iter;
+                    if (!S.reinit) S.n_newton_init = S.ni_iter;
                     S.state = ST_INIT_RDIFF;
                 }
             } else if (S.state == ST_INIT_RDIFF) {
@@ -730,12 +804,13 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 if (SEI) ypo.js = -res.js / S.dt_init;
                 store_lane(m, ro, w.v(V_PHI1), ypo, -dI / S.dt_init, lane);
                 grp_sync();
-                begin_integration(a, w, S, lane);
+                if (S.reinit) reinit_integration(a, w, S, lane);
+                else begin_integration(a, w, S, lane);
             }
             // between evaluations: host loop of solve! until the next evaluation is needed
             while (S.pending != PEND_NONE) {
-                if (S.pending == PEND_RETURNED) S.pending = host_after_return(a, w, S, lane) ? PEND_BEGIN : PEND_FINISH;
-                if (S.pending == PEND_BEGIN) S.pending = solve_begin(m, w, a.o, S, lane) ? PEND_NONE : PEND_RETURNED;
+                if (S.pending == PEND_RETURNED) { const int r = host_after_return(a, w, S, lane); S.pending = r == 1 ? PEND_BEGIN : (r == 0 ? PEND_FINISH : PEND_NONE); }
+                if (S.pending == PEND_BEGIN) S.pending = solve_begin(a, w, S, lane) ? PEND_NONE : PEND_RETURNED;
                 if (S.pending == PEND_FINISH) { finish(a, w, S, true, lane); S.pending = PEND_NONE; }
             }
         }

@@ -175,6 +175,34 @@ gold["summaries"] = {
     "benchmark_median_ms": 2.616,
 }
 
+# ---- function inputs: printed summaries of examples/variable_input_functions.ipynb ----------------------
+import re
+nbf = json.load(open(os.path.join(REF, "examples", "variable_input_functions.ipynb")))
+
+
+def printed(cell):
+    txt = ""
+    for o in nbf["cells"][cell].get("outputs", []):
+        t = o.get("text") or o.get("data", {}).get("text/plain") or []
+        txt += "".join(t)
+    f = lambda key: float(re.search(key + r":\s+([-0-9.]+)", txt).group(1))
+    return {"t_s": f("Time"), "V": f("Voltage"), "P": f("Power"), "SOC": f("SOC")}
+
+
+fi = {}
+for name, cell, extra in (("step", 6, {"tdiscon": []}), ("step_tdiscon", 8, {"tdiscon": [100.0]}),
+                          ("ramp_100", 13, {"ramp_val": 1 / 100}), ("ramp_10", 15, {"ramp_val": 1 / 10})):
+    src = "".join(nbf["cells"][cell]["source"])
+    assert ("I_fun1" in src) == name.startswith("step") and ("tdiscon" in src) == (name == "step_tdiscon"), (name, src)
+    fi[name] = dict(printed(cell), **extra, src="variable_input_functions.ipynb cell %d: %s" % (cell, src.split("\n")[-1 if "ramp" not in name else 1].strip()))
+for name, cell in (("ramp_100", 13), ("ramp_10", 15)):
+    data = [q for q in polylines(cell_svg(nbf, cell)) if len(q) > 2][0]
+    x0, x1 = data[0][0], data[-1][0]
+    fi[name]["t_ladder"] = [(x - x0) / (x1 - x0) * 100.0 for x, _ in data]    # first vertex t = 0, last t = tf = 100
+fi["_note"] = ("I_fun1(t) = t < 100 ? 1 : 0.5 ; I_ramp(t,p) = ramp_val*t ; SOC = 0, LCO defaults; the notebook was executed "
+               "with an older PETLION/Sundials (power printed in W): 4-digit checks")
+gold["function_inputs"] = fi
+
 json.dump(gold, open(OUT, "w"), indent=1, ensure_ascii=False)
 print("wrote", OUT)
 for k, v in ladders.items():
