@@ -235,7 +235,7 @@ def main():
         for k, (rk, bk) in enumerate(segs):
             _lib.check(L.plb_simulate(h, B, theta_ptr or d_theta.data_ptr(), C.byref(rk), None, C.byref(o), C.byref(bk),
                                       soc_ptr or d_soc0.data_ptr(), d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(),
-                                      d_t.data_ptr(), d_sums[k].data_ptr(), 0, None, None, None, None, None,
+                                      d_t.data_ptr(), d_sums[k].data_ptr(), 0, None, None, None, None, None, None,
                                       d_trn.data_ptr(), 1))
 
     def barrier():
@@ -289,7 +289,7 @@ def main():
         def step_e2e():
             _lib.check(L.plb_simulate(h, B, h_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(segs[0][1]),
                                       h_soc0.data_ptr(), h_Y.data_ptr(), None, h_SOC.data_ptr(), h_t.data_ptr(),
-                                      h_sum.data_ptr(), N_SAVE_E2E, h_trt.data_ptr(), h_trV.data_ptr(), None, None, None,
+                                      h_sum.data_ptr(), N_SAVE_E2E, h_trt.data_ptr(), h_trV.data_ptr(), None, None, None, None,
                                       h_trn.data_ptr(), 0))
         h2d = h_theta.numel() * 8 + h_soc0.numel() * 8
         d2h = (h_Y.numel() + h_SOC.numel() + h_t.numel() + h_sum.numel() + h_trt.numel() + h_trV.numel()) * 8 + h_trn.numel() * 4
@@ -329,7 +329,7 @@ def main():
         run_mid = _lib.Run(run.method, 0, run.value, t_mid, 1, 0)
         _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run_mid), None, C.byref(o), C.byref(b),
                                   d_soc0.data_ptr(), d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(),
-                                  d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, None, d_trn.data_ptr(), 1))
+                                  d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, None, None, d_trn.data_ptr(), 1))
         nnz = L.plb_jac_nnz(h, 0)
         d_res = torch.empty(B, N, **f64); d_nz = torch.empty(B, nnz, **f64)
         d_gam = torch.full((B,), 0.05, **f64)

@@ -59,7 +59,9 @@ typedef struct {
     int maxiters;
     int check_bounds;
     int interp_final;
-    int reserved;
+    int skip_alg_deriv;  /* 0 (default): newtons_method! estimates dY_alg/dt (model_evaluation.jl:462-477);
+                            1: its keyword initialize_algebraic_derivatives=false (:433) -- Y'_alg = 0 at the start
+                            of a run, which is also how PETLION versions before that estimate behaved */
 } plb_opts;
 
 /* boundary_stop_conditions: src/structures.jl:237-251 (NaN deactivates a bound) */
@@ -147,13 +149,15 @@ int plb_linear_solve(plb_handle h, int B, const double *Y, const double *YP, con
  *   summary[B]
  *   traj_*[B x n_save_max] (optional, may be NULL; n_save_max may be 0), traj_n[B];
  *   traj_T = temperature_weighting(T) per saved step (thermal models; T0 otherwise)
+ *   traj_Y[B x n_save_max x N] (optional): the full state of every saved row in the reference state order
+ *   -- what set_vars! stores for outputs = :all / (:c_e, :c_s_avg, :j, ...) (save_outputs.jl:11-40)
  */
 int plb_simulate(plb_handle h, int B, const double *theta, const plb_run *run,
                  const double *values, const plb_opts *opts, const plb_bounds *bounds,
                  const double *soc0, double *state_Y, double *state_YP, double *state_SOC,
                  double *state_t, plb_summary *summary, int n_save_max, double *traj_t,
-                 double *traj_V, double *traj_I, double *traj_SOC, double *traj_T, int *traj_n,
-                 int mem);
+                 double *traj_V, double *traj_I, double *traj_SOC, double *traj_T, double *traj_Y,
+                 int *traj_n, int mem);
 
 /* run_function{method,func} (src/structures.jl:55-63; examples/variable_input_functions.ipynb): a
  * time-varying I(t) / V(t) / P(t) / eta_p(t).  A Julia closure cannot cross the C ABI, so the function is
@@ -181,7 +185,7 @@ int plb_simulate_table(plb_handle h, int B, const double *theta, const plb_run *
                        const plb_bounds *bounds, const double *soc0, double *state_Y,
                        double *state_YP, double *state_SOC, double *state_t, plb_summary *summary,
                        int n_save_max, double *traj_t, double *traj_V, double *traj_I,
-                       double *traj_SOC, double *traj_T, int *traj_n, int mem);
+                       double *traj_SOC, double *traj_T, double *traj_Y, int *traj_n, int mem);
 
 /* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI, 3 wide, 4 wide SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared

@@ -49,7 +49,7 @@ class Opts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("abstol_init", C.c_double),
                 ("reltol_init", C.c_double), ("maxiters", C.c_int), ("check_bounds", C.c_int),
                 ("interp_final", C.c_int), ("ida_maxord", C.c_int), ("ida_maxcor", C.c_int),
-                ("ida_maxnef", C.c_int), ("ida_maxncf", C.c_int)]
+                ("ida_maxnef", C.c_int), ("ida_maxncf", C.c_int), ("skip_alg_deriv", C.c_int)]
 
 
 class Bounds(C.Structure):

@@ -105,6 +105,8 @@ typedef struct {
     int ida_maxcor;  /* max_nonlinear_iters */
     int ida_maxnef;  /* max_error_test_failures */
     int ida_maxncf;  /* max_convergence_failures */
+    int skip_alg_deriv; /* 1: newtons_method!(...; initialize_algebraic_derivatives=false) (model_evaluation.jl:433):
+                           Y'_alg = 0 at the start of a run, as PETLION versions before that estimate did */
 } orc_opts;
 
 /* boundary_stop_conditions: src/structures.jl:237-251 (NaN deactivates) */

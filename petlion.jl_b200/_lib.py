@@ -56,7 +56,7 @@ class Run(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("abstol_init", C.c_double),
                 ("reltol_init", C.c_double), ("maxiters", C.c_int), ("check_bounds", C.c_int),
-                ("interp_final", C.c_int), ("reserved", C.c_int)]
+                ("interp_final", C.c_int), ("skip_alg_deriv", C.c_int)]
 
 
 class Bounds(C.Structure):
@@ -119,9 +119,9 @@ def lib():
         L.plb_newton_init.argtypes = [vp, C.c_int, dp, dp, dp, C.POINTER(Run), dp, C.POINTER(Opts), vp, C.c_int]
         L.plb_linear_solve.argtypes = [vp, C.c_int, dp, dp, dp, dp, C.POINTER(Run), dp, dp, dp, vp, C.c_int]
         L.plb_simulate.argtypes = [vp, C.c_int, dp, C.POINTER(Run), dp, C.POINTER(Opts), C.POINTER(Bounds),
-                                   dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, vp, C.c_int]
+                                   dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, dp, vp, C.c_int]
         L.plb_simulate_table.argtypes = [vp, C.c_int, dp, C.POINTER(Run), C.POINTER(InputTable), dp, C.POINTER(Opts),
-                                         C.POINTER(Bounds), dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, vp,
+                                         C.POINTER(Bounds), dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, dp, vp,
                                          C.c_int]
         L.plb_launch_count.argtypes = [vp]
         L.plb_launch_count.restype = C.c_longlong

@@ -60,6 +60,7 @@ class Model:
         self.N.tot = L.plb_nstates(h)
         self.N.diff = L.plb_ndiff(h)
         self.N.alg = self.N.tot - self.N.diff
+        self.ind = self._index_state()
         nth = L.plb_ntheta(h)
         keys = (C.c_char_p * nth)()
         L.plb_theta_keys(h, keys)
@@ -74,9 +75,31 @@ class Model:
         L.plb_opts_defaults(h, C.byref(o))
         self.opts = _NS(SOC=1.0, outputs=("t", "V"), abstol=o.abstol, reltol=o.reltol, maxiters=o.maxiters,
                         check_bounds=bool(o.check_bounds), interp_final=bool(o.interp_final), verbose=False,
-                        n_save_max=512, tdiscon=[])
+                        n_save_max=512, tdiscon=[], initialize_algebraic_derivatives=True)
 
     theta = property(lambda self: self.θ)
+
+    def _index_state(self):
+        """state_indices: src/external.jl:275-365 (0-based slices into a state row; sections in their
+        reference order, c_s_avg particle-major with the surface in the last slot of each particle)"""
+        N, nm = self.N, self.numerics
+        Nx = N.p + N.s + N.n
+        sizes = [("c_e", Nx), ("c_s_avg", N.p * N.r_p + N.n * N.r_n)]
+        if nm.temperature:
+            sizes.append(("T", N.a + Nx + N.z))
+        if nm.aging == "SEI":
+            sizes += [("film", N.n), ("SOH", 1)]
+        sizes += [("j", N.p + N.n), ("Φ_e", Nx), ("Φ_s", N.p + N.n)]
+        if nm.aging == "SEI":
+            sizes.append(("j_s", N.n))
+        sizes.append(("I", 1))
+        ind, k = {}, 0
+        for name, n in sizes:
+            ind[name] = slice(k, k + n)
+            k += n
+        assert k == N.tot, (k, N.tot)
+        ind["Phi_e"], ind["Phi_s"] = ind["Φ_e"], ind["Φ_s"]
+        return ind
 
     def __del__(self):
         try:
@@ -187,6 +210,7 @@ class Solution:
 
     def __init__(self):
         self.t = self.V = self.I = self.SOC = self.T = None
+        self.states = None      # [B, n, N] when simulate(..., outputs=:all or state names)
         self.n_points = None
         self.Y = self.YP = None
         self._SOC_end = self._t_end = None
@@ -197,6 +221,13 @@ class Solution:
 
     def isempty(self):
         return len(self.results) == 0
+
+    def state(self, p, name, system=0):
+        """sol.c_e, sol.c_s_avg, sol.T, sol.j, sol.Φ_e, sol.Φ_s, sol.film, sol.j_s, sol.SOH of one system:
+        rows = saved steps (needs simulate(..., outputs="all") or outputs=(name, ...))"""
+        if self.states is None:
+            raise ValueError("the states were not kept: pass outputs=\"all\" (or the state names) to simulate")
+        return self.states[system, :self.n_points[system], p.ind[name]]
 
 
 def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10, temperature=False,
@@ -226,6 +257,8 @@ def _make_opts(p, kw):
     o.check_bounds = int(p.opts.check_bounds if cb is None else cb)
     itf = kw.get("interp_final")
     o.interp_final = int(p.opts.interp_final if itf is None else itf)
+    iad = kw.get("initialize_algebraic_derivatives")
+    o.skip_alg_deriv = int(not (p.opts.initialize_algebraic_derivatives if iad is None else iad))
     return o
 
 
@@ -268,7 +301,8 @@ class Table:
 
 
 def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_init=None, reltol_init=None,
-             maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, tdiscon=None, **inputs):
+             maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, tdiscon=None,
+             initialize_algebraic_derivatives=None, outputs=None, **inputs):
     """simulate(p, tf; I=..|V=..|P=.., SOC, V_max, V_min, SOC_max, ...) -- model_evaluation.jl:10-86.
 
     Inputs may be numbers (scalar or per-system arrays), "hold" or "rest" (Julia :hold / :rest), or a
@@ -321,7 +355,8 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
         vals = np.ascontiguousarray(np.broadcast_to(vals, (B,)))
     run = _lib.Run(METHODS[name], kind, value, float(np.ravel(tf)[-1]), int(new_run), 0)
     o = _make_opts(p, dict(abstol=abstol, reltol=reltol, abstol_init=abstol_init, reltol_init=reltol_init,
-                           maxiters=maxiters, check_bounds=check_bounds, interp_final=interp_final))
+                           maxiters=maxiters, check_bounds=check_bounds, interp_final=interp_final,
+                           initialize_algebraic_derivatives=initialize_algebraic_derivatives))
     N = p.N.tot
     if new_run:
         sol = Solution() if sol is None else sol
@@ -334,12 +369,24 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     ns = p.opts.n_save_max if n_save_max is None else n_save_max
     summ = np.zeros(B, dtype=_lib.SUMMARY_DTYPE)
     tr = {k: np.full((B, max(ns, 1)), np.nan) for k in ("t", "V", "I", "SOC", "T")}
+    # outputs (params.jl:262, save_outputs.jl:11-40): t, V, I, SOC, T are always kept; :all or any state name
+    # keeps the full state row of every saved step
+    outs = p.opts.outputs if outputs is None else outputs
+    outs = (outs,) if isinstance(outs, str) else tuple(outs)
+    bad = [o for o in outs if o not in ("all", "t", "V", "I", "P", "SOC", "T", "Y", "YP") and o not in p.ind]
+    if bad:
+        raise ValueError(f"unknown output {bad[0]!r}")
+    keep_states = ns > 0 and any(o in ("all", "Y") or (o in p.ind and o not in ("T", "I")) for o in outs)
+    if keep_states and sol is not None and not sol.isempty() and sol.states is None:
+        raise ValueError("cannot start keeping states in the middle of a solution")
+    trY = np.full((B, ns, N), np.nan) if keep_states else None
     trn = np.zeros(B, dtype=np.int32)
     tail = (C.byref(o), C.byref(bounds), None if soc0 is None else soc0.ctypes.data,
             sY.ctypes.data, sYP.ctypes.data, sSOC.ctypes.data, st.ctypes.data,
             summ.ctypes.data, ns, tr["t"].ctypes.data if ns else None,
             tr["V"].ctypes.data if ns else None, tr["I"].ctypes.data if ns else None,
             tr["SOC"].ctypes.data if ns else None, tr["T"].ctypes.data if ns else None,
+            trY.ctypes.data if keep_states else None,
             trn.ctypes.data, 0)
     vptr = None if vals is None else vals.ctypes.data
     if table is not None:
@@ -357,6 +404,7 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     sol.Y, sol.YP, sol._SOC_end, sol._t_end = sY, sYP, sSOC, st
     if sol.t is None or new_run:
         sol.t, sol.V, sol.I, sol.SOC, sol.T, sol.n_points = tr["t"], tr["V"], tr["I"], tr["SOC"], tr["T"], trn.copy()
+        sol.states = trY
     else:
         # append the new run's rows after the existing ones (per system)
         width = int((sol.n_points + trn).max())
@@ -367,6 +415,13 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
                 new[s, :sol.n_points[s]] = old[s, :sol.n_points[s]]
                 new[s, sol.n_points[s]:sol.n_points[s] + trn[s]] = tr[k][s, :trn[s]]
             setattr(sol, k, new)
+        if sol.states is not None:
+            new = np.full((B, width, N), np.nan)
+            for s in range(B):
+                new[s, :sol.n_points[s]] = sol.states[s, :sol.n_points[s]]
+                if trY is not None:
+                    new[s, sol.n_points[s]:sol.n_points[s] + trn[s]] = trY[s, :trn[s]]
+            sol.states = new
         sol.n_points = sol.n_points + trn
     sol.results.append(_NS(run=_NS(method=name, input=inp, tf=run.tf), summary=summ,
                            exit_reason=[EXIT_REASONS.get(int(f), HARD_FAILURES.get(int(f), "?")) for f in summ["flag"]],

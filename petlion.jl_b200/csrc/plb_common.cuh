@@ -61,6 +61,7 @@ struct Opts {
     double abstol, reltol, abstol_init, reltol_init;
     int maxiters, check_bounds, interp_final;
     int maxord, maxcor, maxnef, maxncf;   // Sundials.jl IDA(): 5, 3, 7, 10
+    int skip_alg_deriv;                   // newtons_method!(...; initialize_algebraic_derivatives=false)
 };
 struct Bounds {
     double V_max, V_min, SOC_max, SOC_min, T_max, c_s_n_max, I_max, I_min, eta_plating_min, c_e_min,
@@ -115,6 +116,7 @@ struct SimArgs {
     Summary* out;
     int n_save_max;
     double *tr_t, *tr_V, *tr_I, *tr_SOC, *tr_T;
+    double* tr_Y;             // optional: every saved row's full state [B][n_save_max][N] (outputs = :all, save_outputs.jl:11-40)
     int* tr_n;
     int* counter;
     double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]

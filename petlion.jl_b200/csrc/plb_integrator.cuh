@@ -168,8 +168,12 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     ypo.film = SEI ? res.film : 0.0; ypo.soh = SEI ? res.soh : 0.0; ypo.js = 0.0;
 #pragma unroll
     for (int r = 0; r < NR; r++) ypo.cs[r] = res.cs[r];
-    // estimate dY_alg/dt (:462-477): Delta_t = max(10 reltol_init, sqrt(eps(c_e0)))
-    {
+    ypo.j = 0.0; ypo.pe = 0.0; ypo.ps = 0.0;
+    if (o.skip_alg_deriv) {   // initialize_algebraic_derivatives = false (:433, :462): Y'_alg stays 0
+        store_lane(m, ro, Y, y, I, lane);
+        store_lane(m, ro, YP, ypo, 0.0, lane);
+    } else {
+        // estimate dY_alg/dt (:462-477): Delta_t = max(10 reltol_init, sqrt(eps(c_e0)))
         const double c0 = fabs(w.C.theta[TF_c_e0]);
         const double epsv = ::nextafter(c0, DBL_MAX) - c0;
         const double dt = fmax(10.0 * o.reltol_init, sqrt(epsv));

@@ -286,7 +286,7 @@ int plb_bounds_defaults(plb_handle h, plb_bounds* b) {
 int plb_opts_defaults(plb_handle, plb_opts* o) {
     // src/params.jl:256-280
     o->abstol = 1e-6; o->reltol = 1e-3; o->abstol_init = 1e-6; o->reltol_init = 1e-3;
-    o->maxiters = 10000; o->check_bounds = 1; o->interp_final = 1; o->reserved = 0;
+    o->maxiters = 10000; o->check_bounds = 1; o->interp_final = 1; o->skip_alg_deriv = 0;
     return 0;
 }
 int plb_calc_I1C(plb_handle h, int B, const double* theta, double* I1C) {
@@ -364,6 +364,7 @@ static Opts to_opts(const plb_opts* o) {
     Opts r;
     r.abstol = o->abstol; r.reltol = o->reltol; r.abstol_init = o->abstol_init; r.reltol_init = o->reltol_init;
     r.maxiters = o->maxiters; r.check_bounds = o->check_bounds; r.interp_final = o->interp_final;
+    r.skip_alg_deriv = o->skip_alg_deriv;
     // Sundials.jl IDA() constructor values (third-party): max_order 5, max_nonlinear_iters 3,
     // max_error_test_failures 7, max_convergence_failures 10
     r.maxord = 5; r.maxcor = 3; r.maxnef = 7; r.maxncf = 10;
@@ -482,7 +483,7 @@ int plb_linear_solve(plb_handle h, int B, const double* Y, const double* YP, con
 static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run* run, const plb_input_table* tab,
                          const double* values, const plb_opts* opts, const plb_bounds* bounds, const double* soc0,
                          double* sY, double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
-                         double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
+                         double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, double* tr_Y, int* tr_n, int mem) {
     if (B <= 0) return 0;
     if (!run || !opts || !bounds || !theta || !sY || !sSOC || !st || !summary)
         return fail("plb_simulate: null required argument");
@@ -524,7 +525,7 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     cudaStream_t s = h->stream;
     const size_t BN = (size_t)B * m.N_tot, BS = (size_t)B * (n_save_max > 0 ? n_save_max : 0);
     DevBufs b(h);
-    double *hY, *hYP, *hSOC, *ht, *htt, *htV, *htI, *htS, *htT;
+    double *hY, *hYP, *hSOC, *ht, *htt, *htV, *htI, *htS, *htT, *htY;
     int* htn;
     plb_summary* hsum;
     const bool cont = !run->new_run;
@@ -536,7 +537,7 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
         stage_inout(b[8], tr_t, htt, BS, mem, false, s) || stage_inout(b[9], tr_V, htV, BS, mem, false, s) ||
         stage_inout(b[10], tr_I, htI, BS, mem, false, s) || stage_inout(b[11], tr_SOC, htS, BS, mem, false, s) ||
         stage_inout(b[12], tr_n, htn, (size_t)B, mem, false, s) ||
-        stage_inout(b[13], tr_T, htT, BS, mem, false, s)) return -1;
+        stage_inout(b[13], tr_T, htT, BS, mem, false, s) || stage_inout(b[17], tr_Y, htY, BS * m.N_tot, mem, false, s)) return -1;
     if (tab && (stage_in(b[14], tab_t, (size_t)tab->n, PLB_MEM_HOST, s) || stage_in(b[15], tab_v, (size_t)tab->n, PLB_MEM_HOST, s) ||
                 stage_in(b[16], d_tstops, tstops.size(), PLB_MEM_HOST, s))) return -1;
     SimArgs a;
@@ -547,7 +548,7 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     static_assert(sizeof(plb_bounds) == sizeof(Bounds), "bounds layout");
     a.soc0 = soc0; a.sY = sY; a.sYP = sYP; a.sSOC = sSOC; a.st = st; a.out = (Summary*)summary;
     a.n_save_max = n_save_max > 0 ? n_save_max : 0;
-    a.tr_t = tr_t; a.tr_V = tr_V; a.tr_I = tr_I; a.tr_SOC = tr_SOC; a.tr_T = tr_T; a.tr_n = tr_n;
+    a.tr_t = tr_t; a.tr_V = tr_V; a.tr_I = tr_I; a.tr_SOC = tr_SOC; a.tr_T = tr_T; a.tr_Y = tr_Y; a.tr_n = tr_n;
     a.counter = h->d_counter;
     a.gws = h->d_gws;
     if (tab) { a.tab_n = tab->n; a.tab_t = tab_t; a.tab_v = tab_v; a.n_tstops = (int)tstops.size(); a.tstops = d_tstops; }
@@ -560,7 +561,7 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     if (stage_out(sY, hY, BN, s) || stage_out(sYP, hYP, BN, s) || stage_out(sSOC, hSOC, (size_t)B, s) ||
         stage_out(st, ht, (size_t)B, s) || stage_out(summary, hsum, (size_t)B, s) || stage_out(tr_t, htt, BS, s) ||
         stage_out(tr_V, htV, BS, s) || stage_out(tr_I, htI, BS, s) || stage_out(tr_SOC, htS, BS, s) ||
-        stage_out(tr_n, htn, (size_t)B, s) || stage_out(tr_T, htT, BS, s)) return -1;
+        stage_out(tr_n, htn, (size_t)B, s) || stage_out(tr_T, htT, BS, s) || stage_out(tr_Y, htY, BS * m.N_tot, s)) return -1;
     CUDA_OK(cudaStreamSynchronize(s));
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
     return 0;
@@ -569,16 +570,16 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
 int plb_simulate(plb_handle h, int B, const double* theta, const plb_run* run, const double* values,
                  const plb_opts* opts, const plb_bounds* bounds, const double* soc0, double* sY,
                  double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
-                 double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
+                 double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, double* tr_Y, int* tr_n, int mem) {
     return simulate_impl(h, B, theta, run, nullptr, values, opts, bounds, soc0, sY, sYP, sSOC, st, summary, n_save_max,
-                         tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_n, mem);
+                         tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_Y, tr_n, mem);
 }
 
 int plb_simulate_table(plb_handle h, int B, const double* theta, const plb_run* run, const plb_input_table* table,
                        const double* scale, const plb_opts* opts, const plb_bounds* bounds, const double* soc0,
                        double* sY, double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
-                       double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, int* tr_n, int mem) {
+                       double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, double* tr_Y, int* tr_n, int mem) {
     if (!table) return fail("plb_simulate_table: null table");
     return simulate_impl(h, B, theta, run, table, scale, opts, bounds, soc0, sY, sYP, sSOC, st, summary, n_save_max,
-                         tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_n, mem);
+                         tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_Y, tr_n, mem);
 }

@@ -337,6 +337,11 @@ __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, Si
         const double Tw = weighted_T(m, w, w.K.cvals, S.kord, false, lane);
         if (lane == 0) a.tr_T[so + S.nsave] = Tw;
     }
+    if (a.tr_Y && S.nsave < a.n_save_max) {
+        double* row = a.tr_Y + (so + S.nsave) * N;
+#pragma unroll 1
+        for (int i = lane; i < N; i += LW) row[ref_index(m, i)] = interp_y(w, w.K.cvals, S.kord, i);
+    }
     S.nsave++;
     {   // copies: check_stop is out of line, and S must not have its address taken (it would live in local memory)
         PrevVals pv = S.pv;
@@ -417,6 +422,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
             double yf = yn;
             if (do_interp) { const double ypv = interp_y(w, w.K.cprev, S.kord, i); yf = fr * (yn - ypv) + ypv; }
             a.sY[(size_t)S.sys * N + ref_index(m, i)] = yf;
+            if (a.tr_Y && do_interp && S.nsave >= 1 && S.nsave - 1 < a.n_save_max) a.tr_Y[(so + S.nsave - 1) * N + ref_index(m, i)] = yf;
             if (a.sYP) a.sYP[(size_t)S.sys * N + ref_index(m, i)] = interp_yp(w, w.K.dvals, S.kord, i);
             if (i == iP0) ps0 = yf;
             if (i == iPN) psN = yf;
@@ -613,6 +619,11 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
         const double Tw = weighted_T(m, w, w.K.cvals, 1, false, lane);
         if (lane == 0) a.tr_T[so + S.nsave] = Tw;
     }
+    if (a.tr_Y && S.nsave < a.n_save_max) {
+        double* row = a.tr_Y + (so + S.nsave) * N;
+#pragma unroll 1
+        for (int i = lane; i < N; i += LW) row[ref_index(m, i)] = Y0[i];
+    }
     S.nsave++;
     S.pv.T = -1; S.pv.dfilm = -1;
     S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
@@ -747,6 +758,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         // ------------------------------ POST: per-state glue --------------------------------------------
         __syncwarp();
         if (do_eval) {
+            bool start_now = false;
             if (S.state == ST_NLS) {
                 int retval;
                 if (lsetup_bad) retval = 1;
@@ -796,6 +808,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 const double epsv = ::nextafter(c0, DBL_MAX) - c0;
                 S.dt_init = fmax(10.0 * a.o.reltol_init, sqrt(epsv));   // :464
                 S.state = ST_INIT_DT;
+                start_now = a.o.skip_alg_deriv != 0;   // initialize_algebraic_derivatives = false (:433): Y'_alg stays 0
             } else {   // ST_INIT_DT: YP_alg = -(factor \ R_alg(Y + dt YP)) / dt  (:466-476)
                 LaneVec ypo;
                 double pI;
@@ -804,6 +817,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 if (SEI) ypo.js = -res.js / S.dt_init;
                 store_lane(m, ro, w.v(V_PHI1), ypo, -dI / S.dt_init, lane);
                 grp_sync();
+                start_now = true;
+            }
+            if (start_now) {
                 if (S.reinit) reinit_integration(a, w, S, lane);
                 else begin_integration(a, w, S, lane);
             }

@@ -27,7 +27,7 @@ for pin in (True, False):
         def call():
             _lib.check(L.plb_simulate(h, B, d["theta"].data_ptr(), C.byref(run), None, C.byref(o), C.byref(b), d["soc"].data_ptr(),
                                       d["Y"].data_ptr(), None, d["SOC"].data_ptr(), d["t"].data_ptr(), d["sum"].data_ptr(), ns,
-                                      d["trt"].data_ptr() if ns else None, d["trV"].data_ptr() if ns else None, None, None, None,
+                                      d["trt"].data_ptr() if ns else None, d["trV"].data_ptr() if ns else None, None, None, None, None,
                                       d["trn"].data_ptr(), 0))
         call(); torch.cuda.synchronize()
         t0 = time.perf_counter(); call(); call(); torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 2

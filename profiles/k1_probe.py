@@ -23,7 +23,7 @@ o = _lib.Opts(); L.plb_opts_defaults(h, C.byref(o)); b = _lib.Bounds(); L.plb_bo
 L.plb_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
 run = _lib.Run(0, 0, cur, tmid, 1, 0)
 _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(b), d_soc0.data_ptr(), d_Y.data_ptr(),
-                          d_YP.data_ptr(), d_SOC.data_ptr(), d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, None, d_trn.data_ptr(), 1))
+                          d_YP.data_ptr(), d_SOC.data_ptr(), d_t.data_ptr(), d_sum.data_ptr(), 0, None, None, None, None, None, None, d_trn.data_ptr(), 1))
 nnz = L.plb_jac_nnz(h, 0)
 d_res = torch.empty(B, N, **f64); d_nz = torch.empty(B, nnz, **f64); d_gam = torch.full((B,), 0.05, **f64)
 flush = torch.empty(256 * 1024 * 1024 // 8, **f64)

@@ -29,7 +29,7 @@ ms = []
 for k in range(4):
     _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(b), d_soc0.data_ptr(),
                               d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(), d_t.data_ptr(), d_sum.data_ptr(), 0,
-                              None, None, None, None, None, d_trn.data_ptr(), 1))
+                              None, None, None, None, None, None, d_trn.data_ptr(), 1))
     ms.append(L.plb_last_kernel_ms(h))
 s = d_sum.cpu().numpy().view(_lib.SUMMARY_DTYPE).reshape(-1)
 print(os.path.basename(os.environ.get("PLB_LIB", "default")), fam, "B", B, "ms", [round(x, 1) for x in ms], "sims/s", round(B / (min(ms[1:]) * 1e-3)),

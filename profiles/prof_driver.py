@@ -43,7 +43,7 @@ def sim(B, tf):
     run = _lib.Run(0, 0, CUR, tf, 1, 0)
     _lib.check(L.plb_simulate(h, B, d_theta.data_ptr(), C.byref(run), None, C.byref(o), C.byref(b), d_soc0.data_ptr(),
                               d_Y.data_ptr(), d_YP.data_ptr(), d_SOC.data_ptr(), d_t.data_ptr(), d_sum.data_ptr(), 0,
-                              None, None, None, None, None, d_trn.data_ptr(), 1))
+                              None, None, None, None, None, None, d_trn.data_ptr(), 1))
 
 
 sim(B1, T_MID)                       # launch 1: mid-run states for K1
