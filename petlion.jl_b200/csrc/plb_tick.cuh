@@ -77,8 +77,9 @@ __device__ __noinline__ double table_eval(const double* __restrict__ tt, const d
     const double t0 = __ldg(tt + lo), t1 = __ldg(tt + lo + 1), v0 = __ldg(vv + lo), v1 = __ldg(vv + lo + 1);
     return v0 + (v1 - v0) * ((t - t0) / (t1 - t0));
 }
+template <bool EXT>
 __device__ __forceinline__ double cur_tstop(const SimArgs& a, const SimState& S) {
-    return a.n_tstops ? __ldg(a.tstops + S.itstop) : (S.itstop == 0 ? S.tstop0 : S.tstop1);
+    return (EXT && a.n_tstops) ? __ldg(a.tstops + S.itstop) : (S.itstop == 0 ? S.tstop0 : S.tstop1);
 }
 
 // ---- pieces of ida_nls -------------------------------------------------------------------------------
@@ -167,13 +168,14 @@ __device__ __forceinline__ void attempt_begin(const ModelDesc& m, WarpWS& w, Sim
 
 // IDASolve(ONE_STEP) up to the first residual evaluation.  Returns true if an evaluation is needed
 // (state = ST_NLS), false if the call returned (S.ret_fl / S.ret_t set).
+template <bool EXT>
 __device__ __forceinline__ bool solve_begin(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     const Opts& o = a.o;
     Ida& M = S.M;
     __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const double ur = DBL_EPSILON;
-    const double tout = cur_tstop(a, S);
+    const double tout = cur_tstop<EXT>(a, S);
     M.tstop = tout; M.tstopset = 1;
     if (M.nst == 0) {
         ewt_set(m, w, o, lane);
@@ -287,19 +289,20 @@ __device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const O
 // one turn of solve! after step!(int) returned (model_evaluation.jl:320-328, checks.jl:226-249)
 // returns 1 to continue stepping, 0 to finish, 2 when a re-initialisation (Newton on the algebraic block at
 // t + reltol, then IDAReInit) has been set up and the next tick is its first evaluation
+template <bool EXT>
 __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     Ida& M = S.M;
     __syncwarp();   // S lives in shared memory and is updated by all lanes together: converge first
     const int N = m.N_tot;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
-    const double tcur_stop = cur_tstop(a, S);
+    const double tcur_stop = cur_tstop<EXT>(a, S);
     if (S.ret_fl == 1 || S.ret_t >= tcur_stop) { if (S.itstop < S.ntstops - 1) S.itstop++; }
     S.t = S.ret_t;
     S.iter++;
     // check_solve(run::run_function, ...) (checks.jl:251-268) has no "failed to converge" branch: a failed
     // step stores its point again and the discontinuity check at the end of this function decides
-    if (!a.tab_n && (S.ret_fl < 0 || S.t == S.tprev)) {
+    if (!(EXT && a.tab_n) && (S.ret_fl < 0 || S.t == S.tprev)) {
         if (S.t == 0.0 && S.iter == 2 && !S.retried && M.nst == 0) {
             S.retried = 1;
             const double sc = 1.0 / w.K.psi[0];
@@ -337,7 +340,7 @@ __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, Si
         const double Tw = weighted_T(m, w, w.K.cvals, S.kord, false, lane);
         if (lane == 0) a.tr_T[so + S.nsave] = Tw;
     }
-    if (a.tr_Y && S.nsave < a.n_save_max) {
+    if (EXT && a.tr_Y && S.nsave < a.n_save_max) {
         double* row = a.tr_Y + (so + S.nsave) * N;
 #pragma unroll 1
         for (int i = lane; i < N; i += LW) row[ref_index(m, i)] = interp_y(w, w.K.cvals, S.kord, i);
@@ -357,7 +360,7 @@ __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, Si
     S.tg_prev = tg;
     const double dt_step = S.t - S.tprev;
     S.tprev = S.t;
-    if (a.tab_n && dt_step < 1e-3 * a.o.reltol) {
+    if (EXT && a.tab_n && dt_step < 1e-3 * a.o.reltol) {
         // check_reinitialization! (checks.jl:341-364): value(run) is what the last residual evaluation
         // computed; a jump within the next reltol seconds restarts the DAE there
         const double t_new = S.t + a.o.reltol;
@@ -395,6 +398,7 @@ __device__ __forceinline__ void reinit_integration(const SimArgs& a, WarpWS& w, 
 }
 
 // exit_simulation! (model_evaluation.jl:335-382) + summary / state hand-back
+template <bool EXT>
 __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S, bool integrated, int lane) {
     const ModelDesc& m = a.m;
     const Ida& M = S.M;
@@ -422,7 +426,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
             double yf = yn;
             if (do_interp) { const double ypv = interp_y(w, w.K.cprev, S.kord, i); yf = fr * (yn - ypv) + ypv; }
             a.sY[(size_t)S.sys * N + ref_index(m, i)] = yf;
-            if (a.tr_Y && do_interp && S.nsave >= 1 && S.nsave - 1 < a.n_save_max) a.tr_Y[(so + S.nsave - 1) * N + ref_index(m, i)] = yf;
+            if (EXT && a.tr_Y && do_interp && S.nsave >= 1 && S.nsave - 1 < a.n_save_max) a.tr_Y[(so + S.nsave - 1) * N + ref_index(m, i)] = yf;
             if (a.sYP) a.sYP[(size_t)S.sys * N + ref_index(m, i)] = interp_yp(w, w.K.dvals, S.kord, i);
             if (i == iP0) ps0 = yf;
             if (i == iPN) psN = yf;
@@ -487,7 +491,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
 }
 
 // initialize_simulation! up to the first Newton-init evaluation (model_evaluation.jl:174-214)
-template <int CHEM>
+template <int CHEM, bool EXT>
 __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, const LaneRole& ro, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     int sys = 0;
@@ -499,7 +503,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
     setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
     S.rc.method = a.method;
     S.t_init = 0.0; S.reinit = 0; S.n_reinit = 0; S.scale = 1.0;
-    if (a.tab_n) {   // run_function: initial_current! evaluates the function at t = 0 (input_methods.jl:27-29, 64-74, 104-107)
+    if (EXT && a.tab_n) {   // run_function: initial_current! evaluates the function at t = 0 (input_methods.jl:27-29, 64-74, 104-107)
         S.scale = a.values ? a.values[sys] : 1.0;
         S.rc.value = S.scale * table_eval(a.tab_t, a.tab_v, a.tab_n, 0.0);
     } else S.rc.value = a.values ? a.values[sys] : a.value;
@@ -563,7 +567,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
             S.rc.value = 0.0; Ig = 0.0;
         } else if (S.rc.method == METHOD_I) Ig = S.rc.value;
         else if (S.rc.method == METHOD_V) {
-            if (!a.new_run && (a.tab_n || I_prev_state != 0.0)) Ig = I_prev_state;   // :40-52 / :64-74
+            if (!a.new_run && ((EXT && a.tab_n) || I_prev_state != 0.0)) Ig = I_prev_state;   // :40-52 / :64-74
             else Ig = S.rc.value > V0 ? 1.0 : -1.0;
         } else Ig = S.rc.value / (V0 * w.C.g[GC_I1C]);
         grp_sync();
@@ -581,6 +585,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
 }
 
 // after newtons_method!: rest of initialize_simulation! (model_evaluation.jl:216-231)
+template <bool EXT>
 __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     const int N = m.N_tot;
@@ -590,7 +595,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
         const double I0 = Y0[m.off_I];
         if (I0 != 0 && ((S.SOC >= a.b.SOC_max && I0 > 0) || (S.SOC <= a.b.SOC_min && I0 < 0))) {
             S.flag = FAIL_INIT_BOUNDS;
-            finish(a, w, S, false, lane);
+            finish<EXT>(a, w, S, false, lane);
             return;
         }
     }
@@ -602,7 +607,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
     S.ntstops = 0; S.itstop = 0;
     if (!a.new_run && 1.0 < a.tf) { S.tstop0 = 1.0; S.tstop1 = a.tf; S.ntstops = 2; }
     else { S.tstop0 = a.tf; S.tstop1 = a.tf; S.ntstops = 1; }
-    if (a.n_tstops) S.ntstops = a.n_tstops;
+    if (EXT && a.n_tstops) S.ntstops = a.n_tstops;
     grp_sync();
     if (lane == 0) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = 1.0; }   // y = phi0, yp = phi1 = YP0
     grp_sync();
@@ -619,7 +624,7 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
         const double Tw = weighted_T(m, w, w.K.cvals, 1, false, lane);
         if (lane == 0) a.tr_T[so + S.nsave] = Tw;
     }
-    if (a.tr_Y && S.nsave < a.n_save_max) {
+    if (EXT && a.tr_Y && S.nsave < a.n_save_max) {
         double* row = a.tr_Y + (so + S.nsave) * N;
 #pragma unroll 1
         for (int i = lane; i < N; i += LW) row[ref_index(m, i)] = Y0[i];
@@ -639,7 +644,9 @@ __device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, S
     S.pending = (S.flag == -1) ? PEND_BEGIN : PEND_FINISH;
 }
 
-template <int CHEM>
+// EXT: the run uses a tabulated input and/or keeps every saved state row (compiled out of the plain kernel,
+// whose instruction footprint is what bounds it)
+template <int CHEM, bool EXT>
 __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* smem_raw) {
     const int warp = grp_id(), lane = grp_lane();
     WarpWS w = make_ws(smem_raw, a.gws, warp);
@@ -655,8 +662,8 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
     S.state = ST_FETCH; S.pending = PEND_NONE; S.sys = 0;
     for (;;) {
         // ------------------------------ PRE: get to an evaluation point ---------------------------------
-        if (S.state == ST_FETCH) fetch_and_setup<CHEM>(a, w, ro, S, lane);
-        if (a.tab_n && S.state != ST_EXHAUSTED) {
+        if (S.state == ST_FETCH) fetch_and_setup<CHEM, EXT>(a, w, ro, S, lane);
+        if (EXT && a.tab_n && S.state != ST_EXHAUSTED) {
             // run.func(t) of this tick's evaluation: IDA evaluates F at the trial time tn; newtons_method! at its
             // t, except for the algebraic-derivative estimate, which passes dt itself as the time
             // (model_evaluation.jl:469).  Done here, before the lane vectors are live, to keep the call cheap.
@@ -789,9 +796,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 const bool bad = lsetup_bad || !(s == s) || isinf(s);
                 if (bad || (S.ni_iter >= 100 && !(sqrt(s) < a.o.reltol_init))) {
                     S.flag = FAIL_NEWTON_INIT; S.n_newton_init = FAIL_NEWTON_INIT;
-                    finish(a, w, S, false, lane);   // (also for a failed re-initialisation: the run is reported from its start)
+                    finish<EXT>(a, w, S, false, lane);   // (also for a failed re-initialisation: the run is reported from its start)
                 } else if (sqrt(s) < a.o.reltol_init) {
-                    if (!S.reinit) S.n_newton_init = S.ni_iter;
+                    if (!(EXT && S.reinit)) S.n_newton_init = S.ni_iter;
                     S.state = ST_INIT_RDIFF;
                 }
             } else if (S.state == ST_INIT_RDIFF) {
@@ -820,14 +827,14 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 start_now = true;
             }
             if (start_now) {
-                if (S.reinit) reinit_integration(a, w, S, lane);
-                else begin_integration(a, w, S, lane);
+                if (EXT && S.reinit) reinit_integration(a, w, S, lane);
+                else begin_integration<EXT>(a, w, S, lane);
             }
             // between evaluations: host loop of solve! until the next evaluation is needed
             while (S.pending != PEND_NONE) {
-                if (S.pending == PEND_RETURNED) { const int r = host_after_return(a, w, S, lane); S.pending = r == 1 ? PEND_BEGIN : (r == 0 ? PEND_FINISH : PEND_NONE); }
-                if (S.pending == PEND_BEGIN) S.pending = solve_begin(a, w, S, lane) ? PEND_NONE : PEND_RETURNED;
-                if (S.pending == PEND_FINISH) { finish(a, w, S, true, lane); S.pending = PEND_NONE; }
+                if (S.pending == PEND_RETURNED) { const int r = host_after_return<EXT>(a, w, S, lane); S.pending = r == 1 ? PEND_BEGIN : (r == 0 ? PEND_FINISH : PEND_NONE); }
+                if (S.pending == PEND_BEGIN) S.pending = solve_begin<EXT>(a, w, S, lane) ? PEND_NONE : PEND_RETURNED;
+                if (S.pending == PEND_FINISH) { finish<EXT>(a, w, S, true, lane); S.pending = PEND_NONE; }
             }
         }
     }

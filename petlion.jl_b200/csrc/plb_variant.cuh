@@ -495,7 +495,13 @@ __global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_simulate(const __g
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // persistent CTAs; every warp pulls systems from a global queue (step counts vary ~1.5x across
     // a batch) and all warps of the CTA tick in lockstep through the heavy phases (plb_tick.cuh)
-    simulate_cta<CHEM>(a, smem_raw);
+    simulate_cta<CHEM, false>(a, smem_raw);
+}
+// the same integrator with the optional features compiled in: tabulated inputs (run_function) and per-step state rows
+template <int CHEM>
+__global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_simulate_ext(const __grid_constant__ SimArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    simulate_cta<CHEM, true>(a, smem_raw);
 }
 
 // =================================================================================================
@@ -529,7 +535,10 @@ cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) { PLB_L
 cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_initguess, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_newton, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_linsolve, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
-cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_simulate, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
+cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s) {
+    if (a.tab_n || a.tr_Y) PLB_LAUNCH(k_simulate_ext, a, grid, SIM_WARPS * LW, SIM_SMEM, s);
+    PLB_LAUNCH(k_simulate, a, grid, SIM_WARPS * LW, SIM_SMEM, s);
+}
 
 }  // namespace PLB_NS
 }  // namespace plb
