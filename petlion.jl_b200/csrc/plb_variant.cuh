@@ -58,21 +58,27 @@ __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? j
 
 struct K1Warp {
     double S[K1_NSTAGE][LW];   // lane-computed Jacobian entries
+#if PLB_TH
     double MCs[NR * NR];       // particle stencil coefficients (contiguous with S: one value table)
+#else
+    double PB[2][NR * NR];     // the particle blocks D_s/Rp^2 * M - gamma*I of the two electrodes (contiguous with S)
+#endif
     WarpConst C;
 };
-constexpr size_t K1_SMEM = XCH_BYTES_PER_GROUP * K1_WARPS + sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX;
+constexpr size_t K1_MC_BYTES = TH ? 0 : sizeof(double) * NR * NR;   // CTA-shared copy of the stencil (non-thermal)
+constexpr size_t K1_SMEM = XCH_BYTES_PER_GROUP * K1_WARPS + sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX + K1_MC_BYTES;
 
 // K1: one warp evaluates F and the CSC values of dF/dY + gamma dF/dY' of one system at a time.
 // HBM traffic per system is exactly the algorithmic 8*(3N + n_theta + nnz) bytes: Y, Y', theta rows
 // are read once (lane-mapped, L1-coalesced), res and nzval rows are written once with lane-consecutive
 // 8-byte stores.  Most of nzval is the constant particle stencil scaled by D_s/Rp^2 (minus gamma on
-// the diagonal): those entries are produced in the coalesced, branch-free write loop from a recipe
-// table held in shared memory, never staged; only the lane-computed entries go through a
-// shared-memory stage.
-//   recipe bits: 0-15 index into the warp's value table (lane-computed: slot*32+lane; particle entries:
-//   K1_NSTAGE*32 + r*NR+c), 16 particle-block entry, 17 anode (isothermal: D_s per electrode),
-//   18 diagonal, 19-23 node (thermal: D_s(T) per node)
+// the diagonal).  Isothermal families: D_s is one number per electrode, so the two 10x10 blocks are staged once
+// per system (200 fma) and the write loop is a pure gather  nzval[p] = table[recipe[p]]  -- coalesced,
+// branch-free, ~5 instructions per 32 entries.  Thermal family: D_s(T) differs per node, the block entries are
+// formed in the write loop from the recipe's flag bits.
+//   recipe: index into the warp's value table (lane-computed: slot*LW+lane; particle entries:
+//   K1_NSTAGE*LW + electrode*NR*NR + r*NR+c); thermal: bits 0-15 index (K1_NSTAGE*32 + r*NR+c),
+//   16 particle-block entry, 18 diagonal, 19-23 node
 template <int CHEM>
 __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __grid_constant__ ResJacArgs a) {
     extern __shared__ __align__(16) unsigned char k1_raw0[];
@@ -80,10 +86,15 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
     K1Warp* ws = reinterpret_cast<K1Warp*>(k1_raw);
     int* src_s = reinterpret_cast<int*>(k1_raw + sizeof(K1Warp) * K1_WARPS);
     for (int i = threadIdx.x; i < a.nnz; i += blockDim.x) src_s[i] = a.src[i];
+#if PLB_TH
     {
         K1Warp& w0 = ws[grp_id()];
         for (int i = grp_lane(); i < NR * NR; i += LW) w0.MCs[i] = laws::MC[i / NR][i % NR];
     }
+#else
+    double* mc_s = reinterpret_cast<double*>(k1_raw + sizeof(K1Warp) * K1_WARPS + sizeof(int) * K1_SRC_MAX);
+    for (int i = threadIdx.x; i < NR * NR; i += blockDim.x) mc_s[i] = laws::MC[i / NR][i % NR];
+#endif
     __syncthreads();
     const int warp = grp_id(), lane = grp_lane();
     const ModelDesc& m = a.m;
@@ -186,6 +197,18 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
             w.S[k1_stage_slot(JS_CTRL_TX)][lane] = g * ctrl.gTx;
             w.S[k1_stage_slot(JS_CTRL_EPS)][lane] = ctrl.g_eta;
             w.S[k1_stage_slot(JS_CTRL_EPE)][lane] = -ctrl.g_eta;
+#if !PLB_TH
+            {   // the two particle blocks of this system
+                const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
+#pragma unroll
+                for (int i = lane; i < NR * NR; i += LW) {
+                    const double mc = mc_s[i];
+                    const double gd = (i % (NR + 1) == 0) ? g : 0.0;
+                    w.PB[0][i] = fma(kap_p, mc, -gd);
+                    w.PB[1][i] = fma(kap_n, mc, -gd);
+                }
+            }
+#endif
             grp_sync();
             const double* tab = &w.S[0][0];
             double* __restrict__ gN = a.nzval + (size_t)sys * a.nnz;
@@ -199,15 +222,8 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
                 gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
             }
 #else
-            const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
 #pragma unroll 4
-            for (int p = lane; p < a.nnz; p += LW) {
-                const int rc = src_s[p];
-                const double t = tab[rc & 0xffff];
-                const double kap = (rc & (1 << 17)) ? kap_n : kap_p;
-                const double gd = (rc & (1 << 18)) ? g : 0.0;
-                gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
-            }
+            for (int p = lane; p < a.nnz; p += LW) gN[p] = tab[src_s[p]];
 #endif
         }
         grp_sync();
@@ -338,7 +354,12 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
     if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {
         const int rr = (slot - JS_CS0) / NR, cc = (slot - JS_CS0) % NR;
         const int el = lane >= m.Np + m.Ns ? 1 : 0;
-        return (K1_NSTAGE * LW + rr * NR + cc) | (1 << 16) | (el << 17) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
+#if PLB_TH
+        (void)el;
+        return (K1_NSTAGE * LW + rr * NR + cc) | (1 << 16) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
+#else
+        return K1_NSTAGE * LW + el * NR * NR + rr * NR + cc;
+#endif
     }
     return k1_stage_slot(slot) * LW + lane;
 }
