@@ -221,7 +221,8 @@ constexpr int NEL = (VS + LW - 1) / LW;
 __device__ __forceinline__ void ewt_set(const ModelDesc& m, WarpWS& w, const Opts& o, int lane) {
     const double* p0 = w.v(V_PHI0);
     double* ew = w.v(V_EWT);
-    PLB_FOR_ELEMS(i, m.N_tot) ew[i] = 1.0 / (o.reltol * fabs(p0[i]) + o.abstol);
+    const double rt = o.reltol, at = o.abstol;
+    PLB_FOR_ELEMS(i, m.N_tot) ew[i] = 1.0 / (rt * fabs(p0[i]) + at);
     grp_sync();
 }
 
@@ -285,14 +286,15 @@ __device__ __forceinline__ void predict_pass(const ModelDesc& m, WarpWS& w, cons
     double* yp_ = w.v(V_YPRED);
     double* ypp_ = w.v(V_YPPRED);
     double* ee_ = w.v(V_EE);
+    const int kk = M.kk, ns = M.ns;     // the integrator state lives in shared memory: read it once
     PLB_FOR_ELEMS(i, m.N_tot) {
         double yv = 0.0, ypv = 0.0;
 #pragma unroll
         for (int j = 0; j < 6; j++) {
-            if (j <= M.kk) {
+            if (j <= kk) {
                 double* ph = w.v(V_PHI0 + j);
                 double p = ph[i];
-                if (j >= M.ns) { p *= be[j]; ph[i] = p; }
+                if (j >= ns) { p *= be[j]; ph[i] = p; }
                 yv += p;
                 if (j > 0) ypv = fma(ga[j], p, ypv);
             }
@@ -397,15 +399,19 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
         M.hh = hnew;
     }
     // phi updates: phi[kused+1] = ee ; phi[kused] += ee ; phi[j] += phi[j+1] (j = kused-1..0)
-    PLB_FOR_ELEMS(i, m.N_tot) {
-        const double e = ee[i];
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 5; j >= 0; j--) {
-            double* ph = w.v(V_PHI0 + j);
-            if (j == M.kused + 1 && M.kused < o.maxord) ph[i] = e;
-            if (j == M.kused) { acc = ph[i] + e; ph[i] = acc; }
-            else if (j < M.kused) { acc += ph[i]; ph[i] = acc; }
+    {
+        const int ku = M.kused;         // (shared-memory state: read once)
+        double* const pnew = (ku < o.maxord) ? w.v(V_PHI0 + ku + 1) : nullptr;
+        PLB_FOR_ELEMS(i, m.N_tot) {
+            const double e = ee[i];
+            if (pnew) pnew[i] = e;
+            double acc = e;
+#pragma unroll 1
+            for (int j = ku; j >= 0; j--) {
+                double* ph = w.v(V_PHI0 + j);
+                acc = ph[i] + acc;
+                ph[i] = acc;
+            }
         }
     }
     grp_sync();
