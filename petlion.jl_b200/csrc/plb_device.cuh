@@ -892,9 +892,10 @@ __device__ __forceinline__ void thomas_sweeps(int Nx, const LaneChain& ch, const
         double av[3];
         shfl_from_n<3>(yv, ch.pred, av);
         const double a0 = av[0], a1 = av[1], a2 = av[2];
-        y0 = r[0] - (Wm[0] * a0 + Wm[1] * a1 + Wm[2] * a2);
-        y1 = r[1] - (Wm[3] * a0 + Wm[4] * a1 + Wm[5] * a2);
-        y2 = r[2] - (Wm[6] * a0 + Wm[7] * a1 + Wm[8] * a2);
+        // three dependent fused multiply-adds per row: this recurrence is the serial spine of every solve
+        y0 = fma(-Wm[2], a2, fma(-Wm[1], a1, fma(-Wm[0], a0, r[0])));
+        y1 = fma(-Wm[5], a2, fma(-Wm[4], a1, fma(-Wm[3], a0, r[1])));
+        y2 = fma(-Wm[8], a2, fma(-Wm[7], a1, fma(-Wm[6], a0, r[2])));
     }
     {   // the meeting node takes both neighbours
         const int mid = Nx / 2;
@@ -923,9 +924,9 @@ __device__ __forceinline__ void thomas_sweeps(int Nx, const LaneChain& ch, const
         double av[3];
         shfl_from_n<3>(uv, ch.succ, av);
         const double a0 = av[0], a1 = av[1], a2 = av[2];
-        u0 = c0 - (p0 * a0 + p1 * a1 + p2 * a2);
-        u1 = c1 - (p3 * a0 + p4 * a1 + p5 * a2);
-        u2 = c2 - (p6 * a0 + p7 * a1 + p8 * a2);
+        u0 = fma(-p2, a2, fma(-p1, a1, fma(-p0, a0, c0)));
+        u1 = fma(-p5, a2, fma(-p4, a1, fma(-p3, a0, c1)));
+        u2 = fma(-p8, a2, fma(-p7, a1, fma(-p6, a0, c2)));
     }
     u[0] = u0; u[1] = u1; u[2] = u2;
 }
@@ -937,36 +938,30 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
                                                  WarpFactor& Fa, int lane) {
     // ---- 1. particle inverses -------------------------------------------------------------------
     if (!alg_only) {
-        // two 10x10 Gauss-Jordan inverses on the 32 lanes of the (first) warp: lanes 0-15 cathode, 16-31 anode
+        // The particle block is kap*M - cj*I with the constant stencil M = EV diag(EL) EVI (real spectrum,
+        // laws_generated.cuh), so its inverse is EV diag(1/(kap*EL_i - cj)) EVI: no elimination, no pivot rounds.
+        // Lanes 0-9 of the (first) warp form the ten columns of the cathode block, lanes 16-25 those of the anode.
         const double kap_p = shfl_from(J.kap, 0), kap_n = shfl_from(J.kap, m.Nx - 1);
         const double csj_p = shfl_from(J.cs_j, 0), csj_n = shfl_from(J.cs_j, m.Nx - 1);
         if (lane < 32) {
             const int el = lane >> 4;
-            const int l16 = lane & 15;
+            const int c = lane & 15, cc = c < NR ? c : 0;
             const double kap = el == 0 ? kap_p : kap_n;
-            for (int k = l16; k < NR * NR; k += 16) {
-                const int r = k / NR, c = k - r * NR;
-                Fa.Sinv[k][el] = kap * laws::MC[r][c] - (r == c ? cj : 0.0);
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int p = 0; p < NR; p++) {
-                const double piv = 1.0 / Fa.Sinv[p * NR + p][el];
-                __syncwarp();
-                if (l16 < NR && l16 != p) Fa.Sinv[p * NR + l16][el] *= piv;
-                __syncwarp();
-                for (int k = l16; k < NR * NR; k += 16) {
-                    const int r = k / NR, c = k - r * NR;
-                    if (r != p && c != p)
-                        Fa.Sinv[k][el] = fma(-Fa.Sinv[r * NR + p][el], Fa.Sinv[p * NR + c][el], Fa.Sinv[k][el]);
+            const double pd_own = 1.0 / (kap * laws::EL[cc] - cj);
+            double t[NR];
+#pragma unroll
+            for (int i = 0; i < NR; i++) t[i] = __shfl_sync(FULL, pd_own, (el << 4) + i) * laws::EVI[i][cc];
+            if (c < NR) {
+                const double csj = el == 0 ? csj_p : csj_n;
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NR; i++) acc = fma(laws::EV[r][i], t[i], acc);
+                    Fa.Sinv[r * NR + c][el] = acc;
+                    if (c == NR - 1) Fa.vb[r][el] = acc * csj;   // vb = Sinv * b,  b = cs_j * e_surf
                 }
-                __syncwarp();
-                if (l16 < NR) Fa.Sinv[l16 * NR + p][el] = (l16 == p) ? piv : -Fa.Sinv[l16 * NR + p][el] * piv;
-                __syncwarp();
             }
-            // vb = Sinv * b,  b = cs_j * e_surf
-            const double csj = el == 0 ? csj_p : csj_n;
-            if (l16 < NR) Fa.vb[l16][el] = Fa.Sinv[l16 * NR + NR - 1][el] * csj;
         }
         grp_sync();
     }
