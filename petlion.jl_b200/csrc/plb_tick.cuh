@@ -31,6 +31,9 @@ namespace PLB_NS {
 #ifndef PLB_TICK_SYNC_START
 #define PLB_TICK_SYNC_START 1     // the one barrier per tick that keeps a CTA's systems on one instruction stream
 #endif
+#ifndef PLB_TICK_SYNC_EVERY
+#define PLB_TICK_SYNC_EVERY 1     // barrier every n-th tick (A/B knob)
+#endif
 #ifndef PLB_TICK_VOTE_JAC
 #define PLB_TICK_VOTE_JAC 0       // CTA-wide vote "does any warp factorise in this tick?": 225 k with, 229 k without
 #endif
@@ -660,6 +663,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
     SimState S;
 #endif
     S.state = ST_FETCH; S.pending = PEND_NONE; S.sys = 0;
+#if PLB_TICK_SYNC_EVERY > 1
+    unsigned tick_no = 0;
+#endif
     for (;;) {
         // ------------------------------ PRE: get to an evaluation point ---------------------------------
         if (S.state == ST_FETCH) fetch_and_setup<CHEM, EXT>(a, w, ro, S, lane);
@@ -714,7 +720,11 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         }
         // ------------------------------ aligned heavy phases --------------------------------------------
 #if PLB_TICK_SYNC_START
+#if PLB_TICK_SYNC_EVERY > 1
+        if ((tick_no++ % PLB_TICK_SYNC_EVERY) == 0) { if (!__syncthreads_or(do_eval)) break; }
+#else
         if (!__syncthreads_or(do_eval)) break;
+#endif
 #else
         if (!do_eval) break;
 #endif
