@@ -87,10 +87,10 @@ class Model:
         sizes = [("c_e", Nx), ("c_s_avg", N.p * N.r_p + N.n * N.r_n)]
         if nm.temperature:
             sizes.append(("T", N.a + Nx + N.z))
-        if nm.aging == "SEI":
+        if nm.aging:
             sizes += [("film", N.n), ("SOH", 1)]
         sizes += [("j", N.p + N.n), ("Φ_e", Nx), ("Φ_s", N.p + N.n)]
-        if nm.aging == "SEI":
+        if nm.aging:
             sizes.append(("j_s", N.n))
         sizes.append(("I", 1))
         ind, k = {}, 0

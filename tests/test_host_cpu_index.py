@@ -1,0 +1,23 @@
+"""index_state of the host mirror (external.jl:275-365) for every model family, without a GPU"""
+import types
+
+import pytest
+
+from petlion_b200.api import Model
+
+
+@pytest.mark.parametrize("temperature,aging,grid,ntot", [(False, False, 10, 301), (True, False, 10, 351),
+                                                          (False, "SEI", 10, 322), (False, True, 20, 642),
+                                                          (False, False, 20, 601)])
+def test_index_state_covers_the_state_vector(temperature, aging, grid, ntot):
+    m = Model.__new__(Model)
+    m.N = types.SimpleNamespace(p=grid, s=grid, n=grid, a=10, z=10, r_p=10, r_n=10, tot=ntot)
+    m.numerics = types.SimpleNamespace(temperature=temperature, aging=aging)
+    ind = m._index_state()
+    assert ind["I"] == slice(ntot - 1, ntot)
+    assert ind["c_e"] == slice(0, 3 * grid)
+    assert ("T" in ind) == bool(temperature) and ("j_s" in ind) == bool(aging)
+    # App. A of SURVEY.md: differential block c_e, c_s_avg, T, film, SOH; algebraic block j, Phi_e, Phi_s, j_s, I
+    order = [k for k in ("c_e", "c_s_avg", "T", "film", "SOH", "j", "Φ_e", "Φ_s", "j_s", "I") if k in ind]
+    stops = [ind[k].stop for k in order]
+    assert stops == sorted(stops) and all(ind[a].stop == ind[b].start for a, b in zip(order[:-1], order[1:]))
