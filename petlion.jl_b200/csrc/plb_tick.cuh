@@ -31,6 +31,11 @@ namespace PLB_NS {
 #ifndef PLB_TICK_SYNC_START
 #define PLB_TICK_SYNC_START 1     // the one barrier per tick that keeps a CTA's systems on one instruction stream
 #endif
+// once-per-simulation code (fetch + parameter setup, first row, summary).  A/B knob: out of line (__noinline__) it
+// leaves the tick loop spill-free, but the calls put the workspace descriptors on the stack: 272 k vs 298 k sims/s
+#ifndef PLB_COLD
+#define PLB_COLD __forceinline__
+#endif
 #ifndef PLB_TICK_SYNC_EVERY
 #define PLB_TICK_SYNC_EVERY 1     // barrier every n-th tick (A/B knob)
 #endif
@@ -384,7 +389,7 @@ __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, Si
 }
 
 // IDAReInit(mem, t_new, Y, YP) after the re-initialisation's newtons_method! (checks.jl:358-361)
-__device__ __forceinline__ void reinit_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+__device__ PLB_COLD void reinit_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     for (int k = 2; k < 6; k++) {
 #pragma unroll 1
@@ -402,7 +407,7 @@ __device__ __forceinline__ void reinit_integration(const SimArgs& a, WarpWS& w, 
 
 // exit_simulation! (model_evaluation.jl:335-382) + summary / state hand-back
 template <bool EXT>
-__device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S, bool integrated, int lane) {
+__device__ PLB_COLD void finish(const SimArgs& a, WarpWS& w, SimState& S, bool integrated, int lane) {
     const ModelDesc& m = a.m;
     const Ida& M = S.M;
     const int N = m.N_tot;
@@ -495,7 +500,7 @@ __device__ __forceinline__ void finish(const SimArgs& a, WarpWS& w, SimState& S,
 
 // initialize_simulation! up to the first Newton-init evaluation (model_evaluation.jl:174-214)
 template <int CHEM, bool EXT>
-__device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, const LaneRole& ro, SimState& S, int lane) {
+__device__ PLB_COLD void fetch_and_setup(const SimArgs& a, WarpWS& w, const LaneRole& ro, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     int sys = 0;
     if (lane == 0) sys = atomicAdd(a.counter, 1);
@@ -589,7 +594,7 @@ __device__ __forceinline__ void fetch_and_setup(const SimArgs& a, WarpWS& w, con
 
 // after newtons_method!: rest of initialize_simulation! (model_evaluation.jl:216-231)
 template <bool EXT>
-__device__ __forceinline__ void begin_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
+__device__ PLB_COLD void begin_integration(const SimArgs& a, WarpWS& w, SimState& S, int lane) {
     const ModelDesc& m = a.m;
     const int N = m.N_tot;
     const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
