@@ -163,3 +163,33 @@ def test_table_argument_errors(P, lco):
         P.simulate(lco, 10, I=P.Table([0.0, 1.0, 1.0, 1.0], [1.0, 1.0, 2.0, 3.0]), SOC=0)
     with pytest.raises(ValueError, match="dT takes"):
         P.simulate(P.petlion("LCO", temperature=True), 10, dT=P.Table([0.0, 1.0], [0.0, 0.0]), SOC=0)
+
+
+@pytest.mark.parametrize("family", ["thermal", "sei", "wide"])
+def test_table_and_state_rows_in_the_other_families(P, family):
+    """the extended kernel (tabulated input + kept state rows) of every compiled family against the oracle"""
+    kw = dict(thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=dict(N_p=20, N_s=20, N_n=20))[family]
+    okw = dict(thermal=dict(temperature=True), sei=dict(aging=True), wide=dict(N_p=20, N_s=20, N_n=20))[family]
+    p = P.petlion("LCO", **kw)
+    m = O.make_model("LCO", **okw)
+    B = 6
+    tho = util.oracle_theta_batch(B, first=77)
+    util.set_theta_batch(p, util.product_theta_from_oracle(p, tho))
+    tab = ([0.0, 50.0, 50.0, 120.0], [1.0, 1.0, 2.0, 0.5])          # a jump, then a ramp down
+    sol = P.simulate(p, 120, I=P.Table(*tab), SOC=0.2, tdiscon=[50.0], outputs="all")
+    ref = O.simulate_batch(m, tho, O.make_run("I", tf=120, table=tab, tdiscon=[50.0]), O.default_opts(),
+                           O.default_bounds("LCO"), SOC0=0.2, n_save_max=512, nthreads=6)
+    assert np.all(ref["flag"] == 0)
+    s = sol.results[-1].summary
+    same = s["n_steps"] == ref["n_steps"]
+    assert np.mean(same) >= 0.6
+    np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=1e-6)
+    np.testing.assert_allclose(s["SOC_end"], ref["SOC_end"], rtol=1e-5)
+    np.testing.assert_allclose(s["I_end"], 0.5, rtol=1e-9)
+    for k in range(B):
+        n = sol.n_points[k]
+        ps = sol.states[k, :n, p.ind["Φ_s"]]
+        np.testing.assert_allclose(ps[:, 0] - ps[:, -1], sol.V[k, :n], rtol=1e-13)
+        np.testing.assert_array_equal(sol.states[k, :n, p.ind["I"]][:, 0], sol.I[k, :n])
+        np.testing.assert_array_equal(sol.states[k, n - 1], sol.Y[k])
+        assert np.all(np.isfinite(sol.states[k, :n]))
