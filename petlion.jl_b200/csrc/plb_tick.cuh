@@ -799,6 +799,9 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 }
             } else if (S.state == ST_INIT_ITER) {
                 // Y_new .-= factor \ res ; absolute 2-norm of the update (model_evaluation.jl:451-454)
+                // (Y is re-read from phi_0 here rather than kept live across the factorisation and the solve:
+                // 36+ registers less pressure on the tick's hot phases)
+                load_lane(m, ro, w.v(V_PHI0), y, Iy);
                 double s = 0.0;
                 if (ro.elec) { y.j -= res.j; y.ps -= res.ps; s += res.j * res.j + res.ps * res.ps; }
                 if (ro.act) { y.pe -= res.pe; s += res.pe * res.pe; }
