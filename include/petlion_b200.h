@@ -187,6 +187,11 @@ int plb_simulate_table(plb_handle h, int B, const double *theta, const plb_run *
                        int n_save_max, double *traj_t, double *traj_V, double *traj_I,
                        double *traj_SOC, double *traj_T, double *traj_Y, int *traj_n, int mem);
 
+/* p.opts.tstops (src/params.jl:272, "times when the DAE solver explicitly stops"; merged into the stop list by
+ * postfix_integrator!, model_evaluation.jl:291-293): local times of the run, applied to every later simulate call
+ * of this handle; n = 0 clears them.  HOST array. */
+int plb_set_tstops(plb_handle h, int n, const double *tstops);
+
 /* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI, 3 wide, 4 wide SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared
  * memory per CTA [B], workspace vector stride, Jacobian slots per lane}.  Needs no GPU. */

@@ -42,7 +42,7 @@ class Run(C.Structure):
                 ("input_kind", C.c_int), ("new_run", C.c_int), ("t0", C.c_double),
                 ("tab_n", C.c_int), ("tab_t", C.POINTER(C.c_double)), ("tab_v", C.POINTER(C.c_double)),
                 ("scale", C.c_double), ("n_tdiscon", C.c_int), ("tdiscon", C.POINTER(C.c_double)),
-                ("last_value", C.POINTER(C.c_double))]
+                ("last_value", C.POINTER(C.c_double)), ("n_tstops", C.c_int), ("tstops", C.POINTER(C.c_double))]
 
 
 class Opts(C.Structure):
@@ -142,10 +142,14 @@ INPUT = {"value": 0, "hold": 1, "rest": 2}
 
 
 def make_run(method="I", value=-1.0, tf=1e6, input_kind="value", new_run=True, t0=0.0, table=None,
-             tdiscon=(), scale=1.0):
+             tdiscon=(), scale=1.0, tstops=()):
     """table = (t_knots, v_knots): a run_function restricted to a piecewise-linear table (see orc_run)"""
     r = Run(METHOD[method], float(value), float(tf), INPUT[input_kind], int(new_run), float(t0))
     r.scale = float(scale)
+    if len(tstops):
+        ts = np.ascontiguousarray(tstops, dtype=np.float64)
+        r._keep_ts = ts
+        r.n_tstops = ts.size; r.tstops = _p(ts)
     if table is not None:
         tt = np.ascontiguousarray(table[0], dtype=np.float64)
         vv = np.ascontiguousarray(table[1], dtype=np.float64)

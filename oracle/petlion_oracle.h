@@ -93,6 +93,8 @@ typedef struct {
     int n_tdiscon;
     const double *tdiscon;
     double *last_value;
+    int n_tstops;            /* opts.tstops (params.jl:272): explicit stop times, local to the run */
+    const double *tstops;
 } orc_run;
 
 /* options_simulation: src/structures.jl:266-285, defaults src/params.jl:256-280 */

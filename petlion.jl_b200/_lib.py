@@ -84,7 +84,7 @@ SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", 
 EXPORTS = ["plb_last_error", "plb_create", "plb_destroy", "plb_set_stream", "plb_nstates", "plb_ndiff",
            "plb_ntheta", "plb_jac_nnz", "plb_theta_keys", "plb_theta_index", "plb_theta_defaults",
            "plb_bounds_defaults", "plb_opts_defaults", "plb_calc_I1C", "plb_jac_pattern",
-           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_variant_info", "plb_launch_count",
+           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_set_tstops", "plb_variant_info", "plb_launch_count",
            "plb_last_kernel_ms"]
 
 _lib = None
@@ -123,6 +123,7 @@ def lib():
         L.plb_simulate_table.argtypes = [vp, C.c_int, dp, C.POINTER(Run), C.POINTER(InputTable), dp, C.POINTER(Opts),
                                          C.POINTER(Bounds), dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, dp, vp,
                                          C.c_int]
+        L.plb_set_tstops.argtypes = [vp, C.c_int, dp]
         L.plb_launch_count.argtypes = [vp]
         L.plb_launch_count.restype = C.c_longlong
         L.plb_last_kernel_ms.argtypes = [vp]

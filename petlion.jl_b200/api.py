@@ -75,7 +75,7 @@ class Model:
         L.plb_opts_defaults(h, C.byref(o))
         self.opts = _NS(SOC=1.0, outputs=("t", "V"), abstol=o.abstol, reltol=o.reltol, maxiters=o.maxiters,
                         check_bounds=bool(o.check_bounds), interp_final=bool(o.interp_final), verbose=False,
-                        n_save_max=512, tdiscon=[], initialize_algebraic_derivatives=True)
+                        n_save_max=512, tstops=[], tdiscon=[], initialize_algebraic_derivatives=True)
 
     theta = property(lambda self: self.θ)
 
@@ -302,7 +302,7 @@ class Table:
 
 def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_init=None, reltol_init=None,
              maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, tdiscon=None,
-             initialize_algebraic_derivatives=None, outputs=None, **inputs):
+             initialize_algebraic_derivatives=None, outputs=None, tstops=None, **inputs):
     """simulate(p, tf; I=..|V=..|P=.., SOC, V_max, V_min, SOC_max, ...) -- model_evaluation.jl:10-86.
 
     Inputs may be numbers (scalar or per-system arrays), "hold" or "rest" (Julia :hold / :rest), or a
@@ -381,6 +381,8 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
         raise ValueError("cannot start keeping states in the middle of a solution")
     trY = np.full((B, ns, N), np.nan) if keep_states else None
     trn = np.zeros(B, dtype=np.int32)
+    ts = np.ascontiguousarray(p.opts.tstops if tstops is None else tstops, dtype=np.float64)
+    _lib.check(L.plb_set_tstops(p._h, ts.size, ts.ctypes.data if ts.size else None))
     tail = (C.byref(o), C.byref(bounds), None if soc0 is None else soc0.ctypes.data,
             sY.ctypes.data, sYP.ctypes.data, sSOC.ctypes.data, st.ctypes.data,
             summ.ctypes.data, ns, tr["t"].ctypes.data if ns else None,

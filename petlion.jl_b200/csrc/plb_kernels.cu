@@ -120,6 +120,7 @@ struct plb_handle_s {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
+    std::vector<double> opt_tstops;       // p.opts.tstops (params.jl:272): applied to every simulate call
     float last_ms = 0.f;
     int num_sms = 0;
     // device staging buffers of PLB_MEM_HOST calls: grow-only, reused from call to call (a cudaMalloc /
@@ -501,6 +502,23 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     std::vector<double> tstops;
     const double *tab_t = nullptr, *tab_v = nullptr, *d_tstops = nullptr;
     if (tab) {
+        if (tab->n_tdiscon < 0 || (tab->n_tdiscon > 0 && !tab->tdiscon)) return fail("plb_simulate_table: bad tdiscon");
+        for (int k = 1; k < tab->n_tdiscon; k++)
+            if (tab->tdiscon[k] < tab->tdiscon[k - 1]) return fail("plb_simulate_table: tdiscon must be ascending");
+    }
+    if (tab || !h->opt_tstops.empty()) {
+        // sort([opts.tstops; tdiscon .- reltol/2; 1.0 if continuing; tf]) without the entries <= 0 (and those >= tf)
+        for (double ts : h->opt_tstops) if (ts > 0.0 && ts < run->tf) tstops.push_back(ts);
+        for (int k = 0; tab && k < tab->n_tdiscon; k++) {
+            const double ts = tab->tdiscon[k] - opts->reltol / 2;
+            if (ts > 0.0 && ts < run->tf) tstops.push_back(ts);
+        }
+        if (!run->new_run && 1.0 < run->tf) tstops.push_back(1.0);
+        std::sort(tstops.begin(), tstops.end());
+        tstops.push_back(run->tf);
+        d_tstops = tstops.data();
+    }
+    if (tab) {
         if (run->input_kind != PLB_INPUT_VALUE) return fail("plb_simulate_table: a table input cannot be :hold or :rest");
         if (run->method == PLB_METHOD_DT) return fail("plb_simulate_table: dT takes a number or :hold");
         if (tab->n < 1 || !tab->t || !tab->v) return fail("plb_simulate_table: empty table");
@@ -509,17 +527,7 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
             if (k && tab->t[k] < tab->t[k - 1]) return fail("plb_simulate_table: knot times must be non-decreasing");
             if (k >= 2 && tab->t[k] == tab->t[k - 2]) return fail("plb_simulate_table: more than two knots at one time");
         }
-        if (tab->n_tdiscon < 0 || (tab->n_tdiscon > 0 && !tab->tdiscon)) return fail("plb_simulate_table: bad tdiscon");
-        bool used1 = run->new_run || !(1.0 < run->tf);
-        for (int k = 0; k < tab->n_tdiscon; k++) {
-            if (k && tab->tdiscon[k] < tab->tdiscon[k - 1]) return fail("plb_simulate_table: tdiscon must be ascending");
-            const double ts = tab->tdiscon[k] - opts->reltol / 2;
-            if (!used1 && 1.0 <= ts) { tstops.push_back(1.0); used1 = true; }
-            if (ts > 0.0 && ts < run->tf) tstops.push_back(ts);
-        }
-        if (!used1) tstops.push_back(1.0);
-        tstops.push_back(run->tf);
-        tab_t = tab->t; tab_v = tab->v; d_tstops = tstops.data();
+        tab_t = tab->t; tab_v = tab->v;
     }
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
@@ -538,8 +546,8 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
         stage_inout(b[10], tr_I, htI, BS, mem, false, s) || stage_inout(b[11], tr_SOC, htS, BS, mem, false, s) ||
         stage_inout(b[12], tr_n, htn, (size_t)B, mem, false, s) ||
         stage_inout(b[13], tr_T, htT, BS, mem, false, s) || stage_inout(b[17], tr_Y, htY, BS * m.N_tot, mem, false, s)) return -1;
-    if (tab && (stage_in(b[14], tab_t, (size_t)tab->n, PLB_MEM_HOST, s) || stage_in(b[15], tab_v, (size_t)tab->n, PLB_MEM_HOST, s) ||
-                stage_in(b[16], d_tstops, tstops.size(), PLB_MEM_HOST, s))) return -1;
+    if (tab && (stage_in(b[14], tab_t, (size_t)tab->n, PLB_MEM_HOST, s) || stage_in(b[15], tab_v, (size_t)tab->n, PLB_MEM_HOST, s))) return -1;
+    if (d_tstops && stage_in(b[16], d_tstops, tstops.size(), PLB_MEM_HOST, s)) return -1;
     SimArgs a;
     memset(&a, 0, sizeof a);
     a.m = m; a.B = B; a.theta = theta; a.values = values; a.method = run->method; a.value = run->value;
@@ -551,7 +559,8 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     a.tr_t = tr_t; a.tr_V = tr_V; a.tr_I = tr_I; a.tr_SOC = tr_SOC; a.tr_T = tr_T; a.tr_Y = tr_Y; a.tr_n = tr_n;
     a.counter = h->d_counter;
     a.gws = h->d_gws;
-    if (tab) { a.tab_n = tab->n; a.tab_t = tab_t; a.tab_v = tab_v; a.n_tstops = (int)tstops.size(); a.tstops = d_tstops; }
+    if (tab) { a.tab_n = tab->n; a.tab_t = tab_t; a.tab_v = tab_v; }
+    if (d_tstops) { a.n_tstops = (int)tstops.size(); a.tstops = d_tstops; }
     CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
     const int grid = std::min((B + h->vi.sim_warps - 1) / h->vi.sim_warps, h->sim_grid);
     CUDA_OK(cudaEventRecord(h->ev0, s));
@@ -582,4 +591,11 @@ int plb_simulate_table(plb_handle h, int B, const double* theta, const plb_run* 
     if (!table) return fail("plb_simulate_table: null table");
     return simulate_impl(h, B, theta, run, table, scale, opts, bounds, soc0, sY, sYP, sSOC, st, summary, n_save_max,
                          tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_Y, tr_n, mem);
+}
+
+int plb_set_tstops(plb_handle h, int n, const double* tstops) {
+    if (n < 0 || (n > 0 && !tstops)) return fail("plb_set_tstops: bad arguments");
+    for (int k = 0; k < n; k++) if (!std::isfinite(tstops[k])) return fail("plb_set_tstops: non-finite stop time");
+    h->opt_tstops.assign(tstops, tstops + n);
+    return 0;
 }

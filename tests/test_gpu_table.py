@@ -193,3 +193,33 @@ def test_table_and_state_rows_in_the_other_families(P, family):
         np.testing.assert_array_equal(sol.states[k, :n, p.ind["I"]][:, 0], sol.I[k, :n])
         np.testing.assert_array_equal(sol.states[k, n - 1], sol.Y[k])
         assert np.all(np.isfinite(sol.states[k, :n]))
+
+
+def test_user_stop_times(P, lco):
+    """opts.tstops (params.jl:272): the integrator lands exactly on the requested times; on a continuation they
+    merge with the stop at t = 1 (model_evaluation.jl:288-310)"""
+    m = O.make_model("LCO")
+    B = 10
+    tho = util.oracle_theta_batch(B, first=11)
+    util.set_theta_batch(lco, util.product_theta_from_oracle(lco, tho))
+    ts = [0.5, 100.0, 250.5, 5000.0]
+    sol = P.simulate(lco, 1000, I=-1, SOC=1, tstops=ts)
+    ref = O.simulate_batch(m, tho, O.make_run("I", -1.0, tf=1000, tstops=ts), O.default_opts(), O.default_bounds("LCO"),
+                           SOC0=1.0, n_save_max=512, nthreads=8)
+    _compare_runs(sol, ref, min_identical=0.9)
+    for k in range(B):
+        t = sol.t[k, :sol.n_points[k]]
+        assert all(np.any(t == x) for x in (0.5, 100.0, 250.5)) and t[-1] == 1000.0
+    P.simulate_(sol, lco, 300, I=1, tstops=[0.25, 40.0])
+    ref2 = O.simulate_batch(m, tho, O.make_run("I", 1.0, tf=300, tstops=[0.25, 40.0], new_run=False), O.default_opts(),
+                            O.default_bounds("LCO"), state=ref["state"], n_save_max=512, nthreads=8)
+    s2 = sol.results[-1].summary
+    same = s2["n_steps"] == ref2["n_steps"]
+    assert np.mean(same) >= 0.8
+    np.testing.assert_allclose(s2["V_end"][same], ref2["V_end"][same], rtol=1e-6)
+    for k in range(B):
+        t = sol.t[k, :sol.n_points[k]] - 1000.0
+        assert all(np.any(np.abs(t - x) < 1e-9) for x in (0.25, 1.0, 40.0))
+    # the stop list is a model option: cleared again for the following runs
+    a = P.simulate(lco, 500, I=-1, SOC=1)
+    assert not np.any(a.t[0, :a.n_points[0]] == 100.0)

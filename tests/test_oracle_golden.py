@@ -344,3 +344,16 @@ def test_function_input_current_version(goldens):
             run = O.make_run("I", tf=100, table=([0.0, 100.0], [0.0, 100.0 * g["ramp_val"]]))
         r = O.simulate_batch(m, th, run, O.default_opts(), O.default_bounds("LCO"), SOC0=0.0)
         assert abs(r["V_end"][0] - g["V"]) < tol and abs(r["SOC_end"][0] - g["SOC"]) < 5e-5
+
+
+def test_user_stop_times_merge_like_postfix_integrator():
+    """tstops = sort([opts.tstops; tdiscon .- reltol/2; 1.0 if continuing; tf]) (model_evaluation.jl:288-310)"""
+    m = O.make_model("LCO"); th = O.theta_defaults("LCO")
+    r = O.simulate_batch(m, th, O.make_run("I", -1.0, tf=1000, tstops=[250.5, 100.0, 2000.0, -3.0]), O.default_opts(),
+                         O.default_bounds("LCO"), SOC0=1.0, n_save_max=400)
+    t = r["traj"]["t"][0, :r["traj_n"][0]]
+    assert np.any(t == 100.0) and np.any(t == 250.5) and t[-1] == 1000.0 and r["flag"][0] == 0
+    r2 = O.simulate_batch(m, th, O.make_run("I", 1.0, tf=300, tstops=[0.25, 40.0], new_run=False), O.default_opts(),
+                          O.default_bounds("LCO"), state=r["state"], n_save_max=400)
+    t2 = r2["traj"]["t"][0, :r2["traj_n"][0]] - 1000.0
+    assert all(np.any(np.abs(t2 - x) < 1e-9) for x in (0.25, 1.0, 40.0))
