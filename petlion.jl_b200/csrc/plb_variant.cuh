@@ -48,6 +48,9 @@ enum JacSlot {
     JS_COUNT
 };
 
+#ifndef PLB_K1_UNROLL
+#define PLB_K1_UNROLL 8      // independent recipe -> value -> store chains in flight in the write loop
+#endif
 #ifndef PLB_K1_CTAS
 #define PLB_K1_CTAS (PLB_WIDE ? 1 : (PLB_TH ? 2 : 3))
 #endif
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
                 gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
             }
 #else
-#pragma unroll 4
+            _Pragma(PLB_STR(unroll PLB_K1_UNROLL))
             for (int p = lane; p < a.nnz; p += LW) gN[p] = tab[src_s[p]];
 #endif
         }
