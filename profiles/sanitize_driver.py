@@ -1,0 +1,23 @@
+"""Small runs of every kernel family for compute-sanitizer (memcheck / racecheck): plain and extended integrator,
+K1, Newton init, linear solve.   compute-sanitizer --tool memcheck python profiles/sanitize_driver.py"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import petlion_b200 as P
+
+fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide").split(",")
+for fam in fams:
+    kw = dict(iso={}, thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=dict(N_p=20, N_s=20, N_n=20))[fam]
+    p = P.petlion("LCO", **kw)
+    B = 5
+    p.θ["D_sp"] = np.asarray(p.θ["D_sp"]) * np.linspace(0.8, 1.2, B)
+    sol = P.simulate(p, 200, I=1, SOC=0.1)                                             # plain kernel
+    P.simulate_(sol, p, 100, V="hold")
+    tab = P.Table([0.0, 30.0, 30.0, 60.0], [1.0, 1.0, 2.0, 0.5])
+    sol2 = P.simulate(p, 60, I=tab, SOC=0.2, outputs="all", tstops=[10.0])              # extended kernel
+    Y0 = p.initial_guess(np.full(B, 0.5))
+    st, Y, YP = p.newton_init(Y0, method="I", value=1.0)
+    res, nz = p.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)
+    x, ok = p.linear_solve(Y, YP, np.full(B, 0.1), res, method="I", value=1.0)
+    print(fam, "ok", sol.results[-1].summary["flag"], sol2.results[-1].summary["n_steps"], int(np.isfinite(x).all()), flush=True)
