@@ -146,6 +146,7 @@ __device__ __forceinline__ int nls_post(const ModelDesc& m, WarpWS& w, const Lan
         if (lane == 0) s = fma(d.soh * ewt.soh, d.soh * ewt.soh, s);
     }
     eeI += dI;
+    grp_sync();   // every lane has read the I slot of EE (load_lane) before lane 0 rewrites it (two-warp groups)
     store_lane(m, ro, w.v(V_EE), ee, eeI, lane);
     grp_sync();
     const double delnrm = sqrt((warp_sum(s) + (dI * ewtI) * (dI * ewtI)) / m.N_tot);
@@ -840,6 +841,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 load_lane(m, ro, w.v(V_PHI1), ypo, pI);
                 ypo.j = -res.j / S.dt_init; ypo.pe = -res.pe / S.dt_init; ypo.ps = -res.ps / S.dt_init;
                 if (SEI) ypo.js = -res.js / S.dt_init;
+                grp_sync();   // (as above: the I slot of phi_1 is read by every lane, written by lane 0)
                 store_lane(m, ro, w.v(V_PHI1), ypo, -dI / S.dt_init, lane);
                 grp_sync();
                 start_now = true;
