@@ -21,3 +21,22 @@ def test_index_state_covers_the_state_vector(temperature, aging, grid, ntot):
     order = [k for k in ("c_e", "c_s_avg", "T", "film", "SOH", "j", "Φ_e", "Φ_s", "j_s", "I") if k in ind]
     stops = [ind[k].stop for k in order]
     assert stops == sorted(stops) and all(ind[a].stop == ind[b].start for a, b in zip(order[:-1], order[1:]))
+
+
+def test_table_host_semantics_match_the_oracle_table():
+    """petlion_b200.Table (host side of plb_input_table) evaluates like the oracle's table: right-continuous at a
+    repeated knot, linear between knots, constant outside"""
+    import numpy as np
+    import oracle as O
+    from petlion_b200 import Table
+    t = Table([0.0, 100.0, 100.0, 200.0], [1.0, 1.0, 0.5, 0.25])
+    assert t.jumps() == [100.0]
+    for x in (-1.0, 0.0, 50.0, 99.999999, 100.0, 100.000001, 150.0, 200.0, 1e6):
+        assert t(x) == O.table_eval((t.t, t.v), x)
+    assert t(100.0) == 0.5 and t(99.0) == 1.0
+    s = Table.sample(lambda x: 2.0 * x, np.linspace(0.0, 1.0, 5), scale=3.0)
+    assert s(0.3) == pytest.approx(0.6) and s.scale == 3.0
+    with pytest.raises(ValueError):
+        Table([0.0, 1.0], [1.0])
+    with pytest.raises(ValueError):
+        Table([1.0, 0.0], [1.0, 1.0])
