@@ -36,6 +36,9 @@ namespace PLB_NS {
 #ifndef PLB_COLD
 #define PLB_COLD __forceinline__
 #endif
+#ifndef PLB_TICK_OUTLINE
+#define PLB_TICK_OUTLINE 0        // residual / factorisation / solve as out-of-line calls inside the tick (A/B knob)
+#endif
 #ifndef PLB_TICK_SYNC_EVERY
 #define PLB_TICK_SYNC_EVERY 1     // barrier every n-th tick (A/B knob)
 #endif
@@ -747,8 +750,13 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             // its bits) never depends on which other systems share the CTA
             // the dT control row takes its newtons_method! form during the algebraic initialisation
             const int meth = (alg_only && S.rc.method == METHOD_DT) ? METHOD_DT_ALG : S.rc.method;
+#if PLB_TICK_OUTLINE
+            if (need_jac) lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
+            else lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
+#else
             if (need_jac) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
             else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
+#endif
             S.M.nre++;
         }
         bool lsetup_bad = false;
@@ -757,7 +765,11 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             __syncthreads();
 #endif
             if (do_eval && need_jac) {
+#if PLB_TICK_OUTLINE
+                warp_factor(m, ro, J, ctrl, alg_only ? 0.0 : S.M.cj, alg_only, w.Fa, lane);
+#else
                 warp_factor_impl(m, ro, J, ctrl, alg_only ? 0.0 : S.M.cj, alg_only, w.Fa, lane);
+#endif
                 S.M.nje++;
                 const double chk = w.Fa.schur_inv;
                 lsetup_bad = !(chk == chk) || isinf(chk);
@@ -776,7 +788,11 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
 #pragma unroll
                 for (int r = 0; r < NR; r++) res.cs[r] = -res.cs[r];
             }
+#if PLB_TICK_OUTLINE
+            dI = warp_solve(m, ro, w.Fa, alg_only, res, gI, lane);
+#else
             dI = warp_solve_impl(m, ro, w.Fa, alg_only, res, gI, lane);
+#endif
         }
         // ------------------------------ POST: per-state glue --------------------------------------------
         __syncwarp();
