@@ -39,7 +39,7 @@ constexpr int NGLOBAL = PLB_NGLOBAL;
 constexpr int NSHARED = V_COUNT - NGLOBAL;
 constexpr int GL_FIRST = 6 - NGLOBAL;   // ids [GL_FIRST, 6) are global
 
-struct WarpSmem {
+struct alignas(16) WarpSmem {
     double svec[NSHARED > 0 ? NSHARED : 1][VS];
     WarpConst C;
     WarpFactor Fa;
@@ -217,12 +217,32 @@ constexpr int NEL = (VS + LW - 1) / LW;
 #define PLB_STR_(x) #x
 #define PLB_STR(x) PLB_STR_(x)
 #define PLB_FOR_ELEMS(i, N) _Pragma(PLB_STR(unroll PLB_ELEM_UNROLL)) for (int i = lane; i < (N); i += LW)
+// the hot passes (weights, predictor, error norms, phi update) move two components per 128-bit shared-memory
+// access: pair q = elements 2q, 2q+1.  For odd N the last pair reaches into the padding of the vectors (VS >= N+1),
+// which the integrator zeroes once per launch and which stays zero (its weight is forced to zero).
+#ifndef PLB_VEC2
+#define PLB_VEC2 1
+#endif
+static_assert(VS % 2 == 0 && (VS * sizeof(double)) % 16 == 0, "vector stride must keep 16-byte alignment");
+#define PLB_FOR_PAIRS(q, N) _Pragma(PLB_STR(unroll PLB_ELEM_UNROLL)) for (int q = lane; q < ((N) + 1) / 2; q += LW)
+__device__ __forceinline__ double2 ld2(const double* v, int q) { return reinterpret_cast<const double2*>(v)[q]; }
+__device__ __forceinline__ void st2(double* v, int q, double2 x) { reinterpret_cast<double2*>(v)[q] = x; }
 
 __device__ __forceinline__ void ewt_set(const ModelDesc& m, WarpWS& w, const Opts& o, int lane) {
     const double* p0 = w.v(V_PHI0);
     double* ew = w.v(V_EWT);
     const double rt = o.reltol, at = o.abstol;
+#if PLB_VEC2
+    PLB_FOR_PAIRS(q, m.N_tot) {
+        const double2 p = ld2(p0, q);
+        double2 e;
+        e.x = 1.0 / (rt * fabs(p.x) + at);
+        e.y = (2 * q + 1 < m.N_tot) ? 1.0 / (rt * fabs(p.y) + at) : 0.0;
+        st2(ew, q, e);
+    }
+#else
     PLB_FOR_ELEMS(i, m.N_tot) ew[i] = 1.0 / (rt * fabs(p0[i]) + at);
+#endif
     grp_sync();
 }
 
@@ -287,6 +307,22 @@ __device__ __forceinline__ void predict_pass(const ModelDesc& m, WarpWS& w, cons
     double* ypp_ = w.v(V_YPPRED);
     double* ee_ = w.v(V_EE);
     const int kk = M.kk, ns = M.ns;     // the integrator state lives in shared memory: read it once
+#if PLB_VEC2
+    PLB_FOR_PAIRS(q, m.N_tot) {
+        double2 yv = make_double2(0.0, 0.0), ypv = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            if (j <= kk) {
+                double* ph = w.v(V_PHI0 + j);
+                double2 p = ld2(ph, q);
+                if (j >= ns) { p.x *= be[j]; p.y *= be[j]; st2(ph, q, p); }
+                yv.x += p.x; yv.y += p.y;
+                if (j > 0) { ypv.x = fma(ga[j], p.x, ypv.x); ypv.y = fma(ga[j], p.y, ypv.y); }
+            }
+        }
+        st2(yp_, q, yv); st2(ypp_, q, ypv); st2(ee_, q, make_double2(0.0, 0.0));
+    }
+#else
     PLB_FOR_ELEMS(i, m.N_tot) {
         double yv = 0.0, ypv = 0.0;
 #pragma unroll
@@ -301,6 +337,7 @@ __device__ __forceinline__ void predict_pass(const ModelDesc& m, WarpWS& w, cons
         }
         yp_[i] = yv; ypp_[i] = ypv; ee_[i] = 0.0;
     }
+#endif
     grp_sync();
 }
 
@@ -312,12 +349,25 @@ __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Id
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     const double* pk = w.v(V_PHI0 + M.kk);
     const double* pk1 = w.v(V_PHI0 + (M.kk > 0 ? M.kk - 1 : 0));
+#if PLB_VEC2
+    PLB_FOR_PAIRS(q, m.N_tot) {
+        const double2 e = ld2(ee, q), wt = ld2(ewt, q), k0 = ld2(pk, q), k1 = ld2(pk1, q);
+        const double ax = e.x * wt.x, ay = e.y * wt.y;
+        s0 = fma(ax, ax, s0); s0 = fma(ay, ay, s0);
+        const double d1x = k0.x + e.x, d1y = k0.y + e.y;
+        const double bx = d1x * wt.x, by = d1y * wt.y;
+        s1 = fma(bx, bx, s1); s1 = fma(by, by, s1);
+        const double cx = (d1x + k1.x) * wt.x, cy = (d1y + k1.y) * wt.y;
+        s2 = fma(cx, cx, s2); s2 = fma(cy, cy, s2);
+    }
+#else
     PLB_FOR_ELEMS(i, m.N_tot) {
         const double e = ee[i], wt = ewt[i];
         const double a = e * wt; s0 = fma(a, a, s0);
         const double d1 = (pk[i] + e); const double b = d1 * wt; s1 = fma(b, b, s1);
         const double d2 = (d1 + pk1[i]); const double c = d2 * wt; s2 = fma(c, c, s2);
     }
+#endif
     const double enorm_k = sqrt(warp_sum(s0) / m.N_tot);
     err_k = K.sigma[M.kk] * enorm_k;
     const double terr_k = (M.kk + 1) * err_k;
@@ -402,6 +452,20 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
     {
         const int ku = M.kused;         // (shared-memory state: read once)
         double* const pnew = (ku < o.maxord) ? w.v(V_PHI0 + ku + 1) : nullptr;
+#if PLB_VEC2
+        PLB_FOR_PAIRS(q, m.N_tot) {
+            const double2 e = ld2(ee, q);
+            if (pnew) st2(pnew, q, e);
+            double2 acc = e;
+#pragma unroll 1
+            for (int j = ku; j >= 0; j--) {
+                double* ph = w.v(V_PHI0 + j);
+                const double2 p = ld2(ph, q);
+                acc.x = p.x + acc.x; acc.y = p.y + acc.y;
+                st2(ph, q, acc);
+            }
+        }
+#else
         PLB_FOR_ELEMS(i, m.N_tot) {
             const double e = ee[i];
             if (pnew) pnew[i] = e;
@@ -413,6 +477,7 @@ __device__ __forceinline__ void ida_complete_step(const ModelDesc& m, WarpWS& w,
                 ph[i] = acc;
             }
         }
+#endif
     }
     grp_sync();
 }

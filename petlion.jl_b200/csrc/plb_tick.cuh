@@ -672,6 +672,14 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
     SimState S;
 #endif
     S.state = ST_FETCH; S.pending = PEND_NONE; S.sys = 0;
+#if PLB_VEC2
+    // the paired passes reach one component into the padding of the vectors when N is odd: zero it once
+    for (int k = 0; k < V_COUNT; k++) {
+#pragma unroll 1
+        for (int i = m.N_tot + lane; i < VS; i += LW) w.v(k)[i] = 0.0;
+    }
+    grp_sync();
+#endif
 #if PLB_TICK_SYNC_EVERY > 1
     unsigned tick_no = 0;
 #endif
