@@ -193,7 +193,11 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     CUDA_OK(cudaSetDevice(d->device));
     plb_handle_s* h = new plb_handle_s();
     h->desc = *d;
-    h->v = d->temperature ? &V_TH : (Nx_ > 32 ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
+    // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
+    // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
+    const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
+    const bool wide = Nx_ > 32 || (!d->temperature && Ntot_ > (d->aging ? V_SEI : V_ISO).info().vs);
+    h->v = d->temperature ? &V_TH : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
     h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
     ModelDesc& m = h->m;
