@@ -40,3 +40,28 @@ def test_table_host_semantics_match_the_oracle_table():
         Table([0.0, 1.0], [1.0])
     with pytest.raises(ValueError):
         Table([1.0, 0.0], [1.0, 1.0])
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(temperature=True, aging="SEI"), "not built yet"),
+    (dict(N_r_p=12), "N_r_p = N_r_n = 10"),
+    (dict(N_p=30, N_s=10, N_n=30), "<= 64"),
+    (dict(N_p=1), "2 <= N_p"),
+    (dict(temperature=True, N_p=20, N_s=10, N_n=20), "more than 32 x-nodes"),
+    (dict(temperature=True, N_p=4), "N_p, N_n >= 5"),
+    (dict(temperature=True, N_a=20, N_z=20), "N_a\\+N_z <="),
+])
+def test_unsupported_model_options_are_refused_with_a_message(kw, msg):
+    """plb_create validates the model description before it touches the device: every unsupported option set of
+    SURVEY section 8 is an error with a message, never a silent fallback"""
+    import petlion_b200
+    with pytest.raises(RuntimeError, match=msg):
+        petlion_b200.petlion("LCO", **kw)
+
+
+def test_nmc_has_no_thermal_or_aging_parameters():
+    import petlion_b200
+    with pytest.raises(RuntimeError, match="LCO parameter set"):
+        petlion_b200.petlion("NMC", temperature=True)
+    with pytest.raises(RuntimeError, match="LCO parameter set"):
+        petlion_b200.petlion("NMC", aging="SEI")
