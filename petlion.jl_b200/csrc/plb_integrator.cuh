@@ -58,15 +58,36 @@ struct WarpWS {
     }
 };
 
-// internal vector layout: c_e[Nx] | c_s radial-major [NR][Ne] | [T: a|p|s|n|z] | j[Ne] | Phi_e[Nx] | Phi_s[Ne] | I
-// (the reference layout is particle-major for c_s; radial-major makes lane accesses conflict-free)
+// internal vector layout: c_e[Nx] | c_s | [T: a|p|s|n|z] | j[Ne] | Phi_e[Nx] | Phi_s[Ne] | I
+// PLB_CS_PMAJOR = 1: c_s particle-major [Ne][NR] -- the reference's own order, so the state I/O is the identity map,
+//   and a lane moves its ten radial values with five 128-bit accesses (conflict-free per quarter-warp: lane stride
+//   80 bytes); falls back to 64-bit accesses when N_x is odd (the block then starts on an odd word).
+// PLB_CS_PMAJOR = 0: radial-major [NR][Ne] (64-bit accesses, conflict-free)
+#ifndef PLB_CS_PMAJOR
+#define PLB_CS_PMAJOR 1
+#endif
+static_assert(NR % 2 == 0, "paired particle accesses");
 __device__ __forceinline__ void load_lane(const ModelDesc& m, const LaneRole& ro, const double* v,
                                           LaneVec& y, double& I) {
     y.ce = ro.act ? v[ro.x] : 0.0;
     y.pe = ro.act ? v[m.off_pe + ro.x] : 0.0;
     if (ro.elec) {
+#if PLB_CS_PMAJOR
+        const double* pc = v + m.off_cs + ro.e * NR;
+        if ((m.off_cs & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) {
+                const double2 t = reinterpret_cast<const double2*>(pc)[k];
+                y.cs[2 * k] = t.x; y.cs[2 * k + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) y.cs[r] = pc[r];
+        }
+#else
 #pragma unroll
         for (int r = 0; r < NR; r++) y.cs[r] = v[m.off_cs + r * m.Ne + ro.e];
+#endif
         y.j = v[m.off_j + ro.e];
         y.ps = v[m.off_ps + ro.e];
     } else {
@@ -90,8 +111,19 @@ __device__ __forceinline__ void store_lane(const ModelDesc& m, const LaneRole& r
                                            const LaneVec& y, double I, int lane) {
     if (ro.act) { v[ro.x] = y.ce; v[m.off_pe + ro.x] = y.pe; }
     if (ro.elec) {
+#if PLB_CS_PMAJOR
+        double* pc = v + m.off_cs + ro.e * NR;
+        if ((m.off_cs & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < NR / 2; k++) reinterpret_cast<double2*>(pc)[k] = make_double2(y.cs[2 * k], y.cs[2 * k + 1]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) pc[r] = y.cs[r];
+        }
+#else
 #pragma unroll
         for (int r = 0; r < NR; r++) v[m.off_cs + r * m.Ne + ro.e] = y.cs[r];
+#endif
         v[m.off_j + ro.e] = y.j;
         v[m.off_ps + ro.e] = y.ps;
     }
@@ -108,6 +140,9 @@ __device__ __forceinline__ void store_lane(const ModelDesc& m, const LaneRole& r
 }
 // reference (particle-major) layout <-> internal index
 __device__ __forceinline__ int ref_index(const ModelDesc& m, int i) {
+#if PLB_CS_PMAJOR
+    return i;
+#endif
     if (i < m.off_cs || i >= m.off_cs + NR * m.Ne) return i;
     const int k = i - m.off_cs, r = k / m.Ne, e = k % m.Ne;
     return m.off_cs + e * NR + r;
@@ -595,7 +630,7 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
     // check_stop_c_s_surf :141-161
     if (b.c_s_n_max == b.c_s_n_max) {
         double mx = -INFINITY;
-        for (int e = m.Np + lane; e < m.Ne; e += LW) mx = fmax(mx, interp_y(w, c, kord, m.off_cs + (NR - 1) * m.Ne + e));
+        for (int e = m.Np + lane; e < m.Ne; e += LW) mx = fmax(mx, interp_y(w, c, kord, PLB_CS_PMAJOR ? m.off_cs + e * NR + NR - 1 : m.off_cs + (NR - 1) * m.Ne + e));
         mx = grp_max(mx);
         const double lim = b.c_s_n_max * w.C.theta[TF_c_max_n];
         if (Ic > 0 && mx - lim > eps) {
