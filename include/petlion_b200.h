@@ -90,6 +90,9 @@ typedef struct {
 #define PLB_FAIL_MAXITERS (-4)    /* checks.jl:239 */
 #define PLB_FAIL_NONFINITE (-5)
 #define PLB_FAIL_INIT_BOUNDS (-6) /* check_initial_SOC, checks.jl:327-339 */
+#define PLB_FAIL_PREVIOUS (-7)    /* simulate!() of a system whose earlier segment failed hard: a hard failure leaves
+                                     state_t = NaN, and a continuation passes such a system through untouched (the
+                                     reference would have thrown at the first failure) */
 
 const char *plb_last_error(void);
 
@@ -191,6 +194,17 @@ int plb_simulate_table(plb_handle h, int B, const double *theta, const plb_run *
  * postfix_integrator!, model_evaluation.jl:291-293): local times of the run, applied to every later simulate call
  * of this handle; n = 0 clears them.  HOST array. */
 int plb_set_tstops(plb_handle h, int n, const double *tstops);
+
+/* simulate(p, tf::AbstractVector; ...) (src/model_evaluation.jl:13, 80 -> interp_sol, :148-149): results at
+ * user-requested times.  The reference re-interpolates the saved steps with a cubic spline on the host afterwards
+ * (src/save_outputs.jl:74-133; the host layer keeps that as sol(t)); here the integrator itself evaluates its BDF
+ * interpolant (IDAGetSolution) of the step that covers each requested time, on the device, while it steps.
+ * t_global[n]: ascending GLOBAL times (HOST array, copied).  V/I/SOC/T [B x n], Y [B x n x N] (reference state
+ * order), n_done[B] = rows filled per system: any of them may be NULL; they live where the `mem` of the simulate
+ * call says and must stay valid until it returns.  Rows past the end of a run are NaN.  Applies to the NEXT
+ * plb_simulate / plb_simulate_table call of this handle only; n = 0 clears a pending request. */
+int plb_set_dense_output(plb_handle h, int n, const double *t_global, double *V, double *I, double *SOC,
+                         double *T, double *Y, int *n_done, int mem);
 
 /* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI, 3 wide, 4 wide SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared

@@ -42,7 +42,14 @@ class Run(C.Structure):
                 ("input_kind", C.c_int), ("new_run", C.c_int), ("t0", C.c_double),
                 ("tab_n", C.c_int), ("tab_t", C.POINTER(C.c_double)), ("tab_v", C.POINTER(C.c_double)),
                 ("scale", C.c_double), ("n_tdiscon", C.c_int), ("tdiscon", C.POINTER(C.c_double)),
-                ("last_value", C.POINTER(C.c_double)), ("n_tstops", C.c_int), ("tstops", C.POINTER(C.c_double))]
+                ("last_value", C.POINTER(C.c_double)), ("n_tstops", C.c_int), ("tstops", C.POINTER(C.c_double)),
+                ("dense", C.c_void_p), ("dense_sys", C.c_int)]
+
+
+class Dense(C.Structure):
+    _fields_ = [("n", C.c_int), ("t", C.POINTER(C.c_double)), ("V", C.POINTER(C.c_double)),
+                ("I", C.POINTER(C.c_double)), ("SOC", C.POINTER(C.c_double)), ("T", C.POINTER(C.c_double)),
+                ("Y", C.POINTER(C.c_double)), ("done", C.POINTER(C.c_int))]
 
 
 class Opts(C.Structure):
@@ -215,9 +222,11 @@ def newton_init(m, theta, run, opts, Y):
 
 
 def simulate_batch(m, theta, run, opts, bounds, SOC0=1.0, values=None, state=None, n_save_max=0,
-                   nthreads=1):
+                   nthreads=1, dense_t=None, dense_Y=False):
     """theta: [B, ntheta] (oracle order).  Returns dict of numpy arrays.
-    state: dict(Y, YP, SOC, t) from a previous call (simulate! continuation)."""
+    state: dict(Y, YP, SOC, t) from a previous call (simulate! continuation).
+    dense_t: ascending global times -> res["dense"] = dict(t, V, I, SOC, T[, Y], n): the integrator's own
+    interpolant at those times (rows past the end of a run stay NaN)."""
     L = lib()
     theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
     B = theta.shape[0]
@@ -233,6 +242,20 @@ def simulate_batch(m, theta, run, opts, bounds, SOC0=1.0, values=None, state=Non
     tr = {k: np.full((B, ns), np.nan) for k in ("t", "V", "I", "SOC")}
     trn = np.zeros(B, dtype=np.int32)
     vals = None if values is None else np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), (B,)))
+    dense = None
+    if dense_t is not None:
+        dt_ = np.ascontiguousarray(dense_t, dtype=np.float64)
+        assert dt_.ndim == 1 and np.all(np.diff(dt_) >= 0)
+        dense = dict(t=dt_, n=np.zeros(B, dtype=np.int32))
+        for k in ("V", "I", "SOC", "T"):
+            dense[k] = np.full((B, dt_.size), np.nan)
+        if dense_Y:
+            dense["Y"] = np.full((B, dt_.size, N), np.nan)
+        dstruct = Dense(dt_.size, _p(dt_), _p(dense["V"]), _p(dense["I"]), _p(dense["SOC"]), _p(dense["T"]),
+                        _p(dense["Y"]) if dense_Y else None, dense["n"].ctypes.data_as(_ip))
+        run = _copy_run(run)
+        run._keep_dense = (dstruct, dense)
+        run.dense = C.cast(C.pointer(dstruct), C.c_void_p)
     L.orc_simulate_batch(C.byref(m), B, _p(theta), C.byref(run), None if vals is None else _p(vals),
                          C.byref(opts), C.byref(bounds), _p(soc0), _p(sY), _p(sYP), _p(sSOC), _p(st),
                          out, ns if n_save_max else 0,
@@ -240,8 +263,17 @@ def simulate_batch(m, theta, run, opts, bounds, SOC0=1.0, values=None, state=Non
                          _p(tr["I"]) if n_save_max else None, _p(tr["SOC"]) if n_save_max else None,
                          trn.ctypes.data_as(_ip), int(nthreads))
     res = {f: np.array([getattr(o, f) for o in out]) for f, _ in Summary._fields_}
-    res.update(state=dict(Y=sY, YP=sYP, SOC=sSOC, t=st), traj=tr, traj_n=trn)
+    res.update(state=dict(Y=sY, YP=sYP, SOC=sSOC, t=st), traj=tr, traj_n=trn, dense=dense)
     return res
+
+
+def _copy_run(run):
+    r = Run()
+    C.memmove(C.byref(r), C.byref(run), C.sizeof(Run))
+    for k in ("_keep", "_keep_ts"):
+        if hasattr(run, k):
+            setattr(r, k, getattr(run, k))
+    return r
 
 
 def rng_u01(seed, system_id, param_id):

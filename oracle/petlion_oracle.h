@@ -73,6 +73,7 @@ typedef struct {
     int N_diff, N_alg, N_tot;
 } orc_layout;
 
+struct orc_dense;
 /* run = run_constant{method,value}: src/structures.jl:46-54 */
 typedef struct {
     int method;   /* ORC_METHOD_* */
@@ -95,7 +96,21 @@ typedef struct {
     double *last_value;
     int n_tstops;            /* opts.tstops (params.jl:272): explicit stop times, local to the run */
     const double *tstops;
+    /* dense output (`tf::AbstractVector`, model_evaluation.jl:80, 148-149): the integrator's own BDF
+     * interpolant (IDAGetSolution) evaluated at the requested GLOBAL times, ascending; rows of system
+     * `dense_sys` in the [B][n] output arrays (any of them may be NULL).  dense_done[sys] = rows filled
+     * (times past the end of the run are left untouched). */
+    const struct orc_dense *dense;
+    int dense_sys;
 } orc_run;
+
+typedef struct orc_dense {
+    int n;
+    const double *t;                 /* [n] */
+    double *V, *Icur, *SOC, *T;      /* [B][n] */
+    double *Y;                       /* [B][n][N_tot] */
+    int *done;                       /* [B] */
+} orc_dense;
 
 /* options_simulation: src/structures.jl:266-285, defaults src/params.jl:256-280 */
 typedef struct {
@@ -134,6 +149,7 @@ typedef struct {
 #define ORC_FAIL_MAXITERS (-4)
 #define ORC_FAIL_NONFINITE (-5)
 #define ORC_FAIL_INIT_BOUNDS (-6)
+#define ORC_FAIL_PREVIOUS (-7)    /* continuation of a system whose earlier segment failed (state_t is NaN) */
 
 int orc_ntheta(void);
 const char *orc_theta_name(int i);

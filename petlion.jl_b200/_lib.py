@@ -6,6 +6,7 @@ There is NO CPU fallback: if the CUDA library is missing or no GPU is present, c
 import ctypes as C
 import os
 import subprocess
+import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -24,7 +25,7 @@ def build(force=False, verbose=False):
     srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))
     gen = os.path.join(CSRC, "laws_generated.cuh")
     if not os.path.exists(gen):
-        subprocess.check_call(["python", os.path.join(_HERE, "codegen", "gen_laws.py")])
+        subprocess.check_call([sys.executable, os.path.join(_HERE, "codegen", "gen_laws.py")])
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return LIB_PATH
@@ -84,7 +85,7 @@ SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", 
 EXPORTS = ["plb_last_error", "plb_create", "plb_destroy", "plb_set_stream", "plb_nstates", "plb_ndiff",
            "plb_ntheta", "plb_jac_nnz", "plb_theta_keys", "plb_theta_index", "plb_theta_defaults",
            "plb_bounds_defaults", "plb_opts_defaults", "plb_calc_I1C", "plb_jac_pattern",
-           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_set_tstops", "plb_variant_info", "plb_launch_count",
+           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_set_tstops", "plb_set_dense_output", "plb_variant_info", "plb_launch_count",
            "plb_last_kernel_ms"]
 
 _lib = None
@@ -124,6 +125,7 @@ def lib():
                                          C.POINTER(Bounds), dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, dp, vp,
                                          C.c_int]
         L.plb_set_tstops.argtypes = [vp, C.c_int, dp]
+        L.plb_set_dense_output.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, vp, C.c_int]
         L.plb_launch_count.argtypes = [vp]
         L.plb_launch_count.restype = C.c_longlong
         L.plb_last_kernel_ms.argtypes = [vp]

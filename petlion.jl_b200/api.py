@@ -30,6 +30,7 @@ HARD_FAILURES = {
     -4: "Reached max iterations",                                # checks.jl:239
     -5: "Non-finite state",
     -6: "The initial SOC is outside SOC_min/SOC_max for the requested (dis)charge",  # checks.jl:327-339
+    -7: "An earlier segment of this simulation failed",
 }
 
 
@@ -212,6 +213,8 @@ class Solution:
         self.t = self.V = self.I = self.SOC = self.T = None
         self.states = None      # [B, n, N] when simulate(..., outputs=:all or state names)
         self.n_points = None
+        self.truncated = None   # [B] bool: the run took more steps than n_save_max rows (the summary is complete)
+        self.dense = None       # simulate(p, tf::Vector): dict(t, V, I, SOC, T[, Y], n) at the requested times
         self.Y = self.YP = None
         self._SOC_end = self._t_end = None
         self.results = []
@@ -221,6 +224,47 @@ class Solution:
 
     def isempty(self):
         return len(self.results) == 0
+
+    def __call__(self, t, k=3, interp_bc="interpolate", system=None):
+        """sol(t): the saved rows re-interpolated at times t with a spline of degree k per run, as the reference
+        does with Dierckx.Spline1D (src/save_outputs.jl:74-133); scipy's splrep/splev are the same FITPACK
+        routines.  interp_bc: "interpolate" (nearest value outside a run) or "extrapolate".
+        Returns dict(t, V, I, SOC, T) with [B, len(t)] arrays (or [len(t)] for one `system`)."""
+        from scipy.interpolate import splev, splrep
+        if interp_bc not in ("interpolate", "extrapolate"):
+            raise ValueError("Invalid interp_bc method.")
+        t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        systems = range(self.t.shape[0]) if system is None else [system]
+        out = {key: np.full((len(systems), t.size), np.nan) for key in ("V", "I", "SOC", "T")}
+        for row, s_ in enumerate(systems):
+            # tspans of the runs of this system (results[i].tspan), rows of each run
+            ends = np.cumsum([int(r.n_rows[s_]) for r in self.results])
+            starts = np.concatenate([[0], ends[:-1]])
+            spans = [(self.t[s_, a], self.t[s_, b - 1]) for a, b in zip(starts, ends) if b > a]
+            rows = [(a, b) for a, b in zip(starts, ends) if b > a]
+            which = np.full(t.size, len(spans) - 1)
+            for i in range(len(spans) - 1, -1, -1):      # tspan_index: the first run whose span holds t
+                which[(t >= spans[i][0]) & (t <= spans[i][1])] = i
+            which[t < spans[0][0]] = 0
+            for i, (a, b) in enumerate(rows):
+                sel = which == i
+                if not sel.any():
+                    continue
+                x = self.t[s_, a:b]
+                keep = np.concatenate([[True], np.diff(x) > 0])      # FITPACK needs strictly increasing abscissae
+                for key in out:
+                    y = getattr(self, key)[s_, a:b]
+                    if not np.all(np.isfinite(y[keep])):
+                        continue
+                    kk = min(k, int(keep.sum()) - 1)
+                    if kk < 1:
+                        out[key][row, sel] = y[0]
+                        continue
+                    tck = splrep(x[keep], y[keep], k=kk, s=0)
+                    out[key][row, sel] = splev(t[sel], tck, ext=0 if interp_bc == "extrapolate" else 3)
+        res = {"t": t}
+        res.update({key: (v if system is None else v[0]) for key, v in out.items()})
+        return res
 
     def state(self, p, name, system=0):
         """sol.c_e, sol.c_s_avg, sol.T, sol.j, sol.Φ_e, sol.Φ_s, sol.film, sol.j_s, sol.SOH of one system:
@@ -240,6 +284,8 @@ def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, 
         raise NotImplementedError("only solid_diffusion=:Fickian, Fickian_method=:finite_difference is built")
     if jacobian not in ("symbolic", "AD"):
         raise ValueError("`jacobian` can either be :symbolic or :AD")   # checks.jl:377-383
+    if aging not in (False, True, "SEI"):       # params.jl:119-174: aging = false | :SEI
+        raise ValueError(f"unknown aging model {aging!r}; built: False, \"SEI\"")
     N = _NS(p=N_p, s=N_s, n=N_n, a=N_a, z=N_z, r_p=N_r_p, r_n=N_r_n)
     numerics = _NS(temperature=temperature, solid_diffusion=solid_diffusion, Fickian_method=Fickian_method,
                    aging=aging, jacobian=jacobian, cathode=cathode)
@@ -329,9 +375,7 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     if name == "dT" and not p.numerics.temperature:
         raise ValueError("Temperature must be enabled when using `dT`.")      # input_methods.jl:183
     if isinstance(inp, str):
-        if inp == "hold" and name == "dT":
-            kind = 1       # custom_res!: :hold needs no previous run for a residual input (hold_val = 0)
-        elif inp == "hold":
+        if inp == "hold":
             if new_run:
                 raise ValueError("Cannot use `:hold` without a previous simulation.")   # checks.jl:385
             kind = 1
@@ -353,6 +397,13 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     th = p.theta_matrix(B)
     if vals is not None:
         vals = np.ascontiguousarray(np.broadcast_to(vals, (B,)))
+    # tf::AbstractVector (model_evaluation.jl:13, 80): run to tf[end], results also at every tf[i] (sol.dense)
+    t_dense = None
+    if np.ndim(tf) > 0:
+        t_dense = np.ascontiguousarray(np.ravel(tf), dtype=np.float64)
+        if t_dense.size == 0 or np.any(np.diff(t_dense) < 0):
+            raise ValueError("tf must be a number or an ascending vector of times")
+    # (like the reference, tf[end] is the run's local final time and the requested times are global ones)
     run = _lib.Run(METHODS[name], kind, value, float(np.ravel(tf)[-1]), int(new_run), 0)
     o = _make_opts(p, dict(abstol=abstol, reltol=reltol, abstol_init=abstol_init, reltol_init=reltol_init,
                            maxiters=maxiters, check_bounds=check_bounds, interp_final=interp_final,
@@ -391,6 +442,16 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
             trY.ctypes.data if keep_states else None,
             trn.ctypes.data, 0)
     vptr = None if vals is None else vals.ctypes.data
+    dense = None
+    if t_dense is not None:
+        nd = t_dense.size
+        dense = dict(t=t_dense, n=np.zeros(B, dtype=np.int32))
+        for key in ("V", "I", "SOC", "T"):
+            dense[key] = np.full((B, nd), np.nan)
+        dense["Y"] = np.full((B, nd, N), np.nan) if keep_states else None
+        _lib.check(L.plb_set_dense_output(p._h, nd, t_dense.ctypes.data, dense["V"].ctypes.data, dense["I"].ctypes.data,
+                                          dense["SOC"].ctypes.data, dense["T"].ctypes.data,
+                                          dense["Y"].ctypes.data if keep_states else None, dense["n"].ctypes.data, 0))
     if table is not None:
         dpp = C.POINTER(C.c_double)
         td = np.ascontiguousarray(sorted(tdiscon if tdiscon is not None else p.opts.tdiscon), dtype=np.float64)
@@ -404,6 +465,16 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
         # the reference throws for a single simulation (model_evaluation.jl:456, checks.jl:233-239)
         raise RuntimeError(HARD_FAILURES.get(int(summ["flag"][0]), "simulation failed"))
     sol.Y, sol.YP, sol._SOC_end, sol._t_end = sY, sYP, sSOC, st
+    # the reference keeps every step; here the rows live in caller-sized buffers: say so when a run outgrew them
+    trunc = (summ["n_steps"] + 1 > ns) if ns > 0 else np.zeros(B, dtype=bool)
+    if ns > 0 and trunc.any():
+        import warnings
+        warnings.warn(f"{int(trunc.sum())} of {B} runs took more steps (up to {int(summ['n_steps'].max())}) than "
+                      f"n_save_max = {ns} rows: their trajectories are truncated (summaries and final states are "
+                      f"complete); pass a larger n_save_max", RuntimeWarning, stacklevel=2)
+    sol.truncated = trunc if sol.truncated is None or new_run else (sol.truncated | trunc)
+    if dense is not None:
+        sol.dense = dense
     if sol.t is None or new_run:
         sol.t, sol.V, sol.I, sol.SOC, sol.T, sol.n_points = tr["t"], tr["V"], tr["I"], tr["SOC"], tr["T"], trn.copy()
         sol.states = trY
@@ -425,7 +496,7 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
                     new[s, sol.n_points[s]:sol.n_points[s] + trn[s]] = trY[s, :trn[s]]
             sol.states = new
         sol.n_points = sol.n_points + trn
-    sol.results.append(_NS(run=_NS(method=name, input=inp, tf=run.tf), summary=summ,
+    sol.results.append(_NS(run=_NS(method=name, input=inp, tf=run.tf), summary=summ, n_rows=trn.copy(), truncated=trunc,
                            exit_reason=[EXIT_REASONS.get(int(f), HARD_FAILURES.get(int(f), "?")) for f in summ["flag"]],
                            kernel_ms=L.plb_last_kernel_ms(p._h)))
     return sol

@@ -73,7 +73,7 @@ struct Summary {   // == plb_summary (include/petlion_b200.h), 80 bytes
 };
 
 constexpr int FAIL_NEWTON_INIT = -1, FAIL_CONV = -2, FAIL_ERRTEST = -3, FAIL_MAXITERS = -4,
-              FAIL_NONFINITE = -5, FAIL_INIT_BOUNDS = -6;
+              FAIL_NONFINITE = -5, FAIL_INIT_BOUNDS = -6, FAIL_PREVIOUS = -7;
 
 struct ResJacArgs {
     ModelDesc m;
@@ -126,6 +126,12 @@ struct SimArgs {
     // (model_evaluation.jl:288-310) when a table is given.
     int tab_n, n_tstops;
     const double *tab_t, *tab_v, *tstops;
+    // dense output (`tf::AbstractVector`, model_evaluation.jl:80, 148-149): the BDF interpolant of the step that
+    // covers each requested GLOBAL time (ascending), rows [B][n_dense]; any output may be null
+    int n_dense;
+    const double* dense_t;
+    double *dn_V, *dn_I, *dn_SOC, *dn_T, *dn_Y;
+    int* dn_n;
 };
 
 // what the host needs to know about a compiled variant

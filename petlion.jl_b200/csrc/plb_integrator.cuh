@@ -614,19 +614,6 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
         pv.T = Tw;
     }
 #endif
-#if PLB_SEI
-    // check_stop_dfilm :204-224 (the largest film growth rate over the anode; no derivative-sign test)
-    {
-        double mx = -INFINITY;
-        for (int k = lane; k < m.Nn; k += LW) mx = fmax(mx, interp_yp(w, d, kord, m.off_film + k));
-        mx = grp_max(mx);
-        if (b.dfilm_max == b.dfilm_max && mx - b.dfilm_max > eps) {
-            const double tf_ = (pv.dfilm - b.dfilm_max) / (pv.dfilm - mx);
-            if (tf_ < pv.frac) { pv.frac = tf_; flag = 10; }
-        }
-        pv.dfilm = mx;
-    }
-#endif
     // check_stop_c_s_surf :141-161
     if (b.c_s_n_max == b.c_s_n_max) {
         double mx = -INFINITY;
@@ -661,6 +648,19 @@ __device__ __noinline__ void check_stop(const ModelDesc& m, const WarpWS& w, con
         }
         pv.eta_plating = ep;
     }
+#if PLB_SEI
+    // check_stop_dfilm :204-224 (the largest film growth rate over the anode; no derivative-sign test)
+    {
+        double mx = -INFINITY;
+        for (int k = lane; k < m.Nn; k += LW) mx = fmax(mx, interp_yp(w, d, kord, m.off_film + k));
+        mx = grp_max(mx);
+        if (b.dfilm_max == b.dfilm_max && mx - b.dfilm_max > eps) {
+            const double tf_ = (pv.dfilm - b.dfilm_max) / (pv.dfilm - mx);
+            if (tf_ < pv.frac) { pv.frac = tf_; flag = 10; }
+        }
+        pv.dfilm = mx;
+    }
+#endif
 }
 
 

@@ -125,9 +125,33 @@ struct plb_handle_s {
     int num_sms = 0;
     // device staging buffers of PLB_MEM_HOST calls: grow-only, reused from call to call (a cudaMalloc /
     // cudaFree pair per argument and call costs more than the transfers themselves)
-    void* pool_ptr[20] = {};
-    size_t pool_cap[20] = {};
+    static constexpr int NPOOL = 28;
+    void* pool_ptr[NPOOL] = {};
+    size_t pool_cap[NPOOL] = {};
+    // dense-output request of the next simulate call (plb_set_dense_output): one-shot
+    struct {
+        int n = 0, mem = 0;
+        std::vector<double> t;
+        double *V = nullptr, *I = nullptr, *SOC = nullptr, *T = nullptr, *Y = nullptr;
+        int* n_done = nullptr;
+    } dense;
 };
+
+// Every entry point that touches CUDA runs on the handle's device, whatever the caller's current device is
+// (a process may hold handles on several GPUs, and a host such as torch moves the current device around).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define PLB_ENTER(h, name)                                                       \
+    if (!(h)) return fail(name ": null handle");                                  \
+    DeviceGuard guard_((h)->desc.device);                                         \
+    if (!guard_.ok) return fail(name ": cudaSetDevice failed")
 
 const char* plb_last_error(void) { return g_err.c_str(); }
 
@@ -190,9 +214,17 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plb_create: no CUDA device available (this library has no CPU fallback)");
-    CUDA_OK(cudaSetDevice(d->device));
+    if (d->device < 0 || d->device >= ndev) return fail("plb_create: no such CUDA device");
     plb_handle_s* h = new plb_handle_s();
     h->desc = *d;
+    DeviceGuard guard_(d->device);
+    if (!guard_.ok) { delete h; return fail("plb_create: cudaSetDevice failed"); }
+    // every failure below releases what was allocated so far
+#define CREATE_OK(x)                                                                                \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) { plb_destroy(h); return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } \
+    } while (0)
     // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
     const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
@@ -214,7 +246,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     m.off_j = m.off_SOH + (m.aging ? 1 : 0); m.N_diff = m.off_j;
     m.off_pe = m.off_j + m.Ne; m.off_ps = m.off_pe + m.Nx; m.off_js = m.off_ps + m.Ne;
     m.off_I = m.off_js + (m.aging ? m.Nn : 0); m.N_tot = m.off_I + 1;
-    if (m.N_tot > h->vi.vs) { delete h; return fail("plb_create: system too large for the workspace stride"); }
+    if (m.N_tot > h->vi.vs) { plb_destroy(h); return fail("plb_create: system too large for the workspace stride"); }
     for (int f = 0; f < TF_COUNT; f++) m.slot[f] = -1;
     // used keys in the reference's (code-point sorted) order; KEYS[] is already sorted that way
     for (int k = 0; k < (int)(sizeof(KEYS) / sizeof(KEYS[0])); k++) {
@@ -227,14 +259,15 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     m.ntheta = (int)h->keys.size();
     m.theta_stride = m.ntheta;
     cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, d->device));
+    CREATE_OK(cudaGetDeviceProperties(&prop, d->device));
     h->num_sms = prop.multiProcessorCount;
-    if (build_patterns(h)) { delete h; return -1; }
-    CUDA_OK(cudaMalloc(&h->d_counter, sizeof(int)));
+    if (build_patterns(h)) { const std::string e = g_err; plb_destroy(h); return fail(e); }
+    CREATE_OK(cudaMalloc(&h->d_counter, sizeof(int)));
     h->sim_grid = h->num_sms * h->vi.sim_ctas;
-    CUDA_OK(cudaMalloc(&h->d_gws, (size_t)h->sim_grid * h->vi.sim_warps * (h->vi.nglobal > 0 ? h->vi.nglobal : 1) * h->vi.vs * sizeof(double)));
-    CUDA_OK(cudaEventCreate(&h->ev0));
-    CUDA_OK(cudaEventCreate(&h->ev1));
+    CREATE_OK(cudaMalloc(&h->d_gws, (size_t)h->sim_grid * h->vi.sim_warps * (h->vi.nglobal > 0 ? h->vi.nglobal : 1) * h->vi.vs * sizeof(double)));
+    CREATE_OK(cudaEventCreate(&h->ev0));
+    CREATE_OK(cudaEventCreate(&h->ev1));
+#undef CREATE_OK
     *out = h;
     return 0;
 }
@@ -248,8 +281,9 @@ int plb_variant_info(int family, long long* out) {
 
 int plb_destroy(plb_handle h) {
     if (!h) return 0;
+    DeviceGuard guard_(h->desc.device);
     for (int i = 0; i < N_METHODS; i++) cudaFree(h->d_src[i]);
-    for (int i = 0; i < 20; i++) if (h->pool_ptr[i]) cudaFree(h->pool_ptr[i]);
+    for (int i = 0; i < plb_handle_s::NPOOL; i++) if (h->pool_ptr[i]) cudaFree(h->pool_ptr[i]);
     cudaFree(h->d_counter);
     cudaFree(h->d_gws);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -257,29 +291,33 @@ int plb_destroy(plb_handle h) {
     delete h;
     return 0;
 }
-int plb_set_stream(plb_handle h, void* s) { h->stream = (cudaStream_t)s; return 0; }
-int plb_nstates(plb_handle h) { return h->m.N_tot; }
-int plb_ndiff(plb_handle h) { return h->m.N_diff; }
-int plb_ntheta(plb_handle h) { return h->m.ntheta; }
-int plb_jac_nnz(plb_handle h, int method) { return (!h->method_ok(method)) ? -1 : (int)h->rowval[method].size(); }
-long long plb_launch_count(plb_handle h) { return h->launches; }
-float plb_last_kernel_ms(plb_handle h) { return h->last_ms; }
+int plb_set_stream(plb_handle h, void* s) { if (!h) return fail("plb_set_stream: null handle"); h->stream = (cudaStream_t)s; return 0; }
+int plb_nstates(plb_handle h) { return h ? h->m.N_tot : fail("plb_nstates: null handle"); }
+int plb_ndiff(plb_handle h) { return h ? h->m.N_diff : fail("plb_ndiff: null handle"); }
+int plb_ntheta(plb_handle h) { return h ? h->m.ntheta : fail("plb_ntheta: null handle"); }
+int plb_jac_nnz(plb_handle h, int method) { return (!h || !h->method_ok(method)) ? -1 : (int)h->rowval[method].size(); }
+long long plb_launch_count(plb_handle h) { return h ? h->launches : -1; }
+float plb_last_kernel_ms(plb_handle h) { return h ? h->last_ms : 0.f; }
 
 int plb_theta_keys(plb_handle h, const char** keys) {
+    if (!h || !keys) return fail("plb_theta_keys: null argument");
     for (size_t i = 0; i < h->keys.size(); i++) keys[i] = KEYS[h->keys[i]].utf8;
     return (int)h->keys.size();
 }
 int plb_theta_index(plb_handle h, const char* key) {
+    if (!h || !key) return -1;
     for (size_t i = 0; i < h->keys.size(); i++)
         if (!strcmp(KEYS[h->keys[i]].utf8, key) || !strcmp(KEYS[h->keys[i]].ascii, key)) return (int)i;
     return -1;
 }
 int plb_theta_defaults(plb_handle h, double* row) {
+    if (!h || !row) return fail("plb_theta_defaults: null argument");
     for (size_t i = 0; i < h->keys.size(); i++)
         row[i] = h->desc.cathode == PLB_CATHODE_LCO ? KEYS[h->keys[i]].lco : KEYS[h->keys[i]].nmc;
     return 0;
 }
 int plb_bounds_defaults(plb_handle h, plb_bounds* b) {
+    if (!h || !b) return fail("plb_bounds_defaults: null argument");
     // src/params.jl:233-253 (LCO), :451-471 (NMC)
     const double nan_ = NAN;
     if (h->desc.cathode == PLB_CATHODE_LCO) { b->V_min = 2.5; b->V_max = 4.3; b->T_max = 55 + 273.15; }
@@ -295,6 +333,7 @@ int plb_opts_defaults(plb_handle, plb_opts* o) {
     return 0;
 }
 int plb_calc_I1C(plb_handle h, int B, const double* theta, double* I1C) {
+    if (!h || !theta || !I1C) return fail("plb_calc_I1C: null argument");
     // host-side: update_theta! recomputes I1C from the dict (generate_functions.jl:364-372)
     const ModelDesc& m = h->m;
     for (int s = 0; s < B; s++) {
@@ -308,6 +347,7 @@ int plb_calc_I1C(plb_handle h, int B, const double* theta, double* I1C) {
     return 0;
 }
 int plb_jac_pattern(plb_handle h, int method, int* colptr, int* rowval, int one_based) {
+    if (!h || !colptr || !rowval) return fail("plb_jac_pattern: null argument");
     if (!h->method_ok(method)) return fail("plb_jac_pattern: bad method");
     const int o = one_based ? 1 : 0;
     for (size_t i = 0; i < h->colptr[method].size(); i++) colptr[i] = h->colptr[method][i] + o;
@@ -336,8 +376,8 @@ struct DevBuf {
 };
 // the staging slots of one API call
 struct DevBufs {
-    DevBuf b[20];
-    explicit DevBufs(plb_handle_s* h) { for (int i = 0; i < 20; i++) { b[i].h = h; b[i].k = i; } }
+    DevBuf b[plb_handle_s::NPOOL];
+    explicit DevBufs(plb_handle_s* h) { for (int i = 0; i < plb_handle_s::NPOOL; i++) { b[i].h = h; b[i].k = i; } }
     DevBuf& operator[](int i) { return b[i]; }
 };
 template <class T>
@@ -377,7 +417,9 @@ static Opts to_opts(const plb_opts* o) {
 }
 
 int plb_initial_guess(plb_handle h, int B, const double* soc, const double* theta, double* Y0, int mem) {
+    PLB_ENTER(h, "plb_initial_guess");
     if (B <= 0) return 0;
+    if (!soc || !theta || !Y0) return fail("plb_initial_guess: null argument");
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     DevBufs db(h);
@@ -399,8 +441,10 @@ int plb_initial_guess(plb_handle h, int B, const double* soc, const double* thet
 int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const double* gamma,
                const double* theta, const plb_run* run, const double* values, double* res,
                double* nzval, int mem) {
+    PLB_ENTER(h, "plb_resjac");
     if (B <= 0) return 0;
     if (!run || !h->method_ok(run->method)) return fail("plb_resjac: bad run (dT needs temperature=true)");
+    if (!Y || !YP || !theta) return fail("plb_resjac: null required argument");
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     const int nnz = (int)h->rowval[run->method].size();
@@ -430,8 +474,10 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
 
 int plb_newton_init(plb_handle h, int B, double* Y, double* YP, const double* theta, const plb_run* run,
                     const double* values, const plb_opts* opts, int* status, int mem) {
+    PLB_ENTER(h, "plb_newton_init");
     if (B <= 0) return 0;
-    if (!run || !opts) return fail("plb_newton_init: null run/opts");
+    if (!run || !opts || !Y || !YP || !theta) return fail("plb_newton_init: null required argument");
+    if (!h->method_ok(run->method)) return fail("plb_newton_init: bad method");
     const ModelDesc& m = h->m;
     cudaStream_t s = h->stream;
     DevBufs db(h);
@@ -458,6 +504,7 @@ int plb_newton_init(plb_handle h, int B, double* Y, double* YP, const double* th
 int plb_linear_solve(plb_handle h, int B, const double* Y, const double* YP, const double* gamma,
                      const double* theta, const plb_run* run, const double* values, const double* rhs,
                      double* x, int* status, int mem) {
+    PLB_ENTER(h, "plb_linear_solve");
     if (B <= 0) return 0;
     if (!run || !h->method_ok(run->method)) return fail("plb_linear_solve: bad run");
     if (!Y || !YP || !theta || !rhs || !x) return fail("plb_linear_solve: null required argument");
@@ -489,9 +536,14 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
                          const double* values, const plb_opts* opts, const plb_bounds* bounds, const double* soc0,
                          double* sY, double* sYP, double* sSOC, double* st, plb_summary* summary, int n_save_max,
                          double* tr_t, double* tr_V, double* tr_I, double* tr_SOC, double* tr_T, double* tr_Y, int* tr_n, int mem) {
+    PLB_ENTER(h, "plb_simulate");
+    // the dense-output request is one-shot: whatever happens to this call, the next one starts without it
+    auto dense = h->dense;
+    h->dense = {};
     if (B <= 0) return 0;
     if (!run || !opts || !bounds || !theta || !sY || !sSOC || !st || !summary)
         return fail("plb_simulate: null required argument");
+    if (dense.n && dense.mem != mem) return fail("plb_simulate: the dense-output buffers must live where the other buffers live");
     if (!h->method_ok(run->method))
         return fail(run->method == PLB_METHOD_DT ? "plb_simulate: Temperature must be enabled when using `dT`."   // input_methods.jl:183
                                                  : "plb_simulate: bad method");
@@ -552,6 +604,14 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
         stage_inout(b[13], tr_T, htT, BS, mem, false, s) || stage_inout(b[17], tr_Y, htY, BS * m.N_tot, mem, false, s)) return -1;
     if (tab && (stage_in(b[14], tab_t, (size_t)tab->n, PLB_MEM_HOST, s) || stage_in(b[15], tab_v, (size_t)tab->n, PLB_MEM_HOST, s))) return -1;
     if (d_tstops && stage_in(b[16], d_tstops, tstops.size(), PLB_MEM_HOST, s)) return -1;
+    const double* dn_t = dense.n ? dense.t.data() : nullptr;
+    double *hdV, *hdI, *hdS, *hdT, *hdY;
+    int* hdn;
+    const size_t BD = (size_t)B * dense.n;
+    if (dense.n && (stage_in(b[18], dn_t, (size_t)dense.n, PLB_MEM_HOST, s) || stage_inout(b[19], dense.V, hdV, BD, mem, false, s) ||
+                    stage_inout(b[20], dense.I, hdI, BD, mem, false, s) || stage_inout(b[21], dense.SOC, hdS, BD, mem, false, s) ||
+                    stage_inout(b[22], dense.T, hdT, BD, mem, false, s) || stage_inout(b[23], dense.Y, hdY, BD * m.N_tot, mem, false, s) ||
+                    stage_inout(b[24], dense.n_done, hdn, (size_t)B, mem, false, s))) return -1;
     SimArgs a;
     memset(&a, 0, sizeof a);
     a.m = m; a.B = B; a.theta = theta; a.values = values; a.method = run->method; a.value = run->value;
@@ -565,6 +625,14 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     a.gws = h->d_gws;
     if (tab) { a.tab_n = tab->n; a.tab_t = tab_t; a.tab_v = tab_v; }
     if (d_tstops) { a.n_tstops = (int)tstops.size(); a.tstops = d_tstops; }
+    if (dense.n) {
+        a.n_dense = dense.n; a.dense_t = dn_t;
+        a.dn_V = dense.V; a.dn_I = dense.I; a.dn_SOC = dense.SOC; a.dn_T = dense.T; a.dn_Y = dense.Y; a.dn_n = dense.n_done;
+        // rows past the end of a run stay NaN (0xff bytes), the row counters start at zero
+        for (double* q : {dense.V, dense.I, dense.SOC, dense.T}) if (q) CUDA_OK(cudaMemsetAsync(q, 0xff, BD * sizeof(double), s));
+        if (dense.Y) CUDA_OK(cudaMemsetAsync(dense.Y, 0xff, BD * m.N_tot * sizeof(double), s));
+        if (dense.n_done) CUDA_OK(cudaMemsetAsync(dense.n_done, 0, (size_t)B * sizeof(int), s));
+    }
     CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
     const int grid = std::min((B + h->vi.sim_warps - 1) / h->vi.sim_warps, h->sim_grid);
     CUDA_OK(cudaEventRecord(h->ev0, s));
@@ -575,6 +643,8 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
         stage_out(st, ht, (size_t)B, s) || stage_out(summary, hsum, (size_t)B, s) || stage_out(tr_t, htt, BS, s) ||
         stage_out(tr_V, htV, BS, s) || stage_out(tr_I, htI, BS, s) || stage_out(tr_SOC, htS, BS, s) ||
         stage_out(tr_n, htn, (size_t)B, s) || stage_out(tr_T, htT, BS, s) || stage_out(tr_Y, htY, BS * m.N_tot, s)) return -1;
+    if (dense.n && (stage_out(dense.V, hdV, BD, s) || stage_out(dense.I, hdI, BD, s) || stage_out(dense.SOC, hdS, BD, s) ||
+                    stage_out(dense.T, hdT, BD, s) || stage_out(dense.Y, hdY, BD * m.N_tot, s) || stage_out(dense.n_done, hdn, (size_t)B, s))) return -1;
     CUDA_OK(cudaStreamSynchronize(s));
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
     return 0;
@@ -597,7 +667,23 @@ int plb_simulate_table(plb_handle h, int B, const double* theta, const plb_run* 
                          tr_t, tr_V, tr_I, tr_SOC, tr_T, tr_Y, tr_n, mem);
 }
 
+int plb_set_dense_output(plb_handle h, int n, const double* t_global, double* V, double* I, double* SOC, double* T,
+                         double* Y, int* n_done, int mem) {
+    if (!h) return fail("plb_set_dense_output: null handle");
+    h->dense = {};
+    if (n == 0) return 0;
+    if (n < 0 || !t_global) return fail("plb_set_dense_output: bad arguments");
+    for (int k = 0; k < n; k++) {
+        if (!std::isfinite(t_global[k])) return fail("plb_set_dense_output: non-finite time");
+        if (k && t_global[k] < t_global[k - 1]) return fail("plb_set_dense_output: times must be ascending");
+    }
+    h->dense.n = n; h->dense.mem = mem; h->dense.t.assign(t_global, t_global + n);
+    h->dense.V = V; h->dense.I = I; h->dense.SOC = SOC; h->dense.T = T; h->dense.Y = Y; h->dense.n_done = n_done;
+    return 0;
+}
+
 int plb_set_tstops(plb_handle h, int n, const double* tstops) {
+    if (!h) return fail("plb_set_tstops: null handle");
     if (n < 0 || (n > 0 && !tstops)) return fail("plb_set_tstops: bad arguments");
     for (int k = 0; k < n; k++) if (!std::isfinite(tstops[k])) return fail("plb_set_tstops: non-finite stop time");
     h->opt_tstops.assign(tstops, tstops + n);

@@ -73,6 +73,9 @@ struct SimState {
     // (0, or t + reltol for a re-initialisation at a discontinuity: checks.jl:341-364)
     double scale, t_init;
     int reinit, n_reinit;
+    // dense output: next requested time to fill, SOC before the last accepted step's trapezoid update
+    int idense;
+    double SOC_before;
 };
 
 // value of the tabulated input at local time t: last knot k with tab_t[k] <= t (right-continuous at a
@@ -91,6 +94,52 @@ __device__ __noinline__ double table_eval(const double* __restrict__ tt, const d
 template <bool EXT>
 __device__ __forceinline__ double cur_tstop(const SimArgs& a, const SimState& S) {
     return (EXT && a.n_tstops) ? __ldg(a.tstops + S.itstop) : (S.itstop == 0 ? S.tstop0 : S.tstop1);
+}
+
+// dense output (EXT kernels): fill the rows of the requested global times in (.., tg_limit] that are still open.
+// The state at a requested time is the interpolant of the step that covers it (IDAGetSolution; `initial`: the
+// start state phi_0); SOC follows the trapezoid of set_vars! (save_outputs.jl:31) from the last accepted point.
+__device__ __noinline__ void dense_emit(const SimArgs& a, WarpWS& w, SimState& S, double tg_limit, bool initial, int lane) {
+    const ModelDesc& m = a.m;
+    const int N = m.N_tot;
+    const int iP0 = m.off_ps, iPN = m.off_ps + m.Ne - 1;
+    __syncwarp();
+    int k = S.idense;
+    while (k < a.n_dense) {
+        const double tg = __ldg(a.dense_t + k);
+        if (!(tg <= tg_limit)) break;
+        grp_sync();
+        int kord = 1;
+        if (lane == 0) {
+            if (initial) { w.K.cprev[0] = 1.0; w.K.cprev[1] = 0.0; }
+            else { double dp[6]; kord = getsol_weights(S.M, w.K, tg - S.t0, w.K.cprev, dp); }
+        }
+        kord = grp_bcast_int(kord, 0);
+        grp_sync();
+        const double* c = w.K.cprev;
+        const double Id = interp_y(w, c, kord, m.off_I);
+        const double Vd = interp_y(w, c, kord, iP0) - interp_y(w, c, kord, iPN);
+        const size_t row = (size_t)S.sys * a.n_dense + k;
+        if (a.dn_T) {
+            const double Tw = weighted_T(m, w, c, kord, false, lane);
+            if (lane == 0) a.dn_T[row] = Tw;
+        }
+        if (lane == 0) {
+            if (a.dn_V) a.dn_V[row] = Vd;
+            if (a.dn_I) a.dn_I[row] = Id;
+            if (a.dn_SOC) a.dn_SOC[row] = initial ? S.SOC : S.SOC_before + 0.5 * (tg - S.tg_prev) * (Id + S.I_prev) / 3600.0;
+        }
+        if (a.dn_Y) {
+            double* out = a.dn_Y + row * N;
+#pragma unroll 1
+            for (int i = lane; i < N; i += LW) out[ref_index(m, i)] = interp_y(w, c, kord, i);
+        }
+        k++;
+    }
+    __syncwarp();
+    S.idense = k;
+    if (lane == 0 && a.dn_n) a.dn_n[S.sys] = k;
+    grp_sync();
 }
 
 // ---- pieces of ida_nls -------------------------------------------------------------------------------
@@ -340,6 +389,7 @@ __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, Si
     }
     const double Vc = vp - vn;
     const double tg = S.t + S.t0;
+    if (EXT) S.SOC_before = S.SOC;
     S.SOC = S.SOC + 0.5 * (tg - S.tg_prev) * (Ic + S.I_prev) / 3600.0;
     const size_t so = (size_t)S.sys * a.n_save_max;
     if (lane == 0 && S.nsave < a.n_save_max) {
@@ -368,6 +418,7 @@ __device__ __forceinline__ int host_after_return(const SimArgs& a, WarpWS& w, Si
     if (S.iter == a.o.maxiters) { S.hard = FAIL_MAXITERS; return 0; }
     if (!(Ic == Ic) || !(Vc == Vc) || isinf(Ic) || isinf(Vc)) { S.hard = FAIL_NONFINITE; return 0; }
     if (S.flag != -1) return 0;
+    if (EXT && a.n_dense && S.t > S.tprev) dense_emit(a, w, S, tg, false, lane);
     S.I_prev = Ic;
     S.tg_prev = tg;
     const double dt_step = S.t - S.tprev;
@@ -477,6 +528,8 @@ __device__ PLB_COLD void finish(const SimArgs& a, WarpWS& w, SimState& S, bool i
                 if (a.tr_T) a.tr_T[so + S.nsave - 1] = T_end;
             }
         }
+        // dense output of the last (possibly shortened) step: requested times up to the end of the run
+        if (EXT && a.n_dense && !S.hard && S.flag != -1 && S.t > S.tprev) dense_emit(a, w, S, t_end, false, lane);
     } else {
         // failed before integration: hand the (initial) state back
 #pragma unroll 1
@@ -495,7 +548,7 @@ __device__ PLB_COLD void finish(const SimArgs& a, WarpWS& w, SimState& S, bool i
     if (lane == 0) {
         a.out[S.sys] = out;
         a.sSOC[S.sys] = SOC_end;
-        a.st[S.sys] = t_end;
+        a.st[S.sys] = S.flag < 0 ? NAN : t_end;     // a hard failure poisons the continuation state (PLB_FAIL_PREVIOUS)
         if (a.tr_n) a.tr_n[S.sys] = S.nsave < a.n_save_max ? S.nsave : a.n_save_max;
     }
     grp_sync();
@@ -553,6 +606,14 @@ __device__ PLB_COLD void fetch_and_setup(const SimArgs& a, WarpWS& w, const Lane
         for (int i = lane; i < N; i += LW) Y0[i] = a.sY[(size_t)sys * N + ref_index(m, i)];
         S.SOC = a.sSOC[sys];
         S.t0 = ::nextafter(a.st[sys], DBL_MAX);   // initial_time, model_evaluation.jl:112
+        if (!(S.t0 == S.t0)) {
+            // an earlier segment of this system failed hard: pass it through untouched
+            grp_sync();
+            S.flag = FAIL_PREVIOUS; S.hard = 0; S.nsave = 0; S.t = 0.0; S.n_newton_init = 0; S.n_reinit = 0;
+            S.M.nre = 0; S.M.nje = 0; S.M.netf = 0; S.M.ncfn = 0; S.M.nst = 0;
+            finish<EXT>(a, w, S, false, lane);
+            return;
+        }
     }
     grp_sync();
     const double I_prev_state = Y0[m.off_I];
@@ -593,6 +654,7 @@ __device__ PLB_COLD void fetch_and_setup(const SimArgs& a, WarpWS& w, const Lane
     M.nre = 0; M.nje = 0; M.netf = 0; M.ncfn = 0;
     S.t = 0.0; S.tprev = 0.0; S.flag = -1; S.iter = 1; S.hard = 0; S.nsave = 0; S.kord = 1; S.retried = 0;
     S.ni_iter = 0; S.n_newton_init = 0; S.pending = PEND_NONE;
+    S.idense = 0; S.SOC_before = S.SOC;
     S.state = ST_INIT_ITER;
 }
 
@@ -642,6 +704,12 @@ __device__ PLB_COLD void begin_integration(const SimArgs& a, WarpWS& w, SimState
         for (int i = lane; i < N; i += LW) row[ref_index(m, i)] = Y0[i];
     }
     S.nsave++;
+    if (EXT && a.n_dense) {
+        // requested times before the start of a continuation belong to the earlier runs; the start itself is a row
+        if (lane == 0 && a.dn_n) a.dn_n[S.sys] = 0;
+        if (!a.new_run) { int k = 0; while (k < a.n_dense && __ldg(a.dense_t + k) < S.t0) k++; S.idense = k; }
+        dense_emit(a, w, S, S.t0, true, lane);
+    }
     S.pv.T = -1; S.pv.dfilm = -1;
     S.pv.frac = 1.0; S.pv.V = -1; S.pv.SOC = -1; S.pv.c_s_n = -1; S.pv.I = -1; S.pv.eta_plating = -1; S.pv.c_e_min = -1;
     S.kord = 1;
@@ -685,7 +753,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
 #endif
     for (;;) {
         // ------------------------------ PRE: get to an evaluation point ---------------------------------
-        if (S.state == ST_FETCH) fetch_and_setup<CHEM, EXT>(a, w, ro, S, lane);
+        while (S.state == ST_FETCH) fetch_and_setup<CHEM, EXT>(a, w, ro, S, lane);   // (again after a passed-through system)
         if (EXT && a.tab_n && S.state != ST_EXHAUSTED) {
             // run.func(t) of this tick's evaluation: IDA evaluates F at the trial time tn; newtons_method! at its
             // t, except for the algebraic-derivative estimate, which passes dt itself as the time

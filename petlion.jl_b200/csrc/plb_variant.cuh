@@ -560,7 +560,7 @@ cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s) { PLB_L
 cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_newton, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_linsolve, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 cudaError_t launch_simulate(const SimArgs& a, int grid, cudaStream_t s) {
-    if (a.tab_n || a.tr_Y || a.n_tstops) PLB_LAUNCH(k_simulate_ext, a, grid, SIM_WARPS * LW, SIM_SMEM, s);
+    if (a.tab_n || a.tr_Y || a.n_tstops || a.n_dense) PLB_LAUNCH(k_simulate_ext, a, grid, SIM_WARPS * LW, SIM_SMEM, s);
     PLB_LAUNCH(k_simulate, a, grid, SIM_WARPS * LW, SIM_SMEM, s);
 }
 
