@@ -4,7 +4,7 @@ petlion()/simulate()/simulate!() API and its residual/Jacobian callback surface.
 Only what the hot path needs lives here: csrc/ (CUDA kernels + C ABI), codegen/ (sympy -> CUDA
 constitutive laws) and the host-side mirror of the reference interface (api.py).
 """
-from . import _lib
+from . import _lib, sweep
 from ._lib import build
 from .api import EXIT_REASONS, Model, Solution, Table, petlion, simulate, simulate_
 

@@ -348,7 +348,7 @@ class Table:
 
 def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_init=None, reltol_init=None,
              maxiters=None, check_bounds=None, interp_final=None, n_save_max=None, tdiscon=None,
-             initialize_algebraic_derivatives=None, outputs=None, tstops=None, **inputs):
+             initialize_algebraic_derivatives=None, outputs=None, tstops=None, dense_t=None, **inputs):
     """simulate(p, tf; I=..|V=..|P=.., SOC, V_max, V_min, SOC_max, ...) -- model_evaluation.jl:10-86.
 
     Inputs may be numbers (scalar or per-system arrays), "hold" or "rest" (Julia :hold / :rest), or a
@@ -398,11 +398,14 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     if vals is not None:
         vals = np.ascontiguousarray(np.broadcast_to(vals, (B,)))
     # tf::AbstractVector (model_evaluation.jl:13, 80): run to tf[end], results also at every tf[i] (sol.dense)
+    # dense_t: requested GLOBAL times without touching tf (what a continuation needs: its tf is local to the run)
     t_dense = None
-    if np.ndim(tf) > 0:
-        t_dense = np.ascontiguousarray(np.ravel(tf), dtype=np.float64)
-        if t_dense.size == 0 or np.any(np.diff(t_dense) < 0):
+    if np.ndim(tf) > 0 or dense_t is not None:
+        t_dense = np.ascontiguousarray(np.ravel(tf if dense_t is None else dense_t), dtype=np.float64)
+        if np.ndim(tf) > 0 and (np.size(tf) == 0 or np.any(np.diff(np.ravel(tf)) < 0)):
             raise ValueError("tf must be a number or an ascending vector of times")
+        if t_dense.size == 0 or np.any(np.diff(t_dense) < 0):
+            raise ValueError("the requested times must be ascending")
     # (like the reference, tf[end] is the run's local final time and the requested times are global ones)
     run = _lib.Run(METHODS[name], kind, value, float(np.ravel(tf)[-1]), int(new_run), 0)
     o = _make_opts(p, dict(abstol=abstol, reltol=reltol, abstol_init=abstol_init, reltol_init=reltol_init,

@@ -54,6 +54,7 @@ struct ModelDesc {
     // reference layout offsets (external.jl:275-365):
     //   c_e | c_s (particle-major) | [T: a|p|s|n|z] | [film | SOH] | j | Phi_e | Phi_s | [j_s] | I
     int off_cs, off_T, off_film, off_SOH, off_j, off_pe, off_ps, off_js, off_I, N_diff, N_tot;
+    double inv_n[4];             // 1/Np, 1/Ns, 1/Nn (Delta x of a section, numerical_tools.jl:216)
     int8_t slot[TF_COUNT];       // theta field -> position in the row (-1: not a key of this variant)
 };
 
@@ -84,6 +85,7 @@ struct ResJacArgs {
     double *res, *nzval;
     int nnz;
     const int* src;       // [nnz] recipe per CSC position (see plb_variant.cuh)
+    int use_tma;          // rows staged with bulk copies (needs 16-byte aligned Y, Y', theta arrays)
 };
 
 struct AuxArgs {

@@ -237,19 +237,43 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
     }
     grp_sync();
     const double* th = C.theta;
-    if (lane < 3) {
-        const int s = lane;
+    // The per-section constants need ~20 reciprocals.  Computed by the three "section lanes" one after the other they
+    // were a serial chain of ~450 instructions per system with 29 lanes idle (ncu source page of K1, round 1: 20 % of
+    // the kernel's time); here every lane forms ONE of them (correctly rounded, __drcp_rn) and the section lanes only
+    // multiply.  Reciprocal k (0..2: section p, s, n):  0-2 1/h   3-5 1/por   6-8 1/(rho Cp) [thermal]
+    //   9,10 1/Rp (p, n)   11,12 1/sigma_eff   13,14 1/D_s   15,16 1/c_max   17 1/T0   18 1/(sum of the five lengths)
+    double* const rc = C.beta;     // scratch: the face weights are written after the section constants have used it
+    {
+        const int k = lane, s = k < 9 ? k % 3 : (k - 9) & 1 ? 2 : 0;
         const double eps_f = s == 0 ? th[TF_eps_fp] : th[TF_eps_fn];
         const double eps_e = s == 0 ? th[TF_eps_p] : th[TF_eps_n];
         const double eps_act = 1.0 - (eps_f + eps_e);                                  // active_material
-        const double por = s == 1 ? th[TF_eps_s] : 1.0 - (eps_f + eps_act);            // build_eps!
+        double x = 1.0;
+        if (k < 3) x = m.inv_n[s] * (s == 0 ? th[TF_l_p] : (s == 1 ? th[TF_l_s] : th[TF_l_n]));
+        else if (k < 6) x = s == 1 ? th[TF_eps_s] : 1.0 - (eps_f + eps_act);            // build_eps!
+        else if (k < 9) x = TH ? (s == 0 ? th[TF_rho_p] * th[TF_Cp_p] : (s == 1 ? th[TF_rho_s] * th[TF_Cp_s] : th[TF_rho_n] * th[TF_Cp_n])) : 1.0;
+        else if (k < 11) x = s == 0 ? th[TF_Rp_p] : th[TF_Rp_n];
+        else if (k < 13) x = (s == 0 ? th[TF_sigma_p] : th[TF_sigma_n]) * eps_act;      // build_sigma_eff
+        else if (k < 15) x = s == 0 ? th[TF_D_sp] : th[TF_D_sn];
+        else if (k < 17) x = s == 0 ? th[TF_c_max_p] : th[TF_c_max_n];
+        else if (k == 17) x = th[TF_T0];
+        else if (k == 18) x = TH ? th[TF_l_a] + th[TF_l_p] + th[TF_l_s] + th[TF_l_n] + th[TF_l_z] : 1.0;
+        if (k < 19) rc[k] = __drcp_rn(x);
+    }
+    grp_sync();
+    if (lane < 3) {
+        const int s = lane, e = s == 2 ? 1 : 0;
+        const double eps_f = s == 0 ? th[TF_eps_fp] : th[TF_eps_fn];
+        const double eps_e = s == 0 ? th[TF_eps_p] : th[TF_eps_n];
+        const double eps_act = 1.0 - (eps_f + eps_e);
+        const double por = s == 1 ? th[TF_eps_s] : 1.0 - (eps_f + eps_act);
         const double brg = s == 0 ? th[TF_brugg_p] : (s == 1 ? th[TF_brugg_s] : th[TF_brugg_n]);
         const double l = s == 0 ? th[TF_l_p] : (s == 1 ? th[TF_l_s] : th[TF_l_n]);
-        const int n = s == 0 ? m.Np : (s == 1 ? m.Ns : m.Nn);
-        const double h = (1.0 / n) * l;
+        const double h = m.inv_n[s] * l;
+        const double inv_Rp = rc[9 + e], inv_sig = rc[11 + e], inv_Ds0 = rc[13 + e];
         const double Rp = s == 0 ? th[TF_Rp_p] : th[TF_Rp_n];
-        const double a = s == 1 ? 0.0 : 3 * eps_act / Rp;                               // build_a!
-        const double sig = (s == 0 ? th[TF_sigma_p] : th[TF_sigma_n]) * eps_act;       // build_sigma_eff
+        const double a = s == 1 ? 0.0 : 3 * eps_act * inv_Rp;                           // build_a!
+        const double sig = (s == 0 ? th[TF_sigma_p] : th[TF_sigma_n]) * eps_act;
         const double Dl = s == 0 ? th[TF_D_p] : (s == 1 ? th[TF_D_s] : th[TF_D_n]);
         // por^brugg: the shipped parameter sets use brugg = 4 (LCO) and 1.5 (NMC); a general pow() is ~150
         // instructions that every evaluation of K1 would pay
@@ -257,32 +281,33 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         const double T = th[TF_T0];
         const bool Tref = (T == kTref);   // temperature_switch, custom_functions.jl:1
         double Ds = s == 0 ? th[TF_D_sp] : th[TF_D_sn];
+        double inv_Ds = inv_Ds0;
         double k = s == 0 ? th[TF_k_p] : th[TF_k_n];
         if (!TH && !Tref && s != 1) {     // D_s_eff / rxn_rate Arrhenius, custom_functions.jl:16-57
             const double EaD = s == 0 ? th[TF_Ea_D_sp] : th[TF_Ea_D_sn];
             const double Eak = s == 0 ? th[TF_Ea_k_p] : th[TF_Ea_k_n];
-            Ds = Ds * exp(-EaD / kR * (1.0 / T - 1.0 / kTref));
-            k = k * exp(-(Eak / kR) * (1.0 / T - 1.0 / kTref));
+            const double dre = rc[17] - 1.0 / kTref;
+            const double arD = -EaD / kR * dre;
+            Ds = Ds * exp(arD); inv_Ds = inv_Ds * exp(-arD);
+            k = k * exp(-(Eak / kR) * dre);
         }
         const double cmax = s == 0 ? th[TF_c_max_p] : th[TF_c_max_n];
         C.sec[SC_h][s] = h;
-        C.sec[SC_inv_h][s] = 1.0 / h;
-        C.sec[SC_inv_por][s] = 1.0 / por;
+        C.sec[SC_inv_h][s] = rc[s];
+        C.sec[SC_inv_por][s] = rc[3 + s];
         C.sec[SC_pb][s] = pb;
         C.sec[SC_Dlin][s] = Dl * pb;
         C.sec[SC_src_ce][s] = (1 - th[TF_t_plus]) * a;
         C.sec[SC_hFa][s] = h * kF * a;
-        C.sec[SC_psf][s] = s == 1 ? 0.0 : h * h * a * kF / sig;
-        C.sec[SC_kap][s] = s == 1 ? 0.0 : Ds / (Rp * Rp);
-        C.sec[SC_inv_Rp][s] = s == 1 ? 0.0 : 1.0 / Rp;
-        C.sec[SC_Rp_Ds][s] = s == 1 ? 0.0 : Rp / Ds;
+        C.sec[SC_psf][s] = s == 1 ? 0.0 : h * h * a * kF * inv_sig;
+        C.sec[SC_kap][s] = s == 1 ? 0.0 : Ds * (inv_Rp * inv_Rp);
+        C.sec[SC_inv_Rp][s] = s == 1 ? 0.0 : inv_Rp;
+        C.sec[SC_Rp_Ds][s] = s == 1 ? 0.0 : Rp * inv_Ds;
         C.sec[SC_k2][s] = s == 1 ? 0.0 : 2.0 * k;
         C.sec[SC_cmax][s] = cmax;
-        C.sec[SC_inv_cmax][s] = 1.0 / cmax;
+        C.sec[SC_inv_cmax][s] = rc[15 + e];
         if (TH) {
-            const double rho = s == 0 ? th[TF_rho_p] : (s == 1 ? th[TF_rho_s] : th[TF_rho_n]);
-            const double Cp = s == 0 ? th[TF_Cp_p] : (s == 1 ? th[TF_Cp_s] : th[TF_Cp_n]);
-            C.sec[SC_irc][s] = 1.0 / (rho * Cp);
+            C.sec[SC_irc][s] = rc[6 + s];
             C.sec[SC_Fa][s] = kF * a;
             C.sec[SC_sig][s] = s == 1 ? 0.0 : sig;
             C.sec[SC_EaD][s] = s == 1 ? 0.0 : (s == 0 ? th[TF_Ea_D_sp] : th[TF_Ea_D_sn]) / kR;
@@ -291,10 +316,10 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         if (s == 0) {
             const double I1C = calc_I1C(th);
             C.g[GC_T] = T;
-            C.g[GC_xcoef] = 0.5 * kF / (kR * T);
-            C.g[GC_Kc] = 2 * kR * (1 - th[TF_t_plus]) / kF;
+            C.g[GC_xcoef] = (0.5 * kF / kR) * rc[17];
+            C.g[GC_Kc] = (2 * kR / kF) * (1 - th[TF_t_plus]);
             C.g[GC_I1C] = I1C;
-            C.g[GC_psI_p] = I1C * h / sig;     // d res_Phi_s[first p] / dI   (residuals.jl:679)
+            C.g[GC_psI_p] = I1C * h * inv_sig;   // d res_Phi_s[first p] / dI   (residuals.jl:679)
             C.g[GC_dUdT_on] = (m.chem == CHEM_LCO && (TH || !Tref)) ? 1.0 : 0.0;
             if (SEI) {
                 C.g[GC_RSEI] = th[TF_R_SEI]; C.g[GC_ikag] = 1.0 / th[TF_k_n_aging]; C.g[GC_Uref] = th[TF_Uref_s];
@@ -302,10 +327,10 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
             }
             if (TH) {
                 C.g[GC_Tamb] = th[TF_T_amb];
-                C.g[GC_invL] = 1.0 / (th[TF_l_a] + th[TF_l_p] + th[TF_l_s] + th[TF_l_n] + th[TF_l_z]);
+                C.g[GC_invL] = rc[18];
             }
         }
-        if (s == 2) C.g[GC_psI_n] = -calc_I1C(th) * h / sig;   // d res_Phi_s[last n] / dI (residuals.jl:680)
+        if (s == 2) C.g[GC_psI_n] = -calc_I1C(th) * h * inv_sig;   // d res_Phi_s[last n] / dI (residuals.jl:680)
     }
     grp_sync();
     {
@@ -315,10 +340,10 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         const int x1 = x + 1;
         const int s1 = x1 < m.Np ? 0 : (x1 < m.Np + m.Ns ? 1 : 2);
         const double h0 = C.sec[SC_h][s0], h1 = C.sec[SC_h][s1];
-        double d, b;
-        if (s0 == s1) { d = h0; b = 0.5; }
-        else { d = h0 / 2 + h1 / 2; b = (h0 / 2) / (h1 / 2 + h0 / 2); }
-        C.dinv[lane] = (x < m.Nx - 1) ? 1.0 / d : 0.0;
+        double dinv, b;
+        if (s0 == s1) { dinv = C.sec[SC_inv_h][s0]; b = 0.5; }
+        else { dinv = __drcp_rn(h0 / 2 + h1 / 2); b = (h0 / 2) * dinv; }
+        C.dinv[lane] = (x < m.Nx - 1) ? dinv : 0.0;
         C.beta[lane] = b;
     }
     grp_sync();

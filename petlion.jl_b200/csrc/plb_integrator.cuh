@@ -282,9 +282,10 @@ __device__ __forceinline__ void ewt_set(const ModelDesc& m, WarpWS& w, const Opt
 }
 
 // interpolation weights of IDAGetSolution at time t -> c[0..kord], d[0..kord-1]
-__device__ __forceinline__ int getsol_weights(const Ida& M, const IdaCoef& K, double t, double* c, double* d) {
+// (delt = t - tn.  For the previous step point pass -hused itself: formed as t_prev - tn it loses h's low bits, which
+// matters once h has shrunk to ~1e-8 s in front of a failure -- the weights of phi_2.. are then not exactly zero.)
+__device__ __forceinline__ int getsol_weights_delt(const Ida& M, const IdaCoef& K, double delt, double* c, double* d) {
     int kord = M.kused; if (kord == 0) kord = 1;
-    const double delt = t - M.tn;
     double cc = 1.0, dd = 0.0, gam = delt / K.psi[0];
     c[0] = cc;
 #pragma unroll 1
@@ -295,6 +296,9 @@ __device__ __forceinline__ int getsol_weights(const Ida& M, const IdaCoef& K, do
         c[j] = cc; d[j - 1] = dd;
     }
     return kord;
+}
+__device__ __forceinline__ int getsol_weights(const Ida& M, const IdaCoef& K, double t, double* c, double* d) {
+    return getsol_weights_delt(M, K, t - M.tn, c, d);
 }
 
 // IDASetCoeffs, scalar part (the phi scaling is fused into predict_pass).  Returns ck.

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -123,6 +124,7 @@ struct plb_handle_s {
     std::vector<double> opt_tstops;       // p.opts.tstops (params.jl:272): applied to every simulate call
     float last_ms = 0.f;
     int num_sms = 0;
+    bool k1_no_tma = getenv("PLB_K1_NO_TMA") != nullptr;    // A/B knob (profiles/k1_probe.py)
     // device staging buffers of PLB_MEM_HOST calls: grow-only, reused from call to call (a cudaMalloc /
     // cudaFree pair per argument and call costs more than the transfers themselves)
     static constexpr int NPOOL = 28;
@@ -240,6 +242,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     m.Na = m.thermal ? d->N_a : 0; m.Nz = m.thermal ? d->N_z : 0;
     m.chem = d->cathode == PLB_CATHODE_LCO ? CHEM_LCO : CHEM_NMC;
     m.mid = m.thermal ? m.Np + m.Ns / 2 : m.Nx / 2;
+    m.inv_n[0] = 1.0 / m.Np; m.inv_n[1] = 1.0 / m.Ns; m.inv_n[2] = 1.0 / m.Nn; m.inv_n[3] = 0.0;
     m.off_cs = m.Nx; m.off_T = m.off_cs + NR_HOST * m.Ne;
     m.off_film = m.off_T + (m.thermal ? m.Na + m.Nx + m.Nz : 0);
     m.off_SOH = m.off_film + (m.aging ? m.Nn : 0);
@@ -461,7 +464,10 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
     a.m = m; a.B = B; a.Y = Y; a.YP = YP; a.gamma = gamma; a.theta = theta; a.values = values;
     a.method = run->method; a.value = run->value; a.res = res; a.nzval = nzval; a.nnz = nnz;
     a.src = h->d_src[run->method];
-    const int grid = std::min((B + h->vi.k1_warps - 1) / h->vi.k1_warps, h->num_sms * h->vi.k1_ctas * 2);
+    // the bulk-copy (TMA) kernel needs 16-byte aligned input arrays; anything else takes the per-lane loads
+    a.use_tma = !h->k1_no_tma && (((uintptr_t)Y | (uintptr_t)YP | (uintptr_t)theta) & 15) == 0;
+    // one resident wave: every CTA loads the recipe tables once and then streams its share of the batch
+    const int grid = std::min((B + h->vi.k1_warps - 1) / h->vi.k1_warps, h->num_sms * h->vi.k1_ctas * (a.use_tma ? 1 : 2));
     CUDA_OK(cudaEventRecord(h->ev0, s));
     CUDA_OK(h->v->resjac(a, grid, s));
     CUDA_OK(cudaEventRecord(h->ev1, s));

@@ -311,12 +311,14 @@ __device__ __forceinline__ void after_nls(const ModelDesc& m, WarpWS& w, const O
     M.phase = 1;
     int fail = 0;
     if (retval != 0) {
-        M.ncfn++; S.ncf++;
+        if (lane == 0) M.ncfn++;     // statistics: written by one elected lane, read after the simulation's last barrier
+        S.ncf++;
         M.rr = 0.25;
         M.hh *= M.rr;
         if (S.ncf >= o.maxncf) fail = FAIL_CONV;
     } else {
-        S.nef++; M.netf++;
+        S.nef++;
+        if (lane == 0) M.netf++;
         if (S.nef == 1) {
             const double err_knew = (M.kk == M.knew) ? S.err_k : S.err_km1;
             M.kk = M.knew;
@@ -456,7 +458,8 @@ __device__ PLB_COLD void reinit_integration(const SimArgs& a, WarpWS& w, SimStat
     M.hh = 0.0; M.hused = 0.0; M.cj = 0.0; M.cjlast = 0.0; M.cjold = 0.0; M.cjratio = 1.0;
     M.ss = 20.0; M.rr = 0.0; M.tstop = 0.0;
     M.kk = 0; M.kused = 0; M.knew = 0; M.phase = 0; M.ns = 0; M.nst = 0; M.tstopset = 0;
-    S.reinit = 0; S.n_reinit++;
+    S.reinit = 0;
+    if (lane == 0) S.n_reinit++;
     S.pending = PEND_BEGIN;
 }
 
@@ -479,7 +482,13 @@ __device__ PLB_COLD void finish(const SimArgs& a, WarpWS& w, SimState& S, bool i
         grp_sync();
         if (lane == 0) {
             if (S.nsave <= 1) { w.K.cvals[0] = 1.0; w.K.cvals[1] = 0.0; w.K.dvals[0] = M.nst == 0 ? 1.0 : 1.0 / w.K.psi[0]; }
-            if (do_interp) { double dp[6]; getsol_weights(M, w.K, S.tprev, w.K.cprev, dp); }
+            if (do_interp) {
+                // Y_prev (sol.Y[end] of the reference) = the interpolant at the previous return time; when that was the
+                // previous step point, tn - hused, use the exact step
+                double dp[6];
+                const bool at_step = fabs((M.tn - M.hused) - S.tprev) <= 100.0 * DBL_EPSILON * (fabs(M.tn) + fabs(M.hused));
+                getsol_weights_delt(M, w.K, at_step ? -M.hused : S.tprev - M.tn, w.K.cprev, dp);
+            }
         }
         grp_sync();
         double ps0 = 0.0, psN = 0.0, If = 0.0, Tw = 0.0, aux = 0.0;
@@ -833,7 +842,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             if (need_jac) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
             else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
 #endif
-            S.M.nre++;
+            if (lane == 0) S.M.nre++;
         }
         bool lsetup_bad = false;
         if (any_jac) {
@@ -846,7 +855,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
 #else
                 warp_factor_impl(m, ro, J, ctrl, alg_only ? 0.0 : S.M.cj, alg_only, w.Fa, lane);
 #endif
-                S.M.nje++;
+                if (lane == 0) S.M.nje++;
                 const double chk = w.Fa.schur_inv;
                 lsetup_bad = !(chk == chk) || isinf(chk);
             }

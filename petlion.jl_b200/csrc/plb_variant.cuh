@@ -59,8 +59,12 @@ constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, the
 constexpr int K1_SRC_MAX = WIDE ? 4864 : (TH ? 3072 : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
-struct K1Warp {
-    double S[K1_NSTAGE][LW];   // lane-computed Jacobian entries
+// pitch of the value table: one double of padding per slot row.  Consecutive CSC entries of a column come from
+// different slots of the SAME lane (the rows of column c_e[x] are slots CE_U/CE_D/CE_L/J_CE/PC_* of lanes x-1..x+1),
+// which at pitch 32 all sit in one bank pair: ncu counted 23.6 M shared-memory bank conflicts per launch in the gather
+constexpr int K1_PITCH = LW + 1;
+struct alignas(16) K1Warp {
+    double S[K1_NSTAGE][K1_PITCH];   // lane-computed Jacobian entries
 #if PLB_TH
     double MCs[NR * NR];       // particle stencil coefficients (contiguous with S: one value table)
 #else
@@ -79,8 +83,8 @@ constexpr size_t K1_SMEM = XCH_BYTES_PER_GROUP * K1_WARPS + sizeof(K1Warp) * K1_
 // per system (200 fma) and the write loop is a pure gather  nzval[p] = table[recipe[p]]  -- coalesced,
 // branch-free, ~5 instructions per 32 entries.  Thermal family: D_s(T) differs per node, the block entries are
 // formed in the write loop from the recipe's flag bits.
-//   recipe: index into the warp's value table (lane-computed: slot*LW+lane; particle entries:
-//   K1_NSTAGE*LW + electrode*NR*NR + r*NR+c); thermal: bits 0-15 index (K1_NSTAGE*32 + r*NR+c),
+//   recipe: index into the warp's value table (lane-computed: slot*K1_PITCH+lane; particle entries:
+//   K1_NSTAGE*K1_PITCH + electrode*NR*NR + r*NR+c); thermal: bits 0-15 index (K1_NSTAGE*K1_PITCH + r*NR+c),
 //   16 particle-block entry, 18 diagonal, 19-23 node
 template <int CHEM>
 __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __grid_constant__ ResJacArgs a) {
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
             for (int p = lane; p < a.nnz; p += LW) {
                 const int rc = src_s[p];
                 const double t = tab[rc & 0xffff];
-                const double kap = tab[JS_KAP * 32 + ((rc >> 19) & 31)];
+                const double kap = tab[JS_KAP * K1_PITCH + ((rc >> 19) & 31)];
                 const double gd = (rc & (1 << 18)) ? g : 0.0;
                 gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
             }
@@ -232,6 +236,269 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
         grp_sync();
     }
 }
+
+#if !PLB_WIDE && !PLB_TH
+// =================================================================================================
+// K1, TMA-staged (isothermal and SEI families; the default whenever the caller's arrays are 16-byte aligned)
+// =================================================================================================
+// What the round-1 ncu source page of k_resjac showed (profiles/k1_r1i + profiles/ncu_by_region.py): 18 % of the
+// kernel's time waiting on the theta row (a dependent global load at the head of setup_consts), 20 % in the serial
+// per-section constants, 7 % on the lane-mapped Y / Y' loads (ten 80-byte-strided LDG per lane: 4x more L1 sectors
+// than bytes), 19 % in the gather loop.  Here:
+//   * the Y, Y', theta rows of a warp's NEXT system are bulk-copied (cp.async.bulk global -> shared, completion on
+//     an mbarrier) while the current system is evaluated and written: no lane ever waits on an input row, and L1
+//     sees no strided traffic at all;
+//   * the rows are read from shared memory with 128-bit accesses (a lane's ten radial values: five LDS.128);
+//   * the residual row is transposed through shared memory and leaves with 128-bit coalesced stores;
+//   * the gather loop moves two CSC entries per lane and iteration (one 32-bit recipe pair, two table reads, one
+//     STG.128).
+// Rows have odd length (N = 301, nnz = 2139, 35 parameters): row `sys` of a [B][len] array starts 16-byte aligned
+// only when sys*len is even.  A bulk copy needs 16-byte aligned addresses and sizes, so each row is split into its
+// largest aligned even-length part (bulk) and one edge element (fetched by a lane into a register at issue time);
+// in shared memory the row is shifted by `sh = (sys*len) & 1` doubles, which keeps the (global, shared) pairs
+// aligned alike.
+// nzval is NOT staged for a bulk store: a 17 KB row per warp would leave 6 warps per SM (measured in round 1: the
+// kernel is issue/latency bound, occupancy is what it lives on); its stores are already full 128-byte lines.
+constexpr int K1_VSIN = VS + 2;                       // staged row: N + shift, even
+constexpr int K1_THIN = 64;
+struct alignas(16) K1In {
+    double Y[K1_VSIN], YP[K1_VSIN], TH[K1_THIN];
+    unsigned long long bar;
+    unsigned long long pad;
+};
+constexpr size_t K1T_SMEM = sizeof(K1Warp) * K1_WARPS + sizeof(K1In) * K1_WARPS + sizeof(uint32_t) * K1_SRC_MAX + K1_MC_BYTES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "K1_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra K1_DONE;\n"
+        "bra K1_WAIT;\n"
+        "K1_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// the aligned part of row `sys` of a [B][len] array: shift sh, first bulk element, number of bulk elements,
+// index of the edge element (-1: none)
+struct RowSplit { int sh, cnt, edge; };
+__device__ __forceinline__ RowSplit row_split(long long sys, int len) {
+    RowSplit r;
+    r.sh = (int)((sys * len) & 1);
+    r.cnt = (len - r.sh) & ~1;
+    r.edge = (r.sh + r.cnt < len) ? len - 1 : (r.sh ? 0 : -1);
+    return r;
+}
+
+template <int CHEM>
+__global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac_tma(const __grid_constant__ ResJacArgs a) {
+    extern __shared__ __align__(16) unsigned char k1_raw[];
+    K1Warp* ws = reinterpret_cast<K1Warp*>(k1_raw);
+    K1In* ins = reinterpret_cast<K1In*>(k1_raw + sizeof(K1Warp) * K1_WARPS);
+    // recipe pairs: tabA[q] = (src[2q], src[2q+1]) for rows that start aligned, tabB[q] = (src[2q+1], src[2q+2]) for
+    // rows that start on an odd double; 16 bits each (table indices < 2^16)
+    uint32_t* tabA = reinterpret_cast<uint32_t*>(k1_raw + sizeof(K1Warp) * K1_WARPS + sizeof(K1In) * K1_WARPS);
+    uint32_t* tabB = tabA + K1_SRC_MAX / 2;
+    double* mc_s = reinterpret_cast<double*>(tabA + K1_SRC_MAX);
+    const int nnz = a.nnz;
+    for (int q = threadIdx.x; 2 * q < nnz; q += blockDim.x) {
+        const uint32_t s0 = a.src[2 * q], s1 = 2 * q + 1 < nnz ? a.src[2 * q + 1] : s0, s2 = 2 * q + 2 < nnz ? a.src[2 * q + 2] : s1;
+        tabA[q] = s0 | (s1 << 16);
+        tabB[q] = s1 | (s2 << 16);
+    }
+    for (int i = threadIdx.x; i < NR * NR; i += blockDim.x) mc_s[i] = laws::MC[i / NR][i % NR];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    K1Warp& w = ws[warp];
+    K1In& in = ins[warp];
+    if (lane == 0) mbar_init(&in.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const ModelDesc& m = a.m;
+    const int N = m.N_tot, NT = m.ntheta;
+    const LaneRole ro = make_role(m, lane);
+    const int nwarps = gridDim.x * K1_WARPS;
+    const uint32_t src_first = a.src[0], src_last = a.src[nnz - 1];
+    // ---- issue the bulk copies (and the edge / scalar fetches) of one system into this warp's staging buffer ----
+    double edge = 0.0, g_next = 0.0, v_next = a.value;
+    int edge_slot = -1;
+    auto issue = [&](int sys) {
+        const RowSplit rY = row_split(sys, N), rT = row_split(sys, NT);
+        const double* gY = a.Y + (size_t)sys * N;
+        const double* gYP = a.YP + (size_t)sys * N;
+        const double* gT = a.theta + (size_t)sys * m.theta_stride;
+        if (lane == 0) {
+            // the generic-proxy reads of the buffer (previous system) are complete: order them before the async writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&in.bar, (uint32_t)((2 * rY.cnt + rT.cnt) * sizeof(double)));
+            bulk_g2s(in.Y + 2 * rY.sh, gY + rY.sh, rY.cnt * sizeof(double), &in.bar);
+            bulk_g2s(in.YP + 2 * rY.sh, gYP + rY.sh, rY.cnt * sizeof(double), &in.bar);
+            bulk_g2s(in.TH + 2 * rT.sh, gT + rT.sh, rT.cnt * sizeof(double), &in.bar);
+        }
+        // edge elements: lanes 0, 1, 2 hold the one of Y, Y', theta in a register until the buffer is consumed next
+        edge_slot = -1;
+        if (lane < 2 && rY.edge >= 0) { edge = (lane == 0 ? gY : gYP)[rY.edge]; edge_slot = rY.edge + rY.sh; }
+        if (lane == 2 && rT.edge >= 0) { edge = gT[rT.edge]; edge_slot = rT.edge + rT.sh; }
+        g_next = a.gamma ? a.gamma[sys] : 0.0;
+        v_next = a.values ? a.values[sys] : a.value;
+    };
+    int sys = blockIdx.x * K1_WARPS + warp;
+    uint32_t phase = 0;
+    if (sys < a.B) issue(sys);
+    for (; sys < a.B; sys += nwarps) {
+        const int shY = (int)(((long long)sys * N) & 1), shT = (int)(((long long)sys * NT) & 1);
+        // a row shifted by sh lives at [sh .. sh+len): its bulk part starts at element sh, i.e. at slot 2*sh
+        // (sh = 1: element 1 at slot 2, 16-byte aligned; element 0 at slot 1)
+        if (edge_slot >= 0) (lane == 0 ? in.Y : (lane == 1 ? in.YP : in.TH))[edge_slot] = edge;
+        const double g = g_next, value = v_next;
+        __syncwarp();
+        mbar_wait(&in.bar, phase);
+        phase ^= 1;
+        const double* __restrict__ sY = in.Y + shY;
+        const double* __restrict__ sYP = in.YP + shY;
+        LaneVec y, yp, res;
+        y.ce = ro.act ? sY[ro.x] : 0.0; yp.ce = ro.act ? sYP[ro.x] : 0.0;
+        y.pe = ro.act ? sY[m.off_pe + ro.x] : 0.0; yp.pe = 0.0;
+        if (ro.elec) {
+            const double* pc = sY + m.off_cs + ro.e * NR;
+            const double* pp = sYP + m.off_cs + ro.e * NR;
+            if (((m.off_cs + shY) & 1) == 0) {
+#pragma unroll
+                for (int k = 0; k < NR / 2; k++) {
+                    const double2 t = reinterpret_cast<const double2*>(pc)[k], u = reinterpret_cast<const double2*>(pp)[k];
+                    y.cs[2 * k] = t.x; y.cs[2 * k + 1] = t.y; yp.cs[2 * k] = u.x; yp.cs[2 * k + 1] = u.y;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NR; r++) { y.cs[r] = pc[r]; yp.cs[r] = pp[r]; }
+            }
+            y.j = sY[m.off_j + ro.e]; y.ps = sY[m.off_ps + ro.e];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) { y.cs[r] = 0.0; yp.cs[r] = 0.0; }
+            y.j = 0.0; y.ps = 0.0;
+        }
+        yp.j = 0.0; yp.ps = 0.0;
+        y.T = 0.0; y.Tx = 0.0; yp.T = 0.0; yp.Tx = 0.0;
+        y.js = 0.0; y.film = 0.0; y.soh = 0.0; yp.js = 0.0; yp.film = 0.0; yp.soh = 0.0;
+        if (SEI) {
+            const int k = ro.x - (m.Np + m.Ns);
+            if (ro.sec == 2) { y.js = sY[m.off_js + k]; y.film = sY[m.off_film + k]; yp.film = sYP[m.off_film + k]; }
+            y.soh = sY[m.off_SOH]; yp.soh = sYP[m.off_SOH];
+        }
+        const double Iapp = sY[m.off_I];
+        setup_consts(m, in.TH + shT, w.C, lane);
+        __syncwarp();
+        // every lane has taken what it needs from the staging buffer: refill it with the warp's next system
+        if (sys + nwarps < a.B) issue(sys + nwarps);
+        LaneJac J;
+        CtrlRow ctrl;
+        if (a.nzval) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iapp, a.method, value, res, ctrl, J);
+        else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iapp, a.method, value, res, ctrl, J);
+        if (a.res) {
+            // transpose through shared memory (the value table is free until the Jacobian is staged), then
+            // 128-bit coalesced stores; slot = element + shift keeps the global pairs 16-byte aligned
+            double* row = &w.S[0][0] + shY;
+            if (ro.act) { row[ro.x] = res.ce; row[m.off_pe + ro.x] = res.pe; }
+            if (ro.elec) {
+                double* pc = row + m.off_cs + ro.e * NR;
+                if (((m.off_cs + shY) & 1) == 0) {
+#pragma unroll
+                    for (int k = 0; k < NR / 2; k++) reinterpret_cast<double2*>(pc)[k] = make_double2(res.cs[2 * k], res.cs[2 * k + 1]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) pc[r] = res.cs[r];
+                }
+                row[m.off_j + ro.e] = res.j;
+                row[m.off_ps + ro.e] = res.ps;
+            }
+            if (SEI) {
+                const int k = ro.x - (m.Np + m.Ns);
+                if (ro.sec == 2) { row[m.off_js + k] = res.js; row[m.off_film + k] = res.film; }
+                if (lane == 0) row[m.off_SOH] = res.soh;
+            }
+            if (lane == 0) row[m.off_I] = ctrl.res;
+            __syncwarp();
+            double* __restrict__ gR = a.res + (size_t)sys * N;
+            const double2* row2 = reinterpret_cast<const double2*>(&w.S[0][0]);
+            // pair q = slots (2q, 2q+1) = elements (2q - sh, 2q + 1 - sh)
+#pragma unroll 2
+            for (int q = lane; 2 * q - shY + 1 < N; q += 32) {
+                const int j0 = 2 * q - shY;
+                const double2 v = row2[q];
+                if (j0 >= 0) *reinterpret_cast<double2*>(gR + j0) = v;
+                else gR[0] = v.y;
+            }
+            if (lane == 0 && ((N - shY) & 1)) gR[N - 1] = row[N - 1];
+            __syncwarp();
+        }
+        if (a.nzval) {
+            w.S[JS_CE_L][lane] = J.ceL; w.S[JS_CE_D][lane] = J.ceD - g; w.S[JS_CE_U][lane] = J.ceU; w.S[JS_CE_J][lane] = J.ce_j;
+            w.S[JS_J_CS][lane] = J.j_cs; w.S[JS_J_CE][lane] = J.j_ce; w.S[JS_J_PE][lane] = J.j_pe; w.S[JS_J_PS][lane] = J.j_ps;
+#if PLB_SEI
+            w.S[JS_J_J][lane] = J.j_j;
+            w.S[JS_J_FILM][lane] = J.j_film;
+            w.S[JS_JS_PS][lane] = J.js_ps; w.S[JS_JS_PE][lane] = J.js_pe; w.S[JS_JS_J][lane] = J.js_j;
+            w.S[JS_JS_JS][lane] = J.js_js; w.S[JS_JS_FILM][lane] = J.js_film; w.S[JS_JS_I][lane] = J.js_I;
+            w.S[JS_FILM_JS][lane] = J.film_js; w.S[JS_FILM_D][lane] = -g;
+            w.S[JS_SOH_JS][lane] = J.soh_js; w.S[JS_SOH_D][lane] = -g;
+            w.S[JS_CE_JS][lane] = J.ce_j; w.S[JS_PE_JS][lane] = J.pe_j; w.S[JS_PS_JS][lane] = J.ps_j;
+#else
+            w.S[JS_J_J][lane] = -1.0;
+#endif
+            w.S[JS_PE_L][lane] = J.peL; w.S[JS_PE_D][lane] = J.peD; w.S[JS_PE_U][lane] = J.peU;
+            w.S[JS_PC_L][lane] = J.pcL; w.S[JS_PC_D][lane] = J.pcD; w.S[JS_PC_U][lane] = J.pcU; w.S[JS_PE_J][lane] = J.pe_j;
+            w.S[JS_PS_L][lane] = J.psL; w.S[JS_PS_D][lane] = J.psD; w.S[JS_PS_U][lane] = J.psU; w.S[JS_PS_J][lane] = J.ps_j;
+            w.S[JS_PS_I][lane] = J.ps_I;
+            w.S[JS_CS_J][lane] = J.cs_j;
+            w.S[k1_stage_slot(JS_CTRL_PS0)][lane] = ctrl.g_ps0;
+            w.S[k1_stage_slot(JS_CTRL_PSN)][lane] = ctrl.g_psN;
+            w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
+            w.S[k1_stage_slot(JS_CTRL_T)][lane] = g * ctrl.gTn;
+            w.S[k1_stage_slot(JS_CTRL_TX)][lane] = g * ctrl.gTx;
+            w.S[k1_stage_slot(JS_CTRL_EPS)][lane] = ctrl.g_eta;
+            w.S[k1_stage_slot(JS_CTRL_EPE)][lane] = -ctrl.g_eta;
+            {   // the two particle blocks of this system
+                const double kap_p = w.C.sec[SC_kap][0], kap_n = w.C.sec[SC_kap][2];
+#pragma unroll
+                for (int i = lane; i < NR * NR; i += LW) {
+                    const double mc = mc_s[i];
+                    const double gd = (i % (NR + 1) == 0) ? g : 0.0;
+                    w.PB[0][i] = fma(kap_p, mc, -gd);
+                    w.PB[1][i] = fma(kap_n, mc, -gd);
+                }
+            }
+            __syncwarp();
+            const double* tab = &w.S[0][0];
+            double* __restrict__ gN = a.nzval + (size_t)sys * nnz;
+            const int par = (int)(((long long)sys * nnz) & 1);
+            const uint32_t* __restrict__ tp = par ? tabB : tabA;
+            const int nfull = (nnz - par) >> 1;
+            double2* __restrict__ g2 = reinterpret_cast<double2*>(gN + par);
+            _Pragma(PLB_STR(unroll PLB_K1_UNROLL))
+            for (int q = lane; q < nfull; q += 32) {
+                const uint32_t u = tp[q];
+                g2[q] = make_double2(tab[u & 0xffffu], tab[u >> 16]);
+            }
+            if (lane == 0 && par) gN[0] = tab[src_first];
+            if (lane == 1 && ((nnz - par) & 1)) gN[nnz - 1] = tab[src_last];
+        }
+        __syncwarp();
+    }
+}
+#endif
 
 // structural enumeration of the Jacobian: (row, col) in the reference layout for slot/lane
 bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& col) {
@@ -359,12 +626,12 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
         const int el = lane >= m.Np + m.Ns ? 1 : 0;
 #if PLB_TH
         (void)el;
-        return (K1_NSTAGE * LW + rr * NR + cc) | (1 << 16) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
+        return (K1_NSTAGE * K1_PITCH + rr * NR + cc) | (1 << 16) | ((rr == cc ? 1 : 0) << 18) | (lane << 19);
 #else
-        return K1_NSTAGE * LW + el * NR * NR + rr * NR + cc;
+        return K1_NSTAGE * K1_PITCH + el * NR * NR + rr * NR + cc;
 #endif
     }
-    return k1_stage_slot(slot) * LW + lane;
+    return k1_stage_slot(slot) * K1_PITCH + lane;
 }
 
 // =================================================================================================
@@ -555,7 +822,12 @@ VariantInfo info() {
         return cudaGetLastError();                                                                                  \
     } while (0)
 
-cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_resjac, a, grid, K1_WARPS * LW, K1_SMEM, s); }
+cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) {
+#if !PLB_WIDE && !PLB_TH
+    if (a.use_tma) PLB_LAUNCH(k_resjac_tma, a, grid, K1_WARPS * LW, K1T_SMEM, s);
+#endif
+    PLB_LAUNCH(k_resjac, a, grid, K1_WARPS * LW, K1_SMEM, s);
+}
 cudaError_t launch_initguess(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_initguess, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 cudaError_t launch_newton(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_newton, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }
 cudaError_t launch_linsolve(const AuxArgs& a, int grid, cudaStream_t s) { PLB_LAUNCH(k_linsolve, a, grid, SIM_WARPS * LW, SIM_SMEM, s); }

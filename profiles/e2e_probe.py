@@ -6,11 +6,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P
 from petlion_b200 import _lib
-from bench import synth_theta
+from petlion_b200 import sweep
 L = _lib.lib()
 p = P.petlion("LCO"); h = p._h
 B = int(os.environ.get("B", 65536)); N = p.N.tot
-th, _ = synth_theta(p, B, 0)
+th = sweep.randomised_theta(p, B)
 o = _lib.Opts(); L.plb_opts_defaults(h, C.byref(o))
 b = _lib.Bounds(); L.plb_bounds_defaults(h, C.byref(b))
 run = _lib.Run(0, 0, -1.0, 1e6, 1, 0)

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P
 from petlion_b200 import _lib
-from bench import synth_theta
+from petlion_b200 import sweep  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 fam = sys.argv[2] if len(sys.argv) > 2 else "iso"
 L = _lib.lib()
@@ -13,7 +13,7 @@ grid = dict(N_p=20, N_s=20, N_n=20) if fam == "wsei" else {}
 p = P.petlion("LCO", temperature=fam == "thermal", aging="SEI" if fam in ("sei", "wsei") else False, **grid)
 h = p._h; N = p.N.tot; nth = len(p.θ_keys)
 dev = torch.device("cuda", 0); f64 = dict(dtype=torch.float64, device=dev)
-th, _ = synth_theta(p, B, 0)
+th = sweep.randomised_theta(p, B)
 d_theta = torch.from_numpy(th).to(dev)
 cur, soc, tmid = (4.0, 0.0, 150.0) if fam == "thermal" else ((1.0, 0.0, 1800.0) if fam in ("sei", "wsei") else (-1.0, 1.0, 1800.0))
 d_soc0 = torch.full((B,), soc, **f64)
@@ -37,4 +37,4 @@ for k in range(8):
 bytes_eval = 8 * (3 * N + nth + nnz) + 16
 t = float(np.mean(ms[3:]))
 print(os.path.basename(os.environ.get("PLB_LIB", "default")), fam, "B", B, "ms", round(t, 4), "GB/s", round(B * bytes_eval / t / 1e6), "frac", round(B * bytes_eval / t / 1e6 / 6551, 4),
-      "chk", float(d_nz.sum().item()), flush=True)
+      "chk", float(d_nz.sum().item()), float(d_res.abs().sum().item()), flush=True)

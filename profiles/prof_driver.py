@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P  # noqa: E402
 from petlion_b200 import _lib  # noqa: E402
-from bench import synth_theta  # noqa: E402
+from petlion_b200 import sweep  # noqa: E402
 
 B1 = int(os.environ.get("PROF_B1", 65536))
 B4 = int(os.environ.get("PROF_B4", 8192))
@@ -24,7 +24,7 @@ h = p._h
 N = p.N.tot
 dev = torch.device("cuda", 0)
 f64 = dict(dtype=torch.float64, device=dev)
-th, _ = synth_theta(p, B1, 0)
+th = sweep.randomised_theta(p, B1)
 d_theta = torch.from_numpy(th).to(dev)
 d_soc0 = torch.full((B1,), 1.0 if FAM == "iso" else 0.0, **f64)
 CUR = 4.0 if TH else (1.0 if FAM in ("sei", "wsei") else -1.0)

@@ -13,6 +13,9 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
+# (offset by 7 s: most runs end at t = 3600 s to round-off, a requested time there is filled by one side only)
+DENSE_T = np.concatenate([[0.0], np.arange(7.0, 3700.0, 30.0), [1e6]])
+
 
 @pytest.fixture(scope="module")
 def P():
@@ -102,7 +105,7 @@ def test_newton_init_parity(lco):
         assert np.max(np.abs(YP[s] - yp) / scale) < 1e-6
 
 
-def _compare_runs(sol, ref, rtol=1e-6, min_identical=1.0):
+def _compare_runs(sol, ref, rtol=1e-6, min_identical=1.0, flip_tol=5e-3):
     summ = sol.results[-1].summary
     same_steps = summ["n_steps"] == ref["n_steps"]
     assert np.mean(same_steps) >= min_identical, (np.mean(same_steps), np.where(~same_steps)[0][:10])
@@ -120,6 +123,54 @@ def _compare_runs(sol, ref, rtol=1e-6, min_identical=1.0):
         np.testing.assert_allclose(sol.t[s, :n], ref["traj"]["t"][s, :n], rtol=rtol, atol=1e-9)
         np.testing.assert_allclose(sol.SOC[s, :n], ref["traj"]["SOC"][s, :n], rtol=rtol, atol=1e-8)
     assert worst < rtol, worst
+    if sol.dense is not None and ref.get("dense") is not None:
+        bound_flipped(sol.results[-1].summary, sol.dense, ref, tol=flip_tol)
+    else:
+        bound_flipped_rows(sol, ref, tol=flip_tol)
+    return worst
+
+
+def bound_flipped_rows(sol, ref, tol=5e-3, margin=30.0):
+    """the same bound from the saved rows when no dense output was requested: the GPU's rows of the LAST run of `sol`
+    interpolated linearly at the oracle's step times"""
+    summ = sol.results[-1].summary
+    assert np.array_equal(summ["flag"] < 0, ref["flag"] < 0)
+    okb = (summ["flag"] >= 0) & (ref["flag"] >= 0)
+    n_new = sol.results[-1].n_rows
+    for i in np.where(okb & ((summ["n_steps"] != ref["n_steps"]) | (summ["flag"] != ref["flag"])))[0]:
+        a0 = sol.n_points[i] - n_new[i]
+        gt, gV, gS = (x[i, a0:sol.n_points[i]] for x in (sol.t, sol.V, sol.SOC))
+        n = ref["traj_n"][i]
+        rt, rV, rS = ref["traj"]["t"][i, :n], ref["traj"]["V"][i, :n], ref["traj"]["SOC"][i, :n]
+        sel = rt <= min(gt[-1], rt[-1]) - margin
+        if not sel.any():
+            continue
+        assert np.max(np.abs(np.interp(rt[sel], gt, gV) - rV[sel]) / np.abs(rV[sel])) <= tol
+        assert np.max(np.abs(np.interp(rt[sel], gt, gS) - rS[sel])) <= tol
+        assert abs(summ["t_end"][i] - ref["t_end"][i]) <= tol * max(ref["t_end"][i] - rt[0], 1.0)
+
+
+def bound_flipped(summ, dense, ref, tol=5e-3, margin=30.0):
+    """The systems that took a different discrete decision somewhere (a Newton-convergence or error-test threshold
+    crossed by round-off) are two runs of an adaptive integrator at tolerance reltol = 1e-3: they must still agree to
+    a few reltol (tol = 5 reltol).  Compared on a common grid through the dense output of both sides, up to `margin` seconds before the
+    earlier of the two ends (the last step of a run is the linear blend of interp_final_points!, and where one side
+    exits on V_min and the other on SOC_min the voltage falls by volts per minute).  Returns the worst values."""
+    assert dense is not None and ref.get("dense") is not None, "run both sides with dense output"
+    okb = (summ["flag"] >= 0) & (ref["flag"] >= 0)
+    flipped = okb & ~np.all([summ[k] == ref[k] for k in ("n_steps", "flag", "n_res", "n_jac", "n_netf", "n_ncfn")], axis=0)
+    # hard failures: both sides must agree on WHICH systems fail
+    assert np.array_equal(summ["flag"] < 0, ref["flag"] < 0), (np.where((summ["flag"] < 0) != (ref["flag"] < 0))[0][:10])
+    td = dense["t"]
+    worst = dict(n_flipped=int(flipped.sum()), dV=0.0, dSOC=0.0, dt_end=0.0)
+    for i in np.where(flipped)[0]:
+        sel = td <= min(summ["t_end"][i], ref["t_end"][i]) - margin
+        a, b = dense["V"][i, sel], ref["dense"]["V"][i, sel]
+        assert not np.isnan(a).any() and not np.isnan(b).any()
+        worst["dV"] = max(worst["dV"], float(np.max(np.abs(a - b) / np.abs(b))))
+        worst["dSOC"] = max(worst["dSOC"], float(np.max(np.abs(dense["SOC"][i, sel] - ref["dense"]["SOC"][i, sel]))))
+        worst["dt_end"] = max(worst["dt_end"], abs(summ["t_end"][i] - ref["t_end"][i]) / ref["t_end"][i])
+    assert worst["dV"] <= tol and worst["dSOC"] <= tol and worst["dt_end"] <= tol, worst
     return worst
 
 
@@ -128,9 +179,9 @@ def test_simulate_nominal_1C_discharge(P, lco, goldens):
     m = O.make_model("LCO")
     for k, v in zip(lco.θ_keys, P.petlion("LCO").θ.values()):
         lco.θ[k] = v
-    sol = P.simulate(lco, I=-1, SOC=1)
+    sol = P.simulate(lco, I=-1, SOC=1, dense_t=DENSE_T)
     ref = O.simulate_batch(m, O.theta_defaults("LCO"), O.make_run("I", -1.0), O.default_opts(),
-                           O.default_bounds("LCO"), SOC0=1.0, n_save_max=512)
+                           O.default_bounds("LCO"), SOC0=1.0, n_save_max=512, dense_t=DENSE_T)
     s = sol.results[-1].summary
     assert s["n_steps"][0] == 80 and s["flag"][0] == 3
     assert abs(s["t_end"][0] - 3600.0) < 1e-6
@@ -148,11 +199,33 @@ def test_simulate_randomised_batch_parity(P, lco):
     tho = util.oracle_theta_batch(B)
     th = util.product_theta_from_oracle(lco, tho)
     util.set_theta_batch(lco, th)
-    sol = P.simulate(lco, I=-1, SOC=1)
+    sol = P.simulate(lco, I=-1, SOC=1, dense_t=DENSE_T)
     ref = O.simulate_batch(m, tho, O.make_run("I", -1.0), O.default_opts(), O.default_bounds("LCO"),
-                           SOC0=1.0, n_save_max=512, nthreads=8)
+                           SOC0=1.0, n_save_max=512, nthreads=8, dense_t=DENSE_T)
     assert np.all(np.isin(ref["flag"], (1, 3)))      # SOC_min, or V_min for the slow-diffusion draws
     _compare_runs(sol, ref, min_identical=0.98)
+
+
+def test_flipped_systems_are_bounded_on_a_common_grid(P, lco):
+    """4 096 randomised systems: EVERY system is accounted for -- identical step sequence (V to 1e-6), or a different
+    sequence whose V(t), SOC(t) agree to 5*reltol on a common grid, or a hard failure that the oracle shares."""
+    m = O.make_model("LCO")
+    B = 4096
+    tho = util.oracle_theta_batch(B, first=20000)
+    util.set_theta_batch(lco, util.product_theta_from_oracle(lco, tho))
+    sol = P.simulate(lco, I=-1, SOC=1, dense_t=DENSE_T, n_save_max=0)
+    ref = O.simulate_batch(m, tho, O.make_run("I", -1.0), O.default_opts(), O.default_bounds("LCO"),
+                           SOC0=1.0, nthreads=16, dense_t=DENSE_T)
+    s = sol.results[-1].summary
+    # identical sequence: every counter of the run agrees (steps, residual and Jacobian evaluations, failures)
+    same = (ref["flag"] >= 0) & np.all([s[k] == ref[k] for k in ("n_steps", "flag", "n_res", "n_jac", "n_netf", "n_ncfn")], axis=0)
+    assert same.mean() > 0.9
+    fill = ~np.isnan(ref["dense"]["V"][same]) & ~np.isnan(sol.dense["V"][same])
+    assert (np.isnan(ref["dense"]["V"][same]) != np.isnan(sol.dense["V"][same])).sum(axis=1).max() <= 1
+    np.testing.assert_allclose(sol.dense["V"][same][fill], ref["dense"]["V"][same][fill], rtol=1e-6)
+    np.testing.assert_allclose(s["t_end"][same], ref["t_end"][same], rtol=1e-6)
+    w = bound_flipped(s, sol.dense, ref)
+    print("identical", same.mean(), "flipped", w, "hard failures", int((ref["flag"] < 0).sum()))
 
 
 def test_simulate_cccv_continuation(P, lco):
@@ -162,9 +235,10 @@ def test_simulate_cccv_continuation(P, lco):
     tho = util.oracle_theta_batch(B, first=1000)
     th = util.product_theta_from_oracle(lco, tho)
     util.set_theta_batch(lco, th)
-    sol = P.simulate(lco, I=2, SOC=0, V_max=4.1)
+    sol = P.simulate(lco, I=2, SOC=0, V_max=4.1, dense_t=DENSE_T)
     b = O.default_bounds("LCO", V_max=4.1)
-    ref = O.simulate_batch(m, tho, O.make_run("I", 2.0), O.default_opts(), b, SOC0=0.0, n_save_max=512, nthreads=8)
+    ref = O.simulate_batch(m, tho, O.make_run("I", 2.0), O.default_opts(), b, SOC0=0.0, n_save_max=512, nthreads=8,
+                           dense_t=DENSE_T)
     assert np.all(ref["flag"] == 2)
     _compare_runs(sol, ref, min_identical=0.9)
     n1 = sol.n_points.copy()

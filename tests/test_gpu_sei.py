@@ -177,3 +177,46 @@ def test_simulate_charge_and_discharge(P, lcoS, mS):
     assert np.mean(same) >= 0.8
     np.testing.assert_allclose(s2["V_end"][same], ref2["V_end"][same], rtol=1e-6)
     np.testing.assert_allclose(s2["t_end"][same], ref2["t_end"][same], rtol=1e-5)
+
+
+def test_soh_film_linear_invariant_on_device(P, lcoS, mS):
+    """SOH - 1 = -(K rho_n/M_n) sum_i w_i film_i for every system, whatever steps the integrator took
+    (tests/test_oracle_sei.py derives the weights independently): a known answer for the SEI rows"""
+    from tests.test_oracle_sei import _K, soh_weights
+    B = 64
+    tho = util.oracle_theta_batch(B, first=900)
+    th = util.product_theta_from_oracle(lcoS, tho)
+    util.set_theta_batch(lcoS, th)
+    sol = P.simulate(lcoS, I=1, SOC=0, V_max=4.2, reltol=1e-6, abstol=1e-6)
+    names = O.theta_names()
+    film = sol.Y[:, lcoS.ind["film"]]
+    soh = sol.Y[:, lcoS.ind["SOH"]][:, 0]
+    assert np.array_equal(soh, sol.results[-1].summary["aux_end"])
+    assert film.min() > 0 and np.all(soh < 1)
+    for s in range(B):
+        thd = dict(zip(names, tho[s]))
+        rhs = -_K(thd) * thd["rho_n"] / thd["M_n"] * np.dot(soh_weights(10, thd["l_n"]), film[s])
+        np.testing.assert_allclose(soh[s] - 1.0, rhs, rtol=2e-5)
+
+
+def test_discharge_without_film_resistance_is_the_model_without_aging(P, lcoS):
+    """j_s = 0 on discharge (residuals.jl:546): with R_SEI = 0 the aging model IS the isothermal model -- the GPU's SEI
+    family against the GPU's isothermal family at tight tolerance (their WRMS norms differ by sqrt(322/301))"""
+    B = 16
+    tho = util.oracle_theta_batch(B, first=940)
+    tho[:, O.theta_names().index("R_SEI")] = 0.0
+    iso = P.petlion("LCO")
+    util.set_theta_batch(lcoS, util.product_theta_from_oracle(lcoS, tho))
+    util.set_theta_batch(iso, util.product_theta_from_oracle(iso, tho))
+    td = np.concatenate([np.arange(0.0, 3600.0, 60.0), [1e6]])
+    a = P.simulate(lcoS, td, I=-1, SOC=1, reltol=1e-9, abstol=1e-9, n_save_max=0, outputs="all")
+    b = P.simulate(iso, td, I=-1, SOC=1, reltol=1e-9, abstol=1e-9, n_save_max=0)
+    sa, sb = a.results[-1].summary, b.results[-1].summary
+    assert np.array_equal(sa["flag"], sb["flag"])
+    # (a run that ends on V_min ends on the linear blend of its last step: h^2-accurate, see tests/test_gpu_tight.py)
+    np.testing.assert_allclose(sa["t_end"], sb["t_end"], rtol=1e-4)
+    fill = ~np.isnan(b.dense["V"])
+    assert np.array_equal(fill, ~np.isnan(a.dense["V"]))
+    np.testing.assert_allclose(a.dense["V"][fill], b.dense["V"][fill], rtol=1e-6)
+    assert np.abs(a.Y[:, lcoS.ind["j_s"]]).max() < 1e-20 and np.abs(a.Y[:, lcoS.ind["film"]]).max() < 1e-24
+    assert np.abs(sa["aux_end"] - 1.0).max() < 1e-14

@@ -94,7 +94,8 @@ def test_step_current_randomised_batch_with_scales(P, lco):
     assert np.all(ref["flag"] == 0) and np.all(ref["n_reinit"] >= 1)
     same = s["n_steps"] == ref["n_steps"]
     assert np.array_equal(s["n_reinit"][same], ref["n_reinit"][same])
-    _compare_runs(sol, ref, min_identical=0.9)
+    # (two runs that step over an untold jump of the input differently differ by more than 5 reltol next to it)
+    _compare_runs(sol, ref, min_identical=0.9, flip_tol=2e-2)
     np.testing.assert_allclose(s["I_end"], 0.25 * scale, rtol=1e-9)
 
 

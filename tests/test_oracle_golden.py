@@ -357,3 +357,24 @@ def test_user_stop_times_merge_like_postfix_integrator():
                           O.default_bounds("LCO"), state=r["state"], n_save_max=400)
     t2 = r2["traj"]["t"][0, :r2["traj_n"][0]] - 1000.0
     assert all(np.any(np.abs(t2 - x) < 1e-9) for x in (0.25, 1.0, 40.0))
+
+
+def test_exit_blend_is_second_order():
+    """The END of a run that trips a bound is the linear blend of the last step (interp_final_points!,
+    model_evaluation.jl:369-382): h^2-accurate in the last step size whatever the tolerance.  The oracle against
+    itself at 1e-9 and 1e-10: the trajectory (dense rows, both sides' own interpolant) agrees to 1e-8, the end values
+    only to ~1e-5 -- which is why tests/test_gpu_tight.py holds end values of runs with different last steps to
+    BLEND_TOL instead of 1e-6."""
+    m = O.make_model("LCO")
+    th = O.theta_defaults("LCO")[None, :]
+    td = np.arange(0.0, 3590.0, 100.0)
+    r = {}
+    for tol in (1e-9, 1e-10):
+        o = O.default_opts(reltol=tol, abstol=tol, reltol_init=tol, abstol_init=tol)
+        r[tol] = O.simulate_batch(m, th, O.make_run("I", -2.0), o, O.default_bounds("LCO"), SOC0=1.0, dense_t=td)
+    a, b = r[1e-9], r[1e-10]
+    assert a["flag"][0] == b["flag"][0] == 1 and a["n_steps"][0] != b["n_steps"][0]          # 2C: ends on V_min
+    fill = ~np.isnan(a["dense"]["V"]) & ~np.isnan(b["dense"]["V"])
+    assert np.max(np.abs(a["dense"]["V"][fill] - b["dense"]["V"][fill]) / b["dense"]["V"][fill]) < 2e-8
+    dt = abs(a["t_end"][0] - b["t_end"][0]) / b["t_end"][0]
+    assert 1e-8 < dt < 2e-4

@@ -82,3 +82,57 @@ def random_states(m, th_oracle, seed=1, SOC_lo=0.1, SOC_hi=0.9, rel=0.02):
         Y[s] = y + rel * scale * rng.uniform(-1, 1, size=y.shape)
         YP[s] = yp * (1 + 0.1 * rng.uniform(-1, 1, size=y.shape))
     return Y, YP
+
+
+# ---- protocols of BASELINE.json configs[1..4] (segments: method, input kind, value, local tf, bound overrides) --------
+PROTOCOLS = {
+    "cfg2": dict(cathode="LCO", soc0=1.0, segs=[("I", "value", -1.0, 1e6, {})]),
+    "cfg3": dict(cathode="LCO", temperature=True, soc0=0.0,
+                 segs=[("I", "value", 4.0, 1e6, {"V_max": 4.1}), ("V", "hold", 0.0, 1e6, {"V_max": 4.1})]),
+    # the same with the reference's own end of a CV phase (examples/CC-CV.ipynb: I_min = 1/20) instead of running the
+    # hold to SOC_max or 1e6 s
+    "cfg3i": dict(cathode="LCO", temperature=True, soc0=0.0,
+                  segs=[("I", "value", 4.0, 1e6, {"V_max": 4.1}), ("V", "hold", 0.0, 1e6, {"V_max": 4.1, "I_min": 0.05})]),
+    "cfg4": dict(cathode="NMC", soc0=0.0,
+                 segs=[s for _ in range(20) for s in (("I", "value", 1.0, 180.0, {}), ("I", "rest", 0.0, 7200.0, {}))]),
+    "cfg5": dict(cathode="LCO", aging=True, grid=dict(N_p=20, N_s=20, N_n=20), soc0=0.0,
+                 segs=[("I", "value", 1.0, 1e6, {"V_max": 4.2}), ("I", "value", -1.0, 1e6, {"V_max": 4.2})]),
+    "cfg5n10": dict(cathode="LCO", aging=True, soc0=0.0,
+                    segs=[("I", "value", 1.0, 1e6, {"V_max": 4.2}), ("I", "value", -1.0, 1e6, {"V_max": 4.2})]),
+}
+
+
+def oracle_protocol(W, tho, opts, dense_t=None, nthreads=8, n_segs=None):
+    """the CPU oracle over a protocol; returns the list of per-segment results (dense rows per segment)"""
+    m = O.make_model(W["cathode"], temperature=W.get("temperature", False), aging=W.get("aging", False), **W.get("grid", {}))
+    out, state = [], None
+    for k, (method, kind, value, tf, bo) in enumerate(W["segs"][:n_segs]):
+        b = O.default_bounds(W["cathode"], **bo)
+        run = O.make_run(method, value, tf=tf, input_kind=kind, new_run=(k == 0))
+        r = O.simulate_batch(m, tho, run, opts, b, SOC0=W["soc0"], state=state, nthreads=nthreads, dense_t=dense_t)
+        state = r["state"]
+        out.append(r)
+    return out
+
+
+def gpu_protocol(P, p, W, dense_t=None, n_segs=None, **opts):
+    """the product API over the same protocol: simulate() then simulate!(); returns (sol, [dense per segment])"""
+    sol, dense = None, []
+    for k, (method, kind, value, tf, bo) in enumerate(W["segs"][:n_segs]):
+        inp = {method: value if kind == "value" else kind}
+        if k == 0:
+            sol = P.simulate(p, tf, SOC=W["soc0"], dense_t=dense_t, **inp, **bo, **opts)
+        else:
+            P.simulate_(sol, p, tf, dense_t=dense_t, **inp, **bo, **opts)
+        dense.append(sol.dense)
+    return sol, dense
+
+
+def merge_dense(dense_list, keys=("V", "I", "SOC", "T")):
+    """rows of a multi-segment protocol: every requested time is filled by the segment that covers it"""
+    out = {k: np.full_like(dense_list[0][k], np.nan) for k in keys}
+    for d in dense_list:
+        for k in keys:
+            fill = ~np.isnan(d[k])
+            out[k][fill] = d[k][fill]
+    return out
