@@ -206,6 +206,32 @@ int plb_set_tstops(plb_handle h, int n, const double *tstops);
 int plb_set_dense_output(plb_handle h, int n, const double *t_global, double *V, double *I, double *SOC,
                          double *T, double *Y, int *n_done, int mem);
 
+/* ---- multi-GPU fan-out inside the library ("multi-GPU fan-out is internal"; 8(e)) -----------------
+ * One model on several GPUs of the box.  Simulations are independent, so the path shards with NO data-path collective:
+ * device k owns the contiguous block [k*R, min(B, (k+1)*R)) of systems, R = ceil(B / n_dev); every shard runs
+ * concurrently on its own device, driven by its own host thread, and writes straight into the caller's HOST arrays.
+ * The one collective of the path follows: an ncclAllGather of the fixed-size (80-byte) summaries, after which EVERY
+ * device holds the summaries of the whole batch (plb_group_device_summaries) -- what a device-side consumer of a
+ * sweep (a reduction, a parameter update) needs.  NCCL is loaded at run time (libnccl.so.2); without it the group still
+ * simulates and only the device-side gather is unavailable.  tstops / dense-output / table requests are per-device
+ * features (plb_group_handle) and are not fanned out. */
+typedef struct plb_group_s *plb_group;
+int plb_group_create(const plb_model_desc *desc, int n_dev, const int *devices, plb_group *out);  /* desc->device is ignored */
+int plb_group_destroy(plb_group g);
+int plb_group_size(plb_group g);
+plb_handle plb_group_handle(plb_group g, int k);   /* device k's handle: sizes, keys, patterns, defaults */
+/* plb_simulate over the group; every array is a HOST array of the whole batch (traj_Y is not fanned out) */
+int plb_group_simulate(plb_group g, int B, const double *theta, const plb_run *run, const double *values,
+                       const plb_opts *opts, const plb_bounds *bounds, const double *soc0, double *state_Y,
+                       double *state_YP, double *state_SOC, double *state_t, plb_summary *summary,
+                       int n_save_max, double *traj_t, double *traj_V, double *traj_I, double *traj_SOC,
+                       double *traj_T, int *traj_n);
+/* after plb_group_simulate: device pointer, on device k, to the all-gathered summaries [n_dev x R] (row b of the batch
+ * is entry (b / R) * R + b % R = b; the tail rows of the last block are zero); returns -1 if NCCL is unavailable */
+int plb_group_device_summaries(plb_group g, int k, const plb_summary **out, int *rows);
+/* milliseconds of the last all-gather (CUDA events on device 0's stream), 0 if none */
+float plb_group_last_gather_ms(plb_group g);
+
 /* diagnostic: launch geometry of a compiled model family (0 isothermal, 1 thermal, 2 SEI, 3 wide, 4 wide SEI): out[8] = {integrator warps
  * per CTA, CTAs per SM, dynamic shared memory per CTA [B], K1 warps per CTA, K1 CTAs per SM, K1 shared
  * memory per CTA [B], workspace vector stride, Jacobian slots per lane}.  Needs no GPU. */

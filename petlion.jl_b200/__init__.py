@@ -6,7 +6,7 @@ constitutive laws) and the host-side mirror of the reference interface (api.py).
 """
 from . import _lib, sweep
 from ._lib import build
-from .api import EXIT_REASONS, Model, Solution, Table, petlion, simulate, simulate_
+from .api import EXIT_REASONS, Model, Solution, Table, model_key, petlion, simulate, simulate_
 
 LCO = "LCO"
 NMC = "NMC"

@@ -16,6 +16,26 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+def _build_key(srcs, flags, nvcc):
+    """Compiled-variant cache key, the role of the reference's saved-model directory hash (src/external.jl:417-456:
+    sha1 of the option string + discretisation, invalidated when the generator changes).  There the cache holds the
+    Julia functions generated per model; here every model family is compiled ahead of time into ONE library, so the
+    cached object is the library and the key is the sha1 of everything that determines it: the sources, the flags and
+    the compiler version.  (mtimes do not survive a git checkout or a copy to the GPU box; the key does.)"""
+    import hashlib
+    h = hashlib.sha1()
+    h.update(" ".join(flags).encode())
+    try:
+        h.update(subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.split("release")[-1].encode())
+    except Exception:
+        h.update(b"nvcc?")
+    for f in sorted(srcs):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
     units = ("plb_kernels.cu", "plb_variant_iso.cu", "plb_variant_th.cu", "plb_variant_sei.cu",
@@ -26,10 +46,14 @@ def build(force=False, verbose=False):
     gen = os.path.join(CSRC, "laws_generated.cuh")
     if not os.path.exists(gen):
         subprocess.check_call([sys.executable, os.path.join(_HERE, "codegen", "gen_laws.py")])
-    if (not force and os.path.exists(LIB_PATH)
-            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
-        return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    key_path = LIB_PATH + ".key"
+    key = _build_key(srcs, NVCC_FLAGS, nvcc) if os.path.exists(nvcc) else None
+    if not force and os.path.exists(LIB_PATH):
+        have = open(key_path).read().strip() if os.path.exists(key_path) else None
+        # no compiler on this machine (a deployment box): the shipped library is what there is
+        if key is None or have == key:
+            return LIB_PATH
     # one translation unit per model family (isothermal / thermal) + the host ABI, compiled in parallel
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
     objs, procs = [], []
@@ -40,7 +64,9 @@ def build(force=False, verbose=False):
     for p_ in procs:
         if p_.wait() != 0:
             raise subprocess.CalledProcessError(p_.returncode, p_.args)
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-ldl", "-lpthread"])
+    with open(key_path, "w") as fh:
+        fh.write(key + "\n")
     return LIB_PATH
 
 
@@ -85,7 +111,8 @@ SUMMARY_DTYPE = [("t_end", "f8"), ("V_end", "f8"), ("I_end", "f8"), ("SOC_end", 
 EXPORTS = ["plb_last_error", "plb_create", "plb_destroy", "plb_set_stream", "plb_nstates", "plb_ndiff",
            "plb_ntheta", "plb_jac_nnz", "plb_theta_keys", "plb_theta_index", "plb_theta_defaults",
            "plb_bounds_defaults", "plb_opts_defaults", "plb_calc_I1C", "plb_jac_pattern",
-           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_set_tstops", "plb_set_dense_output", "plb_variant_info", "plb_launch_count",
+           "plb_initial_guess", "plb_resjac", "plb_newton_init", "plb_linear_solve", "plb_simulate", "plb_simulate_table", "plb_set_tstops", "plb_set_dense_output", "plb_group_create", "plb_group_destroy", "plb_group_size",
+           "plb_group_handle", "plb_group_simulate", "plb_group_device_summaries", "plb_group_last_gather_ms", "plb_variant_info", "plb_launch_count",
            "plb_last_kernel_ms"]
 
 _lib = None
@@ -126,6 +153,16 @@ def lib():
                                          C.c_int]
         L.plb_set_tstops.argtypes = [vp, C.c_int, dp]
         L.plb_set_dense_output.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, vp, C.c_int]
+        L.plb_group_create.argtypes = [C.POINTER(ModelDesc), C.c_int, ip, C.POINTER(vp)]
+        L.plb_group_destroy.argtypes = [vp]
+        L.plb_group_size.argtypes = [vp]
+        L.plb_group_handle.argtypes = [vp, C.c_int]
+        L.plb_group_handle.restype = vp
+        L.plb_group_simulate.argtypes = [vp, C.c_int, dp, C.POINTER(Run), dp, C.POINTER(Opts), C.POINTER(Bounds),
+                                         dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, vp]
+        L.plb_group_device_summaries.argtypes = [vp, C.c_int, C.POINTER(vp), ip]
+        L.plb_group_last_gather_ms.argtypes = [vp]
+        L.plb_group_last_gather_ms.restype = C.c_float
         L.plb_launch_count.argtypes = [vp]
         L.plb_launch_count.restype = C.c_longlong
         L.plb_last_kernel_ms.argtypes = [vp]

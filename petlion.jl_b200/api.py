@@ -48,15 +48,26 @@ class _NS:
 class Model:
     """`p = petlion(LCO)`: parameters p.θ, p.opts, p.bounds, p.N, p.numerics (src/external.jl:2-70)."""
 
-    def __init__(self, cathode, N, numerics, device):
+    def __init__(self, cathode, N, numerics, device, devices=None):
         L = _lib.lib()
         self.cathode = cathode
         self.N = N
         self.numerics = numerics
         desc = _lib.ModelDesc(CATHODES[cathode], N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n,
                               int(bool(numerics.temperature)), int(bool(numerics.aging)), int(device))
-        h = C.c_void_p()
-        _lib.check(L.plb_create(C.byref(desc), C.byref(h)))
+        self._g = None
+        self.devices = [int(device)] if devices is None else [int(d) for d in devices]
+        if devices is not None and len(self.devices) > 1:
+            # several GPUs behind one model: the library shards every batch contiguously over them
+            g = C.c_void_p()
+            devs = (C.c_int * len(self.devices))(*self.devices)
+            _lib.check(L.plb_group_create(C.byref(desc), len(self.devices), devs, C.byref(g)))
+            self._g = g
+            h = C.c_void_p(L.plb_group_handle(g, 0))
+        else:
+            desc.device = self.devices[0]
+            h = C.c_void_p()
+            _lib.check(L.plb_create(C.byref(desc), C.byref(h)))
         self._h = h
         self.N.tot = L.plb_nstates(h)
         self.N.diff = L.plb_ndiff(h)
@@ -104,11 +115,23 @@ class Model:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_g", None):
+                _lib.lib().plb_group_destroy(self._g)
+                self._g = self._h = None
+            elif getattr(self, "_h", None):
                 _lib.lib().plb_destroy(self._h)
                 self._h = None
         except Exception:
             pass
+
+    def device_summaries(self, k=0):
+        """(device pointer on self.devices[k], rows per device) of the all-gathered summaries of the last simulate()
+        of a multi-GPU model: every device holds the whole batch's 80-byte records"""
+        if self._g is None:
+            raise ValueError("a single-device model has no gathered summaries")
+        ptr, rows = C.c_void_p(), C.c_int()
+        _lib.check(_lib.lib().plb_group_device_summaries(self._g, k, C.byref(ptr), C.byref(rows)))
+        return ptr.value, rows.value
 
     # ---- parameter batch -----------------------------------------------------------------------
     def batch_size(self, *extra):
@@ -206,6 +229,19 @@ class Model:
         return x, st
 
 
+def model_key(p):
+    """`<Cathode>_<Anode>/<sha1>` of a model's structural options -- the name of the reference's saved-model directory
+    (strings_directory_func, src/external.jl:417-456), built from the same fields in the same order.  Models with the
+    same key share the same compiled family and Jacobian pattern."""
+    import hashlib
+    nm, N = p.numerics, p.N
+    anode = "LiC6" if p.cathode == "LCO" else "LiC6_NMC"
+    fields = [str(nm.temperature).lower(), nm.solid_diffusion, nm.Fickian_method, "SEI" if nm.aging else "false", nm.jacobian,
+              f"Np{N.p}", f"Ns{N.s}", f"Nn{N.n}", f"Na{N.a}_Nz{N.z}" if nm.temperature else "",
+              f"Nr_p{N.r_p}_Nr_n{N.r_n}" if nm.solid_diffusion == "Fickian" else ""]
+    return f"{p.cathode}_{anode}/" + hashlib.sha1("_".join(fields).encode()).hexdigest()
+
+
 class Solution:
     """`sol`: per-system trajectories t, V, I, SOC [B, n] (+ n_points), final state Y, results list."""
 
@@ -276,7 +312,7 @@ class Solution:
 
 def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10, temperature=False,
             solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic",
-            device=0):
+            device=0, devices=None):
     """petlion(cathode; kwargs...) -- src/external.jl:2-18, src/params.jl:119-174."""
     if cathode not in CATHODES:
         raise ValueError(f"unknown cathode {cathode!r}; built: {list(CATHODES)}")
@@ -289,7 +325,7 @@ def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, 
     N = _NS(p=N_p, s=N_s, n=N_n, a=N_a, z=N_z, r_p=N_r_p, r_n=N_r_n)
     numerics = _NS(temperature=temperature, solid_diffusion=solid_diffusion, Fickian_method=Fickian_method,
                    aging=aging, jacobian=jacobian, cathode=cathode)
-    return Model(cathode, N, numerics, device)
+    return Model(cathode, N, numerics, device, devices)
 
 
 def _make_opts(p, kw):
@@ -455,7 +491,12 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
         _lib.check(L.plb_set_dense_output(p._h, nd, t_dense.ctypes.data, dense["V"].ctypes.data, dense["I"].ctypes.data,
                                           dense["SOC"].ctypes.data, dense["T"].ctypes.data,
                                           dense["Y"].ctypes.data if keep_states else None, dense["n"].ctypes.data, 0))
-    if table is not None:
+    if p._g is not None:
+        if table is not None or dense is not None or keep_states or ts.size:
+            raise NotImplementedError("a multi-GPU model fans out plain simulate()/simulate!() calls; tabulated inputs, "
+                                      "requested times, state rows and tstops are per-device features")
+        _lib.check(L.plb_group_simulate(p._g, B, th.ctypes.data, C.byref(run), vptr, *tail[:-3], tail[-2]))
+    elif table is not None:
         dpp = C.POINTER(C.c_double)
         td = np.ascontiguousarray(sorted(tdiscon if tdiscon is not None else p.opts.tdiscon), dtype=np.float64)
         it = _lib.InputTable(table.t.size, table.t.ctypes.data_as(dpp), table.v.ctypes.data_as(dpp), td.size,

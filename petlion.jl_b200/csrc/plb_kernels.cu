@@ -5,6 +5,8 @@
 // Jacobian and the staging of host buffers.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -12,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -693,5 +696,181 @@ int plb_set_tstops(plb_handle h, int n, const double* tstops) {
     if (n < 0 || (n > 0 && !tstops)) return fail("plb_set_tstops: bad arguments");
     for (int k = 0; k < n; k++) if (!std::isfinite(tstops[k])) return fail("plb_set_tstops: non-finite stop time");
     h->opt_tstops.assign(tstops, tstops + n);
+    return 0;
+}
+
+
+// =================================================================================================
+// multi-GPU fan-out: one handle per device, contiguous batch shards, one NCCL all-gather of the summaries
+// =================================================================================================
+namespace {
+// the few NCCL entry points this path needs, bound at run time (the product has no link-time dependency on NCCL)
+struct Nccl {
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+Nccl g_nccl;
+}  // namespace
+
+struct plb_group_s {
+    std::vector<plb_handle_s*> h;
+    std::vector<int> dev;
+    std::vector<void*> comm;                 // ncclComm_t per device (empty: NCCL unavailable)
+    std::vector<cudaStream_t> stream;
+    std::vector<plb_summary*> d_send, d_all; // per device: its block [R], the gathered batch [n_dev x R]
+    size_t cap_rows = 0;
+    int rows = 0;                            // R of the last simulate
+    bool gathered = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float gather_ms = 0.f;
+};
+
+int plb_group_create(const plb_model_desc* desc, int n_dev, const int* devices, plb_group* out) {
+    if (!desc || !devices || !out || n_dev < 1) return fail("plb_group_create: bad arguments");
+    plb_group_s* g = new plb_group_s();
+    for (int k = 0; k < n_dev; k++) {
+        plb_model_desc d = *desc;
+        d.device = devices[k];
+        plb_handle hk = nullptr;
+        if (plb_create(&d, &hk)) { const std::string e = g_err; plb_group_destroy(g); return fail(e); }
+        g->h.push_back(hk);
+        g->dev.push_back(devices[k]);
+    }
+    g->stream.assign(n_dev, nullptr);
+    g->d_send.assign(n_dev, nullptr);
+    g->d_all.assign(n_dev, nullptr);
+    for (int k = 0; k < n_dev; k++) {
+        DeviceGuard guard(devices[k]);
+        if (cudaStreamCreateWithFlags(&g->stream[k], cudaStreamNonBlocking) != cudaSuccess) { plb_group_destroy(g); return fail("plb_group_create: cudaStreamCreate failed"); }
+        g->h[k]->stream = g->stream[k];
+    }
+    if (n_dev > 1 && g_nccl.load()) {
+        g->comm.assign(n_dev, nullptr);
+        const int rc = g_nccl.CommInitAll(g->comm.data(), n_dev, devices);
+        if (rc != 0) { const std::string e = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(rc); g->comm.clear(); plb_group_destroy(g); return fail(e); }
+    }
+    {
+        DeviceGuard guard(devices[0]);
+        cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
+    }
+    *out = g;
+    return 0;
+}
+
+int plb_group_destroy(plb_group g) {
+    if (!g) return 0;
+    for (size_t k = 0; k < g->comm.size(); k++) if (g->comm[k]) g_nccl.CommDestroy(g->comm[k]);
+    for (size_t k = 0; k < g->h.size(); k++) {
+        DeviceGuard guard(g->dev[k]);
+        if (k < g->d_send.size()) { cudaFree(g->d_send[k]); cudaFree(g->d_all[k]); }
+        if (k < g->stream.size() && g->stream[k]) { g->h[k]->stream = nullptr; cudaStreamDestroy(g->stream[k]); }
+        if (k == 0) { if (g->ev0) cudaEventDestroy(g->ev0); if (g->ev1) cudaEventDestroy(g->ev1); }
+        plb_destroy(g->h[k]);
+    }
+    delete g;
+    return 0;
+}
+int plb_group_size(plb_group g) { return g ? (int)g->h.size() : fail("plb_group_size: null group"); }
+plb_handle plb_group_handle(plb_group g, int k) { return (g && k >= 0 && k < (int)g->h.size()) ? g->h[k] : nullptr; }
+float plb_group_last_gather_ms(plb_group g) { return g ? g->gather_ms : 0.f; }
+
+int plb_group_simulate(plb_group g, int B, const double* theta, const plb_run* run, const double* values, const plb_opts* opts,
+                       const plb_bounds* bounds, const double* soc0, double* sY, double* sYP, double* sSOC, double* st,
+                       plb_summary* summary, int n_save_max, double* tr_t, double* tr_V, double* tr_I, double* tr_SOC,
+                       double* tr_T, int* tr_n) {
+    if (!g) return fail("plb_group_simulate: null group");
+    if (B <= 0) return 0;
+    if (!run || !opts || !bounds || !theta || !sY || !sSOC || !st || !summary) return fail("plb_group_simulate: null required argument");
+    const int G = (int)g->h.size();
+    const int R = (B + G - 1) / G;
+    const int N = g->h[0]->m.N_tot, nth = g->h[0]->m.ntheta;
+    const size_t ns = n_save_max > 0 ? n_save_max : 0;
+    g->gathered = false;
+    g->rows = R;
+    // every shard from its own host thread: the per-device calls are synchronous, the devices run side by side
+    std::vector<int> rc(G, 0);
+    std::vector<std::string> err(G);
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; k++) {
+        const int lo = k * R, n = std::max(0, std::min(B, lo + R) - lo);
+        th.emplace_back([=, &rc, &err]() {
+            if (n == 0) return;
+            auto off = [&](auto* p, size_t stride) { return p ? p + (size_t)lo * stride : p; };
+            rc[k] = plb_simulate(g->h[k], n, theta + (size_t)lo * nth, run, off(values, 1), opts, bounds, off(soc0, 1), sY + (size_t)lo * N,
+                                 off(sYP, N), sSOC + lo, st + lo, summary + lo, n_save_max, off(tr_t, ns), off(tr_V, ns), off(tr_I, ns),
+                                 off(tr_SOC, ns), off(tr_T, ns), nullptr, off(tr_n, 1), PLB_MEM_HOST);
+            if (rc[k]) err[k] = g_err;      // (thread-local in the worker: hand it to the caller)
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < G; k++) if (rc[k]) return fail("device " + std::to_string(g->dev[k]) + ": " + err[k]);
+    if (g->comm.empty()) return 0;
+    // ---- the one collective: all-gather of the summaries, so that every device holds the whole batch's ----
+    if (g->cap_rows < (size_t)R) {
+        for (int k = 0; k < G; k++) {
+            DeviceGuard guard(g->dev[k]);
+            cudaFree(g->d_send[k]); cudaFree(g->d_all[k]);
+            g->d_send[k] = g->d_all[k] = nullptr;
+            CUDA_OK(cudaMalloc(&g->d_send[k], (size_t)R * sizeof(plb_summary)));
+            CUDA_OK(cudaMalloc(&g->d_all[k], (size_t)R * G * sizeof(plb_summary)));
+        }
+        g->cap_rows = R;
+    }
+    for (int k = 0; k < G; k++) {
+        DeviceGuard guard(g->dev[k]);
+        const int lo = k * R, n = std::max(0, std::min(B, lo + R) - lo);
+        CUDA_OK(cudaMemsetAsync(g->d_send[k], 0, (size_t)R * sizeof(plb_summary), g->stream[k]));
+        // the device copy of the shard's summaries is still in the handle's staging pool (slot 7 of simulate_impl)
+        if (n) CUDA_OK(cudaMemcpyAsync(g->d_send[k], g->h[k]->pool_ptr[7], (size_t)n * sizeof(plb_summary), cudaMemcpyDeviceToDevice, g->stream[k]));
+    }
+    {
+        DeviceGuard guard(g->dev[0]);
+        CUDA_OK(cudaEventRecord(g->ev0, g->stream[0]));
+    }
+    int nrc = g_nccl.GroupStart();
+    for (int k = 0; k < G && nrc == 0; k++)
+        nrc = g_nccl.AllGather(g->d_send[k], g->d_all[k], (size_t)R * sizeof(plb_summary), /*ncclUint8*/ 1, g->comm[k], g->stream[k]);
+    const int erc = g_nccl.GroupEnd();
+    if (nrc == 0) nrc = erc;
+    if (nrc != 0) return fail(std::string("ncclAllGather: ") + g_nccl.GetErrorString(nrc));
+    {
+        DeviceGuard guard(g->dev[0]);
+        CUDA_OK(cudaEventRecord(g->ev1, g->stream[0]));
+    }
+    for (int k = 0; k < G; k++) {
+        DeviceGuard guard(g->dev[k]);
+        CUDA_OK(cudaStreamSynchronize(g->stream[k]));
+    }
+    cudaEventElapsedTime(&g->gather_ms, g->ev0, g->ev1);
+    g->gathered = true;
+    return 0;
+}
+
+int plb_group_device_summaries(plb_group g, int k, const plb_summary** out, int* rows) {
+    if (!g || !out || k < 0 || k >= (int)g->h.size()) return fail("plb_group_device_summaries: bad arguments");
+    if (!g->gathered) return fail(g->comm.empty() ? "plb_group_device_summaries: NCCL is not available (libnccl.so.2 not found, or one device)"
+                                                  : "plb_group_device_summaries: no gathered batch yet");
+    *out = g->d_all[k];
+    if (rows) *rows = g->rows;
     return 0;
 }

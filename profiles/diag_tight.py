@@ -8,7 +8,7 @@ from tests import util
 from tests.test_gpu_tight import _run_both
 name, B, tol, t1, dt = sys.argv[1], int(sys.argv[2]), float(sys.argv[3]), float(sys.argv[4]), float(sys.argv[5])
 td = np.arange(0.0, t1, dt)
-sol, dense, ref = _run_both(P, name, B, tol, td, first=80000)
+sol, dense, ref = _run_both(P, name, B, tol, td, first=int(os.environ.get("DIAG_FIRST", 80000)), maxiters=400000)
 for k, r in enumerate(ref):
     s = sol.results[k].summary
     g, o = dense[k], r["dense"]
@@ -24,7 +24,14 @@ for k, r in enumerate(ref):
     for q in (int(np.argmax(mism)),):
         print("   mismatch rows sys", q, "gpu filled", td[~np.isnan(g["V"][q])][[0, -1]] if (~np.isnan(g["V"][q])).any() else None,
               "cpu filled", td[~np.isnan(o["V"][q])][[0, -1]] if (~np.isnan(o["V"][q])).any() else None, "t_end", s["t_end"][q], r["t_end"][q], "flags", s["flag"][q], r["flag"][q])
-    if k > 0:
+    errI = np.where(both, np.abs(g["I"] - o["I"]) / np.maximum(np.abs(o["I"]), 1e-3), 0.0)
+    order = np.argsort(-errI.max(axis=1))[:5]
+    for q in order:
+        jj = int(np.argmax(errI[q]))
+        print(f"   worst I: sys {q} t {td[jj]} gpu {g['I'][q, jj]:.8f} cpu {o['I'][q, jj]:.8f} rel {errI[q, jj]:.2e} steps {s['n_steps'][q]} {r['n_steps'][q]} t_end {s['t_end'][q]:.4f} {r['t_end'][q]:.4f} flags {s['flag'][q]} {r['flag'][q]} t_start {sol.results[k-1].summary['t_end'][q] if k else 0:.4f}")
+    for q in np.where(s["flag"] != r["flag"])[0][:4]:
+        print(f"   FLAGDIFF seg {k} sys {q}: flags {s['flag'][q]} {r['flag'][q]} t_end {s['t_end'][q]:.6f} {r['t_end'][q]:.6f} V_end {s['V_end'][q]:.9f} {r['V_end'][q]:.9f} steps {s['n_steps'][q]} {r['n_steps'][q]}")
+    if k > 0 and err.max() > 1e-5:
         # hold / later segments: first rows of the worst system
         fill = np.where(both[i])[0][:6]
         print("   first rows", td[fill], "\n   gpu", g["V"][i, fill], "\n   cpu", o["V"][i, fill], "\n   I gpu", g["I"][i, fill], "\n   I cpu", o["I"][i, fill])

@@ -172,3 +172,70 @@ def test_gloo_world2_sharded_run_equals_single(tmp_path):
     np.testing.assert_array_equal(full[:, 0], r["t_end"])
     np.testing.assert_array_equal(full[:, 1], r["V_end"])
     np.testing.assert_array_equal(full[:, 5], r["n_steps"])
+
+
+def test_julia_shim_covers_the_header():
+    """julia/PETLIONB200.jl (the ccall layer of INTEGRATION.md; Julia itself is not in the image) binds every entry
+    point include/petlion_b200.h declares, mirrors the struct fields in order, and is bracket-balanced"""
+    hdr = open(os.path.join(ROOT, "include", "petlion_b200.h")).read()
+    jl = open(os.path.join(ROOT, "julia", "PETLIONB200.jl")).read()
+    declared = set(re.findall(r"\b(plb_[a-z_0-9A-Z]+)\s*\(", hdr))
+    bound = set(re.findall(r"\(:(plb_[a-z_0-9A-Z]+), lib\)", jl))
+    assert declared == bound, declared ^ bound
+    code = re.sub(r'""".*?"""', "", jl, flags=re.S)
+    code = "\n".join(ln.split("#")[0] for ln in code.split("\n"))
+    code = re.sub(r'"[^"\n]*"', '""', code)
+    for a, b in ("()", "[]", "{}"):
+        assert code.count(a) == code.count(b), (a, code.count(a), code.count(b))
+    assert len(re.findall(r"^\s*(module|struct|function|begin|if)\b", code, flags=re.M)) + len(re.findall(r"\bbegin\s*$", code, flags=re.M)) >= len(re.findall(r"^\s*end\b", code, flags=re.M)) - 1
+
+    def c_fields(name):
+        end = hdr.index("} " + name + ";")
+        body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                out += [x.strip().lstrip("*") for x in decl.split(None, 1)[1].replace("const double", "").split(",")]
+        return [x.split()[-1].lstrip("*") for x in out]
+
+    def jl_fields(name):
+        body = re.search(r"struct " + name + r"\n(.*?)\nend", jl, flags=re.S).group(1)
+        return [x.split("::")[0].strip() for x in re.split(r"[;\n]", body) if "::" in x]
+    for cname, jname in (("plb_model_desc", "ModelDesc"), ("plb_run", "Run"), ("plb_opts", "Opts"), ("plb_summary", "Summary")):
+        assert c_fields(cname) == jl_fields(jname), (cname, c_fields(cname), jl_fields(jname))
+    assert [f.replace("η", "eta") for f in jl_fields("Bounds")] == c_fields("plb_bounds")
+
+
+def test_compiled_variant_cache_key():
+    """the built library is reused exactly when nothing that determines it changed (sources, flags, compiler)"""
+    import petlion_b200
+    from petlion_b200 import _lib
+    path = petlion_b200.build()
+    key_file = path + ".key"
+    assert os.path.exists(key_file)
+    key = open(key_file).read().strip()
+    t0 = os.path.getmtime(path)
+    assert petlion_b200.build() == path and os.path.getmtime(path) == t0          # cache hit: not rebuilt
+    srcs = [os.path.join(_lib.CSRC, f) for f in os.listdir(_lib.CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(ROOT, "include", "petlion_b200.h"))
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    assert _lib._build_key(srcs, _lib.NVCC_FLAGS, nvcc) == key
+    assert _lib._build_key(srcs, _lib.NVCC_FLAGS + ["-DX"], nvcc) != key
+    assert _lib._build_key(srcs[1:], _lib.NVCC_FLAGS, nvcc) != key
+
+
+def test_model_key_follows_the_reference_directory_hash():
+    """strings_directory_func (src/external.jl:417-456): <Cathode>_<Anode>/sha1(options, Np, Ns, Nn[, Na_Nz][, Nr])"""
+    import hashlib
+    from petlion_b200.api import _NS, model_key
+    N = _NS(p=10, s=10, n=10, a=10, z=10, r_p=10, r_n=10)
+    nm = _NS(temperature=False, solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic")
+    k = model_key(_NS(cathode="LCO", numerics=nm, N=N))
+    assert k == "LCO_LiC6/" + hashlib.sha1(b"false_Fickian_finite_difference_false_symbolic_Np10_Ns10_Nn10__Nr_p10_Nr_n10").hexdigest()
+    nm2 = nm.copy(); nm2.temperature = True
+    assert model_key(_NS(cathode="LCO", numerics=nm2, N=N)) != k
+    N2 = N.copy(); N2.a = 5
+    assert model_key(_NS(cathode="LCO", numerics=nm, N=N2)) == k          # N_a only matters to thermal models
+    assert model_key(_NS(cathode="NMC", numerics=nm, N=N)).startswith("NMC_LiC6_NMC/")
