@@ -152,6 +152,13 @@ def lib():
                                          C.POINTER(Bounds), dp, dp, dp, dp, dp, vp, C.c_int, dp, dp, dp, dp, dp, dp, vp,
                                          C.c_int]
         L.plb_set_tstops.argtypes = [vp, C.c_int, dp]
+        L.plb_launch_count.argtypes = [vp]
+        L.plb_launch_count.restype = C.c_longlong
+        L.plb_last_kernel_ms.argtypes = [vp]
+        L.plb_last_kernel_ms.restype = C.c_float
+        if not hasattr(L, "plb_set_dense_output"):      # an older build named by PLB_LIB (A/B probes under profiles/)
+            _lib = L
+            return _lib
         L.plb_set_dense_output.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, vp, C.c_int]
         L.plb_group_create.argtypes = [C.POINTER(ModelDesc), C.c_int, ip, C.POINTER(vp)]
         L.plb_group_destroy.argtypes = [vp]

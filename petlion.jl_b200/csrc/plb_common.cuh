@@ -55,6 +55,8 @@ struct ModelDesc {
     //   c_e | c_s (particle-major) | [T: a|p|s|n|z] | [film | SOH] | j | Phi_e | Phi_s | [j_s] | I
     int off_cs, off_T, off_film, off_SOH, off_j, off_pe, off_ps, off_js, off_I, N_diff, N_tot;
     double inv_n[4];             // 1/Np, 1/Ns, 1/Nn (Delta x of a section, numerical_tools.jl:216)
+    double soh_geo[64];          // aging = :SEI: d trapz(extrapolate_section(y, :n)) / d y_k for a section of unit length
+                                 // (residuals.jl:278-297, external.jl:469-522); depends on N_n only
     int8_t slot[TF_COUNT];       // theta field -> position in the row (-1: not a key of this variant)
 };
 
@@ -144,6 +146,7 @@ struct VariantInfo {
     int vs, nglobal;                // workspace vector stride, history vectors parked in global memory
     int n_slots, n_stage, k1_src_max;
     int lanes;                      // lanes per system: 32, or 64 in the wide families
+    int k1_tma;                     // this family has the TMA-staged K1 (k_resjac_tma)
 };
 
 // launchers, one set per variant (defined in plb_variant.cuh)

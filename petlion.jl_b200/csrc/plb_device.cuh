@@ -352,25 +352,14 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         // residuals_SOH! (residuals.jl:278-297): rhs = F a_n/(3600 I1C) * trapz over the anode of j_s after a
         // quadratic extrapolation to both ends (extrapolate_section / extrap_x_0, external.jl:496-522): linear
         // in j_s, so every anode lane keeps its own weight
-        const int N = m.Nn, k = lane - (m.Np + m.Ns) + 1;      // 1-based node inside the section
+        // The geometry of that functional (the trapezoid weights with both extrapolated ends, for a section of unit
+        // length) depends on N_n only: the host forms it once per model (ModelDesc::soh_geo); here it is scaled by l_n
+        // and F a_n / (3600 I1C).
+        const int k = lane - (m.Np + m.Ns);
         double wk = 0.0;
-        if (k >= 1 && k <= N) {
-            auto xs = [&](int i) -> double { return i <= 0 ? 0.0 : (i > N ? 1.0 : (1.0 / (2.0 * N)) + (i - 1) * ((1.0 - 1.0 / N) / (N - 1))); };
-            const double x1 = xs(1), x2 = xs(2), x3 = xs(3);
-            const double r = (x3 - x1) / (x2 - x1);
-            const double den = x3 * x3 - x1 * x1 - (x2 * x2 - x1 * x1) / (x2 - x1) * (x3 - x1);
-            auto ext = [&](int i) -> double {     // weight of the i-th node from the end (1..3) in the end value
-                const double c = (i == 1 ? r - 1.0 : (i == 2 ? -r : 1.0)) / den;
-                const double b = ((i == 2 ? 1.0 : 0.0) - (i == 1 ? 1.0 : 0.0) - c * (x2 * x2 - x1 * x1)) / (x2 - x1);
-                return (i == 1 ? 1.0 : 0.0) - c * x1 * x1 - b * x1;
-            };
-            const double l = th[TF_l_n];
-            wk = 0.5 * (xs(k + 1) * l - xs(k - 1) * l);
-            const double w0 = 0.5 * (xs(1) * l - xs(0) * l), wN = 0.5 * (xs(N + 1) * l - xs(N) * l);
-            if (k <= 3) wk += w0 * ext(k);
-            if (k >= N - 2) wk += wN * ext(N + 1 - k);
+        if (k >= 0 && k < m.Nn) {
             const double eps_sn = 1.0 - (th[TF_eps_fn] + th[TF_eps_n]);
-            wk *= kF * (3 * eps_sn / th[TF_Rp_n]) / (3600 * C.g[GC_I1C]);
+            wk = m.soh_geo[k] * th[TF_l_n] * (kF * (3 * eps_sn * C.sec[SC_inv_Rp][2]) / (3600 * C.g[GC_I1C]));
         }
         C.cSOH[lane] = wk;
     }
@@ -389,20 +378,46 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
     grp_sync();
     {
         // conductance between the centres of two adjacent cells: lambda/h inside a section, harmonic-mean
-        // lambda over the centre distance across an interface (residuals.jl:363-446)
+        // lambda over the centre distance across an interface (residuals.jl:363-446).  Only 9 distinct conductances
+        // (5 inside the sections a,p,s,n,z, 4 across their interfaces) and 5 scales 1/(h rho Cp) exist: lanes 0..13
+        // form one each (a lane-local lambda with two divisions per call cost ~700 instructions per system)
+        double* const G = C.xq;       // scratch [0..8] conductances, [9..13] scales; xq itself is written below
+        if (lane < 14) {
+            double v;
+            if (lane < 5) v = C.s5[1][lane] / C.s5[0][lane];
+            else if (lane < 9) {
+                const int qa = lane - 5, qb = qa + 1;
+                const double ha = C.s5[0][qa], hb = C.s5[0][qb], la = C.s5[1][qa], lb = C.s5[1][qb];
+                const double be = (ha / 2) / (ha / 2 + hb / 2);
+                const double lm = la * lb / (be * lb + (1.0 - be) * la);
+                v = lm / (ha / 2 + hb / 2);
+            } else v = 1.0 / (C.s5[0][lane - 9] * C.s5[2][lane - 9]);
+            G[lane] = v;
+        }
+        grp_sync();
+        double Gv[14];
+#pragma unroll
+        for (int k = 0; k < 14; k++) Gv[k] = G[k];
+        grp_sync();                   // (every lane holds the table before xq is overwritten)
         auto cond = [&](int qa, int qb) -> double {
-            const double ha = C.s5[0][qa], hb = C.s5[0][qb], la = C.s5[1][qa], lb = C.s5[1][qb];
-            if (qa == qb) return la / ha;
-            const double be = (ha / 2) / (ha / 2 + hb / 2);
-            const double lm = la * lb / (be * lb + (1.0 - be) * la);
-            return lm / (ha / 2 + hb / 2);
+            // qa == qb: inside section qa; else the interface qa | qa+1
+            double r = Gv[0];
+#pragma unroll
+            for (int k = 1; k < 9; k++) r = ((qa == qb ? qa : 5 + qa) == k) ? Gv[k] : r;
+            return r;
+        };
+        auto scale = [&](int q) -> double {
+            double r = Gv[9];
+#pragma unroll
+            for (int k = 1; k < 5; k++) r = (q == k) ? Gv[9 + k] : r;
+            return r;
         };
         const int x = lane;
         auto sec5 = [&](int xx) -> int { return xx < 0 ? 0 : (xx < m.Np ? 1 : (xx < m.Np + m.Ns ? 2 : (xx < m.Nx ? 3 : 4))); };
         double tL = 0.0, tR = 0.0;
         if (x < m.Nx) {
             const int q = sec5(x);
-            const double sc = 1.0 / (C.s5[0][q] * C.s5[2][q]);
+            const double sc = scale(q);
             tL = cond(sec5(x - 1), q) * sc;
             tR = cond(q, sec5(x + 1)) * sc;
         }
@@ -411,14 +426,14 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
         const double I1C = C.g[GC_I1C];
         if (lane < m.Na) {
             const int k = lane;
-            const double sc = 1.0 / (C.s5[0][0] * C.s5[2][0]);
+            const double sc = scale(0);
             xL = k > 0 ? cond(0, 0) * sc : 0.0;
             xR = (k < m.Na - 1 ? cond(0, 0) : cond(0, 1)) * sc;
             xbc = k == 0 ? th[TF_h_cell] * sc : 0.0;                       // T_BC_sx, residuals.jl:318
             xq = I1C * I1C / (th[TF_sigma_a] * C.s5[2][0]);                // residuals.jl:461
         } else if (lane >= m.Nx - m.Nz && lane < m.Nx) {
             const int k = lane - (m.Nx - m.Nz);
-            const double sc = 1.0 / (C.s5[0][4] * C.s5[2][4]);
+            const double sc = scale(4);
             xL = (k > 0 ? cond(4, 4) : cond(3, 4)) * sc;
             xR = k < m.Nz - 1 ? cond(4, 4) * sc : 0.0;
             xbc = k == m.Nz - 1 ? th[TF_h_cell] * sc : 0.0;               // T_BC_dx, residuals.jl:319

@@ -246,6 +246,28 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     m.chem = d->cathode == PLB_CATHODE_LCO ? CHEM_LCO : CHEM_NMC;
     m.mid = m.thermal ? m.Np + m.Ns / 2 : m.Nx / 2;
     m.inv_n[0] = 1.0 / m.Np; m.inv_n[1] = 1.0 / m.Ns; m.inv_n[2] = 1.0 / m.Nn; m.inv_n[3] = 0.0;
+    if (m.aging) {
+        // residuals_SOH! (residuals.jl:278-297): rhs = F a_n/(3600 I1C) * trapz over the anode of j_s after a quadratic
+        // extrapolation to both ends (extrapolate_section / extrap_x_0, external.jl:496-522): linear in j_s, so node k
+        // has a fixed weight.  For a section of unit length:
+        const int N = m.Nn;
+        auto xs = [&](int i) -> double { return i <= 0 ? 0.0 : (i > N ? 1.0 : (1.0 / (2.0 * N)) + (i - 1) * ((1.0 - 1.0 / N) / (N - 1))); };
+        const double x1 = xs(1), x2 = xs(2), x3 = xs(3);
+        const double r = (x3 - x1) / (x2 - x1);
+        const double den = x3 * x3 - x1 * x1 - (x2 * x2 - x1 * x1) / (x2 - x1) * (x3 - x1);
+        auto ext = [&](int i) -> double {     // weight of the i-th node from the end (1..3) in the end value
+            const double c = (i == 1 ? r - 1.0 : (i == 2 ? -r : 1.0)) / den;
+            const double b = ((i == 2 ? 1.0 : 0.0) - (i == 1 ? 1.0 : 0.0) - c * (x2 * x2 - x1 * x1)) / (x2 - x1);
+            return (i == 1 ? 1.0 : 0.0) - c * x1 * x1 - b * x1;
+        };
+        const double w0 = 0.5 * (xs(1) - xs(0)), wN = 0.5 * (xs(N + 1) - xs(N));
+        for (int k = 1; k <= N && k <= 64; k++) {
+            double wk = 0.5 * (xs(k + 1) - xs(k - 1));
+            if (k <= 3) wk += w0 * ext(k);
+            if (k >= N - 2) wk += wN * ext(N + 1 - k);
+            m.soh_geo[k - 1] = wk;
+        }
+    }
     m.off_cs = m.Nx; m.off_T = m.off_cs + NR_HOST * m.Ne;
     m.off_film = m.off_T + (m.thermal ? m.Na + m.Nx + m.Nz : 0);
     m.off_SOH = m.off_film + (m.aging ? m.Nn : 0);
@@ -468,7 +490,7 @@ int plb_resjac(plb_handle h, int B, const double* Y, const double* YP, const dou
     a.method = run->method; a.value = run->value; a.res = res; a.nzval = nzval; a.nnz = nnz;
     a.src = h->d_src[run->method];
     // the bulk-copy (TMA) kernel needs 16-byte aligned input arrays; anything else takes the per-lane loads
-    a.use_tma = !h->k1_no_tma && (((uintptr_t)Y | (uintptr_t)YP | (uintptr_t)theta) & 15) == 0;
+    a.use_tma = h->vi.k1_tma && !h->k1_no_tma && (((uintptr_t)Y | (uintptr_t)YP | (uintptr_t)theta) & 15) == 0;
     // one resident wave: every CTA loads the recipe tables once and then streams its share of the batch
     const int grid = std::min((B + h->vi.k1_warps - 1) / h->vi.k1_warps, h->num_sms * h->vi.k1_ctas * (a.use_tma ? 1 : 2));
     CUDA_OK(cudaEventRecord(h->ev0, s));

@@ -54,7 +54,13 @@ enum JacSlot {
 #ifndef PLB_K1_CTAS
 #define PLB_K1_CTAS (PLB_WIDE ? 1 : (PLB_TH ? 2 : 3))
 #endif
-constexpr int K1_WARPS = WIDE ? 2 : 4;            // systems (lane groups) per CTA
+#ifndef PLB_K1_WARPS
+#define PLB_K1_WARPS (PLB_WIDE ? 2 : 4)
+#endif
+#ifndef PLB_SEI_TMA
+#define PLB_SEI_TMA 0          // A/B knob: the TMA-staged K1 in the SEI family (needs PLB_K1_WARPS=3 to keep three CTAs per SM)
+#endif
+constexpr int K1_WARPS = PLB_K1_WARPS;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
 constexpr int K1_SRC_MAX = WIDE ? 4864 : (TH ? 3072 : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
             }
             w.S[JS_TX_L][lane] = J.Tx_L; w.S[JS_TX_D][lane] = J.Tx_D - g; w.S[JS_TX_U][lane] = J.Tx_U; w.S[JS_TX_I][lane] = J.Tx_I;
             w.S[JS_KAP][lane] = J.kap;
+            if (lane == 0) w.S[JS_KAP][LW] = 1.0;
 #endif
             w.S[k1_stage_slot(JS_CTRL_PS0)][lane] = ctrl.g_ps0;
             w.S[k1_stage_slot(JS_CTRL_PSN)][lane] = ctrl.g_psN;
@@ -222,11 +229,13 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
 #if PLB_TH
 #pragma unroll 4
             for (int p = lane; p < a.nnz; p += LW) {
+                // every entry is kap * t - gd: lane-computed entries point kap at the 1.0 kept in the padding
+                // element of the KAP row (fma(1, t, -0) == t), particle entries at their node's D_s(T)/Rp^2
                 const int rc = src_s[p];
                 const double t = tab[rc & 0xffff];
-                const double kap = tab[JS_KAP * K1_PITCH + ((rc >> 19) & 31)];
+                const double kap = tab[JS_KAP * K1_PITCH + ((rc >> 19) & 63)];
                 const double gd = (rc & (1 << 18)) ? g : 0.0;
-                gN[p] = (rc & (1 << 16)) ? fma(kap, t, -gd) : t;
+                gN[p] = fma(kap, t, -gd);
             }
 #else
             _Pragma(PLB_STR(unroll PLB_K1_UNROLL))
@@ -631,7 +640,11 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
         return K1_NSTAGE * K1_PITCH + el * NR * NR + rr * NR + cc;
 #endif
     }
+#if PLB_TH
+    return (k1_stage_slot(slot) * K1_PITCH + lane) | (LW << 19);      // kap slot LW: the constant 1.0
+#else
     return k1_stage_slot(slot) * K1_PITCH + lane;
+#endif
 }
 
 // =================================================================================================
@@ -803,6 +816,7 @@ VariantInfo info() {
     v.sim_warps = SIM_WARPS; v.sim_ctas = SIM_CTAS; v.k1_warps = K1_WARPS; v.k1_ctas = PLB_K1_CTAS;
     v.sim_smem = SIM_SMEM; v.k1_smem = K1_SMEM; v.vs = VS; v.nglobal = NGLOBAL;
     v.n_slots = JS_COUNT; v.n_stage = K1_NSTAGE; v.k1_src_max = K1_SRC_MAX; v.lanes = LW;
+    v.k1_tma = (!WIDE && !TH && (!SEI || PLB_SEI_TMA)) ? 1 : 0;
     return v;
 }
 
@@ -825,7 +839,7 @@ VariantInfo info() {
 cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) {
 #if !PLB_WIDE && !PLB_TH
     // (SEI: its larger value table leaves two CTAs per SM next to the staging buffers; the per-lane loads stay ahead: 0.65 vs 1.08 ms)
-    if (a.use_tma && !SEI) PLB_LAUNCH(k_resjac_tma, a, grid, K1_WARPS * LW, K1T_SMEM, s);
+    if (a.use_tma) PLB_LAUNCH(k_resjac_tma, a, grid, K1_WARPS * LW, K1T_SMEM, s);
 #endif
     PLB_LAUNCH(k_resjac, a, grid, K1_WARPS * LW, K1_SMEM, s);
 }

@@ -16,8 +16,14 @@ for fam in fams:
     P.simulate_(sol, p, 100, V="hold")
     tab = P.Table([0.0, 30.0, 30.0, 60.0], [1.0, 1.0, 2.0, 0.5])
     sol2 = P.simulate(p, 60, I=tab, SOC=0.2, outputs="all", tstops=[10.0])              # extended kernel
+    sol3 = P.simulate(p, np.array([0.0, 7.0, 33.0, 150.0, 1e6]), I=1, SOC=0.1, V_max=3.9)  # dense output rows
     Y0 = p.initial_guess(np.full(B, 0.5))
     st, Y, YP = p.newton_init(Y0, method="I", value=1.0)
-    res, nz = p.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)
+    res, nz = p.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)                  # K1 (TMA-staged where built)
+    os.environ["PLB_K1_NO_TMA"] = "1"
+    p_old = P.petlion("LCO", **kw); p_old.θ["D_sp"] = p.θ["D_sp"]
+    res_b, nz_b = p_old.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)           # K1, per-lane loads
+    del os.environ["PLB_K1_NO_TMA"]
+    assert np.array_equal(res, res_b) and np.array_equal(nz, nz_b)
     x, ok = p.linear_solve(Y, YP, np.full(B, 0.1), res, method="I", value=1.0)
     print(fam, "ok", sol.results[-1].summary["flag"], sol2.results[-1].summary["n_steps"], int(np.isfinite(x).all()), flush=True)
