@@ -63,6 +63,8 @@ enum SecField {
     SC_irc, SC_Fa, SC_sig, SC_EaD, SC_Eak, SC_COUNT
 };
 enum GlobField { GC_T, GC_xcoef, GC_Kc, GC_I1C, GC_psI_p, GC_psI_n, GC_dUdT_on, GC_Tamb, GC_invL,
+                 GC_xbc_a, GC_xbc_z,     // thermal: convective coefficient of the two outermost collector nodes
+                
                  // aging = :SEI: R_SEI, 1/k_n_aging, Uref_s, i_0_jside/F, w, M_n/rho_n
                  GC_RSEI, GC_ikag, GC_Uref, GC_i0F, GC_w, GC_Mrho, GC_COUNT };
 
@@ -76,7 +78,7 @@ struct WarpConst {
     // heat conduction (residuals.jl:299-446): coefficients of T[x-1]-T[x] and T[x+1]-T[x] in the T row of
     // node x, already divided by h*rho*Cp; same for this lane's current-collector node (xL, xR), its
     // convective boundary term xbc*(T_amb - T) and its Joule term xq*I^2
-    double tL[32], tR[32], xL[32], xR[32], xbc[32], xq[32];
+    double tL[32], tR[32], xL[32], xR[32], xq[32];     // (xbc: two non-zero lanes, kept in g[GC_xbc_a / GC_xbc_z])
     double cinv[32];           // 1 / (distance between the centres of nodes x-1 and x+1)
     double s5[3][8];           // h, lambda, rho*Cp of the five sections a,p,s,n,z
 #endif
@@ -439,7 +441,9 @@ __device__ __forceinline__ void setup_consts(const ModelDesc& m, const double* _
             xbc = k == m.Nz - 1 ? th[TF_h_cell] * sc : 0.0;               // T_BC_dx, residuals.jl:319
             xq = I1C * I1C / (th[TF_sigma_z] * C.s5[2][4]);                // residuals.jl:465
         }
-        C.xL[lane] = xL; C.xR[lane] = xR; C.xbc[lane] = xbc; C.xq[lane] = xq;
+        C.xL[lane] = xL; C.xR[lane] = xR; C.xq[lane] = xq;
+        if (lane == 0) C.g[GC_xbc_a] = xbc;
+        if (lane == m.Nx - 1) C.g[GC_xbc_z] = xbc;
         // central differences of thermal_derivatives (auxiliary_states_and_coefficients.jl:363-486):
         // (f[x+1]-f[x-1]) / (distance between the two centres), also across the section interfaces
         double ci = 0.0;
@@ -753,7 +757,8 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         double TxL = TxU, TxR = TxD;
         if (ro.cha && ro.x == m.Na - 1) TxR = T_first;
         if (ro.chz && ro.x == m.Nx - m.Nz) TxL = T_last;
-        const double xL = C.xL[ro.x], xR = C.xR[ro.x], xbc = C.xbc[ro.x], xq = C.xq[ro.x];
+        const double xL = C.xL[ro.x], xR = C.xR[ro.x], xq = C.xq[ro.x];
+        const double xbc = (ro.cha && ro.x == 0) ? C.g[GC_xbc_a] : ((ro.chz && ro.x == m.Nx - 1) ? C.g[GC_xbc_z] : 0.0);
         res.Tx = (ro.cha || ro.chz)
                      ? xL * (TxL - y.Tx) + xR * (TxR - y.Tx) + xq * Iapp * Iapp + xbc * (C.g[GC_Tamb] - y.Tx) - yp.Tx
                      : 0.0;
@@ -876,6 +881,8 @@ struct WarpFactor {
     double schur_inv;          // 1/(g_I - g_ps0*z_ps[0] - g_psN*z_ps[N-1] - g_eta*(z_ps - z_pe)[first anode node])
     double g_ps0, g_psN;
     double g_eta;
+    double ionly;              // != 0: the control row has only its I entry (current control): z holds the RAW border
+                               // column and dI is folded into the right-hand side before the sweeps (no border solve)
 };
 
 // 3x3 inverse by the adjugate (forward error ~ cond * eps, invariant under row/column scaling)
@@ -1149,6 +1156,23 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #else
     const double zf[3] = {0.0, 0.0, J.ps_I};   // border column e_I restricted to this node (Phi_s rows only)
 #endif
+    // Current control (the headline workload, and newtons_method! for it): the control row is g_I dI = g_I_rhs, so dI is
+    // known before the block system is solved and the border column can be folded into the right-hand side of every
+    // solve -- no border solve here.  That solve was a third of the factorisation, and the factorising warp is the one
+    // the other five wait for at the tick barrier in 61 % of the ticks.
+    const bool ionly = ctrl.g_ps0 == 0.0 && ctrl.g_psN == 0.0 && ctrl.g_eta == 0.0;
+    if (ionly) {
+        Fa.z[0][lane] = zf[0]; Fa.z[1][lane] = zf[1]; Fa.z[2][lane] = zf[2];
+        // (a singular diagonal block no longer reaches schur_inv through z: look at the blocks themselves)
+        const double chk = Di[0] + Di[4] + Di[8];
+        const double bad = grp_max((chk == chk && !isinf(chk)) ? 0.0 : 1.0);
+        if (lane == 0) {
+            Fa.schur_inv = bad != 0.0 ? NAN : 1.0 / ctrl.g_I;
+            Fa.g_ps0 = 0.0; Fa.g_psN = 0.0; Fa.g_eta = 0.0; Fa.ionly = 1.0;
+        }
+        grp_sync();
+        return;
+    }
     double u3[3];
     thomas_sweeps(m.Nx, ch, Wm, Pm, Di, zf, u3);
     Fa.z[0][lane] = u3[0]; Fa.z[1][lane] = u3[1]; Fa.z[2][lane] = u3[2];
@@ -1159,6 +1183,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         Fa.g_ps0 = ctrl.g_ps0;
         Fa.g_psN = ctrl.g_psN;
         Fa.g_eta = ctrl.g_eta;
+        Fa.ionly = 0.0;
     }
     grp_sync();
 }
@@ -1208,13 +1233,20 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     for (int k = 0; k < 9; k++) { Di[k] = Fa.Dinv[k][lane]; Wm[k] = Fa.Wm[k][lane]; Pm[k] = Fa.Pm[k][lane]; }
     double u3[3];
     const LaneChain ch = make_chain(m.Nx, lane);
-    thomas_sweeps(m.Nx, ch, Wm, Pm, Di, rf, u3);
-    // border
-    const double x0 = shfl_from(u3[2], 0), xN = shfl_from(u3[2], m.Nx - 1);
-    double gx = Fa.g_ps0 * x0 + Fa.g_psN * xN;
-    if (Fa.g_eta != 0.0) gx += Fa.g_eta * shfl_from(u3[2] - u3[1], m.Np + m.Ns);      // eta_p control (uniform branch)
-    const double dI = (gI - gx) * Fa.schur_inv;
-    u3[0] -= Fa.z[0][lane] * dI; u3[1] -= Fa.z[1][lane] * dI; u3[2] -= Fa.z[2][lane] * dI;
+    double dI;
+    if (Fa.ionly != 0.0) {       // (uniform) current control: dI first, its column folded into the right-hand side
+        dI = gI * Fa.schur_inv;
+        rf[0] -= Fa.z[0][lane] * dI; rf[1] -= Fa.z[1][lane] * dI; rf[2] -= Fa.z[2][lane] * dI;
+        thomas_sweeps(m.Nx, ch, Wm, Pm, Di, rf, u3);
+    } else {
+        thomas_sweeps(m.Nx, ch, Wm, Pm, Di, rf, u3);
+        // border
+        const double x0 = shfl_from(u3[2], 0), xN = shfl_from(u3[2], m.Nx - 1);
+        double gx = Fa.g_ps0 * x0 + Fa.g_psN * xN;
+        if (Fa.g_eta != 0.0) gx += Fa.g_eta * shfl_from(u3[2] - u3[1], m.Np + m.Ns);      // eta_p control (uniform branch)
+        dI = (gI - gx) * Fa.schur_inv;
+        u3[0] -= Fa.z[0][lane] * dI; u3[1] -= Fa.z[1][lane] * dI; u3[2] -= Fa.z[2][lane] * dI;
+    }
     // back-substitute j (and j_s, film) and the particle
 #if PLB_SEI
     v0 -= Fa.cpl[0][lane] * u3[0] + Fa.cpl[1][lane] * u3[1] + Fa.cpl[2][lane] * u3[2];

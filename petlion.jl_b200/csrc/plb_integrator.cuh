@@ -20,7 +20,11 @@ namespace PLB_NS {
 
 // vector stride in doubles (N_tot padded): 301 / 351 / 322 on the 32-node families, up to 642 (N=(20,20,20) with SEI) wide
 constexpr int VS = WIDE ? 656 : (TH ? 352 : (SEI ? 336 : 304));
-enum VecId { V_PHI0 = 0, V_PHI1, V_PHI2, V_PHI3, V_PHI4, V_PHI5, V_YPRED, V_YPPRED, V_EWT, V_EE, V_COUNT };
+// (Round 2: no predictor vectors.  y_pred = sum_j phi_j and y'_pred = sum_j gamma_j phi_j are re-formed from the
+// history where an evaluation needs them -- kk+1 shared-memory reads per component instead of two -- and phi_4, phi_5
+// live in global memory (PLB_NGLOBAL): six vectors per system in shared memory instead of ten, eight systems per SM
+// instead of six.  Measured marginal gain per additional warp: +39 k sims/s (4, 5, 6 warps: 238, 278, 317 k).)
+enum VecId { V_PHI0 = 0, V_PHI1, V_PHI2, V_PHI3, V_PHI4, V_PHI5, V_EWT, V_EE, V_COUNT };
 
 struct IdaCoef {
     double psi[6], alpha[6], beta[6], sigma[6], gamma[6];
@@ -30,10 +34,10 @@ struct IdaCoef {
 
 // Number of BDF history vectors kept in global memory (L2-resident) instead of shared memory: the
 // LAST PLB_NGLOBAL of phi_0..phi_5.  Measured order histogram of the 1C discharge batch: order 1: 6 %,
-// 2: 47 %, 3: 41 %, 4: 5 %, 5: 0.1 % -- phi_5 and phi_4 are rarely touched, and parking them in L2
-// lets one more system fit per SM.
+// 2: 47 %, 3: 41 %, 4: 5 %, 5: 0.1 % -- phi_5 is hardly ever touched, phi_4 is written once per step at order 3
+// (a fire-and-forget store) and read when an order raise is considered.
 #ifndef PLB_NGLOBAL
-#define PLB_NGLOBAL 0
+#define PLB_NGLOBAL 2
 #endif
 constexpr int NGLOBAL = PLB_NGLOBAL;
 constexpr int NSHARED = V_COUNT - NGLOBAL;
@@ -336,48 +340,64 @@ __device__ __forceinline__ double ida_set_coeffs(const ModelDesc& m, WarpWS& w, 
     return ck;
 }
 
-// phi_k *= beta_k (k = ns..kk: "phi-star"), predictor y = sum phi_j, y' = sum gamma_j phi_j, ee = 0
+// phi_k *= beta_k (k = ns..kk: "phi-star"), ee = 0.  The predictor itself (y = sum phi_j, y' = sum gamma_j phi_j) is
+// formed per lane by predictor_lane() where an evaluation needs it.
 __device__ __forceinline__ void predict_pass(const ModelDesc& m, WarpWS& w, const Ida& M, int lane) {
     const IdaCoef& K = w.K;
-    double be[6], ga[6];
+    double be[6];
 #pragma unroll
-    for (int j = 0; j < 6; j++) { be[j] = K.beta[j]; ga[j] = K.gamma[j]; }
-    double* yp_ = w.v(V_YPRED);
-    double* ypp_ = w.v(V_YPPRED);
+    for (int j = 0; j < 6; j++) be[j] = K.beta[j];
     double* ee_ = w.v(V_EE);
     const int kk = M.kk, ns = M.ns;     // the integrator state lives in shared memory: read it once
 #if PLB_VEC2
     PLB_FOR_PAIRS(q, m.N_tot) {
-        double2 yv = make_double2(0.0, 0.0), ypv = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-            if (j <= kk) {
+        for (int j = 1; j < 6; j++) {
+            if (j >= ns && j <= kk) {
                 double* ph = w.v(V_PHI0 + j);
                 double2 p = ld2(ph, q);
-                if (j >= ns) { p.x *= be[j]; p.y *= be[j]; st2(ph, q, p); }
-                yv.x += p.x; yv.y += p.y;
-                if (j > 0) { ypv.x = fma(ga[j], p.x, ypv.x); ypv.y = fma(ga[j], p.y, ypv.y); }
+                p.x *= be[j]; p.y *= be[j];
+                st2(ph, q, p);
             }
         }
-        st2(yp_, q, yv); st2(ypp_, q, ypv); st2(ee_, q, make_double2(0.0, 0.0));
+        st2(ee_, q, make_double2(0.0, 0.0));
     }
 #else
     PLB_FOR_ELEMS(i, m.N_tot) {
-        double yv = 0.0, ypv = 0.0;
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-            if (j <= kk) {
-                double* ph = w.v(V_PHI0 + j);
-                double p = ph[i];
-                if (j >= ns) { p *= be[j]; ph[i] = p; }
-                yv += p;
-                if (j > 0) ypv = fma(ga[j], p, ypv);
-            }
+        for (int j = 1; j < 6; j++) {
+            if (j >= ns && j <= kk) { double* ph = w.v(V_PHI0 + j); ph[i] *= be[j]; }
         }
-        yp_[i] = yv; ypp_[i] = ypv; ee_[i] = 0.0;
+        ee_[i] = 0.0;
     }
 #endif
     grp_sync();
+}
+
+// y_pred, y'_pred of this lane's components from the (phi-star) history, in the summation order the predictor
+// vectors used to be formed in: y = ((phi_0 + phi_1) + ...), y' = fma(gamma_j, phi_j, y') for j = 1..kk
+__device__ __forceinline__ void predictor_lane(const ModelDesc& m, const LaneRole& ro, WarpWS& w, int kk, LaneVec& y,
+                                               double& Iy, LaneVec& yp) {
+    load_lane(m, ro, w.v(V_PHI0), y, Iy);
+    yp.ce = 0.0; yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.T = 0.0; yp.Tx = 0.0; yp.js = 0.0; yp.film = 0.0; yp.soh = 0.0;
+#pragma unroll
+    for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
+#pragma unroll 1
+    for (int j = 1; j <= kk; j++) {
+        const double ga = w.K.gamma[j];
+        LaneVec p;
+        double pI;
+        load_lane(m, ro, w.v(V_PHI0 + j), p, pI);
+        y.ce += p.ce; y.j += p.j; y.pe += p.pe; y.ps += p.ps; Iy += pI;
+        yp.ce = fma(ga, p.ce, yp.ce);
+        if (TH) { y.T += p.T; y.Tx += p.Tx; yp.T = fma(ga, p.T, yp.T); yp.Tx = fma(ga, p.Tx, yp.Tx); }
+        if (SEI) {
+            y.js += p.js; y.film += p.film; y.soh += p.soh;
+            yp.film = fma(ga, p.film, yp.film); yp.soh = fma(ga, p.soh, yp.soh);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; r++) { y.cs[r] += p.cs[r]; yp.cs[r] = fma(ga, p.cs[r], yp.cs[r]); }
+    }
 }
 
 __device__ __forceinline__ bool ida_test_error(const ModelDesc& m, WarpWS& w, Ida& M, double ck,

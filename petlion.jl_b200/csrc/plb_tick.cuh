@@ -779,21 +779,22 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
         for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
         if (do_eval) {
             if (S.state == ST_NLS) {
-                LaneVec e, p;
-                double eI, pI;
-                load_lane(m, ro, w.v(V_YPRED), y, Iy);
+                LaneVec e;
+                double eI;
+                predictor_lane(m, ro, w, S.M.kk, y, Iy, yp);       // y_pred, y'_pred from the history
                 load_lane(m, ro, w.v(V_EE), e, eI);
-                load_lane(m, ro, w.v(V_YPPRED), p, pI);
                 const double cj = S.M.cj;
                 y.ce += e.ce; y.j += e.j; y.pe += e.pe; y.ps += e.ps; Iy += eI;
-                yp.ce = p.ce + cj * e.ce;
-                if (TH) { y.T += e.T; y.Tx += e.Tx; yp.T = p.T + cj * e.T; yp.Tx = p.Tx + cj * e.Tx; }
+                yp.ce = yp.ce + cj * e.ce;
+                if (TH) { y.T += e.T; y.Tx += e.Tx; yp.T = yp.T + cj * e.T; yp.Tx = yp.Tx + cj * e.Tx; }
                 if (SEI) {
                     y.js += e.js; y.film += e.film; y.soh += e.soh;
-                    yp.film = p.film + cj * e.film; yp.soh = p.soh + cj * e.soh;
+                    yp.film = yp.film + cj * e.film; yp.soh = yp.soh + cj * e.soh;
                 }
 #pragma unroll
-                for (int r = 0; r < NR; r++) { y.cs[r] += e.cs[r]; yp.cs[r] = p.cs[r] + cj * e.cs[r]; }
+                for (int r = 0; r < NR; r++) { y.cs[r] += e.cs[r]; yp.cs[r] = yp.cs[r] + cj * e.cs[r]; }
+                // (the algebraic components of y' never enter a residual)
+                yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.js = 0.0;
                 need_jac = S.callLSetup != 0; do_solve = true;
             } else {
                 load_lane(m, ro, w.v(V_PHI0), y, Iy);

@@ -654,10 +654,11 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // systems (lane groups) in flight per CTA, and CTAs per SM.  One barrier per tick (plb_tick.cuh) keeps the
 // systems of a CTA on one instruction stream; with only that barrier left, one large CTA per SM is best for the
 // 32-lane families (measured, iso, sims/s on one B200: 6x1 229 k, 3x2 213 k, 2x3 200 k).
-#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? 4 : (PLB_SEI ? 5 : 6)))
+// (round 2: six vectors per system in shared memory instead of ten: 8 / 6 / 5 systems per SM instead of 6 / 5 / 4)
+#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? 5 : (PLB_SEI ? 6 : 8)))
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS (PLB_WIDE ? 2 : 1)
+#define PLB_SIM_CTAS (PLB_WIDE ? 3 : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
@@ -665,7 +666,7 @@ constexpr int SIM_CTAS = PLB_SIM_CTAS;
 #ifndef PLB_STATE_SMEM
 #define PLB_STATE_SMEM 1          // measured (iso): 229 k sims/s in registers/local memory, 246 k in shared memory
 #endif
-constexpr size_t STATE_BYTES = PLB_STATE_SMEM ? 640 : 0;           // per physical warp
+constexpr size_t STATE_BYTES = PLB_STATE_SMEM ? 480 : 0;           // per physical warp
 constexpr size_t STATE_OFFSET = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
 constexpr size_t SIM_SMEM = STATE_OFFSET + STATE_BYTES * SIM_WARPS * (LW / 32);
 
