@@ -22,6 +22,8 @@ extern "C" {
 typedef struct plb_handle_s *plb_handle;
 
 enum { PLB_CATHODE_LCO = 0, PLB_CATHODE_NMC = 1 };
+/* reaction rate laws, chosen per electrode (params.jl:51, 114; custom_functions.jl:212-231 rxn_BV, :233-298 rxn_MHC) */
+enum { PLB_RXN_BV = 0, PLB_RXN_MHC = 1 };
 /* method_I / method_V / method_P (scalar_residual.jl:167-202); PLB_METHOD_DT = the `dT` input of thermal
  * models (constant spatially-averaged temperature: control row val - temperature_weighting(Y'[T]),
  * src/physics_equations/input_methods.jl:182-189; dT=:hold == dT=0);
@@ -38,6 +40,8 @@ typedef struct {
                         needs N_p, N_n >= 5 and N_a + N_z <= N_p + N_s + N_n)                  */
     int aging;       /* 0: none.  1: aging=:SEI (LCO, isothermal; adds film, SOH, j_s: N = 322 for 10/10/10) */
     int device;      /* CUDA device ordinal */
+    int rxn_p, rxn_n; /* PLB_RXN_*: reaction rate law of the positive / negative electrode (0 = rxn_BV, the default).
+                        rxn_MHC adds the keys lambda_MHC_p / lambda_MHC_n to theta (LCO parameter set only) */
 } plb_model_desc;
 
 /* run_constant{method,value}: src/structures.jl:46-54; input kinds: src/physics_equations/input_methods.jl:5-74 */

@@ -14,6 +14,7 @@ const lib = "libpetlion_b200"          # petlion.jl_b200/csrc/libpetlion_b200.so
 struct ModelDesc
     cathode::Cint; N_p::Cint; N_s::Cint; N_n::Cint; N_a::Cint; N_z::Cint; N_r_p::Cint; N_r_n::Cint
     temperature::Cint; aging::Cint; device::Cint
+    rxn_p::Cint; rxn_n::Cint          # 0 rxn_BV, 1 rxn_MHC
 end
 struct Run
     method::Cint; input_kind::Cint; value::Cdouble; tf::Cdouble; new_run::Cint; reserved::Cint
@@ -41,8 +42,10 @@ const MEM_HOST, MEM_DEVICE = 0, 1
 check(rc) = rc == 0 || error(unsafe_string(ccall((:plb_last_error, lib), Cstring, ())))
 
 # ---- model handle: petlion(...) (src/external.jl:2-18) ------------------------------------------------------------
-function create(cathode::Symbol, N, temperature::Bool, aging; device::Integer = 0)::Ptr{Cvoid}
-    d = ModelDesc(cathode === :LCO ? 0 : 1, N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, device)
+rxn_code(f) = Symbol(f) === :rxn_MHC ? 1 : 0
+function create(cathode::Symbol, N, temperature::Bool, aging; device::Integer = 0, rxn_p = :rxn_BV, rxn_n = :rxn_BV)::Ptr{Cvoid}
+    d = ModelDesc(cathode === :LCO ? 0 : 1, N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, device,
+                  rxn_code(rxn_p), rxn_code(rxn_n))
     h = Ref{Ptr{Cvoid}}()
     check(ccall((:plb_create, lib), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}), d, h))
     return h[]
@@ -150,8 +153,9 @@ function simulate_table!(h, B, θ, run::Run, tt::Vector{Float64}, vv::Vector{Flo
 end
 
 # ---- several GPUs of the box behind one call (contiguous batch shards, one ncclAllGather of the summaries) --------
-function group_create(cathode::Symbol, N, temperature::Bool, aging, devices::Vector{<:Integer})::Ptr{Cvoid}
-    d = ModelDesc(cathode === :LCO ? 0 : 1, N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, 0)
+function group_create(cathode::Symbol, N, temperature::Bool, aging, devices::Vector{<:Integer}; rxn_p = :rxn_BV, rxn_n = :rxn_BV)::Ptr{Cvoid}
+    d = ModelDesc(cathode === :LCO ? 0 : 1, N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, 0,
+                  rxn_code(rxn_p), rxn_code(rxn_n))
     g = Ref{Ptr{Cvoid}}()
     check(ccall((:plb_group_create, lib), Cint, (Ref{ModelDesc}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), d, length(devices), Cint.(devices), g))
     return g[]

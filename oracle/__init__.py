@@ -28,7 +28,8 @@ def build(force=False):
 
 class Model(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n", "temperature", "aging", "cathode")]
+                ("N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n", "temperature", "aging", "cathode",
+                 "rxn_p", "rxn_n")]
 
 
 class Layout(C.Structure):
@@ -117,10 +118,13 @@ def theta_dict(cathode="LCO"):
     return dict(zip(theta_names(), theta_defaults(cathode)))
 
 
+RXN = {"BV": 0, "MHC": 1, "rxn_BV": 0, "rxn_MHC": 1}
+
+
 def make_model(cathode="LCO", N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10,
-               temperature=False, aging=False):
+               temperature=False, aging=False, rxn_p="BV", rxn_n="BV"):
     return Model(N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, int(bool(temperature)), int(bool(aging)),
-                 CATHODE[cathode])
+                 CATHODE[cathode], RXN[rxn_p], RXN[rxn_n])
 
 
 def layout(m):

@@ -39,7 +39,8 @@ extern "C" {
     X(Cp_a) X(Cp_n) X(Cp_p) X(Cp_s) X(Cp_z) X(h_cell)                                   \
     X(lambda_a) X(lambda_n) X(lambda_p) X(lambda_s) X(lambda_z) /* λ_* */               \
     X(rho_a) X(rho_n) X(rho_p) X(rho_s) X(rho_z) /* ρ_* */                              \
-    X(M_n) X(R_SEI) X(Uref_s) X(i_0_jside) X(k_n_aging) X(w)
+    X(M_n) X(R_SEI) X(Uref_s) X(i_0_jside) X(k_n_aging) X(w)                            \
+    X(lambda_MHC_n) X(lambda_MHC_p) /* λ_MHC_* (rxn_MHC only) */
 
 typedef struct {
 #define X(n) double n;
@@ -50,6 +51,7 @@ typedef struct {
 #define ORC_NTHETA ((int)(sizeof(orc_theta) / sizeof(double)))
 
 enum { ORC_CATHODE_LCO = 0, ORC_CATHODE_NMC = 1 };
+enum { ORC_RXN_BV = 0, ORC_RXN_MHC = 1 };   /* custom_functions.jl:212-231, 241-298 */
 /* method_I / method_V / method_P (scalar_residual.jl:167-202) and `dT` = the constant_temperature
  * residual of input_methods.jl:182-189 (control row  val - temperature_weighting(Y'[T])).
  * ORC_METHOD_DT_ALG is internal: the same row inside newtons_method!, where the reference substitutes
@@ -63,6 +65,7 @@ typedef struct {
     int temperature; /* 0 isothermal, 1 thermal   */
     int aging;       /* 0 none, 1 :SEI            */
     int cathode;     /* ORC_CATHODE_*             */
+    int rxn_p, rxn_n; /* ORC_RXN_*: rxn_BV (default) or rxn_MHC, per electrode (params.jl:51, 114) */
 } orc_model;
 
 /* index layout -- src/external.jl:275-365, SURVEY App. A (0-based here) */

@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
 
 class ModelDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("cathode", "N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n",
-                                       "temperature", "aging", "device")]
+                                       "temperature", "aging", "device", "rxn_p", "rxn_n")]
 
 
 class Run(C.Structure):

@@ -16,6 +16,8 @@ import numpy as np
 from . import _lib
 
 CATHODES = {"LCO": 0, "NMC": 1}
+RXN = {"rxn_BV": 0, "rxn_MHC": 1}      # reaction rate laws (custom_functions.jl:212-298)
+rxn_BV, rxn_MHC = "rxn_BV", "rxn_MHC"
 METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4}
 EXIT_REASONS = {  # src/checks.jl
     -1: "running", 0: "Final time reached", 1: "Below min. voltage", 2: "Above max. voltage",
@@ -54,7 +56,8 @@ class Model:
         self.N = N
         self.numerics = numerics
         desc = _lib.ModelDesc(CATHODES[cathode], N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n,
-                              int(bool(numerics.temperature)), int(bool(numerics.aging)), int(device))
+                              int(bool(numerics.temperature)), int(bool(numerics.aging)), int(device),
+                              RXN[numerics.rxn_p], RXN[numerics.rxn_n])
         self._g = None
         self.devices = [int(device)] if devices is None else [int(d) for d in devices]
         if devices is not None and len(self.devices) > 1:
@@ -236,7 +239,10 @@ def model_key(p):
     import hashlib
     nm, N = p.numerics, p.N
     anode = "LiC6" if p.cathode == "LCO" else "LiC6_NMC"
-    fields = [str(nm.temperature).lower(), nm.solid_diffusion, nm.Fickian_method, "SEI" if nm.aging else "false", nm.jacobian,
+    lco = p.cathode == "LCO"
+    fields = [str(nm.temperature).lower(), nm.solid_diffusion, nm.Fickian_method, "SEI" if nm.aging else "false",
+              nm.rxn_p, nm.rxn_n, "OCV_LCO" if lco else "OCV_NMC", "OCV_LiC6" if lco else "OCV_LiC6_NMC", "D_s_eff", "rxn_rate",
+              "D_eff_linear" if lco else "D_eff", "K_eff", "thermodynamic_factor_linear", nm.jacobian,
               f"Np{N.p}", f"Ns{N.s}", f"Nn{N.n}", f"Na{N.a}_Nz{N.z}" if nm.temperature else "",
               f"Nr_p{N.r_p}_Nr_n{N.r_n}" if nm.solid_diffusion == "Fickian" else ""]
     return f"{p.cathode}_{anode}/" + hashlib.sha1("_".join(fields).encode()).hexdigest()
@@ -312,8 +318,9 @@ class Solution:
 
 def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10, temperature=False,
             solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic",
-            device=0, devices=None):
-    """petlion(cathode; kwargs...) -- src/external.jl:2-18, src/params.jl:119-174."""
+            rxn_p="rxn_BV", rxn_n="rxn_BV", device=0, devices=None):
+    """petlion(cathode; kwargs...) -- src/external.jl:2-18, src/params.jl:119-174.
+    rxn_p / rxn_n: "rxn_BV" (default) or "rxn_MHC" (custom_functions.jl:212-298), per electrode."""
     if cathode not in CATHODES:
         raise ValueError(f"unknown cathode {cathode!r}; built: {list(CATHODES)}")
     if solid_diffusion != "Fickian" or Fickian_method != "finite_difference":
@@ -322,9 +329,12 @@ def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, 
         raise ValueError("`jacobian` can either be :symbolic or :AD")   # checks.jl:377-383
     if aging not in (False, True, "SEI"):       # params.jl:119-174: aging = false | :SEI
         raise ValueError(f"unknown aging model {aging!r}; built: False, \"SEI\"")
+    for r in (rxn_p, rxn_n):
+        if r not in RXN:
+            raise ValueError(f"unknown reaction rate law {r!r}; built: {list(RXN)}")
     N = _NS(p=N_p, s=N_s, n=N_n, a=N_a, z=N_z, r_p=N_r_p, r_n=N_r_n)
     numerics = _NS(temperature=temperature, solid_diffusion=solid_diffusion, Fickian_method=Fickian_method,
-                   aging=aging, jacobian=jacobian, cathode=cathode)
+                   aging=aging, jacobian=jacobian, cathode=cathode, rxn_p=rxn_p, rxn_n=rxn_n)
     return Model(cathode, N, numerics, device, devices)
 
 

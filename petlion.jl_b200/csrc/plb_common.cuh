@@ -38,6 +38,8 @@ enum ThetaField {
     TF_rho_a, TF_rho_n, TF_rho_p, TF_rho_s, TF_rho_z, TF_sigma_a, TF_sigma_z,
     // aging = :SEI (params.jl:58-117); rho_n above is shared with the thermal block
     TF_M_n, TF_R_SEI, TF_Uref_s, TF_i_0_jside, TF_k_n_aging, TF_w,
+    // rxn_MHC (params.jl:16, 67)
+    TF_lambda_MHC_n, TF_lambda_MHC_p,
     TF_COUNT
 };
 
@@ -48,6 +50,7 @@ struct ModelDesc {
     int thermal;                 // temperature = true
     int aging;                   // aging = :SEI
     int chem;                    // CHEM_*
+    int rxn_mhc;                 // bit 0 / 1: rxn_MHC instead of rxn_BV in the positive / negative electrode
     int ntheta;                  // length of one theta row (reference order, used keys only)
     int theta_stride;            // row stride in doubles
     int mid;                     // meeting node of the twisted block elimination

@@ -495,6 +495,38 @@ struct CtrlRow {
     double g_eta;
 };
 
+// rxn_MHC (custom_functions.jl:233-298, the alpha == 0.5 branch -- the only live one): value and partial derivatives
+// with respect to (eta, c_e, c_s_star) at fixed k and T; fT = F/(R T).  Every sqrt of the reference function is
+// sqrt_ReLU, log_ReLU(x; 1e-4) = log(max(1e-4, x)).
+struct MhcRate { double j, d_eta, d_ce, d_cs; };
+__device__ __noinline__ void mhc_rate(double cs, double ce, double eta, double k_i, double fT, double lam, double cmax,
+                                      double ce0, bool with_jac, MhcRate& o) {
+    const double ratio = (ce / ce0) / (cs / cmax);
+    const bool live = ratio > 1e-4;
+    const double eta_f = eta * fT + (live ? log(ratio) : log(1e-4));
+    const double sl = sqrt(fmax(lam, 0.0));
+    const double a = 1.0 + sl;
+    const double k0 = k_i / ((1.0 - erf((lam - sqrt(a)) / (2.0 * sl))) / 2.0);
+    const double r = sqrt(fmax(a + eta_f * eta_f, 0.0));
+    const double u = (lam - r) / (2.0 * sl);
+    const double g = 1.0 - erf(u);
+    const double em = exp(-eta_f);
+    const double sp = 1.0 / (1.0 + em), sm = 1.0 / (1.0 + exp(eta_f));
+    const double B = sp * ce0 * cs - sm * ce * cmax;
+    const double sa = (1.0 - cs / cmax) / ce0;
+    const double Sq = sa > 0.0 ? sqrt(sa) : 0.0;
+    o.j = k0 * g * B * Sq;
+    if (with_jac) {
+        // d g / d eta_f = (2/sqrt(pi)) exp(-u^2) (eta_f / r) / (2 sl)
+        const double dg = r > 0.0 ? 1.1283791670955126 * exp(-u * u) * eta_f / (r * 2.0 * sl) : 0.0;
+        const double dB = (ce0 * cs + ce * cmax) * sp * sm;
+        const double dj_f = k0 * Sq * (dg * B + g * dB);                 // d j / d eta_f
+        o.d_eta = dj_f * fT;
+        o.d_ce = (live ? dj_f / ce : 0.0) - k0 * g * Sq * cmax * sm;
+        o.d_cs = (live ? -dj_f / cs : 0.0) + k0 * g * Sq * ce0 * sp + (Sq > 0.0 ? -k0 * g * B / (2.0 * Sq * cmax * ce0) : 0.0);
+    }
+}
+
 template <int CHEM, bool WITH_JAC>
 __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C, const LaneRole& ro,
                                           const LaneVec& y, const LaneVec& yp, double Iapp,
@@ -612,31 +644,53 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
             else laws::OCV_LiC6_NMC(th, U, dU);
         }
         const double eta = y.ps - y.pe - U - (sei_n ? kF * y.j * Rfilm : 0.0);   // build_eta! (:272-300)
-        // rxn_BV, custom_functions.jl:212-231
         const double cmax = C.sec[SC_cmax][s];
-        const double arg = ce * cs_s * (cmax - cs_s);
-        const double sq = arg > 0.0 ? sqrt(arg) : 0.0;                       // sqrt_ReLU
-        const double xx = xco * eta;
-        const double em = expm1(xx);
-        const double rem = __drcp_rn(em + 1.0);                              // exp(-xx)
-        const double sh = 0.5 * (em + em * rem);                             // sinh(xx)
-        const double k2 = k2x;
-        jcalc = k2 * sq * sh;
-        if (TH) { eta_h = eta; dUdT_h = dUdT; ddUdT_h = ddUdT; dUtot_h = dU; }
-        if (WITH_JAC) {
-            const double ch = sh + rem;                                      // cosh = sinh + exp(-x)
-            const double isq = arg > 0.0 ? 0.5 / sq : 0.0;
-            dj_eta = k2 * sq * ch * xco;
-            dj_ce = k2 * sh * isq * cs_s * (cmax - cs_s);
-            dj_cs = k2 * sh * isq * ce * (cmax - 2.0 * cs_s) - dj_eta * dU * C.sec[SC_inv_cmax][s];
+        if (m.rxn_mhc != 0 && ((m.rxn_mhc >> (ro.sec == 2 ? 1 : 0)) & 1)) {
+            // rxn_MHC, custom_functions.jl:233-298 (out of line: a model option, kept off the registers of rxn_BV)
+            MhcRate o;
+            mhc_rate(cs_s, ce, eta, 0.5 * k2x, 2.0 * xco, C.theta[ro.sec == 2 ? TF_lambda_MHC_n : TF_lambda_MHC_p], cmax,
+                     C.theta[TF_c_e0], WITH_JAC, o);
+            jcalc = o.j;
+            if (TH) { eta_h = eta; dUdT_h = dUdT; ddUdT_h = ddUdT; dUtot_h = dU; }
+            if (WITH_JAC) {
+                dj_eta = o.d_eta;
+                dj_ce = o.d_ce;
+                dj_cs = o.d_cs - dj_eta * dU * C.sec[SC_inv_cmax][s];
 #if PLB_SEI
-            J.j_j = -1.0 - (sei_n ? dj_eta * kF * Rfilm : 0.0);
-            J.j_film = sei_n ? -dj_eta * kF * y.j * C.g[GC_ikag] : 0.0;
+                J.j_j = -1.0 - (sei_n ? dj_eta * kF * Rfilm : 0.0);
+                J.j_film = sei_n ? -dj_eta * kF * y.j * C.g[GC_ikag] : 0.0;
 #endif
-            if (TH) {
-                // d/dT: k(T), eta(T) through U = U0 + dUdT (T - Tref), and the 1/T in the sinh argument
-                const double iT = 1.0 / T;
-                dj_T = jcalc * C.sec[SC_Eak][s] * iT * iT + k2 * sq * ch * (-xco * dUdT - xx * iT);
+                if (TH) {
+                    const double iT = 1.0 / T;       // k(T), U(T), and the 1/T of eta_hat
+                    dj_T = jcalc * C.sec[SC_Eak][s] * iT * iT - dj_eta * dUdT - dj_eta * eta * iT;
+                }
+            }
+        } else {
+            // rxn_BV, custom_functions.jl:212-231
+            const double arg = ce * cs_s * (cmax - cs_s);
+            const double sq = arg > 0.0 ? sqrt(arg) : 0.0;                       // sqrt_ReLU
+            const double xx = xco * eta;
+            const double em = expm1(xx);
+            const double rem = __drcp_rn(em + 1.0);                              // exp(-xx)
+            const double sh = 0.5 * (em + em * rem);                             // sinh(xx)
+            const double k2 = k2x;
+            jcalc = k2 * sq * sh;
+            if (TH) { eta_h = eta; dUdT_h = dUdT; ddUdT_h = ddUdT; dUtot_h = dU; }
+            if (WITH_JAC) {
+                const double ch = sh + rem;                                      // cosh = sinh + exp(-x)
+                const double isq = arg > 0.0 ? 0.5 / sq : 0.0;
+                dj_eta = k2 * sq * ch * xco;
+                dj_ce = k2 * sh * isq * cs_s * (cmax - cs_s);
+                dj_cs = k2 * sh * isq * ce * (cmax - 2.0 * cs_s) - dj_eta * dU * C.sec[SC_inv_cmax][s];
+#if PLB_SEI
+                J.j_j = -1.0 - (sei_n ? dj_eta * kF * Rfilm : 0.0);
+                J.j_film = sei_n ? -dj_eta * kF * y.j * C.g[GC_ikag] : 0.0;
+#endif
+                if (TH) {
+                    // d/dT: k(T), eta(T) through U = U0 + dUdT (T - Tref), and the 1/T in the sinh argument
+                    const double iT = 1.0 / T;
+                    dj_T = jcalc * C.sec[SC_Eak][s] * iT * iT + k2 * sq * ch * (-xco * dUdT - xx * iT);
+                }
             }
         }
     }

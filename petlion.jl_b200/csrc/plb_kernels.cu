@@ -35,7 +35,7 @@ constexpr int NR_HOST = 10;   // N_r of the built variants (laws::NR)
         if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-struct KeyDef { const char* utf8; const char* ascii; int field; double lco, nmc; int only; };   // only: bit 0 thermal, bit 1 aging (0: always)
+struct KeyDef { const char* utf8; const char* ascii; int field; double lco, nmc; int only; };   // only: bit 0 thermal, bit 1 aging, bit 2 / 3 rxn_p / rxn_n = rxn_MHC (0: always)
 // reference keys (UTF-8) <-> canonical fields, with the defaults of src/params.jl:5-117,177-226 (LCO)
 // and :295-367, 428-445 (NMC).  nmc = NaN: key not part of the NMC parameter set.  The table is in the
 // reference's key order (Symbols sorted by code point); `only` marks the keys that the generated functions
@@ -70,6 +70,7 @@ static const KeyDef KEYS[] = {
     {"\xce\xb8_max_p", "theta_max_p", TF_theta_max_p, 0.49550, 0.359749, 0},
     {"\xce\xb8_min_n", "theta_min_n", TF_theta_min_n, 0.01429, 0.001, 0},
     {"\xce\xb8_min_p", "theta_min_p", TF_theta_min_p, 0.99174, 0.955473, 0},
+    {"\xce\xbb_MHC_n", "lambda_MHC_n", TF_lambda_MHC_n, 6.26e-20, NA, 8}, {"\xce\xbb_MHC_p", "lambda_MHC_p", TF_lambda_MHC_p, 6.26e-20, NA, 4},
     {"\xce\xbb_a", "lambda_a", TF_lambda_a, 237.0, NA, 1}, {"\xce\xbb_n", "lambda_n", TF_lambda_n, 1.7, NA, 1},
     {"\xce\xbb_p", "lambda_p", TF_lambda_p, 2.1, NA, 1}, {"\xce\xbb_s", "lambda_s", TF_lambda_s, 0.16, NA, 1},
     {"\xce\xbb_z", "lambda_z", TF_lambda_z, 401.0, NA, 1},
@@ -209,6 +210,11 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (Nx_ > 32 && d->temperature)
         return fail("plb_create: temperature=true on grids with more than 32 x-nodes is not built");
     if (d->cathode != PLB_CATHODE_LCO && d->cathode != PLB_CATHODE_NMC) return fail("plb_create: unknown cathode");
+    if ((d->rxn_p != PLB_RXN_BV && d->rxn_p != PLB_RXN_MHC) || (d->rxn_n != PLB_RXN_BV && d->rxn_n != PLB_RXN_MHC))
+        return fail("plb_create: unknown reaction rate law (built: rxn_BV, rxn_MHC)");
+    // NMC() / LiC6_NMC() define no lambda_MHC_* (params.jl:295-367): the reference throws a KeyError there
+    if ((d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) && d->cathode != PLB_CATHODE_LCO)
+        return fail("plb_create: rxn_MHC needs the LCO parameter set (the NMC set has no lambda_MHC_p / lambda_MHC_n)");
     if (d->temperature) {
         // NMC()/LiC6_NMC() carry no thermal parameters (params.jl:295-367): the reference cannot build it either
         if (d->cathode != PLB_CATHODE_LCO) return fail("plb_create: temperature=true needs the LCO parameter set");
@@ -244,6 +250,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     m.aging = d->aging ? 1 : 0;
     m.Na = m.thermal ? d->N_a : 0; m.Nz = m.thermal ? d->N_z : 0;
     m.chem = d->cathode == PLB_CATHODE_LCO ? CHEM_LCO : CHEM_NMC;
+    m.rxn_mhc = (d->rxn_p == PLB_RXN_MHC ? 1 : 0) | (d->rxn_n == PLB_RXN_MHC ? 2 : 0);
     m.mid = m.thermal ? m.Np + m.Ns / 2 : m.Nx / 2;
     m.inv_n[0] = 1.0 / m.Np; m.inv_n[1] = 1.0 / m.Ns; m.inv_n[2] = 1.0 / m.Nn; m.inv_n[3] = 0.0;
     if (m.aging) {
@@ -280,7 +287,8 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     for (int k = 0; k < (int)(sizeof(KEYS) / sizeof(KEYS[0])); k++) {
         const double dv = d->cathode == PLB_CATHODE_LCO ? KEYS[k].lco : KEYS[k].nmc;
         if (dv != dv) continue;
-        if (KEYS[k].only && !((KEYS[k].only & 1) && m.thermal) && !((KEYS[k].only & 2) && m.aging)) continue;
+        if (KEYS[k].only && !((KEYS[k].only & 1) && m.thermal) && !((KEYS[k].only & 2) && m.aging) &&
+            !((KEYS[k].only & 4) && (m.rxn_mhc & 1)) && !((KEYS[k].only & 8) && (m.rxn_mhc & 2))) continue;
         m.slot[KEYS[k].field] = (int8_t)h->keys.size();
         h->keys.push_back(k);
     }

@@ -227,13 +227,18 @@ def test_compiled_variant_cache_key():
 
 
 def test_model_key_follows_the_reference_directory_hash():
-    """strings_directory_func (src/external.jl:417-456): <Cathode>_<Anode>/sha1(options, Np, Ns, Nn[, Na_Nz][, Nr])"""
+    """strings_directory_func (src/external.jl:417-456): <Cathode>_<Anode>/sha1(every field of options_numerical but
+    cathode and anode (outputs.jl:13-30), Np, Ns, Nn[, Na_Nz][, Nr])"""
     import hashlib
     from petlion_b200.api import _NS, model_key
     N = _NS(p=10, s=10, n=10, a=10, z=10, r_p=10, r_n=10)
-    nm = _NS(temperature=False, solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic")
+    nm = _NS(temperature=False, solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic",
+             rxn_p="rxn_BV", rxn_n="rxn_BV")
     k = model_key(_NS(cathode="LCO", numerics=nm, N=N))
-    assert k == "LCO_LiC6/" + hashlib.sha1(b"false_Fickian_finite_difference_false_symbolic_Np10_Ns10_Nn10__Nr_p10_Nr_n10").hexdigest()
+    assert k == "LCO_LiC6/" + hashlib.sha1(b"false_Fickian_finite_difference_false_rxn_BV_rxn_BV_OCV_LCO_OCV_LiC6_D_s_eff_rxn_rate_"
+                                           b"D_eff_linear_K_eff_thermodynamic_factor_linear_symbolic_Np10_Ns10_Nn10__Nr_p10_Nr_n10").hexdigest()
+    nm3 = nm.copy(); nm3.rxn_n = "rxn_MHC"
+    assert model_key(_NS(cathode="LCO", numerics=nm3, N=N)) != k
     nm2 = nm.copy(); nm2.temperature = True
     assert model_key(_NS(cathode="LCO", numerics=nm2, N=N)) != k
     N2 = N.copy(); N2.a = 5

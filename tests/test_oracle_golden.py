@@ -410,15 +410,21 @@ def test_norm_summation_order_is_not_what_flips_decisions():
 def test_tight_tolerance_cv_phase_is_erratic_in_the_oracle_itself():
     """Why tests/test_gpu_tight.py cannot hold the thermal CV phase to 1e-6 for 100 % of the systems: the restated IDA
     (Sundials.jl's settings: 3 Newton iterations, acceptance on the last rate estimate) is not monotone in the tolerance
-    there.  System 237 of that test's batch, 4C charge to 4.1 V then V = :hold: the current at t = 1845 s is 0.15419 at
-    reltol 1e-6, 1e-8 and 1e-9 -- and 0.14066 at 1e-7 (9 % off; the GPU at 1e-7 gives 0.15419)."""
+    there.  4C charge to 4.1 V then V = :hold on that test's batch: at reltol 1e-7 the CV current of about one system
+    in twenty sits 1-9 % away from its value at 1e-8 (and at 1e-6, 1e-9), the rest agree to 1e-4.  WHICH systems is
+    round-off luck -- it changes with the compiler's contraction choices: one oracle build had system 237 off by 9 %
+    (the GPU agreed with the 1e-8 value there), the next build 26 other systems of the 512 -- so the test counts them
+    instead of naming one."""
     from tests import util
     W = util.PROTOCOLS["cfg3i"]
-    tho = util.oracle_theta_batch(512, first=80000)[[237]]
-    td = np.array([1845.0])
+    tho = util.oracle_theta_batch(128, first=80000)
+    td = np.array([1500.0, 1700.0, 1845.0, 2000.0])
     cur = {}
-    for tol in (1e-6, 1e-7, 1e-8):
+    for tol in (1e-7, 1e-8):
         o = O.default_opts(reltol=tol, abstol=tol, reltol_init=tol, abstol_init=tol, maxiters=400000)
-        cur[tol] = util.oracle_protocol(W, tho, o, dense_t=td, nthreads=1)[1]["dense"]["I"][0, 0]
-    assert abs(cur[1e-6] - cur[1e-8]) < 1e-4 * cur[1e-8]
-    assert abs(cur[1e-7] - cur[1e-8]) > 0.05 * cur[1e-8]
+        cur[tol] = util.oracle_protocol(W, tho, o, dense_t=td, nthreads=16)[1]["dense"]["I"]
+    d = np.abs(cur[1e-7] - cur[1e-8]) / np.abs(cur[1e-8])
+    d = np.where(np.isnan(d), 0.0, d).max(axis=1)
+    assert np.mean(d <= 1e-4) >= 0.8          # most systems: the two tolerances agree
+    assert (d > 1e-2).sum() >= 1              # ... but not all, and not by a little
+    assert d.max() < 0.2                      # (the loose bound tests/test_gpu_tight.py uses for the CV rows)
