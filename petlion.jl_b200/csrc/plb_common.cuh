@@ -170,5 +170,6 @@ PLB_DECLARE_VARIANT(th)
 PLB_DECLARE_VARIANT(sei)
 PLB_DECLARE_VARIANT(wide)
 PLB_DECLARE_VARIANT(wsei)
+PLB_DECLARE_VARIANT(wth)
 
 }  // namespace plb

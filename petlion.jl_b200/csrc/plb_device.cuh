@@ -37,9 +37,6 @@ namespace PLB_NS {
 #ifndef PLB_WIDE
 #define PLB_WIDE 0
 #endif
-#if PLB_TH && PLB_WIDE
-#error "temperature = true on grids with more than 32 nodes is not built"
-#endif
 constexpr bool TH = PLB_TH != 0;
 constexpr bool SEI = PLB_SEI != 0;
 // "Wide" families (grids with 33..64 x-nodes, e.g. N = (20,20,20)): one system is owned by a GROUP of two
@@ -78,8 +75,8 @@ struct WarpConst {
     // heat conduction (residuals.jl:299-446): coefficients of T[x-1]-T[x] and T[x+1]-T[x] in the T row of
     // node x, already divided by h*rho*Cp; same for this lane's current-collector node (xL, xR), its
     // convective boundary term xbc*(T_amb - T) and its Joule term xq*I^2
-    double tL[32], tR[32], xL[32], xR[32], xq[32];     // (xbc: two non-zero lanes, kept in g[GC_xbc_a / GC_xbc_z])
-    double cinv[32];           // 1 / (distance between the centres of nodes x-1 and x+1)
+    double tL[LW], tR[LW], xL[LW], xR[LW], xq[LW];     // (xbc: two non-zero lanes, kept in g[GC_xbc_a / GC_xbc_z])
+    double cinv[LW];           // 1 / (distance between the centres of nodes x-1 and x+1)
     double s5[3][8];           // h, lambda, rho*Cp of the five sections a,p,s,n,z
 #endif
 #if PLB_SEI
@@ -163,6 +160,23 @@ __device__ __forceinline__ double shfl_up(double v) {
     return shfl_from(v, l > 0 ? l - 1 : l);
 #else
     return __shfl_up_sync(FULL, v, 1);
+#endif
+}
+// value of lane+2 / lane-2 (the two end lanes get their own value back, like the warp intrinsics)
+__device__ __forceinline__ double shfl_dn2(double v) {
+#if PLB_WIDE
+    const int l = grp_lane();
+    return shfl_from(v, l < LW - 2 ? l + 2 : l);
+#else
+    return __shfl_down_sync(FULL, v, 2);
+#endif
+}
+__device__ __forceinline__ double shfl_up2(double v) {
+#if PLB_WIDE
+    const int l = grp_lane();
+    return shfl_from(v, l > 1 ? l - 2 : l);
+#else
+    return __shfl_up_sync(FULL, v, 2);
 #endif
 }
 // K values from the same source lane in one exchange
@@ -788,9 +802,9 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
 #pragma unroll
             for (int k = 0; k < 5; k++) { we[k] = 0.0; ws[k] = 0.0; }
         }
-        const double ceL1 = shfl_up(ce), ceL2 = __shfl_up_sync(FULL, ce, 2), ceR2 = __shfl_down_sync(FULL, ce, 2);
-        const double peL1 = shfl_up(y.pe), peL2 = __shfl_up_sync(FULL, y.pe, 2), peR2 = __shfl_down_sync(FULL, y.pe, 2);
-        const double psL2 = __shfl_up_sync(FULL, y.ps, 2), psR2 = __shfl_down_sync(FULL, y.ps, 2);
+        const double ceL1 = shfl_up(ce), ceL2 = shfl_up2(ce), ceR2 = shfl_dn2(ce);
+        const double peL1 = shfl_up(y.pe), peL2 = shfl_up2(y.pe), peR2 = shfl_dn2(y.pe);
+        const double psL2 = shfl_up2(y.ps), psR2 = shfl_dn2(y.ps);
         const double dPe = we[0] * peL2 + we[1] * peL1 + we[2] * y.pe + we[3] * peR + we[4] * peR2;
         const double dCe = we[0] * ceL2 + we[1] * ceL1 + we[2] * ce + we[3] * ceR + we[4] * ceR2;
         const double dPs = ws[0] * psL2 + ws[1] * psL + ws[2] * y.ps + ws[3] * psR + ws[4] * psR2;
@@ -1345,19 +1359,19 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 //   5. the applied current is a border, as in the isothermal variant.
 // ------------------------------------------------------------------------------------------------
 struct WarpFactor {
-    double Dinv[16][32], Wm[16][32], Pm[16][32];
-    double Fr[4][32];          // T-row multiplier for the node two behind in the chain
-    double Eo[3][32];          // chain heads: T-row coupling to (c_e, Phi_e, Phi_s) two nodes ahead
-    double z[4][32], zx[32];   // border column solution
-    double q[5][32];           // j elimination: q_ce, q_pe, q_ps, q_T, inv_den
+    double Dinv[16][LW], Wm[16][LW], Pm[16][LW];
+    double Fr[4][LW];          // T-row multiplier for the node two behind in the chain
+    double Eo[3][LW];          // chain heads: T-row coupling to (c_e, Phi_e, Phi_s) two nodes ahead
+    double z[4][LW], zx[LW];   // border column solution
+    double q[5][LW];           // j elimination: q_ce, q_pe, q_ps, q_T, inv_den
     double jcs[LW];
-    double sj[4][32];          // effective d(row)/dj for rows ce, pe, ps, T
-    double tcs[32];            // T-row coefficient of the surface concentration
-    double pd[NR][32];         // 1 / (kap_x * EL_i - cj)
-    double wT[NR][32];         // EVI * (d res_cs / dT)
-    double csj[32];
-    double chm[32], chip[32], chup[32], hm[32];   // collector chains: multiplier, 1/pivot, successor coupling; end-node multiplier
-    double gT[32], gX[32];     // dT control: border-row entries on this lane's T / collector T
+    double sj[4][LW];          // effective d(row)/dj for rows ce, pe, ps, T
+    double tcs[LW];            // T-row coefficient of the surface concentration
+    double pd[NR][LW];         // 1 / (kap_x * EL_i - cj)
+    double wT[NR][LW];         // EVI * (d res_cs / dT)
+    double csj[LW];
+    double chm[LW], chip[LW], chup[LW], hm[LW];   // collector chains: multiplier, 1/pivot, successor coupling; end-node multiplier
+    double gT[LW], gX[LW];     // dT control: border-row entries on this lane's T / collector T
     double schur_inv, g_ps0, g_psN;
     double mode;               // border row: 0 (Phi_s ends + I), 1 dT in the DAE, 2 dT inside newtons_method!
     double g_eta, pad3;        // eta_p control
@@ -1375,16 +1389,16 @@ __device__ __forceinline__ double border_dot(const ModelDesc& m, const WarpFacto
     if (mode == 1) g += warp_sum(Fa.gT[lane] * u4[3] + Fa.gX[lane] * ux);
     if (mode == 2) {
         double a = Fa.pd[0][lane] * dj;
-        a = fma(Fa.pd[1][lane], __shfl_up_sync(FULL, u4[1], 2), a);
-        a = fma(Fa.pd[2][lane], __shfl_up_sync(FULL, u4[1], 1), a);
+        a = fma(Fa.pd[1][lane], shfl_up2(u4[1]), a);
+        a = fma(Fa.pd[2][lane], shfl_up(u4[1]), a);
         a = fma(Fa.pd[3][lane], u4[1], a);
-        a = fma(Fa.pd[4][lane], __shfl_down_sync(FULL, u4[1], 1), a);
-        a = fma(Fa.pd[5][lane], __shfl_down_sync(FULL, u4[1], 2), a);
-        a = fma(Fa.pd[6][lane], __shfl_up_sync(FULL, u4[2], 2), a);
-        a = fma(Fa.pd[7][lane], __shfl_up_sync(FULL, u4[2], 1), a);
+        a = fma(Fa.pd[4][lane], shfl_dn(u4[1]), a);
+        a = fma(Fa.pd[5][lane], shfl_dn2(u4[1]), a);
+        a = fma(Fa.pd[6][lane], shfl_up2(u4[2]), a);
+        a = fma(Fa.pd[7][lane], shfl_up(u4[2]), a);
         a = fma(Fa.pd[8][lane], u4[2], a);
-        a = fma(Fa.pd[9][lane], __shfl_down_sync(FULL, u4[2], 1), a);
-        a = fma(Fa.wT[0][lane], __shfl_down_sync(FULL, u4[2], 2), a);
+        a = fma(Fa.pd[9][lane], shfl_dn(u4[2]), a);
+        a = fma(Fa.wT[0][lane], shfl_dn2(u4[2]), a);
         g += warp_sum(a);
     }
     return g;
@@ -1445,8 +1459,8 @@ __device__ __forceinline__ LaneChain make_chain(const ModelDesc& m, const LaneRo
     c.posA = m.Np - 1;
     c.posB = m.Nn - 1;
     c.ch = ro.cha || ro.chz;
-    c.cpred = ro.cha ? (lane > 0 ? lane - 1 : 0) : (lane < 31 ? lane + 1 : 31);
-    c.csucc = ro.cha ? (lane < 31 ? lane + 1 : 31) : (lane > 0 ? lane - 1 : 0);
+    c.cpred = ro.cha ? (lane > 0 ? lane - 1 : 0) : (lane < LW - 1 ? lane + 1 : LW - 1);
+    c.csucc = ro.cha ? (lane < LW - 1 ? lane + 1 : LW - 1) : (lane > 0 ? lane - 1 : 0);
     c.is_tail = (ro.cha && lane == m.Na - 1) || (ro.chz && lane == Nx - m.Nz);
     c.ctail = lane == 0 ? m.Na - 1 : Nx - m.Nz;
     c.nch = m.Na > m.Nz ? m.Na : m.Nz;
@@ -1749,7 +1763,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     for (int k = 0; k < 4; k++) Fa.Fr[k][lane] = Fr[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) Fa.Eo[k][lane] = Eout[k];
-    __syncwarp();
+    grp_sync();
     // ---- 5. border: z = core^{-1} (dF/dI column), then the Schur complement ------------------------
     const double zb[4] = {0.0, 0.0, J.ps_I, 0.0};
     double u4[4], ux;
@@ -1758,7 +1772,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     for (int k = 0; k < 4; k++) Fa.z[k][lane] = u4[k];
     Fa.zx[lane] = ux;
     const bool isdt = ctrl.gTn != 0.0 || ctrl.gTx != 0.0;     // same on every active lane
-    const int mode = __any_sync(FULL, isdt) ? (dyn ? 1 : 2) : 0;
+    const int mode = (grp_max(isdt ? 1.0 : 0.0) != 0.0) ? (dyn ? 1 : 2) : 0;
     Fa.gT[lane] = cj * ctrl.gTn; Fa.gX[lane] = cj * ctrl.gTx;
     if (mode == 2) {
         // d(control row)/d(algebraic unknowns) = sum_x gTn[x] * (T row of node x); the collector rows only see I
@@ -1770,12 +1784,12 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         Fa.wT[0][lane] = ctrl.gTn * J.T_ps[4];
     }
     if (lane == 0) { Fa.g_ps0 = ctrl.g_ps0; Fa.g_psN = ctrl.g_psN; Fa.mode = (double)mode; Fa.g_eta = ctrl.g_eta; }
-    __syncwarp();
+    grp_sync();
     // the border column has no entry in the j rows: dj of the column solution is q . z
     const double djz = ro.elec ? q[0] * u4[0] + q[1] * u4[1] + q[2] * u4[2] + q[3] * u4[3] : 0.0;
     const double gz = border_dot(m, Fa, mode, u4, ux, djz, lane);
     if (lane == 0) Fa.schur_inv = 1.0 / (ctrl.g_I - gz);
-    __syncwarp();
+    grp_sync();
 }
 
 // Solve J * d = g for one right-hand side held node-wise in registers (g in, d out, in place).

@@ -108,6 +108,9 @@ static const Variant V_WIDE = {wide::info, wide::slot_rc, wide::slot_recipe, wid
 static const Variant V_WSEI = {wsei::info, wsei::slot_rc, wsei::slot_recipe, wsei::launch_resjac, wsei::launch_initguess,
                                wsei::launch_newton, wsei::launch_linsolve, wsei::launch_simulate};
 
+static const Variant V_WTH = {wth::info, wth::slot_rc, wth::slot_recipe, wth::launch_resjac, wth::launch_initguess,
+                              wth::launch_newton, wth::launch_linsolve, wth::launch_simulate};
+
 struct plb_handle_s {
     plb_model_desc desc;
     ModelDesc m;
@@ -207,8 +210,6 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     const int Nx_ = d->N_p + d->N_s + d->N_n;
     if (d->N_p < 2 || d->N_s < 2 || d->N_n < 2 || Nx_ > 64)
         return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 64 (one lane per node, one or two warps per system)");
-    if (Nx_ > 32 && d->temperature)
-        return fail("plb_create: temperature=true on grids with more than 32 x-nodes is not built");
     if (d->cathode != PLB_CATHODE_LCO && d->cathode != PLB_CATHODE_NMC) return fail("plb_create: unknown cathode");
     if ((d->rxn_p != PLB_RXN_BV && d->rxn_p != PLB_RXN_MHC) || (d->rxn_n != PLB_RXN_BV && d->rxn_n != PLB_RXN_MHC))
         return fail("plb_create: unknown reaction rate law (built: rxn_BV, rxn_MHC)");
@@ -239,8 +240,9 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
     const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
-    const bool wide = Nx_ > 32 || (!d->temperature && Ntot_ > (d->aging ? V_SEI : V_ISO).info().vs);
-    h->v = d->temperature ? &V_TH : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
+    const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
+    const bool wide = Nx_ > 32 || NtotT_ > (d->temperature ? V_TH : (d->aging ? V_SEI : V_ISO)).info().vs;
+    h->v = d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
     h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
     ModelDesc& m = h->m;
@@ -309,7 +311,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
 }
 
 int plb_variant_info(int family, long long* out) {
-    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : iso::info())));
+    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : (family == 5 ? wth::info() : iso::info()))));
     out[0] = v.sim_warps; out[1] = v.sim_ctas; out[2] = (long long)v.sim_smem; out[3] = v.k1_warps;
     out[4] = v.k1_ctas; out[5] = (long long)v.k1_smem; out[6] = v.vs; out[7] = v.n_slots;
     return 0;

@@ -62,7 +62,7 @@ enum JacSlot {
 #endif
 constexpr int K1_WARPS = PLB_K1_WARPS;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
-constexpr int K1_SRC_MAX = WIDE ? 4864 : (TH ? 3072 : 2304);        // >= nnz of every built variant
+constexpr int K1_SRC_MAX = WIDE ? (TH ? 6656 : 4864) : (TH ? 3072 : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 // pitch of the value table: one double of padding per slot row.  Consecutive CSC entries of a column come from
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
                 // element of the KAP row (fma(1, t, -0) == t), particle entries at their node's D_s(T)/Rp^2
                 const int rc = src_s[p];
                 const double t = tab[rc & 0xffff];
-                const double kap = tab[JS_KAP * K1_PITCH + ((rc >> 19) & 63)];
+                const double kap = tab[JS_KAP * K1_PITCH + ((rc >> 19) & 127)];
                 const double gd = (rc & (1 << 18)) ? g : 0.0;
                 gN[p] = fma(kap, t, -gd);
             }
@@ -658,7 +658,7 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 #define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? 5 : (PLB_SEI ? 6 : 8)))
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS (PLB_WIDE ? 3 : 1)
+#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? 2 : 3) : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;

@@ -1,5 +1,6 @@
 """GPU parity tests of the wide families: grids with 33..64 x-nodes, two warps per system.
-BASELINE.json configs[4]: LCO, aging = :SEI, N = (20,20,20) -> 642 DAEs; and the same grid without aging (601)."""
+BASELINE.json configs[4]: LCO, aging = :SEI, N = (20,20,20) -> 642 DAEs; the same grid without aging (601); and with
+temperature = true (681: N_a = N_z = 10)."""
 import numpy as np
 import pytest
 
@@ -17,18 +18,19 @@ def P():
     return petlion_b200
 
 
-@pytest.fixture(scope="module", params=["plain", "sei"])
+@pytest.fixture(scope="module", params=["plain", "sei", "thermal"])
 def fam(request, P):
     aging = request.param == "sei"
-    p = P.petlion("LCO", aging="SEI" if aging else False, **GRID)
-    m = O.make_model("LCO", aging=aging, **GRID)
+    thermal = request.param == "thermal"
+    p = P.petlion("LCO", aging="SEI" if aging else False, temperature=thermal, **GRID)
+    m = O.make_model("LCO", aging=aging, temperature=thermal, **GRID)
     return p, m, aging
 
 
 def test_sizes_and_pattern(fam):
     p, m, aging = fam
     L = O.layout(m)
-    assert p.N.tot == L.N_tot == (642 if aging else 601)
+    assert p.N.tot == L.N_tot == (642 if aging else (681 if m.temperature else 601))
     assert p.N.diff == L.N_diff
     for method in ("I", "V", "P"):
         cp, rv = O.jac_pattern(m, method)
@@ -130,14 +132,51 @@ def test_simulate_parity(P, fam):
         sol = P.simulate(p, I=cur, SOC=soc0, V_max=4.2)
         ref = O.simulate_batch(m, tho, O.make_run("I", cur), O.default_opts(), b, SOC0=soc0, n_save_max=512, nthreads=8)
         s = sol.results[-1].summary
-        same = (s["n_steps"] == ref["n_steps"]) & (s["flag"] == ref["flag"])
+        same = np.ones(B, dtype=bool)          # the same decisions: every counter agrees
+        for c in ("flag", "n_steps", "n_res", "n_jac", "n_netf", "n_ncfn"):
+            same &= s[c] == ref[c]
         print("wide", aging, cur, "identical", float(np.mean(same)), s["n_steps"][:6], ref["n_steps"][:6], s["flag"][:6], ref["flag"][:6])
-        assert np.mean(same) >= 0.8
-        np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=1e-6)
+        assert np.mean(same) >= 0.75
+        np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=5e-6 if m.temperature else 1e-6)
+        np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=5e-3)        # the others: same answer at the integrator's tolerance
         np.testing.assert_allclose(s["t_end"][same], ref["t_end"][same], rtol=1e-5)
         for k in np.where(same)[0]:
             n = ref["traj_n"][k]
-            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=1e-6)
+            # (thermal: the conduction rows carry ~1e-5 K/s of cancellation noise -- tests/test_gpu_thermal.py -- which the
+            #  Newton iterations pass on to V at the 1e-6 level even when both sides take the same decisions)
+            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=5e-6 if m.temperature else 1e-6)
         if aging and cur > 0:
             L = O.layout(m)
             np.testing.assert_allclose(s["aux_end"][same], ref["state"]["Y"][same][:, L.SOH], rtol=1e-9)
+        if m.temperature:
+            np.testing.assert_allclose(s["T_end"][same], ref["T_end"][same], rtol=1e-8)
+            assert np.all(s["T_end"] > 298.2)
+
+
+def test_wide_thermal_protocol_on_a_ragged_grid(P):
+    """temperature = true on 36 x-nodes with unequal sections and collectors: 2C charge -> dT = :hold -> V = :hold
+    (the README's CC-CT-CV shape), every segment against the oracle"""
+    grid = dict(N_p=12, N_s=8, N_n=16, N_a=7, N_z=9)
+    p = P.petlion("LCO", temperature=True, **grid)
+    m = O.make_model("LCO", temperature=True, **grid)
+    assert p.N.tot == O.layout(m).N_tot == 2 * 36 + 12 * 28 + 1 + 36 + 16
+    B = 8
+    tho = util.oracle_theta_batch(B, first=300)
+    util.set_theta_batch(p, util.product_theta_from_oracle(p, tho))
+    segs = [("I", "value", 3.0, 400.0, {}), ("dT", "hold", 0.0, 300.0, {}), ("V", "hold", 0.0, 300.0, {})]
+    W = dict(cathode="LCO", temperature=True, grid=grid, soc0=0.1, segs=segs)
+    ref = util.oracle_protocol(W, tho, O.default_opts())
+    sol, _ = util.gpu_protocol(P, p, W)
+    for k in range(3):
+        s, r = sol.results[k].summary, ref[k]
+        same = np.ones(B, dtype=bool)
+        for c in ("flag", "n_steps", "n_res", "n_jac", "n_netf", "n_ncfn"):
+            same &= s[c] == r[c]
+        print("segment", k, "identical", same.mean(), s["n_steps"], r["n_steps"])
+        assert same.mean() >= 0.6 and (s["flag"] >= 0).all()
+        np.testing.assert_allclose(s["V_end"][same], r["V_end"][same], rtol=1e-6)
+        np.testing.assert_allclose(s["T_end"][same], r["T_end"][same], rtol=1e-7)
+        np.testing.assert_allclose(s["I_end"][same], r["I_end"][same], rtol=1e-5, atol=1e-8)
+        # decision flips: still the same answer at the integrator's tolerance
+        np.testing.assert_allclose(s["V_end"], r["V_end"], rtol=5e-3)
+        np.testing.assert_allclose(s["T_end"], r["T_end"], rtol=5e-3)

@@ -47,7 +47,6 @@ def test_table_host_semantics_match_the_oracle_table():
     (dict(N_r_p=12), "N_r_p = N_r_n = 10"),
     (dict(N_p=30, N_s=10, N_n=30), "<= 64"),
     (dict(N_p=1), "2 <= N_p"),
-    (dict(temperature=True, N_p=20, N_s=10, N_n=20), "more than 32 x-nodes"),
     (dict(temperature=True, N_p=4), "N_p, N_n >= 5"),
     (dict(temperature=True, N_a=20, N_z=20), "N_a\\+N_z <="),
 ])
