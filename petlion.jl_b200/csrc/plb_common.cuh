@@ -171,5 +171,6 @@ PLB_DECLARE_VARIANT(sei)
 PLB_DECLARE_VARIANT(wide)
 PLB_DECLARE_VARIANT(wsei)
 PLB_DECLARE_VARIANT(wth)
+PLB_DECLARE_VARIANT(thsei)
 
 }  // namespace plb

@@ -31,8 +31,8 @@ namespace PLB_NS {
 #ifndef PLB_SEI
 #define PLB_SEI 0
 #endif
-#if PLB_TH && PLB_SEI
-#error "temperature = true together with aging = :SEI is not built"
+#if PLB_TH && PLB_SEI && PLB_WIDE
+#error "temperature = true together with aging = :SEI is built for grids of up to 32 x-nodes only"
 #endif
 #ifndef PLB_WIDE
 #define PLB_WIDE 0
@@ -497,6 +497,11 @@ struct LaneJac {
     // this lane's current-collector node: tridiagonal (Tx_D without -cj) and d/dI
     double Tx_L, Tx_D, Tx_U, Tx_I;
 #endif
+#if PLB_TH && PLB_SEI
+    // both: the side-reaction rate feels T (its Tafel exponent); the heat source F a j_total (T dU/dT + eta) feels j_s
+    // like j, and j / film once more through the film-resistance term of eta
+    double js_T, T_js, T_film;
+#endif
 };
 
 // Control row (scalar_residual.jl:167-202): residual and its three possible Jacobian entries
@@ -756,11 +761,11 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
 #if PLB_SEI
     // ---- aging = :SEI: residuals_j_s! (residuals.jl:519-552), residuals_film! (:260-276), residuals_SOH! (:278-297)
     {
-        double jsc = 0.0, Dn = 0.0;
+        double jsc = 0.0, Dn = 0.0, eta_s = 0.0, xs = 0.0;
         const bool charging = Iapp * C.g[GC_I1C] > 0.0;                   // I_density > 0, :546
         if (sei_n && charging) {
-            const double eta_s = y.ps - y.pe - C.g[GC_Uref] - kF * jtot * Rfilm;
-            const double xs = 0.5 * kF / (kR * T);
+            eta_s = y.ps - y.pe - C.g[GC_Uref] - kF * jtot * Rfilm;
+            xs = 0.5 * kF / (kR * T);
             const double Ir = Iapp * C.g[GC_I1C] / C.g[GC_I1C];
             jsc = -fabs(C.g[GC_i0F] * pow(Ir, C.g[GC_w]) * (-exp(-xs * eta_s)));
             Dn = -xs * jsc;                                               // d j_s_calc / d eta_s
@@ -777,6 +782,9 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
             J.film_js = sei_n ? -C.g[GC_Mrho] : 0.0;
             J.soh_js = sei_n ? C.cSOH[ro.x] : 0.0;
             if (!ro.elec) { J.j_j = -1.0; J.j_film = 0.0; }
+#if PLB_TH
+            J.js_T = -jsc * eta_s * xs / T;                               // -(d j_s_calc / dT): the 1/T of the exponent
+#endif
         }
     }
 #endif
@@ -834,6 +842,11 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
             J.T_TL = tL; J.T_TU = tR;
             J.T_TD = -(tL + tR) + irc * (dKT * dPe * dPe + Kc * dPe * (dCe * ice) * (dKT * T + K));
             J.T_j = ro.elec ? irc * Fa * (T * dUdT_h + eta_h) : 0.0;
+#if PLB_SEI
+            J.T_js = sei_n ? J.T_j : 0.0;
+            J.T_film = sei_n ? -irc * Fa * jtot * kF * y.j * C.g[GC_ikag] : 0.0;      // through eta's film-resistance term
+            if (sei_n) J.T_j -= irc * Fa * jtot * kF * Rfilm;
+#endif
             J.T_cs = ro.elec ? irc * Fa * jtot * (T * ddUdT_h - dUtot_h) * C.sec[SC_inv_cmax][s] : 0.0;
             const double gpe = irc * (2.0 * K * dPe + Kc * K * T * dCe * ice);
             const double gce = irc * Kc * K * T * dPe * ice;
@@ -918,6 +931,24 @@ __device__ __noinline__ void lane_eval_ni(const ModelDesc& m, const WarpConst& C
     lane_eval<CHEM, WITH_JAC>(m, C, ro, y, yp, Iapp, method, value, res, ctrl, J);
 }
 
+// 3x3 inverse by the adjugate (forward error ~ cond * eps, invariant under row/column scaling)
+__device__ __forceinline__ void inv3x3(const double* a, double* o) {
+    const double c00 = a[4] * a[8] - a[5] * a[7];
+    const double c01 = a[5] * a[6] - a[3] * a[8];
+    const double c02 = a[3] * a[7] - a[4] * a[6];
+    const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    const double id = 1.0 / det;
+    o[0] = c00 * id;
+    o[3] = c01 * id;
+    o[6] = c02 * id;
+    o[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+    o[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+    o[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+    o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
 #if !PLB_TH
 // ------------------------------------------------------------------------------------------------
 // structured Newton-matrix factorisation / solve
@@ -952,24 +983,6 @@ struct WarpFactor {
     double ionly;              // != 0: the control row has only its I entry (current control): z holds the RAW border
                                // column and dI is folded into the right-hand side before the sweeps (no border solve)
 };
-
-// 3x3 inverse by the adjugate (forward error ~ cond * eps, invariant under row/column scaling)
-__device__ __forceinline__ void inv3x3(const double* a, double* o) {
-    const double c00 = a[4] * a[8] - a[5] * a[7];
-    const double c01 = a[5] * a[6] - a[3] * a[8];
-    const double c02 = a[3] * a[7] - a[4] * a[6];
-    const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
-    const double id = 1.0 / det;
-    o[0] = c00 * id;
-    o[3] = c01 * id;
-    o[6] = c02 * id;
-    o[1] = (a[2] * a[7] - a[1] * a[8]) * id;
-    o[4] = (a[0] * a[8] - a[2] * a[6]) * id;
-    o[7] = (a[1] * a[6] - a[0] * a[7]) * id;
-    o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
-    o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
-    o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
-}
 
 // Block-Thomas as a "twisted" (two-sided) elimination: nodes 0..mid-1 are eliminated left-to-right,
 // nodes Nx-1..mid+1 right-to-left, both chains meet at node `mid`, and the back-substitution runs
@@ -1372,6 +1385,15 @@ struct WarpFactor {
     double csj[LW];
     double chm[LW], chip[LW], chup[LW], hm[LW];   // collector chains: multiplier, 1/pivot, successor coupling; end-node multiplier
     double gT[LW], gX[LW];     // dT control: border-row entries on this lane's T / collector T
+#if PLB_SEI
+    // aging = :SEI: (j, j_s, film) are eliminated together node-locally (cathode / separator lanes: identity rows).
+    //   M l + Cl u + cI dI = v   ->   l = Mi v + Ql u + QI dI,  Ql = -Mi Cl (3x4), QI = -Mi cI
+    //   reduced rows (c_e, Phi_e, Phi_s, T):  D += Sj Ql,  r -= SM v (SM = Sj Mi, 4x3),  border column += Sj QI
+    double Mi[9][LW], Ql[12][LW], QI[3][LW], SM[12][LW];
+    double sohc[LW];           // d(rhs_SOH)/dj_s
+    double pdjs[LW];           // dT control inside newtons_method!: border-row coefficient of dj_s
+    double cjv, pad4;
+#endif
     double schur_inv, g_ps0, g_psN;
     double mode;               // border row: 0 (Phi_s ends + I), 1 dT in the DAE, 2 dT inside newtons_method!
     double g_eta, pad3;        // eta_p control
@@ -1382,13 +1404,18 @@ struct WarpFactor {
 // are parked in Fa.pd[0..9] / Fa.wT[0] (the particle data is not used in that mode):
 //   pd[0]: j ; pd[1..5]: Phi_e at x-2..x+2 ; pd[6..9], wT[0]: Phi_s at x-2..x+2
 __device__ __forceinline__ double border_dot(const ModelDesc& m, const WarpFactor& Fa, int mode, const double* u4,
-                                             double ux, double dj, int lane) {
+                                             double ux, double dj, double djs, int lane) {
     const double x0 = shfl_from(u4[2], 0), xN = shfl_from(u4[2], m.Nx - 1);
     double g = Fa.g_ps0 * x0 + Fa.g_psN * xN;
     if (Fa.g_eta != 0.0) g += Fa.g_eta * shfl_from(u4[2] - u4[1], m.Np + m.Ns);
     if (mode == 1) g += warp_sum(Fa.gT[lane] * u4[3] + Fa.gX[lane] * ux);
     if (mode == 2) {
         double a = Fa.pd[0][lane] * dj;
+#if PLB_SEI
+        a = fma(Fa.pdjs[lane], djs, a);
+#else
+        (void)djs;
+#endif
         a = fma(Fa.pd[1][lane], shfl_up2(u4[1]), a);
         a = fma(Fa.pd[2][lane], shfl_up(u4[1]), a);
         a = fma(Fa.pd[3][lane], u4[1], a);
@@ -1568,7 +1595,46 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         beta *= J.cs_j;
     }
     Fa.csj[lane] = J.cs_j;
-    // ---- 2. node-local elimination of c_s and j -------------------------------------------------
+    // ---- 2. node-local elimination of c_s and j (and j_s, film) ----------------------------------
+#if PLB_SEI
+    const bool sn = ro.sec == 2;
+    double Ql[12], QIv[3], Sj[12];
+    {
+        double M3[9], Mi[9];
+        M3[0] = ro.elec ? J.j_j - J.j_cs * beta : -1.0; M3[1] = 0.0; M3[2] = (sn && dyn) ? J.j_film : 0.0;
+        M3[3] = sn ? J.js_j : 0.0; M3[4] = sn ? J.js_js : 1.0; M3[5] = (sn && dyn) ? J.js_film : 0.0;
+        M3[6] = 0.0; M3[7] = (sn && dyn) ? J.film_js : 0.0; M3[8] = (sn && dyn) ? -cj : 1.0;
+        inv3x3(M3, Mi);
+        const double Cl[12] = {(ro.elec && dyn) ? J.j_ce : 0.0, ro.elec ? J.j_pe : 0.0, ro.elec ? J.j_ps : 0.0,
+                               (ro.elec && dyn) ? J.j_T - J.j_cs * tau : 0.0,
+                               0.0, sn ? J.js_pe : 0.0, sn ? J.js_ps : 0.0, (sn && dyn) ? J.js_T : 0.0,
+                               0.0, 0.0, 0.0, 0.0};
+        const double cI[3] = {0.0, sn ? J.js_I : 0.0, 0.0};
+        const double Sjv[12] = {(ro.elec && dyn) ? J.ce_j : 0.0, (sn && dyn) ? J.ce_j : 0.0, 0.0,
+                                ro.elec ? J.pe_j : 0.0, sn ? J.pe_j : 0.0, 0.0,
+                                ro.elec ? J.ps_j : 0.0, sn ? J.ps_j : 0.0, 0.0,
+                                (ro.elec && dyn) ? J.T_j - J.T_cs * beta : 0.0, (sn && dyn) ? J.T_js : 0.0, (sn && dyn) ? J.T_film : 0.0};
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) Ql[r * 4 + c] = -(Mi[r * 3 + 0] * Cl[c] + Mi[r * 3 + 1] * Cl[4 + c] + Mi[r * 3 + 2] * Cl[8 + c]);
+            QIv[r] = -(Mi[r * 3 + 0] * cI[0] + Mi[r * 3 + 1] * cI[1] + Mi[r * 3 + 2] * cI[2]);
+        }
+#pragma unroll
+        for (int k = 0; k < 12; k++) { Sj[k] = Sjv[k]; Fa.Ql[k][lane] = Ql[k]; }
+#pragma unroll
+        for (int k = 0; k < 9; k++) Fa.Mi[k][lane] = Mi[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) Fa.QI[k][lane] = QIv[k];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                Fa.SM[r * 3 + c][lane] = Sj[r * 3 + 0] * Mi[c] + Sj[r * 3 + 1] * Mi[3 + c] + Sj[r * 3 + 2] * Mi[6 + c];
+        Fa.sohc[lane] = (sn && dyn) ? J.soh_js : 0.0;
+        if (lane == 0) Fa.cjv = dyn ? cj : 0.0;
+    }
+#else
     double q[4] = {0.0, 0.0, 0.0, 0.0}, inv_den = 0.0;
     if (ro.elec) {
         inv_den = 1.0 / (-1.0 - J.j_cs * beta);
@@ -1581,6 +1647,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
     for (int k = 0; k < 4; k++) { Fa.q[k][lane] = q[k]; Fa.sj[k][lane] = sj[k]; }
     Fa.q[4][lane] = inv_den;
+#endif
     Fa.jcs[lane] = J.j_cs;
     Fa.tcs[lane] = dyn ? J.T_cs : 0.0;
     double Dm[16];
@@ -1592,7 +1659,13 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) Dm[r * 4 + c] = fma(sj[r], q[c], Dm[r * 4 + c]);
+        for (int c = 0; c < 4; c++) {
+#if PLB_SEI
+            Dm[r * 4 + c] += Sj[r * 3 + 0] * Ql[c] + Sj[r * 3 + 1] * Ql[4 + c] + Sj[r * 3 + 2] * Ql[8 + c];
+#else
+            Dm[r * 4 + c] = fma(sj[r], q[c], Dm[r * 4 + c]);
+#endif
+        }
     if (!ro.act) {
 #pragma unroll
         for (int k = 0; k < 16; k++) Dm[k] = (k % 5 == 0) ? 1.0 : 0.0;
@@ -1765,7 +1838,13 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     for (int k = 0; k < 3; k++) Fa.Eo[k][lane] = Eout[k];
     grp_sync();
     // ---- 5. border: z = core^{-1} (dF/dI column), then the Schur complement ------------------------
+#if PLB_SEI
+    // the side-reaction rows depend on I (rate law ~ I^w): their column entry, eliminated node-locally
+    const double zb[4] = {Sj[0] * QIv[0] + Sj[1] * QIv[1] + Sj[2] * QIv[2], Sj[3] * QIv[0] + Sj[4] * QIv[1] + Sj[5] * QIv[2],
+                          J.ps_I + Sj[6] * QIv[0] + Sj[7] * QIv[1] + Sj[8] * QIv[2], Sj[9] * QIv[0] + Sj[10] * QIv[1] + Sj[11] * QIv[2]};
+#else
     const double zb[4] = {0.0, 0.0, J.ps_I, 0.0};
+#endif
     double u4[4], ux;
     core_solve(m, ch, Fa, Di, Wm, Pm, zb, (ch.ch && dyn) ? J.Tx_I : 0.0, u4, ux, lane);
 #pragma unroll
@@ -1782,12 +1861,22 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
         for (int k = 0; k < 4; k++) Fa.pd[6 + k][lane] = ctrl.gTn * J.T_ps[k];
         Fa.wT[0][lane] = ctrl.gTn * J.T_ps[4];
+#if PLB_SEI
+        Fa.pdjs[lane] = ctrl.gTn * J.T_js;
+#endif
     }
     if (lane == 0) { Fa.g_ps0 = ctrl.g_ps0; Fa.g_psN = ctrl.g_psN; Fa.mode = (double)mode; Fa.g_eta = ctrl.g_eta; }
     grp_sync();
+#if PLB_SEI
+    // column solution of the local unknowns: l_z = Mi (cI - Cl u_z) = Ql u_z - QI
+    const double djz = Ql[0] * u4[0] + Ql[1] * u4[1] + Ql[2] * u4[2] + Ql[3] * u4[3] - QIv[0];
+    const double djsz = Ql[4] * u4[0] + Ql[5] * u4[1] + Ql[6] * u4[2] + Ql[7] * u4[3] - QIv[1];
+#else
     // the border column has no entry in the j rows: dj of the column solution is q . z
     const double djz = ro.elec ? q[0] * u4[0] + q[1] * u4[1] + q[2] * u4[2] + q[3] * u4[3] : 0.0;
-    const double gz = border_dot(m, Fa, mode, u4, ux, djz, lane);
+    const double djsz = 0.0;
+#endif
+    const double gz = border_dot(m, Fa, mode, u4, ux, djz, djsz, lane);
     if (lane == 0) Fa.schur_inv = 1.0 / (ctrl.g_I - gz);
     grp_sync();
 }
@@ -1812,12 +1901,24 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 #pragma unroll
         for (int i = 0; i < NR; i++) g.cs[i] = w0[i];
     }
-    const double q0 = ro.elec ? (g.j - Fa.jcs[lane] * s9) * Fa.q[4][lane] : 0.0;
     double rb[4];
+#if PLB_SEI
+    const bool sn = ro.sec == 2;
+    const double v0 = ro.elec ? g.j - Fa.jcs[lane] * s9 : 0.0, v1 = sn ? g.js : 0.0, v2 = (sn && dyn) ? g.film : 0.0;
+    double l0[3];     // Mi v
+#pragma unroll
+    for (int r = 0; r < 3; r++) l0[r] = Fa.Mi[r * 3 + 0][lane] * v0 + Fa.Mi[r * 3 + 1][lane] * v1 + Fa.Mi[r * 3 + 2][lane] * v2;
+    rb[0] = dyn ? g.ce - (Fa.SM[0][lane] * v0 + Fa.SM[1][lane] * v1 + Fa.SM[2][lane] * v2) : 0.0;
+    rb[1] = g.pe - (Fa.SM[3][lane] * v0 + Fa.SM[4][lane] * v1 + Fa.SM[5][lane] * v2);
+    rb[2] = (ro.elec ? g.ps : 0.0) - (Fa.SM[6][lane] * v0 + Fa.SM[7][lane] * v1 + Fa.SM[8][lane] * v2);
+    rb[3] = dyn ? g.T - (Fa.SM[9][lane] * v0 + Fa.SM[10][lane] * v1 + Fa.SM[11][lane] * v2) - Fa.tcs[lane] * s9 : 0.0;
+#else
+    const double q0 = ro.elec ? (g.j - Fa.jcs[lane] * s9) * Fa.q[4][lane] : 0.0;
     rb[0] = dyn ? g.ce - Fa.sj[0][lane] * q0 : 0.0;
     rb[1] = g.pe - Fa.sj[1][lane] * q0;
     rb[2] = (ro.elec ? g.ps : 0.0) - Fa.sj[2][lane] * q0;
     rb[3] = dyn ? g.T - Fa.sj[3][lane] * q0 - Fa.tcs[lane] * s9 : 0.0;
+#endif
     if (!ro.act) { rb[0] = rb[1] = rb[2] = rb[3] = 0.0; }
     double Di[16], Wm[16], Pm[16];
 #pragma unroll
@@ -1826,13 +1927,34 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     core_solve(m, ch, Fa, Di, Wm, Pm, rb, (ch.ch && dyn) ? g.Tx : 0.0, u4, ux, lane);
     // border
     const int mode = (int)Fa.mode;
+#if PLB_SEI
+    const double dj0 = l0[0] + Fa.Ql[0][lane] * u4[0] + Fa.Ql[1][lane] * u4[1] + Fa.Ql[2][lane] * u4[2] + Fa.Ql[3][lane] * u4[3];
+    const double djs0 = l0[1] + Fa.Ql[4][lane] * u4[0] + Fa.Ql[5][lane] * u4[1] + Fa.Ql[6][lane] * u4[2] + Fa.Ql[7][lane] * u4[3];
+#else
     const double dj0 = ro.elec ? q0 + Fa.q[0][lane] * u4[0] + Fa.q[1][lane] * u4[1] + Fa.q[2][lane] * u4[2] + Fa.q[3][lane] * u4[3] : 0.0;
-    const double dI = (gI - border_dot(m, Fa, mode, u4, ux, dj0, lane)) * Fa.schur_inv;
+    const double djs0 = 0.0;
+#endif
+    const double dI = (gI - border_dot(m, Fa, mode, u4, ux, dj0, djs0, lane)) * Fa.schur_inv;
 #pragma unroll
     for (int k = 0; k < 4; k++) u4[k] -= Fa.z[k][lane] * dI;
     ux -= Fa.zx[lane] * dI;
-    // back-substitute j and the particle
+    // back-substitute j (j_s, film) and the particle
+#if PLB_SEI
+    double lf[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        lf[r] = l0[r] + Fa.Ql[r * 4 + 0][lane] * u4[0] + Fa.Ql[r * 4 + 1][lane] * u4[1] + Fa.Ql[r * 4 + 2][lane] * u4[2] +
+                Fa.Ql[r * 4 + 3][lane] * u4[3] + Fa.QI[r][lane] * dI;
+    const double dj = ro.elec ? lf[0] : 0.0;
+    const double djs = sn ? lf[1] : 0.0;
+    // SOH: its column only holds -cj on the diagonal; its row is dense over j_s (residuals.jl:278-297)
+    const double sj_sum = warp_sum(Fa.sohc[lane] * djs);
+    g.soh = dyn ? (g.soh - sj_sum) / (-Fa.cjv) : 0.0;
+    g.js = djs;
+    g.film = (sn && dyn) ? lf[2] : 0.0;
+#else
     const double dj = ro.elec ? q0 + Fa.q[0][lane] * u4[0] + Fa.q[1][lane] * u4[1] + Fa.q[2][lane] * u4[2] + Fa.q[3][lane] * u4[3] : 0.0;
+#endif
     if (dyn) {
         double v[NR];
         const double bj = Fa.csj[lane] * dj;

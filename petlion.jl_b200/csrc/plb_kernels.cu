@@ -111,6 +111,9 @@ static const Variant V_WSEI = {wsei::info, wsei::slot_rc, wsei::slot_recipe, wse
 static const Variant V_WTH = {wth::info, wth::slot_rc, wth::slot_recipe, wth::launch_resjac, wth::launch_initguess,
                               wth::launch_newton, wth::launch_linsolve, wth::launch_simulate};
 
+static const Variant V_THSEI = {thsei::info, thsei::slot_rc, thsei::slot_recipe, thsei::launch_resjac, thsei::launch_initguess,
+                                thsei::launch_newton, thsei::launch_linsolve, thsei::launch_simulate};
+
 struct plb_handle_s {
     plb_model_desc desc;
     ModelDesc m;
@@ -204,7 +207,6 @@ static int build_patterns(plb_handle_s* h) {
 
 int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (!d || !out) return fail("plb_create: null argument");
-    if (d->aging && d->temperature) return fail("plb_create: aging=:SEI together with temperature=true is not built yet");
     if (d->aging && d->cathode != PLB_CATHODE_LCO) return fail("plb_create: aging=:SEI needs the LCO parameter set");
     if (d->N_r_p != NR_HOST || d->N_r_n != NR_HOST) return fail("plb_create: only N_r_p = N_r_n = 10 is built");
     const int Nx_ = d->N_p + d->N_s + d->N_n;
@@ -223,6 +225,13 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
         if (d->N_a < 1 || d->N_z < 1 || d->N_a + d->N_z > d->N_p + d->N_s + d->N_n)
             return fail("plb_create: temperature=true needs 1 <= N_a, N_z and N_a+N_z <= N_p+N_s+N_n (one collector node per lane)");
     }
+    // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
+    const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
+    const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
+    const bool both = d->temperature && d->aging;
+    const bool wide = Nx_ > 32 || NtotT_ > (both ? V_THSEI : (d->temperature ? V_TH : (d->aging ? V_SEI : V_ISO))).info().vs;
+    if (both && wide)
+        return fail("plb_create: aging=:SEI together with temperature=true is built for grids of up to 32 x-nodes (and N <= 384) only");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plb_create: no CUDA device available (this library has no CPU fallback)");
@@ -239,10 +248,8 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     } while (0)
     // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
-    const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
-    const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
-    const bool wide = Nx_ > 32 || NtotT_ > (d->temperature ? V_TH : (d->aging ? V_SEI : V_ISO)).info().vs;
-    h->v = d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO));
+    h->v = both ? &V_THSEI
+                : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
     h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
     ModelDesc& m = h->m;
@@ -311,7 +318,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
 }
 
 int plb_variant_info(int family, long long* out) {
-    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : (family == 5 ? wth::info() : iso::info()))));
+    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : (family == 5 ? wth::info() : (family == 6 ? thsei::info() : iso::info())))));
     out[0] = v.sim_warps; out[1] = v.sim_ctas; out[2] = (long long)v.sim_smem; out[3] = v.k1_warps;
     out[4] = v.k1_ctas; out[5] = (long long)v.k1_smem; out[6] = v.vs; out[7] = v.n_slots;
     return 0;

@@ -507,7 +507,7 @@ __device__ PLB_COLD void finish(const SimArgs& a, WarpWS& w, SimState& S, bool i
             if (i == m.off_SOH) aux = yf;
 #endif
 #if PLB_TH
-            if (i >= m.off_T && i < m.off_j) {   // temperature_weighting of the final state
+            if (i >= m.off_T && i < m.off_film) {   // temperature_weighting of the final state (film | SOH follow the T block)
                 const int k = i - m.off_T, x = k - m.Na;
                 const int q = k < m.Na ? 0 : (x < m.Np ? 1 : (x < m.Np + m.Ns ? 2 : (x < m.Nx ? 3 : 4)));
                 Tw = fma(yf, w.C.s5[0][q], Tw);

@@ -37,6 +37,9 @@ enum JacSlot {
     JS_T_CE0,                                       // 5 slots each: nodes x-2 .. x+2
     JS_T_PE0 = JS_T_CE0 + 5, JS_T_PS0 = JS_T_PE0 + 5,
     JS_TX_L = JS_T_PS0 + 5, JS_TX_D, JS_TX_U, JS_TX_I,
+#if PLB_SEI
+    JS_JS_T, JS_T_JS, JS_T_FILM,                    // temperature = true with aging = :SEI
+#endif
     JS_KAP,                                         // staging only: D_s(T_x)/Rp^2 of the node
     JS_CS0,
 #else
@@ -62,7 +65,7 @@ enum JacSlot {
 #endif
 constexpr int K1_WARPS = PLB_K1_WARPS;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
-constexpr int K1_SRC_MAX = WIDE ? (TH ? 6656 : 4864) : (TH ? 3072 : 2304);        // >= nnz of every built variant
+constexpr int K1_SRC_MAX = WIDE ? (TH ? 6656 : 4864) : (TH ? (SEI ? 3328 : 3072) : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 // pitch of the value table: one double of padding per slot row.  Consecutive CSC entries of a column come from
@@ -201,6 +204,9 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
                 w.S[JS_T_CE0 + k][lane] = J.T_ce[k]; w.S[JS_T_PE0 + k][lane] = J.T_pe[k]; w.S[JS_T_PS0 + k][lane] = J.T_ps[k];
             }
             w.S[JS_TX_L][lane] = J.Tx_L; w.S[JS_TX_D][lane] = J.Tx_D - g; w.S[JS_TX_U][lane] = J.Tx_U; w.S[JS_TX_I][lane] = J.Tx_I;
+#if PLB_SEI
+            w.S[JS_JS_T][lane] = J.js_T; w.S[JS_T_JS][lane] = J.T_js; w.S[JS_T_FILM][lane] = J.T_film;
+#endif
             w.S[JS_KAP][lane] = J.kap;
             if (lane == 0) w.S[JS_KAP][LW] = 1.0;
 #endif
@@ -599,6 +605,11 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         case JS_TX_D: row = rX; col = rX; return cha || chz;
         case JS_TX_U: row = rX; col = rX + 1; return cha || (chz && kx < m.Nz - 1);
         case JS_TX_I: row = rX; col = I; return cha || chz;
+#if PLB_SEI
+        case JS_JS_T: row = m.off_js + x - (Np + Ns); col = rT; return isn;
+        case JS_T_JS: row = rT; col = m.off_js + x - (Np + Ns); return isn;
+        case JS_T_FILM: row = rT; col = m.off_film + x - (Np + Ns); return isn;
+#endif
         case JS_CTRL_T: row = I; col = rT; return method == METHOD_DT;
         case JS_CTRL_TX: row = I; col = rX; return method == METHOD_DT && (cha || chz);
         default: break;
@@ -655,7 +666,7 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // systems of a CTA on one instruction stream; with only that barrier left, one large CTA per SM is best for the
 // 32-lane families (measured, iso, sims/s on one B200: 6x1 229 k, 3x2 213 k, 2x3 200 k).
 // (round 2: six vectors per system in shared memory instead of ten: 8 / 6 / 5 systems per SM instead of 6 / 5 / 4)
-#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? 5 : (PLB_SEI ? 6 : 8)))
+#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 5) : (PLB_SEI ? 6 : 8)))
 #endif
 #ifndef PLB_SIM_CTAS
 #define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? 2 : 3) : 1)
@@ -669,6 +680,7 @@ constexpr int SIM_CTAS = PLB_SIM_CTAS;
 constexpr size_t STATE_BYTES = PLB_STATE_SMEM ? 480 : 0;           // per physical warp
 constexpr size_t STATE_OFFSET = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
 constexpr size_t SIM_SMEM = STATE_OFFSET + STATE_BYTES * SIM_WARPS * (LW / 32);
+static_assert(SIM_SMEM <= 227 * 1024, "the integrator's shared memory exceeds one SM: lower PLB_SIM_WARPS for this family");
 
 __device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw + XCH_BYTES_PER_GROUP * SIM_WARPS)[warp];

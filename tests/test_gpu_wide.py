@@ -149,7 +149,7 @@ def test_simulate_parity(P, fam):
             L = O.layout(m)
             np.testing.assert_allclose(s["aux_end"][same], ref["state"]["Y"][same][:, L.SOH], rtol=1e-9)
         if m.temperature:
-            np.testing.assert_allclose(s["T_end"][same], ref["T_end"][same], rtol=1e-8)
+            np.testing.assert_allclose(s["T_end"][same], ref["T_end"][same], rtol=1e-6)      # 0.3 mK (conduction-row noise, see above)
             assert np.all(s["T_end"] > 298.2)
 
 
