@@ -172,5 +172,6 @@ PLB_DECLARE_VARIANT(wide)
 PLB_DECLARE_VARIANT(wsei)
 PLB_DECLARE_VARIANT(wth)
 PLB_DECLARE_VARIANT(thsei)
+PLB_DECLARE_VARIANT(wthsei)
 
 }  // namespace plb

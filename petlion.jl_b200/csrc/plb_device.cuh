@@ -31,9 +31,6 @@ namespace PLB_NS {
 #ifndef PLB_SEI
 #define PLB_SEI 0
 #endif
-#if PLB_TH && PLB_SEI && PLB_WIDE
-#error "temperature = true together with aging = :SEI is built for grids of up to 32 x-nodes only"
-#endif
 #ifndef PLB_WIDE
 #define PLB_WIDE 0
 #endif

@@ -114,6 +114,9 @@ static const Variant V_WTH = {wth::info, wth::slot_rc, wth::slot_recipe, wth::la
 static const Variant V_THSEI = {thsei::info, thsei::slot_rc, thsei::slot_recipe, thsei::launch_resjac, thsei::launch_initguess,
                                 thsei::launch_newton, thsei::launch_linsolve, thsei::launch_simulate};
 
+static const Variant V_WTHSEI = {wthsei::info, wthsei::slot_rc, wthsei::slot_recipe, wthsei::launch_resjac, wthsei::launch_initguess,
+                                 wthsei::launch_newton, wthsei::launch_linsolve, wthsei::launch_simulate};
+
 struct plb_handle_s {
     plb_model_desc desc;
     ModelDesc m;
@@ -230,8 +233,6 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
     const bool both = d->temperature && d->aging;
     const bool wide = Nx_ > 32 || NtotT_ > (both ? V_THSEI : (d->temperature ? V_TH : (d->aging ? V_SEI : V_ISO))).info().vs;
-    if (both && wide)
-        return fail("plb_create: aging=:SEI together with temperature=true is built for grids of up to 32 x-nodes (and N <= 384) only");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plb_create: no CUDA device available (this library has no CPU fallback)");
@@ -248,7 +249,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     } while (0)
     // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
-    h->v = both ? &V_THSEI
+    h->v = both ? (wide ? &V_WTHSEI : &V_THSEI)
                 : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
     h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
@@ -318,7 +319,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
 }
 
 int plb_variant_info(int family, long long* out) {
-    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : (family == 5 ? wth::info() : (family == 6 ? thsei::info() : iso::info())))));
+    const VariantInfo v = family == 1 ? th::info() : (family == 2 ? sei::info() : (family == 3 ? wide::info() : (family == 4 ? wsei::info() : (family == 5 ? wth::info() : (family == 6 ? thsei::info() : (family == 7 ? wthsei::info() : iso::info()))))));
     out[0] = v.sim_warps; out[1] = v.sim_ctas; out[2] = (long long)v.sim_smem; out[3] = v.k1_warps;
     out[4] = v.k1_ctas; out[5] = (long long)v.k1_smem; out[6] = v.vs; out[7] = v.n_slots;
     return 0;

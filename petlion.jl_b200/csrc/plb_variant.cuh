@@ -65,7 +65,7 @@ enum JacSlot {
 #endif
 constexpr int K1_WARPS = PLB_K1_WARPS;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
-constexpr int K1_SRC_MAX = WIDE ? (TH ? 6656 : 4864) : (TH ? (SEI ? 3328 : 3072) : 2304);        // >= nnz of every built variant
+constexpr int K1_SRC_MAX = WIDE ? (TH ? (SEI ? 7168 : 6656) : 4864) : (TH ? (SEI ? 3328 : 3072) : 2304);        // >= nnz of every built variant
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 // pitch of the value table: one double of padding per slot row.  Consecutive CSC entries of a column come from
@@ -669,7 +669,7 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 #define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 5) : (PLB_SEI ? 6 : 8)))
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? 2 : 3) : 1)
+#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 1 : 2) : 3) : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;

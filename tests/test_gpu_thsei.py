@@ -16,15 +16,17 @@ def P():
     return petlion_b200
 
 
-@pytest.fixture(scope="module")
-def fam(P):
-    return P.petlion("LCO", temperature=True, aging="SEI"), O.make_model("LCO", temperature=True, aging=True)
+@pytest.fixture(scope="module", params=["10-10-10", "20-20-20"])
+def fam(request, P):
+    """one warp per system (N = 372) and, on 60 x-nodes, two warps per system (N = 722)"""
+    grid = {} if request.param == "10-10-10" else dict(N_p=20, N_s=20, N_n=20)
+    return P.petlion("LCO", temperature=True, aging="SEI", **grid), O.make_model("LCO", temperature=True, aging=True, **grid)
 
 
 def test_sizes_and_patterns(fam):
     p, m = fam
     L = O.layout(m)
-    assert p.N.tot == L.N_tot == 372 and p.N.diff == L.N_diff
+    assert p.N.tot == L.N_tot == (372 if m.N_p == 10 else 722) and p.N.diff == L.N_diff
     for method in ("I", "V", "P", "dT", "η_p"):
         cp, rv = O.jac_pattern(m, "eta_p" if method == "η_p" else method)
         cp2, rv2 = p.jac_pattern(method)
@@ -125,7 +127,8 @@ def test_fast_charge_protocol_with_aging(P, fam):
     util.set_theta_batch(p, util.product_theta_from_oracle(p, tho))
     segs = [("I", "value", 4.0, 1e6, {"V_max": 4.1, "T_max": 310.0}), ("dT", "hold", 0.0, 300.0, {"V_max": 4.1}),
             ("V", "hold", 0.0, 600.0, {"V_max": 4.15}), ("I", "value", -1.0, 1200.0, {})]
-    W = dict(cathode="LCO", temperature=True, aging=True, soc0=0.0, segs=segs)
+    W = dict(cathode="LCO", temperature=True, aging=True, soc0=0.0, segs=segs,
+             grid={} if m.N_p == 10 else dict(N_p=20, N_s=20, N_n=20))
     ref = util.oracle_protocol(W, tho, O.default_opts())
     sol, _ = util.gpu_protocol(P, p, W)
     same = np.ones(B, dtype=bool)

@@ -137,14 +137,14 @@ def test_simulate_parity(P, fam):
             same &= s[c] == ref[c]
         print("wide", aging, cur, "identical", float(np.mean(same)), s["n_steps"][:6], ref["n_steps"][:6], s["flag"][:6], ref["flag"][:6])
         assert np.mean(same) >= 0.75
-        np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=5e-6 if m.temperature else 1e-6)
+        np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=2e-5 if m.temperature else 1e-6)
         np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=5e-3)        # the others: same answer at the integrator's tolerance
         np.testing.assert_allclose(s["t_end"][same], ref["t_end"][same], rtol=1e-5)
         for k in np.where(same)[0]:
             n = ref["traj_n"][k]
             # (thermal: the conduction rows carry ~1e-5 K/s of cancellation noise -- tests/test_gpu_thermal.py -- which the
             #  Newton iterations pass on to V at the 1e-6 level even when both sides take the same decisions)
-            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=5e-6 if m.temperature else 1e-6)
+            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=2e-5 if m.temperature else 1e-6)
         if aging and cur > 0:
             L = O.layout(m)
             np.testing.assert_allclose(s["aux_end"][same], ref["state"]["Y"][same][:, L.SOH], rtol=1e-9)
@@ -175,7 +175,7 @@ def test_wide_thermal_protocol_on_a_ragged_grid(P):
         print("segment", k, "identical", same.mean(), s["n_steps"], r["n_steps"])
         assert same.mean() >= 0.6 and (s["flag"] >= 0).all()
         np.testing.assert_allclose(s["V_end"][same], r["V_end"][same], rtol=1e-6)
-        np.testing.assert_allclose(s["T_end"][same], r["T_end"][same], rtol=1e-7)
+        np.testing.assert_allclose(s["T_end"][same], r["T_end"][same], rtol=1e-6)
         np.testing.assert_allclose(s["I_end"][same], r["I_end"][same], rtol=1e-5, atol=1e-8)
         # decision flips: still the same answer at the integrator's tolerance
         np.testing.assert_allclose(s["V_end"], r["V_end"], rtol=5e-3)

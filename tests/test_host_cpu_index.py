@@ -43,7 +43,6 @@ def test_table_host_semantics_match_the_oracle_table():
 
 
 @pytest.mark.parametrize("kw,msg", [
-    (dict(temperature=True, aging="SEI", N_p=20, N_s=10, N_n=20), "up to 32 x-nodes"),
     (dict(N_r_p=12), "N_r_p = N_r_n = 10"),
     (dict(N_p=30, N_s=10, N_n=30), "<= 64"),
     (dict(N_p=1), "2 <= N_p"),
