@@ -15,10 +15,12 @@ for fam in thermal sei wsei; do
   PROF_FAMILY=$fam PROF_B1=32768 PROF_B4=1024 ncu --set full --clock-control none --import-source on -k regex:k_resjac -c 1 -s 1 -o gpurun_out/k1_${fam}_r2z -f python profiles/prof_driver.py > gpurun_out/rz_ncu_k1_$fam.log 2>&1
 done
 for k in k1_r2z k4_r2z k1_thermal_r2z k1_sei_r2z k1_wsei_r2z; do python profiles/ncu_extract.py gpurun_out/$k.ncu-rep > gpurun_out/${k}_ncu_summary.txt 2>/dev/null; done
-compute-sanitizer --tool memcheck python profiles/sanitize_driver.py 2>&1 | tail -8 > gpurun_out/rz_memcheck.txt
+compute-sanitizer --tool memcheck python profiles/sanitize_driver.py 2>&1 | tail -14 > gpurun_out/rz_memcheck.txt
 SAN_FAMILIES=iso compute-sanitizer --tool racecheck python profiles/sanitize_driver.py > gpurun_out/rz_racecheck_full.txt 2>&1
+SAN_FAMILIES=thsei compute-sanitizer --tool racecheck python profiles/sanitize_driver.py 2>&1 | tail -3 > gpurun_out/rz_racecheck_thsei.txt
 SAN_FAMILIES=wide compute-sanitizer --tool racecheck python profiles/sanitize_driver.py > gpurun_out/rz_racecheck_wide_full.txt 2>&1
 SAN_FAMILIES=iso compute-sanitizer --tool synccheck python profiles/sanitize_driver.py 2>&1 | tail -4 > gpurun_out/rz_synccheck.txt
-cat gpurun_out/rz_pytest.log; tail -2 gpurun_out/rz_smoke.log
+for f in iso thermal sei wide wsei wth thsei wthsei mhc; do python profiles/k4_probe.py 16384 $f 2>&1 | tail -1; done > gpurun_out/rz_families.txt
+cat gpurun_out/rz_pytest.log; cat gpurun_out/rz_families.txt; tail -2 gpurun_out/rz_smoke.log
 for f in cfg2 cfg2_reference cfg3 cfg4 cfg5n10; do grep "^{" gpurun_out/rz_bench_$f.json | cut -c1-160; done
 grep -E "RACECHECK SUMMARY|ERROR SUMMARY" gpurun_out/rz_*check*.txt

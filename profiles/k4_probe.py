@@ -1,5 +1,7 @@
 """Times the fused integrator (device-resident buffers, CUDA events) for the library named by PLB_LIB:
-quick A/B of build variants.  usage: PLB_LIB=... python profiles/k4_probe.py [B] [thermal|sei|iso]"""
+quick A/B of build variants.  usage: PLB_LIB=... python profiles/k4_probe.py [B] [iso|thermal|sei|wide|wsei|wth|thsei|wthsei|mhc]
+(one segment: a 1C discharge for iso / wide / mhc, a 4C charge to 4.1 V for the thermal families, a 1C charge to 4.2 V for
+the SEI families)"""
 import ctypes as C, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,19 +12,25 @@ from petlion_b200 import sweep  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 fam = sys.argv[2] if len(sys.argv) > 2 else "iso"
 L = _lib.lib()
-grid = dict(N_p=20, N_s=20, N_n=20) if fam == "wsei" else {}
-p = P.petlion("LCO", temperature=fam == "thermal", aging="SEI" if fam in ("sei", "wsei") else False, **grid)
+grid = dict(N_p=20, N_s=20, N_n=20) if fam in ("wide", "wsei", "wth", "wthsei") else {}
+thermal = fam in ("thermal", "wth", "thsei", "wthsei")
+aging = fam in ("sei", "wsei", "thsei", "wthsei")
+rx = dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC") if fam == "mhc" else {}
+p = P.petlion("LCO", temperature=thermal, aging="SEI" if aging else False, **grid, **rx)
+
 h = p._h; N = p.N.tot
 dev = torch.device("cuda", 0); f64 = dict(dtype=torch.float64, device=dev)
 th = sweep.randomised_theta(p, B)
+if fam == "mhc":      # a physical reorganisation energy (in kT) instead of the reference's 6.26e-20
+    th[:, p.θ_keys.index("λ_MHC_p")] = 15.0; th[:, p.θ_keys.index("λ_MHC_n")] = 12.0
 d_theta = torch.from_numpy(th).to(dev)
-cur, soc = (4.0, 0.0) if fam == "thermal" else ((1.0, 0.0) if fam in ("sei", "wsei") else (-1.0, 1.0))
+cur, soc = (4.0, 0.0) if thermal else ((1.0, 0.0) if aging else (-1.0, 1.0))
 d_soc0 = torch.full((B,), soc, **f64)
 d_Y = torch.zeros(B, N, **f64); d_YP = torch.zeros(B, N, **f64); d_SOC = torch.zeros(B, **f64); d_t = torch.zeros(B, **f64)
 d_sum = torch.zeros(B, 10, **f64); d_trn = torch.zeros(B, dtype=torch.int32, device=dev)
 o = _lib.Opts(); L.plb_opts_defaults(h, C.byref(o)); b = _lib.Bounds(); L.plb_bounds_defaults(h, C.byref(b))
-if fam != "iso":
-    b.V_max = 4.1 if fam == "thermal" else 4.2
+if thermal or aging:
+    b.V_max = 4.1 if thermal else 4.2
 L.plb_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
 run = _lib.Run(0, 0, cur, 1e6, 1, 0)
 ms = []

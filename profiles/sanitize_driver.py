@@ -6,9 +6,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P
 
-fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide").split(",")
+fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc").split(",")
 for fam in fams:
-    kw = dict(iso={}, thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=dict(N_p=20, N_s=20, N_n=20))[fam]
+    G = dict(N_p=20, N_s=20, N_n=20)
+    kw = dict(iso={}, thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=G, wsei=dict(aging="SEI", **G),
+              wth=dict(temperature=True, **G), thsei=dict(temperature=True, aging="SEI"),
+              wthsei=dict(temperature=True, aging="SEI", **G), mhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC"))[fam]
     p = P.petlion("LCO", **kw)
     B = 5
     p.θ["D_sp"] = np.asarray(p.θ["D_sp"]) * np.linspace(0.8, 1.2, B)
