@@ -29,7 +29,13 @@ enum { PLB_RXN_BV = 0, PLB_RXN_MHC = 1 };
  * src/physics_equations/input_methods.jl:182-189; dT=:hold == dT=0);
  * PLB_METHOD_ETA_P = method_eta_p: the plating overpotential Phi_s.n[1] - Phi_e.n[1] held at a value
  * (scalar_residual.jl:92, 199-203; input_methods.jl:108-143) */
-enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2, PLB_METHOD_DT = 3, PLB_METHOD_ETA_P = 4 };
+enum { PLB_METHOD_I = 0, PLB_METHOD_V = 1, PLB_METHOD_P = 2, PLB_METHOD_DT = 3, PLB_METHOD_ETA_P = 4,
+       /* the concentration-rate inputs (input_methods.jl:190-245): the time derivative of the largest / smallest surface
+        * concentration of an electrode, or electrolyte concentration, of the previous solution's last point is held at a
+        * value (`:hold` = 0).  plb_simulate continuation runs of isothermal models without aging only; not available at
+        * operator level (the row depends on the state the run starts from). */
+       PLB_METHOD_DC_S_P_MAX = 6, PLB_METHOD_DC_S_P_MIN = 7, PLB_METHOD_DC_S_N_MAX = 8, PLB_METHOD_DC_S_N_MIN = 9,
+       PLB_METHOD_DC_E_MAX = 10, PLB_METHOD_DC_E_MIN = 11 };
 enum { PLB_MEM_HOST = 0, PLB_MEM_DEVICE = 1 };                /* where the caller's buffers live */
 
 /* petlion(cathode; N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, temperature, aging) -- src/params.jl:119-174 */

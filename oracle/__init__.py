@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
 CATHODE = {"LCO": 0, "NMC": 1}
-METHOD = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4}
+METHOD = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4, "dc": 6, "dc_alg": 7}
+DC_KIND = {"dc_s_p_max": 0, "dc_s_p_min": 1, "dc_s_n_max": 2, "dc_s_n_min": 3, "dc_e_max": 4, "dc_e_min": 5}
 
 
 def build(force=False):
@@ -44,7 +45,7 @@ class Run(C.Structure):
                 ("tab_n", C.c_int), ("tab_t", C.POINTER(C.c_double)), ("tab_v", C.POINTER(C.c_double)),
                 ("scale", C.c_double), ("n_tdiscon", C.c_int), ("tdiscon", C.POINTER(C.c_double)),
                 ("last_value", C.POINTER(C.c_double)), ("n_tstops", C.c_int), ("tstops", C.POINTER(C.c_double)),
-                ("dense", C.c_void_p), ("dense_sys", C.c_int)]
+                ("dense", C.c_void_p), ("dense_sys", C.c_int), ("dc_kind", C.c_int), ("dc_ind", C.c_int)]
 
 
 class Dense(C.Structure):
@@ -155,7 +156,12 @@ INPUT = {"value": 0, "hold": 1, "rest": 2}
 def make_run(method="I", value=-1.0, tf=1e6, input_kind="value", new_run=True, t0=0.0, table=None,
              tdiscon=(), scale=1.0, tstops=()):
     """table = (t_knots, v_knots): a run_function restricted to a piecewise-linear table (see orc_run)"""
-    r = Run(METHOD[method], float(value), float(tf), INPUT[input_kind], int(new_run), float(t0))
+    dc_ind = 0
+    if isinstance(method, tuple):            # ("dc", state index): operator-level calls on a given row
+        method, dc_ind = method
+    dc_kind = DC_KIND.get(method, 0)
+    r = Run(METHOD["dc" if method in DC_KIND else method], float(value), float(tf), INPUT[input_kind], int(new_run), float(t0))
+    r.dc_kind = dc_kind; r.dc_ind = int(dc_ind)
     r.scale = float(scale)
     if len(tstops):
         ts = np.ascontiguousarray(tstops, dtype=np.float64)

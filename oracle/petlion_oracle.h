@@ -57,7 +57,13 @@ enum { ORC_RXN_BV = 0, ORC_RXN_MHC = 1 };   /* custom_functions.jl:212-231, 241-
  * ORC_METHOD_DT_ALG is internal: the same row inside newtons_method!, where the reference substitutes
  * Y'_diff -> rhs_diff(Y) (scalar_residual.jl:347-363). */
 /* ORC_METHOD_ETA: method_eta_p, the plating overpotential Phi_s.n[1] - Phi_e.n[1] (scalar_residual.jl:92, 199-203) */
-enum { ORC_METHOD_I = 0, ORC_METHOD_V = 1, ORC_METHOD_P = 2, ORC_METHOD_DT = 3, ORC_METHOD_ETA = 4, ORC_METHOD_DT_ALG = 5 };
+enum { ORC_METHOD_I = 0, ORC_METHOD_V = 1, ORC_METHOD_P = 2, ORC_METHOD_DT = 3, ORC_METHOD_ETA = 4, ORC_METHOD_DT_ALG = 5,
+       /* the concentration-rate inputs dc_s_p_max/min, dc_s_n_max/min, dc_e_max/min (input_methods.jl:190-245): a
+        * run_residual  val - Y'[ind]  with ind = the arg-max / arg-min state of the previous solution's last point
+        * (orc_run::dc_kind selects which, orc_run::dc_ind is resolved at the start of the run); _ALG: the same row
+        * inside newtons_method! (Y'[ind] -> rhs[ind], scalar_residual.jl:347-363) */
+       ORC_METHOD_DC = 6, ORC_METHOD_DC_ALG = 7 };
+enum { ORC_DC_S_P_MAX = 0, ORC_DC_S_P_MIN, ORC_DC_S_N_MAX, ORC_DC_S_N_MIN, ORC_DC_E_MAX, ORC_DC_E_MIN };
 
 /* model structure: petlion(cathode; N_p, ..., temperature, aging) -- src/params.jl:119-174 */
 typedef struct {
@@ -105,6 +111,8 @@ typedef struct {
      * (times past the end of the run are left untouched). */
     const struct orc_dense *dense;
     int dense_sys;
+    int dc_kind;             /* ORC_DC_* (method ORC_METHOD_DC) */
+    int dc_ind;              /* the state index the row holds; filled in by the run (0-based) */
 } orc_run;
 
 typedef struct orc_dense {

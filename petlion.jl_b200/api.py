@@ -18,7 +18,10 @@ from . import _lib
 CATHODES = {"LCO": 0, "NMC": 1}
 RXN = {"rxn_BV": 0, "rxn_MHC": 1}      # reaction rate laws (custom_functions.jl:212-298)
 rxn_BV, rxn_MHC = "rxn_BV", "rxn_MHC"
-METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4}
+METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4,
+           # concentration-rate inputs (input_methods.jl:190-245): continuation runs of isothermal models without aging
+           "dc_s_p_max": 6, "dc_s_p_min": 7, "dc_s_n_max": 8, "dc_s_n_min": 9, "dc_e_max": 10, "dc_e_min": 11}
+_DC = {k for k in METHODS if k.startswith("dc_")}
 EXIT_REASONS = {  # src/checks.jl
     -1: "running", 0: "Final time reached", 1: "Below min. voltage", 2: "Above max. voltage",
     3: "Below min. SOC", 4: "Above max. SOC", 5: "Above max. temperature", 6: "Above max. c_s_n",
@@ -420,6 +423,11 @@ def simulate(p, tf=1e6, *, sol=None, SOC=None, abstol=None, reltol=None, abstol_
     kind, value, vals, table = 0, 0.0, None, None
     if name == "dT" and not p.numerics.temperature:
         raise ValueError("Temperature must be enabled when using `dT`.")      # input_methods.jl:183
+    if name in _DC:
+        if new_run:
+            raise ValueError(f"`{name}` needs a previous solution: use it with simulate!")     # @assert !isempty(sol.Y), input_methods.jl:196
+        if isinstance(inp, Table) or (isinstance(inp, str) and inp != "hold"):
+            raise ValueError(f"`{name}` takes a number or :hold")
     if isinstance(inp, str):
         if inp == "hold":
             if new_run:

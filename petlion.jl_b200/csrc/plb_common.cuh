@@ -21,7 +21,13 @@ enum { CHEM_LCO = 0, CHEM_NMC = 1 };
 // mode dT (input_methods.jl:182-189): val - temperature_weighting(Y'[T]).  METHOD_DT_ALG is the same row as
 // newtons_method! sees it, with Y'_T replaced by the right-hand side of the T rows (scalar_residual.jl:347-363).
 // METHOD_ETA: method_eta_p, the plating overpotential Phi_s.n[1] - Phi_e.n[1] held at a value (scalar_residual.jl:92, 199-203)
-enum { METHOD_I = 0, METHOD_V = 1, METHOD_P = 2, METHOD_DT = 3, METHOD_ETA = 4, METHOD_DT_ALG = 5 };
+enum { METHOD_I = 0, METHOD_V = 1, METHOD_P = 2, METHOD_DT = 3, METHOD_ETA = 4, METHOD_DT_ALG = 5,
+       // the concentration-rate inputs dc_s_p_max .. dc_e_min (input_methods.jl:190-245): control row val - Y'[ind] with ind
+       // chosen from the previous solution at the start of the run; _ALG: its newtons_method! form (Y'[ind] -> rhs[ind]).
+       // Only the families compiled with PLB_DC carry them (plb_variant_isodc.cu, plb_variant_widedc.cu).  A lane_eval
+       // call passes  method | target lane << 8 | component << 16  (component 0: surface c_s, 1: c_e).
+       METHOD_DC = 6, METHOD_DC_ALG = 7 };
+enum { DC_S_P_MAX = 0, DC_S_P_MIN, DC_S_N_MAX, DC_S_N_MIN, DC_E_MAX, DC_E_MIN };
 constexpr int N_METHODS = 5;
 
 // canonical parameter fields (ASCII names of the reference keys); the thermal block is only part of a
@@ -139,6 +145,7 @@ struct SimArgs {
     const double* dense_t;
     double *dn_V, *dn_I, *dn_SOC, *dn_T, *dn_Y;
     int* dn_n;
+    int dc_kind;              // METHOD_DC: DC_S_P_MAX .. DC_E_MIN
 };
 
 // what the host needs to know about a compiled variant
@@ -173,5 +180,10 @@ PLB_DECLARE_VARIANT(wsei)
 PLB_DECLARE_VARIANT(wth)
 PLB_DECLARE_VARIANT(thsei)
 PLB_DECLARE_VARIANT(wthsei)
+PLB_DECLARE_VARIANT(isomhc)
+PLB_DECLARE_VARIANT(thmhc)
+PLB_DECLARE_VARIANT(seimhc)
+PLB_DECLARE_VARIANT(isodc)
+PLB_DECLARE_VARIANT(widedc)
 
 }  // namespace plb

@@ -34,6 +34,15 @@ namespace PLB_NS {
 #ifndef PLB_WIDE
 #define PLB_WIDE 0
 #endif
+#ifndef PLB_MHC
+#define PLB_MHC 0         // 1: the family also carries rxn_MHC (custom_functions.jl:233-298) next to rxn_BV.  Kept out of the default
+#endif                    // builds: one more branch with an out-of-line call made the 168-register K1 spill (0.70 -> 0.53 of the roofline)
+#ifndef PLB_DC
+#define PLB_DC 0          // 1: the family also carries the concentration-rate inputs (METHOD_DC)
+#endif
+#if PLB_DC && (PLB_TH || PLB_SEI)
+#error "the concentration-rate inputs are built for the isothermal families without aging"
+#endif
 constexpr bool TH = PLB_TH != 0;
 constexpr bool SEI = PLB_SEI != 0;
 // "Wide" families (grids with 33..64 x-nodes, e.g. N = (20,20,20)): one system is owned by a GROUP of two
@@ -509,11 +518,16 @@ struct CtrlRow {
     double gTn, gTx;
     // eta_p control: +g_eta on Phi_s and -g_eta on Phi_e of the first anode node; zero for the other methods
     double g_eta;
+#if PLB_DC
+    // concentration-rate control (METHOD_DC / METHOD_DC_ALG): the row holds one state of lane dc_tgt
+    int dc_on, dc_tgt, dc_comp, dc_alg;
+#endif
 };
 
 // rxn_MHC (custom_functions.jl:233-298, the alpha == 0.5 branch -- the only live one): value and partial derivatives
 // with respect to (eta, c_e, c_s_star) at fixed k and T; fT = F/(R T).  Every sqrt of the reference function is
 // sqrt_ReLU, log_ReLU(x; 1e-4) = log(max(1e-4, x)).
+#if PLB_MHC
 struct MhcRate { double j, d_eta, d_ce, d_cs; };
 __device__ __noinline__ void mhc_rate(double cs, double ce, double eta, double k_i, double fT, double lam, double cmax,
                                       double ce0, bool with_jac, MhcRate& o) {
@@ -542,12 +556,17 @@ __device__ __noinline__ void mhc_rate(double cs, double ce, double eta, double k
         o.d_cs = (live ? -dj_f / cs : 0.0) + k0 * g * Sq * ce0 * sp + (Sq > 0.0 ? -k0 * g * B / (2.0 * Sq * cmax * ce0) : 0.0);
     }
 }
+#endif
 
 template <int CHEM, bool WITH_JAC>
 __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C, const LaneRole& ro,
                                           const LaneVec& y, const LaneVec& yp, double Iapp,
                                           int method, double value, LaneVec& res, CtrlRow& ctrl,
                                           LaneJac& J) {
+#if PLB_DC
+    const int dc_tgt = (method >> 8) & 0xff, dc_comp = (method >> 16) & 1;
+    method &= 0xff;
+#endif
     const int s = ro.sec < 3 ? ro.sec : 1;
     const double T = TH ? (ro.act ? y.T : kTref) : C.g[GC_T];
     // ---- node-local electrolyte properties: build_K_eff!/build_D_eff! (:302-328) -----------------
@@ -661,6 +680,7 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         }
         const double eta = y.ps - y.pe - U - (sei_n ? kF * y.j * Rfilm : 0.0);   // build_eta! (:272-300)
         const double cmax = C.sec[SC_cmax][s];
+#if PLB_MHC
         if (m.rxn_mhc != 0 && ((m.rxn_mhc >> (ro.sec == 2 ? 1 : 0)) & 1)) {
             // rxn_MHC, custom_functions.jl:233-298 (out of line: a model option, kept off the registers of rxn_BV)
             MhcRate o;
@@ -681,7 +701,9 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
                     dj_T = jcalc * C.sec[SC_Eak][s] * iT * iT - dj_eta * dUdT - dj_eta * eta * iT;
                 }
             }
-        } else {
+        } else
+#endif
+        {
             // rxn_BV, custom_functions.jl:212-231
             const double arg = ce * cs_s * (cmax - cs_s);
             const double sq = arg > 0.0 ? sqrt(arg) : 0.0;                       // sqrt_ReLU
@@ -864,6 +886,18 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         const double ps0 = shfl_from(y.ps, 0), psN = shfl_from(y.ps, m.Nx - 1);
         const double V = ps0 - psN;
         ctrl.gTn = 0.0; ctrl.gTx = 0.0; ctrl.g_eta = 0.0;
+#if PLB_DC
+        ctrl.dc_on = 0; ctrl.dc_tgt = dc_tgt; ctrl.dc_comp = dc_comp; ctrl.dc_alg = 0;
+        if (method == METHOD_DC || method == METHOD_DC_ALG) {
+            // run_residual of state_deriv_func(ind): val - Y'[ind] (scalar_residual.jl:172, auxiliary_states_and_coefficients.jl:682);
+            // inside newtons_method! Y'[ind] is replaced by the right-hand side of that state's own row (:347-363)
+            const bool alg = method == METHOD_DC_ALG;
+            const double mine = dc_comp ? (alg ? res.ce + yp.ce : yp.ce) : (alg ? res.cs[NR - 1] + yp.cs[NR - 1] : yp.cs[NR - 1]);
+            ctrl.res = value - shfl_from(mine, dc_tgt);
+            ctrl.g_ps0 = 0.0; ctrl.g_psN = 0.0; ctrl.g_I = 0.0;
+            ctrl.dc_on = 1; ctrl.dc_alg = alg ? 1 : 0;
+        } else
+#endif
         if (method == METHOD_ETA) {
             const int ln = m.Np + m.Ns;                                  // first anode node
             ctrl.res = (shfl_from(y.ps, ln) - shfl_from(y.pe, ln)) - value;   // calc_eta_plating, scalar_residual.jl:92
@@ -979,6 +1013,11 @@ struct WarpFactor {
     double g_eta;
     double ionly;              // != 0: the control row has only its I entry (current control): z holds the RAW border
                                // column and dI is folded into the right-hand side before the sweeps (no border solve)
+#if PLB_DC
+    // concentration-rate control: border row = dc_as * (particle solve, surface) + dc_aj * dj + dc_ace * dc_e, all of lane dc_tgt
+    double dc_on, dc_as, dc_aj, dc_ace;
+    int dc_tgt, dc_pad;
+#endif
 };
 
 // Block-Thomas as a "twisted" (two-sided) elimination: nodes 0..mid-1 are eliminated left-to-right,
@@ -1238,7 +1277,11 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     // known before the block system is solved and the border column can be folded into the right-hand side of every
     // solve -- no border solve here.  That solve was a third of the factorisation, and the factorising warp is the one
     // the other five wait for at the tick barrier in 61 % of the ticks.
+#if PLB_DC
+    const bool ionly = ctrl.g_ps0 == 0.0 && ctrl.g_psN == 0.0 && ctrl.g_eta == 0.0 && !ctrl.dc_on;
+#else
     const bool ionly = ctrl.g_ps0 == 0.0 && ctrl.g_psN == 0.0 && ctrl.g_eta == 0.0;
+#endif
     if (ionly) {
         Fa.z[0][lane] = zf[0]; Fa.z[1][lane] = zf[1]; Fa.z[2][lane] = zf[2];
         // (a singular diagonal block no longer reaches schur_inv through z: look at the blocks themselves)
@@ -1247,6 +1290,9 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         if (lane == 0) {
             Fa.schur_inv = bad != 0.0 ? NAN : 1.0 / ctrl.g_I;
             Fa.g_ps0 = 0.0; Fa.g_psN = 0.0; Fa.g_eta = 0.0; Fa.ionly = 1.0;
+#if PLB_DC
+            Fa.dc_on = 0.0;
+#endif
         }
         grp_sync();
         return;
@@ -1256,8 +1302,26 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     Fa.z[0][lane] = u3[0]; Fa.z[1][lane] = u3[1]; Fa.z[2][lane] = u3[2];
     const double z0 = shfl_from(u3[2], 0), zN = shfl_from(u3[2], m.Nx - 1);
     const double ze = shfl_from(u3[2] - u3[1], m.Np + m.Ns);
+    double gz_dc = 0.0;
+#if PLB_DC
+    {
+        // the row in terms of the reduced unknowns of lane dc_tgt.  DAE form: -cj on the state itself
+        //   surface c_s: d c_s,surf = (S^-1 g_cs)_surf - vb_surf dj      c_e: the block unknown itself
+        // newtons_method! form: -d rhs[ind] / d j  (the only algebraic unknown those rows see)
+        const int elt = ctrl.dc_tgt >= m.Np + m.Ns ? 1 : 0;
+        double as = 0.0, aj = 0.0, ace = 0.0;
+        if (ctrl.dc_on) {
+            if (ctrl.dc_alg) aj = -shfl_from(ctrl.dc_comp ? J.ce_j : J.cs_j, ctrl.dc_tgt);
+            else if (ctrl.dc_comp) ace = -cj;
+            else { as = -cj; aj = cj * Fa.vb[NR - 1][elt]; }
+        }
+        const double djz = ro.elec ? q_ce * u3[0] + q_pe * u3[1] + q_ps * u3[2] : 0.0;      // column solution: no local part
+        gz_dc = shfl_from(aj * djz + ace * u3[0], ctrl.dc_tgt);
+        if (lane == 0) { Fa.dc_on = ctrl.dc_on ? 1.0 : 0.0; Fa.dc_as = as; Fa.dc_aj = aj; Fa.dc_ace = ace; Fa.dc_tgt = ctrl.dc_tgt; }
+    }
+#endif
     if (lane == 0) {
-        Fa.schur_inv = 1.0 / (ctrl.g_I - ctrl.g_ps0 * z0 - ctrl.g_psN * zN - ctrl.g_eta * ze);
+        Fa.schur_inv = 1.0 / (ctrl.g_I - ctrl.g_ps0 * z0 - ctrl.g_psN * zN - ctrl.g_eta * ze - gz_dc);
         Fa.g_ps0 = ctrl.g_ps0;
         Fa.g_psN = ctrl.g_psN;
         Fa.g_eta = ctrl.g_eta;
@@ -1322,6 +1386,12 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
         const double x0 = shfl_from(u3[2], 0), xN = shfl_from(u3[2], m.Nx - 1);
         double gx = Fa.g_ps0 * x0 + Fa.g_psN * xN;
         if (Fa.g_eta != 0.0) gx += Fa.g_eta * shfl_from(u3[2] - u3[1], m.Np + m.Ns);      // eta_p control (uniform branch)
+#if PLB_DC
+        if (Fa.dc_on != 0.0) {                                                              // (uniform branch)
+            const double dj0 = ro.elec ? q0 + Fa.q[0][lane] * u3[0] + Fa.q[1][lane] * u3[1] + Fa.q[2][lane] * u3[2] : 0.0;
+            gx += shfl_from(Fa.dc_as * p0 + Fa.dc_aj * dj0 + Fa.dc_ace * u3[0], Fa.dc_tgt);
+        }
+#endif
         dI = (gI - gx) * Fa.schur_inv;
         u3[0] -= Fa.z[0][lane] * dI; u3[1] -= Fa.z[1][lane] * dI; u3[2] -= Fa.z[2][lane] * dI;
     }

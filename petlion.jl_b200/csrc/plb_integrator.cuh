@@ -160,8 +160,17 @@ __device__ __forceinline__ double wrms(const ModelDesc& m, const double* v, cons
 
 struct RunCtl {
     int method;
+    int dc;            // METHOD_DC: target lane | component << 8 (0: surface c_s, 1: c_e); fills the padding
     double value;
 };
+// the method word a lane_eval call gets (see plb_common.cuh); alg: the newtons_method! form of a Y'-dependent row
+__device__ __forceinline__ int method_word(const RunCtl& rc, bool alg) {
+    if (alg && rc.method == METHOD_DT) return METHOD_DT_ALG;
+#if PLB_DC
+    if (rc.method == METHOD_DC) return (alg ? METHOD_DC_ALG : METHOD_DC) | (rc.dc << 8);
+#endif
+    return rc.method;
+}
 
 // ------------------------------------------------------------------------------------------------
 // newtons_method! -- model_evaluation.jl:430-480.  Y: vector in workspace (in/out), YP: vector (out)
@@ -181,7 +190,7 @@ __device__ __forceinline__ int newton_init(const ModelDesc& m, WarpWS& w, const 
     for (int r = 0; r < NR; r++) yp.cs[r] = 0.0;
     int iter;
     bool ok = false;
-    const int meth = rc.method == METHOD_DT ? METHOD_DT_ALG : rc.method;
+    const int meth = method_word(rc, true);
     for (iter = 1; iter <= 100; iter++) {
         lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, I, meth, rc.value, res, ctrl, J);   // R_alg, J_alg
         n_res++; n_jac++;

@@ -117,10 +117,22 @@ static const Variant V_THSEI = {thsei::info, thsei::slot_rc, thsei::slot_recipe,
 static const Variant V_WTHSEI = {wthsei::info, wthsei::slot_rc, wthsei::slot_recipe, wthsei::launch_resjac, wthsei::launch_initguess,
                                  wthsei::launch_newton, wthsei::launch_linsolve, wthsei::launch_simulate};
 
+// the 32-node families with rxn_MHC compiled in (used by models that select it)
+#define PLB_VARIANT_TABLE(NS) {NS::info, NS::slot_rc, NS::slot_recipe, NS::launch_resjac, NS::launch_initguess, NS::launch_newton, NS::launch_linsolve, NS::launch_simulate}
+static const Variant V_ISOMHC = PLB_VARIANT_TABLE(isomhc);
+static const Variant V_THMHC = PLB_VARIANT_TABLE(thmhc);
+static const Variant V_SEIMHC = PLB_VARIANT_TABLE(seimhc);
+// the isothermal families with the concentration-rate inputs compiled in (used by those runs only)
+static const Variant V_ISODC = {isodc::info, isodc::slot_rc, isodc::slot_recipe, isodc::launch_resjac, isodc::launch_initguess,
+                                isodc::launch_newton, isodc::launch_linsolve, isodc::launch_simulate};
+static const Variant V_WIDEDC = {widedc::info, widedc::slot_rc, widedc::slot_recipe, widedc::launch_resjac, widedc::launch_initguess,
+                                 widedc::launch_newton, widedc::launch_linsolve, widedc::launch_simulate};
+
 struct plb_handle_s {
     plb_model_desc desc;
     ModelDesc m;
     const Variant* v = nullptr;
+    const Variant* v_dc = nullptr;       // the same family with METHOD_DC compiled in (isothermal, no aging), else null
     VariantInfo vi;
     std::vector<int> keys;               // indices into KEYS, reference (sorted) order
     // CSC patterns per method
@@ -233,6 +245,8 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
     const bool both = d->temperature && d->aging;
     const bool wide = Nx_ > 32 || NtotT_ > (both ? V_THSEI : (d->temperature ? V_TH : (d->aging ? V_SEI : V_ISO))).info().vs;
+    if ((d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) && (wide || both))
+        return fail("plb_create: rxn_MHC is built for grids of up to 32 x-nodes, with temperature=true or aging=:SEI but not both");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plb_create: no CUDA device available (this library has no CPU fallback)");
@@ -251,8 +265,22 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
     h->v = both ? (wide ? &V_WTHSEI : &V_THSEI)
                 : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
+    if (d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) {
+        const Variant* mv = h->v == &V_ISO ? &V_ISOMHC : (h->v == &V_TH ? &V_THMHC : (h->v == &V_SEI ? &V_SEIMHC : nullptr));
+        if (!mv) {
+            delete h;
+            return fail("plb_create: rxn_MHC is built for grids of up to 32 x-nodes, with temperature=true or aging=:SEI but not both");
+        }
+        h->v = mv;
+    }
     h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
+    if (h->v == &V_ISO) h->v_dc = &V_ISODC;
+    if (h->v == &V_WIDE) h->v_dc = &V_WIDEDC;
+    if (h->v_dc) {
+        const VariantInfo di = h->v_dc->info();      // same geometry and workspace: the two builds share every buffer
+        if (di.sim_warps != h->vi.sim_warps || di.sim_ctas != h->vi.sim_ctas || di.vs != h->vi.vs || di.nglobal != h->vi.nglobal) h->v_dc = nullptr;
+    }
     ModelDesc& m = h->m;
     memset(&m, 0, sizeof m);
     m.Np = d->N_p; m.Ns = d->N_s; m.Nn = d->N_n; m.Nx = m.Np + m.Ns + m.Nn; m.Ne = m.Np + m.Nn;
@@ -593,7 +621,12 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     if (!run || !opts || !bounds || !theta || !sY || !sSOC || !st || !summary)
         return fail("plb_simulate: null required argument");
     if (dense.n && dense.mem != mem) return fail("plb_simulate: the dense-output buffers must live where the other buffers live");
-    if (!h->method_ok(run->method))
+    const bool dc = run->method >= PLB_METHOD_DC_S_P_MAX && run->method <= PLB_METHOD_DC_E_MIN;
+    if (dc) {
+        if (!h->v_dc) return fail("plb_simulate: the concentration-rate inputs dc_s_* / dc_e_* are built for isothermal models without aging");
+        if (run->new_run) return fail("plb_simulate: dc_s_* / dc_e_* need a previous solution (input_methods.jl:196)");
+        if (run->input_kind == PLB_INPUT_REST || tab) return fail("plb_simulate: dc_s_* / dc_e_* take a number or :hold");
+    } else if (!h->method_ok(run->method))
         return fail(run->method == PLB_METHOD_DT ? "plb_simulate: Temperature must be enabled when using `dT`."   // input_methods.jl:183
                                                  : "plb_simulate: bad method");
     if (run->input_kind != PLB_INPUT_VALUE && run->new_run && run->input_kind == PLB_INPUT_HOLD)
@@ -663,7 +696,8 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
                     stage_inout(b[24], dense.n_done, hdn, (size_t)B, mem, false, s))) return -1;
     SimArgs a;
     memset(&a, 0, sizeof a);
-    a.m = m; a.B = B; a.theta = theta; a.values = values; a.method = run->method; a.value = run->value;
+    a.m = m; a.B = B; a.theta = theta; a.values = values; a.method = dc ? METHOD_DC : run->method; a.value = run->value;
+    a.dc_kind = dc ? run->method - PLB_METHOD_DC_S_P_MAX : 0;
     a.tf = run->tf; a.input_kind = run->input_kind; a.new_run = run->new_run; a.o = to_opts(opts);
     memcpy(&a.b, bounds, sizeof(Bounds));
     static_assert(sizeof(plb_bounds) == sizeof(Bounds), "bounds layout");
@@ -685,7 +719,7 @@ static int simulate_impl(plb_handle h, int B, const double* theta, const plb_run
     CUDA_OK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
     const int grid = std::min((B + h->vi.sim_warps - 1) / h->vi.sim_warps, h->sim_grid);
     CUDA_OK(cudaEventRecord(h->ev0, s));
-    CUDA_OK(h->v->simulate(a, grid, s));
+    CUDA_OK((dc ? h->v_dc : h->v)->simulate(a, grid, s));
     CUDA_OK(cudaEventRecord(h->ev1, s));
     h->launches++;
     if (stage_out(sY, hY, BN, s) || stage_out(sYP, hYP, BN, s) || stage_out(sSOC, hSOC, (size_t)B, s) ||

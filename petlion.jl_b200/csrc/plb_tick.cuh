@@ -575,7 +575,7 @@ __device__ PLB_COLD void fetch_and_setup(const SimArgs& a, WarpWS& w, const Lane
     S.sys = sys;
     const int N = m.N_tot;
     setup_consts(m, a.theta + (size_t)sys * m.theta_stride, w.C, lane);
-    S.rc.method = a.method;
+    S.rc.method = a.method; S.rc.dc = 0;
     S.t_init = 0.0; S.reinit = 0; S.n_reinit = 0; S.scale = 1.0;
     if (EXT && a.tab_n) {   // run_function: initial_current! evaluates the function at t = 0 (input_methods.jl:27-29, 64-74, 104-107)
         S.scale = a.values ? a.values[sys] : 1.0;
@@ -630,6 +630,24 @@ __device__ PLB_COLD void fetch_and_setup(const SimArgs& a, WarpWS& w, const Lane
     {
         double Ig;
         const double V0 = Y0[iP0] - Y0[iPN];
+#if PLB_DC
+        if (S.rc.method == METHOD_DC) {
+            // input_method(::Val{:dc_s_p_max}, ...) etc. (input_methods.jl:195-245): the state with the largest / smallest
+            // value in the last point of the previous solution; argmax / argmin return the first one
+            const int k = a.dc_kind;
+            const bool is_e = k >= DC_E_MAX, is_n = (k == DC_S_N_MAX || k == DC_S_N_MIN);
+            const bool want_max = (k == DC_S_P_MAX || k == DC_S_N_MAX || k == DC_E_MAX);
+            const LaneRole ro_ = make_role(m, lane);
+            const bool cand = is_e ? ro_.act : (ro_.sec == (is_n ? 2 : 0));
+            double v = 0.0;
+            if (cand) v = is_e ? Y0[lane] : Y0[m.off_cs + ro_.e * NR + NR - 1];
+            const double best = want_max ? grp_max(cand ? v : -INFINITY) : grp_min(cand ? v : INFINITY);
+            const int tgt = (int)grp_min((cand && v == best) ? (double)lane : 1e9);
+            S.rc.dc = tgt | ((is_e ? 1 : 0) << 8);
+            if (a.input_kind == 1) S.rc.value = 0.0;          // custom_res!: hold_val = 0
+            Ig = I_prev_state;                                // initial_current! of a run_residual (input_methods.jl:173-176)
+        } else
+#endif
         if (S.rc.method == METHOD_DT) {
             // run_residual: custom_res! (model_evaluation.jl:155-170) -> value, or 0 for :hold;
             // initial_current! (input_methods.jl:173-176): the previous current, else 1
@@ -835,7 +853,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             // each warp picks the variant from its OWN state only, so a system's arithmetic (and therefore
             // its bits) never depends on which other systems share the CTA
             // the dT control row takes its newtons_method! form during the algebraic initialisation
-            const int meth = (alg_only && S.rc.method == METHOD_DT) ? METHOD_DT_ALG : S.rc.method;
+            const int meth = method_word(S.rc, alg_only);
 #if PLB_TICK_OUTLINE
             if (need_jac) lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
             else lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);

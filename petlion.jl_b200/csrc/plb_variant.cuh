@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(SIM_WARPS * LW, SIM_CTAS) k_newton(const __gri
         for (int i = lane; i < N; i += LW) w.v(V_PHI0)[i] = a.Y[(size_t)sys * N + ref_index(m, i)];
         grp_sync();
         RunCtl rc;
-        rc.method = a.method;
+        rc.method = a.method; rc.dc = 0;
         rc.value = a.values ? a.values[sys] : a.value;
         int nres = 0, njac = 0;
         const int it = newton_init<CHEM>(m, w, ro, rc, a.o, w.v(V_PHI0), w.v(V_PHI1), lane, nres, njac);

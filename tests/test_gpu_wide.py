@@ -142,9 +142,10 @@ def test_simulate_parity(P, fam):
         np.testing.assert_allclose(s["t_end"][same], ref["t_end"][same], rtol=1e-5)
         for k in np.where(same)[0]:
             n = ref["traj_n"][k]
-            # (thermal: the conduction rows carry ~1e-5 K/s of cancellation noise -- tests/test_gpu_thermal.py -- which the
-            #  Newton iterations pass on to V at the 1e-6 level even when both sides take the same decisions)
-            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=2e-5 if m.temperature else 1e-6)
+            # (thermal: the conduction rows carry ~1e-5 K/s of cancellation noise -- tests/test_gpu_thermal.py.  It enters
+            #  the error norms, hence the step-size factors: with equal counters the step TIMES still differ by ~1e-4
+            #  relative, and these rows are compared at each side's own step times -- 0.14 mV in the knee of a discharge)
+            np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=1e-4 if m.temperature else 1e-6)
         if aging and cur > 0:
             L = O.layout(m)
             np.testing.assert_allclose(s["aux_end"][same], ref["state"]["Y"][same][:, L.SOH], rtol=1e-9)

@@ -44,6 +44,8 @@ def test_table_host_semantics_match_the_oracle_table():
 
 @pytest.mark.parametrize("kw,msg", [
     (dict(N_r_p=12), "N_r_p = N_r_n = 10"),
+    (dict(rxn_p="rxn_MHC", N_p=20, N_s=10, N_n=20), "rxn_MHC is built for grids of up to 32"),
+    (dict(rxn_n="rxn_MHC", temperature=True, aging="SEI"), "rxn_MHC is built for"),
     (dict(N_p=30, N_s=10, N_n=30), "<= 64"),
     (dict(N_p=1), "2 <= N_p"),
     (dict(temperature=True, N_p=4), "N_p, N_n >= 5"),
