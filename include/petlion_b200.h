@@ -136,7 +136,10 @@ int plb_jac_pattern(plb_handle h, int method, int *colptr, int *rowval, int one_
 int plb_initial_guess(plb_handle h, int B, const double *soc, const double *theta, double *Y0, int mem);
 
 /* R_full(res,t,Y,YP,p,run) -- model_evaluation.jl:263 ;  J_full(J,t,Y,YP,gamma,p,run) -- :264
- * values: per-system control value [B] or NULL (then run->value).  Either output may be NULL. */
+ * values: per-system control value [B] or NULL (then run->value).  Either output may be NULL.
+ * There is no `t` argument: the generated residual depends on time only through a run_function's value
+ * (scalar_residual.jl:169-170), and a closure cannot cross this boundary -- the caller evaluates its input at t and
+ * passes the numbers in `values` (that is what plb_simulate_table does on the device, per step). */
 int plb_resjac(plb_handle h, int B, const double *Y, const double *YP, const double *gamma,
                const double *theta, const plb_run *run, const double *values, double *res,
                double *nzval, int mem);

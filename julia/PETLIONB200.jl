@@ -35,7 +35,9 @@ struct InputTable
     n::Cint; t::Ptr{Cdouble}; v::Ptr{Cdouble}; n_tdiscon::Cint; tdiscon::Ptr{Cdouble}
 end
 
-const METHOD = Dict(:I => 0, :V => 1, :P => 2, :dT => 3, :η_p => 4)     # scalar_residual.jl:167-202
+const METHOD = Dict(:I => 0, :V => 1, :P => 2, :dT => 3, :η_p => 4,       # scalar_residual.jl:167-202
+                    :dc_s_p_max => 6, :dc_s_p_min => 7, :dc_s_n_max => 8, :dc_s_n_min => 9,   # input_methods.jl:190-245
+                    :dc_e_max => 10, :dc_e_min => 11)                       # (simulate! on isothermal models without aging)
 const INPUT_VALUE, INPUT_HOLD, INPUT_REST = 0, 1, 2                      # input_methods.jl:5-74
 const MEM_HOST, MEM_DEVICE = 0, 1
 
