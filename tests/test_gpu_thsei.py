@@ -150,3 +150,33 @@ def test_fast_charge_protocol_with_aging(P, fam):
     assert np.all(soh[0] < 1.0) and np.all(soh[1] < soh[0]) and np.all(soh[2] < soh[1])
     np.testing.assert_array_equal(soh[3], soh[2])          # j_s == 0 on discharge (residuals.jl:546)
     assert np.all(sol.results[0].summary["T_end"] > 299.0)
+
+
+def test_tight_tolerance_whole_trajectory(P):
+    """north_star's tolerance on the new family: at reltol = abstol = 1e-7 (the thermal families' floor, see
+    tests/test_gpu_tight.py) every row of V / T / SOC and of the SOH up to 60 s before the exit agrees to 1e-6 for every
+    system -- a 2C charge with the side reaction running, whatever steps either side takes"""
+    B = 128
+    p = P.petlion("LCO", temperature=True, aging="SEI")
+    m = O.make_model("LCO", temperature=True, aging=True)
+    L = O.layout(m)
+    tho = util.oracle_theta_batch(B, first=5000)
+    util.set_theta_batch(p, util.product_theta_from_oracle(p, tho))
+    tol = 1e-7
+    td = np.arange(7.0, 1700.0, 20.0)
+    sol = P.simulate(p, 1700.0, I=2, SOC=0.0, V_max=4.2, dense_t=td, n_save_max=0, reltol=tol, abstol=tol, maxiters=100000)
+    o = O.default_opts(reltol=tol, abstol=tol, reltol_init=tol, abstol_init=tol, maxiters=100000)
+    ref = O.simulate_batch(m, tho, O.make_run("I", 2.0, tf=1700.0), o, O.default_bounds("LCO", V_max=4.2), SOC0=0.0, nthreads=16,
+                           dense_t=td, dense_Y=True)
+    s = sol.results[0].summary
+    assert (s["flag"] >= 0).all() and (ref["flag"] >= 0).all()
+    before_exit = td[None, :] <= np.minimum(s["t_end"], ref["t_end"])[:, None] - 60.0
+    for key in ("V", "I", "SOC", "T"):
+        g, r = sol.dense[key], ref["dense"][key]
+        both = ~np.isnan(g) & ~np.isnan(r) & before_exit
+        assert both.sum() > 20 * B
+        err = np.abs(g - r)[both] / (np.maximum(np.abs(r[both]), 1e-3) if key != "SOC" else 1.0)
+        assert err.max() <= 1e-6, (key, float(err.max()))
+    # the capacity fade at the end: SOH of the final state
+    np.testing.assert_allclose(s["aux_end"], ref["state"]["Y"][:, L.SOH], rtol=1e-6)
+    assert np.all(s["aux_end"] < 0.9999)
