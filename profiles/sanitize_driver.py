@@ -29,4 +29,8 @@ for fam in fams:
     del os.environ["PLB_K1_NO_TMA"]
     assert np.array_equal(res, res_b) and np.array_equal(nz, nz_b)
     x, ok = p.linear_solve(Y, YP, np.full(B, 0.1), res, method="I", value=1.0)
+    if fam in ("iso", "wide"):            # the concentration-rate inputs run in a sibling build of these two families
+        P.simulate_(sol, p, 50, dc_s_n_max="hold")
+        P.simulate_(sol, p, 50, dc_e_min=-0.01)
+        assert (sol.results[-1].summary["flag"] >= 0).all()
     print(fam, "ok", sol.results[-1].summary["flag"], sol2.results[-1].summary["n_steps"], int(np.isfinite(x).all()), flush=True)

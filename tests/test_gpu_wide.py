@@ -128,26 +128,33 @@ def test_simulate_parity(P, fam):
     th = util.product_theta_from_oracle(p, tho)
     util.set_theta_batch(p, th)
     b = O.default_bounds("LCO", V_max=4.2)
+    td = np.arange(7.0, 3700.0, 45.0)
     for cur, soc0 in ((1.0, 0.0), (-1.0, 1.0)):
-        sol = P.simulate(p, I=cur, SOC=soc0, V_max=4.2)
-        ref = O.simulate_batch(m, tho, O.make_run("I", cur), O.default_opts(), b, SOC0=soc0, n_save_max=512, nthreads=8)
+        sol = P.simulate(p, I=cur, SOC=soc0, V_max=4.2, dense_t=td)
+        ref = O.simulate_batch(m, tho, O.make_run("I", cur), O.default_opts(), b, SOC0=soc0, n_save_max=512, nthreads=8, dense_t=td)
         s = sol.results[-1].summary
         same = np.ones(B, dtype=bool)          # the same decisions: every counter agrees
         for c in ("flag", "n_steps", "n_res", "n_jac", "n_netf", "n_ncfn"):
             same &= s[c] == ref[c]
         print("wide", aging, cur, "identical", float(np.mean(same)), s["n_steps"][:6], ref["n_steps"][:6], s["flag"][:6], ref["flag"][:6])
         assert np.mean(same) >= 0.75
+        # thermal: the conduction rows carry ~1e-5 K/s of cancellation noise (tests/test_gpu_thermal.py).  It enters the error
+        # norms, hence the step-size factors: with equal counters the step TIMES still drift apart by up to ~1e-3 relative, so
+        # rows saved at each side's own step times are not comparable there; compare on a common grid (both sides' dense
+        # output) -- which is also what bounds the systems that took different decisions
         np.testing.assert_allclose(s["V_end"][same], ref["V_end"][same], rtol=2e-5 if m.temperature else 1e-6)
         np.testing.assert_allclose(s["V_end"], ref["V_end"], rtol=5e-3)        # the others: same answer at the integrator's tolerance
         np.testing.assert_allclose(s["t_end"][same], ref["t_end"][same], rtol=1e-5)
-        for k in np.where(same)[0]:
-            n = ref["traj_n"][k]
-            # (thermal: the conduction rows carry ~1e-5 K/s of cancellation noise -- tests/test_gpu_thermal.py.  It enters
-            #  the error norms, hence the step-size factors: with equal counters the step TIMES still differ by ~1e-4
-            #  relative, and these rows are compared at each side's own step times -- 0.14 mV in the knee of a discharge)
-            #  -- so the last rows before the exit, where V falls by 15 mV/s, are left to the V_end / t_end checks above)
-            nn = n - 3 if m.temperature else n
-            np.testing.assert_allclose(sol.V[k, :nn], ref["traj"]["V"][k, :nn], rtol=1e-4 if m.temperature else 1e-6)
+        g, r = sol.dense["V"], ref["dense"]["V"]
+        both = ~np.isnan(g) & ~np.isnan(r) & (td[None, :] <= np.minimum(s["t_end"], ref["t_end"])[:, None] - 30.0)
+        assert both[same].sum() > 30 * same.sum()
+        err = np.where(both, np.abs(g - r) / np.maximum(np.abs(r), 1e-3), 0.0)
+        assert err[same].max() <= (2e-5 if m.temperature else 1e-6), float(err[same].max())
+        assert err.max() <= 5e-3, float(err.max())
+        if not m.temperature:
+            for k in np.where(same)[0]:
+                n = ref["traj_n"][k]
+                np.testing.assert_allclose(sol.V[k, :n], ref["traj"]["V"][k, :n], rtol=1e-6)
         if aging and cur > 0:
             L = O.layout(m)
             np.testing.assert_allclose(s["aux_end"][same], ref["state"]["Y"][same][:, L.SOH], rtol=1e-9)
