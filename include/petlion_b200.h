@@ -21,7 +21,8 @@ extern "C" {
 
 typedef struct plb_handle_s *plb_handle;
 
-enum { PLB_CATHODE_LCO = 0, PLB_CATHODE_NMC = 1 };
+enum { PLB_CATHODE_LCO = 0, PLB_CATHODE_NMC = 1,
+       PLB_CATHODE_NMC_LGM50 = 2 /* NMC_LGM50 + LiC6_LGM50 + system_LGM50_NMC_LiC6 (params.jl:514-849): aging = false only */ };
 /* reaction rate laws, chosen per electrode (params.jl:51, 114; custom_functions.jl:212-231 rxn_BV, :233-298 rxn_MHC) */
 enum { PLB_RXN_BV = 0, PLB_RXN_MHC = 1 };
 /* method_I / method_V / method_P (scalar_residual.jl:167-202); PLB_METHOD_DT = the `dT` input of thermal

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
-CATHODE = {"LCO": 0, "NMC": 1}
+CATHODE = {"LCO": 0, "NMC": 1, "NMC_LGM50": 2, "LGM50": 2}
 METHOD = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4, "dc": 6, "dc_alg": 7}
 DC_KIND = {"dc_s_p_max": 0, "dc_s_p_min": 1, "dc_s_n_max": 2, "dc_s_n_min": 3, "dc_e_max": 4, "dc_e_min": 5}
 

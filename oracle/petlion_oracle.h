@@ -40,7 +40,8 @@ extern "C" {
     X(lambda_a) X(lambda_n) X(lambda_p) X(lambda_s) X(lambda_z) /* λ_* */               \
     X(rho_a) X(rho_n) X(rho_p) X(rho_s) X(rho_z) /* ρ_* */                              \
     X(M_n) X(R_SEI) X(Uref_s) X(i_0_jside) X(k_n_aging) X(w)                            \
-    X(lambda_MHC_n) X(lambda_MHC_p) /* λ_MHC_* (rxn_MHC only) */
+    X(lambda_MHC_n) X(lambda_MHC_p) /* λ_MHC_* (rxn_MHC only) */                        \
+    X(D_e) /* electrolyte diffusivity scale of D_eff_LGM50 (NMC_LGM50 only) */
 
 typedef struct {
 #define X(n) double n;
@@ -50,7 +51,8 @@ typedef struct {
 
 #define ORC_NTHETA ((int)(sizeof(orc_theta) / sizeof(double)))
 
-enum { ORC_CATHODE_LCO = 0, ORC_CATHODE_NMC = 1 };
+enum { ORC_CATHODE_LCO = 0, ORC_CATHODE_NMC = 1,
+       ORC_CATHODE_LGM50 = 2 /* NMC_LGM50 + LiC6_LGM50 + system_LGM50_NMC_LiC6 (Chen et al. 2020), params.jl:514-849 */ };
 enum { ORC_RXN_BV = 0, ORC_RXN_MHC = 1 };   /* custom_functions.jl:212-231, 241-298 */
 /* method_I / method_V / method_P (scalar_residual.jl:167-202) and `dT` = the constant_temperature
  * residual of input_methods.jl:182-189 (control row  val - temperature_weighting(Y'[T])).

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 
-CATHODES = {"LCO": 0, "NMC": 1}
+CATHODES = {"LCO": 0, "NMC": 1, "NMC_LGM50": 2}
 RXN = {"rxn_BV": 0, "rxn_MHC": 1}      # reaction rate laws (custom_functions.jl:212-298)
 rxn_BV, rxn_MHC = "rxn_BV", "rxn_MHC"
 METHODS = {"I": 0, "V": 1, "P": 2, "dT": 3, "η_p": 4, "eta_p": 4,
@@ -241,11 +241,13 @@ def model_key(p):
     same key share the same compiled family and Jacobian pattern."""
     import hashlib
     nm, N = p.numerics, p.N
-    anode = "LiC6" if p.cathode == "LCO" else "LiC6_NMC"
-    lco = p.cathode == "LCO"
+    anode, ocv_p, ocv_n, d_eff, k_eff = {
+        "LCO": ("LiC6", "OCV_LCO", "OCV_LiC6", "D_eff_linear", "K_eff"),
+        "NMC": ("LiC6_NMC", "OCV_NMC", "OCV_LiC6_NMC", "D_eff", "K_eff"),
+        # (the OCVs of this set are closures named OCV_NMC / OCV_LiC6 inside NMC_LGM50 / LiC6_LGM50, params.jl:557, 632)
+        "NMC_LGM50": ("LiC6_LGM50", "OCV_NMC", "OCV_LiC6", "D_eff_LGM50", "K_eff_LGM50")}[p.cathode]
     fields = [str(nm.temperature).lower(), nm.solid_diffusion, nm.Fickian_method, "SEI" if nm.aging else "false",
-              nm.rxn_p, nm.rxn_n, "OCV_LCO" if lco else "OCV_NMC", "OCV_LiC6" if lco else "OCV_LiC6_NMC", "D_s_eff", "rxn_rate",
-              "D_eff_linear" if lco else "D_eff", "K_eff", "thermodynamic_factor_linear", nm.jacobian,
+              nm.rxn_p, nm.rxn_n, ocv_p, ocv_n, "D_s_eff", "rxn_rate", d_eff, k_eff, "thermodynamic_factor_linear", nm.jacobian,
               f"Np{N.p}", f"Ns{N.s}", f"Nn{N.n}", f"Na{N.a}_Nz{N.z}" if nm.temperature else "",
               f"Nr_p{N.r_p}_Nr_n{N.r_n}" if nm.solid_diffusion == "Fickian" else ""]
     return f"{p.cathode}_{anode}/" + hashlib.sha1("_".join(fields).encode()).hexdigest()
@@ -319,13 +321,18 @@ class Solution:
         return self.states[system, :self.n_points[system], p.ind[name]]
 
 
-def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10, temperature=False,
+def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10, temperature=None,
             solid_diffusion="Fickian", Fickian_method="finite_difference", aging=False, jacobian="symbolic",
             rxn_p="rxn_BV", rxn_n="rxn_BV", device=0, devices=None):
     """petlion(cathode; kwargs...) -- src/external.jl:2-18, src/params.jl:119-174.
     rxn_p / rxn_n: "rxn_BV" (default) or "rxn_MHC" (custom_functions.jl:212-298), per electrode."""
     if cathode not in CATHODES:
         raise ValueError(f"unknown cathode {cathode!r}; built: {list(CATHODES)}")
+    if temperature is None:
+        # system_LCO_LiC6 / system_NMC_LiC6 default to temperature = false, system_LGM50_NMC_LiC6 to true (params.jl:139, 686).
+        # (That system's default aging = :stress has no implementation in the reference -- its first stop check throws a
+        #  MethodError, checks.jl:204-206 -- so `aging` defaults to false here for every parameter set.)
+        temperature = cathode == "NMC_LGM50"
     if solid_diffusion != "Fickian" or Fickian_method != "finite_difference":
         raise NotImplementedError("only solid_diffusion=:Fickian, Fickian_method=:finite_difference is built")
     if jacobian not in ("symbolic", "AD"):

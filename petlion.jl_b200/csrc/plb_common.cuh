@@ -16,7 +16,8 @@ constexpr double kR = 8.31446261815324;  // const_Ideal_Gas, structures.jl:11
 constexpr double kTref = 298.15;
 constexpr unsigned FULL = 0xffffffffu;
 
-enum { CHEM_LCO = 0, CHEM_NMC = 1 };
+enum { CHEM_LCO = 0, CHEM_NMC = 1,
+       CHEM_LGM = 2 /* NMC_LGM50 / LiC6_LGM50 (params.jl:514-849): compiled in sibling builds only (plb_variant_{iso,th}lgm.cu) */ };
 // control row (scalar_residual.jl:167-202): applied current / voltage / power, and the constant-temperature
 // mode dT (input_methods.jl:182-189): val - temperature_weighting(Y'[T]).  METHOD_DT_ALG is the same row as
 // newtons_method! sees it, with Y'_T replaced by the right-hand side of the T rows (scalar_residual.jl:347-363).
@@ -46,6 +47,8 @@ enum ThetaField {
     TF_M_n, TF_R_SEI, TF_Uref_s, TF_i_0_jside, TF_k_n_aging, TF_w,
     // rxn_MHC (params.jl:16, 67)
     TF_lambda_MHC_n, TF_lambda_MHC_p,
+    // NMC_LGM50: scale of D_eff_LGM50 (params.jl:648, 714)
+    TF_D_e,
     TF_COUNT
 };
 
@@ -183,6 +186,8 @@ PLB_DECLARE_VARIANT(wthsei)
 PLB_DECLARE_VARIANT(isomhc)
 PLB_DECLARE_VARIANT(thmhc)
 PLB_DECLARE_VARIANT(seimhc)
+PLB_DECLARE_VARIANT(isolgm)
+PLB_DECLARE_VARIANT(thlgm)
 PLB_DECLARE_VARIANT(isodc)
 PLB_DECLARE_VARIANT(widedc)
 

@@ -574,11 +574,20 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
     const double ce = ro.act ? y.ce : 1000.0;
     {
         const double pb = C.sec[SC_pb][s];
-        if (TH) { laws::K_eff_T(ce, T, K, dK, dKT); dKT *= pb; }
-        else laws::K_eff(ce, T, K, dK);
-        K *= pb; dK *= pb;
-        if (CHEM == CHEM_LCO) { D = C.sec[SC_Dlin][s]; dD = 0.0; }   // D_eff_linear
-        else { laws::D_eff_nl(ce, T, D, dD); D *= pb; dD *= pb; }
+        if (CHEM == CHEM_LGM) {
+            // K_eff_LGM50, D_eff_LGM50 (params.jl:648-672): functions of c_e only
+            laws::K_eff_LGM50(ce, sqrt(fmax(ce, 0.0) * 1e-3), K, dK);
+            K *= pb; dK *= pb;
+            laws::D_eff_LGM50(ce, D, dD);
+            const double De = C.theta[TF_D_e] * pb;
+            D *= De; dD *= De;
+        } else {
+            if (TH) { laws::K_eff_T(ce, T, K, dK, dKT); dKT *= pb; }
+            else laws::K_eff(ce, T, K, dK);
+            K *= pb; dK *= pb;
+            if (CHEM == CHEM_LCO) { D = C.sec[SC_Dlin][s]; dD = 0.0; }   // D_eff_linear
+            else { laws::D_eff_nl(ce, T, D, dD); D *= pb; dD *= pb; }
+        }
     }
     // ---- face x|x+1 (owned by lane x): harmonic means and fluxes ---------------------------------
     const double ceR = shfl_dn(ce), peR = shfl_dn(y.pe), KR = shfl_dn(K), dKR = shfl_dn(dK),
@@ -674,6 +683,9 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
                 if (ro.sec == 0) laws::OCV_LCO_U(th, U, dU);
                 else laws::OCV_LiC6_U(th, sq, U, dU);
             }
+        } else if (CHEM == CHEM_LGM) {
+            if (ro.sec == 0) laws::OCV_NMC811(th, U, dU);           // (no entropic term: dU/dT = 0, params.jl:564, 637)
+            else laws::OCV_LiC6_LGM50(th, U, dU);
         } else {
             if (ro.sec == 0) laws::OCV_NMC(th, U, dU);
             else laws::OCV_LiC6_NMC(th, U, dU);

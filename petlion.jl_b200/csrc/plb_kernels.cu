@@ -35,54 +35,55 @@ constexpr int NR_HOST = 10;   // N_r of the built variants (laws::NR)
         if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-struct KeyDef { const char* utf8; const char* ascii; int field; double lco, nmc; int only; };   // only: bit 0 thermal, bit 1 aging, bit 2 / 3 rxn_p / rxn_n = rxn_MHC (0: always)
+struct KeyDef { const char* utf8; const char* ascii; int field; double lco, nmc, lgm; int only; };   // only: bit 0 thermal, bit 1 aging, bit 2 / 3 rxn_p / rxn_n = rxn_MHC (0: always)
 // reference keys (UTF-8) <-> canonical fields, with the defaults of src/params.jl:5-117,177-226 (LCO)
-// and :295-367, 428-445 (NMC).  nmc = NaN: key not part of the NMC parameter set.  The table is in the
+// and :295-367, 428-445 (NMC), :514-745 (lgm: NMC_LGM50 / LiC6_LGM50).  NaN: key not part of that parameter set.  The table is in the
 // reference's key order (Symbols sorted by code point); `only` marks the keys that the generated functions
 // use only when temperature = true (bit 0) and/or aging = :SEI (bit 1).
 static const double NA = NAN;
 static const KeyDef KEYS[] = {
-    {"Cp_a", "Cp_a", TF_Cp_a, 897.0, NA, 1}, {"Cp_n", "Cp_n", TF_Cp_n, 700.0, NA, 1}, {"Cp_p", "Cp_p", TF_Cp_p, 700.0, NA, 1},
-    {"Cp_s", "Cp_s", TF_Cp_s, 700.0, NA, 1}, {"Cp_z", "Cp_z", TF_Cp_z, 385.0, NA, 1},
-    {"D_n", "D_n", TF_D_n, 7.5e-10, NA, 0}, {"D_p", "D_p", TF_D_p, 7.5e-10, NA, 0}, {"D_s", "D_s", TF_D_s, 7.5e-10, NA, 0},
-    {"D_sn", "D_sn", TF_D_sn, 3.9e-14, 1.5e-14, 0}, {"D_sp", "D_sp", TF_D_sp, 1e-14, 2e-14, 0},
-    {"Ea_D_sn", "Ea_D_sn", TF_Ea_D_sn, 5000.0, 4e4, 0}, {"Ea_D_sp", "Ea_D_sp", TF_Ea_D_sp, 5000.0, 2.5e4, 0},
-    {"Ea_k_n", "Ea_k_n", TF_Ea_k_n, 5000.0, 3e4, 0}, {"Ea_k_p", "Ea_k_p", TF_Ea_k_p, 5000.0, 3e4, 0},
-    {"M_n", "M_n", TF_M_n, 7.3e-4, NA, 2}, {"R_SEI", "R_SEI", TF_R_SEI, 0.01, NA, 2},
-    {"Rp_n", "Rp_n", TF_Rp_n, 2e-6, 10e-6, 0}, {"Rp_p", "Rp_p", TF_Rp_p, 2e-6, 7.5e-6, 0},
-    {"T_amb", "T_amb", TF_T_amb, 25 + 273.15, NA, 1},
-    {"T\xe2\x82\x80", "T0", TF_T0, 25 + 273.15, 25 + 273.15, 0},
-    {"Uref_s", "Uref_s", TF_Uref_s, 0.4, NA, 2},
-    {"brugg_n", "brugg_n", TF_brugg_n, 4.0, 1.5, 0}, {"brugg_p", "brugg_p", TF_brugg_p, 4.0, 1.5, 0},
-    {"brugg_s", "brugg_s", TF_brugg_s, 4.0, 1.5, 0},
-    {"c_e\xe2\x82\x80", "c_e0", TF_c_e0, 1000.0, 1200.0, 0},
-    {"c_max_n", "c_max_n", TF_c_max_n, 30555.0, 31080.0, 0}, {"c_max_p", "c_max_p", TF_c_max_p, 51554.0, 51830.0, 0},
-    {"h_cell", "h_cell", TF_h_cell, 1.0, NA, 1},
-    {"i_0_jside", "i_0_jside", TF_i_0_jside, 1.5e-6, NA, 2},
-    {"k_n", "k_n", TF_k_n, 5.0310e-11, 6.3466e-10, 0}, {"k_n_aging", "k_n_aging", TF_k_n_aging, 1.0, NA, 2},
-    {"k_p", "k_p", TF_k_p, 2.334e-11, 6.3066e-10, 0},
-    {"l_a", "l_a", TF_l_a, 10e-6, NA, 1},
-    {"l_n", "l_n", TF_l_n, 88e-6, 48e-6, 0}, {"l_p", "l_p", TF_l_p, 80e-6, 41.6e-6, 0}, {"l_s", "l_s", TF_l_s, 25e-6, 25e-6, 0},
-    {"l_z", "l_z", TF_l_z, 10e-6, NA, 1},
-    {"t\xe2\x82\x8a", "t_plus", TF_t_plus, 0.364, 0.38, 0},
-    {"w", "w", TF_w, 2.0, NA, 2},
-    {"\xce\xb8_max_n", "theta_max_n", TF_theta_max_n, 0.85510, 0.790813, 0},
-    {"\xce\xb8_max_p", "theta_max_p", TF_theta_max_p, 0.49550, 0.359749, 0},
-    {"\xce\xb8_min_n", "theta_min_n", TF_theta_min_n, 0.01429, 0.001, 0},
-    {"\xce\xb8_min_p", "theta_min_p", TF_theta_min_p, 0.99174, 0.955473, 0},
-    {"\xce\xbb_MHC_n", "lambda_MHC_n", TF_lambda_MHC_n, 6.26e-20, NA, 8}, {"\xce\xbb_MHC_p", "lambda_MHC_p", TF_lambda_MHC_p, 6.26e-20, NA, 4},
-    {"\xce\xbb_a", "lambda_a", TF_lambda_a, 237.0, NA, 1}, {"\xce\xbb_n", "lambda_n", TF_lambda_n, 1.7, NA, 1},
-    {"\xce\xbb_p", "lambda_p", TF_lambda_p, 2.1, NA, 1}, {"\xce\xbb_s", "lambda_s", TF_lambda_s, 0.16, NA, 1},
-    {"\xce\xbb_z", "lambda_z", TF_lambda_z, 401.0, NA, 1},
-    {"\xcf\x81_a", "rho_a", TF_rho_a, 2700.0, NA, 1}, {"\xcf\x81_n", "rho_n", TF_rho_n, 2500.0, NA, 3},
-    {"\xcf\x81_p", "rho_p", TF_rho_p, 2500.0, NA, 1}, {"\xcf\x81_s", "rho_s", TF_rho_s, 1100.0, NA, 1},
-    {"\xcf\x81_z", "rho_z", TF_rho_z, 8940.0, NA, 1},
-    {"\xcf\x83_a", "sigma_a", TF_sigma_a, 3.55e7, NA, 1},
-    {"\xcf\x83_n", "sigma_n", TF_sigma_n, 100.0, 100.0, 0}, {"\xcf\x83_p", "sigma_p", TF_sigma_p, 100.0, 100.0, 0},
-    {"\xcf\x83_z", "sigma_z", TF_sigma_z, 5.96e7, NA, 1},
-    {"\xcf\xb5_fn", "eps_fn", TF_eps_fn, 0.0326, 0.038, 0}, {"\xcf\xb5_fp", "eps_fp", TF_eps_fp, 0.025, 0.12, 0},
-    {"\xcf\xb5_n", "eps_n", TF_eps_n, 0.485, 0.3, 0}, {"\xcf\xb5_p", "eps_p", TF_eps_p, 0.385, 0.3, 0},
-    {"\xcf\xb5_s", "eps_s", TF_eps_s, 0.724, 0.4, 0},
+    {"Cp_a", "Cp_a", TF_Cp_a, 897.0, NA, 897.0, 1}, {"Cp_n", "Cp_n", TF_Cp_n, 700.0, NA, 700.0, 1}, {"Cp_p", "Cp_p", TF_Cp_p, 700.0, NA, 700.0, 1},
+    {"Cp_s", "Cp_s", TF_Cp_s, 700.0, NA, 700.0, 1}, {"Cp_z", "Cp_z", TF_Cp_z, 385.0, NA, 385.0, 1},
+    {"D_e", "D_e", TF_D_e, NA, NA, 8.794e-11, 0},
+    {"D_n", "D_n", TF_D_n, 7.5e-10, NA, NA, 0}, {"D_p", "D_p", TF_D_p, 7.5e-10, NA, NA, 0}, {"D_s", "D_s", TF_D_s, 7.5e-10, NA, NA, 0},
+    {"D_sn", "D_sn", TF_D_sn, 3.9e-14, 1.5e-14, 3.3e-14, 0}, {"D_sp", "D_sp", TF_D_sp, 1e-14, 2e-14, 4e-15, 0},
+    {"Ea_D_sn", "Ea_D_sn", TF_Ea_D_sn, 5000.0, 4e4, 3.03e4, 0}, {"Ea_D_sp", "Ea_D_sp", TF_Ea_D_sp, 5000.0, 2.5e4, 0.0, 0},
+    {"Ea_k_n", "Ea_k_n", TF_Ea_k_n, 5000.0, 3e4, 35000.0, 0}, {"Ea_k_p", "Ea_k_p", TF_Ea_k_p, 5000.0, 3e4, 17800.0, 0},
+    {"M_n", "M_n", TF_M_n, 7.3e-4, NA, NA, 2}, {"R_SEI", "R_SEI", TF_R_SEI, 0.01, NA, NA, 2},
+    {"Rp_n", "Rp_n", TF_Rp_n, 2e-6, 10e-6, 5.86e-6, 0}, {"Rp_p", "Rp_p", TF_Rp_p, 2e-6, 7.5e-6, 5.22e-06, 0},
+    {"T_amb", "T_amb", TF_T_amb, 25 + 273.15, NA, 25 + 273.15, 1},
+    {"T\xe2\x82\x80", "T0", TF_T0, 25 + 273.15, 25 + 273.15, 25 + 273.15, 0},
+    {"Uref_s", "Uref_s", TF_Uref_s, 0.4, NA, NA, 2},
+    {"brugg_n", "brugg_n", TF_brugg_n, 4.0, 1.5, 1.5, 0}, {"brugg_p", "brugg_p", TF_brugg_p, 4.0, 1.5, 1.5, 0},
+    {"brugg_s", "brugg_s", TF_brugg_s, 4.0, 1.5, 1.5, 0},
+    {"c_e\xe2\x82\x80", "c_e0", TF_c_e0, 1000.0, 1200.0, 1000.0, 0},
+    {"c_max_n", "c_max_n", TF_c_max_n, 30555.0, 31080.0, 33133.0, 0}, {"c_max_p", "c_max_p", TF_c_max_p, 51554.0, 51830.0, 63104.0, 0},
+    {"h_cell", "h_cell", TF_h_cell, 1.0, NA, 1.0, 1},
+    {"i_0_jside", "i_0_jside", TF_i_0_jside, 1.5e-6, NA, NA, 2},
+    {"k_n", "k_n", TF_k_n, 5.0310e-11, 6.3466e-10, 6.716046737258585e-12, 0}, {"k_n_aging", "k_n_aging", TF_k_n_aging, 1.0, NA, NA, 2},
+    {"k_p", "k_p", TF_k_p, 2.334e-11, 6.3066e-10, 3.5445802224420315e-11, 0},
+    {"l_a", "l_a", TF_l_a, 10e-6, NA, 16e-6, 1},
+    {"l_n", "l_n", TF_l_n, 88e-6, 48e-6, 85.2e-6, 0}, {"l_p", "l_p", TF_l_p, 80e-6, 41.6e-6, 75.6e-6, 0}, {"l_s", "l_s", TF_l_s, 25e-6, 25e-6, 12e-6, 0},
+    {"l_z", "l_z", TF_l_z, 10e-6, NA, 12e-6, 1},
+    {"t\xe2\x82\x8a", "t_plus", TF_t_plus, 0.364, 0.38, 0.2594, 0},
+    {"w", "w", TF_w, 2.0, NA, NA, 2},
+    {"\xce\xb8_max_n", "theta_max_n", TF_theta_max_n, 0.85510, 0.790813, 29866.0 / 33133, 0},
+    {"\xce\xb8_max_p", "theta_max_p", TF_theta_max_p, 0.49550, 0.359749, 17038.0 / 63104.0, 0},
+    {"\xce\xb8_min_n", "theta_min_n", TF_theta_min_n, 0.01429, 0.001, 0.0481727, 0},
+    {"\xce\xb8_min_p", "theta_min_p", TF_theta_min_p, 0.99174, 0.955473, 0.8395, 0},
+    {"\xce\xbb_MHC_n", "lambda_MHC_n", TF_lambda_MHC_n, 6.26e-20, NA, 0.0, 8}, {"\xce\xbb_MHC_p", "lambda_MHC_p", TF_lambda_MHC_p, 6.26e-20, NA, 0.0, 4},
+    {"\xce\xbb_a", "lambda_a", TF_lambda_a, 237.0, NA, 237.0, 1}, {"\xce\xbb_n", "lambda_n", TF_lambda_n, 1.7, NA, 1.7, 1},
+    {"\xce\xbb_p", "lambda_p", TF_lambda_p, 2.1, NA, 2.1, 1}, {"\xce\xbb_s", "lambda_s", TF_lambda_s, 0.16, NA, 0.16, 1},
+    {"\xce\xbb_z", "lambda_z", TF_lambda_z, 401.0, NA, 401.0, 1},
+    {"\xcf\x81_a", "rho_a", TF_rho_a, 2700.0, NA, 2700.0, 1}, {"\xcf\x81_n", "rho_n", TF_rho_n, 2500.0, NA, 1657.0, 3},
+    {"\xcf\x81_p", "rho_p", TF_rho_p, 2500.0, NA, 3262.0, 1}, {"\xcf\x81_s", "rho_s", TF_rho_s, 1100.0, NA, 397.0, 1},
+    {"\xcf\x81_z", "rho_z", TF_rho_z, 8940.0, NA, 8960.0, 1},
+    {"\xcf\x83_a", "sigma_a", TF_sigma_a, 3.55e7, NA, 36.914e6, 1},
+    {"\xcf\x83_n", "sigma_n", TF_sigma_n, 100.0, 100.0, 215.0, 0}, {"\xcf\x83_p", "sigma_p", TF_sigma_p, 100.0, 100.0, 0.18, 0},
+    {"\xcf\x83_z", "sigma_z", TF_sigma_z, 5.96e7, NA, 58.41e6, 1},
+    {"\xcf\xb5_fn", "eps_fn", TF_eps_fn, 0.0326, 0.038, 0.0, 0}, {"\xcf\xb5_fp", "eps_fp", TF_eps_fp, 0.025, 0.12, 0.0, 0},
+    {"\xcf\xb5_n", "eps_n", TF_eps_n, 0.485, 0.3, 0.25, 0}, {"\xcf\xb5_p", "eps_p", TF_eps_p, 0.385, 0.3, 0.335, 0},
+    {"\xcf\xb5_s", "eps_s", TF_eps_s, 0.724, 0.4, 0.47, 0},
 };
 
 // one compiled model family
@@ -119,6 +120,8 @@ static const Variant V_WTHSEI = {wthsei::info, wthsei::slot_rc, wthsei::slot_rec
 
 // the 32-node families with rxn_MHC compiled in (used by models that select it)
 #define PLB_VARIANT_TABLE(NS) {NS::info, NS::slot_rc, NS::slot_recipe, NS::launch_resjac, NS::launch_initguess, NS::launch_newton, NS::launch_linsolve, NS::launch_simulate}
+static const Variant V_ISOLGM = PLB_VARIANT_TABLE(isolgm);      // NMC_LGM50 chemistry (its own instantiation of the iso / th families)
+static const Variant V_THLGM = PLB_VARIANT_TABLE(thlgm);
 static const Variant V_ISOMHC = PLB_VARIANT_TABLE(isomhc);
 static const Variant V_THMHC = PLB_VARIANT_TABLE(thmhc);
 static const Variant V_SEIMHC = PLB_VARIANT_TABLE(seimhc);
@@ -227,15 +230,17 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     const int Nx_ = d->N_p + d->N_s + d->N_n;
     if (d->N_p < 2 || d->N_s < 2 || d->N_n < 2 || Nx_ > 64)
         return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 64 (one lane per node, one or two warps per system)");
-    if (d->cathode != PLB_CATHODE_LCO && d->cathode != PLB_CATHODE_NMC) return fail("plb_create: unknown cathode");
+    if (d->cathode != PLB_CATHODE_LCO && d->cathode != PLB_CATHODE_NMC && d->cathode != PLB_CATHODE_NMC_LGM50) return fail("plb_create: unknown cathode");
+    const bool lgm = d->cathode == PLB_CATHODE_NMC_LGM50;
+    if (lgm && Nx_ > 32) return fail("plb_create: NMC_LGM50 is built for grids of up to 32 x-nodes");
     if ((d->rxn_p != PLB_RXN_BV && d->rxn_p != PLB_RXN_MHC) || (d->rxn_n != PLB_RXN_BV && d->rxn_n != PLB_RXN_MHC))
         return fail("plb_create: unknown reaction rate law (built: rxn_BV, rxn_MHC)");
     // NMC() / LiC6_NMC() define no lambda_MHC_* (params.jl:295-367): the reference throws a KeyError there
     if ((d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) && d->cathode != PLB_CATHODE_LCO)
-        return fail("plb_create: rxn_MHC needs the LCO parameter set (the NMC set has no lambda_MHC_p / lambda_MHC_n)");
+        return fail("plb_create: rxn_MHC is built for the LCO parameter set (the NMC set has no lambda_MHC_p / lambda_MHC_n, NMC_LGM50 sets them to 0)");
     if (d->temperature) {
         // NMC()/LiC6_NMC() carry no thermal parameters (params.jl:295-367): the reference cannot build it either
-        if (d->cathode != PLB_CATHODE_LCO) return fail("plb_create: temperature=true needs the LCO parameter set");
+        if (d->cathode == PLB_CATHODE_NMC) return fail("plb_create: temperature=true needs the LCO or NMC_LGM50 parameter set");
         if (d->N_p < 5 || d->N_n < 5) return fail("plb_create: temperature=true needs N_p, N_n >= 5");
         if (d->N_a < 1 || d->N_z < 1 || d->N_a + d->N_z > d->N_p + d->N_s + d->N_n)
             return fail("plb_create: temperature=true needs 1 <= N_a, N_z and N_a+N_z <= N_p+N_s+N_n (one collector node per lane)");
@@ -265,6 +270,8 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
     h->v = both ? (wide ? &V_WTHSEI : &V_THSEI)
                 : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
+    if (lgm) h->v = h->v == &V_ISO ? &V_ISOLGM : (h->v == &V_TH ? &V_THLGM : nullptr);
+    if (!h->v) { delete h; return fail("plb_create: NMC_LGM50 is built for the isothermal and thermal families on up to 32 x-nodes"); }
     if (d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) {
         const Variant* mv = h->v == &V_ISO ? &V_ISOMHC : (h->v == &V_TH ? &V_THMHC : (h->v == &V_SEI ? &V_SEIMHC : nullptr));
         if (!mv) {
@@ -287,7 +294,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     m.thermal = d->temperature ? 1 : 0;
     m.aging = d->aging ? 1 : 0;
     m.Na = m.thermal ? d->N_a : 0; m.Nz = m.thermal ? d->N_z : 0;
-    m.chem = d->cathode == PLB_CATHODE_LCO ? CHEM_LCO : CHEM_NMC;
+    m.chem = d->cathode == PLB_CATHODE_LCO ? CHEM_LCO : (lgm ? CHEM_LGM : CHEM_NMC);
     m.rxn_mhc = (d->rxn_p == PLB_RXN_MHC ? 1 : 0) | (d->rxn_n == PLB_RXN_MHC ? 2 : 0);
     m.mid = m.thermal ? m.Np + m.Ns / 2 : m.Nx / 2;
     m.inv_n[0] = 1.0 / m.Np; m.inv_n[1] = 1.0 / m.Ns; m.inv_n[2] = 1.0 / m.Nn; m.inv_n[3] = 0.0;
@@ -323,7 +330,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     for (int f = 0; f < TF_COUNT; f++) m.slot[f] = -1;
     // used keys in the reference's (code-point sorted) order; KEYS[] is already sorted that way
     for (int k = 0; k < (int)(sizeof(KEYS) / sizeof(KEYS[0])); k++) {
-        const double dv = d->cathode == PLB_CATHODE_LCO ? KEYS[k].lco : KEYS[k].nmc;
+        const double dv = d->cathode == PLB_CATHODE_LCO ? KEYS[k].lco : (d->cathode == PLB_CATHODE_NMC_LGM50 ? KEYS[k].lgm : KEYS[k].nmc);
         if (dv != dv) continue;
         if (KEYS[k].only && !((KEYS[k].only & 1) && m.thermal) && !((KEYS[k].only & 2) && m.aging) &&
             !((KEYS[k].only & 4) && (m.rxn_mhc & 1)) && !((KEYS[k].only & 8) && (m.rxn_mhc & 2))) continue;
@@ -387,7 +394,8 @@ int plb_theta_index(plb_handle h, const char* key) {
 int plb_theta_defaults(plb_handle h, double* row) {
     if (!h || !row) return fail("plb_theta_defaults: null argument");
     for (size_t i = 0; i < h->keys.size(); i++)
-        row[i] = h->desc.cathode == PLB_CATHODE_LCO ? KEYS[h->keys[i]].lco : KEYS[h->keys[i]].nmc;
+        row[i] = h->desc.cathode == PLB_CATHODE_LCO ? KEYS[h->keys[i]].lco
+                 : (h->desc.cathode == PLB_CATHODE_NMC_LGM50 ? KEYS[h->keys[i]].lgm : KEYS[h->keys[i]].nmc);
     return 0;
 }
 int plb_bounds_defaults(plb_handle h, plb_bounds* b) {
@@ -395,6 +403,7 @@ int plb_bounds_defaults(plb_handle h, plb_bounds* b) {
     // src/params.jl:233-253 (LCO), :451-471 (NMC)
     const double nan_ = NAN;
     if (h->desc.cathode == PLB_CATHODE_LCO) { b->V_min = 2.5; b->V_max = 4.3; b->T_max = 55 + 273.15; }
+    else if (h->desc.cathode == PLB_CATHODE_NMC_LGM50) { b->V_min = 2.5; b->V_max = 4.2; b->T_max = 55 + 273.15; }   // params.jl:760-773
     else { b->V_min = 2.8; b->V_max = 4.2; b->T_max = nan_; }
     b->SOC_min = 0.0; b->SOC_max = 1.0; b->c_s_n_max = nan_; b->I_max = nan_; b->I_min = nan_;
     b->eta_plating_min = nan_; b->c_e_min = nan_; b->dfilm_max = nan_;

@@ -602,6 +602,9 @@ __device__ PLB_COLD void fetch_and_setup(const SimArgs& a, WarpWS& w, const Lane
                 if (ro.sec == 0) laws::OCV_LCO(thx, U, dU, dUdT, ddUdT);
                 else laws::OCV_LiC6(thx, sqrt(fmax(thx, 1e-4)), U, dU, dUdT, ddUdT);
                 if (w.C.g[GC_dUdT_on] != 0.0) U += dUdT * (w.C.g[GC_T] - kTref);
+            } else if (CHEM == CHEM_LGM) {
+                if (ro.sec == 0) laws::OCV_NMC811(thx, U, dU);
+                else laws::OCV_LiC6_LGM50(thx, U, dU);
             } else {
                 if (ro.sec == 0) laws::OCV_NMC(thx, U, dU);
                 else laws::OCV_LiC6_NMC(thx, U, dU);

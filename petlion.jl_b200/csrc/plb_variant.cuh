@@ -716,6 +716,9 @@ __device__ __forceinline__ void initial_lane(const ModelDesc& m, const WarpConst
             if (ro.sec == 0) laws::OCV_LCO(thx, U, dU, dUdT, ddUdT);
             else laws::OCV_LiC6(thx, sqrt(fmax(thx, 1e-4)), U, dU, dUdT, ddUdT);
             if (C.g[GC_dUdT_on] != 0.0) U += dUdT * (C.g[GC_T] - kTref);
+        } else if (CHEM == CHEM_LGM) {
+            if (ro.sec == 0) laws::OCV_NMC811(thx, U, dU);
+            else laws::OCV_LiC6_LGM50(thx, U, dU);
         } else {
             if (ro.sec == 0) laws::OCV_NMC(thx, U, dU);
             else laws::OCV_LiC6_NMC(thx, U, dU);
@@ -833,6 +836,17 @@ VariantInfo info() {
     return v;
 }
 
+#ifdef PLB_ONLY_CHEM
+// sibling build of one more chemistry: only that instantiation exists here
+#define PLB_LAUNCH(KERNEL, ARGS, GRID, BLOCK, SMEM, STREAM)                                                         \
+    do {                                                                                                            \
+        if ((ARGS).m.chem != PLB_ONLY_CHEM) return cudaErrorInvalidValue;                                           \
+        cudaError_t e_ = cudaFuncSetAttribute(KERNEL<PLB_ONLY_CHEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
+        if (e_ != cudaSuccess) return e_;                                                                           \
+        KERNEL<PLB_ONLY_CHEM><<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(ARGS);                                         \
+        return cudaGetLastError();                                                                                  \
+    } while (0)
+#else
 #define PLB_LAUNCH(KERNEL, ARGS, GRID, BLOCK, SMEM, STREAM)                                                         \
     do {                                                                                                            \
         cudaError_t e_;                                                                                             \
@@ -848,6 +862,7 @@ VariantInfo info() {
         }                                                                                                           \
         return cudaGetLastError();                                                                                  \
     } while (0)
+#endif
 
 cudaError_t launch_resjac(const ResJacArgs& a, int grid, cudaStream_t s) {
 #if !PLB_WIDE && !PLB_TH

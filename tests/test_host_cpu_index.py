@@ -61,7 +61,7 @@ def test_unsupported_model_options_are_refused_with_a_message(kw, msg):
 
 def test_nmc_has_no_thermal_or_aging_parameters():
     import petlion_b200
-    with pytest.raises(RuntimeError, match="LCO parameter set"):
+    with pytest.raises(RuntimeError, match="LCO or NMC_LGM50 parameter set"):
         petlion_b200.petlion("NMC", temperature=True)
     with pytest.raises(RuntimeError, match="LCO parameter set"):
         petlion_b200.petlion("NMC", aging="SEI")
