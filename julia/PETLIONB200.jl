@@ -45,8 +45,9 @@ check(rc) = rc == 0 || error(unsafe_string(ccall((:plb_last_error, lib), Cstring
 
 # ---- model handle: petlion(...) (src/external.jl:2-18) ------------------------------------------------------------
 rxn_code(f) = Symbol(f) === :rxn_MHC ? 1 : 0
+cathode_code(c::Symbol) = c === :LCO ? 0 : (c === :NMC_LGM50 ? 2 : 1)          # PLB_CATHODE_*
 function create(cathode::Symbol, N, temperature::Bool, aging; device::Integer = 0, rxn_p = :rxn_BV, rxn_n = :rxn_BV)::Ptr{Cvoid}
-    d = ModelDesc(cathode === :LCO ? 0 : 1, N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, device,
+    d = ModelDesc(cathode_code(cathode), N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, device,
                   rxn_code(rxn_p), rxn_code(rxn_n))
     h = Ref{Ptr{Cvoid}}()
     check(ccall((:plb_create, lib), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}), d, h))
@@ -156,7 +157,7 @@ end
 
 # ---- several GPUs of the box behind one call (contiguous batch shards, one ncclAllGather of the summaries) --------
 function group_create(cathode::Symbol, N, temperature::Bool, aging, devices::Vector{<:Integer}; rxn_p = :rxn_BV, rxn_n = :rxn_BV)::Ptr{Cvoid}
-    d = ModelDesc(cathode === :LCO ? 0 : 1, N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, 0,
+    d = ModelDesc(cathode_code(cathode), N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, 0,
                   rxn_code(rxn_p), rxn_code(rxn_n))
     g = Ref{Ptr{Cvoid}}()
     check(ccall((:plb_group_create, lib), Cint, (Ref{ModelDesc}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), d, length(devices), Cint.(devices), g))

@@ -20,7 +20,7 @@ SAN_FAMILIES=iso compute-sanitizer --tool racecheck python profiles/sanitize_dri
 SAN_FAMILIES=thsei compute-sanitizer --tool racecheck python profiles/sanitize_driver.py 2>&1 | tail -3 > gpurun_out/rz_racecheck_thsei.txt
 SAN_FAMILIES=wide compute-sanitizer --tool racecheck python profiles/sanitize_driver.py > gpurun_out/rz_racecheck_wide_full.txt 2>&1
 SAN_FAMILIES=iso compute-sanitizer --tool synccheck python profiles/sanitize_driver.py 2>&1 | tail -4 > gpurun_out/rz_synccheck.txt
-for f in iso thermal sei wide wsei wth thsei wthsei mhc; do python profiles/k4_probe.py 16384 $f 2>&1 | tail -1; done > gpurun_out/rz_families.txt
+for f in iso thermal sei wide wsei wth thsei wthsei mhc lgm lgmth; do python profiles/k4_probe.py 16384 $f 2>&1 | tail -1; done > gpurun_out/rz_families.txt
 cat gpurun_out/rz_pytest.log; cat gpurun_out/rz_families.txt; tail -2 gpurun_out/rz_smoke.log
 for f in cfg2 cfg2_reference cfg3 cfg4 cfg5n10; do grep "^{" gpurun_out/rz_bench_$f.json | cut -c1-160; done
 grep -E "RACECHECK SUMMARY|ERROR SUMMARY" gpurun_out/rz_*check*.txt

@@ -1,5 +1,5 @@
 """Times the fused integrator (device-resident buffers, CUDA events) for the library named by PLB_LIB:
-quick A/B of build variants.  usage: PLB_LIB=... python profiles/k4_probe.py [B] [iso|thermal|sei|wide|wsei|wth|thsei|wthsei|mhc]
+quick A/B of build variants.  usage: PLB_LIB=... python profiles/k4_probe.py [B] [iso|thermal|sei|wide|wsei|wth|thsei|wthsei|mhc|lgm|lgmth]
 (one segment: a 1C discharge for iso / wide / mhc, a 4C charge to 4.1 V for the thermal families, a 1C charge to 4.2 V for
 the SEI families)"""
 import ctypes as C, os, sys
@@ -13,10 +13,10 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 fam = sys.argv[2] if len(sys.argv) > 2 else "iso"
 L = _lib.lib()
 grid = dict(N_p=20, N_s=20, N_n=20) if fam in ("wide", "wsei", "wth", "wthsei") else {}
-thermal = fam in ("thermal", "wth", "thsei", "wthsei")
+thermal = fam in ("thermal", "wth", "thsei", "wthsei", "lgmth")
 aging = fam in ("sei", "wsei", "thsei", "wthsei")
 rx = dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC") if fam == "mhc" else {}
-p = P.petlion("LCO", temperature=thermal, aging="SEI" if aging else False, **grid, **rx)
+p = P.petlion("NMC_LGM50" if fam.startswith("lgm") else "LCO", temperature=thermal, aging="SEI" if aging else False, **grid, **rx)
 
 h = p._h; N = p.N.tot
 dev = torch.device("cuda", 0); f64 = dict(dtype=torch.float64, device=dev)

@@ -6,13 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P
 
-fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc").split(",")
+fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc,lgm").split(",")
 for fam in fams:
     G = dict(N_p=20, N_s=20, N_n=20)
     kw = dict(iso={}, thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=G, wsei=dict(aging="SEI", **G),
               wth=dict(temperature=True, **G), thsei=dict(temperature=True, aging="SEI"),
-              wthsei=dict(temperature=True, aging="SEI", **G), mhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC"))[fam]
-    p = P.petlion("LCO", **kw)
+              wthsei=dict(temperature=True, aging="SEI", **G), mhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC"), lgm=dict(temperature=True))[fam]
+    p = P.petlion("NMC_LGM50" if fam == "lgm" else "LCO", **kw)
     B = 5
     p.θ["D_sp"] = np.asarray(p.θ["D_sp"]) * np.linspace(0.8, 1.2, B)
     sol = P.simulate(p, 200, I=1, SOC=0.1)                                             # plain kernel
