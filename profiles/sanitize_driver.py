@@ -24,7 +24,7 @@ for fam in fams:
     st, Y, YP = p.newton_init(Y0, method="I", value=1.0)
     res, nz = p.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)                  # K1 (TMA-staged where built)
     os.environ["PLB_K1_NO_TMA"] = "1"
-    p_old = P.petlion("LCO", **kw); p_old.θ["D_sp"] = p.θ["D_sp"]
+    p_old = P.petlion("NMC_LGM50" if fam == "lgm" else "LCO", **kw); p_old.θ["D_sp"] = p.θ["D_sp"]
     res_b, nz_b = p_old.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)           # K1, per-lane loads
     del os.environ["PLB_K1_NO_TMA"]
     assert np.array_equal(res, res_b) and np.array_equal(nz, nz_b)
