@@ -93,6 +93,93 @@ def poly_eval(coeffs, x):
     return sum(rat(c) * x**i for i, c in enumerate(coeffs))
 
 
+NR_BUILT = (10, 12, 14)
+
+
+def emit_particle_operator(out, n):
+    """MC (combined first/second-derivative stencil of a particle with n radial nodes), its structural mask and its
+    eigen-decomposition, inside namespace nr<n>."""
+    M1 = np.zeros((n, n)); M2 = np.zeros((n, n))
+    fb1 = np.array([[-109584.0, 322560, -564480, 752640, -705600, 451584, -188160, 46080, -5040],
+                    [-5040.0, -64224, 141120, -141120, 117600, -70560, 28224, -6720, 720],
+                    [720.0, -11520, -38304, 80640, -50400, 26880, -10080, 2304, -240],
+                    [-240.0, 2880, -20160, -18144, 50400, -20160, 6720, -1440, 144]])
+    mid1 = np.array([144.0, -1536, 8064, -32256, 0, 32256, -8064, 1536, -144])
+    lb1 = np.array([[-144.0, 1440, -6720, 20160, -50400, 18144, 20160, -2880, 240],
+                    [240.0, -2304, 10080, -26880, 50400, -80640, 38304, 11520, -720],
+                    [-720.0, 6720, -28224, 70560, -117600, 141120, -141120, 64224, 5040],
+                    [5040.0, -46080, 188160, -451584, 705600, -752640, 564480, -322560, 109584]])
+    M1[:4, :9] = fb1
+    for k, i in enumerate(range(4, n - 4)):
+        M1[i, k:k + 9] = mid1
+    M1[n - 4:, n - 9:] = lb1
+    fb2 = np.array([[-415 / 6, 96, -36, 32 / 3, -3 / 2, 0], [10.0, -15, -4, 14, -6, 1]])
+    mid2 = np.array([-1.0, 16, -30, 16, -1])
+    lb2 = np.array([[1.0, -6, 14, -4, -15, 10], [0.0, -3 / 2, 32 / 3, -36, 96, -415 / 6]])
+    M2[:2, :6] = fb2
+    for k, i in enumerate(range(2, n - 2)):
+        M2[i, k:k + 5] = mid2
+    M2[n - 2:, n - 6:] = lb2
+    dr = 1.0 / (n - 1)
+    c1 = 1.0 / (40320 * dr); c2 = 1.0 / (12 * dr * dr)
+    Mc = np.zeros((n, n))
+    Mc[0] = 3 * c2 * M2[0]
+    for r in range(1, n - 1):
+        rk = r / (n - 1)
+        Mc[r] = c2 * M2[r] + (2.0 / rk) * c1 * M1[r]
+    Mc[n - 1] = c2 * M2[n - 1]
+    bj = 50 * dr * c2 + 2.0  # multiplies d1_bc = -j*Rp/D_s in the surface row
+    # the structural pattern must not lose an entry to a floating-point cancellation of the two stencils
+    struct = (M1 != 0.0) | (M2 != 0.0)
+    struct[0] = M2[0] != 0.0; struct[n - 1] = M2[n - 1] != 0.0
+    assert np.array_equal(Mc != 0.0, struct), n
+    out.append(f"namespace nr{n} {{")
+    out.append(f"// combined Fickian operator for N_r = {n}:  rhs_cs = kappa*(MC*c_s + BJ*d1bc e_surf),  kappa = D_s/Rp^2")
+    out.append(f"constexpr int NR = {n};")
+    out.append("static __device__ __constant__ double MC[NR][NR] = {")
+    for r in range(n):
+        out.append("    {" + ", ".join(repr(float(v)) for v in Mc[r]) + "},")
+    out.append("};")
+    out.append(f"constexpr double BJ = {bj!r};")
+    # structural pattern of the particle block (which (r,c) are non-zero), as a bit mask per row
+    masks = [sum(1 << cc for cc in range(n) if Mc[r, cc] != 0.0) for r in range(n)]
+    out.append("__host__ __device__ constexpr unsigned mc_mask(int r) {\n    return " +
+               " ".join(f"r == {r} ? {hex(v)}u :" for r, v in enumerate(masks)) + " 0u;\n}")
+    # eigen-decomposition MC = EV diag(EL) EVI (real spectrum, cond(EV) ~ 60): with a node-dependent
+    # D_s(T) the particle block kappa_x*MC - cj*I is different at every node, but it is diagonal in
+    # this fixed basis, so no per-node factorisation is needed (thermal variant).
+    import mpmath as mp
+    mp.mp.dps = 60
+    A = mp.matrix(Mc.tolist())
+    E, ER = mp.eig(A)
+    assert all(abs(mp.im(e)) < mp.mpf(10) ** -40 for e in E), "particle operator has complex eigenvalues"
+    order = sorted(range(n), key=lambda i: float(mp.re(E[i])))
+    EV = mp.matrix(n, n)
+    for k, i in enumerate(order):
+        col = [mp.re(ER[r, i]) for r in range(n)]
+        nrm = mp.sqrt(sum(v * v for v in col))
+        for r in range(n):
+            EV[r, k] = col[r] / nrm
+    EVI = EV ** -1
+    EL = [mp.re(E[i]) for i in order]
+    if abs(EL[-1]) < mp.mpf(10) ** -30:
+        EL[-1] = mp.mpf(0)          # conservation: MC * 1 = 0 exactly
+    chk = max(abs((EV * mp.diag(EL) * EVI - A)[r, cc]) for r in range(n) for cc in range(n))
+    assert chk < mp.mpf(10) ** -40, chk
+
+    def arr(name, Mx):
+        out.append(f"static __device__ __constant__ double {name}[NR][NR] = {{")
+        for r in range(n):
+            out.append("    {" + ", ".join(repr(float(Mx[r, cc])) for cc in range(n)) + "},")
+        out.append("};")
+    out.append("// MC = EV * diag(EL) * EVI (mpmath, 60 digits, rounded to double)")
+    arr("EV", EV)
+    arr("EVI", EVI)
+    out.append("static __device__ __constant__ double EL[NR] = {" + ", ".join(repr(float(v)) for v in EL) + "};")
+    out.append(f"}}  // namespace nr{n}")
+    print("N_r", n, "particle nnz", sum(bin(v).count("1") for v in masks))
+
+
 def main():
     th, c, T = sp.symbols("th c T", real=True)
     out = []
@@ -205,84 +292,17 @@ def main():
     out.append(emit_fn("D_eff_LGM50", ["c"], [("D", D), ("dDdc", sp.diff(D, c))],
                        "D_eff_LGM50(c_e) / D_e and its c_e derivative  (params.jl:648)"))
 
-    # ---- Fickian particle operator (N_r = 10), numerical_tools.jl:8-87, residuals.jl:128-180
-    n = 10
-    M1 = np.zeros((n, n)); M2 = np.zeros((n, n))
-    fb1 = np.array([[-109584.0, 322560, -564480, 752640, -705600, 451584, -188160, 46080, -5040],
-                    [-5040.0, -64224, 141120, -141120, 117600, -70560, 28224, -6720, 720],
-                    [720.0, -11520, -38304, 80640, -50400, 26880, -10080, 2304, -240],
-                    [-240.0, 2880, -20160, -18144, 50400, -20160, 6720, -1440, 144]])
-    mid1 = np.array([144.0, -1536, 8064, -32256, 0, 32256, -8064, 1536, -144])
-    lb1 = np.array([[-144.0, 1440, -6720, 20160, -50400, 18144, 20160, -2880, 240],
-                    [240.0, -2304, 10080, -26880, 50400, -80640, 38304, 11520, -720],
-                    [-720.0, 6720, -28224, 70560, -117600, 141120, -141120, 64224, 5040],
-                    [5040.0, -46080, 188160, -451584, 705600, -752640, 564480, -322560, 109584]])
-    M1[:4, :9] = fb1
-    for k, i in enumerate(range(4, n - 4)):
-        M1[i, k:k + 9] = mid1
-    M1[n - 4:, n - 9:] = lb1
-    fb2 = np.array([[-415 / 6, 96, -36, 32 / 3, -3 / 2, 0], [10.0, -15, -4, 14, -6, 1]])
-    mid2 = np.array([-1.0, 16, -30, 16, -1])
-    lb2 = np.array([[1.0, -6, 14, -4, -15, 10], [0.0, -3 / 2, 32 / 3, -36, 96, -415 / 6]])
-    M2[:2, :6] = fb2
-    for k, i in enumerate(range(2, n - 2)):
-        M2[i, k:k + 5] = mid2
-    M2[n - 2:, n - 6:] = lb2
-    dr = 1.0 / (n - 1)
-    c1 = 1.0 / (40320 * dr); c2 = 1.0 / (12 * dr * dr)
-    Mc = np.zeros((n, n))
-    Mc[0] = 3 * c2 * M2[0]
-    for r in range(1, n - 1):
-        rk = r / (n - 1)
-        Mc[r] = c2 * M2[r] + (2.0 / rk) * c1 * M1[r]
-    Mc[n - 1] = c2 * M2[n - 1]
-    bj = 50 * dr * c2 + 2.0  # multiplies d1_bc = -j*Rp/D_s in the surface row
-    out.append("// combined Fickian operator for N_r = 10:  rhs_cs = kappa*(MC*c_s + BJ*d1bc e_surf),  kappa = D_s/Rp^2")
-    out.append("constexpr int NR = 10;")
-    out.append("static __device__ __constant__ double MC[NR][NR] = {")
-    for r in range(n):
-        out.append("    {" + ", ".join(repr(float(v)) for v in Mc[r]) + "},")
-    out.append("};")
-    out.append(f"constexpr double BJ = {bj!r};")
-    # structural pattern of the particle block (which (r,c) are non-zero), as a bit mask per row
-    masks = [sum(1 << cc for cc in range(n) if Mc[r, cc] != 0.0) for r in range(n)]
-    out.append("__host__ __device__ constexpr unsigned mc_mask(int r) {\n    return " +
-               " ".join(f"r == {r} ? {hex(v)}u :" for r, v in enumerate(masks)) + " 0u;\n}")
-    # eigen-decomposition MC = EV diag(EL) EVI (real spectrum, cond(EV) ~ 60): with a node-dependent
-    # D_s(T) the particle block kappa_x*MC - cj*I is different at every node, but it is diagonal in
-    # this fixed basis, so no per-node factorisation is needed (thermal variant).
-    import mpmath as mp
-    mp.mp.dps = 60
-    A = mp.matrix(Mc.tolist())
-    E, ER = mp.eig(A)
-    assert all(abs(mp.im(e)) < mp.mpf(10) ** -40 for e in E), "particle operator has complex eigenvalues"
-    order = sorted(range(n), key=lambda i: float(mp.re(E[i])))
-    EV = mp.matrix(n, n)
-    for k, i in enumerate(order):
-        col = [mp.re(ER[r, i]) for r in range(n)]
-        nrm = mp.sqrt(sum(v * v for v in col))
-        for r in range(n):
-            EV[r, k] = col[r] / nrm
-    EVI = EV ** -1
-    EL = [mp.re(E[i]) for i in order]
-    if abs(EL[-1]) < mp.mpf(10) ** -30:
-        EL[-1] = mp.mpf(0)          # conservation: MC * 1 = 0 exactly
-    chk = max(abs((EV * mp.diag(EL) * EVI - A)[r, cc]) for r in range(n) for cc in range(n))
-    assert chk < mp.mpf(10) ** -40, chk
-
-    def arr(name, Mx):
-        out.append(f"static __device__ __constant__ double {name}[NR][NR] = {{")
-        for r in range(n):
-            out.append("    {" + ", ".join(repr(float(Mx[r, cc])) for cc in range(n)) + "},")
-        out.append("};")
-    out.append("// MC = EV * diag(EL) * EVI (mpmath, 60 digits, rounded to double)")
-    arr("EV", EV)
-    arr("EVI", EVI)
-    out.append("static __device__ __constant__ double EL[NR] = {" + ", ".join(repr(float(v)) for v in EL) + "};")
+    # ---- Fickian particle operator, numerical_tools.jl:8-87, residuals.jl:128-180: one table set per built N_r
+    # (N_r = 10 is every parameter set's default, params.jl:134-136; the others are sibling builds, -DPLB_NR=n)
+    for n in NR_BUILT:
+        emit_particle_operator(out, n)
+    out.append("#ifndef PLB_NR\n#define PLB_NR 10\n#endif")
+    out.append("#define PLB_NR_NS2_(n) nr##n\n#define PLB_NR_NS_(n) PLB_NR_NS2_(n)")
+    out.append("using namespace PLB_NR_NS_(PLB_NR);   // laws::NR, laws::MC, laws::BJ, laws::mc_mask, laws::EV, laws::EVI, laws::EL")
     out.append("\n}}  // namespace plb::laws\n")
     with open(OUT, "w") as f:
         f.write("\n".join(out))
-    print("wrote", os.path.normpath(OUT), "particle nnz", sum(bin(v).count("1") for v in masks))
+    print("wrote", os.path.normpath(OUT))
 
 
 if __name__ == "__main__":

@@ -154,6 +154,7 @@ struct SimArgs {
 // what the host needs to know about a compiled variant
 struct VariantInfo {
     int sim_warps, sim_ctas;        // warps per CTA / CTAs per SM of the persistent integrator
+    int nr;                         // N_r (radial nodes per particle) this family is compiled for
     int k1_warps, k1_ctas;
     size_t sim_smem, k1_smem;       // dynamic shared memory per CTA
     int vs, nglobal;                // workspace vector stride, history vectors parked in global memory
@@ -190,5 +191,11 @@ PLB_DECLARE_VARIANT(isolgm)
 PLB_DECLARE_VARIANT(thlgm)
 PLB_DECLARE_VARIANT(isodc)
 PLB_DECLARE_VARIANT(widedc)
+PLB_DECLARE_VARIANT(iso12)
+PLB_DECLARE_VARIANT(th12)
+PLB_DECLARE_VARIANT(sei12)
+PLB_DECLARE_VARIANT(iso14)
+PLB_DECLARE_VARIANT(th14)
+PLB_DECLARE_VARIANT(sei14)
 
 }  // namespace plb

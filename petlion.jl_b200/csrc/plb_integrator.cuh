@@ -19,7 +19,8 @@ namespace plb {
 namespace PLB_NS {
 
 // vector stride in doubles (N_tot padded): 301 / 351 / 322 on the 32-node families, up to 642 (N=(20,20,20) with SEI) wide
-constexpr int VS = WIDE ? (TH ? (SEI ? 784 : 736) : 656) : (TH ? (SEI ? 384 : 352) : (SEI ? 336 : 304));
+// (N_r = 12 / 14 sibling builds: (N_r - 10) more doubles per electrode node -- 20 / 40 nodes of the standard grids; 8-aligned)
+constexpr int VS = (WIDE ? (TH ? (SEI ? 784 : 736) : 656) : (TH ? (SEI ? 384 : 352) : (SEI ? 336 : 304))) + (NR - 10) * (WIDE ? 40 : 20);
 // (Round 2: no predictor vectors.  y_pred = sum_j phi_j and y'_pred = sum_j gamma_j phi_j are re-formed from the
 // history where an evaluation needs them -- kk+1 shared-memory reads per component instead of two -- and phi_4, phi_5
 // live in global memory (PLB_NGLOBAL): six vectors per system in shared memory instead of ten, eight systems per SM

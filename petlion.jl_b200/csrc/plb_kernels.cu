@@ -28,7 +28,6 @@ using namespace plb;
 // =================================================================================================
 static thread_local std::string g_err;
 static int fail(const std::string& s) { g_err = s; return -1; }
-constexpr int NR_HOST = 10;   // N_r of the built variants (laws::NR)
 #define CUDA_OK(x)                                                                        \
     do {                                                                                  \
         cudaError_t e_ = (x);                                                             \
@@ -120,6 +119,12 @@ static const Variant V_WTHSEI = {wthsei::info, wthsei::slot_rc, wthsei::slot_rec
 
 // the 32-node families with rxn_MHC compiled in (used by models that select it)
 #define PLB_VARIANT_TABLE(NS) {NS::info, NS::slot_rc, NS::slot_recipe, NS::launch_resjac, NS::launch_initguess, NS::launch_newton, NS::launch_linsolve, NS::launch_simulate}
+static const Variant V_ISO12 = PLB_VARIANT_TABLE(iso12);        // N_r = 12 / 14 sibling builds
+static const Variant V_TH12 = PLB_VARIANT_TABLE(th12);
+static const Variant V_SEI12 = PLB_VARIANT_TABLE(sei12);
+static const Variant V_ISO14 = PLB_VARIANT_TABLE(iso14);
+static const Variant V_TH14 = PLB_VARIANT_TABLE(th14);
+static const Variant V_SEI14 = PLB_VARIANT_TABLE(sei14);
 static const Variant V_ISOLGM = PLB_VARIANT_TABLE(isolgm);      // NMC_LGM50 chemistry (its own instantiation of the iso / th families)
 static const Variant V_THLGM = PLB_VARIANT_TABLE(thlgm);
 static const Variant V_ISOMHC = PLB_VARIANT_TABLE(isomhc);
@@ -226,7 +231,11 @@ static int build_patterns(plb_handle_s* h) {
 int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (!d || !out) return fail("plb_create: null argument");
     if (d->aging && d->cathode != PLB_CATHODE_LCO) return fail("plb_create: aging=:SEI needs the LCO parameter set");
-    if (d->N_r_p != NR_HOST || d->N_r_n != NR_HOST) return fail("plb_create: only N_r_p = N_r_n = 10 is built");
+    // radial nodes per particle (params.jl:134-136): compile-time in every family (the stencil's eigen-basis, a lane's
+    // registers, the recipe tables); 10 everywhere, 12 and 14 as sibling builds of the 32-node iso / th / sei families
+    const int NR_HOST = d->N_r_p;
+    if (d->N_r_p != d->N_r_n || (NR_HOST != 10 && NR_HOST != 12 && NR_HOST != 14))
+        return fail("plb_create: built for N_r_p = N_r_n = 10 (every family), 12 or 14 (isothermal, thermal and SEI families on up to 32 x-nodes)");
     const int Nx_ = d->N_p + d->N_s + d->N_n;
     if (d->N_p < 2 || d->N_s < 2 || d->N_n < 2 || Nx_ > 64)
         return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 64 (one lane per node, one or two warps per system)");
@@ -249,7 +258,14 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
     const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
     const bool both = d->temperature && d->aging;
-    const bool wide = Nx_ > 32 || NtotT_ > (both ? V_THSEI : (d->temperature ? V_TH : (d->aging ? V_SEI : V_ISO))).info().vs;
+    const Variant* narrow = both ? &V_THSEI : (d->temperature ? &V_TH : (d->aging ? &V_SEI : &V_ISO));
+    if (NR_HOST != 10) {
+        const bool r12 = NR_HOST == 12;
+        narrow = narrow == &V_ISO ? (r12 ? &V_ISO12 : &V_ISO14) : (narrow == &V_TH ? (r12 ? &V_TH12 : &V_TH14) : (narrow == &V_SEI ? (r12 ? &V_SEI12 : &V_SEI14) : nullptr));
+        if (!narrow || lgm || d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC || Nx_ > 32 || NtotT_ > narrow->info().vs)
+            return fail("plb_create: N_r = 12 / 14 is built for the isothermal, thermal and SEI families on up to 32 x-nodes (LCO / NMC, rxn_BV)");
+    }
+    const bool wide = Nx_ > 32 || NtotT_ > narrow->info().vs;
     if ((d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) && (wide || both))
         return fail("plb_create: rxn_MHC is built for grids of up to 32 x-nodes, with temperature=true or aging=:SEI but not both");
     int ndev = 0;
@@ -270,6 +286,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
     h->v = both ? (wide ? &V_WTHSEI : &V_THSEI)
                 : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
+    if (NR_HOST != 10) h->v = narrow;
     if (lgm) h->v = h->v == &V_ISO ? &V_ISOLGM : (h->v == &V_TH ? &V_THLGM : nullptr);
     if (!h->v) { delete h; return fail("plb_create: NMC_LGM50 is built for the isothermal and thermal families on up to 32 x-nodes"); }
     if (d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) {

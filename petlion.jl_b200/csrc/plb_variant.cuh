@@ -65,7 +65,8 @@ enum JacSlot {
 #endif
 constexpr int K1_WARPS = PLB_K1_WARPS;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
-constexpr int K1_SRC_MAX = WIDE ? (TH ? (SEI ? 7168 : 6656) : 4864) : (TH ? (SEI ? 3328 : 3072) : 2304);        // >= nnz of every built variant
+constexpr int K1_SRC_MAX = (WIDE ? (TH ? (SEI ? 7168 : 6656) : 4864) : (TH ? (SEI ? 3328 : 3072) : 2304))         // >= nnz of every built variant
+                           + (NR - 10) * 10 * (WIDE ? 64 : 32);   // N_r siblings: 9 (+1 thermal) more block entries per radial node and particle
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 // pitch of the value table: one double of padding per slot row.  Consecutive CSC entries of a column come from
@@ -666,7 +667,11 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // systems of a CTA on one instruction stream; with only that barrier left, one large CTA per SM is best for the
 // 32-lane families (measured, iso, sims/s on one B200: 6x1 229 k, 3x2 213 k, 2x3 200 k).
 // (round 2: six vectors per system in shared memory instead of ten: 8 / 6 / 5 systems per SM instead of 6 / 5 / 4)
+#if PLB_NR == 10
 #define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 5) : (PLB_SEI ? 6 : 8)))
+#else   // N_r = 12 / 14 siblings: longer vectors and larger particle inverses per system
+#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 4) : (PLB_SEI ? 5 : 6)))
+#endif
 #endif
 #ifndef PLB_SIM_CTAS
 #define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 1 : 2) : 3) : 1)
@@ -833,6 +838,7 @@ VariantInfo info() {
     v.sim_smem = SIM_SMEM; v.k1_smem = K1_SMEM; v.vs = VS; v.nglobal = NGLOBAL;
     v.n_slots = JS_COUNT; v.n_stage = K1_NSTAGE; v.k1_src_max = K1_SRC_MAX; v.lanes = LW;
     v.k1_tma = (!WIDE && !TH && (!SEI || PLB_SEI_TMA)) ? 1 : 0;
+    v.nr = NR;
     return v;
 }
 

@@ -1,0 +1,7 @@
+// the thermal family compiled for N_r_p = N_r_n = 14 radial nodes per particle (params.jl:134-136): its own stencil,
+// eigen-basis, lane registers, workspace stride and recipe tables (laws_generated.cuh, namespace nr14); selected by plb_create
+#define PLB_TH 1
+#define PLB_SEI 0
+#define PLB_NR 14
+#define PLB_NS th14
+#include "plb_variant.cuh"

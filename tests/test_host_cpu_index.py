@@ -44,6 +44,11 @@ def test_table_host_semantics_match_the_oracle_table():
 
 @pytest.mark.parametrize("kw,msg", [
     (dict(N_r_p=12), "N_r_p = N_r_n = 10"),
+    (dict(N_r_p=11, N_r_n=11), "N_r_p = N_r_n = 10"),
+    (dict(N_r_p=16, N_r_n=16), "N_r_p = N_r_n = 10"),
+    (dict(N_r_p=12, N_r_n=12, N_p=20, N_s=20, N_n=20), "N_r = 12 / 14 is built for"),
+    (dict(N_r_p=14, N_r_n=14, temperature=True, aging="SEI"), "N_r = 12 / 14 is built for"),
+    (dict(N_r_p=12, N_r_n=12, rxn_p="rxn_MHC"), "N_r = 12 / 14 is built for"),
     (dict(rxn_p="rxn_MHC", N_p=20, N_s=10, N_n=20), "rxn_MHC is built for grids of up to 32"),
     (dict(rxn_n="rxn_MHC", temperature=True, aging="SEI"), "rxn_MHC is built for"),
     (dict(N_p=30, N_s=10, N_n=30), "<= 64"),
