@@ -42,13 +42,15 @@ enum { PLB_MEM_HOST = 0, PLB_MEM_DEVICE = 1 };                /* where the calle
 /* petlion(cathode; N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, temperature, aging) -- src/params.jl:119-174 */
 typedef struct {
     int cathode;
-    int N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n;
+    int N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n;   /* N_r_p = N_r_n = 10 (every family), 12 or 14 (iso / thermal / SEI, <= 32 x-nodes) */
     int temperature; /* 0: isothermal.  1: temperature=true (LCO only: NMC has no thermal parameters;
                         needs N_p, N_n >= 5 and N_a + N_z <= N_p + N_s + N_n)                  */
     int aging;       /* 0: none.  1: aging=:SEI (LCO, isothermal; adds film, SOH, j_s: N = 322 for 10/10/10) */
     int device;      /* CUDA device ordinal */
     int rxn_p, rxn_n; /* PLB_RXN_*: reaction rate law of the positive / negative electrode (0 = rxn_BV, the default).
                         rxn_MHC adds the keys lambda_MHC_p / lambda_MHC_n to theta (LCO parameter set only) */
+    int fickian_spectral; /* 0: Fickian_method = :finite_difference (default); 1: :spectral (params.jl:142, residuals.jl:181-235):
+                        Chebyshev collocation in the particles; isothermal, thermal and SEI families on up to 32 x-nodes, N_r = 10 */
 } plb_model_desc;
 
 /* run_constant{method,value}: src/structures.jl:46-54; input kinds: src/physics_equations/input_methods.jl:5-74 */

@@ -15,6 +15,7 @@ struct ModelDesc
     cathode::Cint; N_p::Cint; N_s::Cint; N_n::Cint; N_a::Cint; N_z::Cint; N_r_p::Cint; N_r_n::Cint
     temperature::Cint; aging::Cint; device::Cint
     rxn_p::Cint; rxn_n::Cint          # 0 rxn_BV, 1 rxn_MHC
+    fickian_spectral::Cint            # p.numerics.Fickian_method === :spectral
 end
 struct Run
     method::Cint; input_kind::Cint; value::Cdouble; tf::Cdouble; new_run::Cint; reserved::Cint
@@ -46,9 +47,9 @@ check(rc) = rc == 0 || error(unsafe_string(ccall((:plb_last_error, lib), Cstring
 # ---- model handle: petlion(...) (src/external.jl:2-18) ------------------------------------------------------------
 rxn_code(f) = Symbol(f) === :rxn_MHC ? 1 : 0
 cathode_code(c::Symbol) = c === :LCO ? 0 : (c === :NMC_LGM50 ? 2 : 1)          # PLB_CATHODE_*
-function create(cathode::Symbol, N, temperature::Bool, aging; device::Integer = 0, rxn_p = :rxn_BV, rxn_n = :rxn_BV)::Ptr{Cvoid}
+function create(cathode::Symbol, N, temperature::Bool, aging; device::Integer = 0, rxn_p = :rxn_BV, rxn_n = :rxn_BV, Fickian_method = :finite_difference)::Ptr{Cvoid}
     d = ModelDesc(cathode_code(cathode), N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, device,
-                  rxn_code(rxn_p), rxn_code(rxn_n))
+                  rxn_code(rxn_p), rxn_code(rxn_n), Fickian_method === :spectral)
     h = Ref{Ptr{Cvoid}}()
     check(ccall((:plb_create, lib), Cint, (Ref{ModelDesc}, Ref{Ptr{Cvoid}}), d, h))
     return h[]
@@ -156,9 +157,9 @@ function simulate_table!(h, B, θ, run::Run, tt::Vector{Float64}, vv::Vector{Flo
 end
 
 # ---- several GPUs of the box behind one call (contiguous batch shards, one ncclAllGather of the summaries) --------
-function group_create(cathode::Symbol, N, temperature::Bool, aging, devices::Vector{<:Integer}; rxn_p = :rxn_BV, rxn_n = :rxn_BV)::Ptr{Cvoid}
+function group_create(cathode::Symbol, N, temperature::Bool, aging, devices::Vector{<:Integer}; rxn_p = :rxn_BV, rxn_n = :rxn_BV, Fickian_method = :finite_difference)::Ptr{Cvoid}
     d = ModelDesc(cathode_code(cathode), N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n, temperature, aging === :SEI, 0,
-                  rxn_code(rxn_p), rxn_code(rxn_n))
+                  rxn_code(rxn_p), rxn_code(rxn_n), Fickian_method === :spectral)
     g = Ref{Ptr{Cvoid}}()
     check(ccall((:plb_group_create, lib), Cint, (Ref{ModelDesc}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), d, length(devices), Cint.(devices), g))
     return g[]

@@ -30,7 +30,7 @@ def build(force=False):
 class Model(C.Structure):
     _fields_ = [(n, C.c_int) for n in
                 ("N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n", "temperature", "aging", "cathode",
-                 "rxn_p", "rxn_n")]
+                 "rxn_p", "rxn_n", "fickian_spectral")]
 
 
 class Layout(C.Structure):
@@ -123,9 +123,9 @@ RXN = {"BV": 0, "MHC": 1, "rxn_BV": 0, "rxn_MHC": 1}
 
 
 def make_model(cathode="LCO", N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, N_r_n=10,
-               temperature=False, aging=False, rxn_p="BV", rxn_n="BV"):
+               temperature=False, aging=False, rxn_p="BV", rxn_n="BV", Fickian_method="finite_difference"):
     return Model(N_p, N_s, N_n, N_a, N_z, N_r_p, N_r_n, int(bool(temperature)), int(bool(aging)),
-                 CATHODE[cathode], RXN[rxn_p], RXN[rxn_n])
+                 CATHODE[cathode], RXN[rxn_p], RXN[rxn_n], {"finite_difference": 0, "spectral": 1}[Fickian_method])
 
 
 def layout(m):

@@ -74,6 +74,7 @@ typedef struct {
     int aging;       /* 0 none, 1 :SEI            */
     int cathode;     /* ORC_CATHODE_*             */
     int rxn_p, rxn_n; /* ORC_RXN_*: rxn_BV (default) or rxn_MHC, per electrode (params.jl:51, 114) */
+    int fickian_spectral; /* 0: Fickian_method = :finite_difference (default), 1: :spectral (params.jl:142, residuals.jl:181-235) */
 } orc_model;
 
 /* index layout -- src/external.jl:275-365, SURVEY App. A (0-based here) */

@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
     units = ("plb_kernels.cu", "plb_variant_iso.cu", "plb_variant_th.cu", "plb_variant_sei.cu",
              "plb_variant_wide.cu", "plb_variant_wsei.cu", "plb_variant_wth.cu", "plb_variant_thsei.cu", "plb_variant_wthsei.cu", "plb_variant_isodc.cu", "plb_variant_widedc.cu", "plb_variant_isomhc.cu", "plb_variant_thmhc.cu", "plb_variant_seimhc.cu", "plb_variant_isolgm.cu", "plb_variant_thlgm.cu",
-             "plb_variant_iso_r12.cu", "plb_variant_th_r12.cu", "plb_variant_sei_r12.cu", "plb_variant_iso_r14.cu", "plb_variant_th_r14.cu", "plb_variant_sei_r14.cu")
+             "plb_variant_iso_r12.cu", "plb_variant_th_r12.cu", "plb_variant_sei_r12.cu", "plb_variant_iso_r14.cu", "plb_variant_th_r14.cu", "plb_variant_sei_r14.cu",
+             "plb_variant_iso_sp.cu", "plb_variant_th_sp.cu", "plb_variant_sei_sp.cu")
     srcs = [os.path.join(CSRC, f) for f in units + ("plb_common.cuh", "plb_variant.cuh", "plb_device.cuh",
                                                     "plb_integrator.cuh", "plb_tick.cuh", "laws_generated.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))
@@ -73,7 +74,7 @@ def build(force=False, verbose=False):
 
 class ModelDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("cathode", "N_p", "N_s", "N_n", "N_a", "N_z", "N_r_p", "N_r_n",
-                                       "temperature", "aging", "device", "rxn_p", "rxn_n")]
+                                       "temperature", "aging", "device", "rxn_p", "rxn_n", "fickian_spectral")]
 
 
 class Run(C.Structure):

@@ -60,7 +60,7 @@ class Model:
         self.numerics = numerics
         desc = _lib.ModelDesc(CATHODES[cathode], N.p, N.s, N.n, N.a, N.z, N.r_p, N.r_n,
                               int(bool(numerics.temperature)), int(bool(numerics.aging)), int(device),
-                              RXN[numerics.rxn_p], RXN[numerics.rxn_n])
+                              RXN[numerics.rxn_p], RXN[numerics.rxn_n], int(numerics.Fickian_method == "spectral"))
         self._g = None
         self.devices = [int(device)] if devices is None else [int(d) for d in devices]
         if devices is not None and len(self.devices) > 1:
@@ -333,8 +333,12 @@ def petlion(cathode="LCO", *, N_p=10, N_s=10, N_n=10, N_a=10, N_z=10, N_r_p=10, 
         # (That system's default aging = :stress has no implementation in the reference -- its first stop check throws a
         #  MethodError, checks.jl:204-206 -- so `aging` defaults to false here for every parameter set.)
         temperature = cathode == "NMC_LGM50"
-    if solid_diffusion != "Fickian" or Fickian_method != "finite_difference":
-        raise NotImplementedError("only solid_diffusion=:Fickian, Fickian_method=:finite_difference is built")
+    if solid_diffusion != "Fickian":
+        # (:quadratic / :polynomial read states[:D_s_eff] before any method creates it and throw a KeyError at model
+        #  construction in the reference itself: DESIGN.md section 7)
+        raise NotImplementedError("only solid_diffusion=:Fickian is built")
+    if Fickian_method not in ("finite_difference", "spectral"):
+        raise ValueError("`Fickian_method` can either be :finite_difference or :spectral")     # params.jl:142
     if jacobian not in ("symbolic", "AD"):
         raise ValueError("`jacobian` can either be :symbolic or :AD")   # checks.jl:377-383
     if aging not in (False, True, "SEI"):       # params.jl:119-174: aging = false | :SEI

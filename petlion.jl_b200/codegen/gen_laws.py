@@ -180,6 +180,78 @@ def emit_particle_operator(out, n):
     print("N_r", n, "particle nnz", sum(bin(v).count("1") for v in masks))
 
 
+def emit_spectral_operator(out, n):
+    """Fickian_method = :spectral ("BETA", residuals.jl:181-235): Chebyshev collocation.  With dc = P D R c (rows of the two
+    boundary conditions removed by P, R = the centre->surface reversal) and dc[surface] = -j Rp / (2 D_s), the reference's
+    right-hand side is linear:  rhs_cs = kappa * (MC c + GJ * d1bc),  kappa = D_s/Rp^2, d1bc = -j Rp/D_s -- the same form
+    as the finite-difference scheme, with a DENSE constant block MC = 4 L1 P D R and a FULL coupling vector GJ = 2 L1 e_1.
+    Formed in 60-digit arithmetic, rounded to double; namespace sp<n>."""
+    import mpmath as mp
+    mp.mp.dps = 60
+    N = n - 1
+    x = [mp.cos(mp.pi * k / N) for k in range(n)]
+    cc = [(2 if k in (0, N) else 1) * (-1) ** k for k in range(n)]
+    D = mp.matrix(n, n)
+    for i in range(n):
+        for k in range(n):
+            D[i, k] = (mp.mpf(cc[i]) / cc[k]) / ((x[i] - x[k]) + (1 if i == k else 0))
+    for i in range(n):
+        D[i, i] -= sum(D[i, k] for k in range(n))
+    R = mp.matrix(n, n)
+    for i in range(n):
+        R[i, n - 1 - i] = 1
+    P = mp.eye(n); P[0, 0] = 0; P[n - 1, n - 1] = 0
+    W = mp.diag([(xi + 1) ** 2 for xi in x])
+    Lnum = R * (D * W)
+    L1 = mp.matrix(n, n)
+    for q in range(n):
+        L1[0, q] = 3 * D[n - 1, q]                     # L'Hopital at the centre
+    for r in range(1, n):
+        for q in range(n):
+            L1[r, q] = Lnum[r, q] / (x[n - 1 - r] + 1) ** 2
+    A = 4 * L1 * P * D * R
+    g = [2 * L1[r, 0] for r in range(n)]
+    E, ER = mp.eig(A)
+    assert all(abs(mp.im(e)) < mp.mpf(10) ** -40 for e in E), "spectral particle operator has complex eigenvalues"
+    order = sorted(range(n), key=lambda i: float(mp.re(E[i])))
+    EV = mp.matrix(n, n)
+    for k, i in enumerate(order):
+        col = [mp.re(ER[r, i]) for r in range(n)]
+        nrm = mp.sqrt(sum(v * v for v in col))
+        for r in range(n):
+            EV[r, k] = col[r] / nrm
+    EVI = EV ** -1
+    EL = [mp.re(E[i]) for i in order]
+    if abs(EL[-1]) < mp.mpf(10) ** -30:
+        EL[-1] = mp.mpf(0)          # conservation: MC * 1 = 0
+    chk = max(abs((EV * mp.diag(EL) * EVI - A)[r, q]) for r in range(n) for q in range(n))
+    assert chk < mp.mpf(10) ** -35, chk
+    EVIG = [sum(EVI[i, q] * g[q] for q in range(n)) for i in range(n)]
+    out.append(f"namespace sp{n} {{")
+    out.append(f"// spectral (Chebyshev) Fickian operator for N_r = {n}:  rhs_cs = kappa*(MC*c_s + GJ*d1bc),  kappa = D_s/Rp^2")
+    out.append(f"constexpr int NR = {n};")
+    out.append("constexpr double BJ = 1.0;      // (the j coupling is GJ[r] on every row)")
+    out.append("__host__ __device__ constexpr unsigned mc_mask(int) { return " + hex((1 << n) - 1) + "u; }   // dense block")
+
+    def arr(name, Mx):
+        out.append(f"static __device__ __constant__ double {name}[NR][NR] = {{")
+        for r in range(n):
+            out.append("    {" + ", ".join(repr(float(Mx[r, q])) for q in range(n)) + "},")
+        out.append("};")
+
+    def vec(name, v):
+        out.append(f"static __device__ __constant__ double {name}[NR] = {{" + ", ".join(repr(float(t)) for t in v) + "};")
+    arr("MC", A)
+    vec("GJ", g)
+    out.append("// MC = EV * diag(EL) * EVI ;  EVIG = EVI * GJ")
+    arr("EV", EV)
+    arr("EVI", EVI)
+    vec("EL", EL)
+    vec("EVIG", EVIG)
+    out.append(f"}}  // namespace sp{n}")
+    print("spectral N_r", n, "cond(EV)", float(mp.norm(EV, 2) * mp.norm(EVI, 2)))
+
+
 def main():
     th, c, T = sp.symbols("th c T", real=True)
     out = []
@@ -296,9 +368,12 @@ def main():
     # (N_r = 10 is every parameter set's default, params.jl:134-136; the others are sibling builds, -DPLB_NR=n)
     for n in NR_BUILT:
         emit_particle_operator(out, n)
+    emit_spectral_operator(out, 10)
     out.append("#ifndef PLB_NR\n#define PLB_NR 10\n#endif")
+    out.append("#ifndef PLB_SPECTRAL\n#define PLB_SPECTRAL 0      // 1: Fickian_method = :spectral (sibling builds, N_r = 10)\n#endif")
     out.append("#define PLB_NR_NS2_(n) nr##n\n#define PLB_NR_NS_(n) PLB_NR_NS2_(n)")
-    out.append("using namespace PLB_NR_NS_(PLB_NR);   // laws::NR, laws::MC, laws::BJ, laws::mc_mask, laws::EV, laws::EVI, laws::EL")
+    out.append("#if PLB_SPECTRAL\n#if PLB_NR != 10\n#error \"the spectral particle operator is generated for N_r = 10\"\n#endif\nusing namespace sp10;\n#else")
+    out.append("using namespace PLB_NR_NS_(PLB_NR);   // laws::NR, laws::MC, laws::BJ, laws::mc_mask, laws::EV, laws::EVI, laws::EL\n#endif")
     out.append("\n}}  // namespace plb::laws\n")
     with open(OUT, "w") as f:
         f.write("\n".join(out))

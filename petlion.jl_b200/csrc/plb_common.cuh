@@ -197,5 +197,8 @@ PLB_DECLARE_VARIANT(sei12)
 PLB_DECLARE_VARIANT(iso14)
 PLB_DECLARE_VARIANT(th14)
 PLB_DECLARE_VARIANT(sei14)
+PLB_DECLARE_VARIANT(isosp)
+PLB_DECLARE_VARIANT(thsp)
+PLB_DECLARE_VARIANT(seisp)
 
 }  // namespace plb

@@ -55,6 +55,13 @@ constexpr int LW = WIDE ? 64 : 32;          // lanes per system
 constexpr int XCH_K = 16;                   // doubles per lane of the exchange scratch (wide only)
 constexpr size_t XCH_BYTES_PER_GROUP = WIDE ? sizeof(double) * XCH_K * LW : 0;
 constexpr int NR = laws::NR;
+// the j coupling of the particle rows in the eigen-basis, EVI * (b / cs_j): the surface column of EVI for the finite-difference
+// scheme (b = cs_j e_surf), EVI * GJ for the spectral one
+#if PLB_SPECTRAL
+#define PLB_EVIB(i) laws::EVIG[i]
+#else
+#define PLB_EVIB(i) laws::EVI[i][NR - 1]
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // per-warp shared-memory constants derived from theta once per system
@@ -766,7 +773,11 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
 #if PLB_TH
             if (WITH_JAC) J.csT[r] = dkapT * acc;     // kap*BJ*d1bc = -BJ*j/Rp does not depend on T
 #endif
+#if PLB_SPECTRAL
+            acc = fma(laws::GJ[r], d1bc, acc);        // Chebyshev collocation: the surface flux reaches every radial row
+#else
             if (r == NR - 1) acc = fma(laws::BJ, d1bc, acc);
+#endif
             res.cs[r] = kap * acc - yp.cs[r];
         }
         res.j = jcalc - y.j;
@@ -957,7 +968,7 @@ __device__ __forceinline__ void lane_eval(const ModelDesc& m, const WarpConst& C
         J.ps_j = ro.elec ? -C.sec[SC_psf][s] : 0.0;
         J.ps_I = (ro.sec == 0 && ro.first_e) ? C.g[GC_psI_p] : ((ro.sec == 2 && ro.last_e) ? C.g[GC_psI_n] : 0.0);
         J.kap = kapx;
-        J.cs_j = ro.elec ? -laws::BJ * C.sec[SC_inv_Rp][s] : 0.0;
+        J.cs_j = ro.elec ? -laws::BJ * C.sec[SC_inv_Rp][s] : 0.0;     // (spectral: BJ = 1, row r carries cs_j * GJ[r])
 #if PLB_TH
         J.j_T = dj_T;
         if (last) { J.peTL = 0.0; J.peTD = 0.0; J.peTU = 0.0; }
@@ -1125,6 +1136,24 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
             const double kap = el == 0 ? kap_p : kap_n;
             const double pd_own = 1.0 / (kap * laws::EL[cc] - cj);
             double t[NR];
+#if PLB_SPECTRAL
+            // b = cs_j * GJ is a full vector: one more lane per electrode (c == NR) forms vb = Sinv b = EV diag(pd) (EVI GJ) cs_j
+            static_assert(NR < 16, "the vb lane of the spectral build");
+            const bool vbl = c == NR;
+#pragma unroll
+            for (int i = 0; i < NR; i++) t[i] = __shfl_sync(FULL, pd_own, (el << 4) + i) * (vbl ? laws::EVIG[i] : laws::EVI[i][cc]);
+            if (c <= NR) {
+                const double csj = el == 0 ? csj_p : csj_n;
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NR; i++) acc = fma(laws::EV[r][i], t[i], acc);
+                    if (vbl) Fa.vb[r][el] = acc * csj;
+                    else Fa.Sinv[r * NR + c][el] = acc;
+                }
+            }
+#else
 #pragma unroll
             for (int i = 0; i < NR; i++) t[i] = __shfl_sync(FULL, pd_own, (el << 4) + i) * laws::EVI[i][cc];
             if (c < NR) {
@@ -1138,6 +1167,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
                     if (c == NR - 1) Fa.vb[r][el] = acc * csj;   // vb = Sinv * b,  b = cs_j * e_surf
                 }
             }
+#endif
         }
         grp_sync();
     }
@@ -1668,7 +1698,7 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
             for (int c = 0; c < NR; c++) w = fma(laws::EVI[i][c], J.csT[c], w);
             Fa.wT[i][lane] = w;
-            beta = fma(laws::EV[NR - 1][i] * pd[i], laws::EVI[i][NR - 1], beta);
+            beta = fma(laws::EV[NR - 1][i] * pd[i], PLB_EVIB(i), beta);
             tau = fma(laws::EV[NR - 1][i] * pd[i], w, tau);
         }
         beta *= J.cs_j;
@@ -2039,7 +2069,7 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
         const double bj = Fa.csj[lane] * dj;
 #pragma unroll
         for (int i = 0; i < NR; i++)
-            v[i] = Fa.pd[i][lane] * (g.cs[i] - laws::EVI[i][NR - 1] * bj - Fa.wT[i][lane] * u4[3]);
+            v[i] = Fa.pd[i][lane] * (g.cs[i] - PLB_EVIB(i) * bj - Fa.wT[i][lane] * u4[3]);
 #pragma unroll
         for (int r = 0; r < NR; r++) {
             double acc = 0.0;

@@ -125,6 +125,9 @@ static const Variant V_SEI12 = PLB_VARIANT_TABLE(sei12);
 static const Variant V_ISO14 = PLB_VARIANT_TABLE(iso14);
 static const Variant V_TH14 = PLB_VARIANT_TABLE(th14);
 static const Variant V_SEI14 = PLB_VARIANT_TABLE(sei14);
+static const Variant V_ISOSP = PLB_VARIANT_TABLE(isosp);        // Fickian_method = :spectral sibling builds
+static const Variant V_THSP = PLB_VARIANT_TABLE(thsp);
+static const Variant V_SEISP = PLB_VARIANT_TABLE(seisp);
 static const Variant V_ISOLGM = PLB_VARIANT_TABLE(isolgm);      // NMC_LGM50 chemistry (its own instantiation of the iso / th families)
 static const Variant V_THLGM = PLB_VARIANT_TABLE(thlgm);
 static const Variant V_ISOMHC = PLB_VARIANT_TABLE(isomhc);
@@ -265,6 +268,13 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
         if (!narrow || lgm || d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC || Nx_ > 32 || NtotT_ > narrow->info().vs)
             return fail("plb_create: N_r = 12 / 14 is built for the isothermal, thermal and SEI families on up to 32 x-nodes (LCO / NMC, rxn_BV)");
     }
+    if (d->fickian_spectral) {
+        // Fickian_method = :spectral (params.jl:142; residuals.jl:181-235, "BETA"): sibling builds of the 32-node families
+        if (d->fickian_spectral != 1) return fail("plb_create: unknown Fickian_method (0 = :finite_difference, 1 = :spectral)");
+        narrow = NR_HOST != 10 ? nullptr : (narrow == &V_ISO ? &V_ISOSP : (narrow == &V_TH ? &V_THSP : (narrow == &V_SEI ? &V_SEISP : nullptr)));
+        if (!narrow || lgm || d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC || Nx_ > 32 || NtotT_ > narrow->info().vs)
+            return fail("plb_create: Fickian_method = :spectral is built for the isothermal, thermal and SEI families on up to 32 x-nodes (LCO / NMC, rxn_BV, N_r = 10)");
+    }
     const bool wide = Nx_ > 32 || NtotT_ > narrow->info().vs;
     if ((d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) && (wide || both))
         return fail("plb_create: rxn_MHC is built for grids of up to 32 x-nodes, with temperature=true or aging=:SEI but not both");
@@ -286,7 +296,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
     h->v = both ? (wide ? &V_WTHSEI : &V_THSEI)
                 : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
-    if (NR_HOST != 10) h->v = narrow;
+    if (NR_HOST != 10 || d->fickian_spectral) h->v = narrow;
     if (lgm) h->v = h->v == &V_ISO ? &V_ISOLGM : (h->v == &V_TH ? &V_THLGM : nullptr);
     if (!h->v) { delete h; return fail("plb_create: NMC_LGM50 is built for the isothermal and thermal families on up to 32 x-nodes"); }
     if (d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) {

@@ -25,6 +25,9 @@ enum JacSlot {
     JS_PE_L, JS_PE_D, JS_PE_U, JS_PC_L, JS_PC_D, JS_PC_U, JS_PE_J,
     JS_PS_L, JS_PS_D, JS_PS_U, JS_PS_J, JS_PS_I,
     JS_CS_J,
+#if PLB_SPECTRAL
+    JS_CS_J_LAST = JS_CS_J + NR - 1,     // Fickian_method = :spectral: NR slots, the j column reaches every radial row
+#endif
 #if PLB_SEI
     // aging = :SEI (anode lanes): j row d/dfilm; j_s row; film row; SOH row; d/dj_s of the c_e, Phi_e, Phi_s rows
     JS_J_FILM, JS_JS_PS, JS_JS_PE, JS_JS_J, JS_JS_JS, JS_JS_FILM, JS_JS_I, JS_FILM_JS, JS_FILM_D,
@@ -66,7 +69,7 @@ enum JacSlot {
 constexpr int K1_WARPS = PLB_K1_WARPS;            // systems (lane groups) per CTA
 constexpr int K1_NSTAGE = JS_CS0 + 7;   // lane-computed slots: 0..JS_CS0-1, then the seven control-row slots
 constexpr int K1_SRC_MAX = (WIDE ? (TH ? (SEI ? 7168 : 6656) : 4864) : (TH ? (SEI ? 3328 : 3072) : 2304))         // >= nnz of every built variant
-                           + (NR - 10) * 10 * (WIDE ? 64 : 32);   // N_r siblings: 9 (+1 thermal) more block entries per radial node and particle
+                           + (NR - 10) * 10 * (WIDE ? 64 : 32) + (PLB_SPECTRAL ? 27 * (WIDE ? 64 : 32) : 0);   // N_r siblings: 9 (+1 thermal) more block entries per radial node and particle
 __host__ __device__ constexpr int k1_stage_slot(int js) { return js < JS_CS0 ? js : JS_CS0 + (js - JS_CTRL_PS0); }
 
 // pitch of the value table: one double of padding per slot row.  Consecutive CSC entries of a column come from
@@ -192,7 +195,12 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac(const __g
             w.S[JS_PC_L][lane] = J.pcL; w.S[JS_PC_D][lane] = J.pcD; w.S[JS_PC_U][lane] = J.pcU; w.S[JS_PE_J][lane] = J.pe_j;
             w.S[JS_PS_L][lane] = J.psL; w.S[JS_PS_D][lane] = J.psD; w.S[JS_PS_U][lane] = J.psU; w.S[JS_PS_J][lane] = J.ps_j;
             w.S[JS_PS_I][lane] = J.ps_I;
+#if PLB_SPECTRAL
+#pragma unroll
+            for (int r = 0; r < NR; r++) w.S[JS_CS_J + r][lane] = J.cs_j * laws::GJ[r];
+#else
             w.S[JS_CS_J][lane] = J.cs_j;
+#endif
 #if PLB_TH
 #pragma unroll
             for (int r = 0; r < NR; r++) w.S[JS_CS_T0 + r][lane] = J.csT[r];
@@ -478,7 +486,12 @@ __global__ void __launch_bounds__(K1_WARPS * LW, PLB_K1_CTAS) k_resjac_tma(const
             w.S[JS_PC_L][lane] = J.pcL; w.S[JS_PC_D][lane] = J.pcD; w.S[JS_PC_U][lane] = J.pcU; w.S[JS_PE_J][lane] = J.pe_j;
             w.S[JS_PS_L][lane] = J.psL; w.S[JS_PS_D][lane] = J.psD; w.S[JS_PS_U][lane] = J.psU; w.S[JS_PS_J][lane] = J.ps_j;
             w.S[JS_PS_I][lane] = J.ps_I;
+#if PLB_SPECTRAL
+#pragma unroll
+            for (int r = 0; r < NR; r++) w.S[JS_CS_J + r][lane] = J.cs_j * laws::GJ[r];
+#else
             w.S[JS_CS_J][lane] = J.cs_j;
+#endif
             w.S[k1_stage_slot(JS_CTRL_PS0)][lane] = ctrl.g_ps0;
             w.S[k1_stage_slot(JS_CTRL_PSN)][lane] = ctrl.g_psN;
             w.S[k1_stage_slot(JS_CTRL_I)][lane] = ctrl.g_I;
@@ -550,7 +563,9 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         case JS_PS_U: row = r_ps; col = r_ps + 1; return elec && !last_e;
         case JS_PS_J: row = r_ps; col = r_j; return elec;
         case JS_PS_I: row = r_ps; col = I; return (isp && first_e) || (isn && last_e);
+#if !PLB_SPECTRAL
         case JS_CS_J: row = cs(NR - 1); col = r_j; return elec;
+#endif
         case JS_CTRL_PS0: row = I; col = m.off_ps; return lane == 0 && (method == METHOD_V || method == METHOD_P);
         case JS_CTRL_PSN: row = I; col = m.off_ps + m.Ne - 1; return lane == Nx - 1 && (method == METHOD_V || method == METHOD_P);
         case JS_CTRL_I: row = I; col = I; return lane == 0 && (method == METHOD_I || method == METHOD_P);
@@ -558,6 +573,9 @@ bool slot_rc(const ModelDesc& m, int method, int slot, int lane, int& row, int& 
         case JS_CTRL_EPE: row = I; col = r_pe; return method == METHOD_ETA && x == Np + Ns;
         default: break;
     }
+#if PLB_SPECTRAL
+    if (slot >= JS_CS_J && slot < JS_CS_J + NR) { row = cs(slot - JS_CS_J); col = r_j; return elec; }
+#endif
     if (slot >= JS_CS0 && slot < JS_CS0 + NR * NR) {
         const int r = (slot - JS_CS0) / NR, c = (slot - JS_CS0) % NR;
         row = cs(r); col = cs(c);

@@ -1,8 +1,9 @@
-"""N_r_p = N_r_n = 12 / 14 radial nodes per particle (params.jl:134-136; every parameter set's default is 10): sibling builds
-of the isothermal, thermal and SEI families with their own stencil, eigen-basis, lane registers, workspace stride and recipe
-tables.  Pattern, residual/Jacobian values, the structured linear solve (against dense LAPACK), the Newton initialisation and
-a CC charge + CV hold against the oracle, which is generic in N_r (tests/test_oracle_nr.py pins its stencil).
-Same tolerances as tests/test_gpu_parity.py / tests/test_gpu_ragged.py."""
+"""Fickian_method = :spectral (params.jl:142; residuals_c_s_avg!, residuals.jl:181-235, labelled "BETA" there): Chebyshev
+collocation in the particles -- a dense constant particle block and a surface-flux coupling on EVERY radial row.  Sibling
+builds of the isothermal, thermal and SEI families (N_r = 10).  Pattern, residual/Jacobian values, the structured linear
+solve (against dense LAPACK), the Newton initialisation and a CC charge + CV hold against the oracle
+(tests/test_oracle_spectral.py checks the oracle's restatement against the closed form the scheme implies; the reference
+executes the option nowhere: unpinned).  Same tolerances as tests/test_gpu_parity.py / tests/test_gpu_ragged.py."""
 import numpy as np
 import pytest
 
@@ -11,9 +12,8 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("iso", 12, {}), ("iso", 14, {}), ("thermal", 12, dict(temperature=True)), ("thermal", 14, dict(temperature=True)),
-         ("sei", 12, dict(aging=True)), ("sei", 14, dict(aging=True))]
-IDS = [f"{c[0]}-Nr{c[1]}" for c in CASES]
+CASES = [("iso", 10, {}), ("thermal", 10, dict(temperature=True)), ("sei", 10, dict(aging=True))]
+IDS = [c[0] for c in CASES]
 
 
 @pytest.fixture(scope="module")
@@ -23,8 +23,8 @@ def P():
 
 
 def _make(P, nr, opt, cathode="LCO"):
-    p = P.petlion(cathode, N_r_p=nr, N_r_n=nr, **{k: ("SEI" if k == "aging" else v) for k, v in opt.items()})
-    m = O.make_model(cathode, N_r_p=nr, N_r_n=nr, **opt)
+    p = P.petlion(cathode, Fickian_method="spectral", **{k: ("SEI" if k == "aging" else v) for k, v in opt.items()})
+    m = O.make_model(cathode, Fickian_method="spectral", **opt)
     return p, m
 
 
@@ -37,6 +37,8 @@ def test_pattern_and_resjac(P, family, nr, opt):
         cp, rv = O.jac_pattern(m, method)
         cp2, rv2 = p.jac_pattern(method)
         assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+    # 27 more entries per particle than the finite-difference scheme: the dense block (100 vs 82) and the j column (10 vs 1)
+    assert cp[-1] - O.jac_pattern(O.make_model("LCO", **opt), "P")[0][-1] == 27 * 20
     B = 6
     tho = util.oracle_theta_batch(B, first=900)
     th = util.product_theta_from_oracle(p, tho)
@@ -133,10 +135,10 @@ def test_newton_and_cccv(P, family, nr, opt):
     np.testing.assert_allclose(s2["SOC_end"], ref2["SOC_end"], rtol=2e-3)
 
 
-def test_nr_discharge_tight_and_nmc(P):
-    """1C discharges to the exit at reltol = abstol = 1e-9 (V at fixed times through both dense outputs, rtol 1e-6), N_r = 12;
-    and the NMC parameter set on N_r = 14."""
-    p, m = _make(P, 12, {})
+def test_spectral_discharge_tight_and_nmc(P):
+    """1C discharges to the exit at reltol = abstol = 1e-9 (V at fixed times through both dense outputs, rtol 1e-6); the NMC
+    parameter set; and the scheme against the finite-difference one: the same cell, a few mV apart at the end of a discharge."""
+    p, m = _make(P, 10, {})
     B = 16
     tho = util.oracle_theta_batch(B, first=77)
     util.set_theta_batch(p, util.product_theta_from_oracle(p, tho))
@@ -152,7 +154,13 @@ def test_nr_discharge_tight_and_nmc(P):
     assert both.mean() > 0.9
     np.testing.assert_allclose(sol.dense["V"][both], ref["dense"]["V"][both], rtol=1e-6)
     np.testing.assert_allclose(sol.dense["SOC"][both], ref["dense"]["SOC"][both], atol=1e-6)
-    pn, mn = _make(P, 14, {}, cathode="NMC")
+    pf = P.petlion("LCO")
+    util.set_theta_batch(pf, util.product_theta_from_oracle(pf, tho))
+    solf = P.simulate(pf, I=-1, SOC=1, n_save_max=0, dense_t=dense_t, reltol=tol, abstol=tol, reltol_init=tol, abstol_init=tol)
+    bothf = both & ~np.isnan(solf.dense["V"])
+    dV = np.abs(sol.dense["V"][bothf] - solf.dense["V"][bothf])
+    assert 1e-7 < dV.max() < 0.02, dV.max()
+    pn, mn = _make(P, 10, {}, cathode="NMC")
     thn = util.oracle_theta_batch(4, cathode="NMC")
     util.set_theta_batch(pn, util.product_theta_from_oracle(pn, thn))
     soln = P.simulate(pn, 1800, I=1, SOC=0)
