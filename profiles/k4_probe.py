@@ -1,5 +1,5 @@
 """Times the fused integrator (device-resident buffers, CUDA events) for the library named by PLB_LIB:
-quick A/B of build variants.  usage: PLB_LIB=... python profiles/k4_probe.py [B] [iso|thermal|sei|wide|wsei|wth|thsei|wthsei|mhc|lgm|lgmth]
+quick A/B of build variants.  usage: PLB_LIB=... python profiles/k4_probe.py [B] [iso|thermal|sei|wide|wsei|wth|thsei|wthsei|mhc|lgm|lgmth][_r12|_r14|_sp]
 (one segment: a 1C discharge for iso / wide / mhc, a 4C charge to 4.1 V for the thermal families, a 1C charge to 4.2 V for
 the SEI families)"""
 import ctypes as C, os, sys
@@ -11,12 +11,17 @@ from petlion_b200 import _lib
 from petlion_b200 import sweep  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 fam = sys.argv[2] if len(sys.argv) > 2 else "iso"
+sib = {}                       # sibling builds: N_r = 12 / 14, Fickian_method = :spectral
+if fam.endswith("_r12") or fam.endswith("_r14"):
+    sib = dict(N_r_p=int(fam[-2:]), N_r_n=int(fam[-2:])); fam = fam[:-4]
+elif fam.endswith("_sp"):
+    sib = dict(Fickian_method="spectral"); fam = fam[:-3]
 L = _lib.lib()
 grid = dict(N_p=20, N_s=20, N_n=20) if fam in ("wide", "wsei", "wth", "wthsei") else {}
 thermal = fam in ("thermal", "wth", "thsei", "wthsei", "lgmth")
 aging = fam in ("sei", "wsei", "thsei", "wthsei")
 rx = dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC") if fam == "mhc" else {}
-p = P.petlion("NMC_LGM50" if fam.startswith("lgm") else "LCO", temperature=thermal, aging="SEI" if aging else False, **grid, **rx)
+p = P.petlion("NMC_LGM50" if fam.startswith("lgm") else "LCO", temperature=thermal, aging="SEI" if aging else False, **grid, **rx, **sib)
 
 h = p._h; N = p.N.tot
 dev = torch.device("cuda", 0); f64 = dict(dtype=torch.float64, device=dev)
@@ -40,5 +45,5 @@ for k in range(4):
                               None, None, None, None, None, None, d_trn.data_ptr(), 1))
     ms.append(L.plb_last_kernel_ms(h))
 s = d_sum.cpu().numpy().view(_lib.SUMMARY_DTYPE).reshape(-1)
-print(os.path.basename(os.environ.get("PLB_LIB", "default")), fam, "B", B, "ms", [round(x, 1) for x in ms], "sims/s", round(B / (min(ms[1:]) * 1e-3)),
+print(os.path.basename(os.environ.get("PLB_LIB", "default")), fam, sib, "B", B, "ms", [round(x, 1) for x in ms], "sims/s", round(B / (min(ms[1:]) * 1e-3)),
       "steps", float(np.mean(s["n_steps"])), "chk", float(np.sum(s["V_end"][s["flag"] >= 0])), flush=True)

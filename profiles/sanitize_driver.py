@@ -6,12 +6,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P
 
-fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc,lgm").split(",")
+fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc,lgm,iso12,th14,sei14,isosp,thsp,seisp").split(",")
 for fam in fams:
     G = dict(N_p=20, N_s=20, N_n=20)
     kw = dict(iso={}, thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=G, wsei=dict(aging="SEI", **G),
               wth=dict(temperature=True, **G), thsei=dict(temperature=True, aging="SEI"),
-              wthsei=dict(temperature=True, aging="SEI", **G), mhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC"), lgm=dict(temperature=True))[fam]
+              wthsei=dict(temperature=True, aging="SEI", **G), mhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC"), lgm=dict(temperature=True),
+              # N_r = 12 / 14 and Fickian_method = :spectral sibling builds
+              iso12=dict(N_r_p=12, N_r_n=12), th14=dict(temperature=True, N_r_p=14, N_r_n=14), sei14=dict(aging="SEI", N_r_p=14, N_r_n=14),
+              isosp=dict(Fickian_method="spectral"), thsp=dict(temperature=True, Fickian_method="spectral"),
+              seisp=dict(aging="SEI", Fickian_method="spectral"))[fam]
     p = P.petlion("NMC_LGM50" if fam == "lgm" else "LCO", **kw)
     B = 5
     p.θ["D_sp"] = np.asarray(p.θ["D_sp"]) * np.linspace(0.8, 1.2, B)
