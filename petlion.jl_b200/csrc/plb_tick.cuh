@@ -42,6 +42,22 @@ namespace PLB_NS {
 #ifndef PLB_TICK_SYNC_EVERY
 #define PLB_TICK_SYNC_EVERY 1     // barrier every n-th tick (A/B knob)
 #endif
+// Every evaluation of a tick runs the residual+Jacobian instantiation lane_eval<true>, whether its warp factorises in this tick or
+// not: ONE copy of the heaviest phase in the tick's instruction stream, and the factorising warps no longer leave the common
+// stream at its start (alone on their own copy they were the stragglers every other warp waited for at the next barrier).
+// ~800 more instructions for the warps that do not need the Jacobian, and still (sims/s, one B200, 0 -> 1): iso 331 k -> 363 k,
+// thermal 136 k -> 154 k, sei 258 k -> 286 k, thsei 92 k -> 104 k, wide SEI 115 k -> 127 k, NMC_LGM50 thermal 100 k -> 120 k
+// (profiles/README.md).  A warp's arithmetic still depends on its own state only.
+#ifndef PLB_TICK_ONE_EVAL
+#define PLB_TICK_ONE_EVAL 1
+#endif
+// A Newton iteration that needs lsetup takes TWO ticks: evaluate + factorise in the first, evaluate + solve + glue in the second
+// (the same evaluation again: same state, same instantiation, same bits -- results do not change).  The factorisation then
+// runs NEXT TO the other warps' solve + glue instead of before the factorising warp's own, and no warp is left alone on the tail
+// of a tick with every other warp of the CTA waiting for it at the next barrier.
+#ifndef PLB_TICK_SPLIT_LSETUP
+#define PLB_TICK_SPLIT_LSETUP 0
+#endif
 #ifndef PLB_TICK_VOTE_JAC
 #define PLB_TICK_VOTE_JAC 0       // CTA-wide vote "does any warp factorise in this tick?": 225 k with, 229 k without
 #endif
@@ -816,7 +832,7 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 for (int r = 0; r < NR; r++) { y.cs[r] += e.cs[r]; yp.cs[r] = yp.cs[r] + cj * e.cs[r]; }
                 // (the algebraic components of y' never enter a residual)
                 yp.j = 0.0; yp.pe = 0.0; yp.ps = 0.0; yp.js = 0.0;
-                need_jac = S.callLSetup != 0; do_solve = true;
+                need_jac = S.callLSetup != 0; do_solve = !(PLB_TICK_SPLIT_LSETUP && need_jac);
             } else {
                 load_lane(m, ro, w.v(V_PHI0), y, Iy);
                 alg_only = true;
@@ -861,10 +877,14 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
             if (need_jac) lane_eval_ni<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
             else lane_eval_ni<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
 #else
+#if PLB_TICK_ONE_EVAL
+            lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
+#else
             if (need_jac) lane_eval<CHEM, true>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
             else lane_eval<CHEM, false>(m, w.C, ro, y, yp, Iy, meth, S.rc.value, res, ctrl, J);
 #endif
-            if (lane == 0) S.M.nre++;
+#endif
+            if (lane == 0 && (do_solve || S.state != ST_NLS)) S.M.nre++;      // (a split lsetup tick repeats its evaluation: counted once)
         }
         bool lsetup_bad = false;
         if (any_jac) {
@@ -910,7 +930,8 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
                 if (lsetup_bad) retval = 1;
                 else {
                     if (need_jac) { S.M.cjold = S.M.cj; S.M.cjratio = 1.0; S.M.ss = 20.0; S.jcur = 1; S.callLSetup = 0; }
-                    retval = nls_post(m, w, ro, a.o, S, res, dI, lane);
+                    if (PLB_TICK_SPLIT_LSETUP && need_jac) retval = -99;      // the iteration itself runs in the next tick, on these factors
+                    else retval = nls_post(m, w, ro, a.o, S, res, dI, lane);
                 }
                 if (retval > 0 && !S.jcur && !lsetup_bad) {
                     // recoverable failure with a stale Jacobian: redo once with a fresh one

@@ -1,11 +1,19 @@
 #!/bin/bash
 # A/B builds: profiles/build_variant.sh NAME -DPLB_X=...   ->  profiles/variants/libplb_NAME.so  (use with PLB_LIB=...)
+# PLB_AB_UNITS="plb_variant_iso plb_variant_th": only these units are compiled with the extra flags, the others are taken from
+# the default build's objects (petlion.jl_b200/csrc/*.o)
 set -e
 cd "$(dirname "$0")/../petlion.jl_b200/csrc"
 name=$1; shift
 out=../../profiles/variants; mkdir -p $out/obj_$name
-for u in plb_kernels plb_variant_iso plb_variant_th plb_variant_sei plb_variant_wide plb_variant_wsei plb_variant_wth plb_variant_thsei plb_variant_wthsei plb_variant_isodc plb_variant_widedc plb_variant_isomhc plb_variant_thmhc plb_variant_seimhc plb_variant_isolgm plb_variant_thlgm; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c -o $out/obj_$name/$u.o $u.cu &
+all=$(ls plb_kernels.cu plb_variant_*.cu | sed 's/\.cu$//')
+units=$(echo ${PLB_AB_UNITS:-$all})
+for u in $all; do
+  if echo " $units " | grep -q " $u "; then
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c -o $out/obj_$name/$u.o $u.cu &
+  else
+    cp $u.o $out/obj_$name/$u.o
+  fi
 done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libplb_$name.so $out/obj_$name/*.o

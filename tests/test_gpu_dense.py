@@ -27,7 +27,11 @@ def test_dense_rows_equal_oracle_interpolant(P):
     ref = O.simulate_batch(m, tho, O.make_run("I", -1.0), O.default_opts(), O.default_bounds("LCO"), SOC0=1.0,
                            nthreads=8, dense_t=td, dense_Y=True)
     s = sol.results[-1].summary
-    same = (s["n_steps"] == ref["n_steps"]) & (s["flag"] == ref["flag"])
+    # the same decisions: EVERY counter agrees (equal step counts alone can hide an error-test failure on one side and a
+    # convergence failure on the other: then the step times differ and so do the rows, at the integrator's tolerance)
+    same = np.ones(B, dtype=bool)
+    for c in ("flag", "n_steps", "n_res", "n_jac", "n_netf", "n_ncfn"):
+        same &= s[c] == ref[c]
     assert same.mean() > 0.9
     d, r = sol.dense, ref["dense"]
     assert np.array_equal(d["n"][same], r["n"][same])
