@@ -58,6 +58,9 @@ namespace PLB_NS {
 #ifndef PLB_TICK_SPLIT_LSETUP
 #define PLB_TICK_SPLIT_LSETUP 0
 #endif
+#ifndef PLB_TICK_SYNC_STEP
+#define PLB_TICK_SYNC_STEP 0
+#endif
 #ifndef PLB_TICK_VOTE_JAC
 #define PLB_TICK_VOTE_JAC 0       // CTA-wide vote "does any warp factorise in this tick?": 225 k with, 229 k without
 #endif
@@ -854,6 +857,11 @@ __device__ __forceinline__ void simulate_cta(const SimArgs& a, unsigned char* sm
 #if PLB_TICK_SYNC_START
 #if PLB_TICK_SYNC_EVERY > 1
         if ((tick_no++ % PLB_TICK_SYNC_EVERY) == 0) { if (!__syncthreads_or(do_eval)) break; }
+#elif PLB_TICK_SYNC_STEP
+        // one barrier per step ATTEMPT, not per evaluation: the second and later Newton iterations of an attempt follow
+        // the first without one (every warp passes the same number of barriers: between two of them it runs one attempt,
+        // or one evaluation of the initialisation, or nothing)
+        if (!(S.state == ST_NLS && S.mi > 0)) { if (!__syncthreads_or(do_eval)) break; }
 #else
         if (!__syncthreads_or(do_eval)) break;
 #endif
