@@ -41,7 +41,9 @@ def build(force=False, verbose=False):
     units = ("plb_kernels.cu", "plb_variant_iso.cu", "plb_variant_th.cu", "plb_variant_sei.cu",
              "plb_variant_wide.cu", "plb_variant_wsei.cu", "plb_variant_wth.cu", "plb_variant_thsei.cu", "plb_variant_wthsei.cu", "plb_variant_isodc.cu", "plb_variant_widedc.cu", "plb_variant_isomhc.cu", "plb_variant_thmhc.cu", "plb_variant_seimhc.cu", "plb_variant_isolgm.cu", "plb_variant_thlgm.cu",
              "plb_variant_iso_r12.cu", "plb_variant_th_r12.cu", "plb_variant_sei_r12.cu", "plb_variant_iso_r14.cu", "plb_variant_th_r14.cu", "plb_variant_sei_r14.cu",
-             "plb_variant_iso_sp.cu", "plb_variant_th_sp.cu", "plb_variant_sei_sp.cu")
+             "plb_variant_iso_sp.cu", "plb_variant_th_sp.cu", "plb_variant_sei_sp.cu",
+             "plb_variant_widemhc.cu", "plb_variant_wseimhc.cu", "plb_variant_wthmhc.cu", "plb_variant_thseimhc.cu", "plb_variant_wthseimhc.cu",
+             "plb_variant_widelgm.cu", "plb_variant_wthlgm.cu")
     srcs = [os.path.join(CSRC, f) for f in units + ("plb_common.cuh", "plb_variant.cuh", "plb_device.cuh",
                                                     "plb_integrator.cuh", "plb_tick.cuh", "laws_generated.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))

@@ -200,5 +200,12 @@ PLB_DECLARE_VARIANT(sei14)
 PLB_DECLARE_VARIANT(isosp)
 PLB_DECLARE_VARIANT(thsp)
 PLB_DECLARE_VARIANT(seisp)
+PLB_DECLARE_VARIANT(widemhc)
+PLB_DECLARE_VARIANT(wseimhc)
+PLB_DECLARE_VARIANT(wthmhc)
+PLB_DECLARE_VARIANT(thseimhc)
+PLB_DECLARE_VARIANT(wthseimhc)
+PLB_DECLARE_VARIANT(widelgm)
+PLB_DECLARE_VARIANT(wthlgm)
 
 }  // namespace plb

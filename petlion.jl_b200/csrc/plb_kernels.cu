@@ -139,6 +139,35 @@ static const Variant V_ISODC = {isodc::info, isodc::slot_rc, isodc::slot_recipe,
 static const Variant V_WIDEDC = {widedc::info, widedc::slot_rc, widedc::slot_recipe, widedc::launch_resjac, widedc::launch_initguess,
                                  widedc::launch_newton, widedc::launch_linsolve, widedc::launch_simulate};
 
+// the rest of the option matrix: rxn_MHC on the two-warp grids and with temperature + aging, NMC_LGM50 on the two-warp grids
+static const Variant V_WIDEMHC = PLB_VARIANT_TABLE(widemhc);
+static const Variant V_WSEIMHC = PLB_VARIANT_TABLE(wseimhc);
+static const Variant V_WTHMHC = PLB_VARIANT_TABLE(wthmhc);
+static const Variant V_THSEIMHC = PLB_VARIANT_TABLE(thseimhc);
+static const Variant V_WTHSEIMHC = PLB_VARIANT_TABLE(wthseimhc);
+static const Variant V_WIDELGM = PLB_VARIANT_TABLE(widelgm);
+static const Variant V_WTHLGM = PLB_VARIANT_TABLE(wthlgm);
+
+// which compiled family runs an option set: (temperature, aging, two warps per system, rxn_MHC compiled in, NMC_LGM50 chemistry,
+// N_r, spectral particle scheme).  Like the reference, which generates one set of functions per option string
+// (strings_directory_func, external.jl:417-456), every row is its own instantiation of the same templates.
+struct VEntry { int th, sei, wide, mhc, lgm, nr, sp; const Variant* v; };
+static const VEntry VTAB[] = {
+    {0, 0, 0, 0, 0, 10, 0, &V_ISO},    {1, 0, 0, 0, 0, 10, 0, &V_TH},    {0, 1, 0, 0, 0, 10, 0, &V_SEI},    {1, 1, 0, 0, 0, 10, 0, &V_THSEI},
+    {0, 0, 1, 0, 0, 10, 0, &V_WIDE},   {1, 0, 1, 0, 0, 10, 0, &V_WTH},   {0, 1, 1, 0, 0, 10, 0, &V_WSEI},   {1, 1, 1, 0, 0, 10, 0, &V_WTHSEI},
+    {0, 0, 0, 1, 0, 10, 0, &V_ISOMHC}, {1, 0, 0, 1, 0, 10, 0, &V_THMHC}, {0, 1, 0, 1, 0, 10, 0, &V_SEIMHC}, {1, 1, 0, 1, 0, 10, 0, &V_THSEIMHC},
+    {0, 0, 1, 1, 0, 10, 0, &V_WIDEMHC}, {1, 0, 1, 1, 0, 10, 0, &V_WTHMHC}, {0, 1, 1, 1, 0, 10, 0, &V_WSEIMHC}, {1, 1, 1, 1, 0, 10, 0, &V_WTHSEIMHC},
+    {0, 0, 0, 0, 1, 10, 0, &V_ISOLGM}, {1, 0, 0, 0, 1, 10, 0, &V_THLGM}, {0, 0, 1, 0, 1, 10, 0, &V_WIDELGM}, {1, 0, 1, 0, 1, 10, 0, &V_WTHLGM},
+    {0, 0, 0, 0, 0, 12, 0, &V_ISO12},  {1, 0, 0, 0, 0, 12, 0, &V_TH12},  {0, 1, 0, 0, 0, 12, 0, &V_SEI12},
+    {0, 0, 0, 0, 0, 14, 0, &V_ISO14},  {1, 0, 0, 0, 0, 14, 0, &V_TH14},  {0, 1, 0, 0, 0, 14, 0, &V_SEI14},
+    {0, 0, 0, 0, 0, 10, 1, &V_ISOSP},  {1, 0, 0, 0, 0, 10, 1, &V_THSP},  {0, 1, 0, 0, 0, 10, 1, &V_SEISP},
+};
+static const Variant* find_variant(int th, int sei, int wide, int mhc, int lgm, int nr, int sp) {
+    for (const VEntry& e : VTAB)
+        if (e.th == th && e.sei == sei && e.wide == wide && e.mhc == mhc && e.lgm == lgm && e.nr == nr && e.sp == sp) return e.v;
+    return nullptr;
+}
+
 struct plb_handle_s {
     plb_model_desc desc;
     ModelDesc m;
@@ -244,7 +273,6 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
         return fail("plb_create: need 2 <= N_p,N_s,N_n and N_p+N_s+N_n <= 64 (one lane per node, one or two warps per system)");
     if (d->cathode != PLB_CATHODE_LCO && d->cathode != PLB_CATHODE_NMC && d->cathode != PLB_CATHODE_NMC_LGM50) return fail("plb_create: unknown cathode");
     const bool lgm = d->cathode == PLB_CATHODE_NMC_LGM50;
-    if (lgm && Nx_ > 32) return fail("plb_create: NMC_LGM50 is built for grids of up to 32 x-nodes");
     if ((d->rxn_p != PLB_RXN_BV && d->rxn_p != PLB_RXN_MHC) || (d->rxn_n != PLB_RXN_BV && d->rxn_n != PLB_RXN_MHC))
         return fail("plb_create: unknown reaction rate law (built: rxn_BV, rxn_MHC)");
     // NMC() / LiC6_NMC() define no lambda_MHC_* (params.jl:295-367): the reference throws a KeyError there
@@ -260,24 +288,20 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
     const int Ntot_ = 2 * Nx_ + (NR_HOST + 2) * (d->N_p + d->N_n) + 1 + (d->aging ? 2 * d->N_n + 1 : 0);
     const int NtotT_ = Ntot_ + (d->temperature ? d->N_a + Nx_ + d->N_z : 0);
-    const bool both = d->temperature && d->aging;
-    const Variant* narrow = both ? &V_THSEI : (d->temperature ? &V_TH : (d->aging ? &V_SEI : &V_ISO));
-    if (NR_HOST != 10) {
-        const bool r12 = NR_HOST == 12;
-        narrow = narrow == &V_ISO ? (r12 ? &V_ISO12 : &V_ISO14) : (narrow == &V_TH ? (r12 ? &V_TH12 : &V_TH14) : (narrow == &V_SEI ? (r12 ? &V_SEI12 : &V_SEI14) : nullptr));
-        if (!narrow || lgm || d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC || Nx_ > 32 || NtotT_ > narrow->info().vs)
+    const int want_mhc = (d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) ? 1 : 0;
+    if (d->fickian_spectral != 0 && d->fickian_spectral != 1) return fail("plb_create: unknown Fickian_method (0 = :finite_difference, 1 = :spectral)");
+    const Variant* narrow = find_variant(d->temperature ? 1 : 0, d->aging ? 1 : 0, 0, want_mhc, lgm ? 1 : 0, NR_HOST, d->fickian_spectral);
+    const bool wide = Nx_ > 32 || !narrow || NtotT_ > narrow->info().vs;
+    const Variant* chosen = wide ? find_variant(d->temperature ? 1 : 0, d->aging ? 1 : 0, 1, want_mhc, lgm ? 1 : 0, NR_HOST, d->fickian_spectral) : narrow;
+    if (chosen && NtotT_ > chosen->info().vs) chosen = nullptr;
+    if (!chosen) {
+        if (NR_HOST != 10)
             return fail("plb_create: N_r = 12 / 14 is built for the isothermal, thermal and SEI families on up to 32 x-nodes (LCO / NMC, rxn_BV)");
-    }
-    if (d->fickian_spectral) {
-        // Fickian_method = :spectral (params.jl:142; residuals.jl:181-235, "BETA"): sibling builds of the 32-node families
-        if (d->fickian_spectral != 1) return fail("plb_create: unknown Fickian_method (0 = :finite_difference, 1 = :spectral)");
-        narrow = NR_HOST != 10 ? nullptr : (narrow == &V_ISO ? &V_ISOSP : (narrow == &V_TH ? &V_THSP : (narrow == &V_SEI ? &V_SEISP : nullptr)));
-        if (!narrow || lgm || d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC || Nx_ > 32 || NtotT_ > narrow->info().vs)
+        if (d->fickian_spectral)
+            // Fickian_method = :spectral (params.jl:142; residuals.jl:181-235, "BETA"): sibling builds of the 32-node families
             return fail("plb_create: Fickian_method = :spectral is built for the isothermal, thermal and SEI families on up to 32 x-nodes (LCO / NMC, rxn_BV, N_r = 10)");
+        return fail("plb_create: no compiled family for this combination of options (system too large for the workspace stride?)");
     }
-    const bool wide = Nx_ > 32 || NtotT_ > narrow->info().vs;
-    if ((d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) && (wide || both))
-        return fail("plb_create: rxn_MHC is built for grids of up to 32 x-nodes, with temperature=true or aging=:SEI but not both");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plb_create: no CUDA device available (this library has no CPU fallback)");
@@ -294,19 +318,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     } while (0)
     // one warp per system up to 32 x-nodes, unless the state vector outgrows that family's workspace stride
     // (many electrode nodes: N = 2 Nx + 12 Ne + 1): then the two-warp family runs it with its upper lanes idle
-    h->v = both ? (wide ? &V_WTHSEI : &V_THSEI)
-                : (d->temperature ? (wide ? &V_WTH : &V_TH) : (wide ? (d->aging ? &V_WSEI : &V_WIDE) : (d->aging ? &V_SEI : &V_ISO)));
-    if (NR_HOST != 10 || d->fickian_spectral) h->v = narrow;
-    if (lgm) h->v = h->v == &V_ISO ? &V_ISOLGM : (h->v == &V_TH ? &V_THLGM : nullptr);
-    if (!h->v) { delete h; return fail("plb_create: NMC_LGM50 is built for the isothermal and thermal families on up to 32 x-nodes"); }
-    if (d->rxn_p == PLB_RXN_MHC || d->rxn_n == PLB_RXN_MHC) {
-        const Variant* mv = h->v == &V_ISO ? &V_ISOMHC : (h->v == &V_TH ? &V_THMHC : (h->v == &V_SEI ? &V_SEIMHC : nullptr));
-        if (!mv) {
-            delete h;
-            return fail("plb_create: rxn_MHC is built for grids of up to 32 x-nodes, with temperature=true or aging=:SEI but not both");
-        }
-        h->v = mv;
-    }
+    h->v = chosen;
     h->has_dT = d->temperature != 0;
     h->vi = h->v->info();
     if (h->v == &V_ISO) h->v_dc = &V_ISODC;

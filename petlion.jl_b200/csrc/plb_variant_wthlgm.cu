@@ -1,0 +1,7 @@
+// NMC_LGM50 / LiC6_LGM50 (params.jl:514-849), temperature = true, on 33..64 x-nodes: the two-warp thermal family instantiated for that chemistry only
+#define PLB_TH 1
+#define PLB_SEI 0
+#define PLB_WIDE 1
+#define PLB_ONLY_CHEM CHEM_LGM
+#define PLB_NS wthlgm
+#include "plb_variant.cuh"

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import petlion_b200 as P
 
-fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc,lgm,iso12,th14,sei14,isosp,thsp,seisp").split(",")
+fams = os.environ.get("SAN_FAMILIES", "iso,thermal,sei,wide,wsei,wth,thsei,wthsei,mhc,lgm,iso12,th14,sei14,isosp,thsp,seisp,widemhc,thseimhc,wthlgm").split(",")
 for fam in fams:
     G = dict(N_p=20, N_s=20, N_n=20)
     kw = dict(iso={}, thermal=dict(temperature=True), sei=dict(aging="SEI"), wide=G, wsei=dict(aging="SEI", **G),
@@ -14,9 +14,11 @@ for fam in fams:
               wthsei=dict(temperature=True, aging="SEI", **G), mhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC"), lgm=dict(temperature=True),
               # N_r = 12 / 14 and Fickian_method = :spectral sibling builds
               iso12=dict(N_r_p=12, N_r_n=12), th14=dict(temperature=True, N_r_p=14, N_r_n=14), sei14=dict(aging="SEI", N_r_p=14, N_r_n=14),
+              widemhc=dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC", **G), thseimhc=dict(temperature=True, aging="SEI", rxn_p="rxn_MHC", rxn_n="rxn_MHC"),
+              wthlgm=dict(temperature=True, **G),
               isosp=dict(Fickian_method="spectral"), thsp=dict(temperature=True, Fickian_method="spectral"),
               seisp=dict(aging="SEI", Fickian_method="spectral"))[fam]
-    p = P.petlion("NMC_LGM50" if fam == "lgm" else "LCO", **kw)
+    p = P.petlion("NMC_LGM50" if fam in ("lgm", "wthlgm") else "LCO", **kw)
     B = 5
     p.θ["D_sp"] = np.asarray(p.θ["D_sp"]) * np.linspace(0.8, 1.2, B)
     sol = P.simulate(p, 200, I=1, SOC=0.1)                                             # plain kernel
@@ -28,7 +30,7 @@ for fam in fams:
     st, Y, YP = p.newton_init(Y0, method="I", value=1.0)
     res, nz = p.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)                  # K1 (TMA-staged where built)
     os.environ["PLB_K1_NO_TMA"] = "1"
-    p_old = P.petlion("NMC_LGM50" if fam == "lgm" else "LCO", **kw); p_old.θ["D_sp"] = p.θ["D_sp"]
+    p_old = P.petlion("NMC_LGM50" if fam in ("lgm", "wthlgm") else "LCO", **kw); p_old.θ["D_sp"] = p.θ["D_sp"]
     res_b, nz_b = p_old.resjac(Y, YP, np.full(B, 0.1), method="I", value=1.0)           # K1, per-lane loads
     del os.environ["PLB_K1_NO_TMA"]
     assert np.array_equal(res, res_b) and np.array_equal(nz, nz_b)

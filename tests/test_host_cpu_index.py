@@ -49,8 +49,9 @@ def test_table_host_semantics_match_the_oracle_table():
     (dict(N_r_p=12, N_r_n=12, N_p=20, N_s=20, N_n=20), "N_r = 12 / 14 is built for"),
     (dict(N_r_p=14, N_r_n=14, temperature=True, aging="SEI"), "N_r = 12 / 14 is built for"),
     (dict(N_r_p=12, N_r_n=12, rxn_p="rxn_MHC"), "N_r = 12 / 14 is built for"),
-    (dict(rxn_p="rxn_MHC", N_p=20, N_s=10, N_n=20), "rxn_MHC is built for grids of up to 32"),
-    (dict(rxn_n="rxn_MHC", temperature=True, aging="SEI"), "rxn_MHC is built for"),
+    (dict(Fickian_method="spectral", N_p=20, N_s=20, N_n=20), "Fickian_method = :spectral is built for"),
+    (dict(Fickian_method="spectral", temperature=True, aging="SEI"), "Fickian_method = :spectral is built for"),
+    (dict(Fickian_method="spectral", N_r_p=12, N_r_n=12), "N_r = 12 / 14 is built for"),
     (dict(N_p=30, N_s=10, N_n=30), "<= 64"),
     (dict(N_p=1), "2 <= N_p"),
     (dict(temperature=True, N_p=4), "N_p, N_n >= 5"),
