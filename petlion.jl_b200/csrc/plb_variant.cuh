@@ -686,13 +686,15 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // 32-lane families (measured, iso, sims/s on one B200: 6x1 229 k, 3x2 213 k, 2x3 200 k).
 // (round 2: six vectors per system in shared memory instead of ten: 8 / 6 / 5 systems per SM instead of 6 / 5 / 4)
 #if PLB_NR == 10
-#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 5) : (PLB_SEI ? 6 : 8)))
+// (wide SEI: its three systems per SM as three groups of ONE CTA, one tick barrier for all of them: 125.8 k -> 134.3 k sims/s;
+//  wide iso keeps three CTAs of one group: 138.6 k vs 137.1 k)
+#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 3 : 1) : (PLB_TH ? (PLB_SEI ? 3 : 5) : (PLB_SEI ? 6 : 8)))
 #else   // N_r = 12 / 14 siblings: longer vectors and larger particle inverses per system
 #define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 4) : (PLB_SEI ? 5 : 6)))
 #endif
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 1 : 2) : 3) : 1)
+#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 1 : 2) : (PLB_SEI ? 1 : 3)) : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
