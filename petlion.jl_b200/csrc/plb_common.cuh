@@ -155,6 +155,7 @@ struct SimArgs {
 struct VariantInfo {
     int sim_warps, sim_ctas;        // warps per CTA / CTAs per SM of the persistent integrator
     int nr;                         // N_r (radial nodes per particle) this family is compiled for
+    int gws_per_slot;               // doubles of global workspace per system in flight
     int k1_warps, k1_ctas;
     size_t sim_smem, k1_smem;       // dynamic shared memory per CTA
     int vs, nglobal;                // workspace vector stride, history vectors parked in global memory

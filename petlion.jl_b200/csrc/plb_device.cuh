@@ -1013,6 +1013,7 @@ __device__ __forceinline__ void inv3x3(const double* a, double* o) {
 //   4. the applied-current unknown I is a border (Schur complement), which also covers the
 //      zero-diagonal control row of voltage/power control (scalar_residual.jl:184-197)
 // ------------------------------------------------------------------------------------------------
+constexpr int FA_GLOBAL = 0;   // (thermal families: the factored blocks live in the global workspace)
 struct WarpFactor {
     double Sinv[NR * NR][2];   // [r*NR+c][electrode 0=p,1=n]
     double vb[NR][2];          // Sinv * b (b = surface-row j coupling)
@@ -1480,8 +1481,20 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 //      and into the last back-substitution step) -- exact, no fill outside the block tridiagonal;
 //   5. the applied current is a border, as in the isothermal variant.
 // ------------------------------------------------------------------------------------------------
+// The factored 4x4 blocks (Dinv, W, P: 48 doubles per lane, 12 KB per system) live in the system's slot of the GLOBAL workspace
+// (L2-resident), not in shared memory: they are written once per factorisation and read once at the head of a solve (48
+// independent coalesced loads per lane), and those 12 KB were what held the thermal families at 5 / 3 systems per SM.
+#ifndef PLB_TH_BLOCKS_GLOBAL
+#define PLB_TH_BLOCKS_GLOBAL 1
+#endif
+constexpr int FA_GLOBAL = PLB_TH_BLOCKS_GLOBAL ? 48 * LW : 0;      // doubles per system slot of the global workspace
 struct WarpFactor {
+#if PLB_TH_BLOCKS_GLOBAL
+    double* blk;               // [3][16][LW]: Dinv, Wm, Pm
+    double* pad_blk;
+#else
     double Dinv[16][LW], Wm[16][LW], Pm[16][LW];
+#endif
     double Fr[4][LW];          // T-row multiplier for the node two behind in the chain
     double Eo[3][LW];          // chain heads: T-row coupling to (c_e, Phi_e, Phi_s) two nodes ahead
     double z[4][LW], zx[LW];   // border column solution
@@ -1939,8 +1952,16 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
             for (int k = 0; k < 16; k++) Pm[k] = Wr[k];
         }
     }
+#if PLB_TH_BLOCKS_GLOBAL
+    {
+        double* const gb = Fa.blk;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { gb[k * LW + lane] = Di[k]; gb[(16 + k) * LW + lane] = Wm[k]; gb[(32 + k) * LW + lane] = Pm[k]; }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 16; k++) { Fa.Dinv[k][lane] = Di[k]; Fa.Wm[k][lane] = Wm[k]; Fa.Pm[k][lane] = Pm[k]; }
+#endif
 #pragma unroll
     for (int k = 0; k < 4; k++) Fa.Fr[k][lane] = Fr[k];
 #pragma unroll
@@ -2030,8 +2051,16 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 #endif
     if (!ro.act) { rb[0] = rb[1] = rb[2] = rb[3] = 0.0; }
     double Di[16], Wm[16], Pm[16];
+#if PLB_TH_BLOCKS_GLOBAL
+    {
+        const double* const gb = Fa.blk;
+#pragma unroll
+        for (int k = 0; k < 16; k++) { Di[k] = gb[k * LW + lane]; Wm[k] = gb[(16 + k) * LW + lane]; Pm[k] = gb[(32 + k) * LW + lane]; }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 16; k++) { Di[k] = Fa.Dinv[k][lane]; Wm[k] = Fa.Wm[k][lane]; Pm[k] = Fa.Pm[k][lane]; }
+#endif
     double u4[4], ux;
     core_solve(m, ch, Fa, Di, Wm, Pm, rb, (ch.ch && dyn) ? g.Tx : 0.0, u4, ux, lane);
     // border

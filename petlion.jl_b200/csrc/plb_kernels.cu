@@ -325,7 +325,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (h->v == &V_WIDE) h->v_dc = &V_WIDEDC;
     if (h->v_dc) {
         const VariantInfo di = h->v_dc->info();      // same geometry and workspace: the two builds share every buffer
-        if (di.sim_warps != h->vi.sim_warps || di.sim_ctas != h->vi.sim_ctas || di.vs != h->vi.vs || di.nglobal != h->vi.nglobal) h->v_dc = nullptr;
+        if (di.sim_warps != h->vi.sim_warps || di.sim_ctas != h->vi.sim_ctas || di.vs != h->vi.vs || di.nglobal != h->vi.nglobal || di.gws_per_slot != h->vi.gws_per_slot) h->v_dc = nullptr;
     }
     ModelDesc& m = h->m;
     memset(&m, 0, sizeof m);
@@ -384,7 +384,7 @@ int plb_create(const plb_model_desc* d, plb_handle* out) {
     if (build_patterns(h)) { const std::string e = g_err; plb_destroy(h); return fail(e); }
     CREATE_OK(cudaMalloc(&h->d_counter, sizeof(int)));
     h->sim_grid = h->num_sms * h->vi.sim_ctas;
-    CREATE_OK(cudaMalloc(&h->d_gws, (size_t)h->sim_grid * h->vi.sim_warps * (h->vi.nglobal > 0 ? h->vi.nglobal : 1) * h->vi.vs * sizeof(double)));
+    CREATE_OK(cudaMalloc(&h->d_gws, (size_t)h->sim_grid * h->vi.sim_warps * h->vi.gws_per_slot * sizeof(double)));
     CREATE_OK(cudaEventCreate(&h->ev0));
     CREATE_OK(cudaEventCreate(&h->ev1));
 #undef CREATE_OK

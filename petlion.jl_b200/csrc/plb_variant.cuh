@@ -688,13 +688,15 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 #if PLB_NR == 10
 // (wide SEI: its three systems per SM as three groups of ONE CTA, one tick barrier for all of them: 125.8 k -> 134.3 k sims/s;
 //  wide iso keeps three CTAs of one group: 138.6 k vs 137.1 k)
-#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 3 : 1) : (PLB_TH ? (PLB_SEI ? 3 : 5) : (PLB_SEI ? 6 : 8)))
+// (second sitting: the thermal families keep their factored blocks in the global workspace: 6 / 5 systems per SM instead of 5 / 3,
+//  wide thermal 3 / 2 instead of 2 / 1)
+#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 3 : 1) : (PLB_TH ? (PLB_SEI ? 5 : 6) : (PLB_SEI ? 6 : 8)))
 #else   // N_r = 12 / 14 siblings: longer vectors and larger particle inverses per system
-#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 3 : 4) : (PLB_SEI ? 5 : 6)))
+#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 4 : 5) : (PLB_SEI ? 5 : 6)))
 #endif
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 1 : 2) : (PLB_SEI ? 1 : 3)) : 1)
+#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 2 : 3) : (PLB_SEI ? 1 : 3)) : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
@@ -705,11 +707,17 @@ constexpr int SIM_CTAS = PLB_SIM_CTAS;
 constexpr size_t STATE_BYTES = PLB_STATE_SMEM ? 480 : 0;           // per physical warp
 constexpr size_t STATE_OFFSET = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
 constexpr size_t SIM_SMEM = STATE_OFFSET + STATE_BYTES * SIM_WARPS * (LW / 32);
+// doubles per system slot of the global workspace: the history vectors parked there + (thermal) the factored blocks
+constexpr int GWS_PER_SLOT = (NGLOBAL > 0 ? NGLOBAL : 1) * VS + FA_GLOBAL;
 static_assert(SIM_SMEM <= 227 * 1024, "the integrator's shared memory exceeds one SM: lower PLB_SIM_WARPS for this family");
 
 __device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw + XCH_BYTES_PER_GROUP * SIM_WARPS)[warp];
-    double* g = gws + ((size_t)blockIdx.x * SIM_WARPS + warp) * (size_t)(NGLOBAL > 0 ? NGLOBAL : 1) * VS;
+    double* g = gws + ((size_t)blockIdx.x * SIM_WARPS + warp) * (size_t)GWS_PER_SLOT;
+#if PLB_TH && PLB_TH_BLOCKS_GLOBAL
+    sm.Fa.blk = g + (size_t)(NGLOBAL > 0 ? NGLOBAL : 1) * VS;     // (every lane of the group writes the same pointer)
+    grp_sync();
+#endif
     return WarpWS{g, &sm.svec[0][0], sm.C, sm.Fa, sm.K};
 }
 
@@ -859,6 +867,7 @@ VariantInfo info() {
     v.n_slots = JS_COUNT; v.n_stage = K1_NSTAGE; v.k1_src_max = K1_SRC_MAX; v.lanes = LW;
     v.k1_tma = (!WIDE && !TH && (!SEI || PLB_SEI_TMA)) ? 1 : 0;
     v.nr = NR;
+    v.gws_per_slot = GWS_PER_SLOT;
     return v;
 }
 
