@@ -1013,14 +1013,26 @@ __device__ __forceinline__ void inv3x3(const double* a, double* o) {
 //   4. the applied-current unknown I is a border (Schur complement), which also covers the
 //      zero-diagonal control row of voltage/power control (scalar_residual.jl:184-197)
 // ------------------------------------------------------------------------------------------------
-constexpr int FA_GLOBAL = 0;   // (thermal families: the factored blocks live in the global workspace)
+// The factored 3x3 blocks (Dinv, W, P: 27 doubles per lane, 6.9 KB per system) live in the system's slot of the GLOBAL workspace
+// (L2-resident), like the thermal families' 4x4 blocks: written once per factorisation, read once at the head of a solve (27
+// independent coalesced loads per lane).  The shared memory they occupied holds phi_4 / phi_5 again (PLB_NGLOBAL = 0), which the
+// BDF vector passes touch far more often.
+#ifndef PLB_BLOCKS_GLOBAL
+#define PLB_BLOCKS_GLOBAL 1
+#endif
+constexpr int FA_GLOBAL = PLB_BLOCKS_GLOBAL ? 27 * LW : 0;      // doubles per system slot of the global workspace
 struct WarpFactor {
     double Sinv[NR * NR][2];   // [r*NR+c][electrode 0=p,1=n]
     double vb[NR][2];          // Sinv * b (b = surface-row j coupling)
     // per-lane data [field][lane]
+#if PLB_BLOCKS_GLOBAL
+    double* blk;               // [3][9][LW]: Dinv, Wm, Pm (below)
+    double* pad_blk;
+#else
     double Dinv[9][LW];        // inverse of the pivoted 3x3 diagonal block D'_x
     double Wm[9][LW];          // W_x = L_x * Dinv_{x-1}     (forward sweep:  y_x = r_x - W_x y_{x-1})
     double Pm[9][LW];          // P_x = Dinv_x * U_x         (backward sweep: u_x = Dinv_x y_x - P_x u_{x+1})
+#endif
     double z[3][LW];           // T^{-1} e_I  (border column)
     double q[4][LW];           // j elimination: q_ce, q_pe, q_ps, inv_den
     double jcs[LW];            // a_cs (j row coefficient of the surface concentration)
@@ -1307,8 +1319,16 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
             for (int k = 0; k < 9; k++) Pm[k] = Wr[k];
         }
     }
+#if PLB_BLOCKS_GLOBAL
+    {
+        double* const gb = Fa.blk;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { gb[k * LW + lane] = Di[k]; gb[(9 + k) * LW + lane] = Wm[k]; gb[(18 + k) * LW + lane] = Pm[k]; }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 9; k++) { Fa.Dinv[k][lane] = Di[k]; Fa.Wm[k][lane] = Wm[k]; Fa.Pm[k][lane] = Pm[k]; }
+#endif
     // ---- 4. border: z = T^{-1} e_I, then the Schur complement ------------------------------------
 #if PLB_SEI
     // border column dF/dI: the Phi_s end rows, plus (through dj + dj_s) the I-dependence of the j_s rows
@@ -1414,8 +1434,16 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     rf[2] = (ro.elec ? g.ps : 0.0) - Fa.sj[2][lane] * q0;
     if (!ro.act) { rf[0] = rf[1] = rf[2] = 0.0; }
     double Di[9], Wm[9], Pm[9];
+#if PLB_BLOCKS_GLOBAL
+    {
+        const double* const gb = Fa.blk;
+#pragma unroll
+        for (int k = 0; k < 9; k++) { Di[k] = gb[k * LW + lane]; Wm[k] = gb[(9 + k) * LW + lane]; Pm[k] = gb[(18 + k) * LW + lane]; }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 9; k++) { Di[k] = Fa.Dinv[k][lane]; Wm[k] = Fa.Wm[k][lane]; Pm[k] = Fa.Pm[k][lane]; }
+#endif
     double u3[3];
     const LaneChain ch = make_chain(m.Nx, lane);
     double dI;

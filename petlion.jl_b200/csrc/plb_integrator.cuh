@@ -37,8 +37,15 @@ struct IdaCoef {
 // LAST PLB_NGLOBAL of phi_0..phi_5.  Measured order histogram of the 1C discharge batch: order 1: 6 %,
 // 2: 47 %, 3: 41 %, 4: 5 %, 5: 0.1 % -- phi_5 is hardly ever touched, phi_4 is written once per step at order 3
 // (a fire-and-forget store) and read when an order raise is considered.
+// (second sitting: with the factored blocks of the linear solve in the global workspace -- plb_device.cuh -- the isothermal, SEI,
+//  wide SEI and wide thermal+SEI families keep ALL history vectors in shared memory again, thermal and wide iso all but phi_5:
+//  iso 369 k -> 432 k sims/s at the same eight systems per SM; measured per family, profiles/ab_r3_blocks_global_geometry.txt)
 #ifndef PLB_NGLOBAL
-#define PLB_NGLOBAL 2
+#if PLB_WIDE
+#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 0 : 2) : (PLB_SEI ? 0 : 1))
+#else
+#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 2 : 1) : 0)
+#endif
 #endif
 constexpr int NGLOBAL = PLB_NGLOBAL;
 constexpr int NSHARED = V_COUNT - NGLOBAL;

@@ -690,13 +690,14 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 //  wide iso keeps three CTAs of one group: 138.6 k vs 137.1 k)
 // (second sitting: the thermal families keep their factored blocks in the global workspace: 6 / 5 systems per SM instead of 5 / 3,
 //  wide thermal 3 / 2 instead of 2 / 1)
-#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 3 : 1) : (PLB_TH ? (PLB_SEI ? 5 : 6) : (PLB_SEI ? 6 : 8)))
+//  ... and the isothermal families theirs: SEI 7 systems per SM instead of 6, wide iso 4 instead of 3)
+#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 3 : 1) : (PLB_TH ? (PLB_SEI ? 5 : 6) : (PLB_SEI ? 7 : 8)))
 #else   // N_r = 12 / 14 siblings: longer vectors and larger particle inverses per system
-#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 4 : 5) : (PLB_SEI ? 5 : 6)))
+#define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 4 : 5) : (PLB_SEI ? (PLB_NR == 12 ? 6 : 5) : (PLB_NR == 12 ? 7 : 6))))
 #endif
 #endif
 #ifndef PLB_SIM_CTAS
-#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 2 : 3) : (PLB_SEI ? 1 : 3)) : 1)
+#define PLB_SIM_CTAS (PLB_WIDE ? (PLB_TH ? (PLB_SEI ? 2 : 3) : (PLB_SEI ? 1 : 4)) : 1)
 #endif
 constexpr int SIM_WARPS = PLB_SIM_WARPS;
 constexpr int SIM_CTAS = PLB_SIM_CTAS;
@@ -714,7 +715,7 @@ static_assert(SIM_SMEM <= 227 * 1024, "the integrator's shared memory exceeds on
 __device__ __forceinline__ WarpWS make_ws(unsigned char* smem_raw, double* gws, int warp) {
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw + XCH_BYTES_PER_GROUP * SIM_WARPS)[warp];
     double* g = gws + ((size_t)blockIdx.x * SIM_WARPS + warp) * (size_t)GWS_PER_SLOT;
-#if PLB_TH && PLB_TH_BLOCKS_GLOBAL
+#if (PLB_TH && PLB_TH_BLOCKS_GLOBAL) || (!PLB_TH && PLB_BLOCKS_GLOBAL)
     sm.Fa.blk = g + (size_t)(NGLOBAL > 0 ? NGLOBAL : 1) * VS;     // (every lane of the group writes the same pointer)
     grp_sync();
 #endif
