@@ -1515,7 +1515,19 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 #ifndef PLB_TH_BLOCKS_GLOBAL
 #define PLB_TH_BLOCKS_GLOBAL 1
 #endif
-constexpr int FA_GLOBAL = PLB_TH_BLOCKS_GLOBAL ? 48 * LW : 0;      // doubles per system slot of the global workspace
+// ... and so do the particle reciprocals pd and the T column of the particle rows in the eigen-basis wT (2 N_r doubles per lane,
+// read twice per solve): 5 KB per system more
+#ifndef PLB_TH_PD_GLOBAL
+#define PLB_TH_PD_GLOBAL PLB_TH_BLOCKS_GLOBAL
+#endif
+constexpr int FA_GLOBAL = PLB_TH_BLOCKS_GLOBAL ? (48 + (PLB_TH_PD_GLOBAL ? 2 * NR : 0)) * LW : 0;      // doubles per system slot of the global workspace
+#if PLB_TH_PD_GLOBAL
+#define FA_PD(i) Fa.blk[(48 + (i)) * LW + lane]
+#define FA_WT(i) Fa.blk[(48 + NR + (i)) * LW + lane]
+#else
+#define FA_PD(i) Fa.pd[i][lane]
+#define FA_WT(i) Fa.wT[i][lane]
+#endif
 struct WarpFactor {
 #if PLB_TH_BLOCKS_GLOBAL
     double* blk;               // [3][16][LW]: Dinv, Wm, Pm
@@ -1530,8 +1542,10 @@ struct WarpFactor {
     double jcs[LW];
     double sj[4][LW];          // effective d(row)/dj for rows ce, pe, ps, T
     double tcs[LW];            // T-row coefficient of the surface concentration
+#if !PLB_TH_PD_GLOBAL
     double pd[NR][LW];         // 1 / (kap_x * EL_i - cj)
     double wT[NR][LW];         // EVI * (d res_cs / dT)
+#endif
     double csj[LW];
     double chm[LW], chip[LW], chup[LW], hm[LW];   // collector chains: multiplier, 1/pivot, successor coupling; end-node multiplier
     double gT[LW], gX[LW];     // dT control: border-row entries on this lane's T / collector T
@@ -1560,22 +1574,22 @@ __device__ __forceinline__ double border_dot(const ModelDesc& m, const WarpFacto
     if (Fa.g_eta != 0.0) g += Fa.g_eta * shfl_from(u4[2] - u4[1], m.Np + m.Ns);
     if (mode == 1) g += warp_sum(Fa.gT[lane] * u4[3] + Fa.gX[lane] * ux);
     if (mode == 2) {
-        double a = Fa.pd[0][lane] * dj;
+        double a = FA_PD(0) * dj;
 #if PLB_SEI
         a = fma(Fa.pdjs[lane], djs, a);
 #else
         (void)djs;
 #endif
-        a = fma(Fa.pd[1][lane], shfl_up2(u4[1]), a);
-        a = fma(Fa.pd[2][lane], shfl_up(u4[1]), a);
-        a = fma(Fa.pd[3][lane], u4[1], a);
-        a = fma(Fa.pd[4][lane], shfl_dn(u4[1]), a);
-        a = fma(Fa.pd[5][lane], shfl_dn2(u4[1]), a);
-        a = fma(Fa.pd[6][lane], shfl_up2(u4[2]), a);
-        a = fma(Fa.pd[7][lane], shfl_up(u4[2]), a);
-        a = fma(Fa.pd[8][lane], u4[2], a);
-        a = fma(Fa.pd[9][lane], shfl_dn(u4[2]), a);
-        a = fma(Fa.wT[0][lane], shfl_dn2(u4[2]), a);
+        a = fma(FA_PD(1), shfl_up2(u4[1]), a);
+        a = fma(FA_PD(2), shfl_up(u4[1]), a);
+        a = fma(FA_PD(3), u4[1], a);
+        a = fma(FA_PD(4), shfl_dn(u4[1]), a);
+        a = fma(FA_PD(5), shfl_dn2(u4[1]), a);
+        a = fma(FA_PD(6), shfl_up2(u4[2]), a);
+        a = fma(FA_PD(7), shfl_up(u4[2]), a);
+        a = fma(FA_PD(8), u4[2], a);
+        a = fma(FA_PD(9), shfl_dn(u4[2]), a);
+        a = fma(FA_WT(0), shfl_dn2(u4[2]), a);
         g += warp_sum(a);
     }
     return g;
@@ -1731,14 +1745,14 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             pd[i] = ro.elec ? 1.0 / (J.kap * laws::EL[i] - cj) : 0.0;
-            Fa.pd[i][lane] = pd[i];
+            FA_PD(i) = pd[i];
         }
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             double w = 0.0;
 #pragma unroll
             for (int c = 0; c < NR; c++) w = fma(laws::EVI[i][c], J.csT[c], w);
-            Fa.wT[i][lane] = w;
+            FA_WT(i) = w;
             beta = fma(laws::EV[NR - 1][i] * pd[i], PLB_EVIB(i), beta);
             tau = fma(laws::EV[NR - 1][i] * pd[i], w, tau);
         }
@@ -2013,12 +2027,12 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
     Fa.gT[lane] = cj * ctrl.gTn; Fa.gX[lane] = cj * ctrl.gTx;
     if (mode == 2) {
         // d(control row)/d(algebraic unknowns) = sum_x gTn[x] * (T row of node x); the collector rows only see I
-        Fa.pd[0][lane] = ctrl.gTn * J.T_j;
+        FA_PD(0) = ctrl.gTn * J.T_j;
 #pragma unroll
-        for (int k = 0; k < 5; k++) Fa.pd[1 + k][lane] = ctrl.gTn * J.T_pe[k];
+        for (int k = 0; k < 5; k++) FA_PD(1 + k) = ctrl.gTn * J.T_pe[k];
 #pragma unroll
-        for (int k = 0; k < 4; k++) Fa.pd[6 + k][lane] = ctrl.gTn * J.T_ps[k];
-        Fa.wT[0][lane] = ctrl.gTn * J.T_ps[4];
+        for (int k = 0; k < 4; k++) FA_PD(6 + k) = ctrl.gTn * J.T_ps[k];
+        FA_WT(0) = ctrl.gTn * J.T_ps[4];
 #if PLB_SEI
         Fa.pdjs[lane] = ctrl.gTn * J.T_js;
 #endif
@@ -2054,7 +2068,7 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
 #pragma unroll
             for (int c = 0; c < NR; c++) w = fma(laws::EVI[i][c], g.cs[c], w);
             w0[i] = ro.elec ? w : 0.0;
-            s9 = fma(laws::EV[NR - 1][i] * Fa.pd[i][lane], w0[i], s9);
+            s9 = fma(laws::EV[NR - 1][i] * FA_PD(i), w0[i], s9);
         }
 #pragma unroll
         for (int i = 0; i < NR; i++) g.cs[i] = w0[i];
@@ -2126,7 +2140,7 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
         const double bj = Fa.csj[lane] * dj;
 #pragma unroll
         for (int i = 0; i < NR; i++)
-            v[i] = Fa.pd[i][lane] * (g.cs[i] - PLB_EVIB(i) * bj - Fa.wT[i][lane] * u4[3]);
+            v[i] = FA_PD(i) * (g.cs[i] - PLB_EVIB(i) * bj - FA_WT(i) * u4[3]);
 #pragma unroll
         for (int r = 0; r < NR; r++) {
             double acc = 0.0;

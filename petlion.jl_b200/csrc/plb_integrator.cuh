@@ -42,9 +42,9 @@ struct IdaCoef {
 //  iso 369 k -> 432 k sims/s at the same eight systems per SM; measured per family, profiles/ab_r3_blocks_global_geometry.txt)
 #ifndef PLB_NGLOBAL
 #if PLB_WIDE
-#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 0 : 2) : (PLB_SEI ? 0 : 1))
+#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 0 : 1) : (PLB_SEI ? 0 : 1))
 #else
-#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 2 : 1) : 0)
+#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 1 : 2) : 0)
 #endif
 #endif
 constexpr int NGLOBAL = PLB_NGLOBAL;
