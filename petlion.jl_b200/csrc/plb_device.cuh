@@ -1020,7 +1020,19 @@ __device__ __forceinline__ void inv3x3(const double* a, double* o) {
 #ifndef PLB_BLOCKS_GLOBAL
 #define PLB_BLOCKS_GLOBAL 1
 #endif
-constexpr int FA_GLOBAL = PLB_BLOCKS_GLOBAL ? 27 * LW : 0;      // doubles per system slot of the global workspace
+// aging = :SEI: the 3x3 local inverse Mi and the six couplings cpl of the (j, j_s, film) elimination live there as well (15 doubles
+// per lane, read once at the head of a solve): the room for a fourth system per SM on the two-warp grid (cfg5)
+#ifndef PLB_SEI_LOCAL_GLOBAL
+#define PLB_SEI_LOCAL_GLOBAL (PLB_SEI && PLB_WIDE && PLB_BLOCKS_GLOBAL)     // (32-node SEI: seven systems fit either way; on chip: 368 k vs 362 k)
+#endif
+constexpr int FA_GLOBAL = PLB_BLOCKS_GLOBAL ? (27 + (PLB_SEI_LOCAL_GLOBAL ? 15 : 0)) * LW : 0;      // doubles per system slot of the global workspace
+#if PLB_SEI_LOCAL_GLOBAL
+#define FA_MI(k) Fa.blk[(27 + (k)) * LW + lane]
+#define FA_CPL(k) Fa.blk[(36 + (k)) * LW + lane]
+#else
+#define FA_MI(k) Fa.Mi[k][lane]
+#define FA_CPL(k) Fa.cpl[k][lane]
+#endif
 struct WarpFactor {
     double Sinv[NR * NR][2];   // [r*NR+c][electrode 0=p,1=n]
     double vb[NR][2];          // Sinv * b (b = surface-row j coupling)
@@ -1041,7 +1053,11 @@ struct WarpFactor {
     // aging = :SEI: j, j_s and film are eliminated together node-locally.  Mi = inverse of the 3x3 local
     // matrix (rows j, j_s, film), cpl = couplings of those rows to (c_e, Phi_e, Phi_s) and I:
     // j_ce, j_pe, j_ps, js_pe, js_ps, js_I ; sohc = d(rhs_SOH)/dj_s ; cjv = cj of this factorisation
+#if PLB_SEI_LOCAL_GLOBAL
+    double sohc[LW];
+#else
     double Mi[9][LW], cpl[6][LW], sohc[LW];
+#endif
     double cjv, pad2;
 #endif
     double schur_inv;          // 1/(g_I - g_ps0*z_ps[0] - g_psN*z_ps[N-1] - g_eta*(z_ps - z_pe)[first anode node])
@@ -1203,11 +1219,11 @@ __device__ __forceinline__ void warp_factor_impl(const ModelDesc& m, const LaneR
         M3[6] = 0.0; M3[7] = (sn && !alg_only) ? J.film_js : 0.0; M3[8] = (sn && !alg_only) ? -cj : 1.0;
         inv3x3(M3, Mi);
 #pragma unroll
-        for (int k = 0; k < 9; k++) Fa.Mi[k][lane] = Mi[k];
+        for (int k = 0; k < 9; k++) FA_MI(k) = Mi[k];
         const double c_jce = (ro.elec && !alg_only) ? J.j_ce : 0.0, c_jpe = ro.elec ? J.j_pe : 0.0, c_jps = ro.elec ? J.j_ps : 0.0;
         const double c_spe = sn ? J.js_pe : 0.0, c_sps = sn ? J.js_ps : 0.0, c_sI = sn ? J.js_I : 0.0;
-        Fa.cpl[0][lane] = c_jce; Fa.cpl[1][lane] = c_jpe; Fa.cpl[2][lane] = c_jps;
-        Fa.cpl[3][lane] = c_spe; Fa.cpl[4][lane] = c_sps; Fa.cpl[5][lane] = c_sI;
+        FA_CPL(0) = c_jce; FA_CPL(1) = c_jpe; FA_CPL(2) = c_jps;
+        FA_CPL(3) = c_spe; FA_CPL(4) = c_sps; FA_CPL(5) = c_sI;
         Fa.sohc[lane] = (sn && !alg_only) ? J.soh_js : 0.0;
         if (lane == 0) Fa.cjv = alg_only ? 0.0 : cj;
         // the other rows see dj + dj_s = m.(local right-hand side), m = (1,1,0) Mi
@@ -1416,9 +1432,11 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     }
 #if PLB_SEI
     const bool sn = ro.sec == 2;
-    double Mi[9];
+    double Mi[9], cplr[6];
 #pragma unroll
-    for (int k = 0; k < 9; k++) Mi[k] = Fa.Mi[k][lane];
+    for (int k = 0; k < 9; k++) Mi[k] = FA_MI(k);
+#pragma unroll
+    for (int k = 0; k < 6; k++) cplr[k] = FA_CPL(k);
     // local right-hand side of (j, j_s, film) after the particle elimination
     double v0 = ro.elec ? g.j - Fa.jcs[lane] * p0 : 0.0;
     double v1 = sn ? g.js : 0.0;
@@ -1468,8 +1486,8 @@ __device__ __forceinline__ double warp_solve_impl(const ModelDesc& m, const Lane
     }
     // back-substitute j (and j_s, film) and the particle
 #if PLB_SEI
-    v0 -= Fa.cpl[0][lane] * u3[0] + Fa.cpl[1][lane] * u3[1] + Fa.cpl[2][lane] * u3[2];
-    v1 -= Fa.cpl[3][lane] * u3[1] + Fa.cpl[4][lane] * u3[2] + Fa.cpl[5][lane] * dI;
+    v0 -= cplr[0] * u3[0] + cplr[1] * u3[1] + cplr[2] * u3[2];
+    v1 -= cplr[3] * u3[1] + cplr[4] * u3[2] + cplr[5] * dI;
     const double dj = ro.elec ? Mi[0] * v0 + Mi[1] * v1 + Mi[2] * v2 : 0.0;
     const double djs = sn ? Mi[3] * v0 + Mi[4] * v1 + Mi[5] * v2 : 0.0;
     const double dfilm = (sn && !alg_only) ? Mi[6] * v0 + Mi[7] * v1 + Mi[8] * v2 : 0.0;

@@ -42,7 +42,7 @@ struct IdaCoef {
 //  iso 369 k -> 432 k sims/s at the same eight systems per SM; measured per family, profiles/ab_r3_blocks_global_geometry.txt)
 #ifndef PLB_NGLOBAL
 #if PLB_WIDE
-#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 0 : 1) : (PLB_SEI ? 0 : 1))
+#define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 0 : 1) : 1)
 #else
 #define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 1 : 2) : 0)
 #endif

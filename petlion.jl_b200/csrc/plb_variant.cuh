@@ -692,7 +692,8 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 //  wide thermal 3 / 2 instead of 2 / 1)
 //  ... and the isothermal families theirs: SEI 7 systems per SM instead of 6, wide iso 4 instead of 3)
 //  (thermal, with pd / wT in the global workspace as well: 8 systems per SM, phi_4 / phi_5 in global memory: 175 k -> 205 k sims/s)
-#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 3 : 1) : (PLB_TH ? (PLB_SEI ? 5 : 8) : (PLB_SEI ? 7 : 8)))
+//  (wide SEI, with Mi / cpl of the node-local elimination in the global workspace as well: four groups of one CTA, phi_5 in global memory)
+#define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 4 : 1) : (PLB_TH ? (PLB_SEI ? 5 : 8) : (PLB_SEI ? 7 : 8)))
 #else   // N_r = 12 / 14 siblings: longer vectors and larger particle inverses per system
 #define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 4 : 7) : (PLB_SEI ? (PLB_NR == 12 ? 6 : 5) : (PLB_NR == 12 ? 7 : 6))))
 #endif
