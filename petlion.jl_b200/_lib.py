@@ -36,15 +36,18 @@ def _build_key(srcs, flags, nvcc):
     return h.hexdigest()
 
 
+# one translation unit per compiled model family (plb_variant_*.cu) + the host ABI
+UNITS = ("plb_kernels.cu", "plb_variant_iso.cu", "plb_variant_th.cu", "plb_variant_sei.cu",
+         "plb_variant_wide.cu", "plb_variant_wsei.cu", "plb_variant_wth.cu", "plb_variant_thsei.cu", "plb_variant_wthsei.cu", "plb_variant_isodc.cu", "plb_variant_widedc.cu", "plb_variant_isomhc.cu", "plb_variant_thmhc.cu", "plb_variant_seimhc.cu", "plb_variant_isolgm.cu", "plb_variant_thlgm.cu",
+         "plb_variant_iso_r12.cu", "plb_variant_th_r12.cu", "plb_variant_sei_r12.cu", "plb_variant_iso_r14.cu", "plb_variant_th_r14.cu", "plb_variant_sei_r14.cu",
+         "plb_variant_iso_sp.cu", "plb_variant_th_sp.cu", "plb_variant_sei_sp.cu",
+         "plb_variant_widemhc.cu", "plb_variant_wseimhc.cu", "plb_variant_wthmhc.cu", "plb_variant_thseimhc.cu", "plb_variant_wthseimhc.cu",
+         "plb_variant_widelgm.cu", "plb_variant_wthlgm.cu")
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (cross-compiles without a GPU)."""
-    units = ("plb_kernels.cu", "plb_variant_iso.cu", "plb_variant_th.cu", "plb_variant_sei.cu",
-             "plb_variant_wide.cu", "plb_variant_wsei.cu", "plb_variant_wth.cu", "plb_variant_thsei.cu", "plb_variant_wthsei.cu", "plb_variant_isodc.cu", "plb_variant_widedc.cu", "plb_variant_isomhc.cu", "plb_variant_thmhc.cu", "plb_variant_seimhc.cu", "plb_variant_isolgm.cu", "plb_variant_thlgm.cu",
-             "plb_variant_iso_r12.cu", "plb_variant_th_r12.cu", "plb_variant_sei_r12.cu", "plb_variant_iso_r14.cu", "plb_variant_th_r14.cu", "plb_variant_sei_r14.cu",
-             "plb_variant_iso_sp.cu", "plb_variant_th_sp.cu", "plb_variant_sei_sp.cu",
-             "plb_variant_widemhc.cu", "plb_variant_wseimhc.cu", "plb_variant_wthmhc.cu", "plb_variant_thseimhc.cu", "plb_variant_wthseimhc.cu",
-             "plb_variant_widelgm.cu", "plb_variant_wthlgm.cu")
-    srcs = [os.path.join(CSRC, f) for f in units + ("plb_common.cuh", "plb_variant.cuh", "plb_device.cuh",
+    srcs = [os.path.join(CSRC, f) for f in UNITS + ("plb_common.cuh", "plb_variant.cuh", "plb_device.cuh",
                                                     "plb_integrator.cuh", "plb_tick.cuh", "laws_generated.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "petlion_b200.h"))
     gen = os.path.join(CSRC, "laws_generated.cuh")
@@ -61,7 +64,7 @@ def build(force=False, verbose=False):
     # one translation unit per model family (isothermal / thermal) + the host ABI, compiled in parallel
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
     objs, procs = [], []
-    for u in units:
+    for u in UNITS:
         o = os.path.join(CSRC, u[:-3] + ".o")
         objs.append(o)
         procs.append(subprocess.Popen([nvcc] + flags + ["-c", "-o", o, os.path.join(CSRC, u)]))

@@ -244,3 +244,29 @@ def test_model_key_follows_the_reference_directory_hash():
     N2 = N.copy(); N2.a = 5
     assert model_key(_NS(cathode="LCO", numerics=nm, N=N2)) == k          # N_a only matters to thermal models
     assert model_key(_NS(cathode="NMC", numerics=nm, N=N)).startswith("NMC_LiC6_NMC/")
+
+
+def test_every_family_unit_is_compiled_and_declared():
+    """one translation unit per compiled family: the build list, the files in csrc/ and the variant declarations of the host
+    (PLB_DECLARE_VARIANT + the VTAB rows plb_create looks a model's family up in) must name the same families"""
+    import glob
+    import re
+    from petlion_b200 import _lib
+    csrc = os.path.join(ROOT, "petlion.jl_b200", "csrc")
+    files = {os.path.basename(f) for f in glob.glob(os.path.join(csrc, "plb_*.cu"))}
+    assert files == set(_lib.UNITS)
+    ns = set()
+    for f in files - {"plb_kernels.cu"}:
+        m = re.search(r"#define PLB_NS (\w+)", open(os.path.join(csrc, f)).read())
+        assert m, f
+        ns.add(m.group(1))
+    assert len(ns) == len(files) - 1                                   # no two units share a namespace
+    declared = set(re.findall(r"^PLB_DECLARE_VARIANT\((\w+)\)", open(os.path.join(csrc, "plb_common.cuh")).read(), re.M))
+    assert declared == ns
+    host = open(os.path.join(csrc, "plb_kernels.cu")).read()
+    tables = set(re.findall(r"static const Variant V_\w+ = (?:PLB_VARIANT_TABLE\((\w+)\)|\{(\w+)::info)", host))
+    assert {a or b for a, b in tables} == ns
+    vtab = host[host.index("static const VEntry VTAB[]"):host.index("static const Variant* find_variant")]
+    rows = re.findall(r"\{(\d), (\d), (\d), (\d), (\d), (\d+), (\d), &(V_\w+)\}", vtab)
+    assert len(rows) == len(set(r[:7] for r in rows)) == len(set(r[7] for r in rows)) == 29      # one family per option set
+    assert len(ns) == 29 + 2                                            # + the two concentration-rate-input siblings (isodc, widedc)
