@@ -71,3 +71,31 @@ def test_nmc_has_no_thermal_or_aging_parameters():
         petlion_b200.petlion("NMC", temperature=True)
     with pytest.raises(RuntimeError, match="LCO parameter set"):
         petlion_b200.petlion("NMC", aging="SEI")
+
+
+_G = dict(N_p=20, N_s=20, N_n=20)
+_MHC = dict(rxn_p="rxn_MHC", rxn_n="rxn_MHC")
+
+
+@pytest.mark.parametrize("cathode,kw", [
+    ("LCO", {}), ("LCO", dict(temperature=True)), ("LCO", dict(aging="SEI")), ("LCO", dict(temperature=True, aging="SEI")),
+    ("LCO", _G), ("LCO", dict(temperature=True, **_G)), ("LCO", dict(aging="SEI", **_G)), ("LCO", dict(temperature=True, aging="SEI", **_G)),
+    ("LCO", _MHC), ("LCO", dict(temperature=True, **_MHC)), ("LCO", dict(aging="SEI", **_MHC)), ("LCO", dict(temperature=True, aging="SEI", **_MHC)),
+    ("LCO", dict(**_G, **_MHC)), ("LCO", dict(temperature=True, **_G, **_MHC)), ("LCO", dict(aging="SEI", **_G, **_MHC)),
+    ("LCO", dict(temperature=True, aging="SEI", **_G, **_MHC)), ("LCO", dict(rxn_n="rxn_MHC", N_p=20, N_s=10, N_n=20)),
+    ("NMC", {}), ("NMC", _G), ("NMC", dict(N_r_p=14, N_r_n=14)), ("NMC", dict(Fickian_method="spectral")),
+    ("NMC_LGM50", {}), ("NMC_LGM50", dict(temperature=False)), ("NMC_LGM50", _G), ("NMC_LGM50", dict(temperature=False, **_G)),
+    ("LCO", dict(N_r_p=12, N_r_n=12)), ("LCO", dict(N_r_p=12, N_r_n=12, temperature=True)), ("LCO", dict(N_r_p=12, N_r_n=12, aging="SEI")),
+    ("LCO", dict(N_r_p=14, N_r_n=14)), ("LCO", dict(N_r_p=14, N_r_n=14, temperature=True)), ("LCO", dict(N_r_p=14, N_r_n=14, aging="SEI")),
+    ("LCO", dict(Fickian_method="spectral")), ("LCO", dict(Fickian_method="spectral", temperature=True)),
+    ("LCO", dict(Fickian_method="spectral", aging="SEI")),
+    ("LCO", dict(N_p=7, N_s=5, N_n=9)), ("LCO", dict(N_p=20, N_s=24, N_n=20)), ("LCO", dict(N_p=15, N_s=2, N_n=15)),
+])
+def test_every_built_option_set_finds_its_family(cathode, kw):
+    """plb_create validates the options and looks the compiled family up BEFORE it touches a device: on a machine without a GPU
+    every built option set gets as far as "no CUDA device available" (and with one it simply succeeds)"""
+    import petlion_b200
+    try:
+        petlion_b200.petlion(cathode, **kw)
+    except RuntimeError as e:
+        assert "no CUDA device available" in str(e), str(e)
