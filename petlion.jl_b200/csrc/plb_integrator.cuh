@@ -22,9 +22,8 @@ namespace PLB_NS {
 // (N_r = 12 / 14 sibling builds: (N_r - 10) more doubles per electrode node -- 20 / 40 nodes of the standard grids; 8-aligned)
 constexpr int VS = (WIDE ? (TH ? (SEI ? 784 : 736) : 656) : (TH ? (SEI ? 384 : 352) : (SEI ? 336 : 304))) + (NR - 10) * (WIDE ? 40 : 20);
 // (Round 2: no predictor vectors.  y_pred = sum_j phi_j and y'_pred = sum_j gamma_j phi_j are re-formed from the
-// history where an evaluation needs them -- kk+1 shared-memory reads per component instead of two -- and phi_4, phi_5
-// live in global memory (PLB_NGLOBAL): six vectors per system in shared memory instead of ten, eight systems per SM
-// instead of six.  Measured marginal gain per additional warp: +39 k sims/s (4, 5, 6 warps: 238, 278, 317 k).)
+// history where an evaluation needs them -- kk+1 shared-memory reads per component instead of two: eight vectors per system
+// instead of ten, of which the last PLB_NGLOBAL history vectors may live in global memory, below.)
 enum VecId { V_PHI0 = 0, V_PHI1, V_PHI2, V_PHI3, V_PHI4, V_PHI5, V_EWT, V_EE, V_COUNT };
 
 struct IdaCoef {
@@ -36,10 +35,11 @@ struct IdaCoef {
 // Number of BDF history vectors kept in global memory (L2-resident) instead of shared memory: the
 // LAST PLB_NGLOBAL of phi_0..phi_5.  Measured order histogram of the 1C discharge batch: order 1: 6 %,
 // 2: 47 %, 3: 41 %, 4: 5 %, 5: 0.1 % -- phi_5 is hardly ever touched, phi_4 is written once per step at order 3
-// (a fire-and-forget store) and read when an order raise is considered.
-// (second sitting: with the factored blocks of the linear solve in the global workspace -- plb_device.cuh -- the isothermal, SEI,
-//  wide SEI and wide thermal+SEI families keep ALL history vectors in shared memory again, thermal and wide iso all but phi_5:
-//  iso 369 k -> 432 k sims/s at the same eight systems per SM; measured per family, profiles/ab_r3_blocks_global_geometry.txt)
+// (a fire-and-forget store) and read when an order raise is considered.  Parking phi_4 and phi_5 there costs 10 % at equal
+// occupancy (first sitting of round 2: it bought 8 instead of 6 systems per SM).  Second sitting: the factored blocks of the
+// linear solve are what belongs in the global workspace (plb_device.cuh: touched once per solve, not once per vector pass); with
+// them gone the isothermal families keep ALL history vectors on chip again (iso 369 k -> 432 k sims/s at the same eight systems
+// per SM), the others park what buys them one more system per SM -- the table in plb_variant.cuh (PLB_SIM_WARPS).
 #ifndef PLB_NGLOBAL
 #if PLB_WIDE
 #define PLB_NGLOBAL (PLB_TH ? (PLB_SEI ? 0 : 1) : 1)

@@ -680,19 +680,22 @@ int slot_recipe(const ModelDesc& m, int slot, int lane) {
 // =================================================================================================
 // initial_guess!, newtons_method!, linear solve, simulate
 // =================================================================================================
+// Systems (lane groups) in flight per CTA, and CTAs per SM.  One barrier per tick (plb_tick.cuh) keeps the systems of a CTA on
+// one instruction stream; with only that barrier left, one large CTA per SM is best for the 32-lane families (measured, iso,
+// round 1: 6x1 229 k sims/s, 3x2 213 k, 2x3 200 k).  How many systems fit is a matter of what lives in shared memory
+// (plb_integrator.cuh: PLB_NGLOBAL; plb_device.cuh: the factored blocks in the global workspace).
+// Final geometry, each entry measured against its neighbours (profiles/ab_r3_*geometry*.txt):
+//   family   groups x CTAs   history vectors in global memory      sims/s per segment, start of the sitting -> final
+//   iso          8 x 1       none                                   331 k -> 426 k   (register-bound at 8: 230 x 256 threads)
+//   sei          7 x 1       none                                   258 k -> 368 k   (6 systems before)
+//   th           8 x 1       phi_4, phi_5                           136 k -> 206 k   (5 before)
+//   thsei        5 x 1       phi_5                                   92 k -> 145 k   (3 before)
+//   wide         1 x 4       phi_5                                  137 k -> 158 k   (3 CTAs before)
+//   wsei         4 x 1       phi_5   (one tick barrier for all)     115 k -> 164 k   (1 x 3 before)
+//   wth          1 x 3       phi_5                                   52 k -> 65.8 k  (2 CTAs before)
+//   wthsei       1 x 2       none                                  28.7 k -> 53.7 k  (1 before)
 #ifndef PLB_SIM_WARPS
-// systems (lane groups) in flight per CTA, and CTAs per SM.  One barrier per tick (plb_tick.cuh) keeps the
-// systems of a CTA on one instruction stream; with only that barrier left, one large CTA per SM is best for the
-// 32-lane families (measured, iso, sims/s on one B200: 6x1 229 k, 3x2 213 k, 2x3 200 k).
-// (round 2: six vectors per system in shared memory instead of ten: 8 / 6 / 5 systems per SM instead of 6 / 5 / 4)
 #if PLB_NR == 10
-// (wide SEI: its three systems per SM as three groups of ONE CTA, one tick barrier for all of them: 125.8 k -> 134.3 k sims/s;
-//  wide iso keeps three CTAs of one group: 138.6 k vs 137.1 k)
-// (second sitting: the thermal families keep their factored blocks in the global workspace: 6 / 5 systems per SM instead of 5 / 3,
-//  wide thermal 3 / 2 instead of 2 / 1)
-//  ... and the isothermal families theirs: SEI 7 systems per SM instead of 6, wide iso 4 instead of 3)
-//  (thermal, with pd / wT in the global workspace as well: 8 systems per SM, phi_4 / phi_5 in global memory: 175 k -> 205 k sims/s)
-//  (wide SEI, with Mi / cpl of the node-local elimination in the global workspace as well: four groups of one CTA, phi_5 in global memory)
 #define PLB_SIM_WARPS (PLB_WIDE ? ((PLB_SEI && !PLB_TH) ? 4 : 1) : (PLB_TH ? (PLB_SEI ? 5 : 8) : (PLB_SEI ? 7 : 8)))
 #else   // N_r = 12 / 14 siblings: longer vectors and larger particle inverses per system
 #define PLB_SIM_WARPS (PLB_WIDE ? 1 : (PLB_TH ? (PLB_SEI ? 4 : 7) : (PLB_SEI ? (PLB_NR == 12 ? 6 : 5) : (PLB_NR == 12 ? 7 : 6))))
