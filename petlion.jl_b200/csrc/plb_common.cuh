@@ -135,7 +135,7 @@ struct SimArgs {
     double* tr_Y;             // optional: every saved row's full state [B][n_save_max][N] (outputs = :all, save_outputs.jl:11-40)
     int* tr_n;
     int* counter;
-    double* gws;              // global workspace: [grid * warps_per_cta][NGLOBAL][VS]
+    double* gws;              // global workspace: [grid * systems per CTA][gws_per_slot]: the parked history vectors, then the factored blocks
     // run_function restricted to a piecewise-linear table of the run's local time (structures.jl:55,
     // scalar_residual.jl:169-170): value(t) = scale[sys] * table(t); `values` then holds the scales.
     // tab_n == 0: run_constant.  tstops: the merged, sorted stop list of postfix_integrator!

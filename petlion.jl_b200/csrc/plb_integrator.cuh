@@ -59,7 +59,7 @@ struct alignas(16) WarpSmem {
 };
 
 struct WarpWS {
-    double* gbase;     // this warp's slice of the global workspace: NGLOBAL vectors of VS doubles
+    double* gbase;     // this system's slot of the global workspace: NGLOBAL vectors of VS doubles (then the factored blocks, Fa.blk)
     double* sbase;     // shared-memory vectors
     WarpConst& C;
     WarpFactor& Fa;

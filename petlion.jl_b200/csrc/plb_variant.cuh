@@ -713,7 +713,7 @@ constexpr int SIM_CTAS = PLB_SIM_CTAS;
 constexpr size_t STATE_BYTES = PLB_STATE_SMEM ? 480 : 0;           // per physical warp
 constexpr size_t STATE_OFFSET = XCH_BYTES_PER_GROUP * SIM_WARPS + sizeof(WarpSmem) * SIM_WARPS;
 constexpr size_t SIM_SMEM = STATE_OFFSET + STATE_BYTES * SIM_WARPS * (LW / 32);
-// doubles per system slot of the global workspace: the history vectors parked there + (thermal) the factored blocks
+// doubles per system slot of the global workspace: the history vectors parked there + the factored blocks of the linear solve
 constexpr int GWS_PER_SLOT = (NGLOBAL > 0 ? NGLOBAL : 1) * VS + FA_GLOBAL;
 static_assert(SIM_SMEM <= 227 * 1024, "the integrator's shared memory exceeds one SM: lower PLB_SIM_WARPS for this family");
 
